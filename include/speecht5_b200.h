@@ -1,0 +1,158 @@
+/*
+ * speecht5_b200 -- C ABI of the B200 (sm_100a) kernel library for the SpeechT5 forward/backward hot path.
+ *
+ * The reference (microsoft/SpeechT5, SpeechT5/speecht5/models/modules/*.py) has no FFI of its own: every device op is
+ * a PyTorch library call made from the nn.Module forward()s. This header is the boundary a maintainer binds instead
+ * (ctypes stub shown in INTEGRATION.md); each entry point names the reference code it replaces (file:line under
+ * /root/reference/SpeechT5/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *   - return value 0 = ok, >0 = cudaError_t, <0 = library argument error; st5_last_error() gives the text
+ *     (allocation failures contain the literal "out of memory", which fairseq/trainer.py:725 greps for);
+ *   - `dtype`: ST5_F32 = 0, ST5_BF16 = 1 is the activation storage type; statistics, biases, LayerNorm/BatchNorm
+ *     parameters, probabilities returned to the caller and all gradients of parameters are fp32;
+ *   - dropout is counter based: keep(i) = philox4x32-10(seed, offset, i/4)[i%4] >= p*2^32 for the element with
+ *     linear index i of the logical tensor, so forward and backward regenerate identical masks without storing them.
+ */
+#ifndef SPEECHT5_B200_H
+#define SPEECHT5_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST5_F32 0
+#define ST5_BF16 1
+#define ST5_ACT_NONE 0
+#define ST5_ACT_RELU 1
+#define ST5_ACT_GELU 2
+#define ST5_ACT_TANH 3
+
+int st5_version(void);
+const char* st5_last_error(void);
+/* sm_100a only: returns 0 when the current device can run the library, else a negative code. */
+int st5_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------- GEMM
+ * D[z][m][n] = epi( alpha * sum_k A[z][m][k] * B[z][n][k] ), bf16 operands, fp32 accumulation in TMEM
+ * (TMA + tcgen05.mma). Replaces every nn.Linear / torch.bmm / F.conv1d on the path:
+ *   models/modules/multihead_attention.py:213-231 (q/k/v), :340 (QK^T), :389 (PV), :397 (out_proj);
+ *   models/modules/transformer_layer.py:127-132, 385-391 (fc1/fc2);
+ *   models/modules/speech_decoder_prenet.py:41-47,69-72; speech_decoder_postnet.py:31-32,39-51 (Conv1d as an
+ *   overlapping-window GEMM over a zero-padded channels-last buffer); and their backward contractions.
+ * Operand storage: *_mn = 0 -> row-major [rows][ld] with k contiguous; *_mn = 1 -> [K][ld] with the row index
+ * contiguous (the operand is used transposed without a copy). ld / batch strides are in elements and must be
+ * multiples of 8 (16 bytes); base pointers 16-byte aligned. Batch index z = b2 * nb1 + b1.
+ * epi(v) = dropout(act(v + c_old*accumulate + bias[n] + bias2[m / bias2_rows][n])) + residual[m][n]; the value before
+ * act() is also stored to c_pre when non-null. */
+typedef struct st5_gemm_args {
+  int32_t M, N, K, nb1, nb2;
+  int32_t a_mn, b_mn, c_fp32, act, accumulate, bias2_rows;
+  const void* a; int64_t a_ld, a_bs1, a_bs2;
+  const void* b; int64_t b_ld, b_bs1, b_bs2;
+  void* c; int64_t c_ld, c_bs1, c_bs2;
+  void* c_pre;
+  const float* bias;
+  const float* bias2;
+  const void* residual;
+  float alpha;
+  float drop_p;
+  uint64_t drop_seed, drop_offset;
+} st5_gemm_args;
+int st5_gemm_bf16(const st5_gemm_args* args, void* stream);
+
+/* fp32 -> bf16 cast of a strided 2-D view. lo != NULL additionally writes the bf16 residual x - float(hi(x)), which
+ * lets callers form hi*hi + hi*lo + lo*hi with three accumulate passes of st5_gemm_bf16 (fp32-grade "parity mode"). */
+int st5_cast_bf16(const float* src, int64_t src_ld, void* hi, void* lo, int64_t dst_ld, int64_t rows, int64_t cols,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------- pre-nets
+ * y[b,t,:] = dropout( (tokens ? E[tokens[b,t]] : x[b,t,:]) + alpha * pe[t,:] ).
+ * text_encoder_prenet.py:36-45 (Embedding -> espnet ScaledPositionalEncoding), speech_decoder_prenet.py:52-67. */
+int st5_posenc_fwd(const int64_t* tokens, const float* emb, const void* x, const float* pe, const float* alpha,
+                   void* y, int dtype, int64_t B, int64_t T, int64_t C, float drop_p, uint64_t seed, uint64_t offset,
+                   void* stream);
+/* Backward: dx (same dtype, may be NULL), demb += (fp32 scatter-add, skipping padding_idx), dalpha += sum(dy*pe). */
+int st5_posenc_bwd(const void* dy, const int64_t* tokens, int64_t padding_idx, const float* pe, void* dx, float* demb,
+                   float* dalpha, int dtype, int64_t B, int64_t T, int64_t C, float drop_p, uint64_t seed,
+                   uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- LayerNorm
+ * s = residual + dropout(x); y = LN(s) * gamma + beta. Saves s (for backward), mean and rstd.
+ * transformer_layer.py:112-132 (post-LN encoder layer), :343-391 (decoder layer), encoder.py:226-227. */
+int st5_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
+               float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
+               uint64_t offset, void* stream);
+/* ds = LN backward wrt s; dx = dropout-backward(ds) (may alias / be NULL when drop_p == 0 and caller reuses ds);
+ * dgamma/dbeta are accumulated (+=) in fp32. `partials` is a caller scratch of 2 * nblk * C floats where
+ * nblk = st5_ln_bwd_blocks(rows). */
+int64_t st5_ln_bwd_blocks(int64_t rows);
+int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* ds,
+               void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C, float drop_p,
+               uint64_t seed, uint64_t offset, void* stream);
+
+/* y = dropout(x) (also its own backward when applied to the gradient). */
+int st5_dropout(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
+                void* stream);
+/* dpre = dropout-backward(dy) * act'(pre). */
+int st5_act_bwd(const void* dy, const void* pre, void* dpre, int dtype, int act, int64_t n, float drop_p, uint64_t seed,
+                uint64_t offset, void* stream);
+/* out[g][n] (+)= sum_{m in group g} x[m][n], groups of `group_rows` consecutive rows (bias gradients). */
+int st5_colsum(const void* x, int64_t ld, float* out, int dtype, int64_t rows, int64_t cols, int64_t group_rows,
+               int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- attention
+ * multihead_attention.py:232-405. q/k/v are read in place from the fused projection outputs:
+ *   element (b, t, h, c) of q lives at q[b * q_bs + t * q_ld + h * 64 + c] (same for k, v with their strides).
+ * scores = scale * q.(k + pe_k[clamp(i-j,-maxpos,maxpos-1)+maxpos]) (RPE, encoder.py:40-59,239-246) ;
+ * causal => j <= i; key_pad[b][j] != 0 => -inf; P = softmax_fp32; out = dropout(P) v.
+ * probs (optional) receives P: [B,H,Tq,p_ld] in `probs_dtype` (fp32 when returned to the user: need_head_weights).
+ * Head dim is fixed at 64 (Base and Large). */
+typedef struct st5_attn_args {
+  int32_t B, H, Tq, Tk, dtype, causal, maxpos, probs_dtype;
+  const void* q; int64_t q_ld, q_bs;
+  const void* k; int64_t k_ld, k_bs;
+  const void* v; int64_t v_ld, v_bs;
+  const uint8_t* key_pad;      /* [B][Tk] or NULL */
+  const float* pe_k;           /* [2*maxpos][64] fp32 or NULL */
+  void* out; int64_t o_ld, o_bs;
+  void* probs; int64_t p_ld;   /* may be NULL in forward only */
+  float scale, drop_p;
+  uint64_t seed, offset;
+  /* backward only */
+  const void* dout;            /* same layout as out */
+  const float* dprobs_ext;     /* optional external gradient wrt P, [B,H,Tq,p_ld] fp32 */
+  float* ds;                   /* scratch [B,H,Tq,p_ld] fp32 */
+  void* dq; void* dk; void* dv;/* same layouts as q, k, v */
+  float* dpe_k;                /* [2*maxpos][64] fp32, accumulated (+=) */
+} st5_attn_args;
+int st5_attn_fwd(const st5_attn_args* args, void* stream);
+int st5_attn_bwd(const st5_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- BatchNorm1d
+ * espnet Tacotron2 Postnet block (speech_decoder_postnet.py:39-51): y = dropout(tanh?(BN(x))) on channels-last
+ * rows [rows][C]; training statistics over all rows (padded frames included, as in the reference). */
+int st5_bn_fwd(const void* x, int64_t x_ld, const float* gamma, const float* beta, float* running_mean,
+               float* running_var, float* save_mean, float* save_rstd, void* y, int64_t y_ld, void* y_pre, int dtype,
+               int64_t rows, int64_t C, int training, float momentum, float eps, int act, float drop_p, uint64_t seed,
+               uint64_t offset, float* scratch, void* stream);
+int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const void* y_pre, const float* gamma,
+               const float* save_mean, const float* save_rstd, void* dx, int64_t dx_ld, float* dgamma, float* dbeta,
+               int dtype, int64_t rows, int64_t C, int act, float drop_p, uint64_t seed, uint64_t offset,
+               float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- optimizer
+ * Replaces fairseq/optim/adam.py + fp16_optimizer.py:106-218 on a flat fp32 parameter buffer: one pass applies the
+ * gradient scale (clip coefficient x 1/loss-scale), Adam(beta1, beta2, eps, weight decay as in torch.optim.Adam /
+ * fairseq Adam: decoupled=0 adds wd*p to the gradient) and refreshes the bf16 shadow copy used by the GEMMs. */
+int st5_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */, void* stream);
+int st5_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
+                  float grad_mul, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

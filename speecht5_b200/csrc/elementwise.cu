@@ -1,0 +1,217 @@
+// Memory-bound helpers around the GEMMs: casts, (embedding +) scaled positional encoding, dropout, activation
+// backward, column sums (bias gradients). All are HBM-bound streaming kernels: one pass, coalesced, fp32 math.
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "gemm.cuh"
+
+namespace st5 {
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g));
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 (hi [, lo])
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t src_ld, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int64_t dst_ld, int64_t rows, int64_t cols) {
+  const int64_t n = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float v = src[r * src_ld + c];
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    hi[r * dst_ld + c] = h;
+    if (lo != nullptr) lo[r * dst_ld + c] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+int cast_bf16_launch(const float* src, int64_t src_ld, void* hi, void* lo, int64_t dst_ld, int64_t rows, int64_t cols,
+                     cudaStream_t s) {
+  if (rows * cols == 0) return 0;
+  cast_bf16_kernel<<<grid_for(rows * cols, 256), 256, 0, s>>>(src, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                              dst_ld, rows, cols);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ (embedding +) alpha * PE, dropout
+template <typename T>
+__global__ void posenc_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb,
+                                  const T* __restrict__ x, const float* __restrict__ pe,
+                                  const float* __restrict__ alpha, T* __restrict__ y, int64_t B, int64_t T_, int64_t C,
+                                  uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  const int64_t n = B * T_ * C;
+  const float a = *alpha;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / C, c = i - bt * C;
+    const int64_t t = bt % T_;
+    float v = tokens != nullptr ? emb[tokens[bt] * C + c] : ldf(x + i);
+    v += a * pe[t * C + c];
+    if (thr != 0) v = dropout_keep(seed, offset, (uint64_t)i, thr) ? v * dscale : 0.f;
+    stf(y + i, v);
+  }
+}
+int posenc_fwd_launch(const int64_t* tokens, const float* emb, const void* x, const float* pe, const float* alpha,
+                      void* y, int dtype, int64_t B, int64_t T, int64_t C, float drop_p, uint64_t seed, uint64_t offset,
+                      cudaStream_t s) {
+  const int64_t n = B * T * C;
+  if (n == 0) return 0;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (dtype == ST5_F32)
+    posenc_fwd_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(tokens, emb, (const float*)x, pe, alpha, (float*)y, B, T,
+                                                              C, thr, ds, seed, offset);
+  else
+    posenc_fwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(
+        tokens, emb, (const __nv_bfloat16*)x, pe, alpha, (__nv_bfloat16*)y, B, T, C, thr, ds, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+__global__ void posenc_bwd_kernel(const T* __restrict__ dy, const int64_t* __restrict__ tokens, int64_t padding_idx,
+                                  const float* __restrict__ pe, T* __restrict__ dx, float* __restrict__ demb,
+                                  float* __restrict__ dalpha, int64_t B, int64_t T_, int64_t C, uint32_t thr,
+                                  float dscale, uint64_t seed, uint64_t offset) {
+  const int64_t n = B * T_ * C;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / C, c = i - bt * C;
+    const int64_t t = bt % T_;
+    float g = ldf(dy + i);
+    if (thr != 0) g = dropout_keep(seed, offset, (uint64_t)i, thr) ? g * dscale : 0.f;
+    acc += g * pe[t * C + c];
+    if (dx != nullptr) stf(dx + i, g);
+    if (tokens != nullptr) {
+      const int64_t tok = tokens[bt];
+      if (tok != padding_idx) atomicAdd(demb + tok * C + c, g);
+    }
+  }
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dalpha, v);
+  }
+}
+int posenc_bwd_launch(const void* dy, const int64_t* tokens, int64_t padding_idx, const float* pe, void* dx,
+                      float* demb, float* dalpha, int dtype, int64_t B, int64_t T, int64_t C, float drop_p,
+                      uint64_t seed, uint64_t offset, cudaStream_t s) {
+  const int64_t n = B * T * C;
+  if (n == 0) return 0;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (dtype == ST5_F32)
+    posenc_bwd_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)dy, tokens, padding_idx, pe, (float*)dx,
+                                                              demb, dalpha, B, T, C, thr, ds, seed, offset);
+  else
+    posenc_bwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>((const __nv_bfloat16*)dy, tokens, padding_idx, pe,
+                                                                      (__nv_bfloat16*)dx, demb, dalpha, B, T, C, thr,
+                                                                      ds, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ dropout
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, uint32_t thr, float dscale,
+                               uint64_t seed, uint64_t offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ldf(x + i);
+    if (thr != 0) v = dropout_keep(seed, offset, (uint64_t)i, thr) ? v * dscale : 0.f;
+    stf(y + i, v);
+  }
+}
+int dropout_launch(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
+                   cudaStream_t s) {
+  if (n == 0) return 0;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (dtype == ST5_F32)
+    dropout_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)x, (float*)y, n, thr, ds, seed, offset);
+  else
+    dropout_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, thr,
+                                                                   ds, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ activation backward (with dropout backward)
+__device__ __forceinline__ float act_grad(float x, int act) {
+  if (act == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  if (act == ACT_GELU) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  }
+  if (act == ACT_TANH) {
+    const float t = tanhf(x);
+    return 1.f - t * t;
+  }
+  return 1.f;
+}
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dpre, int act,
+                               int64_t n, uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = ldf(dy + i);
+    if (thr != 0) g = dropout_keep(seed, offset, (uint64_t)i, thr) ? g * dscale : 0.f;
+    stf(dpre + i, g * act_grad(ldf(pre + i), act));
+  }
+}
+int act_bwd_launch(const void* dy, const void* pre, void* dpre, int dtype, int act, int64_t n, float drop_p,
+                   uint64_t seed, uint64_t offset, cudaStream_t s) {
+  if (n == 0) return 0;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (dtype == ST5_F32)
+    act_bwd_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)dy, (const float*)pre, (float*)dpre, act, n,
+                                                           thr, ds, seed, offset);
+  else
+    act_bwd_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, s>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, act, n, thr, ds, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ grouped column sums (bias gradients)
+// grid: (col tiles of 32, groups, row splits). block (32, 8). Partial sums are combined with fp32 atomics.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows, int64_t cols,
+                              int64_t group_rows, int64_t rows_per_split) {
+  const int64_t col = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int64_t g = blockIdx.y;
+  const int64_t r0 = g * group_rows + (int64_t)blockIdx.z * rows_per_split;
+  int64_t r1 = r0 + rows_per_split;
+  const int64_t gend = (g + 1) * group_rows < rows ? (g + 1) * group_rows : rows;
+  if (r1 > gend) r1 = gend;
+  float acc = 0.f;
+  if (col < cols)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += ldf(x + r * ld + col);
+  __shared__ float red[8][33];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    atomicAdd(out + g * cols + col, v);
+  }
+}
+int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows, int64_t cols, int64_t group_rows,
+                  int accumulate, cudaStream_t s) {
+  if (rows == 0 || cols == 0) return 0;
+  if (group_rows <= 0) group_rows = rows;
+  const int64_t groups = (rows + group_rows - 1) / group_rows;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * groups * cols, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int64_t splits = (group_rows + 255) / 256;
+  if (splits > 64) splits = 64;
+  const int64_t rps = (group_rows + splits - 1) / splits;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)groups, (unsigned)splits), block(32, 8);
+  if (dtype == ST5_F32)
+    colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols, group_rows, rps);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace st5

@@ -1,0 +1,386 @@
+// Batched bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by
+// TMA into 128B-swizzled shared memory through an mbarrier ring. One CTA computes a 128 x BN output tile.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 =
+// epilogue (TMEM -> registers -> fused bias / activation / dropout / residual -> global).
+//
+// This one kernel is the contraction engine for every dense op on the SpeechT5 path: the q/k/v/out projections
+// (reference: speecht5/models/modules/multihead_attention.py:213-231,397), the FFN (transformer_layer.py:127-132,
+// 385-391), pre-/post-net Linear layers, the post-net Conv1d stack expressed as an overlapping-window GEMM, and all
+// of their backward contractions (MN-major operands avoid explicit transposes).
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace st5 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct EpiParams {
+  int M, N, nb1;
+  void* C; int c_fp32; long c_ld, c_bs1, c_bs2;
+  void* C_pre;
+  const float* bias;
+  const float* bias2; int bias2_rows;
+  const void* residual;
+  int act; float alpha; int accumulate;
+  uint32_t drop_thr; float drop_scale; uint64_t drop_seed, drop_offset;
+  int num_k_blocks;
+  int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast over that batch dim (stride 0), else 1
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const EpiParams p) {
+  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  constexpr uint32_t CHUNK_BYTES = 64 * BLOCK_K * 2;  // one 64(mn) x 64(k) MN-major box
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BN;
+  const int z = blockIdx.z;
+  const int b1 = z % p.nb1, b2 = z / p.nb1;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+        uint8_t* sa = smem_a + stage * A_BYTES;
+        uint8_t* sb = smem_b + stage * B_BYTES;
+        const int k0 = kb * BLOCK_K;
+        if (A_MN) {
+#pragma unroll
+          for (int c = 0; c < BLOCK_M / 64; ++c)
+            tma_load_4d(sa + c * CHUNK_BYTES, &map_a, &full_bar[stage], m0 + c * 64, k0, b1 * p.a_m1, b2 * p.a_m2);
+        } else {
+          tma_load_4d(sa, &map_a, &full_bar[stage], k0, m0, b1 * p.a_m1, b2 * p.a_m2);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_4d(sb + c * CHUNK_BYTES, &map_b, &full_bar[stage], n0 + c * 64, k0, b1 * p.b_m1, b2 * p.b_m2);
+        } else {
+          tma_load_4d(sb, &map_b, &full_bar[stage], k0, n0, b1 * p.b_m1, b2 * p.b_m2);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
+        const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major: advance 16 elements (32 B) along the swizzled row. MN-major: advance 16 k-rows (2 KB).
+          const uint64_t da = A_MN ? umma_smem_desc(sa + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
+                                   : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+          const uint64_t db = B_MN ? umma_smem_desc(sb + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
+                                   : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
+        if (kb == nkb - 1) umma_commit(accum_bar);   // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + (int)lane_id();
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    const long zoff = (long)b1 * p.c_bs1 + (long)b2 * p.c_bs2;
+    const long roff = zoff + (long)row * p.c_ld;
+    const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
+    const uint64_t drop_row = ((uint64_t)z * (uint64_t)p.M + (uint64_t)row) * (uint64_t)p.N;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      const bool full = (nb + 32 <= p.N);
+      if (p.accumulate) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
+        const float* src = reinterpret_cast<const float*>(p.C) + roff + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < p.N) v[j] += src[j];
+      }
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+      }
+      if (bias2_row != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < p.N) v[j] += __ldg(bias2_row + nb + j);
+      }
+      const bool vec_ok = full && ((p.c_ld & 7) == 0) && ((zoff & 7) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.C_pre) & 15) == 0);
+      if (p.C_pre != nullptr) {
+        if (p.c_fp32) {
+          float* dst = reinterpret_cast<float*>(p.C_pre) + roff + nb;
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) dst[j] = v[j];
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C_pre) + roff + nb;
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) dst[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      }
+      if (p.drop_thr != 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          // element index (drop_row + nb + j) is a multiple of 4 only when N is; use the generic per-element form
+          // unless aligned.
+          const uint64_t e = drop_row + (uint64_t)(nb + j);
+          if ((e & 3) == 0) {
+            Philox4 rr = philox4x32(p.drop_seed, p.drop_offset, e >> 2);
+            v[j] = rr.x >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
+            v[j + 1] = rr.y >= p.drop_thr ? v[j + 1] * p.drop_scale : 0.f;
+            v[j + 2] = rr.z >= p.drop_thr ? v[j + 2] * p.drop_scale : 0.f;
+            v[j + 3] = rr.w >= p.drop_thr ? v[j + 3] * p.drop_scale : 0.f;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              v[j + t] = dropout_keep(p.drop_seed, p.drop_offset, e + t, p.drop_thr) ? v[j + t] * p.drop_scale : 0.f;
+          }
+        }
+      }
+      if (p.residual != nullptr) {
+        if (p.c_fp32) {
+          const float* rs = reinterpret_cast<const float*>(p.residual) + roff + nb;
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) v[j] += rs[j];
+        } else {
+          const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff + nb;
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) v[j] += __bfloat162float(rs[j]);
+        }
+      }
+      if (p.c_fp32) {
+        float* dst = reinterpret_cast<float*>(p.C) + roff + nb;
+        if (full && ((p.c_ld & 3) == 0) && ((zoff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) dst[j] = v[j];
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + roff + nb;
+        if (vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(dst + j) = pk;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) dst[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// rows x K operand. K-major: memory [rows][ld] (k contiguous). MN-major: memory [K][ld] (row index contiguous).
+static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, int rows, int K, long ld, int nb1,
+                            long bs1, int nb2, long bs2, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -10;
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (mn_major) {
+    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = BLOCK_K;
+  } else {
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
+    box[0] = BLOCK_K; box[1] = (cuuint32_t)box_rows;
+  }
+  if (nb1 > 1 && bs1 == 0) nb1 = 1;  // broadcast operand: the kernel pins that coordinate to 0
+  if (nb2 > 1 && bs2 == 0) nb2 = 1;
+  dims[2] = (cuuint64_t)nb1; dims[3] = (cuuint64_t)nb2;
+  box[2] = 1; box[3] = 1;
+  strides[0] = (cuuint64_t)ld * 2;
+  strides[1] = (cuuint64_t)(nb1 > 1 ? bs1 : ld) * 2;
+  strides[2] = (cuuint64_t)(nb2 > 1 ? bs2 : ld) * 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return -11;  // TMA needs 16-byte aligned base and strides
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -12;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, g.A, g.a_mn, g.M, g.K, g.a_ld, g.nb1, g.a_bs1, g.nb2, g.a_bs2, BLOCK_M);
+  if (rc) return rc;
+  rc = make_operand_map(&mb, g.B, g.b_mn, g.N, g.K, g.b_ld, g.nb1, g.b_bs1, g.nb2, g.b_bs2, BN);
+  if (rc) return rc - 10;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  auto kern = gemm_bf16_tcgen05<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.N + BN - 1) / BN, g.nb1 * g.nb2);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, ep);
+  return (int)cudaGetLastError();
+}
+
+template <int BN, int STAGES>
+static int launch_major(const GemmDesc& g, const EpiParams& ep, cudaStream_t stream) {
+  if (g.a_mn) {
+    if (g.b_mn) return launch_variant<BN, STAGES, true, true>(g, ep, stream);
+    return launch_variant<BN, STAGES, true, false>(g, ep, stream);
+  }
+  if (g.b_mn) return launch_variant<BN, STAGES, false, true>(g, ep, stream);
+  return launch_variant<BN, STAGES, false, false>(g, ep, stream);
+}
+
+int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.nb1 <= 0 || g.nb2 <= 0) return 0;
+  if (g.K <= 0) return -2;
+  if (g.accumulate && !g.c_fp32) return -3;
+  EpiParams ep;
+  ep.M = g.M; ep.N = g.N; ep.nb1 = g.nb1;
+  ep.C = g.C; ep.c_fp32 = g.c_fp32; ep.c_ld = g.c_ld; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2;
+  ep.C_pre = g.C_pre; ep.bias = g.bias; ep.bias2 = g.bias2; ep.bias2_rows = g.bias2_rows > 0 ? g.bias2_rows : 1;
+  ep.residual = g.residual; ep.act = g.act; ep.alpha = g.alpha; ep.accumulate = g.accumulate;
+  if (g.drop_p > 0.f) {
+    double t = (double)g.drop_p * 4294967296.0;
+    ep.drop_thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    ep.drop_scale = 1.f / (1.f - g.drop_p);
+  } else {
+    ep.drop_thr = 0; ep.drop_scale = 1.f;
+  }
+  ep.drop_seed = g.drop_seed; ep.drop_offset = g.drop_offset;
+  ep.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  ep.a_m1 = (g.nb1 > 1 && g.a_bs1 == 0) ? 0 : 1; ep.a_m2 = (g.nb2 > 1 && g.a_bs2 == 0) ? 0 : 1;
+  ep.b_m1 = (g.nb1 > 1 && g.b_bs1 == 0) ? 0 : 1; ep.b_m2 = (g.nb2 > 1 && g.b_bs2 == 0) ? 0 : 1;
+  // Tile choice: wide tiles when N is large enough to keep >= ~1 wave of CTAs, narrow tiles for skinny outputs.
+  const long tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+  const long batch = (long)g.nb1 * g.nb2;
+  if (g.N <= 64) return launch_major<64, 4>(g, ep, stream);
+  if (g.N >= 512 && tiles_m * ((g.N + 255) / 256) * batch >= 148) return launch_major<256, 4>(g, ep, stream);
+  return launch_major<128, 3>(g, ep, stream);
+}
+
+}  // namespace st5

@@ -1,0 +1,34 @@
+// Parameters shared between the host launcher (gemm.cu) and callers inside the library.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace st5 {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
+
+// D[z][m][n] = epilogue( alpha * sum_k A[z][m][k] * B[z][n][k] )
+// Operands are bf16. "K-major" = k is the contiguous index (row-major [rows][K]); "MN-major" = the m (or n)
+// index is contiguous (i.e. the operand is stored transposed, [K][rows]).
+struct GemmDesc {
+  int M, N, K;
+  int nb1, nb2;  // batch = nb1 * nb2, z = b2 * nb1 + b1
+  // A operand
+  const void* A; int a_mn; long a_ld; long a_bs1, a_bs2;  // ld = stride (elements) of the non-contiguous index
+  const void* B; int b_mn; long b_ld; long b_bs1, b_bs2;
+  // output (row-major [M][N] per batch)
+  void* C; int c_fp32; long c_ld; long c_bs1, c_bs2;
+  void* C_pre;            // optional: value before activation/dropout (same layout & dtype as C)
+  const float* bias;      // [N] or null
+  const float* bias2;     // optional row-group bias [M / bias2_rows][N]
+  int bias2_rows;
+  const void* residual;   // optional, same layout & dtype as C, added after activation/dropout
+  int act;
+  float alpha;
+  int accumulate;         // C += result (C must be fp32)
+  float drop_p; uint64_t drop_seed, drop_offset;
+};
+
+int gemm_launch(const GemmDesc& g, cudaStream_t stream);
+
+}  // namespace st5

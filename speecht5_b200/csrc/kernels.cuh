@@ -1,0 +1,69 @@
+// Launcher declarations for the non-GEMM kernels (definitions in elementwise.cu, norm.cu, attention.cu, optim.cu).
+#pragma once
+#include "../../include/speecht5_b200.h"
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace st5 {
+
+// activation storage accessors
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+
+int cast_bf16_launch(const float* src, int64_t src_ld, void* hi, void* lo, int64_t dst_ld, int64_t rows, int64_t cols,
+                     cudaStream_t s);
+int posenc_fwd_launch(const int64_t* tokens, const float* emb, const void* x, const float* pe, const float* alpha,
+                      void* y, int dtype, int64_t B, int64_t T, int64_t C, float drop_p, uint64_t seed, uint64_t offset,
+                      cudaStream_t s);
+int posenc_bwd_launch(const void* dy, const int64_t* tokens, int64_t padding_idx, const float* pe, void* dx,
+                      float* demb, float* dalpha, int dtype, int64_t B, int64_t T, int64_t C, float drop_p,
+                      uint64_t seed, uint64_t offset, cudaStream_t s);
+int ln_fwd_launch(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
+                  float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
+                  uint64_t offset, cudaStream_t s);
+int64_t ln_bwd_blocks(int64_t rows);
+int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
+                  void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
+                  float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s);
+int dropout_launch(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
+                   cudaStream_t s);
+int act_bwd_launch(const void* dy, const void* pre, void* dpre, int dtype, int act, int64_t n, float drop_p,
+                   uint64_t seed, uint64_t offset, cudaStream_t s);
+int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows, int64_t cols, int64_t group_rows,
+                  int accumulate, cudaStream_t s);
+int attn_fwd_launch(const st5_attn_args& a, cudaStream_t s);
+int attn_bwd_launch(const st5_attn_args& a, cudaStream_t s);
+int bn_fwd_launch(const void* x, int64_t x_ld, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, float* save_mean, float* save_rstd, void* y, int64_t y_ld, void* y_pre, int dtype,
+                  int64_t rows, int64_t C, int training, float momentum, float eps, int act, float drop_p,
+                  uint64_t seed, uint64_t offset, float* scratch, cudaStream_t s);
+int bn_bwd_launch(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const void* y_pre, const float* gamma,
+                  const float* save_mean, const float* save_rstd, void* dx, int64_t dx_ld, float* dgamma, float* dbeta,
+                  int dtype, int64_t rows, int64_t C, int act, float drop_p, uint64_t seed, uint64_t offset,
+                  float* scratch, cudaStream_t s);
+int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s);
+int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
+                float grad_mul, cudaStream_t s);
+
+}  // namespace st5

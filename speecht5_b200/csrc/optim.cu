@@ -1,0 +1,77 @@
+// Gradient-norm reduction and fused clip + Adam + bf16-shadow refresh over the flat parameter buffer.
+// Semantics follow the reference trainer: fairseq/trainer.py:796-826 (multiply_grads -> clip_grad_norm -> step),
+// fairseq/utils.py:clip_grad_norm_ (coef = max_norm / (norm + 1e-6), clamped to 1), fairseq/optim/adam.py:Adam.step
+// (denom = sqrt(v) + eps; step = lr * sqrt(1 - b2^t) / (1 - b1^t); weight decay p -= wd * lr * p).
+#include "kernels.cuh"
+
+namespace st5 {
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  float acc = 0.f;
+  const int64_t n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += x[i] * x[i];
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return -2;
+  int64_t g = (n / 4 + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  sumsq_kernel<<<(unsigned)g, 256, 0, s>>>(x, n, out);
+  return (int)cudaGetLastError();
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float beta1,
+                            float beta2, float eps, float wd, float step_size, const float* __restrict__ gnorm_sq,
+                            float max_norm, float grad_mul) {
+  float gscale = grad_mul;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float norm = sqrtf(*gnorm_sq) * grad_mul;
+    const float coef = max_norm / (norm + 1e-6f);
+    gscale *= coef < 1.f ? coef : 1.f;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float pi = p[i];
+    if (wd != 0.f) pi -= wd * lr * pi;
+    pi -= step_size * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    if (pb != nullptr) pb[i] = __float2bfloat16(pi);
+  }
+}
+int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
+                float grad_mul, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (step < 1) return -2;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  int64_t gsz = (n + 255) / 256;
+  if (gsz > 148 * 16) gsz = 148 * 16;
+  adam_kernel<<<(unsigned)gsz, 256, 0, s>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay,
+                                            step_size, grad_norm_sq, max_norm, grad_mul);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace st5

@@ -1,0 +1,176 @@
+"""Raw (non-autograd) Python wrappers over the C ABI. Tensors are torch CUDA tensors used purely as device buffers;
+every call goes to libspeecht5_b200.so on the current CUDA stream. No fallbacks."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, BF16, F32, AttnArgs, GemmArgs
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def dtype_id(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("speecht5_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1,
+         a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None,
+         act=None, alpha=1.0, accumulate=False, drop_p=0.0, seed=0, offset=0):
+    """out[z][m][n] = epi(alpha * sum_k A[z][m][k] B[z][n][k]); see st5_gemm_bf16 in include/speecht5_b200.h."""
+    _require_cuda(a, b, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    g = GemmArgs()
+    g.M, g.N, g.K, g.nb1, g.nb2 = M, N, K, nb1, nb2
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.c_fp32 = 1 if out.dtype == torch.float32 else 0
+    g.act = ACT_IDS[act]
+    g.accumulate = int(accumulate)
+    g.bias2_rows = bias2_rows
+    g.a, g.a_ld, g.a_bs1, g.a_bs2 = a.data_ptr(), (a_ld if a_ld is not None else (M if a_mn else K)), a_bs[0], a_bs[1]
+    g.b, g.b_ld, g.b_bs1, g.b_bs2 = b.data_ptr(), (b_ld if b_ld is not None else (N if b_mn else K)), b_bs[0], b_bs[1]
+    g.c, g.c_ld, g.c_bs1, g.c_bs2 = out.data_ptr(), (c_ld if c_ld is not None else N), c_bs[0], c_bs[1]
+    g.c_pre = None if c_pre is None else c_pre.data_ptr()
+    g.bias = None if bias is None else bias.data_ptr()
+    g.bias2 = None if bias2 is None else bias2.data_ptr()
+    g.residual = None if residual is None else residual.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    if bias2 is not None:
+        assert bias2.dtype == torch.float32
+    if residual is not None:
+        assert residual.dtype == out.dtype
+    if c_pre is not None:
+        assert c_pre.dtype == out.dtype
+    g.alpha = alpha
+    g.drop_p, g.drop_seed, g.drop_offset = drop_p, seed, offset
+    lib = _lib.load()
+    _lib.check(lib.st5_gemm_bf16(C.byref(g), _stream()), "st5_gemm_bf16")
+    return out
+
+
+def cast_bf16(src, hi, lo=None):
+    """2-D strided fp32 -> bf16 (hi) and optional bf16 residual (lo)."""
+    _require_cuda(src, hi)
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    assert hi.stride(1) == 1 and (lo is None or lo.stride() == hi.stride())
+    lib = _lib.load()
+    _lib.check(lib.st5_cast_bf16(_ptr(src), src.stride(0), _ptr(hi), _ptr(lo), hi.stride(0), rows, cols, _stream()),
+               "st5_cast_bf16")
+
+
+def posenc_fwd(tokens, emb, x, pe, alpha, y, drop_p=0.0, seed=0, offset=0):
+    B, T, Cc = y.shape
+    lib = _lib.load()
+    _lib.check(lib.st5_posenc_fwd(_ptr(tokens), _ptr(emb), _ptr(x), _ptr(pe), _ptr(alpha), _ptr(y), dtype_id(y), B, T,
+                                  Cc, drop_p, seed, offset, _stream()), "st5_posenc_fwd")
+
+
+def posenc_bwd(dy, tokens, padding_idx, pe, dx, demb, dalpha, drop_p=0.0, seed=0, offset=0):
+    B, T, Cc = dy.shape
+    lib = _lib.load()
+    _lib.check(lib.st5_posenc_bwd(_ptr(dy), _ptr(tokens), padding_idx, _ptr(pe), _ptr(dx), _ptr(demb), _ptr(dalpha),
+                                  dtype_id(dy), B, T, Cc, drop_p, seed, offset, _stream()), "st5_posenc_bwd")
+
+
+def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    lib = _lib.load()
+    _lib.check(lib.st5_ln_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s_out), _ptr(mean),
+                              _ptr(rstd), dtype_id(x), rows, Cc, eps, drop_p, seed, offset, _stream()), "st5_ln_fwd")
+
+
+def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, offset=0):
+    Cc = dy.shape[-1]
+    rows = dy.numel() // Cc
+    lib = _lib.load()
+    nblk = lib.st5_ln_bwd_blocks(rows)
+    partials = torch.empty(2 * nblk * Cc, dtype=torch.float32, device=dy.device)
+    _lib.check(lib.st5_ln_bwd(_ptr(dy), _ptr(s), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(ds), _ptr(dx),
+                              _ptr(dgamma), _ptr(dbeta), _ptr(partials), dtype_id(dy), rows, Cc, drop_p, seed, offset,
+                              _stream()), "st5_ln_bwd")
+
+
+def dropout(x, y, drop_p, seed, offset):
+    lib = _lib.load()
+    _lib.check(lib.st5_dropout(_ptr(x), _ptr(y), dtype_id(x), x.numel(), drop_p, seed, offset, _stream()),
+               "st5_dropout")
+
+
+def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
+    lib = _lib.load()
+    _lib.check(lib.st5_act_bwd(_ptr(dy), _ptr(pre), _ptr(dpre), dtype_id(dy), ACT_IDS[act], dy.numel(), drop_p, seed,
+                               offset, _stream()), "st5_act_bwd")
+
+
+def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
+    rows, cols = x2d.shape
+    lib = _lib.load()
+    _lib.check(lib.st5_colsum(_ptr(x2d), ld if ld is not None else x2d.stride(0), _ptr(out), dtype_id(x2d), rows, cols,
+                              group_rows, int(accumulate), _stream()), "st5_colsum")
+
+
+def attn_args(**kw):
+    a = AttnArgs()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(a, k, v)
+    return a
+
+
+def attn_fwd(a):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_fwd(C.byref(a), _stream()), "st5_attn_fwd")
+
+
+def attn_bwd(a):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_bwd(C.byref(a), _stream()), "st5_attn_bwd")
+
+
+def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd, y, y_ld, y_pre, rows, Cc, training,
+           momentum, eps, act, drop_p, seed, offset, scratch):
+    lib = _lib.load()
+    _lib.check(lib.st5_bn_fwd(_ptr(x), x_ld, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                              _ptr(save_mean), _ptr(save_rstd), _ptr(y), y_ld, _ptr(y_pre), dtype_id(x), rows, Cc,
+                              int(training), momentum, eps, ACT_IDS[act], drop_p, seed, offset, _ptr(scratch),
+                              _stream()), "st5_bn_fwd")
+
+
+def bn_bwd(dy, dy_ld, x, x_ld, y_pre, gamma, save_mean, save_rstd, dx, dx_ld, dgamma, dbeta, rows, Cc, act, drop_p,
+           seed, offset, scratch):
+    lib = _lib.load()
+    _lib.check(lib.st5_bn_bwd(_ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(y_pre), _ptr(gamma), _ptr(save_mean),
+                              _ptr(save_rstd), _ptr(dx), dx_ld, _ptr(dgamma), _ptr(dbeta), dtype_id(x), rows, Cc,
+                              ACT_IDS[act], drop_p, seed, offset, _ptr(scratch), _stream()), "st5_bn_bwd")
+
+
+def sumsq(x, out):
+    lib = _lib.load()
+    _lib.check(lib.st5_sumsq(_ptr(x), x.numel(), _ptr(out), _stream()), "st5_sumsq")
+
+
+def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_norm_sq, max_norm, grad_mul):
+    lib = _lib.load()
+    _lib.check(lib.st5_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), lr, beta1, beta2, eps,
+                                 weight_decay, step, _ptr(grad_norm_sq), max_norm, grad_mul, _stream()),
+               "st5_adam_step")

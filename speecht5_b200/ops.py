@@ -1,0 +1,503 @@
+"""Autograd-visible operators of the SpeechT5 hot path. PyTorch autograd is used only as the tape; every forward and
+backward computation below is a call into the hand-written CUDA library (speecht5_b200.kernels -> C ABI).
+
+Two numeric modes (Runtime.dtype):
+  * torch.bfloat16 -- throughput mode: bf16 activations, bf16 tensor-core GEMMs with fp32 accumulation, fp32 statistics.
+  * torch.float32  -- parity mode: fp32 activations; each GEMM is evaluated as hi*hi + hi*lo + lo*hi over bf16 splits of
+    both operands (three accumulate passes of the same tcgen05 kernel), i.e. ~2^-16 relative operand error.
+"""
+import torch
+
+from . import kernels as K
+
+
+class Runtime:
+    """Process-wide numeric mode, dropout counter stream and bf16 weight-shadow cache."""
+
+    def __init__(self):
+        self.dtype = torch.bfloat16
+        self.seed = 1
+        self._offset = 0
+        self.param_epoch = 0
+        self._shadows = {}
+
+    def next_offset(self):
+        self._offset += 1
+        return self._offset
+
+    def manual_seed(self, seed):
+        self.seed = int(seed)
+        self._offset = 0
+
+    def invalidate_shadows(self):
+        """Call after parameters change (optimizer step, load_state_dict)."""
+        self.param_epoch += 1
+
+    def shadow(self, key, build):
+        """bf16 (hi, lo) copy of a (possibly fused / re-laid-out) fp32 weight; `build()` returns the fp32 2-D tensor."""
+        ent = self._shadows.get(key)
+        need_lo = self.dtype == torch.float32
+        if ent is not None and ent[0] == self.param_epoch and (ent[2] is not None or not need_lo):
+            return ent[1], ent[2]
+        w = build()
+        w = w.detach()
+        if w.dim() != 2 or w.stride(1) != 1:
+            w = w.reshape(w.shape[0], -1).contiguous()
+        hi = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+        lo = torch.empty_like(hi) if need_lo else None
+        K.cast_bf16(w, hi, lo)
+        self._shadows[key] = (self.param_epoch, hi, lo)
+        return hi, lo
+
+
+RT = Runtime()
+
+
+def _split(x2d):
+    """activation [rows, cols] (strided 2-D, unit inner stride) -> (hi, lo) bf16 operands for the GEMM."""
+    if x2d.dtype == torch.bfloat16:
+        return x2d, None
+    hi = torch.empty(x2d.shape, dtype=torch.bfloat16, device=x2d.device)
+    lo = torch.empty_like(hi)
+    K.cast_bf16(x2d, hi, lo)
+    return hi, lo
+
+
+def mm(a, b, out, *, M, N, Kd, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, **epi):
+    """out = epi(A . B^T) with A, B given as (hi, lo) pairs; lo is None in bf16 mode. Parity mode: 3 passes."""
+    a_hi, a_lo = a
+    b_hi, b_lo = b
+    kw = dict(M=M, N=N, K=Kd, a_mn=a_mn, b_mn=b_mn, a_ld=a_ld, b_ld=b_ld, c_ld=c_ld)
+    if a_lo is None and b_lo is None:
+        return K.gemm(a_hi, b_hi, out, **kw, **epi)
+    assert out.dtype == torch.float32, "split-precision GEMM accumulates in an fp32 output"
+    acc0 = epi.pop("accumulate", False)
+    alpha = epi.pop("alpha", 1.0)
+    passes = [(a_hi, b_hi)]
+    if b_lo is not None:
+        passes.append((a_hi, b_lo))
+    if a_lo is not None:
+        passes.append((a_lo, b_hi))
+    for i, (pa, pb) in enumerate(passes):
+        last = i == len(passes) - 1
+        K.gemm(pa, pb, out, **kw, alpha=alpha, accumulate=(acc0 or i > 0), **(epi if last else {}))
+    return out
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+# =================================================================================================== Linear
+class LinearFn(torch.autograd.Function):
+    """y = dropout(act(x W^T + b (+ rowgroup bias))) (+ residual). W may be several parameters fused along N.
+
+    Replaces nn.Linear call sites of the reference (multihead_attention.py:213-231,397; transformer_layer.py:127-132,
+    385-391; speech_decoder_prenet.py:41-47,69-72; speech_decoder_postnet.py:31-32)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, bias2, opts, *params):
+        nw = opts["n_weights"]
+        weights, biases = params[:nw], params[nw:]
+        key = ("lin",) + tuple(id(w) for w in weights)
+        w_sh = RT.shadow(key, (lambda: weights[0]) if nw == 1 else (lambda: torch.cat([w.detach() for w in weights], 0)))
+        N, Kd = w_sh[0].shape
+        x2 = x.reshape(-1, x.shape[-1])
+        M = x2.shape[0]
+        assert x2.shape[1] == Kd and x2.stride(1) == 1
+        bias = None
+        if len(biases) > 0:
+            bias = biases[0].detach() if len(biases) == 1 else torch.cat([b.detach() for b in biases], 0)
+            bias = bias.float().contiguous()
+        ldc = _pad8(N)
+        out_dtype = opts.get("out_dtype", x.dtype)
+        out = torch.empty((M, ldc), dtype=out_dtype, device=x.device)
+        act, drop_p = opts.get("act"), opts.get("drop_p", 0.0)
+        pre = torch.empty_like(out) if act is not None else None
+        off = RT.next_offset() if drop_p > 0 else 0
+        xa = _split(x2)
+        res2 = residual.reshape(M, -1) if residual is not None else None
+        if res2 is not None:
+            assert res2.shape[1] == N and ldc == N and res2.is_contiguous()
+        mm(xa, w_sh, out, M=M, N=N, Kd=Kd, a_ld=x2.stride(0), b_ld=Kd, c_ld=ldc, bias=bias,
+           bias2=bias2.detach().float().contiguous() if bias2 is not None else None,
+           bias2_rows=opts.get("bias2_rows", 0), residual=res2, c_pre=pre, act=act, drop_p=drop_p, seed=RT.seed,
+           offset=off)
+        ctx.save_for_backward(x2, pre)
+        ctx.meta = (weights, biases, w_sh, xa if x2.dtype == torch.float32 else None, act, drop_p, off, N, Kd, M, ldc,
+                    x.shape, residual is not None, bias2 is not None, opts.get("bias2_rows", 0), RT.seed,
+                    opts.get("need_dx", True))
+        y = out if ldc == N else out[:, :N]
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, pre = ctx.saved_tensors
+        (weights, biases, w_sh, xa, act, drop_p, off, N, Kd, M, ldc, xshape, has_res, has_b2, b2rows, seed,
+         need_dx) = ctx.meta
+        dev = dy.device
+        dy2 = dy.reshape(M, N)
+        if not (dy2.stride(1) == 1 and dy2.stride(0) % 8 == 0 and dy2.data_ptr() % 16 == 0):
+            buf = torch.zeros((M, ldc), dtype=dy.dtype, device=dev)
+            buf[:, :N] = dy2
+            dy2 = buf[:, :N]
+        d_res = dy if has_res else None
+        if act is not None or drop_p > 0:
+            dpre_full = torch.empty((M, dy2.stride(0)), dtype=dy.dtype, device=dev)
+            if act is not None:
+                # elementwise over the padded row pitch: indices must match the forward's logical (m * N + n) index
+                if dy2.stride(0) == N and ldc == N:
+                    K.act_bwd(dy2, pre, dpre_full, act, drop_p, seed, off)
+                else:
+                    dyc = dy2.contiguous()
+                    prec = pre[:, :N].contiguous()
+                    tmp = torch.empty_like(dyc)
+                    K.act_bwd(dyc, prec, tmp, act, drop_p, seed, off)
+                    dpre_full = torch.zeros((M, ldc), dtype=dy.dtype, device=dev)
+                    dpre_full[:, :N] = tmp
+            else:
+                dyc = dy2.contiguous()
+                tmp = torch.empty_like(dyc)
+                K.dropout(dyc, tmp, drop_p, seed, off)
+                dpre_full = torch.zeros((M, ldc), dtype=dy.dtype, device=dev)
+                dpre_full[:, :N] = tmp
+            dpre = dpre_full[:, :N]
+        else:
+            dpre = dy2
+        ga = _split(dpre)
+        dpre_ld = dpre.stride(0)
+        dx = None
+        if need_dx and ctx.needs_input_grad[0]:
+            dx = torch.empty((M, Kd), dtype=dy.dtype, device=dev)
+            # dx[m,k] = sum_n dpre[m,n] W[n,k]: B operand rows = k, stored [n][k] -> MN-major
+            mm(ga, w_sh, dx, M=M, N=Kd, Kd=N, a_ld=dpre_ld, b_mn=True, b_ld=Kd, c_ld=Kd)
+            dx = dx.reshape(xshape)
+        # dW[n,k] = sum_m dpre[m,n] x[m,k]: both operands MN-major
+        dW = torch.empty((N, Kd), dtype=torch.float32, device=dev)
+        xop = xa if xa is not None else (x2, None)
+        mm(ga, xop, dW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd)
+        grads_w, r0 = [], 0
+        for w in weights:
+            grads_w.append(dW[r0:r0 + w.shape[0]].reshape(w.shape))
+            r0 += w.shape[0]
+        grads_b = []
+        d_b2 = None
+        if len(biases) > 0 or has_b2:
+            if len(biases) > 0:
+                db = torch.empty(N, dtype=torch.float32, device=dev)
+                K.colsum(dpre, db, ld=dpre_ld)
+                r0 = 0
+                for b in biases:
+                    grads_b.append(db[r0:r0 + b.shape[0]])
+                    r0 += b.shape[0]
+            if has_b2:
+                d_b2 = torch.empty(((M + b2rows - 1) // b2rows, N), dtype=torch.float32, device=dev)
+                K.colsum(dpre, d_b2, group_rows=b2rows, ld=dpre_ld)
+        return (dx, d_res, d_b2, None, *grads_w, *grads_b)
+
+
+def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=None, bias2_rows=0, out_dtype=None,
+           need_dx=True):
+    if isinstance(weights, torch.Tensor):
+        weights = (weights,)
+    if isinstance(biases, torch.Tensor):
+        biases = (biases,)
+    biases = tuple(b for b in biases if b is not None)
+    opts = dict(n_weights=len(weights), act=act, drop_p=drop_p, bias2_rows=bias2_rows, need_dx=need_dx)
+    if out_dtype is not None:
+        opts["out_dtype"] = out_dtype
+    return LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
+
+
+# =================================================================================================== LayerNorm
+class ResidualLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(residual + dropout(x)) -- the post-LN tail of every reference block
+    (transformer_layer.py:112-132, 343-391) and the encoder input LayerNorm (encoder.py:226-227)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        y = torch.empty_like(x)
+        s = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        off = RT.next_offset() if drop_p > 0 else 0
+        res = residual.contiguous() if residual is not None else None
+        K.ln_fwd(x, res, gamma.detach(), beta.detach(), y, s, mean, rstd, eps, drop_p, RT.seed, off)
+        ctx.save_for_backward(s, mean, rstd, gamma)
+        ctx.meta = (drop_p, off, RT.seed, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, mean, rstd, gamma = ctx.saved_tensors
+        drop_p, off, seed, has_res = ctx.meta
+        dy = dy.contiguous()
+        ds = torch.empty_like(dy)
+        dx = torch.empty_like(dy) if drop_p > 0 else None
+        dgamma = torch.zeros_like(gamma, dtype=torch.float32)
+        dbeta = torch.zeros_like(gamma, dtype=torch.float32)
+        K.ln_bwd(dy, s, mean, rstd, gamma.detach(), ds, dx, dgamma, dbeta, drop_p, seed, off)
+        return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None
+
+
+def residual_layer_norm(x, residual, ln, drop_p=0.0):
+    return ResidualLayerNormFn.apply(x, residual, ln.weight, ln.bias, ln.eps, drop_p)
+
+
+# =================================================================================================== pos. encoding
+class PosEncFn(torch.autograd.Function):
+    """dropout((E[tokens] | x) + alpha * pe): text_encoder_prenet.py:36-45, speech_decoder_prenet.py:52-67."""
+
+    @staticmethod
+    def forward(ctx, tokens, emb, x, pe, alpha, padding_idx, drop_p):
+        if tokens is not None:
+            B, T = tokens.shape
+            Cc = emb.shape[1]
+            y = torch.empty((B, T, Cc), dtype=RT.dtype, device=emb.device)
+        else:
+            x = x.contiguous()
+            B, T, Cc = x.shape
+            y = torch.empty_like(x)
+        off = RT.next_offset() if drop_p > 0 else 0
+        K.posenc_fwd(tokens, emb.detach() if emb is not None else None, x, pe, alpha.detach(), y, drop_p, RT.seed, off)
+        ctx.save_for_backward(tokens, pe)
+        ctx.meta = (emb.shape if emb is not None else None, padding_idx, drop_p, off, RT.seed, x is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        tokens, pe = ctx.saved_tensors
+        emb_shape, padding_idx, drop_p, off, seed, has_x = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy) if has_x else None
+        demb = torch.zeros(emb_shape, dtype=torch.float32, device=dy.device) if emb_shape is not None else None
+        dalpha = torch.zeros((), dtype=torch.float32, device=dy.device)
+        K.posenc_bwd(dy, tokens, padding_idx if padding_idx is not None else -1, pe, dx, demb, dalpha, drop_p, seed, off)
+        return None, demb, dx, None, dalpha, None, None
+
+
+def scaled_posenc(pe, alpha, drop_p, tokens=None, emb=None, padding_idx=None, x=None):
+    return PosEncFn.apply(tokens, emb, x, pe, alpha, padding_idx, drop_p)
+
+
+# =================================================================================================== attention
+class AttentionFn(torch.autograd.Function):
+    """softmax(scale * q (k + pe)^T + masks) v on fused projection buffers.
+
+    q_buf: [B, Tq, nq*d] with q in column block `q_col`; kv_buf: [B, Tk, nk*d] with k / v in blocks k_col / v_col
+    (kv_buf is q_buf for self-attention). Returns (out [B,Tq,d], probs [B,H,Tq,p_ld] fp32 or activation dtype)."""
+
+    @staticmethod
+    def forward(ctx, q_buf, kv_buf, pe_k, key_pad, cfg):
+        ctx.set_materialize_grads(False)
+        same = kv_buf is None
+        kvb = q_buf if same else kv_buf
+        B, Tq = q_buf.shape[0], q_buf.shape[1]
+        Tk = kvb.shape[1]
+        H, d = cfg["H"], cfg["d"]
+        assert d == H * 64
+        dev = q_buf.device
+        out = torch.empty((B, Tq, d), dtype=q_buf.dtype, device=dev)
+        p_ld = _pad8(Tk)
+        probs_dtype = torch.float32 if cfg.get("return_probs") else q_buf.dtype
+        probs = torch.empty((B, H, Tq, p_ld), dtype=probs_dtype, device=dev)
+        drop_p = cfg.get("drop_p", 0.0)
+        off = RT.next_offset() if drop_p > 0 else 0
+        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        esz = q_buf.element_size()
+        common = dict(
+            B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
+            maxpos=cfg.get("maxpos", 0), probs_dtype=K.dtype_id(probs),
+            q=q_buf.data_ptr() + cfg["q_col"] * d * esz, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0),
+            k=kvb.data_ptr() + cfg["k_col"] * d * esz, k_ld=kvb.stride(1), k_bs=kvb.stride(0),
+            v=kvb.data_ptr() + cfg["v_col"] * d * esz, v_ld=kvb.stride(1), v_bs=kvb.stride(0),
+            key_pad=kp, pe_k=pe_k.detach() if pe_k is not None else None,
+            out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld,
+            scale=cfg["scale"], drop_p=drop_p, seed=RT.seed, offset=off)
+        K.attn_fwd(K.attn_args(**common))
+        ctx.save_for_backward(q_buf, kv_buf, pe_k, kp, probs)
+        ctx.meta = (cfg, off, RT.seed, p_ld, same)
+        return out, probs[..., :Tk] if p_ld != Tk else probs
+
+    @staticmethod
+    def backward(ctx, dout, dprobs):
+        q_buf, kv_buf, pe_k, kp, probs = ctx.saved_tensors
+        cfg, off, seed, p_ld, same = ctx.meta
+        kvb = q_buf if same else kv_buf
+        B, Tq = q_buf.shape[0], q_buf.shape[1]
+        Tk = kvb.shape[1]
+        H, d = cfg["H"], cfg["d"]
+        dev = q_buf.device
+        if dout is None:
+            dout = torch.zeros((B, Tq, d), dtype=q_buf.dtype, device=dev)
+        dout = dout.contiguous()
+        dq_buf = torch.zeros_like(q_buf) if q_buf.shape[2] != (3 * d if same else d) else torch.empty_like(q_buf)
+        dkv_buf = dq_buf if same else torch.empty_like(kv_buf)
+        ds = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+        dpe = torch.zeros_like(pe_k, dtype=torch.float32) if pe_k is not None else None
+        dpx = None
+        if dprobs is not None:
+            dpx = dprobs
+            if dpx.dtype != torch.float32 or dpx.shape[-1] != p_ld or not dpx.is_contiguous():
+                buf = torch.zeros((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+                buf[..., :Tk] = dprobs
+                dpx = buf
+        esz = q_buf.element_size()
+        a = K.attn_args(
+            B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
+            maxpos=cfg.get("maxpos", 0), probs_dtype=K.dtype_id(probs),
+            q=q_buf.data_ptr() + cfg["q_col"] * d * esz, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0),
+            k=kvb.data_ptr() + cfg["k_col"] * d * esz, k_ld=kvb.stride(1), k_bs=kvb.stride(0),
+            v=kvb.data_ptr() + cfg["v_col"] * d * esz, v_ld=kvb.stride(1), v_bs=kvb.stride(0),
+            key_pad=kp, pe_k=pe_k.detach() if pe_k is not None else None,
+            out=None, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=cfg["scale"],
+            drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off,
+            dout=dout, dprobs_ext=dpx, ds=ds,
+            dq=dq_buf.data_ptr() + cfg["q_col"] * d * esz, dk=dkv_buf.data_ptr() + cfg["k_col"] * d * esz,
+            dv=dkv_buf.data_ptr() + cfg["v_col"] * d * esz, dpe_k=dpe)
+        K.attn_bwd(a)
+        return dq_buf, (None if same else dkv_buf), dpe, None, None
+
+
+def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, maxpos=0, key_pad=None, causal=False,
+              drop_p=0.0, return_probs=False):
+    cfg = dict(H=H, d=d, q_col=q_col, k_col=k_col, v_col=v_col, scale=scale, maxpos=maxpos, causal=causal,
+               drop_p=drop_p, return_probs=return_probs)
+    return AttentionFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
+
+
+# =================================================================================================== postnet blocks
+class Conv1dK5Fn(torch.autograd.Function):
+    """Conv1d(kernel 5, padding 2, no bias) on channels-last activations [B,T,Cin] as ONE GEMM over an
+    overlapping-window view of the zero-padded buffer (no im2col): out[b,t,:] = W2 . xpad[b, t:t+5, :].ravel().
+    espnet Postnet convs behind speech_decoder_postnet.py:39-51."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        B, T, Cin = x.shape
+        Cout, _, Kw = weight.shape
+        pad = (Kw - 1) // 2
+        Tp = T + 2 * pad
+        xp = torch.zeros((B, Tp, Cin), dtype=x.dtype, device=x.device)
+        xp[:, pad:pad + T] = x
+        w_sh = RT.shadow(("conv_f", id(weight)), lambda: weight.detach().permute(0, 2, 1).reshape(Cout, Kw * Cin))
+        ldc = _pad8(Cout)
+        out = torch.empty((B, T, ldc), dtype=x.dtype, device=x.device)
+        xa = _split(xp.view(B * Tp, Cin))
+        # window GEMM: rows t (per batch b), K = Kw*Cin contiguous starting at xpad[b, t]; ld = Cin
+        _conv_mm(xa, w_sh, out, B=B, T=T, Tp=Tp, Cin=Cin, Cout=Cout, Kw=Kw, ldc=ldc)
+        ctx.save_for_backward(weight)
+        ctx.xa = xa
+        ctx.meta = (B, T, Tp, Cin, Cout, Kw, pad)
+        return out if ldc == Cout else out[..., :Cout]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (weight,) = ctx.saved_tensors
+        B, T, Tp, Cin, Cout, Kw, pad = ctx.meta
+        dev = dy.device
+        dyp = torch.zeros((B, Tp, Cout), dtype=dy.dtype, device=dev)
+        dyp[:, pad:pad + T] = dy
+        ga = _split(dyp.view(B * Tp, Cout))
+        # dx[b,t,ci] = sum_{u,co} dypad[b,t+u,co] * W[co,ci,Kw-1-u]
+        w_b = RT.shadow(("conv_b", id(weight)),
+                        lambda: weight.detach().flip(2).permute(1, 2, 0).reshape(Cin, Kw * Cout))
+        ldx = _pad8(Cin)
+        dx = torch.empty((B, T, ldx), dtype=dy.dtype, device=dev)
+        _conv_mm(ga, w_b, dx, B=B, T=T, Tp=Tp, Cin=Cout, Cout=Cin, Kw=Kw, ldc=ldx)
+        # dW2[co, u*Cin+ci] = sum_rho dypad_flat[rho+pad, co] * xpad_flat[rho+u, ci]  (both MN-major, K = B*Tp - 2*pad)
+        Kd = B * Tp - 2 * pad
+        dW2 = torch.empty((Cout, Kw * Cin), dtype=torch.float32, device=dev)
+        a_ops = tuple(None if t is None else t[pad:] for t in ga)
+        mm(a_ops, ctx.xa, dW2, M=Cout, N=Kw * Cin, Kd=Kd, a_mn=True, a_ld=Cout, b_mn=True, b_ld=Cin, c_ld=Kw * Cin)
+        dW = dW2.view(Cout, Kw, Cin).permute(0, 2, 1).contiguous()
+        ctx.xa = None
+        return (dx if ldx == Cin else dx[..., :Cin]), dW
+
+
+def _conv_mm(xa, w_sh, out, *, B, T, Tp, Cin, Cout, Kw, ldc):
+    """Batched window GEMM used by Conv1dK5Fn (fwd and dgrad). xa = (hi, lo) of the padded [B*Tp, Cin] buffer."""
+    a_hi, a_lo = xa
+    b_hi, b_lo = w_sh
+    kw = dict(M=T, N=Cout, K=Kw * Cin, a_ld=Cin, b_ld=Kw * Cin, c_ld=ldc, nb1=B, nb2=1, a_bs=(Tp * Cin, 0),
+              b_bs=(0, 0), c_bs=(T * ldc, 0))
+    if a_lo is None:
+        K.gemm(a_hi, b_hi, out, **kw)
+        return
+    K.gemm(a_hi, b_hi, out, **kw)
+    K.gemm(a_hi, b_lo, out, accumulate=True, **kw)
+    K.gemm(a_lo, b_hi, out, accumulate=True, **kw)
+
+
+def conv1d_k5(x, weight):
+    return Conv1dK5Fn.apply(x, weight)
+
+
+class BatchNormActFn(torch.autograd.Function):
+    """dropout(act(BatchNorm1d(x))) on channels-last rows; training statistics over all B*T rows."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, act, drop_p):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        dev = x.device
+        y = torch.empty_like(x)
+        y_pre = torch.empty_like(x) if act is not None else None
+        mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        scratch = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+        off = RT.next_offset() if drop_p > 0 else 0
+        K.bn_fwd(x, Cc, gamma.detach(), beta.detach(), running_mean, running_var, mean, rstd, y, Cc, y_pre, rows, Cc,
+                 training, momentum, eps, act, drop_p, RT.seed, off, scratch)
+        ctx.save_for_backward(x, y_pre, gamma, mean, rstd)
+        ctx.meta = (act, drop_p, off, RT.seed, rows, Cc, training)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y_pre, gamma, mean, rstd = ctx.saved_tensors
+        act, drop_p, off, seed, rows, Cc, training = ctx.meta
+        if not training:
+            raise RuntimeError("BatchNormActFn backward is only defined for training-mode statistics")
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        dgamma = torch.zeros(Cc, dtype=torch.float32, device=dy.device)
+        dbeta = torch.zeros_like(dgamma)
+        scratch = torch.empty(2 * Cc, dtype=torch.float32, device=dy.device)
+        K.bn_bwd(dy, Cc, x, Cc, y_pre, gamma.detach(), mean, rstd, dx, Cc, dgamma, dbeta, rows, Cc, act, drop_p, seed,
+                 off, scratch)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, training, act=None, drop_p=0.0):
+    return BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, drop_p)
+
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, drop_p):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        off = RT.next_offset()
+        K.dropout(x, y, drop_p, RT.seed, off)
+        ctx.meta = (drop_p, off, RT.seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        drop_p, off, seed = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        K.dropout(dy, dx, drop_p, seed, off)
+        return dx, None
+
+
+def dropout(x, drop_p, training=True):
+    if drop_p <= 0.0 or not training:
+        return x
+    return DropoutFn.apply(x, drop_p)
