@@ -15,6 +15,8 @@
  *     parameters, probabilities returned to the caller and all gradients of parameters are fp32;
  *   - dropout is counter based: keep(i) = philox4x32-10(seed, offset, i/4)[i%4] >= p*2^32 for the element with
  *     linear index i of the logical tensor, so forward and backward regenerate identical masks without storing them.
+ *     If bit 63 of `offset` is set, `seed` is the device address of a uint64 holding the seed (lets a captured CUDA
+ *     graph draw fresh masks on every replay).
  */
 #ifndef SPEECHT5_B200_H
 #define SPEECHT5_B200_H
@@ -150,7 +152,8 @@ int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const
 int st5_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */, void* stream);
 int st5_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
-                  float grad_mul, void* stream);
+                  float grad_mul, const float* lr_dev /* optional device lr */,
+                  const int64_t* step_dev /* optional device step counter */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,2 @@
+from .speecht5_criterion import SpeechT5Criterion, SpeechT5CriterionConfig  # noqa: F401
+from .text_to_speech_loss import TexttoSpeechLoss  # noqa: F401

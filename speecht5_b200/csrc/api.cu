@@ -133,9 +133,9 @@ int st5_sumsq(const float* x, int64_t n, float* out, void* stream) {
 }
 int st5_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
-                  float grad_mul, void* stream) {
+                  float grad_mul, const float* lr_dev, const int64_t* step_dev, void* stream) {
   return set_error(adam_launch(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, grad_norm_sq, max_norm,
-                               grad_mul, (cudaStream_t)stream),
+                               grad_mul, lr_dev, step_dev, (cudaStream_t)stream),
                    "st5_adam_step");
 }
 

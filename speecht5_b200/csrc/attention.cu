@@ -99,13 +99,15 @@ __global__ void __launch_bounds__(AT) attn_fwd_row(const st5_attn_args a) {
   const float inv = 1.f / denom;
   const uint32_t thr = drop_threshold(a.drop_p);
   const float dscale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  uint64_t dseed = a.seed, doffset = a.offset;
+  if (thr != 0) resolve_seed(dseed, doffset);
   const int64_t prow = (((int64_t)b * a.H + h) * a.Tq + i);
   PT* pout = a.probs != nullptr ? (PT*)a.probs + prow * a.p_ld : nullptr;
   for (int j = tid; j < (int)a.p_ld; j += AT) {
     if (j < a.Tk) {
       float p = sc[j] * inv;
       if (pout != nullptr) { stf(pout + j, p); p = ldf(pout + j); }
-      if (thr != 0) p = dropout_keep(a.seed, a.offset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
+      if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
       sc[j] = p;
     } else if (pout != nullptr) {
       stf(pout + j, 0.f);
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(AT) attn_bwd_q_row(const st5_attn_args a) {
   const float* dpe = a.dprobs_ext != nullptr ? a.dprobs_ext + prow * a.p_ld : nullptr;
   const uint32_t thr = drop_threshold(a.drop_p);
   const float dscale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  uint64_t dseed = a.seed, doffset = a.offset;
+  if (thr != 0) resolve_seed(dseed, doffset);
   const T* vbase = (const T*)a.v + (int64_t)b * a.v_bs + h * HD;
   float ldelta = 0.f;
   for (int j = tid; j < a.Tk; j += AT) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_q_row(const st5_attn_args a) {
       load_row64<T>(vbase + (int64_t)j * a.v_ld, vr);
 #pragma unroll
       for (int c = 0; c < HD; ++c) dp += dO[c] * vr[c];
-      if (thr != 0) dp = dropout_keep(a.seed, a.offset, (uint64_t)(prow * a.Tk + j), thr) ? dp * dscale : 0.f;
+      if (thr != 0) dp = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? dp * dscale : 0.f;
     }
     if (dpe != nullptr) dp += dpe[j];
     dsr[j] = dp;
@@ -196,6 +200,8 @@ __global__ void __launch_bounds__(AT) attn_bwd_kv_row(const st5_attn_args a) {
   const int tid = threadIdx.x, c = tid & (HD - 1), half = tid >> 6;
   const uint32_t thr = drop_threshold(a.drop_p);
   const float dscale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  uint64_t dseed = a.seed, doffset = a.offset;
+  if (thr != 0) resolve_seed(dseed, doffset);
   const int64_t bh = (int64_t)b * a.H + h;
   const T* qb = (const T*)a.q + (int64_t)b * a.q_bs + h * HD + c;
   const T* dob = (const T*)a.dout + (int64_t)b * a.o_bs + h * HD + c;
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kv_row(const st5_attn_args a) {
     const int64_t prow = bh * a.Tq + i;
     const float ds = a.ds[prow * a.p_ld + j];
     float p = ldf((const PT*)a.probs + prow * a.p_ld + j);
-    if (thr != 0) p = dropout_keep(a.seed, a.offset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
+    if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
     dk += ds * ldf(qb + (int64_t)i * a.q_ld);
     dv += p * ldf(dob + (int64_t)i * a.o_ld);
   }

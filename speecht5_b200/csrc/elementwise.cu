@@ -37,6 +37,7 @@ __global__ void posenc_fwd_kernel(const int64_t* __restrict__ tokens, const floa
                                   const T* __restrict__ x, const float* __restrict__ pe,
                                   const float* __restrict__ alpha, T* __restrict__ y, int64_t B, int64_t T_, int64_t C,
                                   uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   const int64_t n = B * T_ * C;
   const float a = *alpha;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -69,6 +70,7 @@ __global__ void posenc_bwd_kernel(const T* __restrict__ dy, const int64_t* __res
                                   const float* __restrict__ pe, T* __restrict__ dx, float* __restrict__ demb,
                                   float* __restrict__ dalpha, int64_t B, int64_t T_, int64_t C, uint32_t thr,
                                   float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   const int64_t n = B * T_ * C;
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -114,6 +116,7 @@ int posenc_bwd_launch(const void* dy, const int64_t* tokens, int64_t padding_idx
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, uint32_t thr, float dscale,
                                uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = ldf(x + i);
     if (thr != 0) v = dropout_keep(seed, offset, (uint64_t)i, thr) ? v * dscale : 0.f;
@@ -150,6 +153,7 @@ __device__ __forceinline__ float act_grad(float x, int act) {
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dpre, int act,
                                int64_t n, uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g = ldf(dy + i);
     if (thr != 0) g = dropout_keep(seed, offset, (uint64_t)i, thr) ? g * dscale : 0.f;

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
     const long roff = zoff + (long)row * p.c_ld;
     const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
     const uint64_t drop_row = ((uint64_t)z * (uint64_t)p.M + (uint64_t)row) * (uint64_t)p.N;
+    uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
+    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
           // unless aligned.
           const uint64_t e = drop_row + (uint64_t)(nb + j);
           if ((e & 3) == 0) {
-            Philox4 rr = philox4x32(p.drop_seed, p.drop_offset, e >> 2);
+            Philox4 rr = philox4x32(dseed, doffset, e >> 2);
             v[j] = rr.x >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
             v[j + 1] = rr.y >= p.drop_thr ? v[j + 1] * p.drop_scale : 0.f;
             v[j + 2] = rr.z >= p.drop_thr ? v[j + 2] * p.drop_scale : 0.f;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
           } else {
 #pragma unroll
             for (int t = 0; t < 4; ++t)
-              v[j + t] = dropout_keep(p.drop_seed, p.drop_offset, e + t, p.drop_thr) ? v[j + t] * p.drop_scale : 0.f;
+              v[j + t] = dropout_keep(dseed, doffset, e + t, p.drop_thr) ? v[j + t] * p.drop_scale : 0.f;
           }
         }
       }

@@ -64,6 +64,6 @@ int bn_bwd_launch(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, co
 int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s);
 int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
-                float grad_mul, cudaStream_t s);
+                float grad_mul, const float* lr_dev, const int64_t* step_dev, cudaStream_t s);
 
 }  // namespace st5

@@ -16,6 +16,7 @@ __global__ void ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res
                               const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ s_out,
                               float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C, float eps,
                               uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -98,6 +99,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s_
                               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ ds,
                               T* __restrict__ dx, float* __restrict__ partials, int64_t rows, int C, uint32_t thr,
                               float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = (C + 31) / 32;
   float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
@@ -261,6 +263,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, int64_t x_ld, const flo
                                 const float* __restrict__ rstd, T* __restrict__ y, int64_t y_ld, T* __restrict__ y_pre,
                                 int64_t rows, int C, int act, uint32_t thr, float dscale, uint64_t seed,
                                 uint64_t offset) {
+  resolve_seed(seed, offset);
   const int64_t n = rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / C;
@@ -341,6 +344,7 @@ __global__ void bn_bwd_stat_kernel(const T* __restrict__ dy, int64_t dy_ld, cons
                                    const float* __restrict__ rstd, float* __restrict__ scratch, int64_t rows, int C,
                                    int64_t rows_per_block, int act, uint32_t thr, float dscale, uint64_t seed,
                                    uint64_t offset) {
+  resolve_seed(seed, offset);
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
@@ -372,6 +376,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t dy_ld, con
                                     const float* __restrict__ scratch, T* __restrict__ dx, int64_t dx_ld,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C, int act,
                                     uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  resolve_seed(seed, offset);
   const int64_t n = rows * C;
   const float inv_n = 1.f / (float)rows;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -39,7 +39,15 @@ int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s) {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float beta1,
                             float beta2, float eps, float wd, float step_size, const float* __restrict__ gnorm_sq,
-                            float max_norm, float grad_mul) {
+                            float max_norm, float grad_mul, const float* __restrict__ lr_dev,
+                            const int64_t* __restrict__ step_dev) {
+  if (lr_dev != nullptr) lr = *lr_dev;
+  if (step_dev != nullptr) {  // device-resident schedule state: a captured CUDA graph stays valid across updates
+    const float t = (float)(*step_dev);
+    step_size = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
+  } else if (lr_dev != nullptr) {
+    step_size = lr * step_size;  // host passed the bias-correction factor only
+  }
   float gscale = grad_mul;
   if (gnorm_sq != nullptr && max_norm > 0.f) {
     const float norm = sqrtf(*gnorm_sq) * grad_mul;
@@ -61,16 +69,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
-                float grad_mul, cudaStream_t s) {
+                float grad_mul, const float* lr_dev, const int64_t* step_dev, cudaStream_t s) {
   if (n == 0) return 0;
-  if (step < 1) return -2;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  if (step < 1 && step_dev == nullptr) return -2;
+  float step_size = 0.f;
+  if (step_dev == nullptr) {
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    step_size = (float)((lr_dev != nullptr ? 1.0 : (double)lr) * sqrt(bc2) / bc1);
+  }
   int64_t gsz = (n + 255) / 256;
   if (gsz > 148 * 16) gsz = 148 * 16;
   adam_kernel<<<(unsigned)gsz, 256, 0, s>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay,
-                                            step_size, grad_norm_sq, max_norm, grad_mul);
+                                            step_size, grad_norm_sq, max_norm, grad_mul, lr_dev, step_dev);
   return (int)cudaGetLastError();
 }
 

@@ -170,6 +170,15 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t o
   }
   return Philox4{c0, c1, c2, c3};
 }
+// Seeds may be passed by value or -- so that a captured CUDA graph draws fresh masks on every replay -- as the device
+// address of a uint64 seed, flagged by bit 63 of `offset`.
+constexpr uint64_t SEED_PTR_FLAG = 1ull << 63;
+__device__ __forceinline__ void resolve_seed(uint64_t& seed, uint64_t& offset) {
+  if (offset & SEED_PTR_FLAG) {
+    seed = *reinterpret_cast<const uint64_t*>(seed);
+    offset &= ~SEED_PTR_FLAG;
+  }
+}
 // keep-mask for element `i` of a tensor: keep iff rand >= p * 2^32. thr = (uint32) min(p*2^32, 2^32-1).
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t i, uint32_t thr) {
   Philox4 r = philox4x32(seed, offset, i >> 2);

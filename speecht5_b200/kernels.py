@@ -8,6 +8,15 @@ from . import _lib
 from ._lib import ACT_IDS, BF16, F32, AttnArgs, GemmArgs
 
 
+LAUNCHES = 0      # kernels of libspeecht5_b200.so launched through this module (bench.py reports it)
+GEMM_RECORD = None  # when a list: every st5_gemm_bf16 argument block is appended (bench.py roofline replay)
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -62,7 +71,18 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
     g.drop_p, g.drop_seed, g.drop_offset = drop_p, seed, offset
     lib = _lib.load()
     _lib.check(lib.st5_gemm_bf16(C.byref(g), _stream()), "st5_gemm_bf16")
+    _count(1)
+    if GEMM_RECORD is not None:
+        GEMM_RECORD.append(g)
     return out
+
+
+def gemm_replay(records):
+    """Re-issue recorded GEMM launches back to back on the current stream (timing only)."""
+    lib = _lib.load()
+    st = _stream()
+    for g in records:
+        _lib.check(lib.st5_gemm_bf16(C.byref(g), st), "st5_gemm_bf16")
 
 
 def cast_bf16(src, hi, lo=None):
@@ -74,6 +94,7 @@ def cast_bf16(src, hi, lo=None):
     lib = _lib.load()
     _lib.check(lib.st5_cast_bf16(_ptr(src), src.stride(0), _ptr(hi), _ptr(lo), hi.stride(0), rows, cols, _stream()),
                "st5_cast_bf16")
+    _count(1)
 
 
 def posenc_fwd(tokens, emb, x, pe, alpha, y, drop_p=0.0, seed=0, offset=0):
@@ -81,6 +102,7 @@ def posenc_fwd(tokens, emb, x, pe, alpha, y, drop_p=0.0, seed=0, offset=0):
     lib = _lib.load()
     _lib.check(lib.st5_posenc_fwd(_ptr(tokens), _ptr(emb), _ptr(x), _ptr(pe), _ptr(alpha), _ptr(y), dtype_id(y), B, T,
                                   Cc, drop_p, seed, offset, _stream()), "st5_posenc_fwd")
+    _count(1)
 
 
 def posenc_bwd(dy, tokens, padding_idx, pe, dx, demb, dalpha, drop_p=0.0, seed=0, offset=0):
@@ -88,6 +110,7 @@ def posenc_bwd(dy, tokens, padding_idx, pe, dx, demb, dalpha, drop_p=0.0, seed=0
     lib = _lib.load()
     _lib.check(lib.st5_posenc_bwd(_ptr(dy), _ptr(tokens), padding_idx, _ptr(pe), _ptr(dx), _ptr(demb), _ptr(dalpha),
                                   dtype_id(dy), B, T, Cc, drop_p, seed, offset, _stream()), "st5_posenc_bwd")
+    _count(1)
 
 
 def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
@@ -96,6 +119,7 @@ def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed
     lib = _lib.load()
     _lib.check(lib.st5_ln_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s_out), _ptr(mean),
                               _ptr(rstd), dtype_id(x), rows, Cc, eps, drop_p, seed, offset, _stream()), "st5_ln_fwd")
+    _count(1)
 
 
 def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, offset=0):
@@ -107,18 +131,21 @@ def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, 
     _lib.check(lib.st5_ln_bwd(_ptr(dy), _ptr(s), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(ds), _ptr(dx),
                               _ptr(dgamma), _ptr(dbeta), _ptr(partials), dtype_id(dy), rows, Cc, drop_p, seed, offset,
                               _stream()), "st5_ln_bwd")
+    _count(2)
 
 
 def dropout(x, y, drop_p, seed, offset):
     lib = _lib.load()
     _lib.check(lib.st5_dropout(_ptr(x), _ptr(y), dtype_id(x), x.numel(), drop_p, seed, offset, _stream()),
                "st5_dropout")
+    _count(1)
 
 
 def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
     lib = _lib.load()
     _lib.check(lib.st5_act_bwd(_ptr(dy), _ptr(pre), _ptr(dpre), dtype_id(dy), ACT_IDS[act], dy.numel(), drop_p, seed,
                                offset, _stream()), "st5_act_bwd")
+    _count(1)
 
 
 def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
@@ -126,6 +153,7 @@ def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
     lib = _lib.load()
     _lib.check(lib.st5_colsum(_ptr(x2d), ld if ld is not None else x2d.stride(0), _ptr(out), dtype_id(x2d), rows, cols,
                               group_rows, int(accumulate), _stream()), "st5_colsum")
+    _count(1)
 
 
 def attn_args(**kw):
@@ -140,11 +168,13 @@ def attn_args(**kw):
 def attn_fwd(a):
     lib = _lib.load()
     _lib.check(lib.st5_attn_fwd(C.byref(a), _stream()), "st5_attn_fwd")
+    _count(1)
 
 
 def attn_bwd(a):
     lib = _lib.load()
     _lib.check(lib.st5_attn_bwd(C.byref(a), _stream()), "st5_attn_bwd")
+    _count(3)
 
 
 def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd, y, y_ld, y_pre, rows, Cc, training,
@@ -154,6 +184,7 @@ def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd
                               _ptr(save_mean), _ptr(save_rstd), _ptr(y), y_ld, _ptr(y_pre), dtype_id(x), rows, Cc,
                               int(training), momentum, eps, ACT_IDS[act], drop_p, seed, offset, _ptr(scratch),
                               _stream()), "st5_bn_fwd")
+    _count(5)
 
 
 def bn_bwd(dy, dy_ld, x, x_ld, y_pre, gamma, save_mean, save_rstd, dx, dx_ld, dgamma, dbeta, rows, Cc, act, drop_p,
@@ -162,15 +193,19 @@ def bn_bwd(dy, dy_ld, x, x_ld, y_pre, gamma, save_mean, save_rstd, dx, dx_ld, dg
     _lib.check(lib.st5_bn_bwd(_ptr(dy), dy_ld, _ptr(x), x_ld, _ptr(y_pre), _ptr(gamma), _ptr(save_mean),
                               _ptr(save_rstd), _ptr(dx), dx_ld, _ptr(dgamma), _ptr(dbeta), dtype_id(x), rows, Cc,
                               ACT_IDS[act], drop_p, seed, offset, _ptr(scratch), _stream()), "st5_bn_bwd")
+    _count(2)
 
 
 def sumsq(x, out):
     lib = _lib.load()
     _lib.check(lib.st5_sumsq(_ptr(x), x.numel(), _ptr(out), _stream()), "st5_sumsq")
+    _count(1)
 
 
-def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_norm_sq, max_norm, grad_mul):
+def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_norm_sq, max_norm, grad_mul,
+              lr_dev=None, step_dev=None):
     lib = _lib.load()
     _lib.check(lib.st5_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), lr, beta1, beta2, eps,
-                                 weight_decay, step, _ptr(grad_norm_sq), max_norm, grad_mul, _stream()),
-               "st5_adam_step")
+                                 weight_decay, step, _ptr(grad_norm_sq), max_norm, grad_mul, _ptr(lr_dev),
+                                 _ptr(step_dev), _stream()), "st5_adam_step")
+    _count(1)

@@ -1,0 +1,276 @@
+"""`t5_transformer` model and its architecture presets on the B200 kernel library -- drop-in for
+speecht5/models/speecht5.py (reference): same registry names (@register_model "t5_transformer"; archs t5_transformer,
+t5_transformer_base, t5_transformer_large, t5_transformer_base_asr :1252,1385,1402,1427), same forward signature
+(:786) and return tuples, same parameter names (checkpoints load with load_state_dict).
+
+Round-1 coverage of forward(): text -> speech (t2s, the BASELINE.json metric path). The speech-input branches
+(speech_encoder_prenet / hubert / codebook / s2c) are SURVEY.md section-8 rows still to come and raise
+NotImplementedError rather than silently falling back to PyTorch."""
+import logging
+from argparse import Namespace
+
+import torch
+import torch.nn as nn
+
+from ..fairseq_shim import FairseqEncoderDecoderModel, register_model, register_model_architecture
+from ..ops import RT
+from .modules.nets import SpeechDecoderPostnet, SpeechDecoderPrenet, TextEncoderPrenet
+from .modules.transformer import MultiheadAttention, TransformerDecoder, TransformerEncoder
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_MAX_TEXT_POSITIONS = 450
+DEFAULT_MAX_SPEECH_POSITIONS = 4000
+
+
+def Embedding(num_embeddings, embedding_dim, padding_idx):  # fairseq/models/transformer.py:1054
+    m = nn.Embedding(num_embeddings, embedding_dim, padding_idx=padding_idx)
+    nn.init.normal_(m.weight, mean=0, std=embedding_dim ** -0.5)
+    nn.init.constant_(m.weight[padding_idx], 0)
+    return m
+
+
+def init_bert_params(module):  # fairseq/modules/transformer_sentence_encoder.py:21-53
+    def normal_(data):
+        data.copy_(data.cpu().normal_(mean=0.0, std=0.02).to(data.device))
+    if isinstance(module, nn.Linear):
+        normal_(module.weight.data)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    if isinstance(module, nn.Embedding):
+        normal_(module.weight.data)
+        if module.padding_idx is not None:
+            module.weight.data[module.padding_idx].zero_()
+    if isinstance(module, MultiheadAttention):
+        normal_(module.q_proj.weight.data)
+        normal_(module.k_proj.weight.data)
+        normal_(module.v_proj.weight.data)
+
+
+class _Dict:
+    """Tiny stand-in for fairseq Dictionary when building without a task (len/pad only)."""
+
+    def __init__(self, n, pad=1):
+        self.n, self._pad = n, pad
+
+    def __len__(self):
+        return self.n
+
+    def pad(self):
+        return self._pad
+
+
+@register_model("t5_transformer")
+class T5TransformerModel(FairseqEncoderDecoderModel):
+    def __init__(self, args, encoder, decoder, text_encoder_prenet, speech_encoder_prenet, text_decoder_prenet,
+                 speech_decoder_prenet, text_decoder_postnet, speech_decoder_postnet, speaker_decoder_postnet,
+                 speech_encoder_postnet):
+        super().__init__(encoder, decoder)
+        self.encoder, self.decoder = encoder, decoder
+        self.text_encoder_prenet = text_encoder_prenet
+        self.speech_encoder_prenet = speech_encoder_prenet
+        self.text_decoder_prenet = text_decoder_prenet
+        self.speech_decoder_prenet = speech_decoder_prenet
+        self.text_decoder_postnet = text_decoder_postnet
+        self.speech_decoder_postnet = speech_decoder_postnet
+        self.speaker_decoder_postnet = speaker_decoder_postnet
+        self.hubert_layer = speech_encoder_postnet
+        self.reduction_factor = args.reduction_factor
+        self.spk_embed_dim = args.spk_embed_dim
+        self.spk_embed_integration_type = args.spk_embed_integration_type
+        assert self.spk_embed_integration_type == "pre" or self.spk_embed_dim is None, \
+            "only spk_embed_integration_type='pre' (the reference default) is implemented"
+        self.use_codebook = args.use_codebook
+        assert not self.use_codebook, "Gumbel-VQ code mixing (pre-training, SURVEY 8a row 22) is a later row"
+        self.num_updates = 0
+        if args.bert_init:
+            self.apply(init_bert_params)
+        self.args = args
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def build_model(cls, args, task=None):
+        base_architecture(args)
+        text_dict = task.dicts["text"] if task is not None else _Dict(getattr(args, "vocab_size", 81))
+
+        def build_embedding(dictionary, embed_dim):
+            return Embedding(len(dictionary), embed_dim, dictionary.pad())
+
+        text_decoder_embed_tokens = build_embedding(text_dict, args.decoder_embed_dim)
+        text_encoder_embed_tokens = (text_decoder_embed_tokens if args.share_input_output_embed
+                                     else build_embedding(text_dict, args.encoder_embed_dim))
+        speech_odim = getattr(args, "speech_odim", 80)
+        encoder = TransformerEncoder(args, text_dict, text_encoder_embed_tokens)
+        decoder = TransformerDecoder(args)
+        text_encoder_prenet = TextEncoderPrenet(text_encoder_embed_tokens, args)
+        speech_decoder_prenet = SpeechDecoderPrenet(speech_odim, args)
+        speech_decoder_postnet = SpeechDecoderPostnet(speech_odim, args)
+        return cls(args, encoder, decoder, text_encoder_prenet, None, None, speech_decoder_prenet, None,
+                   speech_decoder_postnet, None, None)
+
+    # ------------------------------------------------------------------ forward (models/speecht5.py:786-963)
+    def forward(self, source=None, src_tokens=None, src_lengths=None, prev_output_tokens=None, tgt_lengths=None,
+                spkembs=None, target_list=None, task_name=None, padding_mask=None, only_hubert=False, only_ctc=False,
+                feature_only=False, tgt_enc_layer=None, mask=True):
+        assert source is not None or src_tokens is not None
+        input_type = "text" if (source is None and padding_mask is None and not feature_only) else "speech"
+        output_type = "text" if (prev_output_tokens is not None and prev_output_tokens.dim() == 2) else "speech"
+        if input_type != "text" or output_type != "speech" or target_list is not None:
+            raise NotImplementedError(
+                f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built yet in the "
+                "B200 path; round 1 covers text->speech (t2s)")
+        encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
+        encoder_output = self.encoder(encoder_input, encoder_padding_mask, tgt_layer=tgt_enc_layer)
+        if "decoder_input" in encoder_output and encoder_output["decoder_input"][0] is not None:
+            encoder_output["encoder_out"] = encoder_output["decoder_input"]
+            encoder_output["_encoder_out_btc"] = encoder_output["decoder_input"][0].transpose(0, 1)
+        prev_output_tokens, tgt_mask = self.speech_decoder_prenet(prev_output_tokens, tgt_lengths, spkembs)
+        decoder_output, extra = self.decoder(
+            prev_output_tokens, tgt_mask, encoder_output,
+            full_context_alignment=getattr(self.args, "decoder_full_context_alignment", False),
+            alignment_layer=-1)  # target_list is None and output is speech (:921-923)
+        return self.speech_decoder_postnet(decoder_output) + (extra["attn"][0],)
+
+    # ------------------------------------------------------------------ fairseq model API used by callers
+    def set_num_updates(self, num_updates):
+        for m in self.modules():
+            if m is not self and hasattr(m, "set_num_updates"):
+                m.set_num_updates(num_updates)
+        self.num_updates = num_updates
+        RT.invalidate_shadows()  # fairseq calls this once per optimizer update: refresh bf16 weight shadows
+
+    def load_state_dict(self, state_dict, strict=True, model_cfg=None, args=None):
+        """Non-strict per-submodule loading like the reference (:1022-1058): missing sub-modules are skipped."""
+        own = self.state_dict()
+        filtered = {k: v for k, v in state_dict.items() if k in own and own[k].shape == v.shape}
+        dropped = [k for k in state_dict if k not in filtered]
+        if dropped:
+            logger.info("load_state_dict: ignoring %d keys absent/mismatched in the B200 t2s model", len(dropped))
+        out = super().load_state_dict(filtered, strict=False)
+        RT.invalidate_shadows()
+        return out
+
+    def max_positions(self):
+        return (self.args.max_speech_positions, self.args.max_text_positions)
+
+    def forward_text_encoder(self, src_tokens):
+        encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
+        return self.encoder(encoder_input, encoder_padding_mask)
+
+
+# ---------------------------------------------------------------------------------------------- architectures
+@register_model_architecture(model_name="t5_transformer", arch_name="t5_transformer")
+def base_architecture(args):  # models/speecht5.py:1252-1383 (fields used by the built path)
+    g = lambda k, v: setattr(args, k, getattr(args, k, v))  # noqa: E731
+    g("bert_init", False)
+    g("encoder_embed_dim", 768)
+    g("encoder_ffn_embed_dim", 768 * 4)
+    g("encoder_layers", 12)
+    g("encoder_attention_heads", 12)
+    g("encoder_normalize_before", False)
+    g("decoder_embed_dim", args.encoder_embed_dim)
+    g("decoder_ffn_embed_dim", args.encoder_ffn_embed_dim)
+    g("decoder_layers", 6)
+    g("decoder_attention_heads", 12)
+    g("decoder_normalize_before", False)
+    g("dropout", 0.1)
+    g("attention_dropout", args.dropout)
+    g("activation_dropout", args.dropout)
+    g("activation_fn", "gelu")
+    g("decoder_layerdrop", 0.0)
+    g("encoder_layerdrop", 0)
+    g("max_text_positions", DEFAULT_MAX_TEXT_POSITIONS)
+    g("max_speech_positions", DEFAULT_MAX_SPEECH_POSITIONS)
+    g("use_batch_norm", True)
+    g("enc_use_scaled_pos_enc", True)
+    g("dec_use_scaled_pos_enc", True)
+    g("postnet_layers", 5)
+    g("postnet_chans", 256)
+    g("postnet_filts", 5)
+    g("postnet_dropout_rate", 0.5)
+    g("dprenet_dropout_rate", 0.5)
+    g("dprenet_layers", 2)
+    g("dprenet_units", 256)
+    g("initial_encoder_alpha", 1.0)
+    g("initial_decoder_alpha", 1.0)
+    g("spk_embed_integration_type", "pre")
+    g("spk_embed_dim", 512)
+    g("encoder_reduction_factor", 1)
+    g("reduction_factor", 2)
+    g("transformer_enc_positional_dropout_rate", 0.1)
+    g("transformer_dec_positional_dropout_rate", 0.1)
+    g("layer_norm_eps", 1e-5)
+    g("no_scale_embedding", True)
+    g("share_input_output_embed", False)
+    g("share_ctc_embed", False)
+    g("freeze_encoder_updates", 0)
+    g("freeze_decoder_updates", 0)
+    g("no_freeze_encoder_layer", None)
+    g("layer_norm_first", False)
+    g("use_sent_enc_layer", True)
+    g("use_codebook", False)
+    g("relative_position_embedding", False)
+    g("encoder_max_relative_position", 160)
+    g("decoder_max_relative_position", 160)
+    g("feature_grad_mult", 0.1)
+    g("mask_prob", 0.0)
+
+
+@register_model_architecture("t5_transformer", "t5_transformer_base")
+def t5_transformer_base(args):  # :1385-1400
+    g = lambda k, v: setattr(args, k, getattr(args, k, v))  # noqa: E731
+    g("layer_norm_first", False)
+    g("relative_position_embedding", True)
+    g("dropout", 0.1)
+    g("activation_dropout", 0.0)
+    g("attention_dropout", 0.1)
+    g("encoder_layerdrop", 0.05)
+    g("decoder_layerdrop", 0.05)
+    g("mask_prob", 0.80)
+    base_architecture(args)
+
+
+@register_model_architecture("t5_transformer", "t5_transformer_large")
+def t5_transformer_large(args):  # :1402-1425
+    g = lambda k, v: setattr(args, k, getattr(args, k, v))  # noqa: E731
+    g("decoder_normalize_before", True)
+    g("layer_norm_first", True)
+    g("relative_position_embedding", True)
+    g("dropout", 0.0)
+    g("activation_dropout", 0.0)
+    g("attention_dropout", 0.0)
+    g("encoder_layerdrop", 0.0)
+    g("decoder_layerdrop", 0.0)
+    g("encoder_embed_dim", 1024)
+    g("encoder_layers", 24)
+    g("decoder_layers", 6)
+    g("encoder_ffn_embed_dim", 4096)
+    g("encoder_attention_heads", 16)
+    g("decoder_attention_heads", 16)
+    g("feature_grad_mult", 1.0)
+    g("mask_prob", 0.80)
+    base_architecture(args)
+
+
+@register_model_architecture("t5_transformer", "t5_transformer_base_asr")
+def t5_transformer_base_asr(args):  # :1427-1447
+    g = lambda k, v: setattr(args, k, getattr(args, k, v))  # noqa: E731
+    g("layer_norm_first", False)
+    g("relative_position_embedding", True)
+    g("dropout", 0.1)
+    g("activation_dropout", 0.1)
+    g("attention_dropout", 0.1)
+    g("feature_grad_mult", 0.0)
+    g("encoder_layerdrop", 0.1)
+    g("decoder_layerdrop", 0.1)
+    g("mask_prob", 0.75)
+    g("max_text_positions", 600)
+    base_architecture(args)
+
+
+def make_args(arch="t5_transformer_base_asr", **overrides):
+    """Namespace with an arch preset applied (what fairseq's option parser would hand to build_model)."""
+    args = Namespace(**overrides)
+    {"t5_transformer": base_architecture, "t5_transformer_base": t5_transformer_base,
+     "t5_transformer_large": t5_transformer_large, "t5_transformer_base_asr": t5_transformer_base_asr}[arch](args)
+    return args

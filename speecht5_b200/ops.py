@@ -14,20 +14,53 @@ from . import kernels as K
 class Runtime:
     """Process-wide numeric mode, dropout counter stream and bf16 weight-shadow cache."""
 
+    SEED_PTR_FLAG = 1 << 63
+
     def __init__(self):
         self.dtype = torch.bfloat16
-        self.seed = 1
+        self._seed = 1
+        self._seed_t = None  # device-resident seed (CUDA-graph mode): kernels dereference it at run time
         self._offset = 0
         self.param_epoch = 0
         self._shadows = {}
+        self._static = {}
+
+    @property
+    def seed(self):
+        return self._seed_t.data_ptr() if self._seed_t is not None else self._seed
 
     def next_offset(self):
         self._offset += 1
-        return self._offset
+        return (self._offset | self.SEED_PTR_FLAG) if self._seed_t is not None else self._offset
 
     def manual_seed(self, seed):
-        self.seed = int(seed)
+        self._seed = int(seed)
         self._offset = 0
+        if self._seed_t is not None:
+            self._seed_t.fill_(self._seed)
+
+    def enable_device_seed(self, device):
+        """Keep the dropout seed in device memory so a captured graph draws new masks each replay."""
+        if self._seed_t is None or self._seed_t.device != torch.device(device):
+            self._seed_t = torch.full((1,), self._seed, dtype=torch.int64, device=device)
+
+    def disable_device_seed(self):
+        self._seed_t = None
+
+    def advance_seed(self):
+        """New dropout masks for the next step (device op; capturable)."""
+        if self._seed_t is not None:
+            self._seed_t += 1
+        else:
+            self._seed += 1
+        self._offset = 0
+
+    def register_static(self, key, hi):
+        """Shadow that is kept current by someone else (the trainer's flat bf16 buffer refreshed by the Adam kernel)."""
+        self._static[key] = hi
+
+    def clear_static(self):
+        self._static = {}
 
     def invalidate_shadows(self):
         """Call after parameters change (optimizer step, load_state_dict)."""
@@ -35,8 +68,12 @@ class Runtime:
 
     def shadow(self, key, build):
         """bf16 (hi, lo) copy of a (possibly fused / re-laid-out) fp32 weight; `build()` returns the fp32 2-D tensor."""
-        ent = self._shadows.get(key)
         need_lo = self.dtype == torch.float32
+        if not need_lo:
+            st = self._static.get(key)
+            if st is not None:
+                return st, None
+        ent = self._shadows.get(key)
         if ent is not None and ent[0] == self.param_epoch and (ent[2] is not None or not need_lo):
             return ent[1], ent[2]
         w = build()
@@ -57,8 +94,10 @@ def _split(x2d):
     """activation [rows, cols] (strided 2-D, unit inner stride) -> (hi, lo) bf16 operands for the GEMM."""
     if x2d.dtype == torch.bfloat16:
         return x2d, None
-    hi = torch.empty(x2d.shape, dtype=torch.bfloat16, device=x2d.device)
-    lo = torch.empty_like(hi)
+    rows, cols = x2d.shape
+    ld = x2d.stride(0) if rows > 1 else _pad8(cols)  # keep the source row pitch: callers pass it as the GEMM ld
+    hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=x2d.device)[:, :cols]
+    lo = torch.empty((rows, ld), dtype=torch.bfloat16, device=x2d.device)[:, :cols]
     K.cast_bf16(x2d, hi, lo)
     return hi, lo
 
@@ -99,7 +138,7 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, residual, bias2, opts, *params):
         nw = opts["n_weights"]
         weights, biases = params[:nw], params[nw:]
-        key = ("lin",) + tuple(id(w) for w in weights)
+        key = opts.get("key") or (("lin",) + tuple(id(w) for w in weights))
         w_sh = RT.shadow(key, (lambda: weights[0]) if nw == 1 else (lambda: torch.cat([w.detach() for w in weights], 0)))
         N, Kd = w_sh[0].shape
         x2 = x.reshape(-1, x.shape[-1])
@@ -107,8 +146,10 @@ class LinearFn(torch.autograd.Function):
         assert x2.shape[1] == Kd and x2.stride(1) == 1
         bias = None
         if len(biases) > 0:
-            bias = biases[0].detach() if len(biases) == 1 else torch.cat([b.detach() for b in biases], 0)
-            bias = bias.float().contiguous()
+            bias = RT._static.get(("bias",) + tuple(id(b) for b in biases))  # contiguous view of the flat buffer
+            if bias is None:
+                bias = biases[0].detach() if len(biases) == 1 else torch.cat([b.detach() for b in biases], 0)
+                bias = bias.float().contiguous()
         ldc = _pad8(N)
         out_dtype = opts.get("out_dtype", x.dtype)
         out = torch.empty((M, ldc), dtype=out_dtype, device=x.device)
@@ -136,6 +177,8 @@ class LinearFn(torch.autograd.Function):
         (weights, biases, w_sh, xa, act, drop_p, off, N, Kd, M, ldc, xshape, has_res, has_b2, b2rows, seed,
          need_dx) = ctx.meta
         dev = dy.device
+        if dy.dtype != x2.dtype:  # fp32 head outputs of a bf16 network: gradients re-enter the bf16 stream here
+            dy = dy.to(x2.dtype)
         dy2 = dy.reshape(M, N)
         if not (dy2.stride(1) == 1 and dy2.stride(0) % 8 == 0 and dy2.data_ptr() % 16 == 0):
             buf = torch.zeros((M, ldc), dtype=dy.dtype, device=dev)
@@ -197,13 +240,13 @@ class LinearFn(torch.autograd.Function):
 
 
 def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=None, bias2_rows=0, out_dtype=None,
-           need_dx=True):
+           need_dx=True, key=None):
     if isinstance(weights, torch.Tensor):
         weights = (weights,)
     if isinstance(biases, torch.Tensor):
         biases = (biases,)
     biases = tuple(b for b in biases if b is not None)
-    opts = dict(n_weights=len(weights), act=act, drop_p=drop_p, bias2_rows=bias2_rows, need_dx=need_dx)
+    opts = dict(n_weights=len(weights), act=act, drop_p=drop_p, bias2_rows=bias2_rows, need_dx=need_dx, key=key)
     if out_dtype is not None:
         opts["out_dtype"] = out_dtype
     return LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
@@ -474,6 +517,8 @@ class BatchNormActFn(torch.autograd.Function):
 
 
 def batch_norm_act(x, bn, training, act=None, drop_p=0.0):
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1  # torch.nn.BatchNorm1d bookkeeping (checkpoint parity)
     return BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
                                 bn.momentum if bn.momentum is not None else 0.1, bn.eps, act, drop_p)
 

@@ -1,0 +1,235 @@
+"""-m gpu: every CUDA op (called through the C ABI) against a plain PyTorch fp32/fp64 statement of the same math."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def _mode():
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.float32
+    RT.manual_seed(1)
+    RT.invalidate_shadows()
+    yield
+    RT.dtype = torch.bfloat16
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 37, 768), (3, 5, 80), (2, 9, 1024)])
+def test_layer_norm_residual(cuda, dtype, shape):
+    from speecht5_b200 import ops
+    ops.RT.dtype = dtype
+    torch.manual_seed(0)
+    C = shape[-1]
+    ln = torch.nn.LayerNorm(C).to(cuda)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(shape, device=cuda).to(dtype).requires_grad_()
+    r = torch.randn(shape, device=cuda).to(dtype).requires_grad_()
+    y = ops.residual_layer_norm(x, r, ln)
+    g = torch.randn(shape, device=cuda).to(dtype)
+    y.backward(g)
+    xr, rr = x.detach().double().requires_grad_(), r.detach().double().requires_grad_()
+    lnr = torch.nn.LayerNorm(C).to(cuda).double()
+    lnr.load_state_dict(ln.state_dict())
+    yr = lnr(xr + rr)
+    yr.backward(g.double())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol and rel(r.grad, rr.grad) < tol
+    assert rel(ln.weight.grad, lnr.weight.grad) < tol and rel(ln.bias.grad, lnr.bias.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_autograd(cuda, dtype):
+    from speecht5_b200 import ops
+    ops.RT.dtype = dtype
+    torch.manual_seed(0)
+    M, K, N = 200, 768, 328
+    w1 = torch.nn.Parameter(torch.randn(N - 72, K, device=cuda) * 0.05)
+    w2 = torch.nn.Parameter(torch.randn(72, K, device=cuda) * 0.05)
+    b1 = torch.nn.Parameter(torch.randn(N - 72, device=cuda))
+    b2 = torch.nn.Parameter(torch.randn(72, device=cuda))
+    x = torch.randn(4, M // 4, K, device=cuda).to(dtype).requires_grad_()
+    y = ops.linear(x, (w1, w2), (b1, b2), act="gelu")
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().double().requires_grad_()
+    W = torch.cat([w1, w2]).detach().double().requires_grad_()
+    bb = torch.cat([b1, b2]).detach().double().requires_grad_()
+    yr = F.gelu(xr @ W.t() + bb)
+    yr.backward(g.double())
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol
+    assert rel(torch.cat([w1.grad, w2.grad]), W.grad) < tol
+    assert rel(torch.cat([b1.grad, b2.grad]), bb.grad) < tol
+
+
+def _ref_attention(q, k, v, pe, maxpos, key_pad, causal, scale):
+    """multihead_attention.py:340-389 in fp64. q,k,v [B,H,T,64]."""
+    B, H, Tq, _ = q.shape
+    Tk = k.shape[2]
+    s = torch.einsum("bhic,bhjc->bhij", q * scale, k)
+    if pe is not None:
+        i = torch.arange(Tq, device=q.device)[:, None]; j = torch.arange(Tk, device=q.device)[None, :]
+        idx = (i - j).clamp(-maxpos, maxpos - 1) + maxpos
+        pos = pe[idx]  # [Tq,Tk,64]
+        s = s + torch.einsum("bhic,ijc->bhij", q * scale, pos)
+    if causal:
+        s = s + torch.triu(torch.full((Tq, Tk), float("-inf"), device=q.device, dtype=s.dtype), 1)
+    if key_pad is not None:
+        s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhij,bhjc->bhic", p, v), p
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", ["self_rpe", "self_rpe_clip", "self_causal", "cross_probs"])
+def test_attention(cuda, dtype, case):
+    from speecht5_b200 import ops
+    ops.RT.dtype = dtype
+    torch.manual_seed(0)
+    B, H = 2, 3
+    d = H * 64
+    maxpos = 160 if case != "self_rpe_clip" else 8
+    Tq = 45 if case != "self_rpe_clip" else 37
+    Tk = Tq if case.startswith("self") else 29
+    lens = torch.tensor([Tk, Tk - 7], device=cuda)
+    key_pad = torch.arange(Tk, device=cuda)[None, :] >= lens[:, None]
+    pe = None
+    if "rpe" in case:
+        pe = torch.nn.Parameter(torch.randn(2 * maxpos, 64, device=cuda) * 0.3)
+    if case.startswith("self"):
+        qkv = (torch.randn(B, Tq, 3 * d, device=cuda) * 0.7).to(dtype).requires_grad_()
+        out, probs = ops.attention(qkv, None, H=H, d=d, q_col=0, k_col=1, v_col=2, scale=0.125, pe_k=pe,
+                                   maxpos=maxpos, key_pad=key_pad, causal=case == "self_causal")
+        q, k, v = [t.reshape(B, Tq, H, 64).transpose(1, 2) for t in qkv.detach().double().split(d, dim=-1)]
+    else:
+        qb = (torch.randn(B, Tq, d, device=cuda) * 0.7).to(dtype).requires_grad_()
+        kvb = (torch.randn(B, Tk, 2 * d, device=cuda) * 0.7).to(dtype).requires_grad_()
+        out, probs = ops.attention(qb, kvb, H=H, d=d, q_col=0, k_col=0, v_col=1, scale=0.125, key_pad=key_pad,
+                                   return_probs=True)
+        q = qb.detach().double().reshape(B, Tq, H, 64).transpose(1, 2)
+        k, v = [t.reshape(B, Tk, H, 64).transpose(1, 2) for t in kvb.detach().double().split(d, dim=-1)]
+    q, k, v = q.requires_grad_(), k.requires_grad_(), v.requires_grad_()
+    per = pe.detach().double().requires_grad_() if pe is not None else None
+    o_ref, p_ref = _ref_attention(q, k, v, per, maxpos, key_pad, case == "self_causal", 0.125)
+    g = torch.randn(B, Tq, d, device=cuda)
+    gp = torch.randn(B, H, Tq, Tk, device=cuda) if case == "cross_probs" else None
+    loss = (out.float() * g).sum() + ((probs.float() * gp).sum() if gp is not None else 0)
+    loss.backward()
+    lr = (o_ref.transpose(1, 2).reshape(B, Tq, d) * g.double()).sum() + ((p_ref * gp.double()).sum() if gp is not None else 0)
+    lr.backward()
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert rel(out, o_ref.transpose(1, 2).reshape(B, Tq, d)) < tol
+    assert rel(probs, p_ref) < tol
+
+    def flat(t):
+        return t.transpose(1, 2).reshape(B, -1, d)
+    if case.startswith("self"):
+        gref = torch.cat([flat(q.grad), flat(k.grad), flat(v.grad)], -1)
+        assert rel(qkv.grad, gref) < tol
+        if pe is not None:
+            assert rel(pe.grad, per.grad) < tol
+    else:
+        assert rel(qb.grad, flat(q.grad)) < tol
+        assert rel(kvb.grad, torch.cat([flat(k.grad), flat(v.grad)], -1)) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_posenc_embedding(cuda, dtype):
+    from speecht5_b200 import ops
+    from speecht5_b200.models.modules.nets import sinusoid_table
+    ops.RT.dtype = dtype
+    torch.manual_seed(0)
+    V, C, B, T = 81, 768, 3, 23
+    emb = torch.nn.Parameter(torch.randn(V, C, device=cuda))
+    alpha = torch.nn.Parameter(torch.tensor(1.3, device=cuda))
+    tok = torch.randint(0, V, (B, T), device=cuda)
+    tok[1, -4:] = 1
+    pe = sinusoid_table(64, C, cuda)
+    y = ops.scaled_posenc(pe, alpha, 0.0, tokens=tok, emb=emb, padding_idx=1)
+    g = torch.randn(B, T, C, device=cuda)
+    (y.float() * g).sum().backward()
+    er, ar = emb.detach().double().requires_grad_(), alpha.detach().double().requires_grad_()
+    yr = F.embedding(tok, er, padding_idx=1) + ar * pe[:T].double()
+    (yr * g.double()).sum().backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(y, yr) < tol and rel(emb.grad, er.grad) < tol
+    # d(alpha) is a sum of B*T*C random-sign terms: compare on the scale of that random walk
+    scale = (g.double() * pe[:T].double()).norm().item()
+    assert abs(alpha.grad.item() - ar.grad.item()) < (1e-5 if dtype == torch.float32 else 2 ** -8) * scale
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_postnet_conv_bn(cuda, dtype):
+    from speecht5_b200 import ops
+    ops.RT.dtype = dtype
+    torch.manual_seed(0)
+    B, T, Cin, Cout = 3, 50, 80, 256
+    conv = torch.nn.Conv1d(Cin, Cout, 5, padding=2, bias=False).to(cuda)
+    bn = torch.nn.BatchNorm1d(Cout).to(cuda)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(B, T, Cin, device=cuda).to(dtype).requires_grad_()
+    c = ops.conv1d_k5(x, conv.weight)
+    y = ops.batch_norm_act(c, bn, training=True, act="tanh")
+    g = torch.randn(B, T, Cout, device=cuda)
+    (y.float() * g).sum().backward()
+    convr = torch.nn.Conv1d(Cin, Cout, 5, padding=2, bias=False).to(cuda).double()
+    bnr = torch.nn.BatchNorm1d(Cout).to(cuda).double()
+    convr.load_state_dict(conv.state_dict())
+    bnr.weight.data.copy_(bn.weight.data); bnr.bias.data.copy_(bn.bias.data)
+    xr = x.detach().double().requires_grad_()
+    yr = torch.tanh(bnr(convr(xr.transpose(1, 2)))).transpose(1, 2)
+    (yr * g.double()).sum().backward()
+    tol = 3e-5 if dtype == torch.float32 else 3e-2
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol
+    assert rel(conv.weight.grad, convr.weight.grad) < tol
+    assert rel(bn.weight.grad, bnr.weight.grad) < tol and rel(bn.bias.grad, bnr.bias.grad) < tol
+    stol = 1e-3 if dtype == torch.float32 else 2e-2
+    assert rel(bn.running_mean, bnr.running_mean) < stol and rel(bn.running_var, bnr.running_var) < stol
+
+
+def test_dropout_statistics_and_backward_mask(cuda):
+    from speecht5_b200 import ops
+    x = torch.ones(1 << 20, device=cuda, requires_grad=True)
+    y = ops.dropout(x, 0.3)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.7) < 5e-3
+    assert abs(y.max().item() - 1 / 0.7) < 1e-5
+    y.sum().backward()
+    assert torch.equal(x.grad != 0, y != 0)
+
+
+def test_adam_and_gradnorm(cuda):
+    from speecht5_b200 import kernels as K
+    torch.manual_seed(0)
+    n = 100003
+    p = torch.randn(n, device=cuda); g = torch.randn(n, device=cuda) * 3
+    m = torch.zeros(n, device=cuda); v = torch.zeros(n, device=cuda)
+    pb = torch.empty(n, device=cuda, dtype=torch.bfloat16)
+    nsq = torch.zeros(1, device=cuda)
+    K.sumsq(g, nsq)
+    assert abs(nsq.item() - (g.double() ** 2).sum().item()) / nsq.item() < 1e-5
+    pr, mr, vr = p.double().clone(), m.double().clone(), v.double().clone()
+    lr, b1, b2, eps, max_norm = 1e-3, 0.9, 0.98, 1e-8, 25.0
+    for step in (1, 2, 3):
+        K.adam_step(p, g, m, v, pb, lr, b1, b2, eps, 0.0, step, nsq, max_norm, 0.5)
+        gn = math.sqrt((g.double() ** 2).sum().item()) * 0.5
+        gg = g.double() * 0.5 * min(1.0, max_norm / (gn + 1e-6))
+        mr = b1 * mr + (1 - b1) * gg
+        vr = b2 * vr + (1 - b2) * gg * gg
+        pr = pr - lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step) * mr / (vr.sqrt() + eps)
+    assert rel(p, pr) < 1e-5
+    assert rel(pb.float(), pr) < 5e-3

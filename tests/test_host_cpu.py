@@ -1,0 +1,102 @@
+"""CPU: host-side mirror of the reference plugin surface (registry names, signatures, checkpoint keys, arch presets),
+the synthetic collater contract, and the data-parallel gradient exchange over gloo (world_size 2)."""
+import inspect
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_registry_names_and_forward_signature():
+    import speecht5_b200  # noqa: F401
+    from speecht5_b200 import fairseq_shim as fs
+    from speecht5_b200.models.speecht5 import T5TransformerModel
+    if not fs.HAVE_FAIRSEQ:
+        assert fs.MODEL_REGISTRY["t5_transformer"] is T5TransformerModel
+        for arch in ("t5_transformer", "t5_transformer_base", "t5_transformer_large", "t5_transformer_base_asr"):
+            assert arch in fs.ARCH_CONFIG_REGISTRY
+        assert "speecht5" in fs.TASK_REGISTRY and "speecht5" in fs.CRITERION_REGISTRY
+    sig = list(inspect.signature(T5TransformerModel.forward).parameters)
+    assert sig == ["self", "source", "src_tokens", "src_lengths", "prev_output_tokens", "tgt_lengths", "spkembs",
+                   "target_list", "task_name", "padding_mask", "only_hubert", "only_ctc", "feature_only",
+                   "tgt_enc_layer", "mask"]  # models/speecht5.py:786
+
+
+def test_arch_presets_match_reference_defaults():
+    from speecht5_b200.models import make_args
+    a = make_args("t5_transformer_base_asr")
+    assert (a.encoder_layers, a.decoder_layers, a.encoder_embed_dim, a.encoder_attention_heads) == (12, 6, 768, 12)
+    assert a.relative_position_embedding and a.encoder_max_relative_position == 160 and a.reduction_factor == 2
+    assert (a.dropout, a.activation_dropout, a.attention_dropout, a.encoder_layerdrop) == (0.1, 0.1, 0.1, 0.1)
+    lg = make_args("t5_transformer_large")
+    assert (lg.encoder_layers, lg.decoder_layers, lg.encoder_embed_dim, lg.encoder_attention_heads) == (24, 6, 1024, 16)
+    assert lg.layer_norm_first and lg.decoder_normalize_before
+
+
+def test_state_dict_keys_equal_oracle_and_reference_names():
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args
+    from speecht5_b200.models import T5TransformerModel, make_args
+    m = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", encoder_layers=1, decoder_layers=1))
+    o = T5TransformerModelOracle(base_args(encoder_layers=1, decoder_layers=1))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in o.state_dict().items()}
+    for key in ("encoder.layers.0.self_attn.q_proj.weight", "encoder.pos_emb.pe_k.weight",
+                "speech_decoder_postnet.postnet.postnet.0.1.running_mean",
+                "speech_decoder_prenet.decoder_prenet.0.0.prenet.1.0.bias",
+                "text_encoder_prenet.encoder_prenet.1.alpha", "decoder.layers.0.encoder_attn.k_proj.weight"):
+        assert key in m.state_dict()  # SURVEY.md section 5 checkpoint-key contract
+
+
+def test_unbuilt_branches_fail_loudly_not_silently():
+    from speecht5_b200.models import T5TransformerModel, make_args
+    m = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", encoder_layers=1, decoder_layers=1))
+    with pytest.raises(NotImplementedError):
+        m(source=torch.zeros(1, 1600), padding_mask=torch.zeros(1, 1600, dtype=torch.bool),
+          prev_output_tokens=torch.zeros(1, 3, dtype=torch.long), task_name="s2t")
+
+
+def test_synthetic_batch_follows_collater_contract():
+    from speecht5_b200.data import synthetic_tts_batch
+    s = synthetic_tts_batch(4, 160, 626, seed=3)
+    ni = s["net_input"]
+    assert set(ni) == {"src_tokens", "src_lengths", "prev_output_tokens", "tgt_lengths", "spkembs", "task_name"}
+    assert ni["prev_output_tokens"].shape == (4, 313, 80) and (ni["prev_output_tokens"][:, 0] == 0).all()
+    assert torch.equal(ni["prev_output_tokens"][:, 1:], s["dec_target"][:, 1::2][:, :-1])
+    for b in range(4):
+        L = int(s["dec_target_lengths"][b])
+        assert s["labels"][b, L - 1:].min() == 1 and s["labels"][b, :L - 1].max() == 0
+        assert (ni["src_tokens"][b, int(ni["src_lengths"][b]):] == 1).all()
+    from oracle.speecht5_oracle import synthetic_tts_batch as oracle_batch
+    o = oracle_batch(4, 160, 626, seed=3)
+    assert torch.equal(o["net_input"]["src_tokens"], ni["src_tokens"]) and torch.equal(o["labels"], s["labels"])
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from speecht5_b200.trainer import GradBucketer
+    torch.manual_seed(rank)
+    flat = torch.randn(1000)
+    mine = flat.clone()
+    GradBucketer(flat, bucket_elems=256).all_reduce_mean()
+    gathered = [torch.zeros(1000) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    ref = torch.stack(gathered).mean(0)
+    q.put((rank, float((flat - ref).abs().max())))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_is_mean_over_ranks_gloo():
+    """legacy_distributed_data_parallel.py:76-165 semantics: grads /= world, all-reduce(sum); bucketed, world_size 2."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29511 + os.getpid() % 500
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(err < 1e-6 for _, err in res), res

@@ -1,0 +1,127 @@
+"""-m gpu: end-to-end parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixture."""
+import os
+
+import pytest
+import torch
+
+from helpers import NO_DROPOUT, TINY, load_golden, rel, to_device
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz")
+MEL_TOL = 1e-3  # BASELINE.json north_star: mel L2 within 1e-3 relative
+
+
+def _build(dev, dtype, **over):
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = dtype
+    RT.manual_seed(1)
+    RT.invalidate_shadows()
+    args = make_args("t5_transformer_base_asr", **over)
+    return T5TransformerModel.build_model(args).to(dev)
+
+
+def _criterion():
+    from speecht5_b200.criterions import TexttoSpeechLoss
+    return TexttoSpeechLoss(None, use_guided_attn_loss=True)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 6e-2)])
+def test_golden_fixture_forward_backward(cuda, dtype, tol):
+    state, sample, out_ref, loss_ref, grads_ref = load_golden(GOLDEN)
+    model = _build(cuda, dtype, **TINY, **NO_DROPOUT, bert_init=True).train()
+    model.load_state_dict(state)
+    s = to_device(sample, cuda)
+    crit = _criterion()
+    before, after, logits, attn = model(**s["net_input"])
+    assert before.shape == out_ref["before"].shape and len(attn) == 2
+    assert rel(after, out_ref["after"]) < tol
+    assert rel(before, out_ref["before"]) < tol
+    assert rel(logits, out_ref["logits"]) < tol * 3
+    assert rel(torch.stack(attn), out_ref["attn"]) < tol * 3
+    loss, l1, l2, bce, ga = crit.compute_loss(model, (before, after, logits, attn), s)
+    got = torch.stack([loss, l1, l2, bce, ga]).detach().cpu().double()
+    assert ((got - loss_ref).abs() / loss_ref.abs()).max().item() < tol * 3
+    loss.backward()
+    params = dict(model.named_parameters())
+    gtol = 2e-3 if dtype == torch.float32 else 0.25
+    for name, g in grads_ref.items():
+        assert params[name].grad is not None, name
+        assert rel(params[name].grad, g) < gtol, name
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 6e-2)])
+def test_base_dims_against_oracle(cuda, dtype, tol):
+    """SpeechT5-Base widths (d=768, 12 heads, ffn 3072, RPE +-160), 2+2 layers, ragged batch, training-mode BN."""
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args, synthetic_tts_batch, tts_loss
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, **NO_DROPOUT)
+    torch.manual_seed(7)
+    oracle = T5TransformerModelOracle(base_args(**over)).train()
+    with torch.no_grad():
+        for n, p in oracle.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(0.9)
+            elif "q_proj.weight" in n or "k_proj.weight" in n or "pe_k" in n:
+                p.mul_(6.0)  # peaky attention => well-conditioned softmax gradients for an fp32-vs-fp32 comparison
+    sample = synthetic_tts_batch(3, 45, 64, seed=3)
+    state0 = {k: v.clone() for k, v in oracle.state_dict().items()}  # before the oracle's own BN statistics update
+    out_ref = oracle(**sample["net_input"])
+    loss_ref = tts_loss(out_ref, sample)[0]
+    loss_ref.backward()
+    model = _build(cuda, dtype, **over).train()
+    model.load_state_dict(state0)
+    s = to_device(sample, cuda)
+    before, after, logits, attn = model(**s["net_input"])
+    assert rel(after, out_ref[1]) < tol, "mel (after postnet) L2"
+    assert rel(before, out_ref[0]) < tol
+    loss = _criterion().compute_loss(model, (before, after, logits, attn), s)[0]
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < tol * 3
+    loss.backward()
+    ref_grads = dict(oracle.named_parameters())
+    gmax = max(float(p.grad.norm()) for p in oracle.parameters() if p.grad is not None)
+    worst, worst_name = 0.0, None
+    for n, p in model.named_parameters():
+        g_ref = ref_grads[n].grad
+        if g_ref is None:
+            continue
+        assert p.grad is not None, n
+        if float(g_ref.norm()) < 1e-4 * gmax:  # analytically-zero gradients (e.g. k_proj.bias): only roundoff noise
+            assert float(p.grad.float().norm()) < 2e-3 * gmax, n
+            continue
+        e = rel(p.grad, g_ref)
+        if e > worst:
+            worst, worst_name = e, n
+    assert worst < (5e-3 if dtype == torch.float32 else 0.25), (worst, worst_name)
+    # BatchNorm running statistics follow the reference (local batch statistics, padded frames included)
+    bn = "speech_decoder_postnet.postnet.postnet.0.1.running_var"
+    assert rel(model.state_dict()[bn], oracle.state_dict()[bn]) < 1e-2
+
+
+def test_eval_mode_matches_oracle(cuda):
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args, synthetic_tts_batch
+    over = dict(encoder_layers=1, decoder_layers=1, dprenet_dropout_rate=0.0)
+    torch.manual_seed(3)
+    oracle = T5TransformerModelOracle(base_args(**over)).eval()
+    sample = synthetic_tts_batch(2, 30, 40, seed=5)
+    with torch.no_grad():
+        ref = oracle(**sample["net_input"])
+    model = _build(cuda, torch.float32, **over).eval()
+    model.load_state_dict(oracle.state_dict())
+    with torch.no_grad():
+        got = model(**to_device(sample, cuda)["net_input"])
+    assert rel(got[1], ref[1]) < MEL_TOL
+
+
+def test_dropout_training_step_runs_and_is_reproducible(cuda):
+    from oracle.speecht5_oracle import synthetic_tts_batch
+    over = dict(encoder_layers=1, decoder_layers=2, encoder_layerdrop=0.0, decoder_layerdrop=0.0)
+    sample = to_device(synthetic_tts_batch(2, 30, 40, seed=5), cuda)
+    losses = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        model = _build(cuda, torch.bfloat16, **over).train()
+        loss = _criterion().compute_loss(model, model(**sample["net_input"]), sample)[0]
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+        losses.append(loss.item())
+    assert losses[0] == losses[1]
