@@ -126,6 +126,7 @@ class B200Trainer:
         self.model, self.criterion, self.task = model, criterion, task
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.device = next(model.parameters()).device
+        self.criterion.to(self.device)  # criterion buffers (BCE pos_weight) must live on the device for capture
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.fp = FlatParams(model)
         self.bucketer = GradBucketer(self.fp.grads, bucket_elems=bucket_mb * 1024 * 1024 // 4, group=process_group)
