@@ -177,6 +177,28 @@ def attn_bwd(a):
     _count(3)
 
 
+def attn_softmax_fwd(s, qp, key_pad, p, probs_f32, pdrop, B, H, Tq, Tk, p_ld, causal, maxpos, drop_p, seed, offset):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_softmax_fwd(_ptr(s), _ptr(qp), qp.shape[-1] if qp is not None else 0, _ptr(key_pad),
+                                        _ptr(p), _ptr(probs_f32), _ptr(pdrop), B, H, Tq, Tk, p_ld, int(causal), maxpos,
+                                        drop_p, seed, offset, _stream()), "st5_attn_softmax_fwd")
+    _count(1)
+
+
+def attn_ds(p, dp, dp_ext, ds, pdrop, B, H, Tq, Tk, p_ld, drop_p, seed, offset):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_ds(_ptr(p), _ptr(dp), _ptr(dp_ext), _ptr(ds), _ptr(pdrop), B, H, Tq, Tk, p_ld, drop_p, seed,
+                               offset, _stream()), "st5_attn_ds")
+    _count(1)
+
+
+def attn_dqp_scatter(ds, dqp, B, H, Tq, Tk, p_ld, maxpos):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_dqp_scatter(_ptr(ds), _ptr(dqp), B, H, Tq, Tk, p_ld, maxpos, _stream()),
+               "st5_attn_dqp_scatter")
+    _count(1)
+
+
 def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd, y, y_ld, y_pre, rows, Cc, training,
            momentum, eps, act, drop_p, seed, offset, scratch):
     lib = _lib.load()

@@ -24,6 +24,7 @@ class Runtime:
         self.param_epoch = 0
         self._shadows = {}
         self._static = {}
+        self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
 
     @property
     def seed(self):
@@ -405,10 +406,123 @@ class AttentionFn(torch.autograd.Function):
         return dq_buf, (None if same else dkv_buf), dpe, None, None
 
 
+class AttentionTCFn(torch.autograd.Function):
+    """bf16 tensor-core attention: every contraction (QK^T, Q.PE^T, PV and the five backward products) is a batched
+    launch of the tcgen05 GEMM over (head, utterance) reading q/k/v in place from the fused projection buffers; the
+    softmax / dS / relative-position scatter steps are the row kernels of csrc/attention_tc.cu. Same interface and
+    dropout-mask convention as AttentionFn (the exact fp32 row-kernel path used for parity mode)."""
+
+    @staticmethod
+    def _views(q_buf, kvb, cfg):
+        d = cfg["d"]
+        return (q_buf.narrow(2, cfg["q_col"] * d, d), kvb.narrow(2, cfg["k_col"] * d, d),
+                kvb.narrow(2, cfg["v_col"] * d, d))
+
+    @staticmethod
+    def forward(ctx, q_buf, kv_buf, pe_k, key_pad, cfg):
+        ctx.set_materialize_grads(False)
+        same = kv_buf is None
+        kvb = q_buf if same else kv_buf
+        B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
+        H, d, scale = cfg["H"], cfg["d"], cfg["scale"]
+        dev = q_buf.device
+        p_ld = _pad8(Tk)
+        qv, kk, vv = AttentionTCFn._views(q_buf, kvb, cfg)
+        q_ld, q_bs, kv_ld, kv_bs = q_buf.stride(1), q_buf.stride(0), kvb.stride(1), kvb.stride(0)
+        pbs = (Tq * p_ld, H * Tq * p_ld)
+        S = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+        K.gemm(qv, kk, S, M=Tq, N=Tk, K=64, a_ld=q_ld, b_ld=kv_ld, c_ld=p_ld, nb1=H, nb2=B, a_bs=(64, q_bs),
+               b_bs=(64, kv_bs), c_bs=pbs, alpha=scale)
+        QP, pe_hi, R = None, None, 0
+        if pe_k is not None:
+            R = pe_k.shape[0]
+            pe_hi = RT.shadow(("pe", id(pe_k)), lambda: pe_k)[0]
+            QP = torch.empty((B, H, Tq, R), dtype=torch.float32, device=dev)
+            K.gemm(qv, pe_hi, QP, M=Tq, N=R, K=64, a_ld=q_ld, b_ld=64, c_ld=R, nb1=H, nb2=B, a_bs=(64, q_bs),
+                   b_bs=(0, 0), c_bs=(Tq * R, H * Tq * R), alpha=scale)
+        drop_p = cfg.get("drop_p", 0.0)
+        off = RT.next_offset() if drop_p > 0 else 0
+        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        P = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
+        Pd = torch.empty_like(P) if drop_p > 0 else None
+        want = bool(cfg.get("return_probs"))
+        K.attn_softmax_fwd(S, QP, kp, P, S if want else None, Pd, B, H, Tq, Tk, p_ld, cfg.get("causal", False),
+                           cfg.get("maxpos", 0), drop_p, RT.seed, off)
+        out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
+        K.gemm(Pd if Pd is not None else P, vv, out, M=Tq, N=64, K=Tk, a_ld=p_ld, b_mn=True, b_ld=kv_ld, c_ld=d,
+               nb1=H, nb2=B, a_bs=pbs, b_bs=(64, kv_bs), c_bs=(64, Tq * d))
+        ctx.save_for_backward(q_buf, kv_buf, pe_k, P)
+        ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
+        probs = S if want else P
+        return out, probs[..., :Tk] if p_ld != Tk else probs
+
+    @staticmethod
+    def backward(ctx, dout, dprobs):
+        q_buf, kv_buf, pe_k, P = ctx.saved_tensors
+        cfg, off, seed, p_ld, same, pe_hi = ctx.meta
+        kvb = q_buf if same else kv_buf
+        B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
+        H, d, scale = cfg["H"], cfg["d"], cfg["scale"]
+        dev = q_buf.device
+        drop_p = cfg.get("drop_p", 0.0)
+        if dout is None:
+            dout = torch.zeros((B, Tq, d), dtype=torch.bfloat16, device=dev)
+        dout = dout.contiguous()
+        qv, kk, vv = AttentionTCFn._views(q_buf, kvb, cfg)
+        q_ld, q_bs, kv_ld, kv_bs = q_buf.stride(1), q_buf.stride(0), kvb.stride(1), kvb.stride(0)
+        pbs = (Tq * p_ld, H * Tq * p_ld)
+        full = q_buf.shape[2] == (3 * d if same else d)
+        dq_buf = torch.empty_like(q_buf) if full else torch.zeros_like(q_buf)
+        dkv_buf = dq_buf if same else torch.empty_like(kv_buf)
+        dqv, dkk, dvv = AttentionTCFn._views(dq_buf, dkv_buf, cfg)
+        # dP = dO V^T
+        dP = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+        K.gemm(dout, vv, dP, M=Tq, N=Tk, K=64, a_ld=d, b_ld=kv_ld, c_ld=p_ld, nb1=H, nb2=B, a_bs=(64, Tq * d),
+               b_bs=(64, kv_bs), c_bs=pbs)
+        dpx = None
+        if dprobs is not None:
+            dpx = dprobs
+            if dpx.dtype != torch.float32 or dpx.shape[-1] != p_ld or not dpx.is_contiguous():
+                buf = torch.zeros((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+                buf[..., :Tk] = dprobs
+                dpx = buf
+        dS = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
+        Pd = torch.empty_like(P) if drop_p > 0 else None
+        K.attn_ds(P, dP, dpx, dS, Pd, B, H, Tq, Tk, p_ld, drop_p, seed, off)
+        if Pd is None:
+            Pd = P
+        # dV[j,c] = sum_i Pd[i,j] dO[i,c]   (both operands MN-major: no transposes)
+        K.gemm(Pd, dout, dvv, M=Tk, N=64, K=Tq, a_mn=True, a_ld=p_ld, b_mn=True, b_ld=d, c_ld=kv_ld, nb1=H, nb2=B,
+               a_bs=pbs, b_bs=(64, Tq * d), c_bs=(64, kv_bs))
+        # dQ = scale dS K ; dK = scale dS^T Q
+        K.gemm(dS, kk, dqv, M=Tq, N=64, K=Tk, a_ld=p_ld, b_mn=True, b_ld=kv_ld, c_ld=q_ld, nb1=H, nb2=B, a_bs=pbs,
+               b_bs=(64, kv_bs), c_bs=(64, q_bs), alpha=scale)
+        K.gemm(dS, qv, dkk, M=Tk, N=64, K=Tq, a_mn=True, a_ld=p_ld, b_mn=True, b_ld=q_ld, c_ld=kv_ld, nb1=H, nb2=B,
+               a_bs=pbs, b_bs=(64, q_bs), c_bs=(64, kv_bs), alpha=scale)
+        dpe = None
+        if pe_k is not None:
+            R = pe_k.shape[0]
+            dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
+            K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, cfg.get("maxpos", 0))
+            qpbs = (Tq * R, H * Tq * R)
+            # dQ += scale dQP PE
+            K.gemm(dQP, pe_hi, dqv, M=Tq, N=64, K=R, a_ld=R, b_mn=True, b_ld=64, c_ld=q_ld, nb1=H, nb2=B, a_bs=qpbs,
+                   b_bs=(0, 0), c_bs=(64, q_bs), alpha=scale, residual=dqv)
+            # dPE[r,c] = scale sum_{b,h,i} dQP[b,h,i,r] q[b,i,h,c]
+            parts = torch.empty((B, H, R, 64), dtype=torch.float32, device=dev)
+            K.gemm(dQP, qv, parts, M=R, N=64, K=Tq, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=B,
+                   a_bs=qpbs, b_bs=(64, q_bs), c_bs=(R * 64, H * R * 64), alpha=scale)
+            dpe = parts.sum(dim=(0, 1))
+        return dq_buf, (None if same else dkv_buf), dpe, None, None
+
+
 def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, maxpos=0, key_pad=None, causal=False,
               drop_p=0.0, return_probs=False):
     cfg = dict(H=H, d=d, q_col=q_col, k_col=k_col, v_col=v_col, scale=scale, maxpos=maxpos, causal=causal,
                drop_p=drop_p, return_probs=return_probs)
+    Tk = (q_buf if kv_buf is None else kv_buf).shape[1]
+    if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and Tk <= 512:
+        return AttentionTCFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
     return AttentionFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
 
 

@@ -233,3 +233,41 @@ def test_adam_and_gradnorm(cuda):
         pr = pr - lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step) * mr / (vr.sqrt() + eps)
     assert rel(p, pr) < 1e-5
     assert rel(pb.float(), pr) < 5e-3
+
+
+@pytest.mark.parametrize("case", ["self_rpe", "cross"])
+def test_tensor_core_attention_matches_row_kernels_with_dropout(cuda, case):
+    """Same (seed, offset) => same Philox dropout mask in both implementations; outputs and gradients must agree."""
+    from speecht5_b200 import ops
+    ops.RT.dtype = torch.bfloat16
+    torch.manual_seed(0)
+    B, H, Tq = 2, 4, 150
+    d = H * 64
+    Tk = Tq if case == "self_rpe" else 70
+    lens = torch.tensor([Tk, Tk - 9], device=cuda)
+    key_pad = torch.arange(Tk, device=cuda)[None, :] >= lens[:, None]
+    pe = torch.nn.Parameter(torch.randn(320, 64, device=cuda) * 0.3) if case == "self_rpe" else None
+    base_q = (torch.randn(B, Tq, (3 if case == "self_rpe" else 1) * d, device=cuda) * 0.7).to(torch.bfloat16)
+    base_kv = (torch.randn(B, Tk, 2 * d, device=cuda) * 0.7).to(torch.bfloat16)
+    g = torch.randn(B, Tq, d, device=cuda).to(torch.bfloat16)
+    res = []
+    for tc in (True, False):
+        ops.RT.attn_tensor_core = tc
+        ops.RT.manual_seed(5)
+        qb = base_q.clone().requires_grad_()
+        kvb = base_kv.clone().requires_grad_() if case == "cross" else None
+        if pe is not None:
+            pe.grad = None
+        if case == "self_rpe":
+            out, _ = ops.attention(qb, None, H=H, d=d, q_col=0, k_col=1, v_col=2, scale=0.125, pe_k=pe, maxpos=160,
+                                   key_pad=key_pad, drop_p=0.2)
+        else:
+            out, _ = ops.attention(qb, kvb, H=H, d=d, q_col=0, k_col=0, v_col=1, scale=0.125, key_pad=key_pad,
+                                   drop_p=0.2, return_probs=True)
+        out.backward(g)
+        res.append((out.detach(), qb.grad, kvb.grad if kvb is not None else None,
+                    pe.grad.clone() if pe is not None else None))
+    ops.RT.attn_tensor_core = True
+    for a, b in zip(res[0], res[1]):
+        if a is not None:
+            assert rel(a, b) < 3e-2
