@@ -62,6 +62,8 @@ typedef struct st5_gemm_args {
   float alpha;
   float drop_p;
   uint64_t drop_seed, drop_offset;
+  const void* actgrad_pre;   /* optional: result *= act'(actgrad_pre[m][n]) (type actgrad_act), applied after the */
+  int32_t actgrad_act;       /* dropout mask: fuses the activation backward into the dX GEMM of the next layer   */
 } st5_gemm_args;
 int st5_gemm_bf16(const st5_gemm_args* args, void* stream);
 

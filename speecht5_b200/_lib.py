@@ -23,6 +23,7 @@ class GemmArgs(C.Structure):
         ("c", C.c_void_p), ("c_ld", C.c_int64), ("c_bs1", C.c_int64), ("c_bs2", C.c_int64),
         ("c_pre", C.c_void_p), ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p),
         ("alpha", C.c_float), ("drop_p", C.c_float), ("drop_seed", C.c_uint64), ("drop_offset", C.c_uint64),
+        ("actgrad_pre", C.c_void_p), ("actgrad_act", C.c_int32),
     ]
 
 

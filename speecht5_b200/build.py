@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libspeecht5_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "norm.cu", "attention.cu", "attention_tc.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "norm.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "optim.cu"]
 HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", os.path.join("..", "..", "include", "speecht5_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -49,6 +49,7 @@ int st5_gemm_bf16(const st5_gemm_args* a, void* stream) {
   g.C_pre = a->c_pre; g.bias = a->bias; g.bias2 = a->bias2; g.bias2_rows = a->bias2_rows;
   g.residual = a->residual; g.act = a->act; g.alpha = a->alpha; g.accumulate = a->accumulate;
   g.drop_p = a->drop_p; g.drop_seed = a->drop_seed; g.drop_offset = a->drop_offset;
+  g.ag_pre = a->actgrad_pre; g.ag_act = a->actgrad_act;
   return set_error(gemm_launch(g, (cudaStream_t)stream), "st5_gemm_bf16");
 }
 

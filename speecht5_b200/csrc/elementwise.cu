@@ -137,19 +137,6 @@ int dropout_launch(const void* x, void* y, int dtype, int64_t n, float drop_p, u
 }
 
 // ------------------------------------------------------------------ activation backward (with dropout backward)
-__device__ __forceinline__ float act_grad(float x, int act) {
-  if (act == ACT_RELU) return x > 0.f ? 1.f : 0.f;
-  if (act == ACT_GELU) {
-    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    return cdf + x * pdf;
-  }
-  if (act == ACT_TANH) {
-    const float t = tanhf(x);
-    return 1.f - t * t;
-  }
-  return 1.f;
-}
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dpre, int act,
                                int64_t n, uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {

@@ -10,6 +10,7 @@
 // of their backward contractions (MN-major operands avoid explicit transposes).
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "kernels.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -32,6 +33,8 @@ struct EpiParams {
   uint32_t drop_thr; float drop_scale; uint64_t drop_seed, drop_offset;
   int num_k_blocks;
   int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast over that batch dim (stride 0), else 1
+  const void* ag_pre; int ag_act;   // optional: multiply by act'(ag_pre[m][n]) (activation backward fused into dX)
+  int tiles_m, tiles_n, num_tiles;  // persistent schedule: tile = (z * tiles_n + n_blk) * tiles_m + m_blk
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -54,15 +57,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
   uint8_t* smem_b = smem + STAGES * A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
+  // Persistent CTA: loops over output tiles (m fastest, so concurrently running CTAs share the B/weight tile in L2);
+  // two TMEM accumulator stages let the epilogue of tile i overlap the MMA main loop of tile i+1.
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BN;
-  const int z = blockIdx.z;
-  const int b1 = z % p.nb1, b2 = z / p.nb1;
   const int nkb = p.num_k_blocks;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_a);
@@ -71,11 +74,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -88,6 +94,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_mn, rmn = tile - z * tiles_mn;
+      const int m0 = (rmn % p.tiles_m) * BLOCK_M, n0 = (rmn / p.tiles_m) * BN;
+      const int b1 = z % p.nb1, b2 = z / p.nb1;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -110,12 +120,20 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    const int acc = local & 1;
+    const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
+    tc_fence_after();
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
@@ -129,32 +147,46 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
                                    : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
           const uint64_t db = B_MN ? umma_smem_desc(sb + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
                                    : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);              // smem slot reusable once these MMAs retire
-        if (kb == nkb - 1) umma_commit(accum_bar);   // accumulator complete
+        umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
+        if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);    // accumulator complete
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
     const int q = warp & 3;
+    uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
+    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    const int z = tile / tiles_mn, rmn = tile - z * tiles_mn;
+    const int m0 = (rmn % p.tiles_m) * BLOCK_M, n0 = (rmn / p.tiles_m) * BN;
+    const int b1 = z % p.nb1, b2 = z / p.nb1;
+    const int acc = local & 1;
+    const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
     const int row = m0 + q * 32 + (int)lane_id();
-    mbar_wait(accum_bar, 0);
+    mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     const bool row_ok = row < p.M;
     const long zoff = (long)b1 * p.c_bs1 + (long)b2 * p.c_bs2;
     const long roff = zoff + (long)row * p.c_ld;
     const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
     const uint64_t drop_row = ((uint64_t)z * (uint64_t)p.M + (uint64_t)row) * (uint64_t)p.N;
-    uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
-    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
+      if (c == BN / 32 - 1) {  // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+      }
       const int nb = n0 + c * 32;
       if (!row_ok || nb >= p.N) continue;
       float v[32];
@@ -228,6 +260,31 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
           }
         }
       }
+      if (p.ag_pre != nullptr) {
+        if (p.c_fp32) {
+          const float* pr = reinterpret_cast<const float*>(p.ag_pre) + roff + nb;
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) v[j] *= act_grad(pr[j], p.ag_act);
+        } else {
+          const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.ag_pre) + roff + nb;
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(p.ag_pre) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(h[t]);
+                v[j + 2 * t] *= act_grad(f.x, p.ag_act);
+                v[j + 2 * t + 1] *= act_grad(f.y, p.ag_act);
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) v[j] *= act_grad(__bfloat162float(pr[j]), p.ag_act);
+          }
+        }
+      }
       if (p.residual != nullptr) {
         if (p.c_fp32) {
           const float* rs = reinterpret_cast<const float*>(p.residual) + roff + nb;
@@ -269,12 +326,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -294,6 +352,16 @@ static EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(ptr);
   });
   return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 // rows x K operand. K-major: memory [rows][ld] (k contiguous). MN-major: memory [K][ld] (row index contiguous).
@@ -334,7 +402,7 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
   if (rc) return rc;
   rc = make_operand_map(&mb, g.B, g.b_mn, g.N, g.K, g.b_ld, g.nb1, g.b_bs1, g.nb2, g.b_bs2, BN);
   if (rc) return rc - 10;
-  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
   auto kern = gemm_bf16_tcgen05<BN, STAGES, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -342,8 +410,14 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((g.M + BLOCK_M - 1) / BLOCK_M, (g.N + BN - 1) / BN, g.nb1 * g.nb2);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, ep);
+  EpiParams e2 = ep;
+  e2.tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+  e2.tiles_n = (g.N + BN - 1) / BN;
+  const long total = (long)e2.tiles_m * e2.tiles_n * g.nb1 * g.nb2;
+  if (total > 0x7fffffffL) return -4;
+  e2.num_tiles = (int)total;
+  const int grid = (int)(total < num_sms() ? total : num_sms());  // one persistent CTA per SM
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, e2);
   return (int)cudaGetLastError();
 }
 
@@ -365,6 +439,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   ep.M = g.M; ep.N = g.N; ep.nb1 = g.nb1;
   ep.C = g.C; ep.c_fp32 = g.c_fp32; ep.c_ld = g.c_ld; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2;
   ep.C_pre = g.C_pre; ep.bias = g.bias; ep.bias2 = g.bias2; ep.bias2_rows = g.bias2_rows > 0 ? g.bias2_rows : 1;
+  ep.ag_pre = g.ag_pre; ep.ag_act = g.ag_act;
   ep.residual = g.residual; ep.act = g.act; ep.alpha = g.alpha; ep.accumulate = g.accumulate;
   if (g.drop_p > 0.f) {
     double t = (double)g.drop_p * 4294967296.0;
@@ -377,12 +452,22 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   ep.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   ep.a_m1 = (g.nb1 > 1 && g.a_bs1 == 0) ? 0 : 1; ep.a_m2 = (g.nb2 > 1 && g.a_bs2 == 0) ? 0 : 1;
   ep.b_m1 = (g.nb1 > 1 && g.b_bs1 == 0) ? 0 : 1; ep.b_m2 = (g.nb2 > 1 && g.b_bs2 == 0) ? 0 : 1;
-  // Tile choice: wide tiles when N is large enough to keep >= ~1 wave of CTAs, narrow tiles for skinny outputs.
+  // Tile width: minimise (rounds of the persistent grid) x (time per tile). A 128x256 tile reads 12 KB of smem per
+  // 128-cycle MMA (under the 128 B/clk port); 128x128 and 128x64 tiles are smem-port bound, hence the >1 factors.
   const long tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
   const long batch = (long)g.nb1 * g.nb2;
-  if (g.N <= 64) return launch_major<64, 4>(g, ep, stream);
-  if (g.N >= 512 && tiles_m * ((g.N + 255) / 256) * batch >= 148) return launch_major<256, 4>(g, ep, stream);
-  return launch_major<128, 3>(g, ep, stream);
+  const long sms = num_sms();
+  auto cost = [&](int bn, double factor) {
+    const long tiles = tiles_m * ((g.N + bn - 1) / bn) * batch;
+    const long rounds = (tiles + sms - 1) / sms;
+    return (double)rounds * (bn * factor + 24.0);
+  };
+  const double c256 = g.N > 128 ? cost(256, 1.0) : 1e30;
+  const double c128 = g.N > 64 ? cost(128, 1.12) : 1e30;
+  const double c64 = cost(64, 1.35);
+  if (c256 <= c128 && c256 <= c64) return launch_major<256, 4>(g, ep, stream);
+  if (c128 <= c64) return launch_major<128, 6>(g, ep, stream);
+  return launch_major<64, 8>(g, ep, stream);
 }
 
 }  // namespace st5

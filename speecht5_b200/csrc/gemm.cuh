@@ -27,6 +27,7 @@ struct GemmDesc {
   float alpha;
   int accumulate;         // C += result (C must be fp32)
   float drop_p; uint64_t drop_seed, drop_offset;
+  const void* ag_pre; int ag_act;  // optional: out *= act'(ag_pre[m][n]) after the dropout mask (same layout as C)
 };
 
 int gemm_launch(const GemmDesc& g, cudaStream_t stream);

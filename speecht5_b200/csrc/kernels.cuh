@@ -25,6 +25,19 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ float act_grad(float x, int act) {
+  if (act == 1) return x > 0.f ? 1.f : 0.f;
+  if (act == 2) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  }
+  if (act == 3) {
+    const float t = tanhf(x);
+    return 1.f - t * t;
+  }
+  return 1.f;
+}
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
   return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);

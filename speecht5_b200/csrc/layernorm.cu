@@ -1,0 +1,270 @@
+// LayerNorm with fused residual + dropout, forward and backward. HBM-bound: one warp per row, 16-byte vector accesses
+// (8 bf16 / 2x4 fp32 per lane per chunk), fp32 statistics (two-pass variance on registers).
+// Reference semantics: fairseq LayerNorm == torch.nn.LayerNorm (fairseq/modules/layer_norm.py:30-35); post-LN residual
+// tails of transformer_layer.py:112-132 / :343-391 and encoder.py:226-227.
+//   forward : s = residual + dropout(x);  y = (s - mean) * rstd * gamma + beta          (s, mean, rstd saved)
+//   backward: ds = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ;  dx = dropout_bwd(ds)
+//             dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy     (separate column-reduction kernel)
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace st5 {
+
+constexpr int LN_WARPS = 4;
+constexpr int LN_MAX_CHUNKS = 4;  // per lane: C <= 4 * 32 * 8 = 1024
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float* v);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* v) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __bfloat1622float2(h[t]);
+    v[2 * t] = f.x; v[2 * t + 1] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float* v);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// round-trip through the storage type (so forward normalises exactly what backward will re-read)
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16(v));
+}
+
+__device__ __forceinline__ void dropout8(float* v, uint64_t e0, uint32_t thr, float dscale, uint64_t seed,
+                                         uint64_t offset) {
+  // e0 is a multiple of 8 => two aligned Philox groups
+  const Philox4 a = philox4x32(seed, offset, e0 >> 2), b = philox4x32(seed, offset, (e0 >> 2) + 1);
+  v[0] = a.x >= thr ? v[0] * dscale : 0.f; v[1] = a.y >= thr ? v[1] * dscale : 0.f;
+  v[2] = a.z >= thr ? v[2] * dscale : 0.f; v[3] = a.w >= thr ? v[3] * dscale : 0.f;
+  v[4] = b.x >= thr ? v[4] * dscale : 0.f; v[5] = b.y >= thr ? v[5] * dscale : 0.f;
+  v[6] = b.z >= thr ? v[6] * dscale : 0.f; v[7] = b.w >= thr ? v[7] * dscale : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ s_out, float* __restrict__ mean,
+                  float* __restrict__ rstd, int64_t rows, int C, float eps, uint32_t thr, float dscale, uint64_t seed,
+                  uint64_t offset) {
+  if (thr != 0) resolve_seed(seed, offset);
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nchunks = C >> 3;
+  float v[LN_MAX_CHUNKS][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ch = k * 32 + lane;
+    if (ch < nchunks) {
+      const int64_t e0 = row * C + ch * 8;
+      load8<T>(x + e0, v[k]);
+      if (thr != 0) dropout8(v[k], (uint64_t)e0, thr, dscale, seed, offset);
+      if (residual != nullptr) {
+        float r[8];
+        load8<T>(residual + e0, r);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[k][t] += r[t];
+      }
+      if (s_out != nullptr) {
+        store8<T>(s_out + e0, v[k]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[k][t] = round_to<T>(v[k][t]);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sum += v[k][t];
+    }
+  }
+  sum = warp_sum(sum);
+  const float mu = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    if (k * 32 + lane < nchunks) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = v[k][t] - mu;
+        sq += d * d;
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  const float rs = rsqrtf(sq / (float)C + eps);
+  if (lane == 0) {
+    if (mean != nullptr) mean[row] = mu;
+    if (rstd != nullptr) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ch = k * 32 + lane;
+    if (ch < nchunks) {
+      float g[8], b[8], o[8];
+      load8<float>(gamma + ch * 8, g);
+      load8<float>(beta + ch * 8, b);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = (v[k][t] - mu) * rs * g[t] + b[t];
+      store8<T>(y + row * C + ch * 8, o);
+    }
+  }
+}
+
+int ln_fwd_launch(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
+                  float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
+                  uint64_t offset, cudaStream_t s) {
+  if (rows == 0) return 0;
+  if (C > 8 * 32 * LN_MAX_CHUNKS || C <= 0 || (C & 7)) return -2;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  if (dtype == ST5_F32)
+    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y,
+                                                        (float*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed,
+                                                        offset);
+  else
+    ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)s_out,
+        mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
+  return (int)cudaGetLastError();
+}
+
+// number of floats of scratch the caller provides (kept for ABI stability; the reduction now uses fp32 atomics)
+int64_t ln_bwd_blocks(int64_t rows) { (void)rows; return 1; }
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ s_in, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ ds,
+                     T* __restrict__ dx, int64_t rows, int C, uint32_t thr, float dscale, uint64_t seed,
+                     uint64_t offset) {
+  if (thr != 0) resolve_seed(seed, offset);
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nchunks = C >> 3;
+  const float mu = mean[row], rs = rstd[row];
+  float g[LN_MAX_CHUNKS][8], xh[LN_MAX_CHUNKS][8];
+  float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ch = k * 32 + lane;
+    if (ch < nchunks) {
+      const int64_t e0 = row * C + ch * 8;
+      float d[8], sv[8], gm[8];
+      load8<T>(dy + e0, d);
+      load8<T>(s_in + e0, sv);
+      load8<float>(gamma + ch * 8, gm);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        xh[k][t] = (sv[t] - mu) * rs;
+        g[k][t] = d[t] * gm[t];
+        c1 += g[k][t];
+        c2 += g[k][t] * xh[k][t];
+      }
+    }
+  }
+  c1 = warp_sum(c1) / (float)C;
+  c2 = warp_sum(c2) / (float)C;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ch = k * 32 + lane;
+    if (ch < nchunks) {
+      const int64_t e0 = row * C + ch * 8;
+      float r[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) r[t] = rs * (g[k][t] - c1 - xh[k][t] * c2);
+      if (ds != nullptr) store8<T>(ds + e0, r);
+      if (dx != nullptr) {
+        if (thr != 0) dropout8(r, (uint64_t)e0, thr, dscale, seed, offset);
+        store8<T>(dx + e0, r);
+      }
+    }
+  }
+}
+
+// dgamma[c] += sum_r dy[r][c] * xhat[r][c]; dbeta[c] += sum_r dy[r][c].  grid (C/64, row splits), block (32, 8):
+// each lane owns two adjacent columns (4-byte / 8-byte loads), partials combined with fp32 atomics.
+template <typename T> __device__ __forceinline__ float2 load2(const T* p);
+template <> __device__ __forceinline__ float2 load2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+    ln_bwd_param_kernel(const T* __restrict__ dy, const T* __restrict__ s_in, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        int64_t rows, int C, int64_t rows_per_block) {
+  const int c = blockIdx.x * 64 + threadIdx.x * 2;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float ga = 0.f, gb = 0.f, ba = 0.f, bb = 0.f;
+  if (c < C) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float mu = mean[r], rs = rstd[r];
+      const float2 d = load2<T>(dy + r * C + c), sv = load2<T>(s_in + r * C + c);
+      ga += d.x * (sv.x - mu) * rs; gb += d.y * (sv.y - mu) * rs;
+      ba += d.x; bb += d.y;
+    }
+  }
+  __shared__ float red[4][8][33];
+  red[0][threadIdx.y][threadIdx.x] = ga; red[1][threadIdx.y][threadIdx.x] = gb;
+  red[2][threadIdx.y][threadIdx.x] = ba; red[3][threadIdx.y][threadIdx.x] = bb;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s0 += red[0][k][threadIdx.x]; s1 += red[1][k][threadIdx.x];
+      s2 += red[2][k][threadIdx.x]; s3 += red[3][k][threadIdx.x];
+    }
+    if (dgamma != nullptr) { atomicAdd(dgamma + c, s0); atomicAdd(dgamma + c + 1, s1); }
+    if (dbeta != nullptr) { atomicAdd(dbeta + c, s2); atomicAdd(dbeta + c + 1, s3); }
+  }
+}
+
+int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
+                  void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
+                  float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  (void)partials;
+  if (rows == 0) return 0;
+  if (C > 8 * 32 * LN_MAX_CHUNKS || C <= 0 || (C & 7)) return -2;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float dsc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  int64_t splits = (rows + 255) / 256;
+  if (splits > 96) splits = 96;
+  const int64_t rpb = (rows + splits - 1) / splits;
+  dim3 pgrid((unsigned)((C + 63) / 64), (unsigned)splits), pblock(32, 8);
+  if (dtype == ST5_F32) {
+    ln_bwd_dx_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)dy, (const float*)s_in, mean, rstd, gamma,
+                                                           (float*)ds, (float*)dx, rows, (int)C, thr, dsc, seed, offset);
+    if (dgamma != nullptr || dbeta != nullptr)
+      ln_bwd_param_kernel<float><<<pgrid, pblock, 0, s>>>((const float*)dy, (const float*)s_in, mean, rstd, dgamma,
+                                                          dbeta, rows, (int)C, rpb);
+  } else {
+    ln_bwd_dx_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)s_in, mean, rstd, gamma, (__nv_bfloat16*)ds, (__nv_bfloat16*)dx,
+        rows, (int)C, thr, dsc, seed, offset);
+    if (dgamma != nullptr || dbeta != nullptr)
+      ln_bwd_param_kernel<__nv_bfloat16><<<pgrid, pblock, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)s_in,
+                                                                  mean, rstd, dgamma, dbeta, rows, (int)C, rpb);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace st5

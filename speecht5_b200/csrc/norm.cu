@@ -1,4 +1,4 @@
-// LayerNorm (fused residual + dropout) and BatchNorm1d (fused tanh + dropout) forward/backward.
+// BatchNorm1d (fused tanh + dropout) forward/backward (LayerNorm lives in layernorm.cu).
 // Reference semantics: fairseq LayerNorm == torch.nn.LayerNorm (fairseq/modules/layer_norm.py:30-35), post-LN residual
 // blocks of transformer_layer.py:112-132 / :343-391; espnet Tacotron2 Postnet BatchNorm1d blocks
 // (speech_decoder_postnet.py:39-51) with training statistics over every row, padded frames included.
@@ -7,202 +7,6 @@
 #include "gemm.cuh"
 
 namespace st5 {
-
-constexpr int LN_MAX_PER_LANE = 32;  // C <= 1024
-constexpr int LN_WARPS = 4;
-
-template <typename T>
-__global__ void ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ s_out,
-                              float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C, float eps,
-                              uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
-  resolve_seed(seed, offset);
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int per = (C + 31) / 32;
-  float v[LN_MAX_PER_LANE];
-  float sum = 0.f;
-#pragma unroll
-  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-    if (k < per) {
-      const int c = k * 32 + lane;
-      float t = 0.f;
-      if (c < C) {
-        const int64_t i = row * C + c;
-        t = ldf(x + i);
-        if (thr != 0) t = dropout_keep(seed, offset, (uint64_t)i, thr) ? t * dscale : 0.f;
-        if (residual != nullptr) t += ldf(residual + i);
-        if (s_out != nullptr) stf(s_out + i, t);
-        if (s_out != nullptr) t = ldf(s_out + i);  // normalise exactly what backward will read
-        sum += t;
-      }
-      v[k] = t;
-    }
-  }
-  sum = warp_sum(sum);
-  const float mu = sum / (float)C;
-  float sq = 0.f;
-#pragma unroll
-  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-    if (k < per) {
-      const int c = k * 32 + lane;
-      if (c < C) {
-        const float d = v[k] - mu;
-        sq += d * d;
-      }
-    }
-  }
-  sq = warp_sum(sq);
-  const float rs = rsqrtf(sq / (float)C + eps);
-  if (lane == 0) {
-    if (mean != nullptr) mean[row] = mu;
-    if (rstd != nullptr) rstd[row] = rs;
-  }
-#pragma unroll
-  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-    if (k < per) {
-      const int c = k * 32 + lane;
-      if (c < C) stf(y + row * C + c, (v[k] - mu) * rs * gamma[c] + beta[c]);
-    }
-  }
-}
-
-int ln_fwd_launch(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
-                  float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
-                  uint64_t offset, cudaStream_t s) {
-  if (rows == 0) return 0;
-  if (C > 32 * LN_MAX_PER_LANE || C <= 0) return -2;
-  const uint32_t thr = drop_threshold(drop_p);
-  const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
-  if (dtype == ST5_F32)
-    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y,
-                                                        (float*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed,
-                                                        offset);
-  else
-    ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)s_out,
-        mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
-  return (int)cudaGetLastError();
-}
-
-int64_t ln_bwd_blocks(int64_t rows) {
-  int64_t b = (rows + LN_WARPS - 1) / LN_WARPS;
-  if (b > 296) b = 296;
-  if (b < 1) b = 1;
-  return b;
-}
-
-template <typename T>
-__global__ void ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s_in, const float* __restrict__ mean,
-                              const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ ds,
-                              T* __restrict__ dx, float* __restrict__ partials, int64_t rows, int C, uint32_t thr,
-                              float dscale, uint64_t seed, uint64_t offset) {
-  resolve_seed(seed, offset);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (C + 31) / 32;
-  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
-#pragma unroll
-  for (int k = 0; k < LN_MAX_PER_LANE; ++k) dg[k] = db[k] = 0.f;
-  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-      if (k < per) {
-        const int c = k * 32 + lane;
-        float gg = 0.f, xx = 0.f;
-        if (c < C) {
-          const float d = ldf(dy + row * C + c);
-          xx = (ldf(s_in + row * C + c) - mu) * rs;
-          gg = d * gamma[c];
-          dg[k] += d * xx;
-          db[k] += d;
-        }
-        g[k] = gg; xh[k] = xx;
-        c1 += gg; c2 += gg * xx;
-      }
-    }
-    c1 = warp_sum(c1) / (float)C;
-    c2 = warp_sum(c2) / (float)C;
-#pragma unroll
-    for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-      if (k < per) {
-        const int c = k * 32 + lane;
-        if (c < C) {
-          const int64_t i = row * C + c;
-          const float r = rs * (g[k] - c1 - xh[k] * c2);
-          if (ds != nullptr) stf(ds + i, r);
-          if (dx != nullptr) {
-            float rr = r;
-            if (thr != 0) rr = dropout_keep(seed, offset, (uint64_t)i, thr) ? r * dscale : 0.f;
-            stf(dx + i, rr);
-          }
-        }
-      }
-    }
-  }
-  // reduce the per-warp column partials across the block's warps, then one partial row per block
-  extern __shared__ float sm[];  // [LN_WARPS][2][C]
-#pragma unroll
-  for (int k = 0; k < LN_MAX_PER_LANE; ++k) {
-    if (k < per) {
-      const int c = k * 32 + lane;
-      if (c < C) {
-        sm[(warp * 2 + 0) * C + c] = dg[k];
-        sm[(warp * 2 + 1) * C + c] = db[k];
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int w = 0; w < LN_WARPS; ++w) {
-      a += sm[(w * 2 + 0) * C + c];
-      b += sm[(w * 2 + 1) * C + c];
-    }
-    partials[((int64_t)blockIdx.x * 2 + 0) * C + c] = a;
-    partials[((int64_t)blockIdx.x * 2 + 1) * C + c] = b;
-  }
-}
-__global__ void ln_bwd_finalize(const float* __restrict__ partials, float* __restrict__ dgamma,
-                                float* __restrict__ dbeta, int nblk, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int k = 0; k < nblk; ++k) {
-    a += partials[((int64_t)k * 2 + 0) * C + c];
-    b += partials[((int64_t)k * 2 + 1) * C + c];
-  }
-  if (dgamma != nullptr) dgamma[c] += a;
-  if (dbeta != nullptr) dbeta[c] += b;
-}
-
-int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
-                  void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
-                  float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s) {
-  if (rows == 0) return 0;
-  if (C > 32 * LN_MAX_PER_LANE || C <= 0) return -2;
-  const uint32_t thr = drop_threshold(drop_p);
-  const float dsc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int nblk = (int)ln_bwd_blocks(rows);
-  const size_t smem = sizeof(float) * LN_WARPS * 2 * C;
-  if (dtype == ST5_F32)
-    ln_bwd_kernel<float><<<nblk, LN_WARPS * 32, smem, s>>>((const float*)dy, (const float*)s_in, mean, rstd, gamma,
-                                                           (float*)ds, (float*)dx, partials, rows, (int)C, thr, dsc,
-                                                           seed, offset);
-  else
-    ln_bwd_kernel<__nv_bfloat16><<<nblk, LN_WARPS * 32, smem, s>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)s_in, mean, rstd, gamma, (__nv_bfloat16*)ds,
-        (__nv_bfloat16*)dx, partials, rows, (int)C, thr, dsc, seed, offset);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  ln_bwd_finalize<<<(unsigned)((C + 127) / 128), 128, 0, s>>>(partials, dgamma, dbeta, nblk, (int)C);
-  return (int)cudaGetLastError();
-}
 
 // =============================================================================================== BatchNorm1d
 // channels-last rows [rows][C]; block (32 channels, 8 row lanes); per-channel partial sums via fp32 atomics.

@@ -41,7 +41,7 @@ def _require_cuda(*ts):
 
 def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1,
          a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None,
-         act=None, alpha=1.0, accumulate=False, drop_p=0.0, seed=0, offset=0):
+         act=None, alpha=1.0, accumulate=False, drop_p=0.0, seed=0, offset=0, actgrad_pre=None, actgrad_act=None):
     """out[z][m][n] = epi(alpha * sum_k A[z][m][k] B[z][n][k]); see st5_gemm_bf16 in include/speecht5_b200.h."""
     _require_cuda(a, b, out)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -69,10 +69,14 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         assert c_pre.dtype == out.dtype
     g.alpha = alpha
     g.drop_p, g.drop_seed, g.drop_offset = drop_p, seed, offset
+    if actgrad_pre is not None:
+        assert actgrad_pre.dtype == out.dtype
+        g.actgrad_pre, g.actgrad_act = actgrad_pre.data_ptr(), ACT_IDS[actgrad_act]
     lib = _lib.load()
     _lib.check(lib.st5_gemm_bf16(C.byref(g), _stream()), "st5_gemm_bf16")
     _count(1)
     if GEMM_RECORD is not None:
+        g._keep = (a, b, out, c_pre, bias, bias2, residual)  # keep the operands alive for the replay
         GEMM_RECORD.append(g)
     return out
 

@@ -122,14 +122,12 @@ class TransformerSentenceEncoderLayer(nn.Module):
             x = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, drop_p=p, residual=residual)
             residual = x
             h = ops.residual_layer_norm(x, None, self.final_layer_norm)
-            h = ops.linear(h, self.fc1.weight, self.fc1.bias, act=self.activation_fn, drop_p=pa)
-            x = ops.linear(h, self.fc2.weight, self.fc2.bias, drop_p=p, residual=residual)
+            x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
         else:  # :112-132
             a = self.self_attn.self_attend(x, self_attn_padding_mask, pe_k=pos_bias, maxpos=maxpos, training=tr)
             o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
             x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p)
-            h = ops.linear(x, self.fc1.weight, self.fc1.bias, act=self.activation_fn, drop_p=pa)
-            o = ops.linear(h, self.fc2.weight, self.fc2.bias)
+            o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
             x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p)
         return x, None
 
@@ -314,11 +312,9 @@ class TransformerDecoderLayer(nn.Module):
             if self.normalize_before:
                 residual = x
                 h = ops.residual_layer_norm(x, None, self.final_layer_norm)
-                h = ops.linear(h, self.fc1.weight, self.fc1.bias, act=self.activation_fn, drop_p=pa)
-                x = ops.linear(h, self.fc2.weight, self.fc2.bias, drop_p=p, residual=residual)
+                x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
             else:
-                h = ops.linear(x, self.fc1.weight, self.fc1.bias, act=self.activation_fn, drop_p=pa)
-                o = ops.linear(h, self.fc2.weight, self.fc2.bias)
+                o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
                 x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p)
         return x, attn, None
 

@@ -24,6 +24,7 @@ class Runtime:
         self.param_epoch = 0
         self._shadows = {}
         self._static = {}
+        self._static_grad = {}  # key -> fp32 view of the trainer's flat gradient buffer (direct accumulation)
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
 
     @property
@@ -60,8 +61,12 @@ class Runtime:
         """Shadow that is kept current by someone else (the trainer's flat bf16 buffer refreshed by the Adam kernel)."""
         self._static[key] = hi
 
+    def register_static_grad(self, key, view):
+        self._static_grad[key] = view
+
     def clear_static(self):
         self._static = {}
+        self._static_grad = {}
 
     def invalidate_shadows(self):
         """Call after parameters change (optimizer step, load_state_dict)."""
@@ -216,24 +221,36 @@ class LinearFn(torch.autograd.Function):
             # dx[m,k] = sum_n dpre[m,n] W[n,k]: B operand rows = k, stored [n][k] -> MN-major
             mm(ga, w_sh, dx, M=M, N=Kd, Kd=N, a_ld=dpre_ld, b_mn=True, b_ld=Kd, c_ld=Kd)
             dx = dx.reshape(xshape)
-        # dW[n,k] = sum_m dpre[m,n] x[m,k]: both operands MN-major
-        dW = torch.empty((N, Kd), dtype=torch.float32, device=dev)
+        # dW[n,k] = sum_m dpre[m,n] x[m,k]: both operands MN-major. When the trainer owns a flat gradient buffer the
+        # GEMM accumulates straight into it (fused group = one contiguous [N,K] region) and autograd gets None.
         xop = xa if xa is not None else (x2, None)
-        mm(ga, xop, dW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd)
-        grads_w, r0 = [], 0
-        for w in weights:
-            grads_w.append(dW[r0:r0 + w.shape[0]].reshape(w.shape))
-            r0 += w.shape[0]
+        gW = RT._static_grad.get(("lin",) + tuple(id(w) for w in weights))
+        if gW is not None:
+            mm(ga, xop, gW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd,
+               accumulate=True)
+            grads_w = [None] * len(weights)
+        else:
+            dW = torch.empty((N, Kd), dtype=torch.float32, device=dev)
+            mm(ga, xop, dW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd)
+            grads_w, r0 = [], 0
+            for w in weights:
+                grads_w.append(dW[r0:r0 + w.shape[0]].reshape(w.shape))
+                r0 += w.shape[0]
         grads_b = []
         d_b2 = None
         if len(biases) > 0 or has_b2:
             if len(biases) > 0:
-                db = torch.empty(N, dtype=torch.float32, device=dev)
-                K.colsum(dpre, db, ld=dpre_ld)
-                r0 = 0
-                for b in biases:
-                    grads_b.append(db[r0:r0 + b.shape[0]])
-                    r0 += b.shape[0]
+                gB = RT._static_grad.get(("bias",) + tuple(id(b) for b in biases))
+                if gB is not None:
+                    K.colsum(dpre, gB, ld=dpre_ld, accumulate=True)
+                    grads_b = [None] * len(biases)
+                else:
+                    db = torch.empty(N, dtype=torch.float32, device=dev)
+                    K.colsum(dpre, db, ld=dpre_ld)
+                    r0 = 0
+                    for b in biases:
+                        grads_b.append(db[r0:r0 + b.shape[0]])
+                        r0 += b.shape[0]
             if has_b2:
                 d_b2 = torch.empty(((M + b2rows - 1) // b2rows, N), dtype=torch.float32, device=dev)
                 K.colsum(dpre, d_b2, group_rows=b2rows, ld=dpre_ld)
@@ -251,6 +268,94 @@ def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=
     if out_dtype is not None:
         opts["out_dtype"] = out_dtype
     return LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
+
+
+class FFNFn(torch.autograd.Function):
+    """o = dropout_o(fc2(dropout_a(act(fc1(x))))) (+ residual): the position-wise FFN of transformer_layer.py:127-132 /
+    :385-391 as two GEMMs whose epilogues carry bias, GELU (+ pre-activation store) and dropout; in backward the
+    activation/dropout derivative is fused into the epilogue of the dH = dO.W2 GEMM (no elementwise pass over
+    [rows, ffn])."""
+
+    @staticmethod
+    def forward(ctx, x, residual, w1, b1, w2, b2, act, drop_a, drop_o):
+        x2 = x.reshape(-1, x.shape[-1])
+        M, D = x2.shape
+        F_ = w1.shape[0]
+        w1s, w2s = RT.shadow(("lin", id(w1)), lambda: w1), RT.shadow(("lin", id(w2)), lambda: w2)
+        bb1 = RT._static.get(("bias", id(b1)), None)
+        bb1 = bb1 if bb1 is not None else b1.detach().float().contiguous()
+        bb2 = RT._static.get(("bias", id(b2)), None)
+        bb2 = bb2 if bb2 is not None else b2.detach().float().contiguous()
+        h = torch.empty((M, F_), dtype=x.dtype, device=x.device)
+        pre = torch.empty_like(h)
+        off_a = RT.next_offset() if drop_a > 0 else 0
+        xa = _split(x2)
+        mm(xa, w1s, h, M=M, N=F_, Kd=D, a_ld=x2.stride(0), b_ld=D, c_ld=F_, bias=bb1, c_pre=pre, act=act,
+           drop_p=drop_a, seed=RT.seed, offset=off_a)
+        o = torch.empty((M, D), dtype=x.dtype, device=x.device)
+        off_o = RT.next_offset() if drop_o > 0 else 0
+        res2 = residual.reshape(M, D).contiguous() if residual is not None else None
+        ha = _split(h)
+        mm(ha, w2s, o, M=M, N=D, Kd=F_, a_ld=F_, b_ld=F_, c_ld=D, bias=bb2, residual=res2, drop_p=drop_o, seed=RT.seed,
+           offset=off_o)
+        ctx.save_for_backward(x2, h, pre)
+        ctx.meta = (w1, b1, w2, b2, w1s, w2s, act, drop_a, off_a, drop_o, off_o, RT.seed, x.shape, residual is not None,
+                    xa if x2.dtype == torch.float32 else None, ha if x2.dtype == torch.float32 else None)
+        return o.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, do):
+        x2, h, pre = ctx.saved_tensors
+        (w1, b1, w2, b2, w1s, w2s, act, drop_a, off_a, drop_o, off_o, seed, xshape, has_res, xa, ha) = ctx.meta
+        M, D = x2.shape
+        F_ = h.shape[1]
+        dev = do.device
+        do2 = do.reshape(M, D).contiguous()
+        d_res = do if has_res else None
+        if drop_o > 0:
+            tmp = torch.empty_like(do2)
+            K.dropout(do2, tmp, drop_o, seed, off_o)
+            do2 = tmp
+        ga = _split(do2)
+        # dH_pre = (dO W2) * dropmask_a * act'(pre)  -- fused into the GEMM epilogue
+        dhp = torch.empty((M, F_), dtype=do.dtype, device=dev)
+        mm(ga, w2s, dhp, M=M, N=F_, Kd=D, a_ld=D, b_mn=True, b_ld=F_, c_ld=F_, drop_p=drop_a, seed=seed, offset=off_a,
+           actgrad_pre=pre, actgrad_act=act)
+        gh = _split(dhp)
+
+        def wgrad(gy, gy_ld, xin, xin_ld, w, n_out, n_in):
+            gW = RT._static_grad.get(("lin", id(w)))
+            if gW is not None:
+                mm(gy, xin, gW, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in,
+                   accumulate=True)
+                return None
+            dW = torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
+            mm(gy, xin, dW, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in)
+            return dW
+
+        def bgrad(gy2d, b):
+            gB = RT._static_grad.get(("bias", id(b)))
+            if gB is not None:
+                K.colsum(gy2d, gB, accumulate=True)
+                return None
+            db = torch.empty(b.shape[0], dtype=torch.float32, device=dev)
+            K.colsum(gy2d, db)
+            return db
+
+        dW2 = wgrad(ga, D, ha if ha is not None else (h, None), F_, w2, D, F_)
+        db2 = bgrad(do2, b2)
+        dW1 = wgrad(gh, F_, xa if xa is not None else (x2, None), x2.stride(0), w1, F_, D)
+        db1 = bgrad(dhp, b1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, D), dtype=do.dtype, device=dev)
+            mm(gh, w1s, dx, M=M, N=D, Kd=F_, a_ld=F_, b_mn=True, b_ld=D, c_ld=D)
+            dx = dx.reshape(xshape)
+        return dx, d_res, dW1, db1, dW2, db2, None, None, None
+
+
+def ffn(x, fc1, fc2, act, drop_a=0.0, drop_o=0.0, residual=None):
+    return FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o)
 
 
 # =================================================================================================== LayerNorm

@@ -104,13 +104,19 @@ class FlatParams:
             if p.dim() == 2:
                 o = offsets[id(p)]
                 RT.register_static(("lin", id(p)), self.shadow[o:o + p.numel()].view(p.shape))
+                RT.register_static_grad(("lin", id(p)), self.grads[o:o + p.numel()].view(p.shape))
+            elif p.dim() == 1:
+                o = offsets[id(p)]
+                RT.register_static_grad(("bias", id(p)), self.grads[o:o + p.numel()])
         for g in groups:
             o = offsets[id(g[0])]
             n = sum(p.numel() for p in g)
             if g[0].dim() == 2:
                 RT.register_static(("lin",) + tuple(id(p) for p in g), self.shadow[o:o + n].view(-1, g[0].shape[1]))
+                RT.register_static_grad(("lin",) + tuple(id(p) for p in g), self.grads[o:o + n].view(-1, g[0].shape[1]))
             else:
                 RT.register_static(("bias",) + tuple(id(p) for p in g), self.flat[o:o + n])
+                RT.register_static_grad(("bias",) + tuple(id(p) for p in g), self.grads[o:o + n])
         self.params = params
 
     def refresh_shadow(self):

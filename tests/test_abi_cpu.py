@@ -36,7 +36,7 @@ def test_version_and_error_text(lib):
 def test_struct_layout_matches_header():
     from speecht5_b200._lib import AttnArgs, GemmArgs
     # C layout computed by hand from the header: ints first, then 8-byte aligned pointers / int64
-    assert ctypes.sizeof(GemmArgs) == 5 * 4 + 6 * 4 + 4 + 8 * 16 + 4 + 4 + 16
+    assert ctypes.sizeof(GemmArgs) == 5 * 4 + 6 * 4 + 4 + 8 * 16 + 4 + 4 + 16 + 8 + 8
     assert ctypes.sizeof(AttnArgs) % 8 == 0 and AttnArgs.q.offset == 32
 
 
