@@ -184,10 +184,16 @@ def main():
         for i in range(2):
             trainer.train_step([resident[i]])
         torch.cuda.synchronize()
+        K.GEMM_RECORD = []
         torch.cuda.profiler.start()
         trainer.train_step([resident[2]])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.json"), "w") as fh:  # launch-ordered, joins the ncu list
+            json.dump([dict(M=g.M, N=g.N, K=g.K, nb=g.nb1 * g.nb2, a_mn=g.a_mn, b_mn=g.b_mn, c_fp32=g.c_fp32,
+                            acc=g.accumulate, act=g.act, drop=g.drop_p > 0, pre=bool(g.c_pre), ag=bool(g.actgrad_pre))
+                       for g in K.GEMM_RECORD], fh)
         return
     sampler = ClockSampler(local) if rank == 0 else None
 

@@ -135,6 +135,16 @@ typedef struct st5_attn_args {
 int st5_attn_fwd(const st5_attn_args* args, void* stream);
 int st5_attn_bwd(const st5_attn_args* args, void* stream);
 
+/* Fused tcgen05 attention forward (bf16, no relative-position table, Tk <= 320): QK^T -> masks -> softmax -> dropout
+ * -> PV in ONE launch, scores resident in TMEM. Uses the q/k/v/out/probs/key_pad/scale/dropout fields of
+ * st5_attn_args exactly like st5_attn_fwd; additionally writes lse[b][h][i] = log sum_j exp(scale*q_i.k_j) (may be
+ * NULL). probs (optional) receives the undropped probabilities in probs_dtype. */
+int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* stream);
+/* Fused tcgen05 attention backward (flash style: P is recomputed from lse, no Tq x Tk tensor touches HBM). Reads
+ * q/k/v, out (forward result), dout, key_pad, dropout fields; optional dprobs_ext (+ the fp32 probs it refers to);
+ * writes dq/dk/dv (same layouts as q/k/v). Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats. */
+int st5_attn_fused_bwd(const st5_attn_args* args, const float* lse, float* delta, float* dq_acc, void* stream);
+
 /* Tensor-core (bf16) attention path: the contractions run on st5_gemm_bf16 (batched over heads and utterances, q/k/v
  * read in place from the fused projection buffers); these three row kernels are the non-GEMM steps between them.
  * Row index = (b*H + h)*Tq + i everywhere; row pitch p_ld (multiple of 8, >= Tk); dropout indices as in st5_attn_fwd.

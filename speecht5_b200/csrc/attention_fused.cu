@@ -1,0 +1,323 @@
+// Fused attention forward on tcgen05: one CTA = (128 query rows, head, utterance); QK^T and PV run on the tensor
+// cores with the whole score row block resident in TMEM (no HBM round trip for scores / probabilities):
+//
+//   TMA: Q tile [128x64], K [Tk x 64], V [Tk x 64] (read in place from the fused projection buffers, 128B swizzle)
+//   MMA: S[128 x Tk] = Q K^T                                   -> TMEM columns [0, Tk)
+//   softmax warps (1 thread = 1 query row = 1 TMEM lane): scale, causal / key-padding mask, exact two-pass softmax
+//        straight out of TMEM, dropout, P -> shared memory as the K-major A operand (bf16, 128B swizzle),
+//        optional probability output (fp32 for need_head_weights, multihead_attention.py:399-405) and log-sum-exp
+//   MMA: O[128 x 64] = dropout(P) V   (V consumed as an MN-major B operand: no transpose)  -> TMEM columns [448, 512)
+//   epilogue: O / rowsum -> bf16 -> out[b, i, h*64 : h*64+64]
+//
+// Reference semantics: speecht5/models/modules/multihead_attention.py:340-389 (without the relative-position bias;
+// the RPE encoder layers use the GEMM + row-kernel path of attention_tc.cu). Tk <= 320 (S must fit TMEM next to O).
+#include "../../include/speecht5_b200.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tma_map.cuh"
+
+namespace st5 {
+
+int set_error(int code, const char* where);
+
+constexpr int FA_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 softmax warps
+constexpr int FA_BM = 128;
+constexpr int FA_MAX_TK = 320;
+constexpr int FA_KBOX = 160;        // K rows per TMA box (two boxes cover 320 keys)
+constexpr uint32_t FA_O_COL = 448;  // TMEM column of the O accumulator (S occupies [0, 320))
+constexpr size_t FA_SMEM = 16384 + 40960 + 40960 + 81920 + 64 + 2048 + 1024;
+
+struct FusedFwdParams {
+  int B, H, Tq, Tk, causal;
+  float scale_log2;        // scale * log2(e)
+  const uint8_t* key_pad;  // [B][Tk] or null
+  __nv_bfloat16* out; long o_ld, o_bs;
+  float* lse;              // [B][H][Tq] natural-log sum-exp of the scaled scores (for the backward pass)
+  void* probs; int probs_fp32; long p_ld;  // optional undropped probabilities [B][H][Tq][p_ld]
+  uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+    attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                          const __grid_constant__ CUtensorMap map_v, const FusedFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;             // 128 x 128 B
+  uint8_t* sK = sQ + 16384;       // up to 320 x 128 B (K-major B operand of S)
+  uint8_t* sV = sK + 40960;       // up to 5 blocks of [64 keys][128 B] (MN-major B operand of O)
+  uint8_t* sP = sV + 40960;       // up to 5 blocks of [128 rows][128 B] (K-major A operand of O)
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 81920);
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_p = bar_load + 2;
+  uint64_t* bar_o = bar_load + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+  float* red_max = reinterpret_cast<float*>(bar_load + 6);  // [2][128] partial row maxima of the two column halves
+  float* red_sum = red_max + 256;                            // [2][128] partial row sums
+
+  const int warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+  int tk = p.Tk;  // keys this query tile can see
+  if (p.causal && i0 + FA_BM < tk) tk = i0 + FA_BM;
+  const int tk16 = (tk + 15) & ~15;
+  const int nkb = (tk + 63) >> 6;
+  const int n1 = tk16 > FA_KBOX ? FA_KBOX : tk16;  // S is issued as one or two MMAs
+  const int n2 = tk16 - n1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int kboxes = n2 > 0 ? 2 : 1;
+      mbar_expect_tx(bar_load, 16384u + (uint32_t)kboxes * (FA_KBOX * 128u) + (uint32_t)nkb * 8192u);
+      tma_load_4d(sQ, &map_q, bar_load, 0, i0, h, b);
+      tma_load_4d(sK, &map_k, bar_load, 0, 0, h, b);
+      if (kboxes == 2) tma_load_4d(sK + FA_KBOX * 128, &map_k, bar_load, 0, FA_KBOX, h, b);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_4d(sV + kb * 8192, &map_v, bar_load, 0, kb * 64, h, b);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // head dim 64 = 4 x UMMA_K
+        const uint64_t da = umma_smem_desc(aq + k * 32, 16, 1024);
+        umma_bf16(tmem, da, umma_smem_desc(ak + k * 32, 16, 1024), umma_idesc_bf16(128, n1, 0, 0), k != 0);
+        if (n2 > 0)
+          umma_bf16(tmem + (uint32_t)n1, da, umma_smem_desc(ak + FA_KBOX * 128 + k * 32, 16, 1024),
+                    umma_idesc_bf16(128, n2, 0, 0), k != 0);
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+      for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 64 keys = 4 x UMMA_K
+          const uint64_t da = umma_smem_desc(ap + kb * 16384 + k * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc(av + kb * 8192 + k * 2048, 8192, 1024);
+          umma_bf16(tmem + FA_O_COL, da, db, idesc, (kb | k) != 0);
+        }
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: 8 warps, thread = (query row, half of the 32-column chunks) ========
+    const int q = warp & 3;                 // TMEM lane quarter (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;       // chunks c with (c & 1) == half
+    const int r = q * 32 + (int)lane_id();  // row within the tile == TMEM lane
+    const int i = i0 + r;
+    const bool row_ok = i < p.Tq;
+    const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
+    const uint8_t* kp = p.key_pad != nullptr ? p.key_pad + (int64_t)b * p.Tk : nullptr;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    uint64_t dseed = p.seed, doffset = p.offset;
+    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
+    const int nchunks = nkb * 2;  // 32-column chunks (TMEM columns beyond tk16 hold garbage and are masked)
+    // validity bits of chunk c for THIS row: key exists, not padded (one coalesced byte load per lane + ballot), causal
+    auto valid_bits = [&](int c) -> uint32_t {
+      const int j = c * 32 + (int)lane_id();
+      const bool ok = j < tk && !(kp != nullptr && kp[j] != 0);
+      uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (p.causal) {
+        const int lim = i - c * 32;  // columns 0..lim are visible
+        m &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+      }
+      return m;
+    };
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // pass 1: row maximum of the masked, scaled (log2 domain) scores
+    float m = -INFINITY;
+    for (int c = half; c < nchunks; c += 2) {
+      uint32_t v[32];
+      tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+      const uint32_t vb = valid_bits(c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t)
+        if ((vb >> t) & 1u) m = fmaxf(m, __uint_as_float(v[t]) * p.scale_log2);
+    }
+    red_max[half * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(red_max[r], red_max[128 + r]);
+    const float mm = m == -INFINITY ? 0.f : m;
+    // pass 2: exponentials, partial row sum, dropout, P -> smem as the K-major SW128 A operand of the PV MMA.
+    // The normaliser is applied to O at the end (PV is linear in P).
+    float sum = 0.f;
+    for (int c = half; c < nchunks; c += 2) {
+      uint32_t v[32];
+      tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+      const uint32_t vb = valid_bits(c);
+      uint32_t kb_ = 0xffffffffu;
+      if (p.drop_thr != 0)
+        kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * (uint64_t)p.Tk + (uint64_t)(c * 32), p.drop_thr);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float ev = ((vb >> t) & 1u) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - mm) : 0.f;
+        sum += ev;
+        e[t] = ((kb_ >> t) & 1u) ? ev * p.drop_scale : 0.f;
+      }
+      uint8_t* blk = sP + (c >> 1) * 16384 + r * 128;  // block = 64 keys, row r at r*128 B, chunk XOR (r & 7)
+      const int cbase = (c & 1) * 4;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 pk;
+        pk.x = pack_bf16(e[8 * g], e[8 * g + 1]);
+        pk.y = pack_bf16(e[8 * g + 2], e[8 * g + 3]);
+        pk.z = pack_bf16(e[8 * g + 4], e[8 * g + 5]);
+        pk.w = pack_bf16(e[8 * g + 6], e[8 * g + 7]);
+        *reinterpret_cast<uint4*>(blk + (((cbase + g) ^ (r & 7)) << 4)) = pk;
+      }
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(bar_p);
+    red_sum[half * 128 + r] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = red_sum[r] + red_sum[128 + r];
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (half == 0 && row_ok && p.lse != nullptr)
+      p.lse[prow] = (sum > 0.f) ? (mm + log2f(sum)) * 0.6931471805599453f : -INFINITY;
+    if (p.probs != nullptr) {
+      // normalised, undropped probabilities for the caller (overlaps the PV MMA)
+      const int pchunks = (int)((p.p_ld + 31) / 32);
+      for (int c = half; c < pchunks; c += 2) {
+        float pr[32];
+        if (c < nchunks) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+          const uint32_t vb = valid_bits(c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            pr[t] = ((vb >> t) & 1u) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - mm) * inv : 0.f;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) pr[t] = 0.f;
+        }
+        if (row_ok) {
+          const int j0 = c * 32;
+          if (p.probs_fp32) {
+            float* dst = reinterpret_cast<float*>(p.probs) + prow * p.p_ld + j0;
+            if (j0 + 32 <= p.p_ld) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4)
+                *reinterpret_cast<float4*>(dst + t) = make_float4(pr[t], pr[t + 1], pr[t + 2], pr[t + 3]);
+            } else {
+              for (int t = 0; t < 32; ++t)
+                if (j0 + t < p.p_ld) dst[t] = pr[t];
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.probs) + prow * p.p_ld + j0;
+            for (int t = 0; t < 32; ++t)
+              if (j0 + t < p.p_ld) dst[t] = __float2bfloat16(pr[t]);
+          }
+        }
+      }
+    }
+    // epilogue: O / rowsum (each half writes 32 of the 64 channels)
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    {
+      const int c = half;
+      uint32_t v[32];
+      tmem_ld_32x32(trow + FA_O_COL + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      if (row_ok) {
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + c * 32;
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(v[t + 4]) * inv, __uint_as_float(v[t + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(v[t + 6]) * inv, __uint_as_float(v[t + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + t) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, int64_t bs, int H, int B, int box_rows) {
+  const uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ld * 2, 128, (uint64_t)bs * 2};
+  const uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return encode_bf16_map_4d(m, ptr, dims, strides, box);
+}
+
+}  // namespace st5
+
+using namespace st5;
+
+extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stream) {
+  if (a->dtype != ST5_BF16 || a->Tk > FA_MAX_TK || a->Tk <= 0 || a->Tq <= 0 || a->pe_k != nullptr)
+    return set_error(-2, "st5_attn_fused_fwd: needs bf16, Tk <= 320, no relative-position table");
+  if (a->probs != nullptr && a->p_ld < a->Tk) return set_error(-3, "st5_attn_fused_fwd");
+  if ((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->out) & 15))
+    return set_error(-4, "st5_attn_fused_fwd: out must be 16-byte aligned");
+  CUtensorMap mq, mk, mv;
+  int rc = make_map(&mq, a->q, a->Tq, a->q_ld, a->q_bs, a->H, a->B, FA_BM);
+  if (!rc) rc = make_map(&mk, a->k, a->Tk, a->k_ld, a->k_bs, a->H, a->B, FA_KBOX);
+  if (!rc) rc = make_map(&mv, a->v, a->Tk, a->v_ld, a->v_bs, a->H, a->B, 64);
+  if (rc) return set_error(rc, "st5_attn_fused_fwd: tensor map");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FA_SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_fwd");
+    attr_set = true;
+  }
+  FusedFwdParams p;
+  p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.key_pad = a->key_pad;
+  p.out = (__nv_bfloat16*)a->out; p.o_ld = a->o_ld; p.o_bs = a->o_bs;
+  p.lse = lse;
+  p.probs = a->probs; p.probs_fp32 = a->probs_dtype == ST5_F32; p.p_ld = a->p_ld;
+  p.drop_thr = drop_threshold(a->drop_p);
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.seed = a->seed; p.offset = a->offset;
+  dim3 grid((a->Tq + FA_BM - 1) / FA_BM, a->H, a->B);
+  attn_fused_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  return set_error((int)cudaGetLastError(), "st5_attn_fused_fwd");
+}

@@ -1,0 +1,374 @@
+// Fused attention backward on tcgen05 (flash-style: probabilities are recomputed from the saved log-sum-exp, nothing of
+// size Tq x Tk is read from or written to HBM except the optional external dP of the guided-attention loss).
+//
+// One CTA per (head, utterance). Loop: key block kb (128 keys) outer, query tile qt (128 rows) inner:
+//   MMA1   S  = Q_qt K_kb^T  -> TMEM[0,128)        dP = dO_qt V_kb^T -> TMEM[128,256)
+//   threads (1 thread = 1 query row): P = exp(scale*S - lse), dropout mask, dS = P * (dP_masked + dP_ext - delta);
+//            dropout(P) and dS -> shared memory (bf16, 128B-swizzled [q][key] tiles)
+//   MMA2   dV_kb += dropout(P)^T dO_qt   dK_kb += dS^T Q_qt      (A operands = the SAME smem tiles read MN-major)
+//          dQ_qt(kb) = dS K_kb           (A = dS tile read K-major, B = K_kb tile read MN-major)
+//   threads: dQ partial -> fp32 accumulator in HBM (plain RMW: the CTA owns its (b,h)), bf16 on the last key block;
+//            after the last query tile of a key block: dK_kb, dV_kb -> global.
+// Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389 (no relative-position table).
+#include "../../include/speecht5_b200.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tma_map.cuh"
+
+namespace st5 {
+
+int set_error(int code, const char* where);
+
+constexpr int FB_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quarter)
+constexpr int FB_T = 128;  // query tile == key block
+constexpr size_t FB_SMEM = 4 * 16384 + 2 * 32768 + 64 + 1024;
+constexpr uint32_t FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DK = 256, FB_COL_DV = 320, FB_COL_DQ = 384;
+
+struct FusedBwdParams {
+  int B, H, Tq, Tk, causal;
+  float scale, scale_log2;
+  const uint8_t* key_pad;
+  const float* lse; const float* delta;
+  const float* dp_ext; long p_ld;
+  __nv_bfloat16* dq; long q_ld, q_bs;
+  __nv_bfloat16* dk; long k_ld, k_bs;
+  __nv_bfloat16* dv; long v_ld, v_bs;
+  float* dq_acc;  // [B][Tq][H*64] fp32 scratch
+  uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// delta[row] = sum_c dO*O (+ sum_j P*dP_ext): the softmax-backward row constant. One warp per (b,h,i).
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, long o_ld,
+                                  long o_bs, const float* __restrict__ probs, const float* __restrict__ dpx, long p_ld,
+                                  float* __restrict__ delta, int B, int H, int Tq, int Tk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * H * Tq) return;
+  const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
+  const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + lane * 2;
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
+  const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
+  float acc = a.x * o.x + a.y * o.y;
+  if (dpx != nullptr) {
+    const float* pr = probs + row * p_ld;
+    const float* dx = dpx + row * p_ld;
+    for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[row] = acc;
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+    attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                          const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                          const FusedBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;             // [128 keys][128 B]
+  uint8_t* sV = sK + 16384;
+  uint8_t* sQ = sV + 16384;       // [128 rows][128 B]
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sPd = sdO + 16384;     // 2 blocks of [128 rows][64 keys]
+  uint8_t* sdS = sPd + 32768;
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* bar_qdo = bar_kv + 1;
+  uint64_t* bar_sdp = bar_kv + 2;
+  uint64_t* bar_pds = bar_kv + 3;
+  uint64_t* bar_mma2 = bar_kv + 4;
+  uint64_t* bar_tdone = bar_kv + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nkb = (p.Tk + FB_T - 1) / FB_T, nqt = (p.Tq + FB_T - 1) / FB_T;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
+    mbar_init(bar_kv, 1); mbar_init(bar_qdo, 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 8);
+    mbar_init(bar_mma2, 1); mbar_init(bar_tdone, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int it = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int qt0 = p.causal ? kb : 0;
+        for (int qt = qt0; qt < nqt; ++qt, ++it) {
+          if (it > 0) mbar_wait(bar_mma2, (uint32_t)((it - 1) & 1));  // previous tiles fully consumed by the MMAs
+          if (qt == qt0) {
+            mbar_expect_tx(bar_kv, 32768);
+            tma_load_4d(sK, &map_k, bar_kv, 0, kb * FB_T, h, b);
+            tma_load_4d(sV, &map_v, bar_kv, 0, kb * FB_T, h, b);
+          }
+          mbar_expect_tx(bar_qdo, 32768);
+          tma_load_4d(sQ, &map_q, bar_qdo, 0, qt * FB_T, h, b);
+          tma_load_4d(sdO, &map_do, bar_qdo, 0, qt * FB_T, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+    const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
+    int it = 0, kbc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int qt0 = p.causal ? kb : 0;
+      if (qt0 >= nqt) continue;
+      mbar_wait(bar_kv, (uint32_t)(kbc & 1));
+      ++kbc;
+      for (int qt = qt0; qt < nqt; ++qt, ++it) {
+        mbar_wait(bar_qdo, (uint32_t)(it & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t id = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem + FB_COL_S, umma_smem_desc(aQ + k * 32, 16, 1024), umma_smem_desc(aK + k * 32, 16, 1024), id,
+                      k != 0);
+            umma_bf16(tmem + FB_COL_DP, umma_smem_desc(adO + k * 32, 16, 1024), umma_smem_desc(aV + k * 32, 16, 1024),
+                      id, k != 0);
+          }
+          umma_commit(bar_sdp);
+        }
+        __syncwarp();
+        mbar_wait(bar_pds, (uint32_t)(it & 1));
+        if (it > 0) mbar_wait(bar_tdone, (uint32_t)((it - 1) & 1));  // dQ scratch (and dK/dV) of the previous step read
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t acc = qt != qt0;
+          const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);  // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // contraction over the 128 query rows
+            umma_bf16(tmem + FB_COL_DV, umma_smem_desc(aPd + k * 2048, 16384, 1024),
+                      umma_smem_desc(adO + k * 2048, 16384, 1024), id_t, acc | (uint32_t)(k != 0));
+            umma_bf16(tmem + FB_COL_DK, umma_smem_desc(adS + k * 2048, 16384, 1024),
+                      umma_smem_desc(aQ + k * 2048, 16384, 1024), id_t, acc | (uint32_t)(k != 0));
+          }
+          const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);  // A = dS (K-major), B = K (MN-major)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // contraction over the 128 keys: 2 blocks x 4 k-steps
+            const int blk = k >> 2, ks = k & 3;
+            umma_bf16(tmem + FB_COL_DQ, umma_smem_desc(adS + blk * 16384 + ks * 32, 16, 1024),
+                      umma_smem_desc(aK + (blk * 64 + ks * 16) * 128, 16384, 1024), id_q, k != 0);
+          }
+          umma_commit(bar_mma2);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== compute threads (thread = query row / key row) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 64-key half of the block (and which 32-channel half of dQ / dK|dV) this warp owns
+    const int r = q * 32 + (int)lane_id();
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const uint8_t* kp = p.key_pad != nullptr ? p.key_pad + (int64_t)b * p.Tk : nullptr;
+    uint64_t dseed = p.seed, doffset = p.offset;
+    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
+    const float LOG2E = 1.4426950408889634f;
+    int it = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int qt0 = p.causal ? kb : 0;
+      const int k0 = kb * FB_T;
+      for (int qt = qt0; qt < nqt; ++qt, ++it) {
+        const int i = qt * FB_T + r;
+        const bool row_ok = i < p.Tq;
+        const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
+        const float lse2 = row_ok ? p.lse[prow] * LOG2E : 0.f;
+        const float delta = row_ok ? p.delta[prow] : 0.f;
+        const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
+        mbar_wait(bar_sdp, (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half * 2; c < half * 2 + 2; ++c) {  // this warp's 64-key half of the block
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(trow + FB_COL_S + (uint32_t)(c * 32), sv);
+          tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(c * 32), dv);
+          // validity bits: key exists and is not padded (one coalesced byte load per lane + ballot), causal, row in range
+          const int jl = k0 + c * 32 + (int)lane_id();
+          uint32_t vb = __ballot_sync(0xffffffffu, jl < p.Tk && !(kp != nullptr && kp[jl] != 0));
+          if (p.causal) {
+            const int lim = i - (k0 + c * 32);
+            vb &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+          }
+          if (!row_ok) vb = 0u;
+          uint32_t kb_ = 0xffffffffu;
+          if (p.drop_thr != 0)
+            kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * (uint64_t)p.Tk + (uint64_t)(k0 + c * 32),
+                                      p.drop_thr);
+          tmem_ld_wait();
+          float pd[32], ds[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            float pv = 0.f, dpt = 0.f, pdv = 0.f;
+            if ((vb >> t) & 1u) {
+              pv = exp2f(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
+              const bool keep = (kb_ >> t) & 1u;
+              dpt = keep ? __uint_as_float(dv[t]) * p.drop_scale : 0.f;
+              pdv = keep ? pv * p.drop_scale : 0.f;
+              if (dpx != nullptr) dpt += dpx[k0 + c * 32 + t];
+            }
+            pd[t] = pdv;
+            ds[t] = pv * (dpt - delta);
+          }
+          uint8_t* bp = sPd + (c >> 1) * 16384 + r * 128;
+          uint8_t* bs = sdS + (c >> 1) * 16384 + r * 128;
+          const int cbase = (c & 1) * 4;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int sw = ((cbase + g) ^ (r & 7)) << 4;
+            uint4 a, d;
+            a.x = pack2(pd[8 * g], pd[8 * g + 1]); a.y = pack2(pd[8 * g + 2], pd[8 * g + 3]);
+            a.z = pack2(pd[8 * g + 4], pd[8 * g + 5]); a.w = pack2(pd[8 * g + 6], pd[8 * g + 7]);
+            d.x = pack2(ds[8 * g], ds[8 * g + 1]); d.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
+            d.z = pack2(ds[8 * g + 4], ds[8 * g + 5]); d.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
+            *reinterpret_cast<uint4*>(bp + sw) = a;
+            *reinterpret_cast<uint4*>(bs + sw) = d;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_pds);
+        // ---- dQ partial of this (kb, qt)
+        mbar_wait(bar_mma2, (uint32_t)(it & 1));
+        tc_fence_after();
+        const int kb_last = p.causal ? (qt < nkb - 1 ? qt : nkb - 1) : nkb - 1;
+        {
+          const int c = half;  // each warp of the pair takes 32 of the 64 channels
+          uint32_t v[32];
+          tmem_ld_32x32(trow + FB_COL_DQ + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 32;
+            float f[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
+            if (kb > 0) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(acc + t);
+                f[t] += o.x; f[t + 1] += o.y; f[t + 2] += o.z; f[t + 3] += o.w;
+              }
+            }
+            if (kb == kb_last) {
+              __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 32;
+#pragma unroll
+              for (int t = 0; t < 32; t += 8) {
+                uint4 pk;
+                pk.x = pack2(f[t], f[t + 1]); pk.y = pack2(f[t + 2], f[t + 3]);
+                pk.z = pack2(f[t + 4], f[t + 5]); pk.w = pack2(f[t + 6], f[t + 7]);
+                *reinterpret_cast<uint4*>(dst + t) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4)
+                *reinterpret_cast<float4*>(acc + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
+            }
+          }
+        }
+        // ---- dK / dV of this key block after its last query tile (thread = key row)
+        if (qt == nqt - 1) {
+          const int j = k0 + r;
+#pragma unroll
+          for (int c = half * 2; c < half * 2 + 2; ++c) {  // half 0 writes dK, half 1 writes dV
+            uint32_t v[32];
+            tmem_ld_32x32(trow + (c < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((c & 1) * 32), v);
+            tmem_ld_wait();
+            if (j < p.Tk) {
+              const float sc = c < 2 ? p.scale : 1.f;
+              __nv_bfloat16* dst = (c < 2 ? p.dk + (int64_t)b * p.k_bs + (int64_t)j * p.k_ld
+                                          : p.dv + (int64_t)b * p.v_bs + (int64_t)j * p.v_ld) + h * 64 + (c & 1) * 32;
+#pragma unroll
+              for (int t = 0; t < 32; t += 8) {
+                uint4 pk;
+                pk.x = pack2(__uint_as_float(v[t]) * sc, __uint_as_float(v[t + 1]) * sc);
+                pk.y = pack2(__uint_as_float(v[t + 2]) * sc, __uint_as_float(v[t + 3]) * sc);
+                pk.z = pack2(__uint_as_float(v[t + 4]) * sc, __uint_as_float(v[t + 5]) * sc);
+                pk.w = pack2(__uint_as_float(v[t + 6]) * sc, __uint_as_float(v[t + 7]) * sc);
+                *reinterpret_cast<uint4*>(dst + t) = pk;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(bar_tdone);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int make_map128(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, int64_t bs, int H, int B) {
+  const uint64_t dims[4] = {64, (uint64_t)rows, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ld * 2, 128, (uint64_t)bs * 2};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  return encode_bf16_map_4d(m, ptr, dims, strides, box);
+}
+
+}  // namespace st5
+
+using namespace st5;
+
+extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, float* delta, float* dq_acc, void* stream) {
+  if (a->dtype != ST5_BF16 || a->pe_k != nullptr || a->Tk <= 0 || a->Tq <= 0)
+    return set_error(-2, "st5_attn_fused_bwd: needs bf16 and no relative-position table");
+  if (a->dprobs_ext != nullptr && (a->probs == nullptr || a->probs_dtype != ST5_F32 || a->p_ld < a->Tk))
+    return set_error(-3, "st5_attn_fused_bwd: dprobs_ext needs the fp32 probabilities");
+  if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || !lse || !delta || !dq_acc)
+    return set_error(-4, "st5_attn_fused_bwd: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nrows = (int64_t)a->B * a->H * a->Tq;
+  attn_delta_kernel<<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(
+      (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, a->o_ld, a->o_bs,
+      a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
+  CUtensorMap mq, mk, mv, mdo;
+  int rc = make_map128(&mq, a->q, a->Tq, a->q_ld, a->q_bs, a->H, a->B);
+  if (!rc) rc = make_map128(&mk, a->k, a->Tk, a->k_ld, a->k_bs, a->H, a->B);
+  if (!rc) rc = make_map128(&mv, a->v, a->Tk, a->v_ld, a->v_bs, a->H, a->B);
+  if (!rc) rc = make_map128(&mdo, a->dout, a->Tq, a->o_ld, a->o_bs, a->H, a->B);
+  if (rc) return set_error(rc, "st5_attn_fused_bwd: tensor map");
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(attn_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
+    if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd");
+    attr_set = true;
+  }
+  FusedBwdParams p;
+  p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.key_pad = a->key_pad; p.lse = lse; p.delta = delta;
+  p.dp_ext = a->dprobs_ext; p.p_ld = a->p_ld;
+  p.dq = (__nv_bfloat16*)a->dq; p.q_ld = a->q_ld; p.q_bs = a->q_bs;
+  p.dk = (__nv_bfloat16*)a->dk; p.k_ld = a->k_ld; p.k_bs = a->k_bs;
+  p.dv = (__nv_bfloat16*)a->dv; p.v_ld = a->v_ld; p.v_bs = a->v_bs;
+  p.dq_acc = dq_acc;
+  p.drop_thr = drop_threshold(a->drop_p);
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.seed = a->seed; p.offset = a->offset;
+  attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, p);
+  return set_error((int)cudaGetLastError(), "st5_attn_fused_bwd");
+}

@@ -12,6 +12,7 @@
 #include "ptx.cuh"
 #include "kernels.cuh"
 #include <cuda.h>
+#include "tma_map.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -20,7 +21,8 @@ namespace st5 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 16;  // epilogue warps: 4 per TMEM lane quarter, each taking every 4th 32-column chunk
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct EpiParams {
   int M, N, nb1;
@@ -39,13 +41,13 @@ struct EpiParams {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == ACT_GELU) return gelu_fwd(v);
   if (act == ACT_TANH) return tanhf(v);
   return v;
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const EpiParams p) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -158,7 +160,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read (hardware: warp id % 4)
+    constexpr int NGRP = EPI_WARPS / 4;
+    const int grp = (warp - 2) >> 2;             // which 32-column chunks this warp owns: c = grp, grp + NGRP, ...
     uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
     int local = 0;
@@ -177,12 +181,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
     const long roff = zoff + (long)row * p.c_ld;
     const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
     const uint64_t drop_row = ((uint64_t)z * (uint64_t)p.M + (uint64_t)row) * (uint64_t)p.N;
+    if (grp >= BN / 32) {  // narrow tiles: this warp has no chunk, it only releases the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+    }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = grp; c < BN / 32; c += NGRP) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
-      if (c == BN / 32 - 1) {  // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+      if (c + NGRP >= BN / 32) {  // last TMEM read of this warp for this tile: hand the stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
@@ -242,22 +251,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05(const __grid_c
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
       }
       if (p.drop_thr != 0) {
+        const uint64_t e0 = drop_row + (uint64_t)nb;
+        if ((e0 & 7) == 0) {  // aligned: one Philox call per 8 elements
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          // element index (drop_row + nb + j) is a multiple of 4 only when N is; use the generic per-element form
-          // unless aligned.
-          const uint64_t e = drop_row + (uint64_t)(nb + j);
-          if ((e & 3) == 0) {
-            Philox4 rr = philox4x32(dseed, doffset, e >> 2);
-            v[j] = rr.x >= p.drop_thr ? v[j] * p.drop_scale : 0.f;
-            v[j + 1] = rr.y >= p.drop_thr ? v[j + 1] * p.drop_scale : 0.f;
-            v[j + 2] = rr.z >= p.drop_thr ? v[j + 2] * p.drop_scale : 0.f;
-            v[j + 3] = rr.w >= p.drop_thr ? v[j + 3] * p.drop_scale : 0.f;
-          } else {
+          for (int j = 0; j < 32; j += 8) dropout8_apply(v + j, e0 + j, p.drop_thr, p.drop_scale, dseed, doffset);
+        } else {
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              v[j + t] = dropout_keep(dseed, doffset, e + t, p.drop_thr) ? v[j + t] * p.drop_scale : 0.f;
-          }
+          for (int j = 0; j < 32; ++j)
+            v[j] = dropout_keep(dseed, doffset, e0 + j, p.drop_thr) ? v[j] * p.drop_scale : 0.f;
         }
       }
       if (p.ag_pre != nullptr) {
@@ -364,6 +365,23 @@ static int num_sms() {
   return n;
 }
 
+int device_sm_count() { return num_sms(); }
+
+int encode_bf16_map_4d(CUtensorMap* map, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                       const uint32_t box[4]) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -10;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (s[0] & 15) || (s[1] & 15) || (s[2] & 15)) return -11;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), d, s, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -12;
+}
+
 // rows x K operand. K-major: memory [rows][ld] (k contiguous). MN-major: memory [K][ld] (row index contiguous).
 static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, int rows, int K, long ld, int nb1,
                             long bs1, int nb2, long bs2, int box_rows) {
@@ -441,13 +459,8 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   ep.C_pre = g.C_pre; ep.bias = g.bias; ep.bias2 = g.bias2; ep.bias2_rows = g.bias2_rows > 0 ? g.bias2_rows : 1;
   ep.ag_pre = g.ag_pre; ep.ag_act = g.ag_act;
   ep.residual = g.residual; ep.act = g.act; ep.alpha = g.alpha; ep.accumulate = g.accumulate;
-  if (g.drop_p > 0.f) {
-    double t = (double)g.drop_p * 4294967296.0;
-    ep.drop_thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
-    ep.drop_scale = 1.f / (1.f - g.drop_p);
-  } else {
-    ep.drop_thr = 0; ep.drop_scale = 1.f;
-  }
+  ep.drop_thr = drop_threshold(g.drop_p);
+  ep.drop_scale = g.drop_p > 0.f ? 1.f / (1.f - g.drop_p) : 1.f;
   ep.drop_seed = g.drop_seed; ep.drop_offset = g.drop_offset;
   ep.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   ep.a_m1 = (g.nb1 > 1 && g.a_bs1 == 0) ? 0 : 1; ep.a_m2 = (g.nb2 > 1 && g.a_bs2 == 0) ? 0 : 1;

@@ -25,12 +25,27 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and exp(-x^2 / 2) from ONE exponential (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7):
+// the GELU of the reference (fairseq/modules/gelu.py:24 -> F.gelu, exact erf form) and its derivative share it.
+__device__ __forceinline__ float gauss_cdf(float x, float& ex) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  ex = __expf(-z * z);
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
+                              0.254829592f);
+  const float erf_abs = fmaf(-poly, ex, 1.f);
+  return 0.5f * (1.f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fwd(float x) {
+  float ex;
+  return x * gauss_cdf(x, ex);
+}
 __device__ __forceinline__ float act_grad(float x, int act) {
   if (act == 1) return x > 0.f ? 1.f : 0.f;
   if (act == 2) {
-    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float ex;
+    const float cdf = gauss_cdf(x, ex);
+    return fmaf(x * 0.39894228040143267794f, ex, cdf);
   }
   if (act == 3) {
     const float t = tanhf(x);
@@ -39,8 +54,8 @@ __device__ __forceinline__ float act_grad(float x, int act) {
   return 1.f;
 }
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  const float t = p * 65536.f;
+  return p <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
 }
 
 int cast_bf16_launch(const float* src, int64_t src_ld, void* hi, void* lo, int64_t dst_ld, int64_t rows, int64_t cols,

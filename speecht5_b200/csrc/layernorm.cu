@@ -48,12 +48,7 @@ template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) {
 
 __device__ __forceinline__ void dropout8(float* v, uint64_t e0, uint32_t thr, float dscale, uint64_t seed,
                                          uint64_t offset) {
-  // e0 is a multiple of 8 => two aligned Philox groups
-  const Philox4 a = philox4x32(seed, offset, e0 >> 2), b = philox4x32(seed, offset, (e0 >> 2) + 1);
-  v[0] = a.x >= thr ? v[0] * dscale : 0.f; v[1] = a.y >= thr ? v[1] * dscale : 0.f;
-  v[2] = a.z >= thr ? v[2] * dscale : 0.f; v[3] = a.w >= thr ? v[3] * dscale : 0.f;
-  v[4] = b.x >= thr ? v[4] * dscale : 0.f; v[5] = b.y >= thr ? v[5] * dscale : 0.f;
-  v[6] = b.z >= thr ? v[6] * dscale : 0.f; v[7] = b.w >= thr ? v[7] * dscale : 0.f;
+  dropout8_apply(v, e0, thr, dscale, seed, offset);  // e0 is a multiple of 8 (C % 8 == 0)
 }
 
 template <typename T>

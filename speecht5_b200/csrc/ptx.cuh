@@ -179,11 +179,49 @@ __device__ __forceinline__ void resolve_seed(uint64_t& seed, uint64_t& offset) {
     offset &= ~SEED_PTR_FLAG;
   }
 }
-// keep-mask for element `i` of a tensor: keep iff rand >= p * 2^32. thr = (uint32) min(p*2^32, 2^32-1).
+// Dropout keep-mask for element `i` of a tensor. One Philox4x32 call yields eight 16-bit lanes, i.e. the decisions of 8
+// consecutive elements: keep iff lane >= thr16, thr16 = min(p * 65536, 65535) (p is quantised to 1/65536).
+__host__ __device__ __forceinline__ uint32_t philox_lane16(const Philox4& r, int lane) {
+  const uint32_t w = (lane >> 1) == 0 ? r.x : (lane >> 1) == 1 ? r.y : (lane >> 1) == 2 ? r.z : r.w;
+  return (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t i, uint32_t thr) {
-  Philox4 r = philox4x32(seed, offset, i >> 2);
-  uint32_t v = ((i & 3) == 0) ? r.x : ((i & 3) == 1) ? r.y : ((i & 3) == 2) ? r.z : r.w;
-  return v >= thr;
+  const Philox4 r = philox4x32(seed, offset, i >> 3);
+  return philox_lane16(r, (int)(i & 7)) >= thr;
+}
+// keep-bits of 32 consecutive elements e0 .. e0+31 (any alignment): at most 5 Philox calls instead of 32
+__device__ __forceinline__ uint32_t dropout_keep_mask32(uint64_t seed, uint64_t offset, uint64_t e0, uint32_t thr) {
+  uint32_t mask = 0;
+  const int lead = (int)((8 - (e0 & 7)) & 7);  // elements before the first 8-aligned group boundary
+  if (lead != 0) {
+    const Philox4 r = philox4x32(seed, offset, e0 >> 3);
+    for (int t = 0; t < lead; ++t)
+      if (philox_lane16(r, (int)((e0 + t) & 7)) >= thr) mask |= 1u << t;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int t0 = lead + 8 * g;
+    if (t0 < 32) {
+      const Philox4 r = philox4x32(seed, offset, (e0 + t0) >> 3);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const int t = t0 + l;
+        const uint32_t v = (l & 1) ? (w[l >> 1] >> 16) : (w[l >> 1] & 0xFFFFu);
+        if (t < 32 && v >= thr) mask |= 1u << t;
+      }
+    }
+  }
+  return mask;
+}
+// eight consecutive elements starting at e0 (a multiple of 8): v[t] = keep ? v[t] * scale : 0
+__device__ __forceinline__ void dropout8_apply(float* v, uint64_t e0, uint32_t thr, float dscale, uint64_t seed,
+                                               uint64_t offset) {
+  const Philox4 r = philox4x32(seed, offset, e0 >> 3);
+  v[0] = (r.x & 0xFFFFu) >= thr ? v[0] * dscale : 0.f; v[1] = (r.x >> 16) >= thr ? v[1] * dscale : 0.f;
+  v[2] = (r.y & 0xFFFFu) >= thr ? v[2] * dscale : 0.f; v[3] = (r.y >> 16) >= thr ? v[3] * dscale : 0.f;
+  v[4] = (r.z & 0xFFFFu) >= thr ? v[4] * dscale : 0.f; v[5] = (r.z >> 16) >= thr ? v[5] * dscale : 0.f;
+  v[6] = (r.w & 0xFFFFu) >= thr ? v[6] * dscale : 0.f; v[7] = (r.w >> 16) >= thr ? v[7] * dscale : 0.f;
 }
 
 }  // namespace st5

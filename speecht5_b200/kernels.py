@@ -181,6 +181,18 @@ def attn_bwd(a):
     _count(3)
 
 
+def attn_fused_fwd(a, lse):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_fused_fwd(C.byref(a), _ptr(lse), _stream()), "st5_attn_fused_fwd")
+    _count(1)
+
+def attn_fused_bwd(a, lse, delta, dq_acc):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_fused_bwd(C.byref(a), _ptr(lse), _ptr(delta), _ptr(dq_acc), _stream()), "st5_attn_fused_bwd")
+    _count(2)
+
+
+
 def attn_softmax_fwd(s, qp, key_pad, p, probs_f32, pdrop, B, H, Tq, Tk, p_ld, causal, maxpos, drop_p, seed, offset):
     lib = _lib.load()
     _lib.check(lib.st5_attn_softmax_fwd(_ptr(s), _ptr(qp), qp.shape[-1] if qp is not None else 0, _ptr(key_pad),

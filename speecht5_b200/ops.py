@@ -26,6 +26,8 @@ class Runtime:
         self._static = {}
         self._static_grad = {}  # key -> fp32 view of the trainer's flat gradient buffer (direct accumulation)
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
+        self.attn_fused = True        # bf16 mode, no RPE, Tk <= 320: single-launch fused forward (attention_fused.cu)
+        self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
 
     @property
     def seed(self):
@@ -518,6 +520,41 @@ class AttentionTCFn(torch.autograd.Function):
     dropout-mask convention as AttentionFn (the exact fp32 row-kernel path used for parity mode)."""
 
     @staticmethod
+    def _fused_backward(q_buf, kv_buf, probs, cfg, off, seed, p_ld, same, fused, dout, dprobs):
+        """One launch (+ the row-constant pre-pass): flash-style backward on tcgen05 (attention_fused_bwd.cu)."""
+        out, lse, kp = fused
+        kvb = q_buf if same else kv_buf
+        B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
+        H, d = cfg["H"], cfg["d"]
+        dev = q_buf.device
+        if dout is None:
+            dout = torch.zeros((B, Tq, d), dtype=torch.bfloat16, device=dev)
+        dout = dout.contiguous()
+        qv, kk, vv = AttentionTCFn._views(q_buf, kvb, cfg)
+        full = q_buf.shape[2] == (3 * d if same else d)
+        dq_buf = torch.empty_like(q_buf) if full else torch.zeros_like(q_buf)
+        dkv_buf = dq_buf if same else torch.empty_like(kv_buf)
+        dqv, dkk, dvv = AttentionTCFn._views(dq_buf, dkv_buf, cfg)
+        dpx = None
+        if dprobs is not None:
+            assert probs is not None and probs.dtype == torch.float32, "external dP needs the returned fp32 probabilities"
+            dpx = dprobs
+            if dpx.dtype != torch.float32 or dpx.shape[-1] != p_ld or not dpx.is_contiguous():
+                buf = torch.zeros((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
+                buf[..., :Tk] = dprobs
+                dpx = buf
+        delta = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
+        dq_acc = torch.empty((B, Tq, d), dtype=torch.float32, device=dev)
+        a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)), maxpos=0,
+                        probs_dtype=0, q=qv, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0), k=kk, k_ld=kvb.stride(1),
+                        k_bs=kvb.stride(0), v=vv, v_ld=kvb.stride(1), v_bs=kvb.stride(0), key_pad=kp, pe_k=None,
+                        out=out, o_ld=d, o_bs=Tq * d, probs=probs if dpx is not None else None, p_ld=p_ld,
+                        scale=cfg["scale"], drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout,
+                        dprobs_ext=dpx, ds=None, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
+        K.attn_fused_bwd(a, lse, delta, dq_acc)
+        return dq_buf, (None if same else dkv_buf), None, None, None
+
+    @staticmethod
     def _views(q_buf, kvb, cfg):
         d = cfg["d"]
         return (q_buf.narrow(2, cfg["q_col"] * d, d), kvb.narrow(2, cfg["k_col"] * d, d),
@@ -535,6 +572,31 @@ class AttentionTCFn(torch.autograd.Function):
         qv, kk, vv = AttentionTCFn._views(q_buf, kvb, cfg)
         q_ld, q_bs, kv_ld, kv_bs = q_buf.stride(1), q_buf.stride(0), kvb.stride(1), kvb.stride(0)
         pbs = (Tq * p_ld, H * Tq * p_ld)
+        if pe_k is None and Tk <= 320 and RT.attn_fused:
+            # one launch: QK^T -> masks -> softmax -> dropout -> PV with the scores resident in TMEM
+            drop_p = cfg.get("drop_p", 0.0)
+            off = RT.next_offset() if drop_p > 0 else 0
+            kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+            want = bool(cfg.get("return_probs"))
+            # probabilities leave the chip only when the caller wants them (need_head_weights) or the unfused
+            # backward needs them; the fused backward recomputes P from the log-sum-exp
+            probs = None
+            if want or not RT.attn_fused_bwd:
+                probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32 if want else torch.bfloat16, device=dev)
+            out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
+            lse = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
+            a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
+                            maxpos=0, probs_dtype=K.dtype_id(probs) if probs is not None else 0, q=qv, q_ld=q_ld,
+                            q_bs=q_bs, k=kk, k_ld=kv_ld,
+                            k_bs=kv_bs, v=vv, v_ld=kv_ld, v_bs=kv_bs, key_pad=kp, pe_k=None, out=out, o_ld=d,
+                            o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale, drop_p=drop_p, seed=RT.seed, offset=off)
+            K.attn_fused_fwd(a, lse)
+            ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
+            ctx.fused = (out, lse, kp) if RT.attn_fused_bwd else None
+            ctx.meta = (cfg, off, RT.seed, p_ld, same, None)
+            if probs is None:
+                return out, None
+            return out, probs[..., :Tk] if p_ld != Tk else probs
         S = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev)
         K.gemm(qv, kk, S, M=Tq, N=Tk, K=64, a_ld=q_ld, b_ld=kv_ld, c_ld=p_ld, nb1=H, nb2=B, a_bs=(64, q_bs),
                b_bs=(64, kv_bs), c_bs=pbs, alpha=scale)
@@ -565,6 +627,11 @@ class AttentionTCFn(torch.autograd.Function):
     def backward(ctx, dout, dprobs):
         q_buf, kv_buf, pe_k, P = ctx.saved_tensors
         cfg, off, seed, p_ld, same, pe_hi = ctx.meta
+        fused = getattr(ctx, "fused", None)
+        if fused is not None:
+            return AttentionTCFn._fused_backward(q_buf, kv_buf, P, cfg, off, seed, p_ld, same, fused, dout, dprobs)
+        if P.dtype != torch.bfloat16:  # fused forward returned fp32 probabilities to the caller
+            P = P.to(torch.bfloat16)
         kvb = q_buf if same else kv_buf
         B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
         H, d, scale = cfg["H"], cfg["d"], cfg["scale"]
