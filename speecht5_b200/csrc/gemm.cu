@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include "tma_map.cuh"
 #include <mutex>
+#include <stdlib.h>
+#include <string.h>
 #include <unordered_map>
 
 namespace st5 {
@@ -36,6 +38,7 @@ struct EpiParams {
   int num_k_blocks;
   int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast over that batch dim (stride 0), else 1
   const void* ag_pre; int ag_act;   // optional: multiply by act'(ag_pre[m][n]) (activation backward fused into dX)
+  int tma_store;                    // 1: outputs leave through shared memory + TMA store (maps map_c / map_cpre)
   int tiles_m, tiles_n, num_tiles;  // persistent schedule: tile = (z * tiles_n + n_blk) * tiles_m + m_blk
 };
 
@@ -49,6 +52,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_c,
+                                                                  const __grid_constant__ CUtensorMap map_cpre,
                                                                   const EpiParams p) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
@@ -57,7 +62,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint8_t* stg_all = smem_b + STAGES * B_BYTES;  // EPI_WARPS x 4 KB staging blocks for the TMA-store epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + EPI_WARPS * 4096);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained (epilogue -> MMA)
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     const int q = warp & 3;                      // TMEM lane quarter this warp may read (hardware: warp id % 4)
     constexpr int NGRP = EPI_WARPS / 4;
     const int grp = (warp - 2) >> 2;             // which 32-column chunks this warp owns: c = grp, grp + NGRP, ...
+    uint8_t* stg = stg_all + (warp - 2) * 4096;
     uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
     int local = 0;
@@ -197,21 +204,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
         if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
       }
       const int nb = n0 + c * 32;
-      if (!row_ok || nb >= p.N) continue;
+      if (nb >= p.N) continue;  // warp-uniform; rows beyond M keep going (their loads are guarded, stores clipped)
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
       const bool full = (nb + 32 <= p.N);
-      if (p.accumulate) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
+      if (p.accumulate && row_ok) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
         const float* src = reinterpret_cast<const float*>(p.C) + roff + nb;
+        if (full && ((p.c_ld & 3) == 0) && ((zoff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nb + j < p.N) v[j] += src[j];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 o = *reinterpret_cast<const float4*>(src + j);
+            v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) v[j] += src[j];
+        }
       }
-      if (p.bias != nullptr) {
+      if (p.bias != nullptr) {  // one coalesced 128-byte load per warp, then register shuffles
+        const int jn = nb + (int)lane_id();
+        const float bl = jn < p.N ? __ldg(p.bias + jn) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
       }
       if (bias2_row != nullptr) {
 #pragma unroll
@@ -221,13 +237,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
       const bool vec_ok = full && ((p.c_ld & 7) == 0) && ((zoff & 7) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.C_pre) & 15) == 0);
-      if (p.C_pre != nullptr) {
+      // ---- output path: stage the 32x32 block in shared memory and let TMA write it (coalesced, asynchronous,
+      // clipped at the tensor edges); fall back to per-thread stores when the output layout is not TMA-addressable.
+      auto emit = [&](void* base, const CUtensorMap* tmap) {
+        if (p.tma_store) {
+          if (lane_id() == 0) bulk_wait_read0();  // previous block of this warp has left the staging buffer
+          __syncwarp();
+          const int rr = (int)lane_id();
+          if (p.c_fp32) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(stg + rr * 128 + ((g ^ (rr & 7)) << 4)) =
+                  make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * g], v[8 * g + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * g + 2], v[8 * g + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * g + 4], v[8 * g + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * g + 6], v[8 * g + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(stg + rr * 64 + ((g ^ ((rr >> 1) & 3)) << 4)) = pk;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane_id() == 0) {
+            tma_store_4d(tmap, stg, nb, m0 + q * 32, b1, b2);
+            bulk_commit();
+          }
+          return;
+        }
+        if (!row_ok) return;
         if (p.c_fp32) {
-          float* dst = reinterpret_cast<float*>(p.C_pre) + roff + nb;
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) dst[j] = v[j];
+          float* dst = reinterpret_cast<float*>(base) + roff + nb;
+          if (full && ((p.c_ld & 3) == 0) && ((zoff & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) dst[j] = v[j];
+          }
         } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C_pre) + roff + nb;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base) + roff + nb;
           if (vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -245,7 +300,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
               if (full || nb + j < p.N) dst[j] = __float2bfloat16(v[j]);
           }
         }
-      }
+      };
+      if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
       if (p.act != ACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
@@ -261,7 +317,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
             v[j] = dropout_keep(dseed, doffset, e0 + j, p.drop_thr) ? v[j] * p.drop_scale : 0.f;
         }
       }
-      if (p.ag_pre != nullptr) {
+      if (p.ag_pre != nullptr && row_ok) {
         if (p.c_fp32) {
           const float* pr = reinterpret_cast<const float*>(p.ag_pre) + roff + nb;
           for (int j = 0; j < 32; ++j)
@@ -286,48 +342,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           }
         }
       }
-      if (p.residual != nullptr) {
+      if (p.residual != nullptr && row_ok) {
         if (p.c_fp32) {
           const float* rs = reinterpret_cast<const float*>(p.residual) + roff + nb;
           for (int j = 0; j < 32; ++j)
             if (full || nb + j < p.N) v[j] += rs[j];
         } else {
           const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff + nb;
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) v[j] += __bfloat162float(rs[j]);
-        }
-      }
-      if (p.c_fp32) {
-        float* dst = reinterpret_cast<float*>(p.C) + roff + nb;
-        if (full && ((p.c_ld & 3) == 0) && ((zoff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) dst[j] = v[j];
-        }
-      } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + roff + nb;
-        if (vec_ok) {
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(dst + j) = pk;
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(h[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (full || nb + j < p.N) v[j] += __bfloat162float(rs[j]);
           }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) dst[j] = __float2bfloat16(v[j]);
         }
       }
+      emit(p.C, &map_c);
     }
     }
+    if (p.tma_store && lane_id() == 0) bulk_wait_read0();  // staging buffer must outlive the last bulk store
   }
   tc_fence_before();
   __syncthreads();
@@ -366,6 +409,24 @@ static int num_sms() {
 }
 
 int device_sm_count() { return num_sms(); }
+
+int encode_map_4d(CUtensorMap* map, const void* ptr, int is_f32, const uint64_t dims[4],
+                  const uint64_t strides_bytes[3], const uint32_t box[4], int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -10;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (s[0] & 15) || (s[1] & 15) || (s[2] & 15)) return -11;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), d, s, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -12;
+}
 
 int encode_bf16_map_4d(CUtensorMap* map, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                        const uint32_t box[4]) {
@@ -420,7 +481,8 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
   if (rc) return rc;
   rc = make_operand_map(&mb, g.B, g.b_mn, g.N, g.K, g.b_ld, g.nb1, g.b_bs1, g.nb2, g.b_bs2, BN);
   if (rc) return rc - 10;
-  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * 4096 +
+                          (2 * STAGES + 4) * 8 + 16 + 1024;
   auto kern = gemm_bf16_tcgen05<BN, STAGES, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -434,8 +496,29 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
   const long total = (long)e2.tiles_m * e2.tiles_n * g.nb1 * g.nb2;
   if (total > 0x7fffffffL) return -4;
   e2.num_tiles = (int)total;
+  // Output maps for the TMA-store epilogue: 32x32 element boxes, 64B (bf16) / 128B (fp32) swizzle. Needs 16-byte
+  // aligned bases and row / batch pitches; otherwise the epilogue falls back to per-thread stores.
+  CUtensorMap mc, mcp;
+  memset(&mc, 0, sizeof(mc));
+  memset(&mcp, 0, sizeof(mcp));
+  e2.tma_store = 0;
+  {
+    const long es = g.c_fp32 ? 4 : 2;
+    const bool ok = ((g.c_ld * es) % 16 == 0) && (g.nb1 <= 1 || (g.c_bs1 * es) % 16 == 0) &&
+                    (g.nb2 <= 1 || (g.c_bs2 * es) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) &&
+                    (g.C_pre == nullptr || reinterpret_cast<uintptr_t>(g.C_pre) % 16 == 0);
+    if (ok) {
+      const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.nb1, (uint64_t)g.nb2};
+      const uint64_t strides[3] = {(uint64_t)(g.c_ld * es), (uint64_t)((g.nb1 > 1 ? g.c_bs1 : g.c_ld) * es),
+                                   (uint64_t)((g.nb2 > 1 ? g.c_bs2 : g.c_ld) * es)};
+      const uint32_t box[4] = {32, 32, 1, 1};
+      int r2 = encode_map_4d(&mc, g.C, g.c_fp32, dims, strides, box, g.c_fp32 ? 128 : 64);
+      if (!r2 && g.C_pre != nullptr) r2 = encode_map_4d(&mcp, g.C_pre, g.c_fp32, dims, strides, box, g.c_fp32 ? 128 : 64);
+      e2.tma_store = r2 == 0 ? 1 : 0;
+    }
+  }
   const int grid = (int)(total < num_sms() ? total : num_sms());  // one persistent CTA per SM
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, e2);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, mc, mcp, e2);
   return (int)cudaGetLastError();
 }
 
@@ -475,12 +558,19 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
     const long rounds = (tiles + sms - 1) / sms;
     return (double)rounds * (bn * factor + 24.0);
   };
+  static const int force_bn = [] {  // tuning / profiling knob: ST5_GEMM_BN=64|128|256 pins the tile width
+    const char* e = getenv("ST5_GEMM_BN");
+    return e ? atoi(e) : 0;
+  }();
+  if (force_bn == 256) return launch_major<256, 3>(g, ep, stream);
+  if (force_bn == 128) return launch_major<128, 5>(g, ep, stream);
+  if (force_bn == 64) return launch_major<64, 6>(g, ep, stream);
   const double c256 = g.N > 128 ? cost(256, 1.0) : 1e30;
   const double c128 = g.N > 64 ? cost(128, 1.12) : 1e30;
   const double c64 = cost(64, 1.35);
-  if (c256 <= c128 && c256 <= c64) return launch_major<256, 4>(g, ep, stream);
-  if (c128 <= c64) return launch_major<128, 6>(g, ep, stream);
-  return launch_major<64, 8>(g, ep, stream);
+  if (c256 <= c128 && c256 <= c64) return launch_major<256, 3>(g, ep, stream);
+  if (c128 <= c64) return launch_major<128, 5>(g, ep, stream);
+  return launch_major<64, 6>(g, ep, stream);
 }
 
 }  // namespace st5
