@@ -138,6 +138,15 @@ def run_reference(args, emit=True):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _finish(world):
+    """Multi-rank exit: the captured update graph holds NCCL kernels, and tearing the communicator down under it can
+    block in ncclCommAbort; all timed work is done and synchronised, so leave without running the destructors."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -270,8 +279,7 @@ def main():
     if sampler:
         sampler.stop()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     utt_per_step = B * world
     value = utt_per_step / (ms_dev * 1e-3)
@@ -306,8 +314,7 @@ def main():
         torch.cuda.empty_cache()
         line["cpu_baseline"] = run_reference(args, emit=False)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 if __name__ == "__main__":

@@ -135,6 +135,38 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=None):
+    """dW[n_out, n_in] = gy^T . xin (both operands read MN-major, contraction over the M token rows).
+
+    target != None: accumulate into that fp32 view of the flat gradient buffer and return None; else return a new dW.
+    Small outputs (< half a wave of 128-wide tiles) with a long contraction are split along M into S partial products
+    (the split rides on the GEMM's batch dimension: batch stride = chunk rows) that one column-sum launch reduces, so
+    a 768x768 gradient uses ~8x more SMs than its 36 output tiles would."""
+    dev = gy[0].device
+    tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
+    S = 1
+    if gy[1] is None and xin[1] is None and tiles <= 72 and M >= 2048:
+        for cand in (8, 6, 4, 3, 2):
+            if cand * tiles <= 320 and M % cand == 0:
+                S = cand
+                break
+    if S > 1:
+        chunk = M // S
+        parts = torch.empty((S, n_out, n_in), dtype=torch.float32, device=dev)
+        K.gemm(gy[0], xin[0], parts, M=n_out, N=n_in, K=chunk, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld,
+               c_ld=n_in, nb1=S, nb2=1, a_bs=(chunk * gy_ld, 0), b_bs=(chunk * xin_ld, 0), c_bs=(n_out * n_in, 0))
+        out = target if target is not None else torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
+        K.colsum(parts.view(S, n_out * n_in), out.view(-1), accumulate=target is not None)
+        return None if target is not None else out
+    if target is not None:
+        mm(gy, xin, target, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in,
+           accumulate=True)
+        return None
+    dW = torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
+    mm(gy, xin, dW, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in)
+    return dW
+
+
 # =================================================================================================== Linear
 class LinearFn(torch.autograd.Function):
     """y = dropout(act(x W^T + b (+ rowgroup bias))) (+ residual). W may be several parameters fused along N.
@@ -227,13 +259,10 @@ class LinearFn(torch.autograd.Function):
         # GEMM accumulates straight into it (fused group = one contiguous [N,K] region) and autograd gets None.
         xop = xa if xa is not None else (x2, None)
         gW = RT._static_grad.get(("lin",) + tuple(id(w) for w in weights))
-        if gW is not None:
-            mm(ga, xop, gW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd,
-               accumulate=True)
+        dW = wgrad_mm(ga, dpre_ld, xop, x2.stride(0), N, Kd, M, target=gW)
+        if dW is None:
             grads_w = [None] * len(weights)
         else:
-            dW = torch.empty((N, Kd), dtype=torch.float32, device=dev)
-            mm(ga, xop, dW, M=N, N=Kd, Kd=M, a_mn=True, a_ld=dpre_ld, b_mn=True, b_ld=x2.stride(0), c_ld=Kd)
             grads_w, r0 = [], 0
             for w in weights:
                 grads_w.append(dW[r0:r0 + w.shape[0]].reshape(w.shape))
@@ -326,14 +355,7 @@ class FFNFn(torch.autograd.Function):
         gh = _split(dhp)
 
         def wgrad(gy, gy_ld, xin, xin_ld, w, n_out, n_in):
-            gW = RT._static_grad.get(("lin", id(w)))
-            if gW is not None:
-                mm(gy, xin, gW, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in,
-                   accumulate=True)
-                return None
-            dW = torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
-            mm(gy, xin, dW, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in)
-            return dW
+            return wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=RT._static_grad.get(("lin", id(w))))
 
         def bgrad(gy2d, b):
             gB = RT._static_grad.get(("bias", id(b)))
