@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (full || nb + j < p.N) dst[j] = v[j];
           }
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
               *reinterpret_cast<uint4*>(dst + j) = pk;
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (full || nb + j < p.N) dst[j] = __float2bfloat16(v[j]);
           }
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
       if (p.ag_pre != nullptr && row_ok) {
         if (p.c_fp32) {
           const float* pr = reinterpret_cast<const float*>(p.ag_pre) + roff + nb;
+#pragma unroll
           for (int j = 0; j < 32; ++j)
             if (full || nb + j < p.N) v[j] *= act_grad(pr[j], p.ag_act);
         } else {
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
               }
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (full || nb + j < p.N) v[j] *= act_grad(__bfloat162float(pr[j]), p.ag_act);
           }
@@ -345,6 +349,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
       if (p.residual != nullptr && row_ok) {
         if (p.c_fp32) {
           const float* rs = reinterpret_cast<const float*>(p.residual) + roff + nb;
+#pragma unroll
           for (int j = 0; j < 32; ++j)
             if (full || nb + j < p.N) v[j] += rs[j];
         } else {
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
               }
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (full || nb + j < p.N) v[j] += __bfloat162float(rs[j]);
           }

@@ -76,7 +76,7 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
     _lib.check(lib.st5_gemm_bf16(C.byref(g), _stream()), "st5_gemm_bf16")
     _count(1)
     if GEMM_RECORD is not None:
-        g._keep = (a, b, out, c_pre, bias, bias2, residual)  # keep the operands alive for the replay
+        g._keep = (a, b, out, c_pre, bias, bias2, residual, actgrad_pre)  # keep the operands alive for the replay
         GEMM_RECORD.append(g)
     return out
 

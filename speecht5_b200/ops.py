@@ -400,19 +400,25 @@ class ResidualLayerNormFn(torch.autograd.Function):
         res = residual.contiguous() if residual is not None else None
         K.ln_fwd(x, res, gamma.detach(), beta.detach(), y, s, mean, rstd, eps, drop_p, RT.seed, off)
         ctx.save_for_backward(s, mean, rstd, gamma)
-        ctx.meta = (drop_p, off, RT.seed, residual is not None)
+        ctx.meta = (drop_p, off, RT.seed, residual is not None, id(gamma), id(beta))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         s, mean, rstd, gamma = ctx.saved_tensors
-        drop_p, off, seed, has_res = ctx.meta
+        drop_p, off, seed, has_res, gid, bid = ctx.meta
         dy = dy.contiguous()
         ds = torch.empty_like(dy)
         dx = torch.empty_like(dy) if drop_p > 0 else None
-        dgamma = torch.zeros_like(gamma, dtype=torch.float32)
-        dbeta = torch.zeros_like(gamma, dtype=torch.float32)
+        # the parameter-gradient kernel adds its partial sums atomically: aim it at the flat gradient buffer when the
+        # trainer registered one (zeroed at the start of the update), else at fresh zero vectors handed to autograd
+        gG, gB = RT._static_grad.get(("bias", gid)), RT._static_grad.get(("bias", bid))
+        direct = gG is not None and gB is not None
+        dgamma = gG if direct else torch.zeros_like(gamma, dtype=torch.float32)
+        dbeta = gB if direct else torch.zeros_like(gamma, dtype=torch.float32)
         K.ln_bwd(dy, s, mean, rstd, gamma.detach(), ds, dx, dgamma, dbeta, drop_p, seed, off)
+        if direct:
+            dgamma = dbeta = None
         return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None
 
 

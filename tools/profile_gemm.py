@@ -26,6 +26,9 @@ def run(M, N, Kd, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, **epi):
         kw.update(drop_p=0.1, seed=1, offset=3)
     if epi.get("acc"):
         kw["accumulate"] = True
+    if epi.get("ag"):
+        kw["actgrad_pre"] = torch.randn(M, N, device=dev).to(out_dtype)
+        kw["actgrad_act"] = epi["ag"]
     for _ in range(2):
         K.gemm(A, B, out, M=M, N=N, K=Kd, a_mn=a_mn, b_mn=b_mn, **kw)
     torch.cuda.synchronize()
@@ -34,6 +37,7 @@ def run(M, N, Kd, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, **epi):
 run(10016, 768, 768, bias=True)                          # decoder out_proj forward (plain bias epilogue)
 run(5120, 3072, 768, bias=True, act="gelu", drop=True)   # encoder fc1: GELU + pre-activation store + dropout
 run(5120, 768, 3072, bias=True)                          # encoder fc2
+run(5120, 3072, 768, b_mn=True, drop=True, ag="gelu")    # dH = (dY . W2) * dropmask * gelu'(pre)
 run(768, 768, 10016, a_mn=True, b_mn=True, out_dtype=torch.float32, acc=True)   # dW of a 768x768 projection
 run(3072, 768, 5120, a_mn=True, b_mn=True, out_dtype=torch.float32, acc=True)   # dW of fc1
 run(8192, 8192, 8192)                                     # large square reference point
