@@ -135,14 +135,19 @@ typedef struct st5_attn_args {
 int st5_attn_fwd(const st5_attn_args* args, void* stream);
 int st5_attn_bwd(const st5_attn_args* args, void* stream);
 
-/* Fused tcgen05 attention forward (bf16, no relative-position table, Tk <= 320): QK^T -> masks -> softmax -> dropout
- * -> PV in ONE launch, scores resident in TMEM. Uses the q/k/v/out/probs/key_pad/scale/dropout fields of
- * st5_attn_args exactly like st5_attn_fwd; additionally writes lse[b][h][i] = log sum_j exp(scale*q_i.k_j) (may be
- * NULL). probs (optional) receives the undropped probabilities in probs_dtype. */
+/* Fused tcgen05 attention forward (bf16, Tk <= 320): QK^T -> masks -> softmax -> dropout -> PV in ONE launch, scores
+ * resident in TMEM. Uses the q/k/v/out/probs/key_pad/scale/dropout fields of st5_attn_args exactly like st5_attn_fwd;
+ * additionally writes lse[b][h][i] = log sum_j exp(scale*q_i.k_j) (may be NULL). probs (optional) receives the
+ * undropped probabilities in probs_dtype.
+ * Relative positions (encoder.py:239-246): pe_k != NULL selects the skewed-bias variant; here pe_k must point to a
+ * BF16 copy of the [2*maxpos][64] table, and Tq, Tk <= maxpos <= 160 (clamp(i-j) never clips), no causal mask. */
 int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* stream);
 /* Fused tcgen05 attention backward (flash style: P is recomputed from lse, no Tq x Tk tensor touches HBM). Reads
  * q/k/v, out (forward result), dout, key_pad, dropout fields; optional dprobs_ext (+ the fp32 probs it refers to);
- * writes dq/dk/dv (same layouts as q/k/v). Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats. */
+ * writes dq/dk/dv (same layouts as q/k/v). Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
+ * Relative positions (pe_k != NULL): probs must be the BF16 probabilities st5_attn_fused_fwd saved (read instead of
+ * recomputed; lse may be NULL) and args->ds receives dS as BF16 [B,H,Tq,p_ld] for st5_attn_dqp_scatter and the two
+ * table GEMMs; dq then holds only the q.k part of the gradient. */
 int st5_attn_fused_bwd(const st5_attn_args* args, const float* lse, float* delta, float* dq_acc, void* stream);
 
 /* Tensor-core (bf16) attention path: the contractions run on st5_gemm_bf16 (batched over heads and utterances, q/k/v

@@ -9,8 +9,15 @@
 //   MMA: O[128 x 64] = dropout(P) V   (V consumed as an MN-major B operand: no transpose)  -> TMEM columns [448, 512)
 //   epilogue: O / rowsum -> bf16 -> out[b, i, h*64 : h*64+64]
 //
-// Reference semantics: speecht5/models/modules/multihead_attention.py:340-389 (without the relative-position bias;
-// the RPE encoder layers use the GEMM + row-kernel path of attention_tc.cu). Tk <= 320 (S must fit TMEM next to O).
+// Reference semantics: speecht5/models/modules/multihead_attention.py:340-389. Tk <= 320 (S must fit TMEM next to O).
+//
+// RPE variant (encoder self-attention, encoder.py:239-246 + multihead_attention.py:356-364; Tq, Tk <= maxpos <= 160 so
+// that clamp(i-j) never clips): the bias q_i . pe[i-j+maxpos] is a *skewed* read of QP = Q PE^T. The kernel computes
+//   MMA: QP[128 x 288] = Q PE'^T, PE' = the 288 table rows this query tile can reach -> TMEM columns [160, 448)
+// and every softmax thread pulls its row's 64-column window through a private shared-memory row (conflict-free odd
+// pitch), reads it back reversed and shifted by its lane, adds it to S and parks the sum in TMEM (tcgen05.st) for the
+// second softmax pass. Nothing of size T x T or T x 2*maxpos goes to HBM except the bf16 probabilities the backward
+// pass consumes.
 #include "../../include/speecht5_b200.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -26,6 +33,13 @@ constexpr int FA_MAX_TK = 320;
 constexpr int FA_KBOX = 160;        // K rows per TMA box (two boxes cover 320 keys)
 constexpr uint32_t FA_O_COL = 448;  // TMEM column of the O accumulator (S occupies [0, 320))
 constexpr size_t FA_SMEM = 16384 + 40960 + 40960 + 81920 + 64 + 2048 + 1024;
+// RPE variant: Tk <= 160. Q 16K | K 20K | V 3x8K | PE' 288 rows x 128 B | P 3x16K | 8 warps x (32 rows x 68 floats) staging
+constexpr int FR_MAX_T = 160;
+constexpr int FR_PE_ROWS = 288;
+constexpr uint32_t FR_QP_COL = 160;
+constexpr int FR_STAGE_PITCH = 68;  // floats per staged row: 16-byte aligned, 4*lane mod 32 banks -> conflict-free
+constexpr size_t FR_STAGE_BYTES = 32 * FR_STAGE_PITCH * 4;
+constexpr size_t FR_SMEM = 16384 + 20480 + 24576 + FR_PE_ROWS * 128 + 49152 + 8 * FR_STAGE_BYTES + 64 + 2048 + 1024;
 
 struct FusedFwdParams {
   int B, H, Tq, Tk, causal;
@@ -35,6 +49,7 @@ struct FusedFwdParams {
   float* lse;              // [B][H][Tq] natural-log sum-exp of the scaled scores (for the backward pass)
   void* probs; int probs_fp32; long p_ld;  // optional undropped probabilities [B][H][Tq][p_ld]
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
+  int pe_row0;             // RPE: table row held by PE' row 0 of query tile 0 (= 1 + maxpos - 160; may be negative)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -42,16 +57,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+template <bool RPE>
 __global__ void __launch_bounds__(FA_THREADS, 1)
     attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                          const __grid_constant__ CUtensorMap map_v, const FusedFwdParams p) {
+                          const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_pe,
+                          const FusedFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;             // 128 x 128 B
-  uint8_t* sK = sQ + 16384;       // up to 320 x 128 B (K-major B operand of S)
-  uint8_t* sV = sK + 40960;       // up to 5 blocks of [64 keys][128 B] (MN-major B operand of O)
-  uint8_t* sP = sV + 40960;       // up to 5 blocks of [128 rows][128 B] (K-major A operand of O)
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 81920);
+  uint8_t* sQ = smem;                             // 128 x 128 B
+  uint8_t* sK = sQ + 16384;                       // up to 320 (RPE: 160) x 128 B (K-major B operand of S)
+  uint8_t* sV = sK + (RPE ? 20480 : 40960);       // blocks of [64 keys][128 B] (MN-major B operand of O)
+  uint8_t* sPE = sV + (RPE ? 24576 : 40960);      // RPE only: 288 x 128 B (K-major B operand of QP)
+  uint8_t* sP = sPE + (RPE ? FR_PE_ROWS * 128 : 0);  // blocks of [128 rows][128 B] (K-major A operand of O)
+  uint8_t* sStage = sP + (RPE ? 49152 : 81920);   // RPE only: per-warp window staging
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sStage + (RPE ? 8 * FR_STAGE_BYTES : 0));
   uint64_t* bar_s = bar_load + 1;
   uint64_t* bar_p = bar_load + 2;
   uint64_t* bar_o = bar_load + 3;
@@ -72,6 +91,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
+    if constexpr (RPE) tma_prefetch_desc(&map_pe);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 8);
@@ -91,7 +111,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     // ===================== TMA producer =====================
     if (elect_one()) {
       const int kboxes = n2 > 0 ? 2 : 1;
-      mbar_expect_tx(bar_load, 16384u + (uint32_t)kboxes * (FA_KBOX * 128u) + (uint32_t)nkb * 8192u);
+      mbar_expect_tx(bar_load, 16384u + (uint32_t)kboxes * (FA_KBOX * 128u) + (uint32_t)nkb * 8192u +
+                                   (RPE ? (uint32_t)FR_PE_ROWS * 128u : 0u));
+      if constexpr (RPE) {  // rows outside the table (negative / beyond 2*maxpos) arrive as zeros and are never selected
+        tma_load_4d(sPE, &map_pe, bar_load, 0, p.pe_row0 + i0, 0, 0);
+        tma_load_4d(sPE + 144 * 128, &map_pe, bar_load, 0, p.pe_row0 + i0 + 144, 0, 0);
+      }
       tma_load_4d(sQ, &map_q, bar_load, 0, i0, h, b);
       tma_load_4d(sK, &map_k, bar_load, 0, 0, h, b);
       if (kboxes == 2) tma_load_4d(sK + FA_KBOX * 128, &map_k, bar_load, 0, FA_KBOX, h, b);
@@ -110,6 +135,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         if (n2 > 0)
           umma_bf16(tmem + (uint32_t)n1, da, umma_smem_desc(ak + FA_KBOX * 128 + k * 32, 16, 1024),
                     umma_idesc_bf16(128, n2, 0, 0), k != 0);
+        if constexpr (RPE) {  // QP = Q PE'^T: 288 columns as 160 + 128
+          const uint32_t ape = smem_u32(sPE);
+          umma_bf16(tmem + FR_QP_COL, da, umma_smem_desc(ape + k * 32, 16, 1024), umma_idesc_bf16(128, 160, 0, 0),
+                    k != 0);
+          umma_bf16(tmem + FR_QP_COL + 160, da, umma_smem_desc(ape + 160 * 128 + k * 32, 16, 1024),
+                    umma_idesc_bf16(128, 128, 0, 0), k != 0);
+        }
       }
       umma_commit(bar_s);
     }
@@ -158,15 +190,48 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     tc_fence_after();
     // pass 1: row maximum of the masked, scaled (log2 domain) scores
     float m = -INFINITY;
+#pragma unroll 1
     for (int c = half; c < nchunks; c += 2) {
+      if (RPE && c * 32 >= tk) continue;  // warp-uniform: nothing visible in this chunk (pass 2 masks it by vb == 0)
       uint32_t v[32];
       tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
       const uint32_t vb = valid_bits(c);
-      tmem_ld_wait();
+      if constexpr (RPE) {
+        // row i = i0 + 32q + lane, key j = 32c + u  ->  PE' column (32q - 32c + 128) + (lane + 31 - u)
+        const uint32_t w0c = FR_QP_COL + (uint32_t)(q * 32 - c * 32 + 128);
+        float* st = reinterpret_cast<float*>(sStage + (size_t)(warp - 2) * FR_STAGE_BYTES) +
+                    (int)lane_id() * FR_STAGE_PITCH;
+        {
+          uint32_t w[32];
+          tmem_ld_32x32(trow + w0c, w);
+          tmem_ld_wait();
 #pragma unroll
-      for (int t = 0; t < 32; ++t)
-        if ((vb >> t) & 1u) m = fmaxf(m, __uint_as_float(v[t]) * p.scale_log2);
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(st + 4 * g) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+          tmem_ld_32x32(trow + w0c + 32, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(st + 32 + 4 * g) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+        }
+        __syncwarp();  // (each thread re-reads only its own row; this is the compiler/memory fence)
+        const float* rd = st + (int)lane_id() + 31;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float comb = __uint_as_float(v[t]) + rd[-t];
+          v[t] = __float_as_uint(comb);
+          if ((vb >> t) & 1u) m = fmaxf(m, comb * p.scale_log2);
+        }
+        __syncwarp();
+        tmem_st_32x32(trow + (uint32_t)(c * 32), v);  // S <- S + bias, read back by pass 2 (same warp, same lanes)
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if ((vb >> t) & 1u) m = fmaxf(m, __uint_as_float(v[t]) * p.scale_log2);
+      }
     }
+    if constexpr (RPE) tmem_st_wait();
     red_max[half * 128 + r] = m;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     m = fmaxf(red_max[r], red_max[128 + r]);
@@ -237,13 +302,24 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
               for (int t = 0; t < 32; t += 4)
                 *reinterpret_cast<float4*>(dst + t) = make_float4(pr[t], pr[t + 1], pr[t + 2], pr[t + 3]);
             } else {
+#pragma unroll
               for (int t = 0; t < 32; ++t)
                 if (j0 + t < p.p_ld) dst[t] = pr[t];
             }
           } else {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.probs) + prow * p.p_ld + j0;
-            for (int t = 0; t < 32; ++t)
-              if (j0 + t < p.p_ld) dst[t] = __float2bfloat16(pr[t]);
+            if ((p.p_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(p.probs) & 15) == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (j0 + 8 * g + 8 <= p.p_ld)
+                  *reinterpret_cast<uint4*>(dst + 8 * g) =
+                      make_uint4(pack_bf16(pr[8 * g], pr[8 * g + 1]), pack_bf16(pr[8 * g + 2], pr[8 * g + 3]),
+                                 pack_bf16(pr[8 * g + 4], pr[8 * g + 5]), pack_bf16(pr[8 * g + 6], pr[8 * g + 7]));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (j0 + t < p.p_ld) dst[t] = __float2bfloat16(pr[t]);
+            }
           }
         }
       }
@@ -290,8 +366,11 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, i
 using namespace st5;
 
 extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stream) {
-  if (a->dtype != ST5_BF16 || a->Tk > FA_MAX_TK || a->Tk <= 0 || a->Tq <= 0 || a->pe_k != nullptr)
-    return set_error(-2, "st5_attn_fused_fwd: needs bf16, Tk <= 320, no relative-position table");
+  const bool rpe = a->pe_k != nullptr;
+  if (a->dtype != ST5_BF16 || a->Tk > FA_MAX_TK || a->Tk <= 0 || a->Tq <= 0)
+    return set_error(-2, "st5_attn_fused_fwd: needs bf16 and Tk <= 320");
+  if (rpe && (a->causal || a->maxpos <= 0 || a->maxpos > FR_MAX_T || a->Tk > a->maxpos || a->Tq > a->maxpos))
+    return set_error(-5, "st5_attn_fused_fwd: relative positions need Tq, Tk <= maxpos <= 160 (no clipping), no causal mask");
   if (a->probs != nullptr && a->p_ld < a->Tk) return set_error(-3, "st5_attn_fused_fwd");
   if ((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return set_error(-4, "st5_attn_fused_fwd: out must be 16-byte aligned");
@@ -299,11 +378,20 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stre
   int rc = make_map(&mq, a->q, a->Tq, a->q_ld, a->q_bs, a->H, a->B, FA_BM);
   if (!rc) rc = make_map(&mk, a->k, a->Tk, a->k_ld, a->k_bs, a->H, a->B, FA_KBOX);
   if (!rc) rc = make_map(&mv, a->v, a->Tk, a->v_ld, a->v_bs, a->H, a->B, 64);
+  CUtensorMap mpe = mq;
+  if (!rc && rpe) {  // the bf16 table [2*maxpos][64] as a rank-4 map with unit outer dimensions
+    const uint64_t dims[4] = {64, (uint64_t)(2 * a->maxpos), 1, 1};
+    const uint64_t strides[3] = {128, (uint64_t)(2 * a->maxpos) * 128, (uint64_t)(2 * a->maxpos) * 128};
+    const uint32_t box[4] = {64, 144, 1, 1};
+    rc = encode_bf16_map_4d(&mpe, a->pe_k, dims, strides, box);
+  }
   if (rc) return set_error(rc, "st5_attn_fused_fwd: tensor map");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FA_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM);
     if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_fwd");
     attr_set = true;
   }
@@ -317,7 +405,11 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stre
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.seed = a->seed; p.offset = a->offset;
+  p.pe_row0 = 1 + a->maxpos - FR_MAX_T;
   dim3 grid((a->Tq + FA_BM - 1) / FA_BM, a->H, a->B);
-  attn_fused_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  if (rpe)
+    attn_fused_fwd_kernel<true><<<grid, FA_THREADS, FR_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+  else
+    attn_fused_fwd_kernel<false><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_fwd");
 }

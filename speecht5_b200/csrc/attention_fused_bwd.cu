@@ -9,7 +9,10 @@
 //          dQ_qt(kb) = dS K_kb           (A = dS tile read K-major, B = K_kb tile read MN-major)
 //   threads: dQ partial -> fp32 accumulator in HBM (plain RMW: the CTA owns its (b,h)), bf16 on the last key block;
 //            after the last query tile of a key block: dK_kb, dV_kb -> global.
-// Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389 (no relative-position table).
+// Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389.
+// Relative-position layers (probs_in != null): the forward kernel saved the bf16 probabilities, so P is read instead
+// of recomputed (no S MMA, no bias gather), and dS is also written out (bf16) -- the two table contractions
+// dQ += dQP PE and dPE = dQP^T Q run on the batched GEMM after st5_attn_dqp_scatter.
 #include "../../include/speecht5_b200.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -34,6 +37,8 @@ struct FusedBwdParams {
   __nv_bfloat16* dk; long k_ld, k_bs;
   __nv_bfloat16* dv; long v_ld, v_bs;
   float* dq_acc;  // [B][Tq][H*64] fp32 scratch
+  const __nv_bfloat16* probs_in;  // optional [B][H][Tq][p_ld]: P from the forward pass (instead of exp(S - lse))
+  __nv_bfloat16* ds_out;          // optional [B][H][Tq][p_ld]: dS for the relative-position contractions
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
 };
 
@@ -138,8 +143,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           const uint32_t id = umma_idesc_bf16(128, 128, 0, 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem + FB_COL_S, umma_smem_desc(aQ + k * 32, 16, 1024), umma_smem_desc(aK + k * 32, 16, 1024), id,
-                      k != 0);
+            if (p.probs_in == nullptr)
+              umma_bf16(tmem + FB_COL_S, umma_smem_desc(aQ + k * 32, 16, 1024), umma_smem_desc(aK + k * 32, 16, 1024),
+                        id, k != 0);
             umma_bf16(tmem + FB_COL_DP, umma_smem_desc(adO + k * 32, 16, 1024), umma_smem_desc(aV + k * 32, 16, 1024),
                       id, k != 0);
           }
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const int i = qt * FB_T + r;
         const bool row_ok = i < p.Tq;
         const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
-        const float lse2 = row_ok ? p.lse[prow] * LOG2E : 0.f;
+        const float lse2 = (row_ok && p.lse != nullptr) ? p.lse[prow] * LOG2E : 0.f;
         const float delta = row_ok ? p.delta[prow] : 0.f;
         const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
         mbar_wait(bar_sdp, (uint32_t)(it & 1));
@@ -197,7 +203,24 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 #pragma unroll 1
         for (int c = half * 2; c < half * 2 + 2; ++c) {  // this warp's 64-key half of the block
           uint32_t sv[32], dv[32];
-          tmem_ld_32x32(trow + FB_COL_S + (uint32_t)(c * 32), sv);
+          const int col0 = k0 + c * 32;
+          if (p.probs_in == nullptr) {
+            tmem_ld_32x32(trow + FB_COL_S + (uint32_t)(c * 32), sv);
+          } else {  // saved probabilities: 64 contiguous bytes of this row (zero beyond the row pitch / for dead rows)
+            const __nv_bfloat16* pr = p.probs_in + prow * p.p_ld + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok && col0 + 8 * g + 8 <= p.p_ld) u = __ldg(reinterpret_cast<const uint4*>(pr + 8 * g));
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                sv[8 * g + 2 * e] = __float_as_uint(f.x);
+                sv[8 * g + 2 * e + 1] = __float_as_uint(f.y);
+              }
+            }
+          }
           tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(c * 32), dv);
           // validity bits: key exists and is not padded (one coalesced byte load per lane + ballot), causal, row in range
           const int jl = k0 + c * 32 + (int)lane_id();
@@ -217,7 +240,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           for (int t = 0; t < 32; ++t) {
             float pv = 0.f, dpt = 0.f, pdv = 0.f;
             if ((vb >> t) & 1u) {
-              pv = exp2f(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
+              pv = p.probs_in != nullptr ? __uint_as_float(sv[t])
+                                         : exp2f(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
               const bool keep = (kb_ >> t) & 1u;
               dpt = keep ? __uint_as_float(dv[t]) * p.drop_scale : 0.f;
               pdv = keep ? pv * p.drop_scale : 0.f;
@@ -239,6 +263,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             d.z = pack2(ds[8 * g + 4], ds[8 * g + 5]); d.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
             *reinterpret_cast<uint4*>(bp + sw) = a;
             *reinterpret_cast<uint4*>(bs + sw) = d;
+            if (p.ds_out != nullptr && row_ok && col0 + 8 * g + 8 <= p.p_ld)
+              *reinterpret_cast<uint4*>(p.ds_out + prow * p.p_ld + col0 + 8 * g) = d;
           }
         }
         fence_proxy_async();
@@ -332,11 +358,15 @@ static int make_map128(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld
 using namespace st5;
 
 extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, float* delta, float* dq_acc, void* stream) {
-  if (a->dtype != ST5_BF16 || a->pe_k != nullptr || a->Tk <= 0 || a->Tq <= 0)
-    return set_error(-2, "st5_attn_fused_bwd: needs bf16 and no relative-position table");
+  const bool rpe = a->pe_k != nullptr;
+  if (a->dtype != ST5_BF16 || a->Tk <= 0 || a->Tq <= 0) return set_error(-2, "st5_attn_fused_bwd: needs bf16");
+  if (rpe && (a->probs == nullptr || a->probs_dtype != ST5_BF16 || a->ds == nullptr || a->dprobs_ext != nullptr ||
+              a->causal || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(a->probs) & 15) ||
+              (reinterpret_cast<uintptr_t>(a->ds) & 15)))
+    return set_error(-5, "st5_attn_fused_bwd: relative positions need the saved bf16 probabilities and a dS buffer");
   if (a->dprobs_ext != nullptr && (a->probs == nullptr || a->probs_dtype != ST5_F32 || a->p_ld < a->Tk))
     return set_error(-3, "st5_attn_fused_bwd: dprobs_ext needs the fp32 probabilities");
-  if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || !lse || !delta || !dq_acc)
+  if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || (!lse && !rpe) || !delta || !dq_acc)
     return set_error(-4, "st5_attn_fused_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nrows = (int64_t)a->B * a->H * a->Tq;
@@ -366,6 +396,8 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, floa
   p.dk = (__nv_bfloat16*)a->dk; p.k_ld = a->k_ld; p.k_bs = a->k_bs;
   p.dv = (__nv_bfloat16*)a->dv; p.v_ld = a->v_ld; p.v_bs = a->v_bs;
   p.dq_acc = dq_acc;
+  p.probs_in = rpe ? (const __nv_bfloat16*)a->probs : nullptr;
+  p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.seed = a->seed; p.offset = a->offset;

@@ -185,6 +185,52 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __rest
     atomicAdd(out + g * cols + col, v);
   }
 }
+// Vector variant: a lane owns VEC consecutive columns (one 16-byte load per row), so a warp reads 512 contiguous bytes
+// of every row it visits. Used whenever the layout is 16-byte addressable; also the reduction of split-K partials.
+template <typename T, int VEC>
+__global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows,
+                                  int64_t cols, int64_t group_rows, int64_t rows_per_split) {
+  const int64_t col = ((int64_t)blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int64_t g = blockIdx.y;
+  const int64_t r0 = g * group_rows + (int64_t)blockIdx.z * rows_per_split;
+  int64_t r1 = r0 + rows_per_split;
+  const int64_t gend = (g + 1) * group_rows < rows ? (g + 1) * group_rows : rows;
+  if (r1 > gend) r1 = gend;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (col < cols) {
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ld + col));
+      if constexpr (VEC == 4) {
+        acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y);
+        acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
+      } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+    }
+  }
+  __shared__ float red[8][32 * VEC + 1];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x * VEC + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.y * 32 + threadIdx.x; c < 32 * VEC; c += 256) {
+    const int64_t oc = (int64_t)blockIdx.x * 32 * VEC + c;
+    if (oc < cols) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][c];
+      atomicAdd(out + g * cols + oc, v);
+    }
+  }
+}
 int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows, int64_t cols, int64_t group_rows,
                   int accumulate, cudaStream_t s) {
   if (rows == 0 || cols == 0) return 0;
@@ -194,11 +240,23 @@ int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * groups * cols, s);
     if (e != cudaSuccess) return (int)e;
   }
-  int64_t splits = (group_rows + 255) / 256;
-  if (splits > 64) splits = 64;
+  const int vec = dtype == ST5_F32 ? 4 : 8;
+  const bool vec_ok = (cols % vec == 0) && (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int64_t cw = vec_ok ? 32 * vec : 32;  // columns per block
+  const int64_t col_blocks = (cols + cw - 1) / cw;
+  // enough row splits to fill the machine a few times over, each split at least 64 rows deep
+  int64_t splits = (4 * 148 + col_blocks * groups - 1) / (col_blocks * groups);
+  const int64_t max_splits = (group_rows + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
   const int64_t rps = (group_rows + splits - 1) / splits;
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)groups, (unsigned)splits), block(32, 8);
-  if (dtype == ST5_F32)
+  dim3 grid((unsigned)col_blocks, (unsigned)groups, (unsigned)splits), block(32, 8);
+  if (vec_ok && dtype == ST5_F32)
+    colsum_vec_kernel<float, 4><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
+  else if (vec_ok)
+    colsum_vec_kernel<__nv_bfloat16, 8><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols,
+                                                               group_rows, rps);
+  else if (dtype == ST5_F32)
     colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
   else
     colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols, group_rows, rps);

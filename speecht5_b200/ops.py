@@ -583,6 +583,47 @@ class AttentionTCFn(torch.autograd.Function):
         return dq_buf, (None if same else dkv_buf), None, None, None
 
     @staticmethod
+    def _fused_backward_rpe(q_buf, pe_k, pe_hi, P, cfg, off, seed, p_ld, fused, dout, dprobs):
+        """Relative-position self-attention: the fused kernel (P read back, dS written) + the two table contractions."""
+        assert dprobs is None, "external dP is not supported together with relative positions"
+        out, _, kp = fused
+        B, Tq, _ = q_buf.shape
+        Tk = Tq
+        H, d, scale, maxpos = cfg["H"], cfg["d"], cfg["scale"], cfg["maxpos"]
+        dev = q_buf.device
+        if dout is None:
+            dout = torch.zeros((B, Tq, d), dtype=torch.bfloat16, device=dev)
+        dout = dout.contiguous()
+        qv, kk, vv = AttentionTCFn._views(q_buf, q_buf, cfg)
+        q_ld, q_bs = q_buf.stride(1), q_buf.stride(0)
+        full = q_buf.shape[2] == 3 * d
+        dq_buf = torch.empty_like(q_buf) if full else torch.zeros_like(q_buf)
+        dqv, dkk, dvv = AttentionTCFn._views(dq_buf, dq_buf, cfg)
+        delta = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
+        dq_acc = torch.empty((B, Tq, d), dtype=torch.float32, device=dev)
+        dS = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
+        a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=0, maxpos=maxpos,
+                        probs_dtype=K.dtype_id(P), q=qv, q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=q_ld, k_bs=q_bs, v=vv,
+                        v_ld=q_ld, v_bs=q_bs, key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=P, p_ld=p_ld,
+                        scale=scale, drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout, dprobs_ext=None,
+                        ds=dS, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
+        K.attn_fused_bwd(a, None, delta, dq_acc)
+        R = pe_k.shape[0]
+        dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
+        K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos)
+        qpbs = (Tq * R, H * Tq * R)
+        # dQ += scale dQP PE
+        K.gemm(dQP, pe_hi, dqv, M=Tq, N=64, K=R, a_ld=R, b_mn=True, b_ld=64, c_ld=q_ld, nb1=H, nb2=B, a_bs=qpbs,
+               b_bs=(0, 0), c_bs=(64, q_bs), alpha=scale, residual=dqv)
+        # dPE[r,c] = scale sum_{b,h,i} dQP[b,h,i,r] q[b,i,h,c]
+        parts = torch.empty((B * H, R * 64), dtype=torch.float32, device=dev)
+        K.gemm(dQP, qv, parts, M=R, N=64, K=Tq, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=B,
+               a_bs=qpbs, b_bs=(64, q_bs), c_bs=(R * 64, H * R * 64), alpha=scale)
+        dpe = torch.empty((R, 64), dtype=torch.float32, device=dev)
+        K.colsum(parts, dpe.view(-1))
+        return dq_buf, None, dpe, None, None
+
+    @staticmethod
     def _views(q_buf, kvb, cfg):
         d = cfg["d"]
         return (q_buf.narrow(2, cfg["q_col"] * d, d), kvb.narrow(2, cfg["k_col"] * d, d),
@@ -600,6 +641,28 @@ class AttentionTCFn(torch.autograd.Function):
         qv, kk, vv = AttentionTCFn._views(q_buf, kvb, cfg)
         q_ld, q_bs, kv_ld, kv_bs = q_buf.stride(1), q_buf.stride(0), kvb.stride(1), kvb.stride(0)
         pbs = (Tq * p_ld, H * Tq * p_ld)
+        maxpos = cfg.get("maxpos", 0)
+        rpe_fused = (pe_k is not None and RT.attn_fused and not cfg.get("causal", False) and 0 < maxpos <= 160
+                     and Tq <= maxpos and Tk <= maxpos and pe_k.shape[0] == 2 * maxpos)
+        if rpe_fused:
+            # same single launch with the relative-position bias gathered on chip from QP = Q PE^T (TMEM); the bf16
+            # probabilities are saved for the backward pass (T <= 160: 50 KB per head)
+            drop_p = cfg.get("drop_p", 0.0)
+            off = RT.next_offset() if drop_p > 0 else 0
+            kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+            pe_hi = RT.shadow(("pe", id(pe_k)), lambda: pe_k)[0]
+            P = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
+            out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
+            a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=0, maxpos=maxpos,
+                            probs_dtype=K.dtype_id(P), q=qv, q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=kv_ld, k_bs=kv_bs, v=vv,
+                            v_ld=kv_ld, v_bs=kv_bs, key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=P,
+                            p_ld=p_ld, scale=scale, drop_p=drop_p, seed=RT.seed, offset=off)
+            K.attn_fused_fwd(a, None)
+            ctx.save_for_backward(q_buf, kv_buf, pe_k, P)
+            ctx.fused = (out, None, kp) if RT.attn_fused_bwd else None
+            ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
+            probs = P.float() if cfg.get("return_probs") else P
+            return out, probs[..., :Tk] if p_ld != Tk else probs
         if pe_k is None and Tk <= 320 and RT.attn_fused:
             # one launch: QK^T -> masks -> softmax -> dropout -> PV with the scores resident in TMEM
             drop_p = cfg.get("drop_p", 0.0)
@@ -656,6 +719,8 @@ class AttentionTCFn(torch.autograd.Function):
         q_buf, kv_buf, pe_k, P = ctx.saved_tensors
         cfg, off, seed, p_ld, same, pe_hi = ctx.meta
         fused = getattr(ctx, "fused", None)
+        if fused is not None and pe_k is not None:
+            return AttentionTCFn._fused_backward_rpe(q_buf, pe_k, pe_hi, P, cfg, off, seed, p_ld, fused, dout, dprobs)
         if fused is not None:
             return AttentionTCFn._fused_backward(q_buf, kv_buf, P, cfg, off, seed, p_ld, same, fused, dout, dprobs)
         if P.dtype != torch.bfloat16:  # fused forward returned fp32 probabilities to the caller
