@@ -13,8 +13,9 @@
  *     (allocation failures contain the literal "out of memory", which fairseq/trainer.py:725 greps for);
  *   - `dtype`: ST5_F32 = 0, ST5_BF16 = 1 is the activation storage type; statistics, biases, LayerNorm/BatchNorm
  *     parameters, probabilities returned to the caller and all gradients of parameters are fp32;
- *   - dropout is counter based: keep(i) = philox4x32-10(seed, offset, i/4)[i%4] >= p*2^32 for the element with
- *     linear index i of the logical tensor, so forward and backward regenerate identical masks without storing them.
+ *   - dropout is counter based: one Philox4x32-7(seed, offset, i/8) call yields eight 16-bit lanes; element i is kept
+ *     iff lane i%8 >= p*65536, i = linear index in the logical tensor (attention probabilities: row pitch rounded up
+ *     to a multiple of 32 keys), so forward and backward regenerate identical masks without storing them.
  *     If bit 63 of `offset` is set, `seed` is the device address of a uint64 holding the seed (lets a captured CUDA
  *     graph draw fresh masks on every replay).
  */

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(AT) attn_fwd_row(const st5_attn_args a) {
     if (j < a.Tk) {
       float p = sc[j] * inv;
       if (pout != nullptr) { stf(pout + j, p); p = ldf(pout + j); }
-      if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
+      if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)prow * attn_drop_pitch(a.Tk) + (uint64_t)j, thr) ? p * dscale : 0.f;
       sc[j] = p;
     } else if (pout != nullptr) {
       stf(pout + j, 0.f);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_q_row(const st5_attn_args a) {
       load_row64<T>(vbase + (int64_t)j * a.v_ld, vr);
 #pragma unroll
       for (int c = 0; c < HD; ++c) dp += dO[c] * vr[c];
-      if (thr != 0) dp = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? dp * dscale : 0.f;
+      if (thr != 0) dp = dropout_keep(dseed, doffset, (uint64_t)prow * attn_drop_pitch(a.Tk) + (uint64_t)j, thr) ? dp * dscale : 0.f;
     }
     if (dpe != nullptr) dp += dpe[j];
     dsr[j] = dp;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(AT) attn_bwd_kv_row(const st5_attn_args a) {
     const int64_t prow = bh * a.Tq + i;
     const float ds = a.ds[prow * a.p_ld + j];
     float p = ldf((const PT*)a.probs + prow * a.p_ld + j);
-    if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)(prow * a.Tk + j), thr) ? p * dscale : 0.f;
+    if (thr != 0) p = dropout_keep(dseed, doffset, (uint64_t)prow * attn_drop_pitch(a.Tk) + (uint64_t)j, thr) ? p * dscale : 0.f;
     dk += ds * ldf(qb + (int64_t)i * a.q_ld);
     dv += p * ldf(dob + (int64_t)i * a.o_ld);
   }

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       const uint32_t vb = valid_bits(c);
       uint32_t kb_ = 0xffffffffu;
       if (p.drop_thr != 0)
-        kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * (uint64_t)p.Tk + (uint64_t)(c * 32), p.drop_thr);
+        kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(c * 32), p.drop_thr);
       tmem_ld_wait();
       float e[32];
 #pragma unroll

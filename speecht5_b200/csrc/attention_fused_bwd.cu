@@ -9,6 +9,9 @@
 //          dQ_qt(kb) = dS K_kb           (A = dS tile read K-major, B = K_kb tile read MN-major)
 //   threads: dQ partial -> fp32 accumulator in HBM (plain RMW: the CTA owns its (b,h)), bf16 on the last key block;
 //            after the last query tile of a key block: dK_kb, dV_kb -> global.
+// Software pipeline: Q/dO tiles are double buffered and the compute threads run the element phase of step it BEFORE the
+// dQ/dK/dV read-out of step it-1, so MMA2(it-1) + MMA1(it) + the TMA loads of it+1 overlap the read-out and its HBM
+// round trip instead of sitting on the critical path.
 // Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389.
 // Relative-position layers (probs_in != null): the forward kernel saved the bf16 probabilities, so P is read instead
 // of recomputed (no S MMA, no bias gather), and dS is also written out (bf16) -- the two table contractions
@@ -24,7 +27,7 @@ int set_error(int code, const char* where);
 
 constexpr int FB_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quarter)
 constexpr int FB_T = 128;  // query tile == key block
-constexpr size_t FB_SMEM = 4 * 16384 + 2 * 32768 + 64 + 1024;
+constexpr size_t FB_SMEM = 6 * 16384 + 2 * 32768 + 128 + 1024;
 constexpr uint32_t FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DK = 256, FB_COL_DV = 320, FB_COL_DQ = 384;
 
 struct FusedBwdParams {
@@ -76,17 +79,18 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;             // [128 keys][128 B]
   uint8_t* sV = sK + 16384;
-  uint8_t* sQ = sV + 16384;       // [128 rows][128 B]
-  uint8_t* sdO = sQ + 16384;
-  uint8_t* sPd = sdO + 16384;     // 2 blocks of [128 rows][64 keys]
+  uint8_t* sQ = sV + 16384;       // 2 x [128 rows][128 B]
+  uint8_t* sdO = sQ + 32768;      // 2 x [128 rows][128 B]
+  uint8_t* sPd = sdO + 32768;     // 2 blocks of [128 rows][64 keys]
   uint8_t* sdS = sPd + 32768;
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sdS + 32768);
-  uint64_t* bar_qdo = bar_kv + 1;
-  uint64_t* bar_sdp = bar_kv + 2;
-  uint64_t* bar_pds = bar_kv + 3;
-  uint64_t* bar_mma2 = bar_kv + 4;
-  uint64_t* bar_tdone = bar_kv + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 6);
+  uint64_t* bar_qdo = bar_kv + 1;    // [2] Q/dO buffer filled
+  uint64_t* bar_qfree = bar_kv + 3;  // [2] Q/dO buffer consumed by MMA2
+  uint64_t* bar_sdp = bar_kv + 5;
+  uint64_t* bar_pds = bar_kv + 6;
+  uint64_t* bar_mma2 = bar_kv + 7;
+  uint64_t* bar_tdone = bar_kv + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 9);
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -94,8 +98,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
-    mbar_init(bar_kv, 1); mbar_init(bar_qdo, 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 8);
-    mbar_init(bar_mma2, 1); mbar_init(bar_tdone, 8);
+    mbar_init(bar_kv, 1); mbar_init(&bar_qdo[0], 1); mbar_init(&bar_qdo[1], 1); mbar_init(&bar_qfree[0], 1);
+    mbar_init(&bar_qfree[1], 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 8); mbar_init(bar_mma2, 1);
+    mbar_init(bar_tdone, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -114,21 +119,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       for (int kb = 0; kb < nkb; ++kb) {
         const int qt0 = p.causal ? kb : 0;
         for (int qt = qt0; qt < nqt; ++qt, ++it) {
-          if (it > 0) mbar_wait(bar_mma2, (uint32_t)((it - 1) & 1));  // previous tiles fully consumed by the MMAs
+          const int buf = it & 1;
           if (qt == qt0) {
+            if (it > 0) mbar_wait(bar_mma2, (uint32_t)((it - 1) & 1));  // every MMA of the previous key block is done
             mbar_expect_tx(bar_kv, 32768);
             tma_load_4d(sK, &map_k, bar_kv, 0, kb * FB_T, h, b);
             tma_load_4d(sV, &map_v, bar_kv, 0, kb * FB_T, h, b);
           }
-          mbar_expect_tx(bar_qdo, 32768);
-          tma_load_4d(sQ, &map_q, bar_qdo, 0, qt * FB_T, h, b);
-          tma_load_4d(sdO, &map_do, bar_qdo, 0, qt * FB_T, h, b);
+          if (it >= 2) mbar_wait(&bar_qfree[buf], (uint32_t)(((it >> 1) - 1) & 1));  // MMA2(it-2) has read this buffer
+          mbar_expect_tx(&bar_qdo[buf], 32768);
+          tma_load_4d(sQ + buf * 16384, &map_q, &bar_qdo[buf], 0, qt * FB_T, h, b);
+          tma_load_4d(sdO + buf * 16384, &map_do, &bar_qdo[buf], 0, qt * FB_T, h, b);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO);
     const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
     int it = 0, kbc = 0;
     for (int kb = 0; kb < nkb; ++kb) {
@@ -137,7 +144,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       mbar_wait(bar_kv, (uint32_t)(kbc & 1));
       ++kbc;
       for (int qt = qt0; qt < nqt; ++qt, ++it) {
-        mbar_wait(bar_qdo, (uint32_t)(it & 1));
+        const int buf = it & 1;
+        const uint32_t aQ = aQ0 + (uint32_t)buf * 16384u, adO = adO0 + (uint32_t)buf * 16384u;
+        mbar_wait(&bar_qdo[buf], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         if (elect_one()) {
           const uint32_t id = umma_idesc_bf16(128, 128, 0, 0);
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
                       umma_smem_desc(aK + (blk * 64 + ks * 16) * 128, 16384, 1024), id_q, k != 0);
           }
           umma_commit(bar_mma2);
+          umma_commit(&bar_qfree[buf]);
         }
         __syncwarp();
       }
@@ -187,7 +197,75 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     uint64_t dseed = p.seed, doffset = p.offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
     const float LOG2E = 1.4426950408889634f;
-    int it = 0;
+    // ---- read-out of one finished step: dQ partial of (kb, qt); dK / dV after the last query tile of a key block
+    auto read_out = [&](int kb, int qt, int it) {
+      const int k0 = kb * FB_T;
+      const int i = qt * FB_T + r;
+      const bool row_ok = i < p.Tq;
+      mbar_wait(bar_mma2, (uint32_t)(it & 1));
+      tc_fence_after();
+      const int kb_last = p.causal ? (qt < nkb - 1 ? qt : nkb - 1) : nkb - 1;
+      {
+        const int c = half;  // each warp of the pair takes 32 of the 64 channels
+        uint32_t v[32];
+        tmem_ld_32x32(trow + FB_COL_DQ + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 32;
+          float f[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
+          if (kb > 0) {
+#pragma unroll
+            for (int t = 0; t < 32; t += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(acc + t);
+              f[t] += o.x; f[t + 1] += o.y; f[t + 2] += o.z; f[t + 3] += o.w;
+            }
+          }
+          if (kb == kb_last) {
+            __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 32;
+#pragma unroll
+            for (int t = 0; t < 32; t += 8) {
+              uint4 pk;
+              pk.x = pack2(f[t], f[t + 1]); pk.y = pack2(f[t + 2], f[t + 3]);
+              pk.z = pack2(f[t + 4], f[t + 5]); pk.w = pack2(f[t + 6], f[t + 7]);
+              *reinterpret_cast<uint4*>(dst + t) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; t += 4)
+              *reinterpret_cast<float4*>(acc + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
+          }
+        }
+      }
+      if (qt == nqt - 1) {  // thread = key row
+        const int j = k0 + r;
+#pragma unroll
+        for (int c = half * 2; c < half * 2 + 2; ++c) {  // half 0 writes dK, half 1 writes dV
+          uint32_t v[32];
+          tmem_ld_32x32(trow + (c < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((c & 1) * 32), v);
+          tmem_ld_wait();
+          if (j < p.Tk) {
+            const float sc = c < 2 ? p.scale : 1.f;
+            __nv_bfloat16* dst = (c < 2 ? p.dk + (int64_t)b * p.k_bs + (int64_t)j * p.k_ld
+                                        : p.dv + (int64_t)b * p.v_bs + (int64_t)j * p.v_ld) + h * 64 + (c & 1) * 32;
+#pragma unroll
+            for (int t = 0; t < 32; t += 8) {
+              uint4 pk;
+              pk.x = pack2(__uint_as_float(v[t]) * sc, __uint_as_float(v[t + 1]) * sc);
+              pk.y = pack2(__uint_as_float(v[t + 2]) * sc, __uint_as_float(v[t + 3]) * sc);
+              pk.z = pack2(__uint_as_float(v[t + 4]) * sc, __uint_as_float(v[t + 5]) * sc);
+              pk.w = pack2(__uint_as_float(v[t + 6]) * sc, __uint_as_float(v[t + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + t) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(bar_tdone);
+    };
+    int it = 0, pend_kb = -1, pend_qt = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int qt0 = p.causal ? kb : 0;
       const int k0 = kb * FB_T;
@@ -232,7 +310,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           if (!row_ok) vb = 0u;
           uint32_t kb_ = 0xffffffffu;
           if (p.drop_thr != 0)
-            kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * (uint64_t)p.Tk + (uint64_t)(k0 + c * 32),
+            kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(k0 + c * 32),
                                       p.drop_thr);
           tmem_ld_wait();
           float pd[32], ds[32];
@@ -271,72 +349,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(bar_pds);
-        // ---- dQ partial of this (kb, qt)
-        mbar_wait(bar_mma2, (uint32_t)(it & 1));
-        tc_fence_after();
-        const int kb_last = p.causal ? (qt < nkb - 1 ? qt : nkb - 1) : nkb - 1;
-        {
-          const int c = half;  // each warp of the pair takes 32 of the 64 channels
-          uint32_t v[32];
-          tmem_ld_32x32(trow + FB_COL_DQ + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-          if (row_ok) {
-            float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 32;
-            float f[32];
-#pragma unroll
-            for (int t = 0; t < 32; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
-            if (kb > 0) {
-#pragma unroll
-              for (int t = 0; t < 32; t += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(acc + t);
-                f[t] += o.x; f[t + 1] += o.y; f[t + 2] += o.z; f[t + 3] += o.w;
-              }
-            }
-            if (kb == kb_last) {
-              __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 32;
-#pragma unroll
-              for (int t = 0; t < 32; t += 8) {
-                uint4 pk;
-                pk.x = pack2(f[t], f[t + 1]); pk.y = pack2(f[t + 2], f[t + 3]);
-                pk.z = pack2(f[t + 4], f[t + 5]); pk.w = pack2(f[t + 6], f[t + 7]);
-                *reinterpret_cast<uint4*>(dst + t) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; t += 4)
-                *reinterpret_cast<float4*>(acc + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
-            }
-          }
-        }
-        // ---- dK / dV of this key block after its last query tile (thread = key row)
-        if (qt == nqt - 1) {
-          const int j = k0 + r;
-#pragma unroll
-          for (int c = half * 2; c < half * 2 + 2; ++c) {  // half 0 writes dK, half 1 writes dV
-            uint32_t v[32];
-            tmem_ld_32x32(trow + (c < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((c & 1) * 32), v);
-            tmem_ld_wait();
-            if (j < p.Tk) {
-              const float sc = c < 2 ? p.scale : 1.f;
-              __nv_bfloat16* dst = (c < 2 ? p.dk + (int64_t)b * p.k_bs + (int64_t)j * p.k_ld
-                                          : p.dv + (int64_t)b * p.v_bs + (int64_t)j * p.v_ld) + h * 64 + (c & 1) * 32;
-#pragma unroll
-              for (int t = 0; t < 32; t += 8) {
-                uint4 pk;
-                pk.x = pack2(__uint_as_float(v[t]) * sc, __uint_as_float(v[t + 1]) * sc);
-                pk.y = pack2(__uint_as_float(v[t + 2]) * sc, __uint_as_float(v[t + 3]) * sc);
-                pk.z = pack2(__uint_as_float(v[t + 4]) * sc, __uint_as_float(v[t + 5]) * sc);
-                pk.w = pack2(__uint_as_float(v[t + 6]) * sc, __uint_as_float(v[t + 7]) * sc);
-                *reinterpret_cast<uint4*>(dst + t) = pk;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(bar_tdone);
+        // ---- the previous step's accumulators are read while MMA2 of this step and MMA1 of the next one run
+        if (pend_kb >= 0) read_out(pend_kb, pend_qt, it - 1);
+        pend_kb = kb;
+        pend_qt = qt;
       }
     }
+    if (pend_kb >= 0) read_out(pend_kb, pend_qt, it - 1);
   }
   tc_fence_before();
   __syncthreads();

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
       if (pdrow != nullptr) {
         float pd = __bfloat162float(pb);
         if (thr != 0 && j < Tk)
-          pd = dropout_keep(seed, offset, (uint64_t)(row * Tk + j), thr) ? pd * dscale : 0.f;
+          pd = dropout_keep(seed, offset, (uint64_t)row * attn_drop_pitch(Tk) + (uint64_t)j, thr) ? pd * dscale : 0.f;
         pdrow[j] = __float2bfloat16(pd);
       }
     }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
       d = dprow[j];
       bool keep = true;
       if (thr != 0) {
-        keep = dropout_keep(seed, offset, (uint64_t)(row * Tk + j), thr);
+        keep = dropout_keep(seed, offset, (uint64_t)row * attn_drop_pitch(Tk) + (uint64_t)j, thr);
         d = keep ? d * dscale : 0.f;
       }
       if (Pd != nullptr) Pd[row * p_ld + j] = __float2bfloat16(keep ? p * dscale : 0.f);

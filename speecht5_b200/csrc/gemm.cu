@@ -42,11 +42,26 @@ struct EpiParams {
   int tiles_m, tiles_n, num_tiles;  // persistent schedule: tile = (z * tiles_n + n_blk) * tiles_m + m_blk
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return gelu_fwd(v);
-  if (act == ACT_TANH) return tanhf(v);
-  return v;
+// Activation / activation-derivative over one 32-column chunk with the kind fixed at compile time: the runtime switch
+// sits outside the unrolled element loop (one uniform branch per chunk instead of three per element).
+template <int ACT>
+__device__ __forceinline__ void act_chunk(float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if constexpr (ACT == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+    if constexpr (ACT == ACT_GELU) v[j] = gelu_fwd(v[j]);
+    if constexpr (ACT == ACT_TANH) v[j] = tanhf(v[j]);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ void actgrad8(float* v, const uint4 u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __bfloat1622float2(h[t]);
+    v[2 * t] *= act_grad(f.x, ACT);
+    v[2 * t + 1] *= act_grad(f.y, ACT);
+  }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
@@ -207,7 +222,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
       if (nb >= p.N) continue;  // warp-uniform; rows beyond M keep going (their loads are guarded, stores clipped)
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+      }
       const bool full = (nb + 32 <= p.N);
       if (p.accumulate && row_ok) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
         const float* src = reinterpret_cast<const float*>(p.C) + roff + nb;
@@ -223,11 +242,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
             if (full || nb + j < p.N) v[j] += src[j];
         }
       }
-      if (p.bias != nullptr) {  // one coalesced 128-byte load per warp, then register shuffles
-        const int jn = nb + (int)lane_id();
-        const float bl = jn < p.N ? __ldg(p.bias + jn) : 0.f;
+      if (p.bias != nullptr) {
+        if (full && ((reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0)) {
+          // every lane needs the same 32 values: eight 16-byte loads of one address per warp (L1 broadcast)
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        } else {  // ragged edge: one coalesced load per warp, then register shuffles
+          const int jn = nb + (int)lane_id();
+          const float bl = jn < p.N ? __ldg(p.bias + jn) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+        }
       }
       if (bias2_row != nullptr) {
 #pragma unroll
@@ -304,19 +333,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
         }
       };
       if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
-      if (p.act != ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-      }
+      if (p.act == ACT_GELU) act_chunk<ACT_GELU>(v);
+      else if (p.act == ACT_RELU) act_chunk<ACT_RELU>(v);
+      else if (p.act == ACT_TANH) act_chunk<ACT_TANH>(v);
       if (p.drop_thr != 0) {
         const uint64_t e0 = drop_row + (uint64_t)nb;
         if ((e0 & 7) == 0) {  // aligned: one Philox call per 8 elements
 #pragma unroll
           for (int j = 0; j < 32; j += 8) dropout8_apply(v + j, e0 + j, p.drop_thr, p.drop_scale, dseed, doffset);
-        } else {
+        } else {  // odd row pitch: assemble the 32 keep bits from at most five calls
+          const uint32_t keep = dropout_keep_mask32(dseed, doffset, e0, p.drop_thr);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = dropout_keep(dseed, doffset, e0 + j, p.drop_thr) ? v[j] * p.drop_scale : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop_scale : 0.f;
         }
       }
       if (p.ag_pre != nullptr && row_ok) {
@@ -331,13 +359,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __bfloat1622float2(h[t]);
-                v[j + 2 * t] *= act_grad(f.x, p.ag_act);
-                v[j + 2 * t + 1] *= act_grad(f.y, p.ag_act);
-              }
+              if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
+              else if (p.ag_act == ACT_RELU) actgrad8<ACT_RELU>(v + j, u);
+              else actgrad8<ACT_TANH>(v + j, u);
             }
           } else {
 #pragma unroll

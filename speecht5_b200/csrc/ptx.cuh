@@ -175,7 +175,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn, i
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- counter-based RNG (Philox4x32-10)
+// ---------------------------------------------------------------- counter-based RNG (Philox4x32-7)
+// Seven rounds: the smallest round count of Philox4x32 that passes BigCrush (Salmon et al., SC'11, table 2); dropout
+// needs decorrelated keep decisions, not a cryptographic margin, and the generator sits inside GEMM / attention
+// epilogues where every round is ~8 issue slots per 8 outputs.
+constexpr int PHILOX_ROUNDS = 7;
 struct Philox4 {
   uint32_t x, y, z, w;
 };
@@ -186,7 +190,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t o
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < PHILOX_ROUNDS; ++i) {
     uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
     uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
     uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
@@ -214,6 +218,9 @@ __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t of
   const Philox4 r = philox4x32(seed, offset, i >> 3);
   return philox_lane16(r, (int)(i & 7)) >= thr;
 }
+// Attention probabilities are indexed with a row pitch rounded up to 32 keys, so that every 32-column chunk of a row
+// starts on a Philox group boundary (4 calls per chunk, no ragged head).
+__host__ __device__ __forceinline__ uint64_t attn_drop_pitch(int Tk) { return (uint64_t)((Tk + 31) & ~31); }
 // keep-bits of 32 consecutive elements e0 .. e0+31 (any alignment): at most 5 Philox calls instead of 32
 __device__ __forceinline__ uint32_t dropout_keep_mask32(uint64_t seed, uint64_t offset, uint64_t e0, uint32_t thr) {
   uint32_t mask = 0;
