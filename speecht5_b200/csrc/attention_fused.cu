@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       float e[32];
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
-        const float ev = ((vb >> t) & 1u) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - mm) : 0.f;
+        const float ev = ((vb >> t) & 1u) ? fast_ex2(__uint_as_float(v[t]) * p.scale_log2 - mm) : 0.f;
         sum += ev;
         e[t] = ((kb_ >> t) & 1u) ? ev * p.drop_scale : 0.f;
       }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           tmem_ld_wait();
 #pragma unroll
           for (int t = 0; t < 32; ++t)
-            pr[t] = ((vb >> t) & 1u) ? exp2f(__uint_as_float(v[t]) * p.scale_log2 - mm) * inv : 0.f;
+            pr[t] = ((vb >> t) & 1u) ? fast_ex2(__uint_as_float(v[t]) * p.scale_log2 - mm) * inv : 0.f;
         } else {
 #pragma unroll
           for (int t = 0; t < 32; ++t) pr[t] = 0.f;

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   uint64_t* bar_pds = bar_kv + 6;
   uint64_t* bar_mma2 = bar_kv + 7;
   uint64_t* bar_tdone = bar_kv + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 9);
+  uint64_t* bar_kvfree = bar_kv + 9;  // every MMA that reads this key block's K/V tiles has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 10);
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
     mbar_init(bar_kv, 1); mbar_init(&bar_qdo[0], 1); mbar_init(&bar_qdo[1], 1); mbar_init(&bar_qfree[0], 1);
     mbar_init(&bar_qfree[1], 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 8); mbar_init(bar_mma2, 1);
-    mbar_init(bar_tdone, 8);
+    mbar_init(bar_tdone, 8); mbar_init(bar_kvfree, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -115,13 +116,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int it = 0;
+      // (each barrier is waited on phase by phase, in order: a parity wait on a barrier that is two phases behind
+      // would fall through, so the K/V hand-back has its own barrier instead of sampling bar_mma2)
+      int it = 0, kbc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int qt0 = p.causal ? kb : 0;
         for (int qt = qt0; qt < nqt; ++qt, ++it) {
           const int buf = it & 1;
           if (qt == qt0) {
-            if (it > 0) mbar_wait(bar_mma2, (uint32_t)((it - 1) & 1));  // every MMA of the previous key block is done
+            if (kbc > 0) mbar_wait(bar_kvfree, (uint32_t)((kbc - 1) & 1));  // MMAs of the previous key block are done
+            ++kbc;
             mbar_expect_tx(bar_kv, 32768);
             tma_load_4d(sK, &map_k, bar_kv, 0, kb * FB_T, h, b);
             tma_load_4d(sV, &map_v, bar_kv, 0, kb * FB_T, h, b);
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           }
           umma_commit(bar_mma2);
           umma_commit(&bar_qfree[buf]);
+          if (qt == nqt - 1) umma_commit(bar_kvfree);
         }
         __syncwarp();
       }
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             float pv = 0.f, dpt = 0.f, pdv = 0.f;
             if ((vb >> t) & 1u) {
               pv = p.probs_in != nullptr ? __uint_as_float(sv[t])
-                                         : exp2f(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
+                                         : fast_ex2(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
               const bool keep = (kb_ >> t) & 1u;
               dpt = keep ? __uint_as_float(dv[t]) * p.drop_scale : 0.f;
               pdv = keep ? pv * p.drop_scale : 0.f;

@@ -27,10 +27,23 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 // Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and exp(-x^2 / 2) from ONE exponential (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7):
 // the GELU of the reference (fairseq/modules/gelu.py:24 -> F.gelu, exact erf form) and its derivative share it.
+// MUFU approximations without the denormal fix-up code nvcc wraps around __expf / __fdividef / exp2f (7 extra
+// instructions per call in an epilogue that runs once per output element). Arguments here are never subnormal
+// (rcp: >= 1) or underflow harmlessly to zero (ex2 of a large negative number).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gauss_cdf(float x, float& ex) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  ex = __expf(-z * z);
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
+  ex = fast_ex2(-1.4426950408889634f * z * z);
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
                               0.254829592f);
   const float erf_abs = fmaf(-poly, ex, 1.f);
