@@ -114,7 +114,7 @@ def run_reference(args, emit=True):
         return loss.item()
 
     warm = 1
-    steps = max(1, min(args.steps, 3)) if emit else 2
+    steps = max(1, min(args.steps, 10)) if emit else 8  # ~10-15 s of CPU work: a bounded sample of the same workload
     for _ in range(warm):
         step()
     t0 = time.time()

@@ -27,19 +27,23 @@ namespace st5 {
 
 int set_error(int code, const char* where);
 
-constexpr int FA_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 softmax warps
+// TMA warp, MMA warp, then NG groups of 4 softmax warps (one per TMEM lane quarter); group g owns the 32-column chunks
+// c with c % NG == g. 16 softmax warps (4 per scheduler) hide the MUFU / TMEM-load latencies of the row passes; the
+// RPE variant keeps 8 (its per-warp window staging would not fit shared memory otherwise).
+template <bool RPE> constexpr int fa_groups() { return RPE ? 2 : 4; }
+template <bool RPE> constexpr int fa_threads() { return 64 + fa_groups<RPE>() * 128; }
 constexpr int FA_BM = 128;
 constexpr int FA_MAX_TK = 320;
 constexpr int FA_KBOX = 160;        // K rows per TMA box (two boxes cover 320 keys)
 constexpr uint32_t FA_O_COL = 448;  // TMEM column of the O accumulator (S occupies [0, 320))
-constexpr size_t FA_SMEM = 16384 + 40960 + 40960 + 81920 + 64 + 2048 + 1024;
+constexpr size_t FA_SMEM = 16384 + 40960 + 40960 + 81920 + 64 + 4096 + 1024;
 // RPE variant: Tk <= 160. Q 16K | K 20K | V 3x8K | PE' 288 rows x 128 B | P 3x16K | 8 warps x (32 rows x 68 floats) staging
 constexpr int FR_MAX_T = 160;
 constexpr int FR_PE_ROWS = 288;
 constexpr uint32_t FR_QP_COL = 160;
 constexpr int FR_STAGE_PITCH = 68;  // floats per staged row: 16-byte aligned, 4*lane mod 32 banks -> conflict-free
 constexpr size_t FR_STAGE_BYTES = 32 * FR_STAGE_PITCH * 4;
-constexpr size_t FR_SMEM = 16384 + 20480 + 24576 + FR_PE_ROWS * 128 + 49152 + 8 * FR_STAGE_BYTES + 64 + 2048 + 1024;
+constexpr size_t FR_SMEM = 16384 + 20480 + 24576 + FR_PE_ROWS * 128 + 49152 + 8 * FR_STAGE_BYTES + 64 + 4096 + 1024;
 
 struct FusedFwdParams {
   int B, H, Tq, Tk, causal;
@@ -58,7 +62,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <bool RPE>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(fa_threads<RPE>(), 1)
     attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_pe,
                           const FusedFwdParams p) {
@@ -75,8 +79,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint64_t* bar_p = bar_load + 2;
   uint64_t* bar_o = bar_load + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
-  float* red_max = reinterpret_cast<float*>(bar_load + 6);  // [2][128] partial row maxima of the two column halves
-  float* red_sum = red_max + 256;                            // [2][128] partial row sums
+  constexpr int NG = fa_groups<RPE>();
+  float* red_max = reinterpret_cast<float*>(bar_load + 6);  // [NG][128] partial row maxima of the column groups
+  float* red_sum = red_max + 512;                            // [NG][128] partial row sums
 
   const int warp = threadIdx.x >> 5;
   const int i0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     if constexpr (RPE) tma_prefetch_desc(&map_pe);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 8);
+    mbar_init(bar_p, NG * 4);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   } else {
     // ===================== softmax + epilogue: 8 warps, thread = (query row, half of the 32-column chunks) ========
     const int q = warp & 3;                 // TMEM lane quarter (hardware: warp id % 4)
-    const int half = (warp - 2) >> 2;       // chunks c with (c & 1) == half
+    const int half = (warp - 2) >> 2;       // column group: chunks c with c % NG == half
     const int r = q * 32 + (int)lane_id();  // row within the tile == TMEM lane
     const int i = i0 + r;
     const bool row_ok = i < p.Tq;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     // pass 1: row maximum of the masked, scaled (log2 domain) scores
     float m = -INFINITY;
 #pragma unroll 1
-    for (int c = half; c < nchunks; c += 2) {
+    for (int c = half; c < nchunks; c += NG) {
       if (RPE && c * 32 >= tk) continue;  // warp-uniform: nothing visible in this chunk (pass 2 masks it by vb == 0)
       uint32_t v[32];
       tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
@@ -233,13 +238,15 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     }
     if constexpr (RPE) tmem_st_wait();
     red_max[half * 128 + r] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(red_max[r], red_max[128 + r]);
+    asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
+    m = red_max[r];
+#pragma unroll
+    for (int g = 1; g < NG; ++g) m = fmaxf(m, red_max[g * 128 + r]);
     const float mm = m == -INFINITY ? 0.f : m;
     // pass 2: exponentials, partial row sum, dropout, P -> smem as the K-major SW128 A operand of the PV MMA.
     // The normaliser is applied to O at the end (PV is linear in P).
     float sum = 0.f;
-    for (int c = half; c < nchunks; c += 2) {
+    for (int c = half; c < nchunks; c += NG) {
       uint32_t v[32];
       tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
       const uint32_t vb = valid_bits(c);
@@ -271,15 +278,17 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     __syncwarp();
     if (lane_id() == 0) mbar_arrive(bar_p);
     red_sum[half * 128 + r] = sum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    sum = red_sum[r] + red_sum[128 + r];
+    asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
+    sum = red_sum[r];
+#pragma unroll
+    for (int g = 1; g < NG; ++g) sum += red_sum[g * 128 + r];
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     if (half == 0 && row_ok && p.lse != nullptr)
       p.lse[prow] = (sum > 0.f) ? (mm + log2f(sum)) * 0.6931471805599453f : -INFINITY;
     if (p.probs != nullptr) {
       // normalised, undropped probabilities for the caller (overlaps the PV MMA)
       const int pchunks = (int)((p.p_ld + 31) / 32);
-      for (int c = half; c < pchunks; c += 2) {
+      for (int c = half; c < pchunks; c += NG) {
         float pr[32];
         if (c < nchunks) {
           uint32_t v[32];
@@ -324,10 +333,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         }
       }
     }
-    // epilogue: O / rowsum (each half writes 32 of the 64 channels)
+    // epilogue: O / rowsum (each column group writes 64 / NG of the 64 channels)
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    {
+    if constexpr (NG == 2) {
       const int c = half;
       uint32_t v[32];
       tmem_ld_32x32(trow + FA_O_COL + (uint32_t)(c * 32), v);
@@ -336,6 +345,23 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + c * 32;
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(v[t + 4]) * inv, __uint_as_float(v[t + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(v[t + 6]) * inv, __uint_as_float(v[t + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + t) = pk;
+        }
+      }
+    } else {
+      const int c = half;
+      uint32_t v[16];
+      tmem_ld_32x16(trow + FA_O_COL + (uint32_t)(c * 16), v);
+      tmem_ld_wait();
+      if (row_ok) {
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + c * 16;
+#pragma unroll
+        for (int t = 0; t < 16; t += 8) {
           uint4 pk;
           pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
           pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
@@ -408,8 +434,8 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stre
   p.pe_row0 = 1 + a->maxpos - FR_MAX_T;
   dim3 grid((a->Tq + FA_BM - 1) / FA_BM, a->H, a->B);
   if (rpe)
-    attn_fused_fwd_kernel<true><<<grid, FA_THREADS, FR_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    attn_fused_fwd_kernel<true><<<grid, fa_threads<true>(), FR_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
   else
-    attn_fused_fwd_kernel<false><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    attn_fused_fwd_kernel<false><<<grid, fa_threads<false>(), FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_fwd");
 }

@@ -25,7 +25,8 @@ namespace st5 {
 
 int set_error(int code, const char* where);
 
-constexpr int FB_THREADS = 64 + 256;  // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quarter)
+constexpr int FB_NG = 4;                       // compute warp groups: group g owns 32-key chunk g of the 128-key block
+constexpr int FB_THREADS = 64 + FB_NG * 128;  // TMA warp, MMA warp, 16 compute warps (4 per TMEM lane quarter)
 constexpr int FB_T = 128;  // query tile == key block
 constexpr size_t FB_SMEM = 6 * 16384 + 2 * 32768 + 128 + 1024;
 constexpr uint32_t FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DK = 256, FB_COL_DV = 320, FB_COL_DQ = 384;
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
     mbar_init(bar_kv, 1); mbar_init(&bar_qdo[0], 1); mbar_init(&bar_qdo[1], 1); mbar_init(&bar_qfree[0], 1);
-    mbar_init(&bar_qfree[1], 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, 8); mbar_init(bar_mma2, 1);
-    mbar_init(bar_tdone, 8); mbar_init(bar_kvfree, 1);
+    mbar_init(&bar_qfree[1], 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, FB_NG * 4); mbar_init(bar_mma2, 1);
+    mbar_init(bar_tdone, FB_NG * 4); mbar_init(bar_kvfree, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   } else {
     // ===================== compute threads (thread = query row / key row) =====================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // which 64-key half of the block (and which 32-channel half of dQ / dK|dV) this warp owns
+    const int half = (warp - 2) >> 2;  // column group: 32-key chunk of the block, 16-channel slice of dQ, 32-channel slice of dK|dV
     const int r = q * 32 + (int)lane_id();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint8_t* kp = p.key_pad != nullptr ? p.key_pad + (int64_t)b * p.Tk : nullptr;
@@ -211,26 +212,26 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
       tc_fence_after();
       const int kb_last = p.causal ? (qt < nkb - 1 ? qt : nkb - 1) : nkb - 1;
       {
-        const int c = half;  // each warp of the pair takes 32 of the 64 channels
-        uint32_t v[32];
-        tmem_ld_32x32(trow + FB_COL_DQ + (uint32_t)(c * 32), v);
+        const int c = half;  // each group takes 16 of the 64 channels
+        uint32_t v[16];
+        tmem_ld_32x16(trow + FB_COL_DQ + (uint32_t)(c * 16), v);
         tmem_ld_wait();
         if (row_ok) {
-          float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 32;
-          float f[32];
+          float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 16;
+          float f[16];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
+          for (int t = 0; t < 16; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
           if (kb > 0) {
 #pragma unroll
-            for (int t = 0; t < 32; t += 4) {
+            for (int t = 0; t < 16; t += 4) {
               const float4 o = *reinterpret_cast<const float4*>(acc + t);
               f[t] += o.x; f[t + 1] += o.y; f[t + 2] += o.z; f[t + 3] += o.w;
             }
           }
           if (kb == kb_last) {
-            __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 32;
+            __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 16;
 #pragma unroll
-            for (int t = 0; t < 32; t += 8) {
+            for (int t = 0; t < 16; t += 8) {
               uint4 pk;
               pk.x = pack2(f[t], f[t + 1]); pk.y = pack2(f[t + 2], f[t + 3]);
               pk.z = pack2(f[t + 4], f[t + 5]); pk.w = pack2(f[t + 6], f[t + 7]);
@@ -238,15 +239,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             }
           } else {
 #pragma unroll
-            for (int t = 0; t < 32; t += 4)
+            for (int t = 0; t < 16; t += 4)
               *reinterpret_cast<float4*>(acc + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
           }
         }
       }
       if (qt == nqt - 1) {  // thread = key row
         const int j = k0 + r;
-#pragma unroll
-        for (int c = half * 2; c < half * 2 + 2; ++c) {  // half 0 writes dK, half 1 writes dV
+        {
+          const int c = half;  // groups 0,1 write the two 32-channel halves of dK, groups 2,3 those of dV
           uint32_t v[32];
           tmem_ld_32x32(trow + (c < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((c & 1) * 32), v);
           tmem_ld_wait();
@@ -283,8 +284,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
         const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
         mbar_wait(bar_sdp, (uint32_t)(it & 1));
         tc_fence_after();
-#pragma unroll 1
-        for (int c = half * 2; c < half * 2 + 2; ++c) {  // this warp's 64-key half of the block
+        {
+          const int c = half;  // this warp's 32-key chunk of the block
           uint32_t sv[32], dv[32];
           const int col0 = k0 + c * 32;
           if (p.probs_in == nullptr) {

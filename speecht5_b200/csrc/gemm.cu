@@ -111,6 +111,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above touched only this CTA's shared / tensor memory, so it may run
+  // while the preceding grid drains. Wait for that grid's memory here, before the first global access, and let the
+  // grid behind us start its own prologue (both are no-ops when the launch carries no programmatic attribute).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -548,7 +553,22 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
     }
   }
   const int grid = (int)(total < num_sms() ? total : num_sms());  // one persistent CTA per SM
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, mc, mcp, e2);
+  static const bool pdl = [] {
+    const char* e = getenv("ST5_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mcp, e2);
+  if (le != cudaSuccess) return (int)le;
   return (int)cudaGetLastError();
 }
 
