@@ -74,33 +74,36 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
   uint8_t* sPE = sV + (RPE ? 24576 : 40960);      // RPE only: 288 x 128 B (K-major B operand of QP)
   uint8_t* sP = sPE + (RPE ? FR_PE_ROWS * 128 : 0);  // blocks of [128 rows][128 B] (K-major A operand of O)
   uint8_t* sStage = sP + (RPE ? 49152 : 81920);   // RPE only: per-warp window staging
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sStage + (RPE ? 8 * FR_STAGE_BYTES : 0));
-  uint64_t* bar_s = bar_load + 1;
-  uint64_t* bar_p = bar_load + 2;
-  uint64_t* bar_o = bar_load + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+  // One CTA = one (head, utterance); it walks the query tiles with K / V resident. Barrier phases count query tiles.
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sStage + (RPE ? 8 * FR_STAGE_BYTES : 0));  // K, V landed (once)
+  uint64_t* bar_q = bar_kv + 1;      // Q (+ PE') tile landed
+  uint64_t* bar_s = bar_kv + 2;      // S (+ QP) MMAs complete  (=> sQ / sPE may be refilled)
+  uint64_t* bar_p = bar_kv + 3;      // P in shared memory
+  uint64_t* bar_sfree = bar_kv + 4;  // last read of S done (probabilities written)  (=> next S MMA may start)
+  uint64_t* bar_o = bar_kv + 5;      // PV MMA complete  (=> sP may be rewritten)
+  uint64_t* bar_ofree = bar_kv + 6;  // O read out  (=> next PV MMA may start)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 7);
   constexpr int NG = fa_groups<RPE>();
-  float* red_max = reinterpret_cast<float*>(bar_load + 6);  // [NG][128] partial row maxima of the column groups
-  float* red_sum = red_max + 512;                            // [NG][128] partial row sums
+  float* red_max = reinterpret_cast<float*>(bar_kv + 8);  // [NG][128] partial row maxima of the column groups
+  float* red_sum = red_max + 512;                          // [NG][128] partial row sums
 
   const int warp = threadIdx.x >> 5;
-  const int i0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
-  int tk = p.Tk;  // keys this query tile can see
-  if (p.causal && i0 + FA_BM < tk) tk = i0 + FA_BM;
-  const int tk16 = (tk + 15) & ~15;
-  const int nkb = (tk + 63) >> 6;
-  const int n1 = tk16 > FA_KBOX ? FA_KBOX : tk16;  // S is issued as one or two MMAs
-  const int n2 = tk16 - n1;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nqt = (p.Tq + FA_BM - 1) / FA_BM;
+  const int nkb_all = (p.Tk + 63) >> 6;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     if constexpr (RPE) tma_prefetch_desc(&map_pe);
-    mbar_init(bar_load, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, NG * 4);
+    mbar_init(bar_sfree, NG * 4);
     mbar_init(bar_o, 1);
+    mbar_init(bar_ofree, NG * 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -115,70 +118,118 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const int kboxes = n2 > 0 ? 2 : 1;
-      mbar_expect_tx(bar_load, 16384u + (uint32_t)kboxes * (FA_KBOX * 128u) + (uint32_t)nkb * 8192u +
-                                   (RPE ? (uint32_t)FR_PE_ROWS * 128u : 0u));
-      if constexpr (RPE) {  // rows outside the table (negative / beyond 2*maxpos) arrive as zeros and are never selected
-        tma_load_4d(sPE, &map_pe, bar_load, 0, p.pe_row0 + i0, 0, 0);
-        tma_load_4d(sPE + 144 * 128, &map_pe, bar_load, 0, p.pe_row0 + i0 + 144, 0, 0);
+      const int kboxes = ((p.Tk + 15) & ~15) > FA_KBOX ? 2 : 1;
+      mbar_expect_tx(bar_kv, (uint32_t)kboxes * (FA_KBOX * 128u) + (uint32_t)nkb_all * 8192u);
+      tma_load_4d(sK, &map_k, bar_kv, 0, 0, h, b);
+      if (kboxes == 2) tma_load_4d(sK + FA_KBOX * 128, &map_k, bar_kv, 0, FA_KBOX, h, b);
+      for (int kb = 0; kb < nkb_all; ++kb) tma_load_4d(sV + kb * 8192, &map_v, bar_kv, 0, kb * 64, h, b);
+      for (int n = 0; n < nqt; ++n) {
+        if (n > 0) mbar_wait(bar_s, (uint32_t)((n - 1) & 1));  // the MMAs that read sQ / sPE have completed
+        mbar_expect_tx(bar_q, 16384u + (RPE ? (uint32_t)FR_PE_ROWS * 128u : 0u));
+        if constexpr (RPE) {  // rows outside the table (negative / beyond 2*maxpos) arrive as zeros, never selected
+          tma_load_4d(sPE, &map_pe, bar_q, 0, p.pe_row0 + n * FA_BM, 0, 0);
+          tma_load_4d(sPE + 144 * 128, &map_pe, bar_q, 0, p.pe_row0 + n * FA_BM + 144, 0, 0);
+        }
+        tma_load_4d(sQ, &map_q, bar_q, 0, n * FA_BM, h, b);
       }
-      tma_load_4d(sQ, &map_q, bar_load, 0, i0, h, b);
-      tma_load_4d(sK, &map_k, bar_load, 0, 0, h, b);
-      if (kboxes == 2) tma_load_4d(sK + FA_KBOX * 128, &map_k, bar_load, 0, FA_KBOX, h, b);
-      for (int kb = 0; kb < nkb; ++kb) tma_load_4d(sV + kb * 8192, &map_v, bar_load, 0, kb * 64, h, b);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    mbar_wait(bar_load, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+    mbar_wait(bar_kv, 0);
+    for (int n = 0; n < nqt; ++n) {
+      int tk = p.Tk;  // keys this query tile can see
+      if (p.causal && n * FA_BM + FA_BM < tk) tk = n * FA_BM + FA_BM;
+      const int tk16 = (tk + 15) & ~15;
+      const int nkb = (tk + 63) >> 6;
+      const int n1 = tk16 > FA_KBOX ? FA_KBOX : tk16;  // S is issued as one or two MMAs
+      const int n2 = tk16 - n1;
+      mbar_wait(bar_q, (uint32_t)(n & 1));
+      if (n > 0) mbar_wait(bar_sfree, (uint32_t)((n - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {  // head dim 64 = 4 x UMMA_K
-        const uint64_t da = umma_smem_desc(aq + k * 32, 16, 1024);
-        umma_bf16(tmem, da, umma_smem_desc(ak + k * 32, 16, 1024), umma_idesc_bf16(128, n1, 0, 0), k != 0);
-        if (n2 > 0)
-          umma_bf16(tmem + (uint32_t)n1, da, umma_smem_desc(ak + FA_KBOX * 128 + k * 32, 16, 1024),
-                    umma_idesc_bf16(128, n2, 0, 0), k != 0);
-        if constexpr (RPE) {  // QP = Q PE'^T: 288 columns as 160 + 128
-          const uint32_t ape = smem_u32(sPE);
-          umma_bf16(tmem + FR_QP_COL, da, umma_smem_desc(ape + k * 32, 16, 1024), umma_idesc_bf16(128, 160, 0, 0),
-                    k != 0);
-          umma_bf16(tmem + FR_QP_COL + 160, da, umma_smem_desc(ape + 160 * 128 + k * 32, 16, 1024),
-                    umma_idesc_bf16(128, 128, 0, 0), k != 0);
+        for (int k = 0; k < 4; ++k) {  // head dim 64 = 4 x UMMA_K
+          const uint64_t da = umma_smem_desc(aq + k * 32, 16, 1024);
+          umma_bf16(tmem, da, umma_smem_desc(ak + k * 32, 16, 1024), umma_idesc_bf16(128, n1, 0, 0), k != 0);
+          if (n2 > 0)
+            umma_bf16(tmem + (uint32_t)n1, da, umma_smem_desc(ak + FA_KBOX * 128 + k * 32, 16, 1024),
+                      umma_idesc_bf16(128, n2, 0, 0), k != 0);
+          if constexpr (RPE) {  // QP = Q PE'^T: 288 columns as 160 + 128
+            const uint32_t ape = smem_u32(sPE);
+            umma_bf16(tmem + FR_QP_COL, da, umma_smem_desc(ape + k * 32, 16, 1024), umma_idesc_bf16(128, 160, 0, 0),
+                      k != 0);
+            umma_bf16(tmem + FR_QP_COL + 160, da, umma_smem_desc(ape + 160 * 128 + k * 32, 16, 1024),
+                      umma_idesc_bf16(128, 128, 0, 0), k != 0);
+          }
         }
+        umma_commit(bar_s);
       }
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_p, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
-      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
-      for (int kb = 0; kb < nkb; ++kb) {
+      __syncwarp();
+      mbar_wait(bar_p, (uint32_t)(n & 1));
+      if (n > 0) mbar_wait(bar_ofree, (uint32_t)((n - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+        const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+        for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 64 keys = 4 x UMMA_K
-          const uint64_t da = umma_smem_desc(ap + kb * 16384 + k * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(av + kb * 8192 + k * 2048, 8192, 1024);
-          umma_bf16(tmem + FA_O_COL, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {  // 64 keys = 4 x UMMA_K
+            const uint64_t da = umma_smem_desc(ap + kb * 16384 + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(av + kb * 8192 + k * 2048, 8192, 1024);
+            umma_bf16(tmem + FA_O_COL, da, db, idesc, (kb | k) != 0);
+          }
         }
+        umma_commit(bar_o);
       }
-      umma_commit(bar_o);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ===================== softmax + epilogue: 8 warps, thread = (query row, half of the 32-column chunks) ========
+    // ===================== softmax + epilogue: NG x 4 warps, thread = (query row, every NG-th 32-column chunk) =====
     const int q = warp & 3;                 // TMEM lane quarter (hardware: warp id % 4)
     const int half = (warp - 2) >> 2;       // column group: chunks c with c % NG == half
     const int r = q * 32 + (int)lane_id();  // row within the tile == TMEM lane
-    const int i = i0 + r;
-    const bool row_ok = i < p.Tq;
-    const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
     const uint8_t* kp = p.key_pad != nullptr ? p.key_pad + (int64_t)b * p.Tk : nullptr;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint64_t dseed = p.seed, doffset = p.offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
+    // O / rowsum of a finished tile (each column group writes 64 / NG of the 64 channels). Deferred by one tile so the
+    // PV MMA and the next S MMA run under the first softmax pass of the following tile.
+    auto epilogue = [&](int n, float inv) {
+      const int i = n * FA_BM + r;
+      const bool row_ok = i < p.Tq;
+      mbar_wait(bar_o, (uint32_t)(n & 1));
+      tc_fence_after();
+      constexpr int CW = 64 / NG;
+      uint32_t v[CW];
+      if constexpr (NG == 2) tmem_ld_32x32(trow + FA_O_COL + (uint32_t)(half * CW), v);
+      else tmem_ld_32x16(trow + FA_O_COL + (uint32_t)(half * CW), v);
+      tmem_ld_wait();
+      if (row_ok) {
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + half * CW;
+#pragma unroll
+        for (int t = 0; t < CW; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(v[t + 4]) * inv, __uint_as_float(v[t + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(v[t + 6]) * inv, __uint_as_float(v[t + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + t) = pk;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(bar_ofree);
+    };
+    float inv_prev = 0.f;
+    for (int n = 0; n < nqt; ++n) {
+    const int i0 = n * FA_BM;
+    int tk = p.Tk;
+    if (p.causal && i0 + FA_BM < tk) tk = i0 + FA_BM;
+    const int nkb = (tk + 63) >> 6;
+    const int i = i0 + r;
+    const bool row_ok = i < p.Tq;
+    const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
     const int nchunks = nkb * 2;  // 32-column chunks (TMEM columns beyond tk16 hold garbage and are masked)
     // validity bits of chunk c for THIS row: key exists, not padded (one coalesced byte load per lane + ballot), causal
     auto valid_bits = [&](int c) -> uint32_t {
@@ -191,7 +242,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       }
       return m;
     };
-    mbar_wait(bar_s, 0);
+    mbar_wait(bar_s, (uint32_t)(n & 1));
     tc_fence_after();
     // pass 1: row maximum of the masked, scaled (log2 domain) scores
     float m = -INFINITY;
@@ -243,6 +294,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
 #pragma unroll
     for (int g = 1; g < NG; ++g) m = fmaxf(m, red_max[g * 128 + r]);
     const float mm = m == -INFINITY ? 0.f : m;
+    if (n > 0) epilogue(n - 1, inv_prev);  // (waits for PV(n-1): sP is free again after this)
     // pass 2: exponentials, partial row sum, dropout, P -> smem as the K-major SW128 A operand of the PV MMA.
     // The normaliser is applied to O at the end (PV is linear in P).
     float sum = 0.f;
@@ -333,44 +385,12 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
         }
       }
     }
-    // epilogue: O / rowsum (each column group writes 64 / NG of the 64 channels)
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    if constexpr (NG == 2) {
-      const int c = half;
-      uint32_t v[32];
-      tmem_ld_32x32(trow + FA_O_COL + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      if (row_ok) {
-        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + c * 32;
-#pragma unroll
-        for (int t = 0; t < 32; t += 8) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
-          pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
-          pk.z = pack_bf16(__uint_as_float(v[t + 4]) * inv, __uint_as_float(v[t + 5]) * inv);
-          pk.w = pack_bf16(__uint_as_float(v[t + 6]) * inv, __uint_as_float(v[t + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + t) = pk;
-        }
-      }
-    } else {
-      const int c = half;
-      uint32_t v[16];
-      tmem_ld_32x16(trow + FA_O_COL + (uint32_t)(c * 16), v);
-      tmem_ld_wait();
-      if (row_ok) {
-        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + c * 16;
-#pragma unroll
-        for (int t = 0; t < 16; t += 8) {
-          uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv);
-          pk.y = pack_bf16(__uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
-          pk.z = pack_bf16(__uint_as_float(v[t + 4]) * inv, __uint_as_float(v[t + 5]) * inv);
-          pk.w = pack_bf16(__uint_as_float(v[t + 6]) * inv, __uint_as_float(v[t + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + t) = pk;
-        }
-      }
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(bar_sfree);
+    inv_prev = inv;
     }
+    epilogue(nqt - 1, inv_prev);
   }
   tc_fence_before();
   __syncthreads();
@@ -432,7 +452,7 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stre
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.seed = a->seed; p.offset = a->offset;
   p.pe_row0 = 1 + a->maxpos - FR_MAX_T;
-  dim3 grid((a->Tq + FA_BM - 1) / FA_BM, a->H, a->B);
+  dim3 grid(a->H, a->B);  // one persistent CTA per (head, utterance)
   if (rpe)
     attn_fused_fwd_kernel<true><<<grid, fa_threads<true>(), FR_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
   else

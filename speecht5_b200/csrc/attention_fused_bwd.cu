@@ -51,23 +51,46 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// delta[row] = sum_c dO*O (+ sum_j P*dP_ext): the softmax-backward row constant. One warp per (b,h,i).
+// delta[row] = sum_c dO*O (+ sum_j P*dP_ext): the softmax-backward row constant.
+// Plain case: 8 lanes per (b,h,i) row (one 16-byte load of dO and O each), 4 rows per warp. With an external dP the
+// row also needs sum_j P*dP_ext over Tk fp32 pairs: one warp per row.
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, long o_ld,
                                   long o_bs, const float* __restrict__ probs, const float* __restrict__ dpx, long p_ld,
                                   float* __restrict__ delta, int B, int H, int Tq, int Tk) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= (int64_t)B * H * Tq) return;
+  const int64_t nrows = (int64_t)B * H * Tq;
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (dpx == nullptr) {
+    const int64_t row = gw * 4 + (lane >> 3);
+    float acc = 0.f;
+    if (row < nrows) {
+      const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
+      const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + (lane & 7) * 8;
+      const uint4 ua = *reinterpret_cast<const uint4*>(dO + off), uo = *reinterpret_cast<const uint4*>(O + off);
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+      const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 a = __bfloat1622float2(ha[t]), o = __bfloat1622float2(ho[t]);
+        acc += a.x * o.x + a.y * o.y;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if ((lane & 7) == 0 && row < nrows) delta[row] = acc;
+    return;
+  }
+  const int64_t row = gw;
+  if (row >= nrows) return;
   const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
   const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + lane * 2;
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
   const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
   float acc = a.x * o.x + a.y * o.y;
-  if (dpx != nullptr) {
-    const float* pr = probs + row * p_ld;
-    const float* dx = dpx + row * p_ld;
-    for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
-  }
+  const float* pr = probs + row * p_ld;
+  const float* dx = dpx + row * p_ld;
+  for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
   acc = warp_sum(acc);
   if (lane == 0) delta[row] = acc;
 }
@@ -395,7 +418,12 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, floa
     return set_error(-4, "st5_attn_fused_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nrows = (int64_t)a->B * a->H * a->Tq;
-  attn_delta_kernel<<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(
+  const bool ext = a->dprobs_ext != nullptr;
+  if (!ext && ((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->dout) & 15) ||
+               (reinterpret_cast<uintptr_t>(a->out) & 15)))
+    return set_error(-4, "st5_attn_fused_bwd: out / dout must be 16-byte aligned");
+  const int64_t warps_needed = ext ? nrows : (nrows + 3) / 4;
+  attn_delta_kernel<<<(unsigned)((warps_needed + 7) / 8), 256, 0, s>>>(
       (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, a->o_ld, a->o_bs,
       a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk);
   cudaError_t e = cudaGetLastError();
