@@ -342,20 +342,40 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(k0 + c * 32),
                                       p.drop_thr);
           tmem_ld_wait();
+          // dP as seen by the softmax: dropout backward of dO V^T, plus the caller's gradient on the probabilities
+          // (this row's 32 floats = one 128-byte line, fetched as eight 16-byte loads)
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            dv[t] = ((kb_ >> t) & 1u) ? __float_as_uint(__uint_as_float(dv[t]) * p.drop_scale) : 0u;
+          if (dpx != nullptr) {
+            if ((p.p_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dp_ext) & 15) == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (col0 + 4 * g + 4 <= p.p_ld) {
+                  const float4 x = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 4 * g));
+                  dv[4 * g] = __float_as_uint(__uint_as_float(dv[4 * g]) + x.x);
+                  dv[4 * g + 1] = __float_as_uint(__uint_as_float(dv[4 * g + 1]) + x.y);
+                  dv[4 * g + 2] = __float_as_uint(__uint_as_float(dv[4 * g + 2]) + x.z);
+                  dv[4 * g + 3] = __float_as_uint(__uint_as_float(dv[4 * g + 3]) + x.w);
+                }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (col0 + t < p.Tk) dv[t] = __float_as_uint(__uint_as_float(dv[t]) + dpx[col0 + t]);
+            }
+          }
           float pd[32], ds[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            float pv = 0.f, dpt = 0.f, pdv = 0.f;
+            float pdv = 0.f, dsv = 0.f;  // (columns outside the mask may hold non-finite TMEM garbage: never multiply them)
             if ((vb >> t) & 1u) {
-              pv = p.probs_in != nullptr ? __uint_as_float(sv[t])
-                                         : fast_ex2(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
-              const bool keep = (kb_ >> t) & 1u;
-              dpt = keep ? __uint_as_float(dv[t]) * p.drop_scale : 0.f;
-              pdv = keep ? pv * p.drop_scale : 0.f;
-              if (dpx != nullptr) dpt += dpx[k0 + c * 32 + t];
+              const float pv = p.probs_in != nullptr ? __uint_as_float(sv[t])
+                                                     : fast_ex2(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
+              pdv = ((kb_ >> t) & 1u) ? pv * p.drop_scale : 0.f;
+              dsv = pv * (__uint_as_float(dv[t]) - delta);
             }
             pd[t] = pdv;
-            ds[t] = pv * (dpt - delta);
+            ds[t] = dsv;
           }
           uint8_t* bp = sPd + (c >> 1) * 16384 + r * 128;
           uint8_t* bs = sdS + (c >> 1) * 16384 + r * 128;
