@@ -32,6 +32,7 @@ extern "C" {
 #define ST5_ACT_RELU 1
 #define ST5_ACT_GELU 2
 #define ST5_ACT_TANH 3
+#define ST5_ACT_GELU_TANH 4 /* tanh-form GELU on the MUFU unit: |error| <= 4.8e-4 vs the erf form; bf16 throughput mode */
 
 int st5_version(void);
 const char* st5_last_error(void);

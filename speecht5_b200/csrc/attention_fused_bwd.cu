@@ -1,21 +1,19 @@
-// Fused attention backward on tcgen05 (flash-style: probabilities are recomputed from the saved log-sum-exp, nothing of
-// size Tq x Tk is read from or written to HBM except the optional external dP of the guided-attention loss).
+// Fused attention backward on tcgen05. The probabilities come from the forward pass (bf16, or the fp32 copy returned
+// to the caller), so one step needs a single score-sized MMA and the schedule can be fully overlapped.
 //
-// One CTA per (head, utterance). Loop: key block kb (128 keys) outer, query tile qt (128 rows) inner:
-//   MMA1   S  = Q_qt K_kb^T  -> TMEM[0,128)        dP = dO_qt V_kb^T -> TMEM[128,256)
-//   threads (1 thread = 1 query row): P = exp(scale*S - lse), dropout mask, dS = P * (dP_masked + dP_ext - delta);
-//            dropout(P) and dS -> shared memory (bf16, 128B-swizzled [q][key] tiles)
-//   MMA2   dV_kb += dropout(P)^T dO_qt   dK_kb += dS^T Q_qt      (A operands = the SAME smem tiles read MN-major)
-//          dQ_qt(kb) = dS K_kb           (A = dS tile read K-major, B = K_kb tile read MN-major)
-//   threads: dQ partial -> fp32 accumulator in HBM (plain RMW: the CTA owns its (b,h)), bf16 on the last key block;
-//            after the last query tile of a key block: dK_kb, dV_kb -> global.
-// Software pipeline: Q/dO tiles are double buffered and the compute threads run the element phase of step it BEFORE the
-// dQ/dK/dV read-out of step it-1, so MMA2(it-1) + MMA1(it) + the TMA loads of it+1 overlap the read-out and its HBM
-// round trip instead of sitting on the critical path.
-// Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389.
-// Relative-position layers (probs_in != null): the forward kernel saved the bf16 probabilities, so P is read instead
-// of recomputed (no S MMA, no bias gather), and dS is also written out (bf16) -- the two table contractions
-// dQ += dQP PE and dPE = dQP^T Q run on the batched GEMM after st5_attn_dqp_scatter.
+// One CTA per (head, utterance). Loop: key block kb (128 keys) outer, query tile qt (128 rows) inner; step it:
+//   MMA1(it)   dP = dO_qt V_kb^T                     -> TMEM dP[it & 1]               (issued one step AHEAD)
+//   threads    (16 warps, 1 thread = 1 query row x 32 keys): dropout mask, dS = P * (dP_masked + dP_ext - delta);
+//              dropout(P) and dS -> shared memory tiles [it & 1] (bf16, 128B-swizzled [q][key])
+//   MMA2(it)   dV_kb += dropout(P)^T dO_qt, dK_kb += dS^T Q_qt   (A = the smem tiles read MN-major)
+//              dQ_qt(kb) = dS K_kb                    -> TMEM dQ[it & 1]
+//   threads    read-out of step it-1 (after the element phase of step it): dQ partial -> fp32 accumulator in HBM
+//              (plain RMW: the CTA owns its (b,h)), bf16 on the last key block; dK_kb / dV_kb after the last tile.
+// dP, the two smem tiles, dQ and the Q/dO buffers are all double buffered: while the threads work on step it, the tensor
+// core runs MMA2(it-1) and MMA1(it+1) and TMA fetches Q/dO(it+1). Every mbarrier belongs to one buffer and is waited
+// phase by phase in order (a parity wait on a barrier two phases behind would fall through).
+// Semantics: backward of speecht5/models/modules/multihead_attention.py:340-389. With relative positions the two table
+// contractions dQ += dQP PE and dPE = dQP^T Q run on the batched GEMM from the dS written here.
 #include "../../include/speecht5_b200.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -28,8 +26,8 @@ int set_error(int code, const char* where);
 constexpr int FB_NG = 4;                       // compute warp groups: group g owns 32-key chunk g of the 128-key block
 constexpr int FB_THREADS = 64 + FB_NG * 128;  // TMA warp, MMA warp, 16 compute warps (4 per TMEM lane quarter)
 constexpr int FB_T = 128;  // query tile == key block
-constexpr size_t FB_SMEM = 6 * 16384 + 2 * 32768 + 128 + 1024;
-constexpr uint32_t FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DK = 256, FB_COL_DV = 320, FB_COL_DQ = 384;
+constexpr size_t FB_SMEM = 6 * 16384 + 4 * 32768 + 256 + 1024;  // K V | Q x2 | dO x2 | dropout(P) x2 | dS x2 | barriers
+constexpr uint32_t FB_COL_DP = 0, FB_COL_DK = 256, FB_COL_DV = 320, FB_COL_DQ = 384;  // dP: 2 x 128, dQ: 2 x 64 columns
 
 struct FusedBwdParams {
   int B, H, Tq, Tk, causal;
@@ -41,7 +39,7 @@ struct FusedBwdParams {
   __nv_bfloat16* dk; long k_ld, k_bs;
   __nv_bfloat16* dv; long v_ld, v_bs;
   float* dq_acc;  // [B][Tq][H*64] fp32 scratch
-  const __nv_bfloat16* probs_in;  // optional [B][H][Tq][p_ld]: P from the forward pass (instead of exp(S - lse))
+  const void* probs_in; int probs_fp32;  // [B][H][Tq][p_ld]: P from the forward pass (bf16 or fp32)
   __nv_bfloat16* ds_out;          // optional [B][H][Tq][p_ld]: dS for the relative-position contractions
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
 };
@@ -105,17 +103,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   uint8_t* sV = sK + 16384;
   uint8_t* sQ = sV + 16384;       // 2 x [128 rows][128 B]
   uint8_t* sdO = sQ + 32768;      // 2 x [128 rows][128 B]
-  uint8_t* sPd = sdO + 32768;     // 2 blocks of [128 rows][64 keys]
-  uint8_t* sdS = sPd + 32768;
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sdS + 32768);
-  uint64_t* bar_qdo = bar_kv + 1;    // [2] Q/dO buffer filled
-  uint64_t* bar_qfree = bar_kv + 3;  // [2] Q/dO buffer consumed by MMA2
-  uint64_t* bar_sdp = bar_kv + 5;
-  uint64_t* bar_pds = bar_kv + 6;
-  uint64_t* bar_mma2 = bar_kv + 7;
-  uint64_t* bar_tdone = bar_kv + 8;
-  uint64_t* bar_kvfree = bar_kv + 9;  // every MMA that reads this key block's K/V tiles has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 10);
+  uint8_t* sPd = sdO + 32768;     // 2 x (2 blocks of [128 rows][64 keys])
+  uint8_t* sdS = sPd + 65536;     // 2 x (2 blocks of [128 rows][64 keys])
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sdS + 65536);  // K/V of a key block landed
+  uint64_t* bar_kvfree = bar_kv + 1;  // every MMA that reads this key block's K/V tiles has completed
+  uint64_t* bar_qdo = bar_kv + 2;     // [2] Q/dO buffer filled
+  uint64_t* bar_qfree = bar_kv + 4;   // [2] Q/dO buffer consumed by MMA2
+  uint64_t* bar_dp = bar_kv + 6;      // [2] MMA1 complete: dP buffer valid
+  uint64_t* bar_pds = bar_kv + 8;     // [2] threads: dropout(P)/dS tiles written, dP buffer read
+  uint64_t* bar_mma2 = bar_kv + 10;   // [2] MMA2 complete: dQ buffer (and dK/dV) valid, smem tiles free
+  uint64_t* bar_tdone = bar_kv + 12;  // [2] threads: dQ buffer (and dK/dV) read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 14);
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -123,9 +121,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
-    mbar_init(bar_kv, 1); mbar_init(&bar_qdo[0], 1); mbar_init(&bar_qdo[1], 1); mbar_init(&bar_qfree[0], 1);
-    mbar_init(&bar_qfree[1], 1); mbar_init(bar_sdp, 1); mbar_init(bar_pds, FB_NG * 4); mbar_init(bar_mma2, 1);
-    mbar_init(bar_tdone, FB_NG * 4); mbar_init(bar_kvfree, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_kvfree, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_qdo[s], 1); mbar_init(&bar_qfree[s], 1); mbar_init(&bar_dp[s], 1);
+      mbar_init(&bar_pds[s], FB_NG * 4); mbar_init(&bar_mma2[s], 1); mbar_init(&bar_tdone[s], FB_NG * 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -140,8 +140,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      // (each barrier is waited on phase by phase, in order: a parity wait on a barrier that is two phases behind
-      // would fall through, so the K/V hand-back has its own barrier instead of sampling bar_mma2)
       int it = 0, kbc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int qt0 = p.causal ? kb : 0;
@@ -164,35 +162,42 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO);
-    const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
+    const uint32_t aPd0 = smem_u32(sPd), adS0 = smem_u32(sdS);
+    // dP(j) = dO V^T into dP[j & 1]. That buffer was last read by the threads in step j-2, which this warp has
+    // already waited for (bar_pds) before issuing MMA2(j-2).
+    auto issue1 = [&](int j) {
+      const int buf = j & 1;
+      mbar_wait(&bar_qdo[buf], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t adO = adO0 + (uint32_t)buf * 16384u;
+        const uint32_t id = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + FB_COL_DP + (uint32_t)buf * 128u, umma_smem_desc(adO + k * 32, 16, 1024),
+                    umma_smem_desc(aV + k * 32, 16, 1024), id, k != 0);
+        umma_commit(&bar_dp[buf]);
+      }
+      __syncwarp();
+    };
     int it = 0, kbc = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int qt0 = p.causal ? kb : 0;
       if (qt0 >= nqt) continue;
       mbar_wait(bar_kv, (uint32_t)(kbc & 1));
       ++kbc;
+      issue1(it);
       for (int qt = qt0; qt < nqt; ++qt, ++it) {
         const int buf = it & 1;
-        const uint32_t aQ = aQ0 + (uint32_t)buf * 16384u, adO = adO0 + (uint32_t)buf * 16384u;
-        mbar_wait(&bar_qdo[buf], (uint32_t)((it >> 1) & 1));
+        if (qt + 1 < nqt) issue1(it + 1);  // one step ahead (same key block: K/V stay put)
+        mbar_wait(&bar_pds[buf], (uint32_t)((it >> 1) & 1));
+        if (it >= 2) mbar_wait(&bar_tdone[buf], (uint32_t)(((it >> 1) - 1) & 1));  // dQ[buf] of step it-2 read out
+        // first step of a key block overwrites dK/dV: the previous block's read-out (step it-1) must be over
+        if (qt == qt0 && it >= 1) mbar_wait(&bar_tdone[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t id = umma_idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (p.probs_in == nullptr)
-              umma_bf16(tmem + FB_COL_S, umma_smem_desc(aQ + k * 32, 16, 1024), umma_smem_desc(aK + k * 32, 16, 1024),
-                        id, k != 0);
-            umma_bf16(tmem + FB_COL_DP, umma_smem_desc(adO + k * 32, 16, 1024), umma_smem_desc(aV + k * 32, 16, 1024),
-                      id, k != 0);
-          }
-          umma_commit(bar_sdp);
-        }
-        __syncwarp();
-        mbar_wait(bar_pds, (uint32_t)(it & 1));
-        if (it > 0) mbar_wait(bar_tdone, (uint32_t)((it - 1) & 1));  // dQ scratch (and dK/dV) of the previous step read
-        tc_fence_after();
-        if (elect_one()) {
+          const uint32_t aQ = aQ0 + (uint32_t)buf * 16384u, adO = adO0 + (uint32_t)buf * 16384u;
+          const uint32_t aPd = aPd0 + (uint32_t)buf * 32768u, adS = adS0 + (uint32_t)buf * 32768u;
           const uint32_t acc = qt != qt0;
           const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);  // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
 #pragma unroll
@@ -206,10 +211,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // contraction over the 128 keys: 2 blocks x 4 k-steps
             const int blk = k >> 2, ks = k & 3;
-            umma_bf16(tmem + FB_COL_DQ, umma_smem_desc(adS + blk * 16384 + ks * 32, 16, 1024),
+            umma_bf16(tmem + FB_COL_DQ + (uint32_t)buf * 64u, umma_smem_desc(adS + blk * 16384 + ks * 32, 16, 1024),
                       umma_smem_desc(aK + (blk * 64 + ks * 16) * 128, 16384, 1024), id_q, k != 0);
           }
-          umma_commit(bar_mma2);
+          umma_commit(&bar_mma2[buf]);
           umma_commit(&bar_qfree[buf]);
           if (qt == nqt - 1) umma_commit(bar_kvfree);
         }
@@ -219,28 +224,26 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   } else {
     // ===================== compute threads (thread = query row / key row) =====================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;  // column group: 32-key chunk of the block, 16-channel slice of dQ, 32-channel slice of dK|dV
+    const int grp = (warp - 2) >> 2;  // 32-key chunk of the block, 16-channel slice of dQ, 32-channel slice of dK|dV
     const int r = q * 32 + (int)lane_id();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    const uint8_t* kp = p.key_pad != nullptr ? p.key_pad + (int64_t)b * p.Tk : nullptr;
     uint64_t dseed = p.seed, doffset = p.offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
-    const float LOG2E = 1.4426950408889634f;
     // ---- read-out of one finished step: dQ partial of (kb, qt); dK / dV after the last query tile of a key block
-    auto read_out = [&](int kb, int qt, int it) {
+    auto read_out = [&](int kb, int qt, int j) {
+      const int buf = j & 1;
       const int k0 = kb * FB_T;
       const int i = qt * FB_T + r;
       const bool row_ok = i < p.Tq;
-      mbar_wait(bar_mma2, (uint32_t)(it & 1));
+      mbar_wait(&bar_mma2[buf], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const int kb_last = p.causal ? (qt < nkb - 1 ? qt : nkb - 1) : nkb - 1;
       {
-        const int c = half;  // each group takes 16 of the 64 channels
         uint32_t v[16];
-        tmem_ld_32x16(trow + FB_COL_DQ + (uint32_t)(c * 16), v);
+        tmem_ld_32x16(trow + FB_COL_DQ + (uint32_t)(buf * 64 + grp * 16), v);
         tmem_ld_wait();
         if (row_ok) {
-          float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + c * 16;
+          float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + grp * 16;
           float f[16];
 #pragma unroll
           for (int t = 0; t < 16; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             }
           }
           if (kb == kb_last) {
-            __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + c * 16;
+            __nv_bfloat16* dst = p.dq + (int64_t)b * p.q_bs + (int64_t)i * p.q_ld + h * 64 + grp * 16;
 #pragma unroll
             for (int t = 0; t < 16; t += 8) {
               uint4 pk;
@@ -267,138 +270,142 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
           }
         }
       }
-      if (qt == nqt - 1) {  // thread = key row
-        const int j = k0 + r;
-        {
-          const int c = half;  // groups 0,1 write the two 32-channel halves of dK, groups 2,3 those of dV
-          uint32_t v[32];
-          tmem_ld_32x32(trow + (c < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((c & 1) * 32), v);
-          tmem_ld_wait();
-          if (j < p.Tk) {
-            const float sc = c < 2 ? p.scale : 1.f;
-            __nv_bfloat16* dst = (c < 2 ? p.dk + (int64_t)b * p.k_bs + (int64_t)j * p.k_ld
-                                        : p.dv + (int64_t)b * p.v_bs + (int64_t)j * p.v_ld) + h * 64 + (c & 1) * 32;
+      if (qt == nqt - 1) {  // thread = key row; groups 0,1 write the two 32-channel halves of dK, groups 2,3 those of dV
+        const int j_key = k0 + r;
+        uint32_t v[32];
+        tmem_ld_32x32(trow + (grp < 2 ? FB_COL_DK : FB_COL_DV) + (uint32_t)((grp & 1) * 32), v);
+        tmem_ld_wait();
+        if (j_key < p.Tk) {
+          const float sc = grp < 2 ? p.scale : 1.f;
+          __nv_bfloat16* dst = (grp < 2 ? p.dk + (int64_t)b * p.k_bs + (int64_t)j_key * p.k_ld
+                                        : p.dv + (int64_t)b * p.v_bs + (int64_t)j_key * p.v_ld) + h * 64 + (grp & 1) * 32;
 #pragma unroll
-            for (int t = 0; t < 32; t += 8) {
-              uint4 pk;
-              pk.x = pack2(__uint_as_float(v[t]) * sc, __uint_as_float(v[t + 1]) * sc);
-              pk.y = pack2(__uint_as_float(v[t + 2]) * sc, __uint_as_float(v[t + 3]) * sc);
-              pk.z = pack2(__uint_as_float(v[t + 4]) * sc, __uint_as_float(v[t + 5]) * sc);
-              pk.w = pack2(__uint_as_float(v[t + 6]) * sc, __uint_as_float(v[t + 7]) * sc);
-              *reinterpret_cast<uint4*>(dst + t) = pk;
-            }
+          for (int t = 0; t < 32; t += 8) {
+            uint4 pk;
+            pk.x = pack2(__uint_as_float(v[t]) * sc, __uint_as_float(v[t + 1]) * sc);
+            pk.y = pack2(__uint_as_float(v[t + 2]) * sc, __uint_as_float(v[t + 3]) * sc);
+            pk.z = pack2(__uint_as_float(v[t + 4]) * sc, __uint_as_float(v[t + 5]) * sc);
+            pk.w = pack2(__uint_as_float(v[t + 6]) * sc, __uint_as_float(v[t + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + t) = pk;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(bar_tdone);
+      if (lane_id() == 0) mbar_arrive(&bar_tdone[buf]);
     };
+    // 64 bytes of this thread's row of P for step (kb2, qt2), as raw bf16x8 words
+    auto fetch_p = [&](int kb2, int qt2, uint4 (&dst)[4]) {
+      const int i2 = qt2 * FB_T + r;
+      const int col = kb2 * FB_T + grp * 32;
+      const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.probs_in) +
+                                (((int64_t)b * p.H + h) * p.Tq + i2) * p.p_ld + col;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        dst[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (i2 < p.Tq && col + 8 * g + 8 <= p.p_ld) dst[g] = __ldg(reinterpret_cast<const uint4*>(pr + 8 * g));
+      }
+    };
+    uint4 pcur[4], pnext[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pcur[g] = pnext[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (!p.probs_fp32 && nkb > 0 && nqt > 0) fetch_p(0, 0, pcur);
     int it = 0, pend_kb = -1, pend_qt = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int qt0 = p.causal ? kb : 0;
       const int k0 = kb * FB_T;
       for (int qt = qt0; qt < nqt; ++qt, ++it) {
+        const int buf = it & 1;
         const int i = qt * FB_T + r;
         const bool row_ok = i < p.Tq;
         const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
-        const float lse2 = (row_ok && p.lse != nullptr) ? p.lse[prow] * LOG2E : 0.f;
         const float delta = row_ok ? p.delta[prow] : 0.f;
         const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
-        mbar_wait(bar_sdp, (uint32_t)(it & 1));
+        const int c = grp;  // this warp's 32-key chunk of the block
+        const int col0 = k0 + c * 32;
+        // saved probabilities of this row's chunk (zero where masked, beyond the row pitch and for dead rows): the
+        // bf16 copy was prefetched during the previous step (pcur); the next step's chunk is requested now
+        if (!p.probs_fp32) {
+          int kb2 = kb, qt2 = qt + 1;
+          if (qt2 >= nqt) { kb2 = kb + 1; qt2 = p.causal ? kb2 : 0; }
+          if (kb2 < nkb && qt2 < nqt) fetch_p(kb2, qt2, pnext);
+        }
+        uint32_t kb_ = 0xffffffffu;
+        if (p.drop_thr != 0)
+          kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)col0, p.drop_thr);
+        mbar_wait(&bar_dp[buf], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
-        {
-          const int c = half;  // this warp's 32-key chunk of the block
-          uint32_t sv[32], dv[32];
-          const int col0 = k0 + c * 32;
-          if (p.probs_in == nullptr) {
-            tmem_ld_32x32(trow + FB_COL_S + (uint32_t)(c * 32), sv);
-          } else {  // saved probabilities: 64 contiguous bytes of this row (zero beyond the row pitch / for dead rows)
-            const __nv_bfloat16* pr = p.probs_in + prow * p.p_ld + col0;
+        uint32_t dv[32];
+        tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(buf * 128 + c * 32), dv);
+        tmem_ld_wait();
+        // dP as seen by the softmax: dropout backward of dO V^T, plus the caller's gradient on the probabilities
+        // (this row's 32 floats = one 128-byte line, fetched as eight 16-byte loads)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u = make_uint4(0u, 0u, 0u, 0u);
-              if (row_ok && col0 + 8 * g + 8 <= p.p_ld) u = __ldg(reinterpret_cast<const uint4*>(pr + 8 * g));
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+        for (int t = 0; t < 32; ++t)
+          dv[t] = ((kb_ >> t) & 1u) ? __float_as_uint(__uint_as_float(dv[t]) * p.drop_scale) : 0u;
+        if (dpx != nullptr) {
+          if ((p.p_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dp_ext) & 15) == 0) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(hh[e]);
-                sv[8 * g + 2 * e] = __float_as_uint(f.x);
-                sv[8 * g + 2 * e + 1] = __float_as_uint(f.y);
+            for (int g = 0; g < 8; ++g)
+              if (col0 + 4 * g + 4 <= p.p_ld) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 4 * g));
+                dv[4 * g] = __float_as_uint(__uint_as_float(dv[4 * g]) + x.x);
+                dv[4 * g + 1] = __float_as_uint(__uint_as_float(dv[4 * g + 1]) + x.y);
+                dv[4 * g + 2] = __float_as_uint(__uint_as_float(dv[4 * g + 2]) + x.z);
+                dv[4 * g + 3] = __float_as_uint(__uint_as_float(dv[4 * g + 3]) + x.w);
               }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (col0 + t < p.Tk) dv[t] = __float_as_uint(__uint_as_float(dv[t]) + dpx[col0 + t]);
+          }
+        }
+        // (dP is finite everywhere: V rows beyond Tk and dO rows beyond Tq arrive as zeros from TMA)
+        uint8_t* bp = sPd + buf * 32768 + (c >> 1) * 16384 + r * 128;
+        uint8_t* bs = sdS + buf * 32768 + (c >> 1) * 16384 + r * 128;
+        const int cbase = (c & 1) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pd8[8], ds8[8], pv8[8];
+          if (p.probs_fp32) {
+            const float* pr = reinterpret_cast<const float*>(p.probs_in) + prow * p.p_ld + col0 + 8 * g;
+            float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+            if (row_ok && col0 + 8 * g + 8 <= p.p_ld) {
+              u0 = __ldg(reinterpret_cast<const float4*>(pr));
+              u1 = __ldg(reinterpret_cast<const float4*>(pr + 4));
+            }
+            pv8[0] = u0.x; pv8[1] = u0.y; pv8[2] = u0.z; pv8[3] = u0.w;
+            pv8[4] = u1.x; pv8[5] = u1.y; pv8[6] = u1.z; pv8[7] = u1.w;
+          } else {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pcur[g]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(hh[e]);
+              pv8[2 * e] = f.x;
+              pv8[2 * e + 1] = f.y;
             }
           }
-          tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(c * 32), dv);
-          // validity bits: key exists and is not padded (one coalesced byte load per lane + ballot), causal, row in range
-          const int jl = k0 + c * 32 + (int)lane_id();
-          uint32_t vb = __ballot_sync(0xffffffffu, jl < p.Tk && !(kp != nullptr && kp[jl] != 0));
-          if (p.causal) {
-            const int lim = i - (k0 + c * 32);
-            vb &= lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            pd8[t] = ((kb_ >> (8 * g + t)) & 1u) ? pv8[t] * p.drop_scale : 0.f;
+            ds8[t] = pv8[t] * (__uint_as_float(dv[8 * g + t]) - delta);
           }
-          if (!row_ok) vb = 0u;
-          uint32_t kb_ = 0xffffffffu;
-          if (p.drop_thr != 0)
-            kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(k0 + c * 32),
-                                      p.drop_thr);
-          tmem_ld_wait();
-          // dP as seen by the softmax: dropout backward of dO V^T, plus the caller's gradient on the probabilities
-          // (this row's 32 floats = one 128-byte line, fetched as eight 16-byte loads)
-#pragma unroll
-          for (int t = 0; t < 32; ++t)
-            dv[t] = ((kb_ >> t) & 1u) ? __float_as_uint(__uint_as_float(dv[t]) * p.drop_scale) : 0u;
-          if (dpx != nullptr) {
-            if ((p.p_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dp_ext) & 15) == 0) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (col0 + 4 * g + 4 <= p.p_ld) {
-                  const float4 x = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 4 * g));
-                  dv[4 * g] = __float_as_uint(__uint_as_float(dv[4 * g]) + x.x);
-                  dv[4 * g + 1] = __float_as_uint(__uint_as_float(dv[4 * g + 1]) + x.y);
-                  dv[4 * g + 2] = __float_as_uint(__uint_as_float(dv[4 * g + 2]) + x.z);
-                  dv[4 * g + 3] = __float_as_uint(__uint_as_float(dv[4 * g + 3]) + x.w);
-                }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; ++t)
-                if (col0 + t < p.Tk) dv[t] = __float_as_uint(__uint_as_float(dv[t]) + dpx[col0 + t]);
-            }
-          }
-          float pd[32], ds[32];
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            float pdv = 0.f, dsv = 0.f;  // (columns outside the mask may hold non-finite TMEM garbage: never multiply them)
-            if ((vb >> t) & 1u) {
-              const float pv = p.probs_in != nullptr ? __uint_as_float(sv[t])
-                                                     : fast_ex2(__uint_as_float(sv[t]) * p.scale_log2 - lse2);
-              pdv = ((kb_ >> t) & 1u) ? pv * p.drop_scale : 0.f;
-              dsv = pv * (__uint_as_float(dv[t]) - delta);
-            }
-            pd[t] = pdv;
-            ds[t] = dsv;
-          }
-          uint8_t* bp = sPd + (c >> 1) * 16384 + r * 128;
-          uint8_t* bs = sdS + (c >> 1) * 16384 + r * 128;
-          const int cbase = (c & 1) * 4;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int sw = ((cbase + g) ^ (r & 7)) << 4;
-            uint4 a, d;
-            a.x = pack2(pd[8 * g], pd[8 * g + 1]); a.y = pack2(pd[8 * g + 2], pd[8 * g + 3]);
-            a.z = pack2(pd[8 * g + 4], pd[8 * g + 5]); a.w = pack2(pd[8 * g + 6], pd[8 * g + 7]);
-            d.x = pack2(ds[8 * g], ds[8 * g + 1]); d.y = pack2(ds[8 * g + 2], ds[8 * g + 3]);
-            d.z = pack2(ds[8 * g + 4], ds[8 * g + 5]); d.w = pack2(ds[8 * g + 6], ds[8 * g + 7]);
-            *reinterpret_cast<uint4*>(bp + sw) = a;
-            *reinterpret_cast<uint4*>(bs + sw) = d;
-            if (p.ds_out != nullptr && row_ok && col0 + 8 * g + 8 <= p.p_ld)
-              *reinterpret_cast<uint4*>(p.ds_out + prow * p.p_ld + col0 + 8 * g) = d;
-          }
+          const int sw = ((cbase + g) ^ (r & 7)) << 4;
+          uint4 a, d;
+          a.x = pack2(pd8[0], pd8[1]); a.y = pack2(pd8[2], pd8[3]); a.z = pack2(pd8[4], pd8[5]); a.w = pack2(pd8[6], pd8[7]);
+          d.x = pack2(ds8[0], ds8[1]); d.y = pack2(ds8[2], ds8[3]); d.z = pack2(ds8[4], ds8[5]); d.w = pack2(ds8[6], ds8[7]);
+          *reinterpret_cast<uint4*>(bp + sw) = a;
+          *reinterpret_cast<uint4*>(bs + sw) = d;
+          if (p.ds_out != nullptr && row_ok && col0 + 8 * g + 8 <= p.p_ld)
+            *reinterpret_cast<uint4*>(p.ds_out + prow * p.p_ld + col0 + 8 * g) = d;
         }
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
-        if (lane_id() == 0) mbar_arrive(bar_pds);
-        // ---- the previous step's accumulators are read while MMA2 of this step and MMA1 of the next one run
+        if (lane_id() == 0) mbar_arrive(&bar_pds[buf]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pcur[g] = pnext[g];
+        // ---- the previous step's accumulators are read while the tensor core works on this step and the next
         if (pend_kb >= 0) read_out(pend_kb, pend_qt, it - 1);
         pend_kb = kb;
         pend_qt = qt;
@@ -428,13 +435,14 @@ using namespace st5;
 extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, float* delta, float* dq_acc, void* stream) {
   const bool rpe = a->pe_k != nullptr;
   if (a->dtype != ST5_BF16 || a->Tk <= 0 || a->Tq <= 0) return set_error(-2, "st5_attn_fused_bwd: needs bf16");
-  if (rpe && (a->probs == nullptr || a->probs_dtype != ST5_BF16 || a->ds == nullptr || a->dprobs_ext != nullptr ||
-              a->causal || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(a->probs) & 15) ||
-              (reinterpret_cast<uintptr_t>(a->ds) & 15)))
-    return set_error(-5, "st5_attn_fused_bwd: relative positions need the saved bf16 probabilities and a dS buffer");
-  if (a->dprobs_ext != nullptr && (a->probs == nullptr || a->probs_dtype != ST5_F32 || a->p_ld < a->Tk))
+  if (a->probs == nullptr || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(a->probs) & 15))
+    return set_error(-5, "st5_attn_fused_bwd: needs the probabilities saved by st5_attn_fused_fwd (16-byte aligned, "
+                         "row pitch a multiple of 8)");
+  if (rpe && (a->ds == nullptr || a->dprobs_ext != nullptr || a->causal || (reinterpret_cast<uintptr_t>(a->ds) & 15)))
+    return set_error(-5, "st5_attn_fused_bwd: relative positions need a dS buffer and take no external dP");
+  if (a->dprobs_ext != nullptr && a->probs_dtype != ST5_F32)
     return set_error(-3, "st5_attn_fused_bwd: dprobs_ext needs the fp32 probabilities");
-  if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || (!lse && !rpe) || !delta || !dq_acc)
+  if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || !delta || !dq_acc)
     return set_error(-4, "st5_attn_fused_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nrows = (int64_t)a->B * a->H * a->Tq;
@@ -469,7 +477,8 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, floa
   p.dk = (__nv_bfloat16*)a->dk; p.k_ld = a->k_ld; p.k_bs = a->k_bs;
   p.dv = (__nv_bfloat16*)a->dv; p.v_ld = a->v_ld; p.v_bs = a->v_bs;
   p.dq_acc = dq_acc;
-  p.probs_in = rpe ? (const __nv_bfloat16*)a->probs : nullptr;
+  p.probs_in = a->probs;
+  p.probs_fp32 = a->probs_dtype == ST5_F32;
   p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;

@@ -51,6 +51,7 @@ __device__ __forceinline__ void act_chunk(float (&v)[32]) {
     if constexpr (ACT == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
     if constexpr (ACT == ACT_GELU) v[j] = gelu_fwd(v[j]);
     if constexpr (ACT == ACT_TANH) v[j] = tanhf(v[j]);
+    if constexpr (ACT == ACT_GELU_TANH) v[j] = gelu_tanh_fwd(v[j]);
   }
 }
 template <int ACT>
@@ -338,7 +339,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
         }
       };
       if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
-      if (p.act == ACT_GELU) act_chunk<ACT_GELU>(v);
+      if (p.act == ACT_GELU_TANH) act_chunk<ACT_GELU_TANH>(v);
+      else if (p.act == ACT_GELU) act_chunk<ACT_GELU>(v);
       else if (p.act == ACT_RELU) act_chunk<ACT_RELU>(v);
       else if (p.act == ACT_TANH) act_chunk<ACT_TANH>(v);
       if (p.drop_thr != 0) {
@@ -364,7 +366,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
-              if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
+              if (p.ag_act == ACT_GELU_TANH) actgrad8<ACT_GELU_TANH>(v + j, u);
+              else if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
               else if (p.ag_act == ACT_RELU) actgrad8<ACT_RELU>(v + j, u);
               else actgrad8<ACT_TANH>(v + j, u);
             }

@@ -5,7 +5,7 @@
 
 namespace st5 {
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4 };
 
 // D[z][m][n] = epilogue( alpha * sum_k A[z][m][k] * B[z][n][k] )
 // Operands are bf16. "K-major" = k is the contiguous index (row-major [rows][K]); "MN-major" = the m (or n)

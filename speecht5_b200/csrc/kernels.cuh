@@ -53,7 +53,27 @@ __device__ __forceinline__ float gelu_fwd(float x) {
   float ex;
   return x * gauss_cdf(x, ex);
 }
+// Throughput-mode GELU (bf16 activations): the tanh form 0.5 x (1 + tanh(sqrt(2/pi)(x + 0.044715 x^3))) on the MUFU
+// tanh unit -- 7 instructions instead of 16. |gelu_tanh - gelu_erf| <= 4.8e-4 absolute (< half a bf16 ulp for every
+// |y| > 0.13, and vanishing like x^5 near 0); the parity mode (fp32 activations) always uses the exact erf form above.
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fwd(float x) {
+  const float t = fast_tanh(x * fmaf(0.0356774081f, x * x, 0.7978845608f));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float x2 = x * x;
+  const float t = fast_tanh(x * fmaf(0.0356774081f, x2, 0.7978845608f));
+  const float du = fmaf(0.1070322243f, x2, 0.7978845608f);
+  return fmaf(0.5f * x * fmaf(-t, t, 1.f), du, fmaf(0.5f, t, 0.5f));
+}
 __device__ __forceinline__ float act_grad(float x, int act) {
+  if (act == 4) return gelu_tanh_grad(x);
   if (act == 1) return x > 0.f ? 1.f : 0.f;
   if (act == 2) {
     float ex;

@@ -135,6 +135,12 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _resolve_act(act, dtype):
+    """Throughput mode (bf16 activations) evaluates GELU in its tanh form on the MUFU unit (|error| <= 4.8e-4, below
+    bf16 rounding of the result); parity mode (fp32) keeps the reference's exact erf form (fairseq/modules/gelu.py:24)."""
+    return "gelu_tanh" if (act == "gelu" and dtype == torch.bfloat16) else act
+
+
 def wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=None):
     """dW[n_out, n_in] = gy^T . xin (both operands read MN-major, contraction over the M token rows).
 
@@ -193,7 +199,7 @@ class LinearFn(torch.autograd.Function):
         ldc = _pad8(N)
         out_dtype = opts.get("out_dtype", x.dtype)
         out = torch.empty((M, ldc), dtype=out_dtype, device=x.device)
-        act, drop_p = opts.get("act"), opts.get("drop_p", 0.0)
+        act, drop_p = _resolve_act(opts.get("act"), out.dtype), opts.get("drop_p", 0.0)
         pre = torch.empty_like(out) if act is not None else None
         off = RT.next_offset() if drop_p > 0 else 0
         xa = _split(x2)
@@ -312,6 +318,7 @@ class FFNFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         M, D = x2.shape
         F_ = w1.shape[0]
+        act = _resolve_act(act, x.dtype)
         w1s, w2s = RT.shadow(("lin", id(w1)), lambda: w1), RT.shadow(("lin", id(w2)), lambda: w2)
         bb1 = RT._static.get(("bias", id(b1)), None)
         bb1 = bb1 if bb1 is not None else b1.detach().float().contiguous()
@@ -574,9 +581,9 @@ class AttentionTCFn(torch.autograd.Function):
         delta = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
         dq_acc = torch.empty((B, Tq, d), dtype=torch.float32, device=dev)
         a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)), maxpos=0,
-                        probs_dtype=0, q=qv, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0), k=kk, k_ld=kvb.stride(1),
+                        probs_dtype=K.dtype_id(probs), q=qv, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0), k=kk, k_ld=kvb.stride(1),
                         k_bs=kvb.stride(0), v=vv, v_ld=kvb.stride(1), v_bs=kvb.stride(0), key_pad=kp, pe_k=None,
-                        out=out, o_ld=d, o_bs=Tq * d, probs=probs if dpx is not None else None, p_ld=p_ld,
+                        out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld,
                         scale=cfg["scale"], drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout,
                         dprobs_ext=dpx, ds=None, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
         K.attn_fused_bwd(a, lse, delta, dq_acc)
@@ -669,11 +676,9 @@ class AttentionTCFn(torch.autograd.Function):
             off = RT.next_offset() if drop_p > 0 else 0
             kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
             want = bool(cfg.get("return_probs"))
-            # probabilities leave the chip only when the caller wants them (need_head_weights) or the unfused
-            # backward needs them; the fused backward recomputes P from the log-sum-exp
-            probs = None
-            if want or not RT.attn_fused_bwd:
-                probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32 if want else torch.bfloat16, device=dev)
+            # the probabilities are saved for the backward pass (bf16; fp32 when the caller wants them returned --
+            # need_head_weights): one score-sized MMA less per backward step, which lets that kernel overlap fully
+            probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32 if want else torch.bfloat16, device=dev)
             out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
             lse = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
             a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
