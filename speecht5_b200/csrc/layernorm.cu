@@ -7,49 +7,12 @@
 //             dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy     (separate column-reduction kernel)
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "vec8.cuh"
 
 namespace st5 {
 
 constexpr int LN_WARPS = 4;
 constexpr int LN_MAX_CHUNKS = 4;  // per lane: C <= 4 * 32 * 8 = 1024
-
-template <typename T> __device__ __forceinline__ void load8(const T* p, float* v);
-template <> __device__ __forceinline__ void load8<float>(const float* p, float* v) {
-  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float2 f = __bfloat1622float2(h[t]);
-    v[2 * t] = f.x; v[2 * t + 1] = f.y;
-  }
-}
-template <typename T> __device__ __forceinline__ void store8(T* p, const float* v);
-template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-// round-trip through the storage type (so forward normalises exactly what backward will re-read)
-template <typename T> __device__ __forceinline__ float round_to(float v);
-template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
-template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) {
-  return __bfloat162float(__float2bfloat16(v));
-}
-
-__device__ __forceinline__ void dropout8(float* v, uint64_t e0, uint32_t thr, float dscale, uint64_t seed,
-                                         uint64_t offset) {
-  dropout8_apply(v, e0, thr, dscale, seed, offset);  // e0 is a multiple of 8 (C % 8 == 0)
-}
 
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)

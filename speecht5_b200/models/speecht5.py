@@ -124,6 +124,9 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if "decoder_input" in encoder_output and encoder_output["decoder_input"][0] is not None:
             encoder_output["encoder_out"] = encoder_output["decoder_input"]
             encoder_output["_encoder_out_btc"] = encoder_output["decoder_input"][0].transpose(0, 1)
+        hook = getattr(self, "_encoder_grad_hook", None)  # set by B200Trainer: gradient-exchange overlap point
+        if hook is not None and encoder_output["encoder_out"][0].requires_grad:
+            encoder_output["encoder_out"][0].register_hook(hook)
         prev_output_tokens, tgt_mask = self.speech_decoder_prenet(prev_output_tokens, tgt_lengths, spkembs)
         decoder_output, extra = self.decoder(
             prev_output_tokens, tgt_mask, encoder_output,

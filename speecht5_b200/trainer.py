@@ -12,6 +12,8 @@ LegacyDistributedDataParallel semantics for the gradient exchange (legacy_distri
   * the whole update (zero, forward, backward, exchange, norm, Adam) is captured once into a CUDA graph and replayed --
     the ~1.5k kernel launches per step otherwise leave the GPU waiting on Python.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -37,6 +39,16 @@ class GradBucketer:
             chunk = self.flat[s:e]
             chunk.div_(self.world)  # legacy_ddp.py:110 (div before the sum keeps fp16/bf16 ranges safe)
             dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_sum(self, lo=0, hi=None):
+        """Sum (not mean) of flat[lo:hi] over the ranks, bucket by bucket; the caller folds 1/world into the gradient
+        multiplier it applies anyway (fp32 buffer: no range concern, one elementwise pass over the buffer less)."""
+        if self.world == 1:
+            return
+        hi = self.flat.numel() if hi is None else hi
+        step = self.bounds[0][1] - self.bounds[0][0] if self.bounds else hi
+        for s in range(lo, hi, max(1, step)):
+            dist.all_reduce(self.flat[s:min(hi, s + step)], op=dist.ReduceOp.SUM, group=self.group)
 
 
 def _fused_groups(model):
@@ -78,13 +90,22 @@ class FlatParams:
             if id(g[0]) not in seen:
                 order.append(g)
                 seen.update(id(q) for q in g)
-        offsets, off = {}, 0
+        # encoder-side groups first, everything whose gradient is complete once d(encoder_out) exists (decoder, decoder
+        # prenet, postnet) behind them: the second range can be exchanged while the encoder is still in backward
+        names = {id(p): n for n, p in model.named_parameters()}
+        enc_side = ("encoder.", "text_encoder_prenet.", "speech_encoder_prenet.")
+        is_enc = lambda g: names.get(id(g[0]), "").startswith(enc_side)  # noqa: E731
+        order = [g for g in order if is_enc(g)] + [g for g in order if not is_enc(g)]
+        offsets, off, split = {}, 0, None
         for g in order:
             off = (off + 7) // 8 * 8  # 16-byte alignment of every bf16 operand (TMA)
+            if split is None and not is_enc(g):
+                split = off
             for p in g:
                 offsets[id(p)] = off
                 off += p.numel()
         self.numel = (off + 7) // 8 * 8
+        self.split = self.numel if split is None else split  # [0, split) encoder side, [split, numel) decoder side
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.grads = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
@@ -136,6 +157,15 @@ class B200Trainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.fp = FlatParams(model)
         self.bucketer = GradBucketer(self.fp.grads, bucket_elems=bucket_mb * 1024 * 1024 // 4, group=process_group)
+        # overlap of the exchange with backward: when d(encoder_out) arrives, every decoder-side gradient is final
+        # (autograd runs the later-created decoder nodes first), so that range is all-reduced on a side stream while
+        # the encoder layers are still in backward. ST5_OVERLAP_AR=0 disables it.
+        self._tail_launched, self._last_micro = False, False
+        self._side = None
+        if (self.world > 1 and self.device.type == "cuda" and os.environ.get("ST5_OVERLAP_AR", "1") != "0"
+                and 0 < self.fp.split < self.fp.numel):
+            self._side = torch.cuda.Stream(device=self.device)
+            model._encoder_grad_hook = self._on_decoder_grads_final
         self.num_updates = 0
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=self.device)
@@ -147,18 +177,37 @@ class B200Trainer:
         self._static_out = None
         RT.enable_device_seed(self.device)
 
+    def _on_decoder_grads_final(self, grad):
+        if self._side is None or not self._last_micro or self._tail_launched:
+            return None
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self.bucketer.all_reduce_sum(self.fp.split, self.fp.numel)
+        self._tail_launched = True
+        return None
+
     # ------------------------------------------------------------------ the update, as a sequence of device work
     def _update(self, samples):
         self.fp.grads.zero_()
         losses, stats = [], []
-        for sample in samples:  # --update-freq micro-batches
+        self._tail_launched = False
+        for k, sample in enumerate(samples):  # --update-freq micro-batches
+            self._last_micro = k == len(samples) - 1
             loss, sample_size, logging_output = self.task.train_step(sample, self.model, self.criterion, None,
                                                                      self.num_updates)
             losses.append(loss)
             stats.append(logging_output.get("_stats"))
-        self.bucketer.all_reduce_mean()
-        # trainer.py:796 multiply_grads(world / sample_size): every micro-batch on every rank reports sample_size 1
-        grad_mul = float(self.world) / float(self.world * len(samples))
+        # exchange: sum over ranks (mean folded into grad_mul below). The decoder-side range may already be in flight
+        # on the side stream (launched from the encoder_out gradient hook); join it, then reduce the rest.
+        if self._tail_launched:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self.bucketer.all_reduce_sum(0, self.fp.split)
+        else:
+            self.bucketer.all_reduce_sum()
+        self._last_micro = False
+        # legacy_ddp.py:110 divides by world before the sum; trainer.py:796 multiply_grads(world / sample_size) with
+        # sample_size = world * n_micro (every micro-batch on every rank reports 1). Net factor on the summed gradient:
+        grad_mul = 1.0 / float(self.world * len(samples))
         self.gnorm_sq.zero_()
         K.sumsq(self.fp.grads, self.gnorm_sq)
         self.step_dev += 1
