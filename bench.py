@@ -275,6 +275,15 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PF sustained"
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    # DRAM traffic of the same kernel from the committed ncu pass (profiles/, per launch like `achieved`): measured
+    # under ncu (cold L2 per launch), so it is an upper bound of what the warm step moves
+    traffic, traffic_note = None, "no ncu traffic file committed"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = tj.get("note", "")
+    except Exception:  # noqa: BLE001
+        pass
     clocks = sampler.window(*win_dev) if sampler else None
     if sampler:
         sampler.stop()
@@ -303,7 +312,8 @@ def main():
         "step_tflops": 3.0 * (29.07 + 6.0 * args.decoder_layers + 2.36) * value / 1e3,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all GEMM launches of one step)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "peak_source": peak_src, "launches": len(records),
+                     "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                     "launches": len(records),
                      "avg_launch_us": gemm_ms * 1e3 / max(1, len(records)), "gemm_ms_per_step": gemm_ms,
                      "gemm_share_of_step": gemm_ms / ms_dev,
                      "how": "algorithmic 2*M*N*K of every st5_gemm_bf16 launch of one update (recorded from the live "
