@@ -370,7 +370,13 @@ int bn_bwd_launch(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, co
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   if (bn_vec_ok(C, {dy_ld, x_ld, dx_ld}, {dy, x, y_pre, dx, gamma, save_mean, save_rstd, scratch})) {
-    dim3 vgrid((unsigned)((C + 255) / 256), (unsigned)nb);
+    // (each block covers 256 channels: split the rows finer than the scalar kernel to keep ~4 blocks per SM busy)
+    const int64_t cblocks = (C + 255) / 256;
+    int64_t vnb = (592 + cblocks - 1) / cblocks;
+    if (vnb > (rows + 31) / 32) vnb = (rows + 31) / 32;
+    if (vnb < 1) vnb = 1;
+    rpb = (rows + vnb - 1) / vnb;
+    dim3 vgrid((unsigned)cblocks, (unsigned)((rows + rpb - 1) / rpb));
     int64_t gv = (n / 8 + 255) / 256;
     if (gv > 148 * 16) gv = 148 * 16;
     if (dtype == ST5_F32) {
