@@ -189,7 +189,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __rest
 // of every row it visits. Used whenever the layout is 16-byte addressable; also the reduction of split-K partials.
 template <typename T, int VEC>
 __global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows,
-                                  int64_t cols, int64_t group_rows, int64_t rows_per_split) {
+                                  int64_t cols, int64_t group_rows, int64_t rows_per_split, int mode) {
   const int64_t col = ((int64_t)blockIdx.x * 32 + threadIdx.x) * VEC;
   const int64_t g = blockIdx.y;
   const int64_t r0 = g * group_rows + (int64_t)blockIdx.z * rows_per_split;
@@ -227,7 +227,11 @@ __global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, float* __
       float v = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) v += red[k][c];
-      atomicAdd(out + g * cols + oc, v);
+      // mode 0: several row splits share an output (fp32 atomics, output pre-zeroed or accumulated into);
+      // mode 1 / 2: this block owns its outputs (store / add) -- no memset, no atomics
+      if (mode == 0) atomicAdd(out + g * cols + oc, v);
+      else if (mode == 1) out[g * cols + oc] = v;
+      else out[g * cols + oc] += v;
     }
   }
 }
@@ -236,10 +240,6 @@ int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows
   if (rows == 0 || cols == 0) return 0;
   if (group_rows <= 0) group_rows = rows;
   const int64_t groups = (rows + group_rows - 1) / group_rows;
-  if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * groups * cols, s);
-    if (e != cudaSuccess) return (int)e;
-  }
   const int vec = dtype == ST5_F32 ? 4 : 8;
   const bool vec_ok = (cols % vec == 0) && (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int64_t cw = vec_ok ? 32 * vec : 32;  // columns per block
@@ -251,11 +251,16 @@ int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows
   if (splits < 1) splits = 1;
   const int64_t rps = (group_rows + splits - 1) / splits;
   dim3 grid((unsigned)col_blocks, (unsigned)groups, (unsigned)splits), block(32, 8);
+  const int mode = (vec_ok && splits == 1) ? (accumulate ? 2 : 1) : 0;
+  if (mode == 0 && !accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * groups * cols, s);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (vec_ok && dtype == ST5_F32)
-    colsum_vec_kernel<float, 4><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
+    colsum_vec_kernel<float, 4><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps, mode);
   else if (vec_ok)
     colsum_vec_kernel<__nv_bfloat16, 8><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols,
-                                                               group_rows, rps);
+                                                               group_rows, rps, mode);
   else if (dtype == ST5_F32)
     colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
   else
