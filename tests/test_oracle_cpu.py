@@ -80,3 +80,84 @@ def test_oracle_rpe_matches_reference_formulation():
             s[:, i, j] += (q[:, i] * pos.pe_k.weight[idx[i, j]]).sum(-1)
     ref = mha.out_proj(torch.bmm(torch.softmax(s, -1), v).transpose(0, 1).reshape(T, B, d))
     assert rel(out, ref) < 1e-6  # the reference (and the oracle) take the softmax in fp32
+
+
+# ---------------------------------------------------------------------------------------------- speech-in / text-out
+ASR_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "asr_tiny.npz")
+
+
+def _load_asr_golden():
+    import numpy as np
+    z = np.load(ASR_GOLDEN)
+    state = {k[len("state/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state/")}
+    ni = {k[len("in/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in/")}
+    sample = {"net_input": ni, "target": torch.from_numpy(z["sample/target"]),
+              "target_lengths": torch.from_numpy(z["sample/target_lengths"])}
+    out = {k[len("out/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("out/")}
+    grads = {k[len("grad/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+    return state, sample, out, torch.from_numpy(z["loss"]), grads
+
+
+def test_asr_oracle_reproduces_golden_fixture():
+    """SURVEY 8a rows 2, 3, 9, 14, 18 (conv front-end, speech prenet with time/channel masks, text decoder pre/post-net,
+    label-smoothed CE + CTC): fixture generated by tests/golden/make_golden_asr.py."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_asr import TINY as ASR_TINY
+    from oracle.speecht5_oracle_asr import T5TransformerModelASROracle, asr_loss, base_asr_args
+    state, sample, out_ref, loss_ref, grads_ref = _load_asr_golden()
+    model = T5TransformerModelASROracle(base_asr_args(**ASR_TINY), vocab_size=41).double().train()
+    model.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in state.items()})
+    sample["net_input"]["source"] = sample["net_input"]["source"].double()
+    loss, ce, ctc, ss = asr_loss(model, sample)
+    got = torch.stack([loss.detach(), ce.detach(), ctc.detach()])
+    assert ((got - loss_ref[:3]).abs() / loss_ref[:3].abs()).max() < 1e-6 and ss == int(loss_ref[3])
+    loss.backward()
+    with torch.no_grad():
+        (logits, _), enc = model(**sample["net_input"])
+    assert rel(logits, out_ref["logits"]) < 1e-6 and rel(enc["encoder_out"][0], out_ref["encoder_out"]) < 1e-6
+    assert torch.equal(enc["encoder_padding_mask"][0], out_ref["encoder_padding_mask"])
+    params = dict(model.named_parameters())
+    for n, g in grads_ref.items():
+        assert rel(params[n].grad, g) < 1e-5, n
+
+
+def test_asr_oracle_matches_hf_port():
+    """Independent pin: oracle weights remapped onto transformers' SpeechT5ForSpeechToText (conv front-end with
+    GroupNorm, weight-normed positional conv, sinusoidal positions, shared stacks, LM head)."""
+    pytest.importorskip("transformers")
+    from oracle.hf_crosscheck_asr import compare
+    err = compare(n_enc=2, n_dec=2, B=2, n_samples=8000, T_tgt=11, seed=0)
+    assert err["logits"] < 1e-5 and err["encoder"] < 1e-5, err
+
+
+def test_asr_frame_padding_mask_and_lengths_follow_the_reference_rule():
+    """speech_encoder_prenet.py:219-229: a frame is padding iff ALL samples of its (equal-sized) chunk are; the trailing
+    remainder samples are dropped. And :365-374: conv output lengths."""
+    from oracle.speecht5_oracle_asr import ConvFeatureExtractionModel, SpeechEncoderPrenet, base_asr_args
+    fe = ConvFeatureExtractionModel()
+    assert fe.get_out_seq_lens_tensor(torch.tensor([160000, 64000, 250000])).tolist() == [499, 199, 781]
+    pre = SpeechEncoderPrenet(base_asr_args())
+    n, T = 1000, 3  # chunks of 333 samples, one remainder sample dropped
+    lens = torch.tensor([1000, 667, 666, 1])
+    pm = torch.arange(n)[None, :] >= lens[:, None]
+    got = pre.forward_padding_mask(torch.zeros(4, T, 1), pm)
+    assert got.tolist() == [[False, False, False], [False, False, False], [False, False, True], [False, True, True]]
+
+
+def test_asr_label_smoothing_matches_closed_form():
+    """criterions/speech_to_text_loss.py:93-110: eps spread over the V-1 other classes."""
+    from oracle.speecht5_oracle_asr import label_smoothed_nll_loss
+    torch.manual_seed(0)
+    V, N, eps = 7, 5, 0.1
+    lp = torch.log_softmax(torch.randn(N, V, dtype=torch.float64), -1)
+    tgt = torch.tensor([3, 1, 6, 1, 0])
+    loss, nll = label_smoothed_nll_loss(lp, tgt, eps, ignore_index=1)
+    want = 0.0
+    for i in range(N):
+        if int(tgt[i]) == 1:
+            continue
+        q = torch.full((V,), eps / (V - 1), dtype=torch.float64)
+        q[tgt[i]] = 1.0 - eps
+        want += float(-(q * lp[i]).sum())
+    assert abs(float(loss) - want) < 1e-12
