@@ -161,3 +161,61 @@ def test_asr_label_smoothing_matches_closed_form():
         q[tgt[i]] = 1.0 - eps
         want += float(-(q * lp[i]).sum())
     assert abs(float(loss) - want) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------- audio ends (rows 15, 16)
+AUDIO_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "audio_tiny.npz")
+
+
+def test_logmel_oracle_matches_torchaudio_and_hf_feature_extractor():
+    """text_to_speech_dataset.py:95-138 (librosa stft + slaney mel, unvendored): two independent implementations."""
+    import numpy as np
+    from oracle.audio_oracle import logmelfilterbank
+    rng = np.random.default_rng(0)
+    wav = (rng.standard_normal(64000) * 0.1).astype(np.float32)  # 4 s -> 251 frames (SURVEY 8: 1 + n // 256)
+    lm = logmelfilterbank(wav)
+    assert lm.shape == (251, 80)
+    ta = pytest.importorskip("torchaudio")
+    ms = ta.transforms.MelSpectrogram(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, f_min=80,
+                                      f_max=7600, n_mels=80, power=1.0, norm="slaney", mel_scale="slaney", center=True,
+                                      pad_mode="reflect", window_fn=torch.hann_window)
+    ref = torch.log10(torch.clamp(ms(torch.from_numpy(wav)), min=1e-10)).T.numpy()
+    assert np.linalg.norm(lm - ref) / np.linalg.norm(ref) < 1e-5
+    tr = pytest.importorskip("transformers")
+    hf = tr.SpeechT5FeatureExtractor()(audio_target=wav, sampling_rate=16000, return_tensors="np")["input_values"][0]
+    assert np.linalg.norm(lm - hf) / np.linalg.norm(hf) < 1e-5
+
+
+def test_hifigan_oracle_matches_hf_port_and_golden():
+    """SpeechUT/fairseq/.../hifigan.py:13-170 restated; pinned against transformers.SpeechT5HifiGan at the SpeechT5
+    vocoder configuration, and the committed small-config fixture."""
+    import numpy as np
+    import sys
+    from oracle.audio_oracle import HifiGanGenerator, hifigan_to_hf_state, logmelfilterbank
+    tr = pytest.importorskip("transformers")
+    gen = HifiGanGenerator(seed=7).eval()
+    with torch.no_grad():
+        gen.mean.normal_(0, 0.5)
+        gen.scale.uniform_(0.5, 2.0)
+        for m in gen.modules():
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.mul_(3.0)
+                m.bias.normal_(0, 0.01)
+    hf = tr.SpeechT5HifiGan(tr.SpeechT5HifiGanConfig()).eval()
+    missing, unexpected = hf.load_state_dict(hifigan_to_hf_state(gen.state_dict()), strict=False)
+    assert not missing and not unexpected
+    mel = torch.randn(2, 40, 80, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        a, b = gen(mel), hf(mel)
+    assert a.shape == (2, 40 * 256) and rel(a, b) < 1e-6
+    # committed fixture (small configuration)
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_audio import TINY_VOCODER
+    z = np.load(AUDIO_GOLDEN)
+    small = HifiGanGenerator(TINY_VOCODER).double().eval()
+    small.load_state_dict({k[len("voc/state/"):]: torch.from_numpy(z[k]).double() for k in z.files
+                           if k.startswith("voc/state/")})
+    with torch.no_grad():
+        out = small(torch.from_numpy(z["voc/in"]).double())
+    assert rel(out, torch.from_numpy(z["voc/out"])) < 1e-6
+    assert np.allclose(logmelfilterbank(z["mel/wav"]), z["mel/logmel"], atol=1e-5)
