@@ -475,6 +475,41 @@ class T5TransformerModelOracle(nn.Module):
         decoder_output, extra = self.decoder(dec_in, tgt_mask, encoder_output, alignment_layer=-1)  # :921-923
         return self.speech_decoder_postnet(decoder_output) + (extra["attn"][0],)
 
+    @torch.no_grad()
+    def generate_speech(self, src_tokens=None, spkembs=None, **kwargs):
+        """models/speecht5.py:1188-1249 for text input: greedy frame-by-frame synthesis until a stop probability of
+        the current r-frame group reaches the threshold (or maxlen). The reference reads the "threshold" key for all
+        three knobs (:1190-1199: threshold, minlenratio AND maxlenratio) -- restated as is: without that key the
+        values are 0.5 / 0.0 / 20.0. The decoder is re-run on the whole prefix each step, which equals the
+        reference's incremental state because the self-attention is causal (identical only with the always-on
+        prenet dropout set to 0: the reference draws a fresh mask for the whole prefix at every step but feeds just
+        the last frame). Returns (mel [L, odim], stop probabilities [L], cross-attention [layers, heads, L/r, T])."""
+        assert src_tokens is not None and src_tokens.size(0) == 1
+        threshold = kwargs.get("threshold", 0.5)
+        minlenratio = kwargs.get("threshold", 0.0)
+        maxlenratio = kwargs.get("threshold", 20.0)
+        encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
+        encoder_out = self.encoder(encoder_input, encoder_padding_mask)
+        r, odim = self.reduction_factor, self.speech_decoder_postnet.odim
+        T_enc = encoder_out["encoder_out"][0].size(0)
+        maxlen, minlen = int(T_enc * maxlenratio / r), int(T_enc * minlenratio / r)
+        ys = encoder_out["encoder_out"][0].new_zeros(1, 1, odim)
+        outs, probs, attns, idx = [], [], [], 0
+        while True:
+            idx += 1
+            decoder_in, _ = self.speech_decoder_prenet(ys, spkembs=spkembs)
+            z, extra = self.decoder(decoder_in, None, encoder_out, alignment_layer=-1)
+            outs.append(self.speech_decoder_postnet.feat_out(z[0, -1]).view(r, odim))
+            probs.append(torch.sigmoid(self.speech_decoder_postnet.prob_out(z[0, -1])))
+            ys = torch.cat((ys, outs[-1][-1].view(1, 1, odim)), dim=1)
+            attns.append(torch.stack([a[0, :, -1:, :] for a in extra["attn"][0]], dim=0))  # [layers, H, 1, T]
+            if int((probs[-1] >= threshold).sum()) > 0 or idx >= maxlen:
+                if idx < minlen:
+                    continue
+                mel = torch.cat(outs, dim=0).unsqueeze(0).transpose(1, 2)  # [1, odim, L]
+                mel = mel + self.speech_decoder_postnet.postnet(mel)
+                return mel.transpose(2, 1).squeeze(0), torch.cat(probs, dim=0), torch.cat(attns, dim=2)
+
 
 # ------------------------------------------------------------------------------------------------ criterion
 def guided_attention_loss(att_ws, ilens, olens, sigma=0.4, alpha=1.0):

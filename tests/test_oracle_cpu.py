@@ -219,3 +219,30 @@ def test_hifigan_oracle_matches_hf_port_and_golden():
         out = small(torch.from_numpy(z["voc/in"]).double())
     assert rel(out, torch.from_numpy(z["voc/out"])) < 1e-6
     assert np.allclose(logmelfilterbank(z["mel/wav"]), z["mel/logmel"], atol=1e-5)
+
+
+def test_tts_generate_speech_matches_hf_port():
+    """models/speecht5.py:1188-1249 (greedy frame-by-frame synthesis with the stop threshold) against the HF port's
+    generate_speech, prenet dropout 0 on both sides; one run to the length cap, one that stops on the threshold."""
+    pytest.importorskip("transformers")
+    from oracle.hf_crosscheck import build_hf
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args
+    for bias, seed in ((-1.5, 0), (0.0, 3)):
+        torch.manual_seed(seed)
+        oracle = T5TransformerModelOracle(base_args(encoder_layers=2, decoder_layers=2, dprenet_dropout_rate=0.0,
+                                                    bert_init=True)).eval()
+        with torch.no_grad():
+            for n, p in oracle.named_parameters():
+                if n.endswith("alpha"):
+                    p.fill_(1.1)
+                if "prob_out.bias" in n:
+                    p.fill_(bias)
+                if "prob_out.weight" in n:
+                    p.mul_(20.0)  # decisive stop logits: no borderline sigmoid(x) ~ 0.5 ties between implementations
+        hf = build_hf(oracle, 2, 2)
+        tok = torch.randint(4, 81, (1, 10))
+        spk = torch.randn(1, 512)
+        mel, probs, attn = oracle.generate_speech(src_tokens=tok, spkembs=spk)
+        ref = hf.generate_speech(tok, speaker_embeddings=spk, threshold=0.5, minlenratio=0.0, maxlenratio=20.0)
+        assert mel.shape == ref.shape and rel(mel, ref) < 1e-5
+        assert probs.numel() == mel.shape[0] and attn.shape[2] == mel.shape[0] // 2
