@@ -151,26 +151,32 @@ class SpeechDecoderPostnet(nn.Module):
         self.num_updates = 0
         self.freeze_decoder_updates = args.freeze_decoder_updates
 
+    def project(self, zs):
+        """zs [B, L/r, C] -> (before [B,L,odim] fp32, stop logits [B,L] fp32): feat_out | prob_out as one GEMM."""
+        B = zs.size(0)
+        nf = self.feat_out.weight.shape[0]
+        fo = ops.linear(zs, (self.feat_out.weight, self.prob_out.weight), (self.feat_out.bias, self.prob_out.bias),
+                        out_dtype=torch.float32)
+        return fo[..., :nf].reshape(B, -1, self.odim), fo[..., nf:].reshape(B, -1)
+
+    def refine(self, before_outs):
+        """before + Postnet(before) (speech_decoder_postnet.py:66-70), channels-last."""
+        if self.postnet is None:
+            return before_outs
+        x = before_outs.to(RT.dtype)  # channels-last [B, L, odim]: the conv GEMM wants time-major rows
+        n = len(self.postnet.postnet)
+        for i, blk in enumerate(self.postnet.postnet):
+            c = ops.conv1d_k5(x, blk[0].weight)
+            x = ops.batch_norm_act(c, blk[1], training=self.training, act="tanh" if i < n - 1 else None,
+                                   drop_p=self.postnet.dropout_rate if self.training else 0.0)
+        return before_outs + x.float()
+
     def forward(self, zs):
         """zs [B, L/r, C] -> before [B,L,odim] fp32, after [B,L,odim] fp32, logits [B,L] fp32."""
         ft = self.freeze_decoder_updates <= self.num_updates
         with torch.no_grad() if not ft else contextlib.ExitStack():
-            B = zs.size(0)
-            nf = self.feat_out.weight.shape[0]
-            fo = ops.linear(zs, (self.feat_out.weight, self.prob_out.weight), (self.feat_out.bias, self.prob_out.bias),
-                            out_dtype=torch.float32)
-            before_outs = fo[..., :nf].reshape(B, -1, self.odim)
-            logits = fo[..., nf:].reshape(B, -1)
-            if self.postnet is None:
-                after_outs = before_outs
-            else:
-                x = before_outs.to(RT.dtype)  # channels-last [B, L, odim]: the conv GEMM wants time-major rows
-                n = len(self.postnet.postnet)
-                for i, blk in enumerate(self.postnet.postnet):
-                    c = ops.conv1d_k5(x, blk[0].weight)
-                    x = ops.batch_norm_act(c, blk[1], training=self.training, act="tanh" if i < n - 1 else None,
-                                           drop_p=self.postnet.dropout_rate if self.training else 0.0)
-                after_outs = before_outs + x.float()
+            before_outs, logits = self.project(zs)
+            after_outs = self.refine(before_outs)
         return before_outs, after_outs, logits
 
     def set_num_updates(self, num_updates):

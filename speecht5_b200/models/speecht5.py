@@ -160,6 +160,50 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
         return self.encoder(encoder_input, encoder_padding_mask)
 
+    @torch.no_grad()
+    def generate_speech(self, source=None, src_tokens=None, spkembs=None, **kwargs):
+        """models/speecht5.py:1188-1249, text input: greedy frame-by-frame synthesis until a stop probability of the
+        current r-frame group reaches the threshold (or maxlen). Same knobs and quirk as the reference, which reads
+        kwargs["threshold"] for the threshold, minlenratio AND maxlenratio (:1190-1199); defaults 0.5 / 0.0 / 20.0.
+        Returns (mel [L, odim] fp32, stop probabilities [L], cross-attention [layers, H, L/r, T_text]).
+
+        The decoder is re-run on the whole prefix every step (causal self-attention makes that equal to the
+        reference's incremental state, and every step reuses the training kernels); a KV cache is the SURVEY 8f
+        follow-up. The always-on prenet dropout therefore draws one mask per step for the whole prefix, where the
+        reference keeps the cached keys/values of earlier draws -- identical in distribution for the newest frame."""
+        assert source is not None or src_tokens is not None
+        if source is not None:
+            raise NotImplementedError("generate_speech from speech input (voice conversion) is not built yet")
+        assert src_tokens.size(0) == 1
+        threshold = kwargs.get("threshold", 0.5)
+        minlenratio = kwargs.get("threshold", 0.0)
+        maxlenratio = kwargs.get("threshold", 20.0)
+        if spkembs is not None and getattr(self.args, "spk_embed_integration_type", "pre") != "pre":
+            raise NotImplementedError("spk_embed_integration_type != 'pre'")
+        encoder_out = self.forward_text_encoder(src_tokens)
+        post = self.speech_decoder_postnet
+        r, odim = self.reduction_factor, post.odim
+        T_enc = encoder_out["encoder_out"][0].size(0)
+        maxlen, minlen = int(T_enc * maxlenratio / r), int(T_enc * minlenratio / r)
+        ys = torch.zeros(1, 1, odim, dtype=torch.float32, device=src_tokens.device)
+        outs, probs, attns, idx = [], [], [], 0
+        while True:
+            idx += 1
+            decoder_in, _ = self.speech_decoder_prenet(ys, spkembs=spkembs)
+            z, extra = self.decoder(decoder_in, None, encoder_out, alignment_layer=-1)
+            before, logits = post.project(z[:, -1:].contiguous())  # [1, r, odim], [1, r]
+            outs.append(before[0])
+            probs.append(torch.sigmoid(logits[0]))
+            ys = torch.cat((ys, before[:, -1:, :]), dim=1)
+            layer_attn = extra["attn"][0]
+            layer_attn = layer_attn if isinstance(layer_attn, (list, tuple)) else [layer_attn]
+            attns.append(torch.stack([a[0, :, -1:, :].float() for a in layer_attn], dim=0))  # [layers, H, 1, T]
+            if bool((probs[-1] >= threshold).any()) or idx >= maxlen:
+                if idx < minlen:
+                    continue
+                mel = post.refine(torch.cat(outs, dim=0).unsqueeze(0))[0]
+                return mel, torch.cat(probs, dim=0), torch.cat(attns, dim=2)
+
 
 # ---------------------------------------------------------------------------------------------- architectures
 @register_model_architecture(model_name="t5_transformer", arch_name="t5_transformer")

@@ -125,3 +125,34 @@ def test_dropout_training_step_runs_and_is_reproducible(cuda):
         assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
         losses.append(loss.item())
     assert losses[0] == losses[1]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 6e-2)])
+def test_generate_speech_matches_oracle(cuda, dtype, tol):
+    """models/speecht5.py:1188-1249 greedy synthesis: (a) the reference's quirk -- kwargs["threshold"] also sets the
+    length ratios, so threshold=0.5 runs exactly int(T * 0.5 / r) steps; (b) defaults with decisive stop logits."""
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args
+    over = dict(encoder_layers=2, decoder_layers=2, dprenet_dropout_rate=0.0, bert_init=True)
+    torch.manual_seed(11)
+    oracle = T5TransformerModelOracle(base_args(**over)).eval()
+    with torch.no_grad():
+        for n, p in oracle.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(1.1)
+            if "prob_out.weight" in n:
+                p.mul_(20.0)  # decisive stop logits: no sigmoid(x) ~ 0.5 ties between the implementations
+    model = _build(cuda, dtype, **over).eval()
+    model.load_state_dict(oracle.state_dict())
+    tok = torch.randint(4, 81, (1, 12))
+    spk = torch.randn(1, 512)
+    for kw in (dict(threshold=0.5), dict()):
+        if not kw:  # (b): stop early for sure -- a large positive bias on the second frame's stop logit
+            with torch.no_grad():
+                oracle.speech_decoder_postnet.prob_out.bias[1] = 50.0
+            model.load_state_dict(oracle.state_dict())
+        mel_ref, probs_ref, attn_ref = oracle.generate_speech(src_tokens=tok, spkembs=spk, **kw)
+        mel, probs, attn = model.generate_speech(src_tokens=tok.to(cuda), spkembs=spk.to(cuda), **kw)
+        assert mel.shape == mel_ref.shape and probs.shape == probs_ref.shape and attn.shape == attn_ref.shape
+        assert rel(mel, mel_ref) < tol
+        assert rel(attn, attn_ref) < max(tol, 1e-3)
+    assert mel_ref.shape[0] == 2  # case (b) stopped on the first step
