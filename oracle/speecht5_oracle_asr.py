@@ -357,3 +357,52 @@ def compute_mask_indices_static(B, T, padding_mask, mask_prob, mask_length, rng,
             idc = rng.choice(idc, min_len, replace=False)
         mask[b, idc] = True
     return torch.from_numpy(mask)
+
+
+# ------------------------------------------------------------------------------------------------ greedy decode (row 21)
+@torch.no_grad()
+def greedy_decode(model, source, padding_mask=None, max_len_a=0.0, max_len_b=200, min_len=1, max_positions=600,
+                  pad=1, eos=2, unk=3, blank=0, mask_idx=None, unk_penalty=0.0, temperature=1.0):
+    """speecht5/sequence_generator.py:207-655 with beam 1, ctc_weight 0, no LM fusion (the `generate.py` greedy
+    setting the north-star parity statement refers to: token ids must match bit for bit).
+
+    Encoder once (speecht5.py:1133-1149 forward_encoder); per step the decoder on the prefix, log_softmax / T
+    (:1151-1164), then the reference's masking order (:430-446): eos forbidden before min_len, NaN -> -inf, pad never,
+    unk penalty, CTC blank (and mask symbol) never, only eos at step >= max_len; argmax. The prefix starts with eos
+    (bos_token None, :303). max_len = min(int(a * src_len + b), max_positions - 1) where src_len is the PADDED source
+    length (waveform samples for speech input, :249,262-265). Returns a list of 1-D token tensors ending in eos."""
+    B = source.size(0)
+    src_len = source.size(1)
+    max_len = min(int(max_len_a * src_len + max_len_b), max_positions - 1)
+    assert min_len <= max_len
+    x, enc_pad, _ = model.speech_encoder_prenet(source, padding_mask, None, None)
+    enc = model.encoder(x, enc_pad)
+    tokens = torch.full((B, max_len + 2), pad, dtype=torch.long)
+    tokens[:, 0] = eos
+    done = [False] * B
+    out = [None] * B
+    for step in range(max_len + 1):
+        dec_in, tgt_mask = model.text_decoder_prenet(tokens[:, : step + 1])
+        z, _ = model.decoder(dec_in, tgt_mask, enc, alignment_layer=None)
+        logits = model.text_decoder_postnet(z[:, -1:, :])[:, -1, :]
+        lprobs = F.log_softmax(logits.float() / temperature, dim=-1)
+        if step < min_len:
+            lprobs[:, eos] = -math.inf
+        lprobs[lprobs != lprobs] = -math.inf
+        lprobs[:, pad] = -math.inf
+        lprobs[:, unk] -= unk_penalty
+        lprobs[:, blank] = -math.inf
+        if mask_idx is not None and mask_idx != unk:
+            lprobs[:, mask_idx] = -math.inf
+        if step >= max_len:
+            lprobs[:, :eos] = -math.inf
+            lprobs[:, eos + 1:] = -math.inf
+        nxt = lprobs.argmax(dim=-1)
+        tokens[:, step + 1] = nxt
+        for b in range(B):
+            if not done[b] and int(nxt[b]) == eos:
+                done[b] = True
+                out[b] = tokens[b, 1: step + 2].clone()
+        if all(done):
+            break
+    return out

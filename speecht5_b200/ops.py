@@ -135,6 +135,18 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _pe_bf16(pe_k):
+    """bf16 copy of the relative-position table. A Parameter is cached per parameter epoch; a computed tensor (the
+    pre-LN layers pass norm_k(table), transformer_layer.py:94-95) is cast every call -- its id() is not stable."""
+    if isinstance(pe_k, torch.nn.Parameter):
+        return RT.shadow(("pe", id(pe_k)), lambda: pe_k)[0]
+    src = pe_k.detach()
+    src = src if (src.dtype == torch.float32 and src.is_contiguous()) else src.float().contiguous()
+    hi = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    K.cast_bf16(src, hi, None)
+    return hi
+
+
 def _resolve_act(act, dtype):
     """Throughput mode (bf16 activations) evaluates GELU in its tanh form on the MUFU unit (|error| <= 4.8e-4, below
     bf16 rounding of the result); parity mode (fp32) keeps the reference's exact erf form (fairseq/modules/gelu.py:24)."""
@@ -657,7 +669,7 @@ class AttentionTCFn(torch.autograd.Function):
             drop_p = cfg.get("drop_p", 0.0)
             off = RT.next_offset() if drop_p > 0 else 0
             kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
-            pe_hi = RT.shadow(("pe", id(pe_k)), lambda: pe_k)[0]
+            pe_hi = _pe_bf16(pe_k)
             P = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
             out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
             a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=0, maxpos=maxpos,
@@ -699,7 +711,7 @@ class AttentionTCFn(torch.autograd.Function):
         QP, pe_hi, R = None, None, 0
         if pe_k is not None:
             R = pe_k.shape[0]
-            pe_hi = RT.shadow(("pe", id(pe_k)), lambda: pe_k)[0]
+            pe_hi = _pe_bf16(pe_k)
             QP = torch.empty((B, H, Tq, R), dtype=torch.float32, device=dev)
             K.gemm(qv, pe_hi, QP, M=Tq, N=R, K=64, a_ld=q_ld, b_ld=64, c_ld=R, nb1=H, nb2=B, a_bs=(64, q_bs),
                    b_bs=(0, 0), c_bs=(Tq * R, H * Tq * R), alpha=scale)

@@ -156,3 +156,45 @@ def test_generate_speech_matches_oracle(cuda, dtype, tol):
         assert rel(mel, mel_ref) < tol
         assert rel(attn, attn_ref) < max(tol, 1e-3)
     assert mel_ref.shape[0] == 2  # case (b) stopped on the first step
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 8e-2)])
+def test_large_style_pre_layernorm_against_oracle(cuda, dtype, tol):
+    """t5_transformer_large structure (models/speecht5.py:1402-1425): pre-LN encoder layers with norm_k on the
+    relative-position table (transformer_layer.py:90-111), pre-LN decoder layers + final decoder LayerNorm
+    (decoder_normalize_before), at reduced width; forward, loss and gradients incl. norm_k and the table."""
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args, synthetic_tts_batch, tts_loss
+    over = dict(encoder_layers=2, decoder_layers=2, encoder_embed_dim=128, encoder_ffn_embed_dim=256,
+                encoder_attention_heads=2, decoder_embed_dim=128, decoder_ffn_embed_dim=256, decoder_attention_heads=2,
+                layer_norm_first=True, decoder_normalize_before=True, bert_init=True, **NO_DROPOUT)
+    torch.manual_seed(13)
+    oracle = T5TransformerModelOracle(base_args(**over)).train()
+    with torch.no_grad():
+        for n, p in oracle.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(0.9)
+            elif "q_proj.weight" in n or "k_proj.weight" in n or "pe_k" in n:
+                p.mul_(6.0)
+            elif "norm_k" in n or "layer_norm" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+    sample = synthetic_tts_batch(3, 37, 50, seed=4)
+    state0 = {k: v.clone() for k, v in oracle.state_dict().items()}
+    out_ref = oracle(**sample["net_input"])
+    loss_ref = tts_loss(out_ref, sample)[0]
+    loss_ref.backward()
+    model = _build(cuda, dtype, **over).train()
+    model.load_state_dict(state0)
+    s = to_device(sample, cuda)
+    before, after, logits, attn = model(**s["net_input"])
+    assert rel(after, out_ref[1]) < tol and rel(before, out_ref[0]) < tol
+    loss = _criterion().compute_loss(model, (before, after, logits, attn), s)[0]
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < tol * 3
+    loss.backward()
+    ref = dict(oracle.named_parameters())
+    got = dict(model.named_parameters())
+    gtol = 5e-3 if dtype == torch.float32 else 0.25
+    for n in ("encoder.layers.0.norm_k.weight", "encoder.layers.1.norm_k.bias", "encoder.pos_emb.pe_k.weight",
+              "encoder.layers.0.self_attn_layer_norm.weight", "decoder.layer_norm.weight",
+              "decoder.layers.1.fc1.weight", "encoder.layers.1.fc2.weight"):
+        assert got[n].grad is not None, n
+        assert rel(got[n].grad, ref[n].grad) < gtol, (n, rel(got[n].grad, ref[n].grad))

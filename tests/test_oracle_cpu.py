@@ -246,3 +246,27 @@ def test_tts_generate_speech_matches_hf_port():
         ref = hf.generate_speech(tok, speaker_embeddings=spk, threshold=0.5, minlenratio=0.0, maxlenratio=20.0)
         assert mel.shape == ref.shape and rel(mel, ref) < 1e-5
         assert probs.numel() == mel.shape[0] and attn.shape[2] == mel.shape[0] // 2
+
+
+def test_asr_greedy_decode_matches_hf_generate():
+    """sequence_generator.py greedy path (beam 1, no CTC/LM fusion) vs transformers' greedy generate with the same
+    start token and pad/blank suppression: identical token ids up to the length cap, where the reference forces eos."""
+    pytest.importorskip("transformers")
+    from oracle.hf_crosscheck_asr import build_hf_asr
+    from oracle.speecht5_oracle_asr import T5TransformerModelASROracle, base_asr_args, greedy_decode
+    torch.manual_seed(1)
+    oracle = T5TransformerModelASROracle(base_asr_args(encoder_layers=2, decoder_layers=2, bert_init=True)).eval()
+    with torch.no_grad():
+        oracle.text_decoder_postnet.output_projection.weight.mul_(30.0)  # decisive logits (no argmax ties)
+    hf = build_hf_asr(oracle, 2, 2)
+    wav = torch.randn(2, 8000) * 0.1
+    cap = 12
+    hyp = greedy_decode(oracle, wav, None, max_len_b=cap)
+    gen = hf.generate(input_values=wav, do_sample=False, num_beams=1, max_new_tokens=cap, min_new_tokens=2,
+                      decoder_start_token_id=2, eos_token_id=2, pad_token_id=1, suppress_tokens=[0, 1])
+    for b in range(2):
+        h = hyp[b].tolist()
+        assert h[-1] == 2 and len(h) <= cap + 1
+        ref = gen[b, 1:].tolist()
+        n = min(len(h) - 1, len(ref))
+        assert h[:n] == ref[:n]
