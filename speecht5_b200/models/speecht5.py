@@ -11,6 +11,7 @@ from argparse import Namespace
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..fairseq_shim import FairseqEncoderDecoderModel, register_model, register_model_architecture
 from ..ops import RT
@@ -155,6 +156,45 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
 
     def max_positions(self):
         return (self.args.max_speech_positions, self.args.max_text_positions)
+
+    # ---- criterion-facing helpers of the reference model (models/speecht5.py:731-784). They post-process tensors the
+    # device path produced (vocabulary-sized softmax of the text heads); the text-output heads themselves are "next" rows.
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        logits = net_output[0]
+        out = F.log_softmax(logits.float(), dim=-1) if log_probs else F.softmax(logits.float(), dim=-1)
+        out.batch_first = True  # :739
+        return out
+
+    def get_normalized_probs_for_ctc(self, net_output, log_probs):
+        logits = net_output["encoder_out_for_ctc"][0]
+        return F.log_softmax(logits.float(), dim=-1) if log_probs else F.softmax(logits.float(), dim=-1)
+
+    def get_logits(self, net_output, is_masked=True):
+        logits_list = net_output["logit_m_list"] if is_masked else net_output["logit_u_list"]
+        return [x.float() for x in logits_list if x is not None]
+
+    def get_targets(self, sample, net_output, is_masked=True):
+        if "logit_m_list" in net_output:
+            return [x.new_zeros(x.size(0), dtype=torch.long) for x in self.get_logits(net_output, is_masked)]
+        return sample["target"]
+
+    def get_extra_losses(self, net_output):
+        extra_losses, names = [], []
+        if "features_pen" in net_output:
+            extra_losses.append(net_output["features_pen"])
+            names.append("features_pen")
+        if "prob_perplexity" in net_output:
+            extra_losses.append((net_output["num_vars"] - net_output["prob_perplexity"]) / net_output["num_vars"])
+            names.append("prob_perplexity")
+        return extra_losses, names
+
+    def forward_encoder(self, source, padding_mask=None):
+        raise NotImplementedError("speech input (conv feature extractor + speech encoder prenet) is a 'next' row: "
+                                  "SURVEY.md section 8a rows 2-3; use forward_text_encoder for text input")
+
+    def forward_decoder(self, tokens, encoder_out, incremental_state):
+        raise NotImplementedError("text decoding (text decoder pre/post-net, incremental state) is a 'next' row: "
+                                  "SURVEY.md section 8a rows 9, 14, 21")
 
     def forward_text_encoder(self, src_tokens):
         encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)

@@ -108,3 +108,27 @@ def test_gradient_exchange_is_mean_over_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(err < 1e-6 for _, err in res), res
+
+
+def test_model_exposes_the_reference_model_api():
+    """SURVEY 8(b) Python face: the callers' methods exist with the reference behaviour; unbuilt branches raise
+    NotImplementedError instead of falling back."""
+    import pytest
+    from speecht5_b200.models import T5TransformerModel
+    for m in ("build_model", "forward", "set_num_updates", "load_state_dict", "max_positions", "forward_text_encoder",
+              "generate_speech", "get_normalized_probs", "get_normalized_probs_for_ctc", "get_logits", "get_targets",
+              "get_extra_losses", "forward_encoder", "forward_decoder"):
+        assert callable(getattr(T5TransformerModel, m)), m
+    dummy = T5TransformerModel.__new__(T5TransformerModel)
+    logits = torch.randn(2, 5, 11)
+    lp = T5TransformerModel.get_normalized_probs(dummy, (logits, None), log_probs=True)
+    assert lp.batch_first and torch.allclose(lp.exp().sum(-1), torch.ones(2, 5), atol=1e-5)
+    ctc = T5TransformerModel.get_normalized_probs_for_ctc(dummy, {"encoder_out_for_ctc": [logits]}, log_probs=False)
+    assert torch.allclose(ctc.sum(-1), torch.ones(2, 5), atol=1e-5)
+    assert T5TransformerModel.get_targets(dummy, {"target": 7}, {}) == 7
+    losses, names = T5TransformerModel.get_extra_losses(dummy, {"features_pen": torch.tensor(2.0)})
+    assert names == ["features_pen"] and float(losses[0]) == 2.0
+    with pytest.raises(NotImplementedError):
+        T5TransformerModel.forward_encoder(dummy, torch.zeros(1, 16000))
+    with pytest.raises(NotImplementedError):
+        T5TransformerModel.forward_decoder(dummy, None, None, None)
