@@ -406,3 +406,39 @@ def greedy_decode(model, source, padding_mask=None, max_len_a=0.0, max_len_b=200
         if all(done):
             break
     return out
+
+
+# ------------------------------------------------------------------------------------------------ text in / text out
+class T5TransformerModelT2TOracle(nn.Module):
+    """models/speecht5.py:786-963, text input + text output (the BART-style text branch of pre-training and the MT-like
+    fine-tunes): text encoder prenet (espnet scaled positional encoding) -> shared encoder -> text decoder prenet ->
+    decoder -> vocabulary projection. Returns the reference's ((logits, None), codebook_out = {}, encoder_output)."""
+
+    def __init__(self, args, vocab_size=81, padding_idx=1):
+        super().__init__()
+        from .speecht5_oracle import TextEncoderPrenet
+        self.args = args
+        d = args.encoder_embed_dim
+
+        def embedding():
+            m = nn.Embedding(vocab_size, d, padding_idx=padding_idx)
+            nn.init.normal_(m.weight, mean=0, std=d ** -0.5)
+            nn.init.constant_(m.weight[padding_idx], 0)
+            return m
+
+        dec_embed = embedding()
+        enc_embed = dec_embed if args.share_input_output_embed else embedding()
+        self.encoder = TransformerEncoder(args, vocab_size, enc_embed)
+        self.decoder = TransformerDecoder(args)
+        self.text_encoder_prenet = TextEncoderPrenet(enc_embed, args)
+        self.text_decoder_prenet = TextDecoderPrenet(dec_embed, args)
+        self.text_decoder_postnet = TextDecoderPostnet(dec_embed, vocab_size, args)
+        if args.bert_init:
+            self.apply(init_bert_params)
+
+    def forward(self, src_tokens=None, prev_output_tokens=None, **unused):
+        encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
+        encoder_output = self.encoder(encoder_input, encoder_padding_mask)
+        dec_in, tgt_mask = self.text_decoder_prenet(prev_output_tokens)
+        decoder_output, _ = self.decoder(dec_in, tgt_mask, encoder_output, alignment_layer=None)
+        return (self.text_decoder_postnet(decoder_output), None), {}, encoder_output

@@ -62,6 +62,91 @@ class TextEncoderPrenet(nn.Module):
         return x, src_tokens.eq(self.padding_idx)
 
 
+def fairseq_sinusoid_table(num_embeddings, dim, padding_idx, device):
+    """fairseq/modules/sinusoidal_positional_embedding.py:36-58: [sin | cos] halves, divisor half_dim - 1, zero row at
+    padding_idx (fp64 build, fp32 storage)."""
+    half = dim // 2
+    step = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float64) * -step)
+    ang = torch.arange(num_embeddings, dtype=torch.float64)[:, None] * freq[None, :]
+    emb = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
+    if dim % 2 == 1:
+        emb = torch.cat([emb, torch.zeros(num_embeddings, 1, dtype=torch.float64)], dim=1)
+    emb[padding_idx, :] = 0
+    return emb.float().to(device)
+
+
+class TextDecoderPrenet(nn.Module):
+    """models/modules/text_decoder_prenet.py:29-124: embed_scale * E[tok] + sinusoidal positions (fairseq layout),
+    dropout. One launch (the embedding + positional kernel of the text encoder prenet with a unit alpha).
+
+    Targets are right-padded (fairseq collaters), so the position of the t-th symbol is padding_idx + 1 + t
+    (fairseq/utils.py:247-257); padded slots get a position row too, but they are masked as keys and ignored by
+    every loss. Built configuration: no_scale_embedding (the arch default), sinusoidal positions, no LayerNorm on the
+    embedding, no quant noise -- anything else raises at construction."""
+
+    def __init__(self, embed_tokens, args):
+        super().__init__()
+        assert args.no_scale_embedding, "embed_scale != 1 is not built (arch default: no_scale_embedding=True)"
+        assert not getattr(args, "decoder_learned_pos", False) and not getattr(args, "layernorm_embedding", False)
+        assert not getattr(args, "no_token_positional_embeddings", False) and getattr(args, "quant_noise_pq", 0) == 0
+        self.embed_tokens = embed_tokens
+        self.padding_idx = embed_tokens.padding_idx
+        self.embed_dim = args.decoder_embed_dim
+        self.dropout_p = args.dropout
+        self.max_positions = args.max_text_positions
+        self.register_buffer("_unit", torch.ones(()), persistent=False)
+        self._pe = None
+        self.num_updates = 0
+        self.freeze_decoder_updates = args.freeze_decoder_updates
+
+    def _table(self, length, device):
+        need = self.padding_idx + 1 + length
+        if self._pe is None or self._pe.shape[0] < need or self._pe.device != device:
+            self._pe = fairseq_sinusoid_table(max(need, self.padding_idx + 1 + self.max_positions), self.embed_dim,
+                                              self.padding_idx, device)
+        return self._pe[self.padding_idx + 1: self.padding_idx + 1 + length]
+
+    def forward(self, prev_output_tokens, incremental_state=None):
+        if incremental_state is not None:
+            raise NotImplementedError("incremental decoding is a 'next' row (SURVEY.md section 8f)")
+        ft = self.freeze_decoder_updates <= self.num_updates
+        with torch.no_grad() if not ft else contextlib.ExitStack():
+            pe = self._table(prev_output_tokens.shape[1], prev_output_tokens.device)
+            x = ops.scaled_posenc(pe, self._unit, self.dropout_p if self.training else 0.0,
+                                  tokens=prev_output_tokens.contiguous(), emb=self.embed_tokens.weight,
+                                  padding_idx=self.padding_idx)
+        return x, prev_output_tokens.eq(self.padding_idx), incremental_state
+
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+
+
+class TextDecoderPostnet(nn.Module):
+    """models/modules/text_decoder_postnet.py:21-93: vocabulary projection, tied to the embedding under
+    --share-input-output-embed (no adaptive softmax)."""
+
+    def __init__(self, embed_tokens, vocab_size, args):
+        super().__init__()
+        assert getattr(args, "adaptive_softmax_cutoff", None) is None, "adaptive softmax is not built"
+        d = getattr(args, "decoder_output_dim", args.decoder_embed_dim)
+        self.output_projection = nn.Linear(d, vocab_size, bias=False)
+        if args.share_input_output_embed:
+            self.output_projection.weight = embed_tokens.weight
+        else:
+            nn.init.normal_(self.output_projection.weight, mean=0, std=d ** -0.5)
+        self.num_updates = 0
+        self.freeze_decoder_updates = args.freeze_decoder_updates
+
+    def forward(self, x):
+        ft = self.freeze_decoder_updates <= self.num_updates
+        with torch.no_grad() if not ft else contextlib.ExitStack():
+            return ops.linear(x, self.output_projection.weight, (), out_dtype=torch.float32)
+
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+
+
 class _TacotronPrenet(nn.Module):
     """espnet tacotron2.decoder.Prenet holder: prenet.{i}.0 = Linear; dropout is ALWAYS active (F.dropout default)."""
 

@@ -15,7 +15,8 @@ import torch.nn.functional as F
 
 from ..fairseq_shim import FairseqEncoderDecoderModel, register_model, register_model_architecture
 from ..ops import RT
-from .modules.nets import SpeechDecoderPostnet, SpeechDecoderPrenet, TextEncoderPrenet
+from .modules.nets import (SpeechDecoderPostnet, SpeechDecoderPrenet, TextDecoderPostnet, TextDecoderPrenet,
+                           TextEncoderPrenet)
 from .modules.transformer import MultiheadAttention, TransformerDecoder, TransformerEncoder
 
 logger = logging.getLogger(__name__)
@@ -106,8 +107,14 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         text_encoder_prenet = TextEncoderPrenet(text_encoder_embed_tokens, args)
         speech_decoder_prenet = SpeechDecoderPrenet(speech_odim, args)
         speech_decoder_postnet = SpeechDecoderPostnet(speech_odim, args)
-        return cls(args, encoder, decoder, text_encoder_prenet, None, None, speech_decoder_prenet, None,
-                   speech_decoder_postnet, None, None)
+        # text decoder pre/post-net: opt-in (--build-text-decoder) until the rest of the
+        # text-output path (ASR front-end, incremental decoding) is built; the reference always constructs them
+        text_decoder_prenet = text_decoder_postnet = None
+        if getattr(args, "build_text_decoder", False):
+            text_decoder_prenet = TextDecoderPrenet(text_decoder_embed_tokens, args)
+            text_decoder_postnet = TextDecoderPostnet(text_decoder_embed_tokens, len(text_dict), args)
+        return cls(args, encoder, decoder, text_encoder_prenet, None, text_decoder_prenet, speech_decoder_prenet,
+                   text_decoder_postnet, speech_decoder_postnet, None, None)
 
     # ------------------------------------------------------------------ forward (models/speecht5.py:786-963)
     def forward(self, source=None, src_tokens=None, src_lengths=None, prev_output_tokens=None, tgt_lengths=None,
@@ -116,7 +123,9 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         assert source is not None or src_tokens is not None
         input_type = "text" if (source is None and padding_mask is None and not feature_only) else "speech"
         output_type = "text" if (prev_output_tokens is not None and prev_output_tokens.dim() == 2) else "speech"
-        if input_type != "text" or output_type != "speech" or target_list is not None:
+        t2t = input_type == "text" and output_type == "text" and self.text_decoder_prenet is not None
+        if (input_type != "text" or output_type != "speech" or target_list is not None) and not (
+                t2t and target_list is None):
             raise NotImplementedError(
                 f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built yet in the "
                 "B200 path; round 1 covers text->speech (t2s)")
@@ -128,6 +137,13 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         hook = getattr(self, "_encoder_grad_hook", None)  # set by B200Trainer: gradient-exchange overlap point
         if hook is not None and encoder_output["encoder_out"][0].requires_grad:
             encoder_output["encoder_out"][0].register_hook(hook)
+        if t2t:  # text in / text out (:901-903, 955-957): decoder on token embeddings, vocabulary logits
+            dec_in, tgt_mask, _ = self.text_decoder_prenet(prev_output_tokens)
+            decoder_output, extra = self.decoder(
+                dec_in, tgt_mask, encoder_output,
+                full_context_alignment=getattr(self.args, "decoder_full_context_alignment", False),
+                alignment_layer=None)
+            return (self.text_decoder_postnet(decoder_output), None), {}, encoder_output
         prev_output_tokens, tgt_mask = self.speech_decoder_prenet(prev_output_tokens, tgt_lengths, spkembs)
         decoder_output, extra = self.decoder(
             prev_output_tokens, tgt_mask, encoder_output,

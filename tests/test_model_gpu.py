@@ -201,3 +201,62 @@ def test_large_style_pre_layernorm_against_oracle(cuda, dtype, tol):
               "decoder.layers.1.fc1.weight", "encoder.layers.1.fc2.weight"):
         assert got[n].grad is not None, n
         assert rel(got[n].grad, ref[n].grad) < gtol, (n, rel(got[n].grad, ref[n].grad))
+
+
+@pytest.mark.skipif(os.environ.get("ST5_TEST_T2T") != "1",
+                    reason="opt-in branch (--build-text-decoder) not yet confirmed on a B200: run with ST5_TEST_T2T=1")
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 6e-2)])
+def test_text_to_text_branch_against_oracle(cuda, dtype, tol):
+    """SURVEY 8a rows 9 + 14 on the CUDA path (opt-in --build-text-decoder): text decoder prenet (embedding + fairseq
+    sinusoidal positions), decoder, tied vocabulary projection; logits, label-smoothed CE and gradients vs the oracle."""
+    from oracle.speecht5_oracle_asr import T5TransformerModelT2TOracle, base_asr_args, label_smoothed_nll_loss
+    import torch.nn.functional as F
+    over = dict(encoder_layers=2, decoder_layers=2, share_input_output_embed=True, bert_init=True, **NO_DROPOUT)
+    torch.manual_seed(21)
+    oracle = T5TransformerModelT2TOracle(base_asr_args(**over)).train()
+    with torch.no_grad():
+        for n, p in oracle.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(0.9)
+            elif "q_proj.weight" in n or "k_proj.weight" in n or "pe_k" in n:
+                p.mul_(6.0)
+    g = torch.Generator().manual_seed(5)
+    B, Ts, Tt, V, pad, eos = 3, 19, 14, 81, 1, 2
+    src = torch.randint(4, V, (B, Ts), generator=g)
+    src[1, 15:] = pad
+    tgt = torch.randint(4, V, (B, Tt), generator=g)
+    tgt[:, -1] = eos
+    tgt[2, 9] = eos
+    tgt[2, 10:] = pad
+    prev = torch.full_like(tgt, pad)
+    prev[:, 0] = eos
+    prev[:, 1:] = tgt[:, :-1]
+    prev[2, 10:] = pad
+
+    def loss_of(logits):
+        lp = F.log_softmax(logits.float(), dim=-1)
+        return label_smoothed_nll_loss(lp.view(-1, V), tgt.to(logits.device).view(-1), 0.1, pad)[0]
+
+    (logits_ref, _), _, _ = oracle(src_tokens=src, prev_output_tokens=prev)
+    loss_ref = loss_of(logits_ref)
+    loss_ref.backward()
+    model = _build(cuda, dtype, build_text_decoder=True, **over).train()
+    model.load_state_dict(oracle.state_dict())
+    (logits, _), codebook_out, enc_out = model(src_tokens=src.to(cuda), prev_output_tokens=prev.to(cuda))
+    keep = tgt.ne(pad)
+    assert codebook_out == {} and logits.shape == logits_ref.shape
+    assert rel(logits.cpu()[keep], logits_ref[keep]) < tol
+    loss = loss_of(logits)
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < tol * 3
+    loss.backward()
+    ref, got = dict(oracle.named_parameters()), dict(model.named_parameters())
+    gtol = 5e-3 if dtype == torch.float32 else 0.25
+    # the embedding is shared by the text encoder prenet, the text decoder prenet and the output projection
+    e_got, e_ref = model.text_decoder_prenet.embed_tokens.weight, oracle.text_decoder_prenet.embed_tokens.weight
+    assert model.text_decoder_postnet.output_projection.weight is e_got
+    assert rel(e_got.grad, e_ref.grad) < gtol, rel(e_got.grad, e_ref.grad)
+    for n in ("decoder.layers.0.self_attn.v_proj.weight",
+              "decoder.layers.1.encoder_attn.q_proj.weight", "encoder.layers.1.fc1.weight",
+              "text_encoder_prenet.encoder_prenet.1.alpha"):
+        assert got[n].grad is not None, n
+        assert rel(got[n].grad, ref[n].grad) < gtol, (n, rel(got[n].grad, ref[n].grad))
