@@ -270,3 +270,61 @@ def test_asr_greedy_decode_matches_hf_generate():
         ref = gen[b, 1:].tolist()
         n = min(len(h) - 1, len(ref))
         assert h[:n] == ref[:n]
+
+
+# ---------------------------------------------------------------------------------------------- pre-training extras (row 22)
+def test_gumbel_quantizer_oracle_matches_hf_wav2vec2_quantizer_in_eval():
+    """fairseq GumbelVectorQuantizer restated; pinned in eval mode (hard codes) against the independent transformers
+    Wav2Vec2GumbelVectorQuantizer (same variables layout [1, G*V, d/G], same projection)."""
+    tr = pytest.importorskip("transformers")
+    from transformers.models.wav2vec2.modeling_wav2vec2 import Wav2Vec2GumbelVectorQuantizer
+    from oracle.pretrain_oracle import GumbelVectorQuantizer
+    torch.manual_seed(0)
+    d, V, G = 64, 10, 2
+    q = GumbelVectorQuantizer(dim=d, num_vars=V, groups=G, vq_dim=d).eval()
+    cfg = tr.Wav2Vec2Config(conv_dim=(d,), conv_stride=(2,), conv_kernel=(2,), num_codevectors_per_group=V,
+                            num_codevector_groups=G, codevector_dim=d)
+    hf = Wav2Vec2GumbelVectorQuantizer(cfg).eval()
+    with torch.no_grad():
+        hf.codevectors.copy_(q.vars)
+        hf.weight_proj.weight.copy_(q.weight_proj.weight)
+        hf.weight_proj.bias.copy_(q.weight_proj.bias)
+    x = torch.randn(3, 17, d)
+    with torch.no_grad():
+        out = q(x)
+        ref, ppl = hf(x)
+    assert rel(out["x"], ref) < 1e-6
+    assert abs(float(out["code_perplexity"]) - float(ppl)) / float(ppl) < 1e-5
+    # training mode with an explicit noise draw: straight-through one-hot of argmax((logits + g) / tau)
+    q.train()
+    g = -torch.empty(3 * 17 * G, V).exponential_().log()
+    out_t = q(x, gumbel_noise=g)
+    logits = q.weight_proj(x.reshape(-1, d)).view(-1, V)
+    idx = (logits + g).argmax(-1).view(3 * 17, G)
+    want = torch.cat([q.vars[0, idx[:, gi] + gi * V] for gi in range(G)], dim=-1).view(3, 17, d)
+    assert rel(out_t["x"], want) < 1e-5
+
+
+def test_hubert_head_oracle_closed_form():
+    """speech_encoder_postnet.py:61-74: logits[n, 0] = cos(proj(x_n), e[target_n]) / T and logits[n, 1 + c] =
+    cos(proj(x_n), e[c]) / T, with the duplicate of the positive among the negatives masked to -inf."""
+    import torch.nn.functional as F
+    from oracle.pretrain_oracle import SpeechEncoderPostnet
+    torch.manual_seed(1)
+    head = SpeechEncoderPostnet([7], encoder_embed_dim=32, final_dim=16, logit_temp=0.1)
+    x = torch.randn(2, 9, 32)
+    pad = torch.zeros(2, 9, dtype=torch.bool)
+    pad[1, 7:] = True
+    mask = torch.rand(2, 9) < 0.5
+    tgt = torch.randint(0, 7, (2, 9))
+    out = head(x, pad, mask, [tgt])
+    sel = ~pad & mask
+    proj = head.final_proj(x[sel])
+    e = head.label_embs_concat
+    want = torch.stack([F.cosine_similarity(proj, e[tgt[sel]], dim=-1)] +
+                       [F.cosine_similarity(proj, e[c].expand_as(proj), dim=-1) for c in range(7)], dim=1) / 0.1
+    got = out["logit_m_list"][0]
+    dup = torch.zeros_like(want, dtype=torch.bool)
+    dup[torch.arange(want.size(0)), 1 + tgt[sel]] = True
+    assert torch.isinf(got[dup]).all() and rel(got[~dup], want[~dup]) < 1e-6
+    assert out["logit_u_list"][0].shape == (int((~pad & ~mask).sum()), 8)
