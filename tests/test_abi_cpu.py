@@ -33,11 +33,38 @@ def test_version_and_error_text(lib):
     assert isinstance(lib.st5_last_error(), bytes)
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors in speecht5_b200/_lib.py must have exactly the layout a C compiler gives the structs of
+    include/speecht5_b200.h: gcc compiles the header and prints sizeof / offsetof of every field."""
+    import shutil
+    import subprocess
     from speecht5_b200._lib import AttnArgs, GemmArgs
-    # C layout computed by hand from the header: ints first, then 8-byte aligned pointers / int64
-    assert ctypes.sizeof(GemmArgs) == 5 * 4 + 6 * 4 + 4 + 8 * 16 + 4 + 4 + 16 + 8 + 8
-    assert ctypes.sizeof(AttnArgs) % 8 == 0 and AttnArgs.q.offset == 32
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"st5_gemm_args": GemmArgs, "st5_attn_args": AttnArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "speecht5_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line.strip():
+            continue
+        cname, field, val = line.split()
+        cls = structs[cname]
+        if field == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, field).offset == int(val), (cname, field, getattr(cls, field).offset, val)
+        seen += 1
+    assert seen == 2 + len(GemmArgs._fields_) + len(AttnArgs._fields_)
 
 
 def test_product_path_refuses_cpu_tensors():
