@@ -26,6 +26,15 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(EXPORTS), declared ^ set(EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
+    # every prototype in the ctypes table has as many parameters as the declaration in the header
+    from speecht5_b200._lib import _PROTOS
+    flat = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    for name in declared:
+        m = re.search(r"\b" + name + r"\s*\(([^;{]*?)\)\s*;", flat, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_PROTOS[name][1]), (name, n, len(_PROTOS[name][1]))
 
 
 def test_version_and_error_text(lib):
