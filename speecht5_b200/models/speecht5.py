@@ -6,6 +6,7 @@ t5_transformer_base, t5_transformer_large, t5_transformer_base_asr :1252,1385,14
 Round-1 coverage of forward(): text -> speech (t2s, the BASELINE.json metric path). The speech-input branches
 (speech_encoder_prenet / hubert / codebook / s2c) are SURVEY.md section-8 rows still to come and raise
 NotImplementedError rather than silently falling back to PyTorch."""
+import argparse
 import logging
 from argparse import Namespace
 
@@ -88,6 +89,71 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if args.bert_init:
             self.apply(init_bert_params)
         self.args = args
+
+    # ------------------------------------------------------------------ command-line surface (models/speecht5.py:118-700)
+    # Same option names and types as the reference, so a recipe's command line parses unchanged. Options of branches
+    # that are not built are accepted and rejected at build time if they are switched on.
+    _OPTIONS = (
+        ("--activation-fn", dict(type=str, choices=["relu", "gelu", "gelu_fast", "gelu_accurate", "tanh", "linear"])),
+        ("--dropout", dict(type=float, metavar="D")),
+        ("--attention-dropout", dict(type=float, metavar="D")),
+        (("--activation-dropout", "--relu-dropout"), dict(type=float, metavar="D")),
+        ("--encoder-embed-dim", dict(type=int, metavar="N")),
+        ("--encoder-ffn-embed-dim", dict(type=int, metavar="N")),
+        ("--encoder-layers", dict(type=int, metavar="N")),
+        ("--encoder-attention-heads", dict(type=int, metavar="N")),
+        ("--encoder-normalize-before", dict(action="store_true")),
+        ("--decoder-normalize-before", dict(action="store_true")),
+        ("--decoder-embed-dim", dict(type=int, metavar="N")),
+        ("--decoder-ffn-embed-dim", dict(type=int, metavar="N")),
+        ("--decoder-layers", dict(type=int, metavar="N")),
+        ("--decoder-attention-heads", dict(type=int, metavar="N")),
+        ("--reduction-factor", dict(type=int)),
+        ("--spk-embed-dim", dict(type=int)),
+        ("--layernorm-embedding", dict(action="store_true")),
+        ("--load-pretrained-encoder-from", dict(type=str, metavar="STR")),
+        ("--share-input-output-embed", dict(action="store_true")),
+        ("--share-ctc-embed", dict(action="store_true")),
+        ("--encoder-speech-prenet", dict(default="conv", type=str, choices=["conv", "linear"])),
+        ("--spk-embed-integration-type", dict(type=str, choices=["pre", "add"])),
+        ("--dprenet-dropout-rate", dict(default=0.5, type=float)),
+        ("--modules-filter", dict(default=None, type=str)),
+        ("--encoder-layerdrop", dict(type=float, metavar="D")),
+        ("--decoder-layerdrop", dict(type=float, metavar="D")),
+        ("--mask-selection", dict(type=str, choices=["static", "uniform", "normal", "poisson"])),
+        ("--mask-channel-selection", dict(type=str, choices=["static", "uniform", "normal", "poisson"])),
+        ("--use-codebook", dict(action="store_true")),
+        ("--codebook-prob", dict(type=float)),
+        ("--latent-vars", dict(type=int)),
+        ("--latent-groups", dict(type=int)),
+        ("--latent-dim", dict(type=int)),
+        ("--latent-temp", dict(type=str)),
+        ("--quantizer-depth", dict(type=int)),
+        ("--quantizer-factor", dict(type=int)),
+        ("--relative-position-embedding", dict(action="store_true")),
+        ("--num-buckets", dict(type=int)),
+        ("--max-distance", dict(type=int)),
+        ("--encoder-max-relative-position", dict(type=int)),
+        ("--decoder-max-relative-position", dict(type=int)),
+        ("--conv-feature-layers", dict(type=str, metavar="EXPR")),
+        ("--conv-bias", dict(action="store_true")),
+        ("--extractor-mode", dict(choices=["default", "layer_norm"])),
+        ("--bert-init", dict(action="store_true")),
+        ("--unb-enc-layer", dict(type=int, default=-1)),
+        # this implementation only: construct the text decoder pre/post-net (the reference always does)
+        ("--build-text-decoder", dict(action="store_true")),
+    )
+
+    @classmethod
+    def add_args(cls, parser):
+        for flags, kw in cls._OPTIONS:
+            flags = flags if isinstance(flags, tuple) else (flags,)
+            kw = dict(kw)
+            if kw.get("action") != "store_true" and "default" not in kw:
+                kw["default"] = argparse.SUPPRESS  # unset options fall through to the arch function, like fairseq's
+            elif kw.get("action") == "store_true":
+                kw["default"] = argparse.SUPPRESS
+            parser.add_argument(*flags, **kw)
 
     # ------------------------------------------------------------------ construction
     @classmethod

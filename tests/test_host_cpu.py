@@ -132,3 +132,22 @@ def test_model_exposes_the_reference_model_api():
         T5TransformerModel.forward_encoder(dummy, torch.zeros(1, 16000))
     with pytest.raises(NotImplementedError):
         T5TransformerModel.forward_decoder(dummy, None, None, None)
+
+
+def test_model_add_args_parses_the_recipe_command_line():
+    """models/speecht5.py:118-700 option surface: the TTS fine-tune recipe's model flags (SpeechT5/README.md) parse into
+    the namespace the arch function completes; unset options are left to the arch defaults."""
+    import argparse
+    from speecht5_b200.models import T5TransformerModel
+    from speecht5_b200.models.speecht5 import t5_transformer_base_asr
+    parser = argparse.ArgumentParser()
+    T5TransformerModel.add_args(parser)
+    args = parser.parse_args("--share-input-output-embed --bert-init --relative-position-embedding "
+                             "--encoder-layers 2 --decoder-layers 1 --relu-dropout 0.05 --dropout 0.2".split())
+    assert args.share_input_output_embed and args.bert_init and args.relative_position_embedding
+    assert args.encoder_layers == 2 and args.activation_dropout == 0.05 and not hasattr(args, "decoder_ffn_embed_dim")
+    t5_transformer_base_asr(args)
+    assert args.decoder_ffn_embed_dim == 3072 and args.encoder_max_relative_position == 160 and args.dropout == 0.2
+    model = T5TransformerModel.build_model(args)
+    assert len(model.encoder.layers) == 2 and len(model.decoder.layers) == 1
+    assert model.text_encoder_prenet.encoder_prenet[0].weight.shape == (81, 768)
