@@ -16,6 +16,53 @@ class SpeechT5Task(LegacyFairseqTask):
         self.config = config
         self.t5_task = getattr(args, "t5_task", "t2s")
 
+    # tasks/speecht5.py:44-213: the task's command-line surface (same option names, types and defaults), so that a
+    # recipe's command line parses unchanged; the dataset-side options are consumed by the host data pipeline only.
+    TASK_NAME = ["s2t", "t2s", "s2s", "s2c", "pretrain"]
+    _OPTIONS = (
+        ("--config-yaml", dict(type=str, default="config.yaml")),
+        ("--max-speech-sample-size", dict(default=None, type=int, metavar="N")),
+        ("--min-speech-sample-size", dict(default=None, type=int, metavar="N")),
+        ("--max-speech-positions", dict(default=4000, type=int, metavar="N")),
+        ("--max-text-positions", dict(default=450, type=int, metavar="N")),
+        ("--t5-task", dict(choices=TASK_NAME)),
+        ("--bpe-tokenizer", dict(type=str, default=None)),
+        ("--finetune-from-modules", dict(default=None)),
+        ("--finetune-out-of-modules", dict(default=None)),
+        ("--shorten-method", dict(default="none", choices=["none", "truncate", "random_crop"])),
+        ("--shorten-data-split-list", dict(default="")),
+        ("--tokens-per-sample", dict(default=512, type=int)),
+        ("--sample-break-mode", dict(default="eos", type=str)),
+        ("--mask", dict(default=0.3, type=float)),
+        ("--mask-random", dict(default=0.1, type=float)),
+        ("--insert", dict(default=0.0, type=float)),
+        ("--permute", dict(default=0.0, type=float)),
+        ("--rotate", dict(default=0.0, type=float)),
+        ("--poisson-lambda", dict(default=3.5, type=float)),
+        ("--permute-sentences", dict(default=0.0, type=float)),
+        ("--mask-length", dict(default="span-poisson", type=str, choices=["subword", "word", "span-poisson"])),
+        ("--replace-length", dict(default=1, type=int)),
+        ("--iid-noise-target", dict(action="store_true")),
+        ("--hubert-labels", dict(nargs="*", type=str, default=["km"])),
+        ("--hubert-label-dir", dict(type=str, default=None)),
+        ("--sample-rate", dict(default=100, type=float)),
+        ("--label-rates", dict(default=-1, type=float)),
+        ("--normalize", dict(action="store_true")),
+        ("--enable-padding", dict(action="store_true")),
+        ("--pad-audio", dict(action="store_true")),
+        ("--random-crop", dict(action="store_true")),
+        ("--single-target", dict(action="store_true")),
+        ("--batch-ratio", dict(default=None, type=str)),
+        ("--sample-ratios", dict(default=None, type=str)),
+        ("--ctc-weight", dict(type=float, default=0.0)),
+    )
+
+    @classmethod
+    def add_args(cls, parser):
+        parser.add_argument("data", help="manifest root path")
+        for flag, kw in cls._OPTIONS:
+            parser.add_argument(flag, **kw)
+
     @classmethod
     def setup_task(cls, args, **kwargs):
         return cls(args)

@@ -151,3 +151,17 @@ def test_model_add_args_parses_the_recipe_command_line():
     model = T5TransformerModel.build_model(args)
     assert len(model.encoder.layers) == 2 and len(model.decoder.layers) == 1
     assert model.text_encoder_prenet.encoder_prenet[0].weight.shape == (81, 768)
+
+
+def test_task_add_args_parses_the_recipe_command_line():
+    """tasks/speecht5.py:44-213 option surface (TTS fine-tune recipe, SpeechT5/README.md)."""
+    import argparse
+    from speecht5_b200.tasks import SpeechT5Task
+    parser = argparse.ArgumentParser()
+    SpeechT5Task.add_args(parser)
+    args = parser.parse_args("/data/root --config-yaml config.yaml --t5-task t2s --max-speech-positions 1876 "
+                             "--max-text-positions 600 --sample-rate 16000 --bpe-tokenizer spm_char.model".split())
+    assert args.data == "/data/root" and args.t5_task == "t2s" and args.max_speech_positions == 1876
+    assert args.sample_rate == 16000.0 and args.hubert_labels == ["km"] and args.ctc_weight == 0.0
+    task = SpeechT5Task.setup_task(args)
+    assert task.t5_task == "t2s"
