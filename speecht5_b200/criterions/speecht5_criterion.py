@@ -9,14 +9,35 @@ from .text_to_speech_loss import TexttoSpeechLoss
 
 @dataclass
 class SpeechT5CriterionConfig:
+    """Union of the reference's criterion configs (speecht5_criterion.py:23-30 inherits the text-to-speech,
+    speech-to-text, label-smoothed CE and pre-training configs), so every recipe's `--criterion speecht5 ...` flags
+    parse. Fields of branches that are not built yet are accepted and only matter once that branch is called."""
     sentence_avg: bool = field(default=True)
+    # text_to_speech_loss.py:21-69
     use_masking: bool = field(default=True)
+    use_weighted_masking: bool = field(default=False)
     loss_type: str = field(default="L1")
     bce_pos_weight: float = field(default=5.0)
     bce_loss_lambda: float = field(default=1.0)
     use_guided_attn_loss: bool = field(default=False)
     guided_attn_loss_sigma: float = field(default=0.4)
+    guided_attn_loss_lambda: float = field(default=10.0)
+    num_layers_applied_guided_attn: int = field(default=2)
     num_heads_applied_guided_attn: int = field(default=2)
+    # speech_to_text_loss.py:27-91 / label-smoothed CE
+    zero_infinity: bool = field(default=False)
+    post_process: str = field(default="sentencepiece")
+    label_smoothing: float = field(default=0.0)
+    report_accuracy: bool = field(default=False)
+    ignore_prefix_size: int = field(default=0)
+    ce_weight: float = field(default=1.0)
+    ctc_weight: float = field(default=0.0)
+    # pre-training criteria (speech_pretrain_criterion.py, text_pretrain_criterion.py)
+    pred_masked_weight: float = field(default=1.0)
+    pred_nomask_weight: float = field(default=0.0)
+    dec_weight: float = field(default=0.5)
+    bart_weight: float = field(default=1.0)
+    hubert_weight: float = field(default=1.0)
 
 
 @register_criterion("speecht5", dataclass=SpeechT5CriterionConfig)
