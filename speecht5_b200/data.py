@@ -33,6 +33,50 @@ def synthetic_tts_batch(B, T_txt, T_mel, vocab=81, odim=80, r=2, seed=1, ragged=
     return sample
 
 
+def collate_frames(frames, is_audio_input=False):
+    """text_to_speech_dataset.py:25-45 _collate_frames: zero-padded stack of [L_i, F] (or [L_i]) tensors."""
+    max_len = max(f.size(0) for f in frames)
+    shape = (len(frames), max_len) if is_audio_input else (len(frames), max_len, frames[0].size(1))
+    out = frames[0].new_zeros(shape)
+    for i, v in enumerate(frames):
+        out[i, : v.size(0)] = v
+    return out
+
+
+def collate_tts(samples, reduction_factor=2, pad=1):
+    """TextToSpeechDataset.collater (text_to_speech_dataset.py:226-281) over in-memory items
+    {"id", "source": [LongTensor tokens], "target": FloatTensor [L, odim], "spkembs": FloatTensor [512],
+    "audio_name"}: the batch dict the task, the criterion and the trainer consume. Host-side work only."""
+    samples = [s for s in samples if s["source"] is not None]
+    if len(samples) == 0:
+        return {}
+    fbanks = [s["target"] for s in samples]
+    fbank_sizes = [len(f) for f in fbanks]
+    collated = collate_frames(fbanks)
+    sizes = torch.tensor(fbank_sizes, dtype=torch.long)
+    r = reduction_factor
+    if r > 1:  # thin out frames for the reduction factor: (B, Lmax, odim) -> (B, Lmax // r, odim)
+        fb_in = collated[:, r - 1::r]
+        sizes_in = torch.div(sizes, r, rounding_mode="floor")
+    else:
+        fb_in, sizes_in = collated, sizes
+    prev = torch.cat([fb_in.new_zeros((fb_in.shape[0], 1, fb_in.shape[2])), fb_in[:, :-1]], dim=1)
+    labels = collated.new_zeros(collated.size(0), collated.size(1))
+    for i, n in enumerate(fbank_sizes):
+        labels[i, n - 1:] = 1.0
+    spkembs = collate_frames([s["spkembs"] for s in samples], is_audio_input=True)
+    toks = [s["source"][0] for s in samples]
+    lengths = torch.LongTensor([len(t) for t in toks])
+    src = toks[0].new_full((len(toks), int(lengths.max())), pad)  # data_utils.collate_tokens(left_pad=False)
+    for i, t in enumerate(toks):
+        src[i, : len(t)] = t
+    net_input = {"src_tokens": src, "src_lengths": lengths, "prev_output_tokens": prev, "tgt_lengths": sizes_in,
+                 "spkembs": spkembs, "task_name": "t2s"}
+    return {"id": torch.LongTensor([s["id"] for s in samples]), "name": [s.get("audio_name") for s in samples],
+            "net_input": net_input, "labels": labels, "dec_target": collated, "dec_target_lengths": sizes,
+            "src_lengths": lengths, "task_name": "t2s", "ntokens": int(lengths.sum().item()), "target": collated}
+
+
 def _pin(obj):
     if torch.is_tensor(obj):
         return obj.pin_memory()

@@ -165,3 +165,23 @@ def test_task_add_args_parses_the_recipe_command_line():
     assert args.sample_rate == 16000.0 and args.hubert_labels == ["km"] and args.ctc_weight == 0.0
     task = SpeechT5Task.setup_task(args)
     assert task.t5_task == "t2s"
+
+
+def test_collate_tts_reproduces_the_reference_batch_contract():
+    """text_to_speech_dataset.py:226-281: un-collating a synthetic batch and collating it again gives it back, and
+    the derived fields follow the collater's rules (every r-th frame shifted right, stop labels from the last frame)."""
+    from speecht5_b200.data import collate_tts, synthetic_tts_batch
+    ref = synthetic_tts_batch(4, 23, 37, seed=9)
+    items = []
+    for b in range(4):
+        n_txt, n_mel = int(ref["src_lengths"][b]), int(ref["dec_target_lengths"][b])
+        items.append({"id": b, "source": [ref["net_input"]["src_tokens"][b, :n_txt]],
+                      "target": ref["dec_target"][b, :n_mel], "spkembs": ref["net_input"]["spkembs"][b],
+                      "audio_name": f"utt{b}"})
+    got = collate_tts(items, reduction_factor=2)
+    for k in ("src_tokens", "src_lengths", "prev_output_tokens", "tgt_lengths", "spkembs"):
+        assert torch.equal(got["net_input"][k], ref["net_input"][k]), k
+    for k in ("labels", "dec_target", "dec_target_lengths", "src_lengths", "target"):
+        assert torch.equal(got[k], ref[k]), k
+    assert got["ntokens"] == ref["ntokens"] and got["task_name"] == "t2s" and got["name"][2] == "utt2"
+    assert collate_tts([{"source": None}]) == {}
