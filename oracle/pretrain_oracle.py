@@ -9,7 +9,6 @@ transformers.models.wav2vec2.Wav2Vec2GumbelVectorQuantizer; the prediction head 
 F.gumbel_softmax; here the noise is an explicit input so that a device path can be fed the same draw."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 class SpeechEncoderPostnet(nn.Module):

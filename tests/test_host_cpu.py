@@ -2,7 +2,6 @@
 the synthetic collater contract, and the data-parallel gradient exchange over gloo (world_size 2)."""
 import inspect
 import os
-import sys
 
 import pytest
 import torch

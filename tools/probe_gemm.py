@@ -2,7 +2,6 @@
 import json
 import os
 import sys
-import time
 
 import torch
 
