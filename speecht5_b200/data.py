@@ -77,6 +77,52 @@ def collate_tts(samples, reduction_factor=2, pad=1):
             "src_lengths": lengths, "task_name": "t2s", "ntokens": int(lengths.sum().item()), "target": collated}
 
 
+def compute_mask_indices(shape, padding_mask, mask_prob, mask_length, mask_type="static", mask_other=0.0, min_masks=0,
+                         no_overlap=False, min_space=0):
+    """Span masks for the speech prenet (speech_encoder_prenet.py:236-262 calls fairseq/data/data_utils.py:393-517).
+    Host-side numpy, drawing from the GLOBAL np.random stream in the reference's order (one rand() for the whole
+    batch, one more per row when a padding mask is given, the span lengths, the span starts, then the per-row
+    thinning to the common count), so a run seeded like the reference masks the same frames. Returns a bool ndarray
+    [B, T]. `no_overlap` (off in every SpeechT5 recipe) is not built."""
+    import numpy as np
+    if no_overlap:
+        raise NotImplementedError("no_overlap span placement is not built (unused by the SpeechT5 recipes)")
+    bsz, all_sz = shape
+    mask = np.full((bsz, all_sz), False)
+    all_num_mask = max(min_masks, int(mask_prob * all_sz / float(mask_length) + np.random.rand()))
+    mask_idcs = []
+    for i in range(bsz):
+        if padding_mask is not None:
+            sz = all_sz - int(padding_mask[i].long().sum().item())
+            num_mask = max(min_masks, int(mask_prob * sz / float(mask_length) + np.random.rand()))
+        else:
+            sz, num_mask = all_sz, all_num_mask
+        if mask_type == "static":
+            lengths = np.full(num_mask, mask_length)
+        elif mask_type == "uniform":
+            lengths = np.random.randint(mask_other, mask_length * 2 + 1, size=num_mask)
+        elif mask_type == "normal":
+            lengths = [max(1, int(round(x))) for x in np.random.normal(mask_length, mask_other, size=num_mask)]
+        elif mask_type == "poisson":
+            lengths = [int(round(x)) for x in np.random.poisson(mask_length, size=num_mask)]
+        else:
+            raise Exception("unknown mask selection " + mask_type)
+        if sum(lengths) == 0:
+            lengths[0] = min(mask_length, sz - 1)
+        min_len = min(lengths)
+        if sz - min_len <= num_mask:
+            min_len = sz - num_mask - 1
+        starts = np.random.choice(sz - min_len, num_mask, replace=False)
+        idc = np.asarray([starts[j] + off for j in range(len(starts)) for off in range(lengths[j])])
+        mask_idcs.append(np.unique(idc[idc < sz]))
+    min_len = min(len(m) for m in mask_idcs)
+    for i, idc in enumerate(mask_idcs):
+        if len(idc) > min_len:
+            idc = np.random.choice(idc, min_len, replace=False)
+        mask[i, idc] = True
+    return mask
+
+
 def _pin(obj):
     if torch.is_tensor(obj):
         return obj.pin_memory()

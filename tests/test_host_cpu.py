@@ -184,3 +184,36 @@ def test_collate_tts_reproduces_the_reference_batch_contract():
         assert torch.equal(got[k], ref[k]), k
     assert got["ntokens"] == ref["ntokens"] and got["task_name"] == "t2s" and got["name"][2] == "utt2"
     assert collate_tts([{"source": None}]) == {}
+
+
+def test_compute_mask_indices_properties_and_determinism():
+    """fairseq/data/data_utils.py:393-517 (static spans, as the SpeechT5 recipes use them): every row ends up with the
+    same number of masked frames, none on padding, spans of the requested length, reproducible from np.random.seed."""
+    import numpy as np
+    from speecht5_b200.data import compute_mask_indices
+    B, T, L = 4, 499, 10
+    lens = torch.tensor([499, 450, 400, 320])
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    np.random.seed(3)
+    m1 = compute_mask_indices((B, T), pad, 0.75, L, "static", 0, min_masks=2)
+    np.random.seed(3)
+    m2 = compute_mask_indices((B, T), pad, 0.75, L, "static", 0, min_masks=2)
+    assert m1.dtype == bool and m1.shape == (B, T) and (m1 == m2).all()
+    counts = m1.sum(1)
+    assert (counts == counts[0]).all() and counts[0] > 0
+    assert not (m1 & pad.numpy()).any()
+    # without thinning (single row) every masked run is a union of length-L spans
+    np.random.seed(5)
+    m = compute_mask_indices((1, 200), None, 0.3, L, "static", 0, min_masks=2)[0]
+    runs, n = [], 0
+    for v in list(m) + [False]:
+        if v:
+            n += 1
+        elif n:
+            runs.append(n)
+            n = 0
+    assert runs and all(r >= L for r in runs)
+    # channel masks: no padding mask -> one shared span count
+    np.random.seed(7)
+    mc = compute_mask_indices((3, 768), None, 0.5, 64, "static", 0)
+    assert (mc.sum(1) == mc.sum(1)[0]).all()
