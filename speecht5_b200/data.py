@@ -77,6 +77,37 @@ def collate_tts(samples, reduction_factor=2, pad=1):
             "src_lengths": lengths, "task_name": "t2s", "ntokens": int(lengths.sum().item()), "target": collated}
 
 
+def collate_asr(samples, pad=1, eos=2):
+    """SpeechToTextDataset.collater (speecht5/data/speech_to_text_dataset.py:150-222) over in-memory items
+    {"id", "source": FloatTensor [N] waveform, "label_list": [LongTensor tokens]}: zero-padded waveforms with their
+    boolean padding mask, targets = tokens + eos (right padded), prev_output_tokens = the same with eos moved to the
+    front (fairseq collate_tokens(move_eos_to_beginning=True)). Host-side work only."""
+    samples = [s for s in samples if s["source"] is not None]
+    if len(samples) == 0:
+        return {}
+    audios = [s["source"] for s in samples]
+    n = max(len(a) for a in audios)
+    source = audios[0].new_zeros(len(audios), n)
+    padding_mask = torch.zeros(len(audios), n, dtype=torch.bool)
+    for i, a in enumerate(audios):
+        source[i, : len(a)] = a
+        padding_mask[i, len(a):] = True
+    labels = [torch.cat((s["label_list"][0].long(), torch.tensor([eos]))) for s in samples]
+    lengths = torch.tensor([len(t) for t in labels], dtype=torch.long)
+    T = int(lengths.max())
+    target = torch.full((len(labels), T), pad, dtype=torch.long)
+    prev = torch.full((len(labels), T), pad, dtype=torch.long)
+    for i, t in enumerate(labels):
+        target[i, : len(t)] = t
+        prev[i, 0] = eos
+        prev[i, 1: len(t)] = t[:-1]
+    ntokens = int(sum(len(s["label_list"][0]) for s in samples))
+    return {"id": torch.LongTensor([s["id"] for s in samples]),
+            "net_input": {"source": source, "padding_mask": padding_mask, "prev_output_tokens": prev,
+                          "task_name": "s2t"},
+            "target": target, "target_lengths": lengths, "task_name": "s2t", "ntokens": ntokens}
+
+
 def compute_mask_indices(shape, padding_mask, mask_prob, mask_length, mask_type="static", mask_other=0.0, min_masks=0,
                          no_overlap=False, min_space=0):
     """Span masks for the speech prenet (speech_encoder_prenet.py:236-262 calls fairseq/data/data_utils.py:393-517).

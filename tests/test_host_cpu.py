@@ -217,3 +217,16 @@ def test_compute_mask_indices_properties_and_determinism():
     np.random.seed(7)
     mc = compute_mask_indices((3, 768), None, 0.5, 64, "static", 0)
     assert (mc.sum(1) == mc.sum(1)[0]).all()
+
+
+def test_collate_asr_follows_the_reference_collater():
+    """speech_to_text_dataset.py:150-222: padding mask, eos-terminated targets, eos-first decoder inputs."""
+    from speecht5_b200.data import collate_asr
+    items = [{"id": 0, "source": torch.arange(1.0, 6.0), "label_list": [torch.tensor([7, 8, 9])]},
+             {"id": 1, "source": torch.arange(1.0, 4.0), "label_list": [torch.tensor([5])]}]
+    b = collate_asr(items)
+    assert b["net_input"]["source"].tolist() == [[1, 2, 3, 4, 5], [1, 2, 3, 0, 0]]
+    assert b["net_input"]["padding_mask"].tolist() == [[False] * 5, [False, False, False, True, True]]
+    assert b["target"].tolist() == [[7, 8, 9, 2], [5, 2, 1, 1]]
+    assert b["net_input"]["prev_output_tokens"].tolist() == [[2, 7, 8, 9], [2, 5, 1, 1]]
+    assert b["target_lengths"].tolist() == [4, 2] and b["ntokens"] == 4 and b["task_name"] == "s2t"
