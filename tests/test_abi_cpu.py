@@ -89,3 +89,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_argument_errors_are_reported_without_touching_a_device(lib):
+    """Error behaviour of the C ABI: negative return code + st5_last_error() text, decided before any CUDA call (so it
+    holds on a box without a GPU); st5_device_ok() itself fails loudly here instead of pretending."""
+    from speecht5_b200 import _lib
+    g = _lib.GemmArgs()
+    g.M, g.N, g.K, g.nb1, g.nb2 = 8, 8, 0, 1, 1
+    assert lib.st5_gemm_bf16(ctypes.byref(g), None) == -2 and b"st5_gemm_bf16" in lib.st5_last_error()
+    g.K, g.accumulate, g.c_fp32 = 8, 1, 0  # accumulation needs an fp32 output
+    assert lib.st5_gemm_bf16(ctypes.byref(g), None) == -3
+    a = _lib.AttnArgs()
+    a.B, a.H, a.Tq, a.Tk, a.dtype = 1, 1, 4, 4, 0  # fp32 activations: the fused kernels are bf16 only
+    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None) == -2 and b"bf16" in lib.st5_last_error()
+    a.dtype, a.Tk = 1, 400
+    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None) == -2
+    if not torch.cuda.is_available():
+        assert lib.st5_device_ok() != 0
+    with pytest.raises(RuntimeError, match="st5_gemm_bf16"):
+        _lib.check(-2, "st5_gemm_bf16")
