@@ -1,0 +1,47 @@
+"""CPU: statistics of the counter-based dropout generator. tests/csrc/philox_host.cu includes the kernels' own
+__host__ __device__ functions (speecht5_b200/csrc/ptx.cuh: Philox4x32-7, eight 16-bit lanes per call), is built with
+nvcc and runs on the host: keep rates, lane uniformity, serial / cross-site correlations, known answers."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def stats(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+    if nvcc is None:
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path_factory.mktemp("philox") / "philox_host")
+    src = os.path.join(ROOT, "tests", "csrc", "philox_host.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", src, "-o", exe],
+                   check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    res = {}
+    for line in out.splitlines():
+        parts = line.split()
+        res[" ".join(parts[:-1]) if parts[0] == "keep_rate" else parts[0]] = parts[1:] if parts[0] in ("kat", "pitch") \
+            else float(parts[-1])
+    return res
+
+
+def test_keep_rates(stats):
+    # 2^21 Bernoulli draws: sd = sqrt(p(1-p)/n) ~ 2e-4 (p=0.1), 3.5e-4 (p=0.5); 5 sigma bounds
+    assert abs(stats["keep_rate p=0.10"] - 0.9) < 1.1e-3
+    assert abs(stats["keep_rate p=0.50"] - 0.5) < 1.8e-3
+
+
+def test_lane_uniformity_and_independence(stats):
+    assert 255 - 5 * 22.6 < stats["chi2_256"] < 255 + 5 * 22.6  # chi-square, 255 degrees of freedom
+    for k in ("corr_adjacent", "corr_row", "corr_offset", "corr_seed"):
+        assert abs(stats[k]) < 5e-3, (k, stats[k])  # 2^20 samples: sd ~ 1e-3
+
+
+def test_known_answers(stats):
+    """A change of the generator (rounds, constants, lane layout) must be deliberate: forward and backward kernels, and
+    any checkpointed seed, depend on it."""
+    assert stats["kat"] == ["15da0e38", "90b50218", "61766a43", "4b911f60"]
+    assert stats["pitch"] == ["320", "160"]
