@@ -1,4 +1,5 @@
-"""CPU: statistics of the counter-based dropout generator. tests/csrc/philox_host.cu includes the kernels' own
+"""CPU: device-side math restated or rebuilt on the host -- statistics of the counter-based dropout generator and the
+error bounds of the GELU evaluations. tests/csrc/philox_host.cu includes the kernels' own
 __host__ __device__ functions (speecht5_b200/csrc/ptx.cuh: Philox4x32-7, eight 16-bit lanes per call), is built with
 nvcc and runs on the host: keep rates, lane uniformity, serial / cross-site correlations, known answers."""
 import os
@@ -45,3 +46,26 @@ def test_known_answers(stats):
     any checkpointed seed, depend on it."""
     assert stats["kat"] == ["15da0e38", "90b50218", "61766a43", "4b911f60"]
     assert stats["pitch"] == ["320", "160"]
+
+
+def test_gelu_formulas_meet_their_documented_error_bounds():
+    """The two GELU evaluations of the GEMM epilogue (speecht5_b200/csrc/kernels.cuh), restated in float64 numpy:
+    Abramowitz-Stegun 7.1.26 for the exact (erf) form used in parity mode, and the tanh form of the bf16 throughput
+    mode. The bounds are the ones quoted in the header / DESIGN.md."""
+    import math
+    import numpy as np
+    x = np.linspace(-8.0, 8.0, 400001)
+    exact = 0.5 * x * (1.0 + np.vectorize(math.erf)(x / math.sqrt(2.0)))
+    # gauss_cdf(): t = 1 / (1 + p z), z = |x| / sqrt 2, erf ~ 1 - poly(t) exp(-z^2)
+    z = np.abs(x) / math.sqrt(2.0)
+    t = 1.0 / (1.0 + 0.3275911 * z)
+    poly = t * (0.254829592 + t * (-0.284496736 + t * (1.421413741 + t * (-1.453152027 + t * 1.061405429))))
+    cdf = 0.5 * (1.0 + np.copysign(1.0 - poly * np.exp(-z * z), x))
+    assert np.abs(x * cdf - exact).max() < 1.5e-7 * 8  # |erf error| <= 1.5e-7, times |x| / 2 <= 4
+    tanh_form = 0.5 * x * (1.0 + np.tanh(x * (0.7978845608 + 0.0356774081 * x * x)))
+    assert np.abs(tanh_form - exact).max() < 4.8e-4
+    # derivative of the tanh form as coded in gelu_tanh_grad()
+    th = np.tanh(x * (0.7978845608 + 0.0356774081 * x * x))
+    grad = 0.5 * x * (1.0 - th * th) * (0.7978845608 + 0.1070322243 * x * x) + 0.5 * th + 0.5
+    num = np.gradient(tanh_form, x)
+    assert np.abs(grad - num)[5:-5].max() < 1e-6
