@@ -24,8 +24,8 @@ def stats(tmp_path_factory):
     res = {}
     for line in out.splitlines():
         parts = line.split()
-        res[" ".join(parts[:-1]) if parts[0] == "keep_rate" else parts[0]] = parts[1:] if parts[0] in ("kat", "pitch") \
-            else float(parts[-1])
+        res[" ".join(parts[:-1]) if parts[0] == "keep_rate" else parts[0]] = parts[1:] \
+            if parts[0] in ("kat", "pitch", "idesc") else float(parts[-1])
     return res
 
 
@@ -46,6 +46,10 @@ def test_known_answers(stats):
     any checkpointed seed, depend on it."""
     assert stats["kat"] == ["15da0e38", "90b50218", "61766a43", "4b911f60"]
     assert stats["pitch"] == ["320", "160"]
+    # instruction descriptors: (1<<4)|(1<<7)|(1<<10) | a_mn<<15 | b_mn<<16 | (N>>3)<<17 | (M>>4)<<24
+    base = (1 << 4) | (1 << 7) | (1 << 10) | ((128 >> 4) << 24)
+    want = [base | ((256 >> 3) << 17), base | (1 << 15) | (1 << 16) | ((64 >> 3) << 17), base | (1 << 16) | ((160 >> 3) << 17)]
+    assert [int(v, 16) for v in stats["idesc"]] == want
 
 
 def test_gelu_formulas_meet_their_documented_error_bounds():
