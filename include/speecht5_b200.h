@@ -99,13 +99,17 @@ int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rs
                void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C, float drop_p,
                uint64_t seed, uint64_t offset, void* stream);
 
-/* y = dropout(x) (also its own backward when applied to the gradient). */
+/* y = dropout(x) (also its own backward when applied to the gradient). fairseq/modules/fairseq_dropout.py:23-37
+ * (F.dropout semantics: keep with probability 1-p, scale by 1/(1-p)); mask = the counter-based generator above. */
 int st5_dropout(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
                 void* stream);
-/* dpre = dropout-backward(dy) * act'(pre). */
+/* dpre = dropout-backward(dy) * act'(pre): backward of activation_fn + activation dropout
+ * (transformer_layer.py:127-129, speech_decoder_prenet.py:41-47 via espnet Prenet). */
 int st5_act_bwd(const void* dy, const void* pre, void* dpre, int dtype, int act, int64_t n, float drop_p, uint64_t seed,
                 uint64_t offset, void* stream);
-/* out[g][n] (+)= sum_{m in group g} x[m][n], groups of `group_rows` consecutive rows (bias gradients). */
+/* out[g][n] (+)= sum_{m in group g} x[m][n], groups of `group_rows` consecutive rows: bias gradients of every
+ * nn.Linear on the path (and, per utterance, of the x-vector term of speech_decoder_prenet.py:69-72); also the reduction
+ * of split-K partial products. */
 int st5_colsum(const void* x, int64_t ld, float* out, int dtype, int64_t rows, int64_t cols, int64_t group_rows,
                int accumulate, void* stream);
 
@@ -144,12 +148,14 @@ int st5_attn_bwd(const st5_attn_args* args, void* stream);
  * Relative positions (encoder.py:239-246): pe_k != NULL selects the skewed-bias variant; here pe_k must point to a
  * BF16 copy of the [2*maxpos][64] table, and Tq, Tk <= maxpos <= 160 (clamp(i-j) never clips), no causal mask. */
 int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* stream);
-/* Fused tcgen05 attention backward (flash style: P is recomputed from lse, no Tq x Tk tensor touches HBM). Reads
- * q/k/v, out (forward result), dout, key_pad, dropout fields; optional dprobs_ext (+ the fp32 probs it refers to);
- * writes dq/dk/dv (same layouts as q/k/v). Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
- * Relative positions (pe_k != NULL): probs must be the BF16 probabilities st5_attn_fused_fwd saved (read instead of
- * recomputed; lse may be NULL) and args->ds receives dS as BF16 [B,H,Tq,p_ld] for st5_attn_dqp_scatter and the two
- * table GEMMs; dq then holds only the q.k part of the gradient. */
+/* Fused tcgen05 attention backward (multihead_attention.py:340-389 differentiated). args->probs must be the
+ * probabilities st5_attn_fused_fwd saved (BF16, or the FP32 copy returned to the caller; p_ld a multiple of 8): they are
+ * read back instead of recomputed, so every step needs one score-sized MMA (dP = dO V^T) and the kernel double buffers
+ * dP, the dropout(P)/dS operand tiles, dQ and the Q/dO tiles. Reads q/k/v, out (forward result), dout and the dropout
+ * fields; optional dprobs_ext (needs FP32 probs); writes dq/dk/dv (same layouts as q/k/v). lse is unused (may be NULL).
+ * Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
+ * Relative positions (pe_k != NULL): args->ds additionally receives dS as BF16 [B,H,Tq,p_ld] for st5_attn_dqp_scatter
+ * and the two table GEMMs; dq then holds only the q.k part of the gradient. */
 int st5_attn_fused_bwd(const st5_attn_args* args, const float* lse, float* delta, float* dq_acc, void* stream);
 
 /* Tensor-core (bf16) attention path: the contractions run on st5_gemm_bf16 (batched over heads and utterances, q/k/v
@@ -182,8 +188,11 @@ int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const
 
 /* ------------------------------------------------------------------------------------------------- optimizer
  * Replaces fairseq/optim/adam.py + fp16_optimizer.py:106-218 on a flat fp32 parameter buffer: one pass applies the
- * gradient scale (clip coefficient x 1/loss-scale), Adam(beta1, beta2, eps, weight decay as in torch.optim.Adam /
- * fairseq Adam: decoupled=0 adds wd*p to the gradient) and refreshes the bf16 shadow copy used by the GEMMs. */
+ * gradient scale (grad_mul x clip coefficient max_norm / (norm + 1e-6) capped at 1: fairseq/utils.py clip_grad_norm_,
+ * fairseq/trainer.py:796-826), Adam as fairseq/optim/adam.py:Adam.step writes it (denominator sqrt(v) + eps, step size
+ * lr * sqrt(1 - b2^t) / (1 - b1^t), weight decay p -= wd * lr * p) and refreshes the bf16 shadow copy the GEMMs read.
+ * st5_sumsq accumulates sum(x^2) (the squared gradient norm) into *out. lr_dev / step_dev: device-resident schedule
+ * state so that a captured CUDA graph stays valid across updates. */
 int st5_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */, void* stream);
 int st5_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,
