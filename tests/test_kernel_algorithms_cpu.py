@@ -90,3 +90,78 @@ def test_groupnorm_with_one_channel_per_group_is_per_utterance_batchnorm_statist
     out = ((rows - mean) / torch.sqrt(var + 1e-5) * g + b).transpose(1, 2)
     assert torch.allclose(out, ref, atol=1e-5)
     assert np.isfinite(out.numpy()).all()
+
+
+def _ctc_numpy(logits, targets, input_len, target_len, blank=0):
+    """CTC negative log-likelihood and its gradient wrt the logits of ONE utterance, the way the device kernel will do
+    it (criterions/speech_to_text_loss.py:303-335 calls F.ctc_loss(reduction="sum", zero_infinity=...)): log-space
+    alpha / beta recursions over the extended label sequence l' = (blank, l1, blank, ..., lL, blank), one thread per
+    extended position s, T sequential steps; grad[t, k] = y[t, k] - sum_{s: l'_s = k} exp(alpha[t, s] + beta[t, s] -
+    lp[t, k] + nll), rows t >= input_len zero."""
+    T, V = logits.shape
+    lp = logits - np.logaddexp.reduce(logits, axis=1, keepdims=True)
+    L = int(target_len)
+    ext = np.full(2 * L + 1, blank, dtype=np.int64)
+    ext[1::2] = targets[:L]
+    S, Tn = 2 * L + 1, int(input_len)
+    ninf = -np.inf
+    alpha = np.full((Tn, S), ninf)
+    beta = np.full((Tn, S), ninf)
+    alpha[0, 0] = lp[0, blank]
+    if S > 1:
+        alpha[0, 1] = lp[0, ext[1]]
+    for t in range(1, Tn):
+        for s in range(S):
+            a = alpha[t - 1, s]
+            if s >= 1:
+                a = np.logaddexp(a, alpha[t - 1, s - 1])
+            if s >= 2 and ext[s] != blank and ext[s] != ext[s - 2]:
+                a = np.logaddexp(a, alpha[t - 1, s - 2])
+            alpha[t, s] = a + lp[t, ext[s]]
+    beta[Tn - 1, S - 1] = lp[Tn - 1, blank]
+    if S > 1:
+        beta[Tn - 1, S - 2] = lp[Tn - 1, ext[S - 2]]
+    for t in range(Tn - 2, -1, -1):
+        for s in range(S):
+            b = beta[t + 1, s]
+            if s + 1 < S:
+                b = np.logaddexp(b, beta[t + 1, s + 1])
+            if s + 2 < S and ext[s] != blank and ext[s] != ext[s + 2]:
+                b = np.logaddexp(b, beta[t + 1, s + 2])
+            beta[t, s] = b + lp[t, ext[s]]
+    ll = alpha[Tn - 1, S - 1] if S == 1 else np.logaddexp(alpha[Tn - 1, S - 1], alpha[Tn - 1, S - 2])
+    nll = -ll
+    grad = np.zeros_like(logits)
+    if np.isfinite(nll):
+        grad[:Tn] = np.exp(lp[:Tn])
+        for t in range(Tn):
+            acc = np.full(V, ninf)
+            for s in range(S):
+                acc[ext[s]] = np.logaddexp(acc[ext[s]], alpha[t, s] + beta[t, s])
+            grad[t] -= np.exp(acc - lp[t] + nll)
+    return nll, grad
+
+
+def test_ctc_recursion_and_gradient_match_torch():
+    """The ASR criterion's CTC term (speech_to_text_loss.py:303-335): per-utterance alpha/beta recursion and the
+    closed-form gradient wrt the logits, against torch's ctc_loss + log_softmax autograd (repeated labels, ragged
+    input / target lengths, an infeasible utterance under zero_infinity)."""
+    torch.manual_seed(4)
+    T, B, V = 23, 4, 9
+    logits = torch.randn(T, B, V, dtype=torch.float64, requires_grad=True)
+    targets = [torch.tensor([3, 3, 5, 1, 1, 2]), torch.tensor([4, 2]), torch.tensor([7, 7, 7, 7, 7, 7, 7, 7]),
+               torch.tensor([1, 2, 3])]
+    input_lengths = torch.tensor([23, 15, 12, 20])  # utterance 2: 8 repeated labels need 15 frames > 12 -> infeasible
+    target_lengths = torch.tensor([len(t) for t in targets])
+    lp = F.log_softmax(logits, dim=-1)
+    loss = F.ctc_loss(lp, torch.cat(targets), input_lengths, target_lengths, blank=0, reduction="sum",
+                      zero_infinity=True)
+    loss.backward()
+    total = 0.0
+    for b in range(B):
+        nll, grad = _ctc_numpy(logits.detach().numpy()[:, b], targets[b].numpy(), input_lengths[b], target_lengths[b])
+        if not np.isfinite(nll):  # zero_infinity: the utterance contributes neither loss nor gradient
+            nll, grad = 0.0, np.zeros_like(grad)
+        total += nll
+        assert np.allclose(grad, logits.grad[:, b].numpy(), atol=1e-9), b
+    assert abs(total - loss.item()) < 1e-9
