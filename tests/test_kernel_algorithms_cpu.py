@@ -165,3 +165,50 @@ def test_ctc_recursion_and_gradient_match_torch():
         total += nll
         assert np.allclose(grad, logits.grad[:, b].numpy(), atol=1e-9), b
     assert abs(total - loss.item()) < 1e-9
+
+
+def _split_bf16(x):
+    hi = x.to(torch.bfloat16).float()
+    lo = (x - hi).to(torch.bfloat16).float()
+    return hi, lo
+
+
+def test_logmel_as_two_gemms_with_split_precision():
+    """SURVEY section 8a row 15 (text_to_speech_dataset.py:95-138) as the device path will run it: the framed,
+    reflect-padded waveform [n_frames, 1024] times ONE windowed real-DFT matrix [1024, 2*513] (cos | -sin with the
+    periodic hann folded in) on the existing GEMM kernel, a magnitude epilogue over column pairs, then the [513, 80] mel
+    GEMM with a log10(max(eps, .)) epilogue. Checked against the oracle's FFT formulation in fp32, and in the GEMM
+    kernel's split-bf16 parity arithmetic (hi*hi + hi*lo + lo*hi, fp32 accumulate) to bound what that mode costs."""
+    from oracle.audio_oracle import logmelfilterbank, mel_basis
+    rng = np.random.default_rng(11)
+    n = 16000
+    t = np.arange(n) / 16000.0
+    audio = (0.3 * np.sin(2 * np.pi * 220 * t) + 0.1 * np.sin(2 * np.pi * 3100 * t) + 0.02 * rng.standard_normal(n))
+    audio = audio.astype(np.float32)
+    want = logmelfilterbank(audio)
+    nfft, hop = 1024, 256
+    x = np.pad(audio, (nfft // 2, nfft // 2), mode="reflect")
+    n_frames = 1 + (x.size - nfft) // hop
+    frames = torch.from_numpy(x[np.arange(nfft)[None, :] + hop * np.arange(n_frames)[:, None]])
+    k = np.arange(nfft // 2 + 1)[None, :]
+    ang = 2.0 * np.pi * (np.arange(nfft)[:, None] * k % nfft) / nfft  # exact argument reduction on the host
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(nfft) / nfft)
+    dft = torch.from_numpy(np.concatenate([np.cos(ang), -np.sin(ang)], axis=1) * win[:, None]).float()
+    basis = torch.from_numpy(mel_basis()).t().contiguous()
+
+    def finish(spec2):
+        mag = torch.sqrt(spec2[:, :513] ** 2 + spec2[:, 513:] ** 2)
+        return mag
+
+    def split_mm(a, b):
+        ah, al = _split_bf16(a)
+        bh, bl = _split_bf16(b)
+        return ah @ bh + ah @ bl + al @ bh
+
+    got32 = torch.log10(torch.clamp(finish(frames @ dft) @ basis, min=1e-10)).numpy()
+    assert got32.shape == want.shape == (1 + n // hop, 80)
+    assert np.abs(got32 - want).max() < 2e-4
+    mag_s = finish(split_mm(frames, dft))
+    got_s = torch.log10(torch.clamp(split_mm(mag_s, basis), min=1e-10)).numpy()
+    # log10 domain: an absolute error of 1e-3 is a 0.23 % magnitude error, inside the TTS target noise floor
+    assert np.abs(got_s - want).max() < 1e-3, np.abs(got_s - want).max()
