@@ -212,3 +212,54 @@ def test_logmel_as_two_gemms_with_split_precision():
     got_s = torch.log10(torch.clamp(split_mm(mag_s, basis), min=1e-10)).numpy()
     # log10 domain: an absolute error of 1e-3 is a 0.23 % magnitude error, inside the TTS target noise floor
     assert np.abs(got_s - want).max() < 1e-3, np.abs(got_s - want).max()
+
+
+def test_incremental_decode_with_kv_cache_equals_prefix_recompute():
+    """Synthesis (models/speecht5.py:1188-1249; the reference keeps fairseq incremental state,
+    multihead_attention.py:255-330): the planned device decode loop projects the cross-attention K/V of every decoder
+    layer ONCE per utterance, appends one self-attention K/V row per step to a [layer, H, T_max, 64] cache and runs
+    one-row attention -- O(L) work per step instead of the O(L^2) prefix recompute generate_speech does today. Same
+    numbers as the prefix recompute at every step (causality), including the per-layer cross-attention rows the
+    guided-attention diagnostics read."""
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args
+    torch.manual_seed(5)
+    args = base_args(encoder_layers=1, decoder_layers=2, dprenet_dropout_rate=0.0)
+    m = T5TransformerModelOracle(args).double().eval()
+    d, H = args.decoder_embed_dim, args.decoder_attention_heads
+    hd = d // H
+    src = torch.randint(4, 81, (1, 9))
+    spk = torch.randn(1, 512, dtype=torch.float64)
+    enc_in, enc_mask = m.text_encoder_prenet(src)
+    enc_out = m.encoder(enc_in, enc_mask)
+    enc = enc_out["encoder_out"][0]  # [S, 1, d]
+    L = 7
+    frames = torch.randn(1, L, 80, dtype=torch.float64)
+
+    def heads(x):  # [T, 1, d] -> [H, T, hd]
+        return x.view(x.size(0), H, hd).transpose(0, 1)
+
+    with torch.no_grad():
+        cross = [(heads(l.encoder_attn.k_proj(enc)), heads(l.encoder_attn.v_proj(enc))) for l in m.decoder.layers]
+        cache_k = [torch.zeros(H, L, hd, dtype=torch.float64) for _ in m.decoder.layers]
+        cache_v = [torch.zeros(H, L, hd, dtype=torch.float64) for _ in m.decoder.layers]
+        for t in range(L):
+            x_all, _ = m.speech_decoder_prenet(frames[:, : t + 1], spkembs=spk)
+            want, extra = m.decoder(x_all, None, enc_out, alignment_layer=-1)
+            x = x_all[:, t:].transpose(0, 1)  # the new row only, [1, 1, d]
+            for li, l in enumerate(m.decoder.layers):
+                assert not l.normalize_before
+                a = l.self_attn
+                cache_k[li][:, t] = heads(a.k_proj(x))[:, 0]
+                cache_v[li][:, t] = heads(a.v_proj(x))[:, 0]
+                q = heads(a.q_proj(x) * a.scaling)  # [H, 1, hd]
+                p = torch.softmax(q @ cache_k[li][:, : t + 1].transpose(1, 2), dim=-1)
+                o = (p @ cache_v[li][:, : t + 1]).transpose(0, 1).reshape(1, 1, d)
+                x = l.self_attn_layer_norm(x + a.out_proj(o))
+                c = l.encoder_attn
+                q = heads(c.q_proj(x) * c.scaling)
+                pc = torch.softmax(q @ cross[li][0].transpose(1, 2), dim=-1)  # [H, 1, S]
+                o = (pc @ cross[li][1]).transpose(0, 1).reshape(1, 1, d)
+                x = l.encoder_attn_layer_norm(x + c.out_proj(o))
+                x = l.final_layer_norm(x + l.fc2(F.gelu(l.fc1(x).float()).type_as(x)))  # fp32 GELU as the reference
+                assert torch.allclose(pc[:, 0], extra["attn"][0][li][0, :, -1], atol=1e-12)
+            assert torch.allclose(x[0, 0], want[0, -1], atol=1e-6), t  # the fp32 GELU rounding bounds it
