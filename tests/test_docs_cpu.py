@@ -1,0 +1,32 @@
+"""Documentation integrity: reference citations (file:line) in sources, header and docs resolve against the mounted
+reference tree (skipped on the GPU box, where /root/reference does not exist)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_reference_citations_resolve():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_citations.py")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_header_entry_points_all_cite_the_reference():
+    """include/speecht5_b200.h: every exported entry point carries a doc comment that names what it replaces."""
+    import re
+    text = open(os.path.join(ROOT, "include", "speecht5_b200.h")).read()
+    protos = list(re.finditer(r"\n(?:ST5_API\s+)?(?:int|void|const char\s*\*|size_t)\s+(st5_\w+)\s*\(", text))
+    assert len(protos) > 20
+    missing = []
+    for m in protos:
+        if m.group(1) in ("st5_version", "st5_last_error", "st5_device_ok", "st5_cast_bf16", "st5_ln_bwd_blocks"):
+            continue  # library plumbing without a reference counterpart
+        block = text[max(0, m.start() - 2500): m.start()]  # the section comment above the prototype group
+        if not re.search(r"\.py:\d+", block):
+            missing.append(m.group(1))
+    assert not missing, missing
