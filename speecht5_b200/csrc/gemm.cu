@@ -65,14 +65,19 @@ __device__ __forceinline__ void actgrad8(float* v, const uint4 u) {
   }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// CTAS = 2 (SURVEY section 8f / DESIGN section 8 item 1): the two CTAs of a cluster -- the two SMs of one TPC -- share a
+// 256 x BN output tile. Each stages its own 128 rows of A and BN/2 columns of B (a third less operand traffic per
+// output element than 128 x 256), the leader's MMA warp issues tcgen05.mma.cta_group::2 for both, and each CTA drains
+// its own 128 accumulator rows. All pipeline barriers that cross the pair live in the leader's shared memory.
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_c,
                                                                   const __grid_constant__ CUtensorMap map_cpre,
                                                                   const EpiParams p) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  constexpr int B_ROWS = BN / CTAS;  // B columns (= rows of the [N, K] operand) this CTA stages
+  constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K * 2;
   constexpr uint32_t CHUNK_BYTES = 64 * BLOCK_K * 2;  // one 64(mn) x 64(k) MN-major box
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,6 +95,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
   const int warp = threadIdx.x >> 5;
   const int nkb = p.num_k_blocks;
   const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;           // 0 = leader of the pair
+// first tile / stride of this CTA (pair) in the persistent schedule -- kept as expressions, not locals, so that the
+// single-CTA instantiations compile to the code they had before the pair variant existed
+#define ST5_TILE0 (CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define ST5_TILE_STEP (CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+  constexpr int TILE_M = BLOCK_M * CTAS;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_a);
@@ -100,16 +111,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, 2 * BN);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above touched only this CTA's shared / tensor memory, so it may run
@@ -123,16 +140,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = ST5_TILE0; tile < p.num_tiles; tile += ST5_TILE_STEP) {
       const int z = tile / tiles_mn, rmn = tile - z * tiles_mn;
-      const int m0 = (rmn % p.tiles_m) * BLOCK_M, n0 = (rmn / p.tiles_m) * BN;
+      const int m0 = (rmn % p.tiles_m) * TILE_M + rank * BLOCK_M, n0 = (rmn / p.tiles_m) * BN + rank * B_ROWS;
       const int b1 = z % p.nb1, b2 = z / p.nb1;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
         uint8_t* sa = smem_a + stage * A_BYTES;
         uint8_t* sb = smem_b + stage * B_BYTES;
         const int k0 = kb * BLOCK_K;
+        if constexpr (CTAS == 2) {
+          // both producers credit the LEADER's full barrier, which expects the bytes of both halves of the stage
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_4d_pair(sa + c * CHUNK_BYTES, &map_a, fb, m0 + c * 64, k0, b1 * p.a_m1, b2 * p.a_m2);
+          } else {
+            tma_load_4d_pair(sa, &map_a, fb, k0, m0, b1 * p.a_m1, b2 * p.a_m2);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < B_ROWS / 64; ++c)
+              tma_load_4d_pair(sb + c * CHUNK_BYTES, &map_b, fb, n0 + c * 64, k0, b1 * p.b_m1, b2 * p.b_m2);
+          } else {
+            tma_load_4d_pair(sb, &map_b, fb, k0, n0, b1 * p.b_m1, b2 * p.b_m2);
+          }
+        } else {
+        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
         if (A_MN) {
 #pragma unroll
           for (int c = 0; c < BLOCK_M / 64; ++c)
@@ -147,17 +183,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
         } else {
           tma_load_4d(sb, &map_b, &full_bar[stage], k0, n0, b1 * p.b_m1, b2 * p.b_m2);
         }
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      }
+      if constexpr (CTAS == 2) {
+        // tail: the leader's multicast commits arrive on THIS CTA's empty barriers; stay until every slot has been
+        // released so that none of them lands in the shared memory of a CTA that already left
+#pragma unroll 1
+        for (int i = 0; i < STAGES; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    // (pair: only the leader's MMA warp issues; the peer's warp 1 just owns its half of the TMEM allocation)
+    for (int tile = (CTAS == 2 && rank != 0) ? p.num_tiles : ST5_TILE0; tile < p.num_tiles; tile += ST5_TILE_STEP, ++local) {
     const int acc = local & 1;
     const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
     const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
@@ -176,10 +223,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
                                    : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
           const uint64_t db = B_MN ? umma_smem_desc(sb + k * (UMMA_K * 128), CHUNK_BYTES, 1024)
                                    : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_bf16(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (CTAS == 2) umma_bf16_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
+        if constexpr (CTAS == 2) {  // the same barrier offsets in both CTAs of the pair
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (kb == nkb - 1) umma_commit_pair(&tfull_bar[acc], 3);
+        } else {
         umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
         if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);    // accumulator complete
+        }
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -194,9 +247,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     uint64_t dseed = p.drop_seed, doffset = p.drop_offset;
     if (p.drop_thr != 0) resolve_seed(dseed, doffset);
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = ST5_TILE0; tile < p.num_tiles; tile += ST5_TILE_STEP, ++local) {
     const int z = tile / tiles_mn, rmn = tile - z * tiles_mn;
-    const int m0 = (rmn % p.tiles_m) * BLOCK_M, n0 = (rmn / p.tiles_m) * BN;
+    const int m0 = (rmn % p.tiles_m) * TILE_M + rank * BLOCK_M, n0 = (rmn / p.tiles_m) * BN;
     const int b1 = z % p.nb1, b2 = z / p.nb1;
     const int acc = local & 1;
     const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
@@ -212,7 +265,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     if (grp >= BN / 32) {  // narrow tiles: this warp has no chunk, it only releases the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane_id() == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
 #pragma unroll 1
     for (int c = grp; c < BN / 32; c += NGRP) {
@@ -222,7 +278,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
       if (c + NGRP >= BN / 32) {  // last TMEM read of this warp for this tile: hand the stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane_id() == 0) {
+          if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
       const int nb = n0 + c * 32;
       if (nb >= p.N) continue;  // warp-uniform; rows beyond M keep going (their loads are guarded, stores clipped)
@@ -412,11 +471,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // neither CTA may leave while the other's MMAs / TMA still target it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
+
+#undef ST5_TILE0
+#undef ST5_TILE_STEP
 
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -512,16 +576,17 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, int
   return r == CUDA_SUCCESS ? 0 : -12;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS = 1>
 static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t stream) {
+  constexpr int TILE_M = BLOCK_M * CTAS;  // CTAS = 2: one CTA pair per 256 x BN tile, B columns split between the CTAs
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, g.A, g.a_mn, g.M, g.K, g.a_ld, g.nb1, g.a_bs1, g.nb2, g.a_bs2, BLOCK_M);
   if (rc) return rc;
-  rc = make_operand_map(&mb, g.B, g.b_mn, g.N, g.K, g.b_ld, g.nb1, g.b_bs1, g.nb2, g.b_bs2, BN);
+  rc = make_operand_map(&mb, g.B, g.b_mn, g.N, g.K, g.b_ld, g.nb1, g.b_bs1, g.nb2, g.b_bs2, BN / CTAS);
   if (rc) return rc - 10;
-  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * 4096 +
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + (BN / CTAS) * BLOCK_K * 2) + EPI_WARPS * 4096 +
                           (2 * STAGES + 4) * 8 + 16 + 1024;
-  auto kern = gemm_bf16_tcgen05<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05<BN, STAGES, A_MN, B_MN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -529,7 +594,7 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
     attr_set = true;
   }
   EpiParams e2 = ep;
-  e2.tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+  e2.tiles_m = (g.M + TILE_M - 1) / TILE_M;
   e2.tiles_n = (g.N + BN - 1) / BN;
   const long total = (long)e2.tiles_m * e2.tiles_n * g.nb1 * g.nb2;
   if (total > 0x7fffffffL) return -4;
@@ -555,7 +620,8 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
       e2.tma_store = r2 == 0 ? 1 : 0;
     }
   }
-  const int grid = (int)(total < num_sms() ? total : num_sms());  // one persistent CTA per SM
+  const long slots = num_sms() / CTAS;
+  const int grid = (int)(total < slots ? total : slots) * CTAS;  // one persistent CTA (or CTA pair per TPC) per SM
   static const bool pdl = [] {
     const char* e = getenv("ST5_PDL");
     return e == nullptr || atoi(e) != 0;
@@ -565,24 +631,35 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mcp, e2);
   if (le != cudaSuccess) return (int)le;
   return (int)cudaGetLastError();
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS = 1>
 static int launch_major(const GemmDesc& g, const EpiParams& ep, cudaStream_t stream) {
   if (g.a_mn) {
-    if (g.b_mn) return launch_variant<BN, STAGES, true, true>(g, ep, stream);
-    return launch_variant<BN, STAGES, true, false>(g, ep, stream);
+    if (g.b_mn) return launch_variant<BN, STAGES, true, true, CTAS>(g, ep, stream);
+    return launch_variant<BN, STAGES, true, false, CTAS>(g, ep, stream);
   }
-  if (g.b_mn) return launch_variant<BN, STAGES, false, true>(g, ep, stream);
-  return launch_variant<BN, STAGES, false, false>(g, ep, stream);
+  if (g.b_mn) return launch_variant<BN, STAGES, false, true, CTAS>(g, ep, stream);
+  return launch_variant<BN, STAGES, false, false, CTAS>(g, ep, stream);
 }
 
 int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
@@ -615,13 +692,22 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
     const char* e = getenv("ST5_GEMM_BN");
     return e ? atoi(e) : 0;
   }();
+  // ST5_GEMM_PAIR=1 (experimental, off by default until measured on the GPU): 256 x 256 tiles on CTA pairs for every
+  // problem the 256-wide tile would have been chosen for and that has at least one full pair of row blocks.
+  static const int pair_mode = [] {
+    const char* e = getenv("ST5_GEMM_PAIR");
+    return e ? atoi(e) : 0;
+  }();
   if (force_bn == 256) return launch_major<256, 3>(g, ep, stream);
   if (force_bn == 128) return launch_major<128, 5>(g, ep, stream);
   if (force_bn == 64) return launch_major<64, 6>(g, ep, stream);
   const double c256 = g.N > 128 ? cost(256, 1.0) : 1e30;
   const double c128 = g.N > 64 ? cost(128, 1.12) : 1e30;
   const double c64 = cost(64, 1.35);
-  if (c256 <= c128 && c256 <= c64) return launch_major<256, 3>(g, ep, stream);
+  if (c256 <= c128 && c256 <= c64) {
+    if (pair_mode && g.M > BLOCK_M) return launch_major<256, 4, 2>(g, ep, stream);
+    return launch_major<256, 3>(g, ep, stream);
+  }
   if (c128 <= c64) return launch_major<128, 5>(g, ep, stream);
   return launch_major<64, 6>(g, ep, stream);
 }

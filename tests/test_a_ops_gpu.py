@@ -326,3 +326,16 @@ def test_fused_attention_forward_and_backward(cuda, case):
         assert rel(kvb.grad, torch.cat([flat(k.grad), flat(v.grad)], -1)) < 3e-2
     else:
         assert rel(qkv.grad, torch.cat([flat(q.grad), flat(k.grad), flat(v.grad)], -1)) < 3e-2
+
+
+@pytest.mark.skipif(os.environ.get("ST5_TEST_PAIR") != "1",
+                    reason="experimental CTA-pair GEMM (ST5_GEMM_PAIR=1), not yet measured on the GPU: opt-in")
+def test_cta_pair_gemm_is_bit_identical_to_the_single_cta_kernel(cuda):
+    """tools/check_gemm_pair.py: every GEMM class of the step through the 256 x 256 cta_group::2 variant, compared bit
+    for bit with the default kernel (same fp32 accumulation order per output element)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_gemm_pair.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
