@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     }
     fence_mbar_init();
   }
+  if constexpr (CTAS == 2) cluster_sync_all();  // both CTAs of the pair are resident before the paired TMEM allocation
   if (warp == 1) {
     if constexpr (CTAS == 2) {
       tmem_alloc_pair(tmem_slot, 2 * BN);

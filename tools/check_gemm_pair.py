@@ -3,7 +3,8 @@ against the default single-CTA kernel. The switch is read once per process, so e
 the parent compares the outputs BIT FOR BIT (both kernels accumulate the k blocks of an output element in the same order
 in fp32 TMEM) and prints the per-shape times.
 usage (GPU box): timeout 300 python tools/check_gemm_pair.py            # exit 0 = identical everywhere
-       worker : python tools/check_gemm_pair.py --worker OUT.pt          (mode from the environment)"""
+       worker : python tools/check_gemm_pair.py --worker OUT.pt          (mode from the environment)
+       quick  : ST5_GEMM_PAIR=1 python tools/check_gemm_pair.py --quick  (one process, fp32 reference only)"""
 import os
 import subprocess
 import sys
@@ -30,11 +31,13 @@ SHAPES = [
 ]
 
 
-def worker(out_path):
+def worker(out_path, quick=False):
     from speecht5_b200 import kernels as K
     dev = "cuda"
     res = {}
     for i, (M, N, Kd, a_mn, b_mn, f32, nb, epi) in enumerate(SHAPES):
+        if quick and M * N * Kd > 2 ** 36:
+            continue
         g = torch.Generator(device=dev).manual_seed(100 + i)
         A = (torch.randn((nb, Kd, M) if a_mn else (nb, M, Kd), device=dev, generator=g) * 0.25).to(torch.bfloat16)
         B = (torch.randn((nb, Kd, N) if b_mn else (nb, N, Kd), device=dev, generator=g) * 0.25).to(torch.bfloat16)
@@ -62,7 +65,7 @@ def worker(out_path):
         torch.cuda.synchronize()
         first = out.clone()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        reps = 20
+        reps = 2 if quick else 20
         if epi.get("acc"):
             out.copy_(out0)
         ev[0].record()
@@ -72,22 +75,35 @@ def worker(out_path):
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / reps
         ref = None
-        if not epi and M * N * Kd <= 2 ** 33:  # plain product: fp32 statement of the same contraction
+        plain = not (set(epi) - {"bias"})
+        if plain and M * N * Kd <= 2 ** 35:  # plain product (+ bias): fp32 statement of the same contraction
             Af = (A.transpose(1, 2) if a_mn else A).float()
             Bf = (B.transpose(1, 2) if b_mn else B).float()
             ref = torch.bmm(Af, Bf.transpose(1, 2))
+            if epi.get("bias"):
+                ref = ref + kw["bias"]
             err = ((first.float() - ref).norm() / ref.norm()).item()
         else:
             err = None
         res[i] = dict(out=first.cpu(), pre=None if pre is None else pre.cpu(), ms=ms, err=err)
         print(f"shape {i} {SHAPES[i][:7]} {ms * 1e3:8.1f} us  {2.0 * nb * M * N * Kd / ms / 1e9:7.1f} TFLOP/s"
               f"  rel-err-vs-fp32 {err}", flush=True)
+    if quick:
+        errs = [r["err"] for r in res.values() if r["err"] is not None]
+        finite = all(bool(torch.isfinite(r["out"].float()).all()) for r in res.values())
+        ok = finite and len(errs) > 0 and max(errs) < 1e-2
+        print(f"QUICK mode={os.environ.get('ST5_GEMM_PAIR', '0')}: max rel err {max(errs):.3e}, finite={finite} ->",
+              "OK" if ok else "FAILED")
+        return 0 if ok else 1
     torch.save(res, out_path)
+    return 0
 
 
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--worker":
         return worker(sys.argv[2])
+    if len(sys.argv) > 1 and sys.argv[1] == "--quick":  # one process, mode from the environment, fp32 reference only
+        return worker(None, quick=True)
     outs = {}
     for mode in ("0", "1"):
         path = f"/tmp/gemm_pair_{mode}.pt"
