@@ -30,3 +30,19 @@ def test_header_entry_points_all_cite_the_reference():
         if not re.search(r"\.py:\d+", block):
             missing.append(m.group(1))
     assert not missing, missing
+
+
+def test_integration_md_binding_matches_the_shipped_ctypes_struct():
+    """The ctypes stub INTEGRATION.md shows a maintainer is the struct the package itself binds (same field names, order
+    and C types), and its example call compiles."""
+    import ctypes
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class st5_gemm_args(ctypes.Structure)"): text.index("lib.st5_gemm_bf16.argtypes")]
+    ns = {"ctypes": ctypes}
+    exec(block, ns)  # the documentation snippet itself
+    doc_fields = [(n, t) for n, t in ns["st5_gemm_args"]._fields_]
+    from speecht5_b200._lib import GemmArgs
+    assert [(n, t) for n, t in GemmArgs._fields_] == doc_fields
+    assert ctypes.sizeof(GemmArgs) == ctypes.sizeof(ns["st5_gemm_args"])
+    assert re.search(r"act=2\b", text) and "ST5_ACT_GELU" in open(os.path.join(ROOT, "include", "speecht5_b200.h")).read()
