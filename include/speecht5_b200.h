@@ -186,6 +186,24 @@ int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const
                int dtype, int64_t rows, int64_t C, int act, float drop_p, uint64_t seed, uint64_t offset,
                float* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------------- waveform front end
+ * (speech-input branch, SURVEY section 8a row 2 -- EXPERIMENTAL: written without GPU time, not yet validated on device)
+ * Layer 0 of ConvFeatureExtractionModel in mode "default" (speech_encoder_prenet.py:290-327,349-354): Conv1d(1 -> C, K
+ * taps, `stride`, no bias) + Fp32GroupNorm(C groups: statistics per utterance and channel over time) + GELU
+ * (fairseq/modules/gelu.py:24), fused. wave [B, n_samples] fp32; w [C, K]; y [B, T0, C] channels-last in `dtype`,
+ * T0 = (n_samples - K) / stride + 1; mean / rstd [B, C] are saved for the backward. The convolution is recomputed from
+ * the waveform in every pass, so the [B, T0, C] tensor is written once (forward) and dy read twice (backward).
+ * ws: st5_conv0_ws_floats(...) floats of scratch. act: ST5_ACT_GELU or ST5_ACT_GELU_TANH. C <= 1024, K <= 16.
+ * Backward: dw [C, K], dgamma [C], dbeta [C] are ACCUMULATED (+=); the input is the waveform: no input gradient. */
+int64_t st5_conv0_ws_floats(int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride);
+int st5_conv0_gn_gelu_fwd(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                          float* mean, float* rstd, float* ws, int32_t B, int64_t n_samples, int32_t C, int32_t K,
+                          int32_t stride, float eps, int act, void* stream);
+int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws,
+                          int dtype, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride, int act,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------------- optimizer
  * Replaces fairseq/optim/adam.py + fp16_optimizer.py:106-218 on a flat fp32 parameter buffer: one pass applies the
  * gradient scale (grad_mul x clip coefficient max_norm / (norm + 1e-6) capped at 1: fairseq/utils.py clip_grad_norm_,

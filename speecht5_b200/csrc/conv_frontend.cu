@@ -1,0 +1,264 @@
+// First layer of the waveform feature extractor, fused: Conv1d(1 -> C, k, stride, no bias) + GroupNorm(C groups, i.e.
+// per-(utterance, channel) statistics over time, fp32) + GELU, channels-last output for the window GEMMs of the next
+// layers. Reference: speecht5/models/modules/speech_encoder_prenet.py:290-327,349-354 (block builder, mode "default"),
+// fairseq Fp32GroupNorm, fairseq/modules/gelu.py:24. SURVEY section 8a row 2: in the reference this layer makes ~4 full
+// passes over a 65 MB/utterance fp32 tensor (conv write, GroupNorm read x2, GELU read/write); here the k-tap
+// convolution is cheap enough (k MACs per output) to be RECOMPUTED from the waveform in every pass, so nothing but the
+// final bf16 activations (and 2 floats of statistics per utterance and channel) ever touches HBM:
+//   forward : pass 1 statistics (reads the waveform only), pass 2 normalise + GELU + store  -> 1 write of [B, T, C]
+//   backward: pass 1 sums of g and g*xhat (reads dy), pass 2 weight gradient (reads dy)      -> 2 reads of [B, T, C]
+// The input is the waveform, so there is no input gradient. One thread per channel, TCH output frames per block, the
+// waveform segment of the block staged in shared memory (every thread reads the same address: broadcast).
+//
+// Written at the end of round 1 without GPU time: validated only through its CPU restatement
+// (tests/test_kernel_algorithms_cpu.py); the gated GPU test compares it with oracle/speecht5_oracle_asr.py.
+#include "kernels.cuh"
+
+namespace st5 {
+
+constexpr int C0_TCH = 128;   // output frames per block
+constexpr int C0_KMAX = 16;   // taps held in registers
+
+__device__ __forceinline__ float c0_act(float z, int act) { return act == 4 ? gelu_tanh_fwd(z) : gelu_fwd(z); }
+
+// stages wave[b][t0*S .. t0*S + (nt-1)*S + K) and this thread's taps; returns the number of frames of the block
+__device__ __forceinline__ int c0_stage(const float* __restrict__ wave, const float* __restrict__ w, float* seg,
+                                        float (&wr)[C0_KMAX], int64_t n, int T0, int C, int K, int S, int& t0) {
+  const int b = blockIdx.y, c = threadIdx.x;
+  t0 = blockIdx.x * C0_TCH;
+  const int nt = min(C0_TCH, T0 - t0);
+  const int len = (nt - 1) * S + K;
+  const float* src = wave + (int64_t)b * n + (int64_t)t0 * S;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) seg[i] = src[i];
+#pragma unroll
+  for (int k = 0; k < C0_KMAX; ++k) wr[k] = (k < K && c < C) ? w[c * K + k] : 0.f;
+  __syncthreads();
+  return nt;
+}
+__device__ __forceinline__ float c0_conv(const float* seg, const float (&wr)[C0_KMAX], int t, int K, int S) {
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < C0_KMAX; ++k)
+    if (k < K) v = fmaf(wr[k], seg[t * S + k], v);
+  return v;
+}
+
+// part[((b * chunks + chunk) * 2 + {0: sum, 1: centred sum of squares}) * C + c]
+__global__ void conv0_stats_kernel(const float* __restrict__ wave, const float* __restrict__ w, float* __restrict__ part,
+                                   int64_t n, int T0, int C, int K, int S) {
+  extern __shared__ float seg[];
+  float wr[C0_KMAX];
+  int t0;
+  const int nt = c0_stage(wave, w, seg, wr, n, T0, C, K, S, t0);
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float sum = 0.f;
+  for (int t = 0; t < nt; ++t) sum += c0_conv(seg, wr, t, K, S);
+  const float mu = sum / (float)nt;
+  float m2 = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const float d = c0_conv(seg, wr, t, K, S) - mu;
+    m2 = fmaf(d, d, m2);
+  }
+  float* dst = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
+  dst[c] = sum;
+  dst[C + c] = m2;
+}
+
+// Chan's pairwise combination of the per-chunk (sum, M2) in double: mean / rstd per (utterance, channel)
+__global__ void conv0_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
+                                      int T0, int C, int chunks, float eps) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= C) return;
+  const float* p = part + (int64_t)b * chunks * 2 * C;
+  double tot = 0.0;
+  for (int i = 0; i < chunks; ++i) tot += (double)p[(int64_t)i * 2 * C + c];
+  const double mu = tot / (double)T0;
+  double m2 = 0.0;
+  for (int i = 0; i < chunks; ++i) {
+    const int ni = min(C0_TCH, T0 - i * C0_TCH);
+    const double d = (double)p[(int64_t)i * 2 * C + c] / (double)ni - mu;
+    m2 += (double)p[(int64_t)i * 2 * C + C + c] + (double)ni * d * d;
+  }
+  mean[b * C + c] = (float)mu;
+  rstd[b * C + c] = (float)(1.0 / sqrt(m2 / (double)T0 + (double)eps));  // biased variance, as GroupNorm
+}
+
+template <typename T>
+__global__ void conv0_apply_kernel(const float* __restrict__ wave, const float* __restrict__ w,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ y,
+                                   int64_t n, int T0, int C, int K, int S, int act) {
+  extern __shared__ float seg[];
+  float wr[C0_KMAX];
+  int t0;
+  const int nt = c0_stage(wave, w, seg, wr, n, T0, C, K, S, t0);
+  const int b = blockIdx.y, c = threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[b * C + c];
+  const float sc = rstd[b * C + c] * gamma[c];
+  const float sh = beta[c];
+  T* dst = y + ((int64_t)b * T0 + t0) * C + c;
+  for (int t = 0; t < nt; ++t) {
+    const float z = fmaf(c0_conv(seg, wr, t, K, S) - mu, sc, sh);
+    stf<T>(dst + (int64_t)t * C, c0_act(z, act));
+  }
+}
+
+// backward pass 1: part[.. * 2 + {0: sum g, 1: sum g * xhat}], g = dy * act'(z)
+template <typename T>
+__global__ void conv0_bwd_sums_kernel(const T* __restrict__ dy, const float* __restrict__ wave,
+                                      const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, float* __restrict__ part, int64_t n, int T0, int C,
+                                      int K, int S, int act) {
+  extern __shared__ float seg[];
+  float wr[C0_KMAX];
+  int t0;
+  const int nt = c0_stage(wave, w, seg, wr, n, T0, C, K, S, t0);
+  const int b = blockIdx.y, c = threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[b * C + c], rs = rstd[b * C + c], ga = gamma[c], be = beta[c];
+  const T* src = dy + ((int64_t)b * T0 + t0) * C + c;
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const float xh = (c0_conv(seg, wr, t, K, S) - mu) * rs;
+    const float g = ldf<T>(src + (int64_t)t * C) * act_grad(fmaf(xh, ga, be), act);
+    s1 += g;
+    s2 = fmaf(g, xh, s2);
+  }
+  float* dst = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
+  dst[c] = s1;
+  dst[C + c] = s2;
+}
+
+// totals per (utterance, channel) + the affine gradients: dbeta[c] += sum_b S1, dgamma[c] += sum_b S2
+__global__ void conv0_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ sums,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int chunks) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= C) return;
+  const float* p = part + (int64_t)b * chunks * 2 * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < chunks; ++i) {
+    s1 += (double)p[(int64_t)i * 2 * C + c];
+    s2 += (double)p[(int64_t)i * 2 * C + C + c];
+  }
+  sums[(b * 2) * C + c] = (float)s1;
+  sums[(b * 2 + 1) * C + c] = (float)s2;
+  atomicAdd(dbeta + c, (float)s1);
+  atomicAdd(dgamma + c, (float)s2);
+}
+
+// backward pass 2: dv = rstd * gamma * (g - S1/T - xhat * S2/T); per-block partial dW[c][k] = sum_t dv[t] * wave[t*S + k]
+template <typename T>
+__global__ void conv0_bwd_w_kernel(const T* __restrict__ dy, const float* __restrict__ wave, const float* __restrict__ w,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ sums, float* __restrict__ part, int64_t n, int T0, int C,
+                                   int K, int S, int act) {
+  extern __shared__ float seg[];
+  float wr[C0_KMAX];
+  int t0;
+  const int nt = c0_stage(wave, w, seg, wr, n, T0, C, K, S, t0);
+  const int b = blockIdx.y, c = threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[b * C + c], rs = rstd[b * C + c], ga = gamma[c], be = beta[c];
+  const float inv_t = 1.f / (float)T0;
+  const float m1 = sums[(b * 2) * C + c] * inv_t, m2 = sums[(b * 2 + 1) * C + c] * inv_t;
+  const T* src = dy + ((int64_t)b * T0 + t0) * C + c;
+  float acc[C0_KMAX];
+#pragma unroll
+  for (int k = 0; k < C0_KMAX; ++k) acc[k] = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    const float xh = (c0_conv(seg, wr, t, K, S) - mu) * rs;
+    const float g = ldf<T>(src + (int64_t)t * C) * act_grad(fmaf(xh, ga, be), act);
+    const float dv = rs * ga * (g - m1 - xh * m2);
+#pragma unroll
+    for (int k = 0; k < C0_KMAX; ++k)
+      if (k < K) acc[k] = fmaf(dv, seg[t * S + k], acc[k]);
+  }
+  float* dst = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (int64_t)C * K + (int64_t)c * K;
+#pragma unroll
+  for (int k = 0; k < C0_KMAX; ++k)
+    if (k < K) dst[k] = acc[k];
+}
+
+// dw[i] += sum over the per-block partial rows (row range split over blockIdx.y, one atomic per thread)
+__global__ void conv0_reduce_w_kernel(const float* __restrict__ part, float* __restrict__ dw, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cols) return;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += part[(int64_t)r * cols + i];
+  if (r1 > r0) atomicAdd(dw + i, s);
+}
+
+static inline int c0_frames(int64_t n, int K, int S) { return n < K ? 0 : (int)((n - K) / S + 1); }
+static inline int c0_threads(int C) { return (C + 31) / 32 * 32; }
+
+int64_t conv0_ws_floats(int32_t B, int64_t n, int32_t C, int32_t K, int32_t S) {
+  const int T0 = c0_frames(n, K, S);
+  const int64_t chunks = (T0 + C0_TCH - 1) / C0_TCH;
+  return (int64_t)B * chunks * C * (K > 2 ? K : 2) + 2 * (int64_t)B * C;
+}
+
+static int c0_check(int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act) {
+  if (B <= 0 || C <= 0 || C > 1024 || K <= 0 || K > C0_KMAX || S <= 0) return -2;
+  if (act != 2 && act != 4) return -3;
+  if (c0_frames(n, K, S) <= 0) return -4;
+  return 0;
+}
+
+int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                     float* mean, float* rstd, float* ws, int32_t B, int64_t n, int32_t C, int32_t K, int32_t S,
+                     float eps, int act, cudaStream_t st) {
+  const int rc = c0_check(B, n, C, K, S, act);
+  if (rc) return rc;
+  const int T0 = c0_frames(n, K, S);
+  const int chunks = (T0 + C0_TCH - 1) / C0_TCH;
+  const dim3 grid(chunks, B), block(c0_threads(C));
+  const size_t smem = ((size_t)(C0_TCH - 1) * S + K) * sizeof(float);
+  if (smem > 48 * 1024) return -5;
+  conv0_stats_kernel<<<grid, block, smem, st>>>(wave, w, ws, n, T0, C, K, S);
+  conv0_finalize_kernel<<<B, block, 0, st>>>(ws, mean, rstd, T0, C, chunks, eps);
+  if (dtype == ST5_BF16)
+    conv0_apply_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(wave, w, gamma, beta, mean, rstd,
+                                                                 reinterpret_cast<__nv_bfloat16*>(y), n, T0, C, K, S, act);
+  else
+    conv0_apply_kernel<float><<<grid, block, smem, st>>>(wave, w, gamma, beta, mean, rstd, reinterpret_cast<float*>(y),
+                                                        n, T0, C, K, S, act);
+  return (int)cudaGetLastError();
+}
+
+int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                     const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
+                     int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t st) {
+  const int rc = c0_check(B, n, C, K, S, act);
+  if (rc) return rc;
+  const int T0 = c0_frames(n, K, S);
+  const int chunks = (T0 + C0_TCH - 1) / C0_TCH;
+  const dim3 grid(chunks, B), block(c0_threads(C));
+  const size_t smem = ((size_t)(C0_TCH - 1) * S + K) * sizeof(float);
+  if (smem > 48 * 1024) return -5;
+  float* sums = ws + (int64_t)B * chunks * C * (K > 2 ? K : 2);
+  if (dtype == ST5_BF16) {
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(dy);
+    conv0_bwd_sums_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, ws, n, T0, C, K,
+                                                                    S, act);
+    conv0_bwd_finalize_kernel<<<B, block, 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
+    conv0_bwd_w_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, sums, ws, n, T0, C,
+                                                                 K, S, act);
+  } else {
+    const float* g = reinterpret_cast<const float*>(dy);
+    conv0_bwd_sums_kernel<float><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, ws, n, T0, C, K, S, act);
+    conv0_bwd_finalize_kernel<<<B, block, 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
+    conv0_bwd_w_kernel<float><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, sums, ws, n, T0, C, K, S,
+                                                         act);
+  }
+  const int cols = C * K;
+  conv0_reduce_w_kernel<<<dim3((cols + 127) / 128, 32), 128, 0, st>>>(ws, dw, B * chunks, cols);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace st5

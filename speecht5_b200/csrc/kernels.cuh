@@ -122,6 +122,13 @@ int bn_bwd_launch(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, co
                   const float* save_mean, const float* save_rstd, void* dx, int64_t dx_ld, float* dgamma, float* dbeta,
                   int dtype, int64_t rows, int64_t C, int act, float drop_p, uint64_t seed, uint64_t offset,
                   float* scratch, cudaStream_t s);
+int64_t conv0_ws_floats(int32_t B, int64_t n, int32_t C, int32_t K, int32_t S);
+int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                     float* mean, float* rstd, float* ws, int32_t B, int64_t n, int32_t C, int32_t K, int32_t S,
+                     float eps, int act, cudaStream_t s);
+int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                     const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
+                     int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
 int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s);
 int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,

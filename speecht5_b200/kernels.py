@@ -234,6 +234,34 @@ def bn_bwd(dy, dy_ld, x, x_ld, y_pre, gamma, save_mean, save_rstd, dx, dx_ld, dg
     _count(2)
 
 
+def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
+    """EXPERIMENTAL (not yet validated on a GPU). wave [B, n] fp32, w [C, K] fp32 -> y [B, T0, C] (y.dtype)."""
+    _require_cuda(wave, w, y)
+    assert wave.dtype == torch.float32 and w.dtype == torch.float32 and wave.is_contiguous() and w.is_contiguous()
+    B, n = wave.shape
+    Cc, Kt = w.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.st5_conv0_ws_floats(B, n, Cc, Kt, stride), device=wave.device, dtype=torch.float32)
+    _lib.check(lib.st5_conv0_gn_gelu_fwd(_ptr(wave), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(y), dtype_id(y), _ptr(mean),
+                                         _ptr(rstd), _ptr(ws), B, n, Cc, Kt, stride, eps, ACT_IDS[act], _stream()),
+               "st5_conv0_gn_gelu_fwd")
+    _count(3)
+
+
+def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, stride, act):
+    """EXPERIMENTAL. dw / dgamma / dbeta (fp32) are accumulated."""
+    _require_cuda(dy, wave, w)
+    assert dy.is_contiguous()
+    B, n = wave.shape
+    Cc, Kt = w.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.st5_conv0_ws_floats(B, n, Cc, Kt, stride), device=wave.device, dtype=torch.float32)
+    _lib.check(lib.st5_conv0_gn_gelu_bwd(_ptr(dy), _ptr(wave), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd),
+                                         _ptr(dw), _ptr(dgamma), _ptr(dbeta), _ptr(ws), dtype_id(dy), B, n, Cc, Kt,
+                                         stride, ACT_IDS[act], _stream()), "st5_conv0_gn_gelu_bwd")
+    _count(4)
+
+
 def sumsq(x, out):
     lib = _lib.load()
     _lib.check(lib.st5_sumsq(_ptr(x), x.numel(), _ptr(out), _stream()), "st5_sumsq")

@@ -339,3 +339,42 @@ def test_cta_pair_gemm_is_bit_identical_to_the_single_cta_kernel(cuda):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_gemm_pair.py")], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("ST5_TEST_CONV0") != "1",
+                    reason="fused conv0 + GroupNorm + GELU front-end kernel: written without GPU time, opt-in until run")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv0_groupnorm_gelu_against_the_oracle_layer(cuda, dtype):
+    """csrc/conv_frontend.cu vs layer 0 of oracle ConvFeatureExtractionModel (mode "default"): forward activations and
+    the gradients of the conv weight and the GroupNorm affine, ragged T (last block partial)."""
+    from oracle.speecht5_oracle_asr import ConvFeatureExtractionModel
+    from speecht5_b200 import kernels as K
+    torch.manual_seed(3)
+    B, n = 3, 5 * 700 + 10 + 3
+    fe = ConvFeatureExtractionModel([(512, 10, 5)], mode="default").double()
+    with torch.no_grad():
+        fe.conv_layers[0][2].weight.add_(0.1 * torch.randn(512, dtype=torch.float64))
+        fe.conv_layers[0][2].bias.add_(0.1 * torch.randn(512, dtype=torch.float64))
+    wave = torch.randn(B, n, dtype=torch.float64) * 0.5 + 0.1
+    y_ref = fe(wave).transpose(1, 2)  # [B, T0, C]
+    T0 = y_ref.shape[1]
+    assert T0 == (n - 10) // 5 + 1 and T0 % 128 != 0
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    conv, gn = fe.conv_layers[0][0], fe.conv_layers[0][2]
+    w = conv.weight.detach().float().reshape(512, 10).contiguous().to(cuda)
+    gamma, beta = gn.weight.detach().float().to(cuda), gn.bias.detach().float().to(cuda)
+    wv = wave.float().to(cuda)
+    y = torch.empty(B, T0, 512, device=cuda, dtype=dtype)
+    mean = torch.empty(B, 512, device=cuda)
+    rstd = torch.empty(B, 512, device=cuda)
+    K.conv0_gn_gelu_fwd(wv, w, gamma, beta, y, mean, rstd, 5, gn.eps, "gelu")
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel(y.cpu(), y_ref) < tol
+    dw = torch.zeros(512, 10, device=cuda)
+    dg = torch.zeros(512, device=cuda)
+    db = torch.zeros(512, device=cuda)
+    K.conv0_gn_gelu_bwd(dy.to(cuda).to(dtype).contiguous(), wv, w, gamma, beta, mean, rstd, dw, dg, db, 5, "gelu")
+    assert rel(dw.cpu(), conv.weight.grad.reshape(512, 10)) < tol
+    assert rel(dg.cpu(), gn.weight.grad) < tol
+    assert rel(db.cpu(), gn.bias.grad) < tol

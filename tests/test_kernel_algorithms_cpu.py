@@ -1,6 +1,8 @@
 """CPU: executable design notes for the convolution rows that come next. Each test states, in
 numpy/torch on the host, the exact operand VIEW the device GEMM will be given -- no im2col copies -- and checks it
 against torch's convolution. The postnet's 5-tap convolution already runs this way (speecht5_b200/ops.py:Conv1dK5Fn)."""
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -263,3 +265,49 @@ def test_incremental_decode_with_kv_cache_equals_prefix_recompute():
                 x = l.final_layer_norm(x + l.fc2(F.gelu(l.fc1(x).float()).type_as(x)))  # fp32 GELU as the reference
                 assert torch.allclose(pc[:, 0], extra["attn"][0][li][0, :, -1], atol=1e-12)
             assert torch.allclose(x[0, 0], want[0, -1], atol=1e-6), t  # the fp32 GELU rounding bounds it
+
+
+def test_fused_conv0_groupnorm_gelu_statement_matches_autograd():
+    """csrc/conv_frontend.cu, restated step by step in numpy/torch on the CPU: chunked (sum, centred M2) statistics
+    combined with Chan's formula, y = gelu((v - mean) rstd gamma + beta), and the backward the kernels use --
+    g = dy gelu'(z), S1 = sum_t g, S2 = sum_t g xhat, dbeta = sum_b S1, dgamma = sum_b S2,
+    dv = rstd gamma (g - S1/T - xhat S2/T), dW[c, k] = sum_{b,t} dv[b, t, c] wave[b, t*stride + k] -- against autograd
+    through Conv1d -> GroupNorm(C, C) -> GELU (speech_encoder_prenet.py:290-327)."""
+    torch.manual_seed(8)
+    B, n, Cc, Kt, S, TCH = 2, 1403, 6, 10, 5, 128
+    wave = torch.randn(B, n, dtype=torch.float64) + 0.3
+    w = torch.randn(Cc, Kt, dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(Cc, dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(Cc, dtype=torch.float64, requires_grad=True)
+    eps = 1e-5
+    v_ref = F.conv1d(wave[:, None], w[:, None], stride=S)  # [B, C, T0]
+    y_ref = F.gelu(F.group_norm(v_ref, Cc, gamma, beta, eps)).transpose(1, 2)  # channels-last [B, T0, C]
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    T0 = (n - Kt) // S + 1
+    assert y_ref.shape == (B, T0, Cc)
+    with torch.no_grad():
+        win = wave.unfold(1, Kt, S)  # [B, T0, K] overlapping windows of the waveform
+        v = win @ w.t()  # [B, T0, C]
+        # forward statistics: per chunk (sum, M2 about the chunk mean), then Chan's combination
+        tot, parts = torch.zeros(B, Cc, dtype=torch.float64), []
+        for t0 in range(0, T0, TCH):
+            blk = v[:, t0:t0 + TCH]
+            s = blk.sum(1)
+            parts.append((blk.shape[1], s, ((blk - s[:, None] / blk.shape[1]) ** 2).sum(1)))
+            tot += s
+        mean = tot / T0
+        m2 = sum(p[2] + p[0] * (p[1] / p[0] - mean) ** 2 for p in parts)
+        rstd = 1.0 / torch.sqrt(m2 / T0 + eps)
+        xh = (v - mean[:, None]) * rstd[:, None]
+        z = xh * gamma + beta
+        assert torch.allclose(F.gelu(z), y_ref, atol=1e-12)
+        # backward
+        cdf = 0.5 * (1 + torch.erf(z / math.sqrt(2)))
+        g = dy * (cdf + z * torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi))
+        s1, s2 = g.sum(1), (g * xh).sum(1)
+        assert torch.allclose(s1.sum(0), beta.grad, atol=1e-10)
+        assert torch.allclose(s2.sum(0), gamma.grad, atol=1e-10)
+        dv = rstd[:, None] * gamma * (g - s1[:, None] / T0 - xh * s2[:, None] / T0)
+        dw = torch.einsum("btc,btk->ck", dv, win)
+        assert torch.allclose(dw, w.grad, atol=1e-9)
