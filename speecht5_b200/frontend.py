@@ -1,0 +1,187 @@
+"""Waveform feature extractor of the speech-input branch (reference
+speecht5/models/modules/speech_encoder_prenet.py:277-374, mode "default"): seven bias-free Conv1d layers
+[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2, GroupNorm(512 groups) after the first, GELU after each.
+
+EXPERIMENTAL -- written at the end of round 1 without GPU time. The index algebra is checked on the CPU against
+torch's convolutions through a GEMM emulator (tests/test_frontend_cpu.py); the device run is the gated GPU test
+(ST5_TEST_CONV0=1 / ST5_TEST_FRONTEND=1). Nothing on the validated TTS path imports this module.
+
+Device formulation (channels-last activations [B, T, C] throughout, no im2col, no transposes):
+* layer 0: csrc/conv_frontend.cu -- conv + GroupNorm + GELU fused, the convolution recomputed from the waveform in
+  every pass (kernels.conv0_gn_gelu_fwd / _bwd);
+* layers 1..6 forward: ONE batched tcgen05 GEMM each over an overlapping-window view of the input -- row t of
+  utterance b is the k*C_in contiguous elements starting at frame t*stride (row pitch stride*C_in) -- with GELU and
+  the pre-activation store in the epilogue;
+* input gradient: the transposed convolution split by output phase r = i mod stride; phase r is a window GEMM over
+  the (front-padded) gradient with the taps t = r, r+stride, ... in reverse order, written with row pitch stride*C_in;
+* weight gradient: per utterance dW2[b] = g_b^T . windows_b (both operands read MN-major), summed over b."""
+import torch
+
+from . import kernels as K
+from .ops import RT, _resolve_act, _split
+
+
+def _passes(a, b, out, kw, epi=None):
+    """One GEMM in bf16 mode; hi*hi + hi*lo + lo*hi (fp32 accumulate in `out`) in parity mode. a, b: (hi, lo) pairs."""
+    a_hi, a_lo = a
+    b_hi, b_lo = b
+    epi = epi or {}
+    if a_lo is None and b_lo is None:
+        return K.gemm(a_hi, b_hi, out, **kw, **epi)
+    assert out.dtype == torch.float32
+    K.gemm(a_hi, b_hi, out, **kw)
+    K.gemm(a_hi, b_lo, out, accumulate=True, **kw)
+    K.gemm(a_lo, b_hi, out, accumulate=True, **kw, **epi)
+    return out
+
+
+def _off(pair, elems):
+    """The (hi, lo) operand pair advanced by `elems` elements of the flat buffer."""
+    return tuple(None if t is None else t.reshape(-1)[elems:] for t in pair)
+
+
+def conv_out_len(T, k, s):
+    return (T - k) // s + 1
+
+
+class StridedConvGeluFn(torch.autograd.Function):
+    """y = GELU(Conv1d(C_in -> C_out, k, stride, no bias)(x)) on channels-last x [B, T, C_in] -> [B, T_out, C_out]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        x = x.contiguous()
+        B, T, Cin = x.shape
+        Cout, _, k = weight.shape
+        s = int(stride)
+        To = conv_out_len(T, k, s)
+        act = _resolve_act("gelu", x.dtype)
+        w2 = RT.shadow(("fe_f", id(weight)), lambda: weight.detach().permute(0, 2, 1).reshape(Cout, k * Cin))
+        xa = _split(x.view(B * T, Cin))
+        y = torch.empty((B, To, Cout), dtype=x.dtype, device=x.device)
+        pre = torch.empty_like(y)
+        kw = dict(M=To, N=Cout, K=k * Cin, a_ld=s * Cin, b_ld=k * Cin, c_ld=Cout, nb1=B, nb2=1, a_bs=(T * Cin, 0),
+                  b_bs=(0, 0), c_bs=(To * Cout, 0))
+        _passes(xa, w2, y, kw, dict(act=act, c_pre=pre))
+        ctx.save_for_backward(weight, pre)
+        ctx.xa = xa
+        ctx.meta = (B, T, Cin, Cout, k, s, To, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        weight, pre = ctx.saved_tensors
+        B, T, Cin, Cout, k, s, To, act = ctx.meta
+        dev, dt = dy.device, dy.dtype
+        jmax = (k + s - 1) // s                      # taps per output phase, at most
+        mmax = (T + s - 1) // s                      # rows of one phase of dx, at most
+        front = jmax - 1
+        rows_p = front + max(To, mmax) + jmax        # zero rows in front (window history) and behind (untouched tail)
+        gp = torch.zeros((B, rows_p, Cout), dtype=dt, device=dev)
+        g = gp[:, front:front + To]
+        # g = dy * gelu'(pre), written straight into the padded buffer the phase GEMMs read
+        gtmp = torch.empty((B, To, Cout), dtype=dt, device=dev)
+        K.act_bwd(dy.contiguous(), pre, gtmp, act)
+        g.copy_(gtmp)
+        ga = _split(gp.view(B * rows_p, Cout))
+        # ---- input gradient, one window GEMM per phase r: dx[b, s*m + r, :] = sum_q gpad[b, m + q', :] . Wr[q]
+        dx = torch.empty((B, T, Cin), dtype=dt, device=dev)  # every frame belongs to exactly one phase
+        for r in range(s):
+            taps = list(range(r, k, s))              # t = r + s*j, j = 0..J-1
+            J = len(taps)
+            Mr = (T - r + s - 1) // s                # x frames with index = r (mod s)
+            if Mr <= 0:
+                continue
+            if J == 0:
+                dx[:, r::s].zero_()
+                continue
+            # window position q <-> tap j = J-1-q; W_r[ci, q*Cout + co] = W[co, ci, r + s*(J-1-q)]
+            wr = RT.shadow(("fe_b", id(weight), r), lambda taps=taps: weight.detach()[:, :, taps[::-1]]
+                           .permute(1, 2, 0).reshape(Cin, len(taps) * Cout))
+            a_ops = _off(ga, (front - (J - 1)) * Cout)
+            out_r = dx.reshape(-1)[r * Cin:]
+            kw = dict(M=Mr, N=Cin, K=J * Cout, a_ld=Cout, b_ld=J * Cout, c_ld=s * Cin, nb1=B, nb2=1,
+                      a_bs=(rows_p * Cout, 0), b_bs=(0, 0), c_bs=(T * Cin, 0))
+            _passes(a_ops, wr, out_r, kw)
+        # ---- weight gradient: dW2[b][co, t*Cin + ci] = sum_o g[b, o, co] * x[b, s*o + t, ci]
+        dW2 = torch.empty((B, Cout, k * Cin), dtype=torch.float32, device=dev)
+        kw = dict(M=Cout, N=k * Cin, K=To, a_mn=True, b_mn=True, a_ld=Cout, b_ld=s * Cin, c_ld=k * Cin, nb1=B, nb2=1,
+                  a_bs=(rows_p * Cout, 0), b_bs=(T * Cin, 0), c_bs=(Cout * k * Cin, 0))
+        _passes(_off(ga, front * Cout), ctx.xa, dW2, kw)
+        dW = dW2.sum(0).view(Cout, k, Cin).permute(0, 2, 1).contiguous()
+        ctx.xa = None
+        return dx, dW, None
+
+
+class Conv0GroupNormGeluFn(torch.autograd.Function):
+    """Layer 0: waveform [B, n] fp32 -> GELU(GroupNorm_C(Conv1d(1 -> C, k, stride))) channels-last [B, T0, C]."""
+
+    @staticmethod
+    def forward(ctx, wave, weight, gamma, beta, stride, eps, out_dtype):
+        wave = wave.float().contiguous()
+        B, n = wave.shape
+        Cc, _, k = weight.shape
+        s = int(stride)
+        T0 = conv_out_len(n, k, s)
+        act = _resolve_act("gelu", out_dtype)
+        w2 = weight.detach().reshape(Cc, k).float().contiguous()
+        y = torch.empty((B, T0, Cc), dtype=out_dtype, device=wave.device)
+        mean = torch.empty((B, Cc), dtype=torch.float32, device=wave.device)
+        rstd = torch.empty_like(mean)
+        K.conv0_gn_gelu_fwd(wave, w2, gamma.detach().float(), beta.detach().float(), y, mean, rstd, s, eps, act)
+        ctx.save_for_backward(wave, w2, gamma, beta, mean, rstd)
+        ctx.meta = (s, act, tuple(weight.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        wave, w2, gamma, beta, mean, rstd = ctx.saved_tensors
+        s, act, wshape = ctx.meta
+        dw = torch.zeros_like(w2)
+        dg = torch.zeros_like(mean[0])
+        db = torch.zeros_like(mean[0])
+        K.conv0_gn_gelu_bwd(dy.contiguous(), wave, w2, gamma.detach().float(), beta.detach().float(), mean, rstd, dw, dg,
+                            db, s, act)
+        return None, dw.view(wshape), dg, db, None, None, None
+
+
+CONV_FEATURE_LAYERS = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+
+
+class ConvFeatureExtractor(torch.nn.Module):
+    """speech_encoder_prenet.py:277-374 in mode "default" (the Base recipes). Parameter names follow the reference
+    (`conv_layers.{i}.0.weight` [C_out, C_in, k], GroupNorm affine at `conv_layers.0.2.{weight,bias}`). Output is
+    channels-last [B, T, C] -- the reference's [B, C, T] transposed, which is what its caller does next (:169)."""
+
+    def __init__(self, conv_layers=None, mode="default", conv_bias=False):
+        super().__init__()
+        if mode != "default" or conv_bias:
+            raise NotImplementedError("only extractor_mode=default without conv bias (the Base recipes) is built")
+        self.specs = list(conv_layers or CONV_FEATURE_LAYERS)
+        assert self.specs[0][1] <= 16
+        self.conv_layers = torch.nn.ModuleList()
+        in_d = 1
+        for i, (dim, k, s) in enumerate(self.specs):
+            conv = torch.nn.Conv1d(in_d, dim, k, stride=s, bias=False)
+            torch.nn.init.kaiming_normal_(conv.weight)
+            mods = [conv, torch.nn.Dropout(0.0)]
+            if i == 0:
+                mods.append(torch.nn.GroupNorm(dim, dim, affine=True))
+            mods.append(torch.nn.GELU())
+            self.conv_layers.append(torch.nn.Sequential(*mods))
+            in_d = dim
+
+    def forward(self, wave):
+        if not wave.is_cuda:
+            raise RuntimeError("speecht5_b200 kernels need CUDA tensors (no CPU fallback)")
+        blk0 = self.conv_layers[0]
+        x = Conv0GroupNormGeluFn.apply(wave, blk0[0].weight, blk0[2].weight, blk0[2].bias, self.specs[0][2],
+                                       blk0[2].eps, RT.dtype)
+        for i in range(1, len(self.specs)):
+            x = StridedConvGeluFn.apply(x, self.conv_layers[i][0].weight, self.specs[i][2])
+        return x
+
+    def get_out_seq_lens_tensor(self, lengths):
+        out = lengths.clone()
+        for _, k, s in self.specs:
+            out = torch.div(out - k, s, rounding_mode="floor") + 1
+        return out

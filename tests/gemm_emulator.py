@@ -1,0 +1,71 @@
+"""CPU emulation of the C-ABI entry points the host-side compositions call (st5_gemm_bf16 semantics as documented in
+include/speecht5_b200.h, st5_cast_bf16, st5_act_bwd), so that the INDEX ALGEBRA of a composition -- operand views, row
+pitches, batch strides, phase offsets -- can be checked on the CPU against torch. Test infrastructure only: the product
+path has no CPU fallback; tests install these with monkeypatch."""
+import math
+
+import torch
+
+
+def _view(t, nb1, rows, K, mn, ld, bs1):
+    base = t.storage_offset()
+    if mn:  # memory [K][ld], row index contiguous
+        v = torch.as_strided(t, (nb1, K, rows), (bs1, ld, 1), base)
+        return v.transpose(1, 2)
+    return torch.as_strided(t, (nb1, rows, K), (bs1, ld, 1), base)
+
+
+def _gelu_grad(z):
+    return 0.5 * (1 + torch.erf(z / math.sqrt(2))) + z * torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
+
+
+def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1, a_bs=(0, 0),
+         b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None, act=None, alpha=1.0,
+         accumulate=False, drop_p=0.0, seed=0, offset=0, actgrad_pre=None, actgrad_act=None):
+    assert nb2 == 1 and drop_p == 0.0 and bias2 is None and actgrad_pre is None and residual is None
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    a_ld = a_ld if a_ld is not None else (M if a_mn else K)
+    b_ld = b_ld if b_ld is not None else (N if b_mn else K)
+    c_ld = c_ld if c_ld is not None else N
+    for t, ld, bs in ((a, a_ld, a_bs[0]), (b, b_ld, b_bs[0])):  # what cuTensorMapEncodeTiled demands of an operand
+        assert (t.storage_offset() * 2) % 16 == 0 and (ld * 2) % 16 == 0 and (bs * 2) % 16 == 0, "TMA alignment"
+    A = _view(a, nb1, M, K, a_mn, a_ld, a_bs[0]).double()
+    B = _view(b, nb1, N, K, b_mn, b_ld, b_bs[0]).double()
+    C = torch.as_strided(out, (nb1, M, N), (c_bs[0], c_ld, 1), out.storage_offset())
+    v = alpha * torch.bmm(A, B.transpose(1, 2))
+    if accumulate:
+        v = v + C.double()
+    if bias is not None:
+        v = v + bias.double()
+    if c_pre is not None:
+        torch.as_strided(c_pre, (nb1, M, N), (c_bs[0], c_ld, 1), c_pre.storage_offset()).copy_(v.to(c_pre.dtype))
+    if act in ("gelu", "gelu_tanh"):
+        v = torch.nn.functional.gelu(v)
+    elif act == "relu":
+        v = torch.relu(v)
+    elif act == "tanh":
+        v = torch.tanh(v)
+    else:
+        assert act in (None, "none")
+    C.copy_(v.to(out.dtype))
+    return out
+
+
+def cast_bf16(src, hi, lo=None):
+    h = src.to(torch.bfloat16)
+    hi.copy_(h)
+    if lo is not None:
+        lo.copy_((src - h.float()).to(torch.bfloat16))
+
+
+def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
+    assert drop_p == 0.0 and act in ("gelu", "gelu_tanh")
+    dpre.copy_((dy.double() * _gelu_grad(pre.double())).to(dpre.dtype))
+
+
+def install(monkeypatch):
+    from speecht5_b200 import kernels as K
+    monkeypatch.setattr(K, "gemm", gemm)
+    monkeypatch.setattr(K, "cast_bf16", cast_bf16)
+    monkeypatch.setattr(K, "act_bwd", act_bwd)
+    monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)

@@ -1,0 +1,38 @@
+"""CPU: the host-side composition of the waveform front end (speecht5_b200/frontend.py) -- which operand views, row
+pitches, batch strides and phase offsets it hands to st5_gemm_bf16 -- run through the GEMM emulator and compared with
+torch's Conv1d + GELU autograd. (The kernels themselves are covered by the -m gpu tests.)"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gemm_emulator
+
+
+@pytest.mark.parametrize("k,s,T", [(3, 2, 41), (2, 2, 37), (3, 2, 40), (5, 3, 50), (4, 2, 23)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_strided_conv_gelu_composition(monkeypatch, k, s, T, dtype):
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", dtype)
+    RT.invalidate_shadows()
+    torch.manual_seed(k * 100 + s * 10 + T)
+    B, Cin, Cout = 3, 16, 24
+    x = (torch.randn(B, T, Cin) * 0.7).to(dtype).requires_grad_()
+    w = torch.nn.Parameter(torch.randn(Cout, Cin, k) * 0.3)
+    y = frontend.StridedConvGeluFn.apply(x, w, s)
+    dy = torch.randn(y.shape).to(dtype)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_()
+    wr = w.detach().double().requires_grad_()
+    yr = F.gelu(F.conv1d(xr.transpose(1, 2), wr, stride=s)).transpose(1, 2)
+    yr.backward(dy.double())
+    assert y.shape == yr.shape == (B, (T - k) // s + 1, Cout)
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+    tol = 3e-5 if dtype == torch.float32 else 2e-2
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol
+    assert rel(w.grad, wr.grad) < tol
+    RT.invalidate_shadows()
