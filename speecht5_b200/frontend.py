@@ -185,3 +185,86 @@ class ConvFeatureExtractor(torch.nn.Module):
         for _, k, s in self.specs:
             out = torch.div(out - k, s, rounding_mode="floor") + 1
         return out
+
+
+def _cast_pair(w2d):
+    """(hi, lo) bf16 operands of a freshly computed fp32 2-D tensor (not a Parameter: nothing to cache on)."""
+    w2d = w2d.detach().float().contiguous()
+    hi = torch.empty(w2d.shape, dtype=torch.bfloat16, device=w2d.device)
+    lo = torch.empty_like(hi) if RT.dtype == torch.float32 else None
+    K.cast_bf16(w2d, hi, lo)
+    return hi, lo
+
+
+class GroupedPosConvFn(torch.autograd.Function):
+    """y = x + GELU(SamePad(Conv1d(C, C, k, padding k//2, groups G)(x)) + bias) on channels-last x [B, T, C]
+    (speech_encoder_prenet.py:105-119,187-192; k even: the last output frame is dropped). `weight` [C, C/G, k] is the
+    weight-normed tensor g*v/||v|| computed by the caller with torch ops, so its gradient flows on to g and v.
+
+    Per group: the input is regrouped once into a zero-padded group-major buffer [G, B, T+k, C/G]; the convolution is
+    then a window GEMM (row t = the k*(C/G) contiguous elements from frame t, row pitch C/G) that writes its 48-column
+    slice of the channels-last output directly (bias, GELU, pre-activation store and the residual x in the epilogue).
+    Input gradient: the same GEMM over the padded gradient with reversed taps (residual = dy). Weight gradient: one
+    MN-major GEMM per group contracting over the flattened (utterance, frame) axis -- the zero padding between
+    utterances removes the cross terms."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups):
+        x = x.contiguous()
+        B, T, Cc = x.shape
+        G = int(groups)
+        cg = Cc // G
+        k = weight.shape[2]
+        assert weight.shape == (Cc, cg, k) and k % 2 == 0
+        half, Tp = k // 2, T + k
+        act = _resolve_act("gelu", x.dtype)
+        dev, dt = x.device, x.dtype
+        xg = torch.zeros((G, B, Tp, cg), dtype=dt, device=dev)
+        xg[:, :, half:half + T] = x.view(B, T, G, cg).permute(2, 0, 1, 3)
+        xa = _split(xg.view(G * B * Tp, cg))
+        # W_f[g][co, j*cg + ci] = W[g*cg + co, ci, j]
+        wf = _cast_pair(weight.detach().view(G, cg, cg, k).permute(0, 1, 3, 2).reshape(G * cg, k * cg))
+        y = torch.empty_like(x)
+        pre = torch.empty_like(x)
+        bias_f = bias.detach().float().contiguous()
+        for g in range(G):
+            kw = dict(M=T, N=cg, K=k * cg, a_ld=cg, b_ld=k * cg, c_ld=Cc, nb1=B, nb2=1, a_bs=(Tp * cg, 0), b_bs=(0, 0),
+                      c_bs=(T * Cc, 0))
+            _passes(_off(xa, g * B * Tp * cg), _off(wf, g * cg * k * cg), y.reshape(-1)[g * cg:], kw,
+                    dict(bias=bias_f[g * cg:], act=act, c_pre=pre.reshape(-1)[g * cg:],
+                         residual=x.reshape(-1)[g * cg:]))
+        ctx.save_for_backward(weight, pre)
+        ctx.xa = xa
+        ctx.meta = (B, T, Cc, G, cg, k, half, Tp, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        weight, pre = ctx.saved_tensors
+        B, T, Cc, G, cg, k, half, Tp, act = ctx.meta
+        dev, dt = dy.device, dy.dtype
+        dy = dy.contiguous()
+        gq = torch.empty_like(dy)
+        K.act_bwd(dy, pre, gq, act)                       # g = dy * gelu'(pre), channels-last
+        dbias = torch.zeros(Cc, dtype=torch.float32, device=dev)
+        K.colsum(gq.view(B * T, Cc), dbias, accumulate=True)
+        front = half - 1                                  # gbuf[p] = g[p - front]
+        gg = torch.zeros((G, B, Tp, cg), dtype=dt, device=dev)
+        gg[:, :, front:front + T] = gq.view(B, T, G, cg).permute(2, 0, 1, 3)
+        ga = _split(gg.view(G * B * Tp, cg))
+        # W_b[g][ci, q*cg + co] = W[g*cg + co, ci, k-1-q]
+        wb = _cast_pair(weight.detach().view(G, cg, cg, k).flip(3).permute(0, 2, 3, 1).reshape(G * cg, k * cg))
+        dx = torch.empty_like(dy)
+        dW2 = torch.empty((G, cg, k * cg), dtype=torch.float32, device=dev)
+        Kd = B * Tp - (k - 1)                             # flattened (utterance, frame) rows with a full window
+        for g in range(G):
+            kw = dict(M=T, N=cg, K=k * cg, a_ld=cg, b_ld=k * cg, c_ld=Cc, nb1=B, nb2=1, a_bs=(Tp * cg, 0), b_bs=(0, 0),
+                      c_bs=(T * Cc, 0))
+            _passes(_off(ga, g * B * Tp * cg), _off(wb, g * cg * k * cg), dx.reshape(-1)[g * cg:], kw,
+                    dict(residual=dy.reshape(-1)[g * cg:]))
+            # dW2[g][co, j*cg + ci] = sum_rho gbuf_flat[rho + front, co] * xpad_flat[rho + j, ci]
+            kw = dict(M=cg, N=k * cg, K=Kd, a_mn=True, b_mn=True, a_ld=cg, b_ld=cg, c_ld=k * cg)
+            _passes(_off(ga, (g * B * Tp + front) * cg), _off(ctx.xa, g * B * Tp * cg), dW2[g], kw)
+        dW = dW2.view(G, cg, k, cg).permute(0, 1, 3, 2).reshape(Cc, cg, k).contiguous()
+        ctx.xa = None
+        return dx, dW, dbias, None

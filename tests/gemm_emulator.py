@@ -22,7 +22,7 @@ def _gelu_grad(z):
 def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1, a_bs=(0, 0),
          b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None, act=None, alpha=1.0,
          accumulate=False, drop_p=0.0, seed=0, offset=0, actgrad_pre=None, actgrad_act=None):
-    assert nb2 == 1 and drop_p == 0.0 and bias2 is None and actgrad_pre is None and residual is None
+    assert nb2 == 1 and drop_p == 0.0 and bias2 is None and actgrad_pre is None
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a_ld = a_ld if a_ld is not None else (M if a_mn else K)
     b_ld = b_ld if b_ld is not None else (N if b_mn else K)
@@ -36,7 +36,8 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
     if accumulate:
         v = v + C.double()
     if bias is not None:
-        v = v + bias.double()
+        assert bias.dtype == torch.float32
+        v = v + bias[:N].double()
     if c_pre is not None:
         torch.as_strided(c_pre, (nb1, M, N), (c_bs[0], c_ld, 1), c_pre.storage_offset()).copy_(v.to(c_pre.dtype))
     if act in ("gelu", "gelu_tanh"):
@@ -47,6 +48,9 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         v = torch.tanh(v)
     else:
         assert act in (None, "none")
+    if residual is not None:  # same layout and dtype as C, added after the activation
+        assert residual.dtype == out.dtype
+        v = v + torch.as_strided(residual, (nb1, M, N), (c_bs[0], c_ld, 1), residual.storage_offset()).double()
     C.copy_(v.to(out.dtype))
     return out
 
@@ -63,9 +67,16 @@ def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
     dpre.copy_((dy.double() * _gelu_grad(pre.double())).to(dpre.dtype))
 
 
+def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
+    assert group_rows == 0 and ld is None
+    tot = x2d.double().sum(0)
+    out.copy_(((out.double() if accumulate else 0) + tot).to(out.dtype))
+
+
 def install(monkeypatch):
     from speecht5_b200 import kernels as K
     monkeypatch.setattr(K, "gemm", gemm)
     monkeypatch.setattr(K, "cast_bf16", cast_bf16)
     monkeypatch.setattr(K, "act_bwd", act_bwd)
+    monkeypatch.setattr(K, "colsum", colsum)
     monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)

@@ -36,3 +36,39 @@ def test_strided_conv_gelu_composition(monkeypatch, k, s, T, dtype):
     assert rel(x.grad, xr.grad) < tol
     assert rel(w.grad, wr.grad) < tol
     RT.invalidate_shadows()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T", [19, 64])
+def test_grouped_positional_conv_composition(monkeypatch, dtype, T):
+    """x + GELU(SamePad(grouped Conv1d(k even)) + bias) with a weight-normed weight: forward, dx, and the gradients
+    that flow through the torch-side weight norm to g and v (speech_encoder_prenet.py:105-119,187-192)."""
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", dtype)
+    torch.manual_seed(T)
+    B, Cc, G, k = 2, 32, 4, 8
+    x = (torch.randn(B, T, Cc) * 0.8).to(dtype).requires_grad_()
+    v = torch.nn.Parameter(torch.randn(Cc, Cc // G, k) * 0.2)
+    gpar = torch.nn.Parameter(v.detach().norm(dim=(0, 1), keepdim=True) * 1.1)
+    bias = torch.nn.Parameter(torch.randn(Cc) * 0.1)
+    w = gpar * v / v.norm(dim=(0, 1), keepdim=True)
+    y = frontend.GroupedPosConvFn.apply(x, w, bias, G)
+    dy = torch.randn(y.shape).to(dtype)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_()
+    vr, gr, br = (t.detach().double().requires_grad_() for t in (v, gpar, bias))
+    wr = gr * vr / vr.norm(dim=(0, 1), keepdim=True)
+    pos = F.conv1d(xr.transpose(1, 2), wr, br, padding=k // 2, groups=G)[:, :, :-1]
+    yr = xr + F.gelu(pos).transpose(1, 2)
+    yr.backward(dy.double())
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+    tol = 3e-5 if dtype == torch.float32 else 2e-2
+    assert rel(y, yr) < tol
+    assert rel(x.grad, xr.grad) < tol
+    assert rel(v.grad, vr.grad) < tol
+    assert rel(gpar.grad, gr.grad) < tol
+    assert rel(bias.grad, br.grad) < tol
