@@ -268,3 +268,112 @@ class GroupedPosConvFn(torch.autograd.Function):
         dW = dW2.view(G, cg, k, cg).permute(0, 1, 3, 2).reshape(Cc, cg, k).contiguous()
         ctx.xa = None
         return dx, dW, dbias, None
+
+
+# ------------------------------------------------------------------------------------------------ speech encoder prenet
+def downsample_padding_mask(padding_mask, n_frames):
+    """speech_encoder_prenet.py:219-229: a frame is padding iff ALL the samples it was cut from are (the samples that
+    do not fill a whole frame are dropped first)."""
+    extra = padding_mask.size(1) % n_frames
+    if extra > 0:
+        padding_mask = padding_mask[:, :-extra]
+    return padding_mask.view(padding_mask.size(0), n_frames, -1).all(-1)
+
+
+def padding_mask_positions(frame_padding_mask, padding_idx=1):
+    """The reference feeds the BOOLEAN frame mask to the sinusoidal embedding as if it were tokens
+    (speech_encoder_prenet.py:196-198 -> fairseq/utils.py:247-257 make_positions): padded frames (True == padding_idx 1)
+    stay at padding_idx (the zero row), real frames count up from padding_idx + 1."""
+    keep = (~frame_padding_mask).long()
+    return torch.cumsum(keep, dim=1) * keep + padding_idx
+
+
+class _WeightNormConv(torch.nn.Module):
+    """Holds the parameters of nn.utils.weight_norm(Conv1d(d, d, k, groups), dim=2) under the reference's checkpoint
+    names (`weight_g` [1, 1, k], `weight_v` [d, d/groups, k], `bias`)."""
+
+    def __init__(self, d, k, groups):
+        super().__init__()
+        import math
+        v = torch.empty(d, d // groups, k).normal_(0.0, math.sqrt(4.0 / (k * d)))
+        self.weight_g = torch.nn.Parameter(v.norm(dim=(0, 1), keepdim=True))
+        self.weight_v = torch.nn.Parameter(v)
+        self.bias = torch.nn.Parameter(torch.zeros(d))
+        self.groups = groups
+
+    def weight(self):
+        v = self.weight_v
+        return self.weight_g * v / v.norm(dim=(0, 1), keepdim=True)
+
+
+class SpeechEncoderPrenet(torch.nn.Module):
+    """speech_encoder_prenet.py:57-275 for the built configuration (encoder_speech_prenet "conv", extractor_mode
+    "default", use_conv_pos and use_sinc_pos as in the Base arch): waveform -> [B, T, d], frame padding mask and the
+    mean-square feature penalty. The HuBERT-style mask draw stays on the host (speecht5_b200.data.compute_mask_indices,
+    numpy, like the reference :236-262); its result is applied here. EXPERIMENTAL (see module docstring)."""
+
+    def __init__(self, args):
+        super().__init__()
+        from .models.modules.nets import fairseq_sinusoid_table  # noqa: F401  (table builder shared with the text prenet)
+        layers = eval(args.conv_feature_layers) if isinstance(args.conv_feature_layers, str) else list(
+            args.conv_feature_layers)
+        if getattr(args, "encoder_speech_prenet", "conv") != "conv" or getattr(args, "use_abs_pos", False):
+            raise NotImplementedError("only the conv speech prenet with conv + sinusoidal positions is built")
+        self.embed = layers[-1][0]
+        d = args.encoder_embed_dim
+        self.feature_extractor = ConvFeatureExtractor(layers, args.extractor_mode, args.conv_bias)
+        self.post_extract_proj = torch.nn.Linear(self.embed, d) if self.embed != d else None
+        self.feature_grad_mult = args.feature_grad_mult
+        self.dropout_p = args.dropout
+        self.use_conv_pos, self.use_sinc_pos = args.use_conv_pos, args.use_sinc_pos
+        self.padding_idx = 1
+        if self.use_conv_pos:
+            self.layer_norm = torch.nn.LayerNorm(self.embed)
+            self.pos_conv = torch.nn.Sequential(_WeightNormConv(d, args.conv_pos, args.conv_pos_groups))
+        self.mask_emb = torch.nn.Parameter(torch.empty(d).uniform_())
+        self.mask_prob, self.mask_length = args.mask_prob, args.hubert_mask_length
+        self.mask_selection, self.mask_other = args.mask_selection, args.mask_other
+        self.no_mask_overlap, self.mask_min_space = args.no_mask_overlap, args.mask_min_space
+        self._pe = None
+        self.embed_dim = d
+
+    def _positions(self, frame_mask, B, T, device):
+        if self._pe is None or self._pe.shape[0] < self.padding_idx + 1 + T or self._pe.device != device:
+            from .models.modules.nets import fairseq_sinusoid_table
+            self._pe = fairseq_sinusoid_table(self.padding_idx + 1 + max(T, 4000), self.embed_dim, self.padding_idx,
+                                              device)
+        pm = frame_mask if frame_mask is not None else torch.zeros((B, T), dtype=torch.bool, device=device)
+        return self._pe.index_select(0, padding_mask_positions(pm, self.padding_idx).view(-1)).view(B, T, -1)
+
+    def forward(self, source, padding_mask=None, mask=True, mask_indices=None):
+        from . import ops
+        if self.feature_grad_mult > 0:
+            x = self.feature_extractor(source)
+            if self.feature_grad_mult != 1.0:  # GradMultiply (:156-160): identity forward, scaled gradient
+                x = x * self.feature_grad_mult + x.detach() * (1.0 - self.feature_grad_mult)
+        else:
+            with torch.no_grad():
+                x = self.feature_extractor(source)
+        features_pen = x.float().pow(2).mean()
+        B, T, _ = x.shape
+        x = ops.residual_layer_norm(x, None, self.layer_norm)
+        frame_mask = downsample_padding_mask(padding_mask, T) if padding_mask is not None else None
+        drop = self.dropout_p if self.training else 0.0
+        if self.post_extract_proj is not None:
+            x = ops.linear(x, self.post_extract_proj.weight, self.post_extract_proj.bias, drop_p=drop)
+        else:
+            x = ops.dropout(x, drop, self.training)
+        if mask and mask_indices is None and self.training and self.mask_prob > 0:
+            from .data import compute_mask_indices
+            mask_indices = torch.from_numpy(compute_mask_indices(
+                (B, T), frame_mask.cpu() if frame_mask is not None else None, self.mask_prob, self.mask_length,
+                self.mask_selection, self.mask_other, min_masks=2, no_overlap=self.no_mask_overlap,
+                min_space=self.mask_min_space)).to(x.device)
+        if mask_indices is not None:
+            x = torch.where(mask_indices.unsqueeze(-1), self.mask_emb.to(x.dtype), x)
+        if self.use_conv_pos:
+            wn = self.pos_conv[0]
+            x = GroupedPosConvFn.apply(x, wn.weight(), wn.bias, wn.groups)
+        if self.use_sinc_pos:
+            x = x + self._positions(frame_mask, B, T, x.device).to(x.dtype)
+        return x, frame_mask, features_pen

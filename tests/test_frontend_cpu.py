@@ -72,3 +72,46 @@ def test_grouped_positional_conv_composition(monkeypatch, dtype, T):
     assert rel(v.grad, vr.grad) < tol
     assert rel(gpar.grad, gr.grad) < tol
     assert rel(bias.grad, br.grad) < tol
+
+
+def test_padding_mask_downsampling_and_positions_match_the_oracle():
+    """Host logic of the speech prenet: frame mask = all-samples-padded after trimming the remainder
+    (speech_encoder_prenet.py:219-229) and the positions the reference derives from the BOOLEAN mask (:196-198)."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.models.modules.nets import fairseq_sinusoid_table
+    torch.manual_seed(0)
+    B, n, T = 3, 3217, 10
+    lengths = torch.tensor([3217, 2000, 655])
+    pm = torch.arange(n)[None, :] >= lengths[:, None]
+    args = O.base_asr_args(encoder_layers=1, decoder_layers=1)
+    want = O.SpeechEncoderPrenet(args).forward_padding_mask(torch.zeros(B, T, 4), pm)
+    got = frontend.downsample_padding_mask(pm, T)
+    assert torch.equal(got, want) and got.any() and not got.all()
+    emb = O.SinusoidalPositionalEmbedding(16, 1)(got)
+    table = fairseq_sinusoid_table(2 + T, 16, 1, "cpu")
+    mine = table.index_select(0, frontend.padding_mask_positions(got, 1).view(-1)).view(B, T, -1)
+    assert torch.allclose(mine, emb.float(), atol=1e-6)
+    assert (mine[got] == 0).all()
+
+
+def test_speech_prenet_state_dict_uses_the_reference_names():
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    args = O.base_asr_args(encoder_layers=1, decoder_layers=1)
+    for k, v in dict(conv_feature_layers="[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2", encoder_speech_prenet="conv",
+                     mask_prob=0.65, hubert_mask_length=10, mask_selection="static", mask_other=0.0,
+                     no_mask_overlap=False, mask_min_space=1).items():
+        if not hasattr(args, k) or k == "conv_feature_layers":
+            setattr(args, k, v)
+    m = frontend.SpeechEncoderPrenet(args)
+    keys = set(m.state_dict().keys())
+    for name in ("feature_extractor.conv_layers.0.0.weight", "feature_extractor.conv_layers.0.2.weight",
+                 "feature_extractor.conv_layers.0.2.bias", "feature_extractor.conv_layers.6.0.weight",
+                 "post_extract_proj.weight", "post_extract_proj.bias", "layer_norm.weight", "layer_norm.bias",
+                 "pos_conv.0.bias", "pos_conv.0.weight_g", "pos_conv.0.weight_v", "mask_emb"):
+        assert name in keys, name
+    assert m.state_dict()["pos_conv.0.weight_g"].shape == (1, 1, args.conv_pos)
+    assert m.state_dict()["pos_conv.0.weight_v"].shape == (768, 768 // args.conv_pos_groups, args.conv_pos)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4000))  # CPU tensors: the product path refuses instead of falling back
