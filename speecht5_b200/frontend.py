@@ -319,6 +319,8 @@ class SpeechEncoderPrenet(torch.nn.Module):
             args.conv_feature_layers)
         if getattr(args, "encoder_speech_prenet", "conv") != "conv" or getattr(args, "use_abs_pos", False):
             raise NotImplementedError("only the conv speech prenet with conv + sinusoidal positions is built")
+        if not args.use_conv_pos:  # the reference's forward needs the LayerNorm it only builds under use_conv_pos (:102-104,174)
+            raise NotImplementedError("--use-conv-pos is required (as in every speech-input recipe)")
         self.embed = layers[-1][0]
         d = args.encoder_embed_dim
         self.feature_extractor = ConvFeatureExtractor(layers, args.extractor_mode, args.conv_bias)
@@ -336,6 +338,10 @@ class SpeechEncoderPrenet(torch.nn.Module):
         self.no_mask_overlap, self.mask_min_space = args.no_mask_overlap, args.mask_min_space
         self._pe = None
         self.embed_dim = d
+        self.freeze_encoder_updates = getattr(args, "freeze_encoder_updates", 0)
+        self.num_updates = 0
+        if getattr(args, "mask_channel_prob", 0.0) > 0:
+            raise NotImplementedError("channel masking (mask_channel_prob > 0) is not built (0 in every SpeechT5 recipe)")
 
     def _positions(self, frame_mask, B, T, device):
         if self._pe is None or self._pe.shape[0] < self.padding_idx + 1 + T or self._pe.device != device:
@@ -345,7 +351,22 @@ class SpeechEncoderPrenet(torch.nn.Module):
         pm = frame_mask if frame_mask is not None else torch.zeros((B, T), dtype=torch.bool, device=device)
         return self._pe.index_select(0, padding_mask_positions(pm, self.padding_idx).view(-1)).view(B, T, -1)
 
-    def forward(self, source, padding_mask=None, mask=True, mask_indices=None):
+    def set_num_updates(self, num_updates):
+        self.num_updates = num_updates
+
+    def forward(self, src_tokens, require_feat_pen=False, target_list=None, padding_mask=None, mask=True,
+                mask_indices=None):
+        """Reference signature and returns (speech_encoder_prenet.py:151-204): `(x, frame_padding_mask)`, or with
+        require_feat_pen `((x, features_pen, mask_indices, target_list), frame_padding_mask)`. `mask_indices` (extra,
+        optional) injects a precomputed mask draw instead of sampling one."""
+        import contextlib
+        if target_list is not None:
+            raise NotImplementedError("pre-training targets (forward_targets, SURVEY 8a row 22) are a later row")
+        ft = self.freeze_encoder_updates <= self.num_updates
+        with torch.no_grad() if not ft else contextlib.ExitStack():
+            return self._forward(src_tokens, require_feat_pen, padding_mask, mask, mask_indices)
+
+    def _forward(self, source, require_feat_pen, padding_mask, mask, mask_indices):
         from . import ops
         if self.feature_grad_mult > 0:
             x = self.feature_extractor(source)
@@ -363,7 +384,7 @@ class SpeechEncoderPrenet(torch.nn.Module):
             x = ops.linear(x, self.post_extract_proj.weight, self.post_extract_proj.bias, drop_p=drop)
         else:
             x = ops.dropout(x, drop, self.training)
-        if mask and mask_indices is None and self.training and self.mask_prob > 0:
+        if mask and mask_indices is None and self.mask_prob > 0:  # apply_hubert_mask (:234-272): host draw, numpy
             from .data import compute_mask_indices
             mask_indices = torch.from_numpy(compute_mask_indices(
                 (B, T), frame_mask.cpu() if frame_mask is not None else None, self.mask_prob, self.mask_length,
@@ -376,4 +397,6 @@ class SpeechEncoderPrenet(torch.nn.Module):
             x = GroupedPosConvFn.apply(x, wn.weight(), wn.bias, wn.groups)
         if self.use_sinc_pos:
             x = x + self._positions(frame_mask, B, T, x.device).to(x.dtype)
-        return x, frame_mask, features_pen
+        if require_feat_pen:
+            return (x, features_pen, mask_indices, None), frame_mask
+        return x, frame_mask

@@ -142,6 +142,7 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         ("--unb-enc-layer", dict(type=int, default=-1)),
         # this implementation only: construct the text decoder pre/post-net (the reference always does)
         ("--build-text-decoder", dict(action="store_true")),
+        ("--build-speech-encoder", dict(action="store_true")),
     )
 
     @classmethod
@@ -179,8 +180,13 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if getattr(args, "build_text_decoder", False):
             text_decoder_prenet = TextDecoderPrenet(text_decoder_embed_tokens, args)
             text_decoder_postnet = TextDecoderPostnet(text_decoder_embed_tokens, len(text_dict), args)
-        return cls(args, encoder, decoder, text_encoder_prenet, None, text_decoder_prenet, speech_decoder_prenet,
-                   text_decoder_postnet, speech_decoder_postnet, None, None)
+        # waveform front end: opt-in (--build-speech-encoder), EXPERIMENTAL -- see frontend.py
+        speech_encoder_prenet = None
+        if getattr(args, "build_speech_encoder", False):
+            from ..frontend import SpeechEncoderPrenet
+            speech_encoder_prenet = SpeechEncoderPrenet(args)
+        return cls(args, encoder, decoder, text_encoder_prenet, speech_encoder_prenet, text_decoder_prenet,
+                   speech_decoder_prenet, text_decoder_postnet, speech_decoder_postnet, None, None)
 
     # ------------------------------------------------------------------ forward (models/speecht5.py:786-963)
     def forward(self, source=None, src_tokens=None, src_lengths=None, prev_output_tokens=None, tgt_lengths=None,
@@ -189,27 +195,42 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         assert source is not None or src_tokens is not None
         input_type = "text" if (source is None and padding_mask is None and not feature_only) else "speech"
         output_type = "text" if (prev_output_tokens is not None and prev_output_tokens.dim() == 2) else "speech"
-        t2t = input_type == "text" and output_type == "text" and self.text_decoder_prenet is not None
-        if (input_type != "text" or output_type != "speech" or target_list is not None) and not (
-                t2t and target_list is None):
+        text_out = output_type == "text" and self.text_decoder_prenet is not None
+        t2t = input_type == "text" and text_out
+        speech_in = input_type == "speech" and self.speech_encoder_prenet is not None and not feature_only
+        built = (input_type == "text" and output_type == "speech") or t2t or (
+            speech_in and (text_out or output_type == "speech" or prev_output_tokens is None))
+        if not built or target_list is not None or only_hubert:
             raise NotImplementedError(
                 f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built yet in the "
-                "B200 path; round 1 covers text->speech (t2s)")
-        encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
+                "B200 path; round 1 covers text->speech (t2s), opt-in: text output and speech input")
+        if speech_in:  # (:815-820) waveform -> frames; the HuBERT-style mask is drawn only in training
+            encoder_input, encoder_padding_mask = self.speech_encoder_prenet(source, padding_mask=padding_mask,
+                                                                             mask=self.training)
+        else:
+            encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
         encoder_output = self.encoder(encoder_input, encoder_padding_mask, tgt_layer=tgt_enc_layer)
         if "decoder_input" in encoder_output and encoder_output["decoder_input"][0] is not None:
             encoder_output["encoder_out"] = encoder_output["decoder_input"]
             encoder_output["_encoder_out_btc"] = encoder_output["decoder_input"][0].transpose(0, 1)
+        if speech_in and task_name == "s2t":  # (:885-888)
+            if only_ctc:
+                return None, encoder_output
+            if not self.training and prev_output_tokens is None:
+                return encoder_output
         hook = getattr(self, "_encoder_grad_hook", None)  # set by B200Trainer: gradient-exchange overlap point
         if hook is not None and encoder_output["encoder_out"][0].requires_grad:
             encoder_output["encoder_out"][0].register_hook(hook)
-        if t2t:  # text in / text out (:901-903, 955-957): decoder on token embeddings, vocabulary logits
+        if text_out:  # (:901-903, 955-957): decoder on token embeddings, vocabulary logits
             dec_in, tgt_mask, _ = self.text_decoder_prenet(prev_output_tokens)
             decoder_output, extra = self.decoder(
                 dec_in, tgt_mask, encoder_output,
                 full_context_alignment=getattr(self.args, "decoder_full_context_alignment", False),
                 alignment_layer=None)
-            return (self.text_decoder_postnet(decoder_output), None), {}, encoder_output
+            logits = self.text_decoder_postnet(decoder_output)
+            if task_name == "s2t":  # (:955-956)
+                return (logits, None), encoder_output
+            return (logits, None), {}, encoder_output
         prev_output_tokens, tgt_mask = self.speech_decoder_prenet(prev_output_tokens, tgt_lengths, spkembs)
         decoder_output, extra = self.decoder(
             prev_output_tokens, tgt_mask, encoder_output,
@@ -271,6 +292,10 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         return extra_losses, names
 
     def forward_encoder(self, source, padding_mask=None):
+        if getattr(self, "speech_encoder_prenet", None) is not None:  # (:1133-1140)
+            encoder_input, encoder_padding_mask = self.speech_encoder_prenet(source, padding_mask=padding_mask,
+                                                                             mask=False)
+            return self.encoder(encoder_input, encoder_padding_mask)
         raise NotImplementedError("speech input (conv feature extractor + speech encoder prenet) is a 'next' row: "
                                   "SURVEY.md section 8a rows 2-3; use forward_text_encoder for text input")
 
@@ -383,6 +408,21 @@ def base_architecture(args):  # models/speecht5.py:1252-1383 (fields used by the
     g("decoder_max_relative_position", 160)
     g("feature_grad_mult", 0.1)
     g("mask_prob", 0.0)
+    # waveform front end (:1337-1368), read only by the opt-in speech encoder prenet
+    g("conv_pos", 128)
+    g("conv_pos_groups", 16)
+    g("extractor_mode", "default")
+    g("conv_feature_layers", "[(512,10,5)] + [(512,3,2)] * 4 + [(512,2,2)] * 2")
+    g("conv_bias", False)
+    g("hubert_mask_length", 10)
+    g("mask_selection", "static")
+    g("mask_other", 0)
+    g("no_mask_overlap", False)
+    g("mask_min_space", 1)
+    g("mask_channel_prob", 0.0)
+    g("use_conv_pos", False)
+    g("use_sinc_pos", False)
+    g("encoder_speech_prenet", "conv")
 
 
 @register_model_architecture("t5_transformer", "t5_transformer_base")

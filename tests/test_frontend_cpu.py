@@ -101,7 +101,7 @@ def test_speech_prenet_state_dict_uses_the_reference_names():
     args = O.base_asr_args(encoder_layers=1, decoder_layers=1)
     for k, v in dict(conv_feature_layers="[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2", encoder_speech_prenet="conv",
                      mask_prob=0.65, hubert_mask_length=10, mask_selection="static", mask_other=0.0,
-                     no_mask_overlap=False, mask_min_space=1).items():
+                     no_mask_overlap=False, mask_min_space=1, mask_channel_prob=0.0, freeze_encoder_updates=0).items():
         if not hasattr(args, k) or k == "conv_feature_layers":
             setattr(args, k, v)
     m = frontend.SpeechEncoderPrenet(args)

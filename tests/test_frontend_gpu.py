@@ -77,7 +77,8 @@ def test_speech_encoder_prenet_against_the_oracle(cuda, dtype):
     mi[0, 3:9] = True
     mi[1, 1:4] = True
     xr, mr, pen_r = ref(wave, pm, mask_indices=mi)
-    x, m, pen = mine(wave.float().to(cuda), pm.to(cuda), mask_indices=mi.to(cuda))
+    (x, pen, _, _), m = mine(wave.float().to(cuda), require_feat_pen=True, padding_mask=pm.to(cuda), mask=True,
+                             mask_indices=mi.to(cuda))
     tol = 1e-4 if dtype == torch.float32 else 3e-2
     assert torch.equal(m.cpu(), mr)
     assert rel(x.cpu(), xr) < tol
