@@ -1,2 +1,3 @@
 from .speecht5_criterion import SpeechT5Criterion, SpeechT5CriterionConfig  # noqa: F401
 from .text_to_speech_loss import TexttoSpeechLoss  # noqa: F401
+from .speech_to_text_loss import SpeechtoTextLoss  # noqa: F401

@@ -4,6 +4,7 @@ guided_attn_loss_lambda, so the effective guided-attention weight is 1.0 (speech
 from dataclasses import dataclass, field
 
 from ..fairseq_shim import FairseqCriterion, register_criterion
+from .speech_to_text_loss import SpeechtoTextLoss
 from .text_to_speech_loss import TexttoSpeechLoss
 
 
@@ -44,16 +45,22 @@ class SpeechT5CriterionConfig:
 class SpeechT5Criterion(FairseqCriterion):
     def __init__(self, task, sentence_avg=True, use_masking=True, loss_type="L1", bce_pos_weight=5.0,
                  bce_loss_lambda=1.0, use_guided_attn_loss=False, guided_attn_loss_sigma=0.4,
-                 num_heads_applied_guided_attn=2, **unused):
+                 num_heads_applied_guided_attn=2, label_smoothing=0.0, ignore_prefix_size=0, report_accuracy=False,
+                 ce_weight=1.0, ctc_weight=0.0, zero_infinity=False, post_process="sentencepiece", **unused):
         super().__init__(task)
         self.text_to_speech_loss = TexttoSpeechLoss(
             task, sentence_avg, use_masking, False, loss_type, bce_pos_weight, bce_loss_lambda, use_guided_attn_loss,
             guided_attn_loss_sigma, 1.0, 2, num_heads_applied_guided_attn)
+        # s2t branch (speecht5_criterion.py:72-81); meaningful only with the opt-in speech-input / text-output model
+        self.speech_to_text_loss = SpeechtoTextLoss(task, sentence_avg, label_smoothing, ignore_prefix_size,
+                                                    report_accuracy, ce_weight, ctc_weight, zero_infinity, post_process)
 
     def forward(self, model, sample, reduce=True):
         task_name = sample["task_name"]
         if task_name in ("t2s", "s2s"):
             return self.text_to_speech_loss(model, sample)
+        if task_name == "s2t":
+            return self.speech_to_text_loss(model, sample, reduce)
         raise NotImplementedError(f"criterion branch '{task_name}' is not built yet in the B200 path (round 1: t2s)")
 
     @staticmethod

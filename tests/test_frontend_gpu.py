@@ -84,3 +84,50 @@ def test_speech_encoder_prenet_against_the_oracle(cuda, dtype):
     assert rel(x.cpu(), xr) < tol
     assert abs(pen.item() - pen_r.item()) / pen_r.item() < tol
     RT.dtype = torch.bfloat16
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_speech_to_text_step_against_the_oracle(cuda, dtype):
+    """Opt-in s2t branch end to end (waveform front end -> encoder + CTC head -> text decoder): logits, CE + CTC loss
+    and a few gradients vs oracle T5TransformerModelASROracle / asr_loss (SURVEY 8d config 3 shapes, reduced)."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = dtype
+    RT.manual_seed(1)
+    RT.invalidate_shadows()
+    torch.manual_seed(4)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, dropout=0.0, attention_dropout=0.0,
+                activation_dropout=0.0, encoder_layerdrop=0.0, decoder_layerdrop=0.0, mask_prob=0.0,
+                feature_grad_mult=1.0)
+    oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).train()
+    args = make_args("t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
+                     use_sinc_pos=True, **over)
+    model = T5TransformerModel.build_model(args).to(cuda).train()
+    sd = dict(oracle.state_dict())
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd["speech_encoder_prenet." + b] = sd.pop("speech_encoder_prenet." + a)
+    model.load_state_dict(sd)
+    s = O.synthetic_asr_batch(2, 16000, 12, seed=3)
+    want, ce, ctc, _ = O.asr_loss(oracle, s, ce_weight=0.5, ctc_weight=0.5, label_smoothing=0.1)
+    want.backward()
+    sample = {"net_input": {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in s["net_input"].items()},
+              "target": s["target"].to(cuda), "target_lengths": s["target_lengths"].to(cuda), "ntokens": s["ntokens"],
+              "task_name": "s2t"}
+    crit = SpeechT5Criterion(None, label_smoothing=0.1, ce_weight=0.5, ctc_weight=0.5)
+    loss, _, log = crit(model, sample)
+    tol = 1e-3 if dtype == torch.float32 else 6e-2
+    assert abs(loss.item() - want.item()) / abs(want.item()) < tol, (loss.item(), want.item(), log)
+    loss.backward()
+    ref, got = dict(oracle.named_parameters()), dict(model.named_parameters())
+    gtol = 1e-2 if dtype == torch.float32 else 0.3
+    for name in ("speech_encoder_prenet.feature_extractor.conv_layers.3.0.weight",
+                 "speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight",
+                 "speech_encoder_prenet.post_extract_proj.weight", "encoder.layers.1.fc1.weight",
+                 "decoder.layers.0.encoder_attn.q_proj.weight", "encoder.proj.weight"):
+        assert rel(got[name].grad.cpu(), ref[name].grad) < gtol, name
+    wg = got["speech_encoder_prenet.pos_conv.0.weight_v"].grad.cpu()
+    assert rel(wg, ref["speech_encoder_prenet.pos_conv_v"].grad) < gtol
+    RT.dtype = torch.bfloat16

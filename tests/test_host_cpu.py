@@ -230,3 +230,77 @@ def test_collate_asr_follows_the_reference_collater():
     assert b["target"].tolist() == [[7, 8, 9, 2], [5, 2, 1, 1]]
     assert b["net_input"]["prev_output_tokens"].tolist() == [[2, 7, 8, 9], [2, 5, 1, 1]]
     assert b["target_lengths"].tolist() == [4, 2] and b["ntokens"] == 4 and b["task_name"] == "s2t"
+
+
+def test_speech_to_text_criterion_matches_the_oracle_loss():
+    """criterions/speech_to_text_loss.py restated (label-smoothed CE + CTC with target_lengths - 1, the unscaled
+    single-term case, logging keys, greedy-CTC unit errors at eval) against oracle asr_loss on a stub model."""
+    import torch.nn.functional as F
+    from oracle.speecht5_oracle_asr import asr_loss, synthetic_asr_batch
+    from speecht5_b200.criterions import SpeechT5Criterion, SpeechtoTextLoss
+    torch.manual_seed(2)
+    B, Td, Te, V = 3, 9, 40, 81
+    s = synthetic_asr_batch(B, 4000, Td, seed=5)
+    s["task_name"] = "s2t"
+    dec_logits = torch.randn(B, Td, V, requires_grad=True)
+    ctc_logits = torch.randn(Te, B, V, requires_grad=True)
+    pm = torch.zeros(B, Te, dtype=torch.bool)
+    pm[1, 30:] = True
+
+    class Stub(torch.nn.Module):
+        def forward(self, **kw):
+            assert kw["task_name"] == "s2t" and "only_ctc" not in kw
+            return (dec_logits, None), {"encoder_out_for_ctc": [ctc_logits], "encoder_padding_mask": [pm]}
+
+        def get_normalized_probs(self, net_output, log_probs, sample=None):
+            out = F.log_softmax(net_output[0].float(), dim=-1)
+            out.batch_first = True
+            return out
+
+        def get_normalized_probs_for_ctc(self, net_output, log_probs):
+            return F.log_softmax(net_output["encoder_out_for_ctc"][0].float(), dim=-1)
+
+        def get_targets(self, sample, net_output):
+            return sample["target"]
+
+    m = Stub().train()
+    want, ce, ctc, ss = asr_loss(m, s, ce_weight=0.5, ctc_weight=0.5, label_smoothing=0.1)
+    crit = SpeechT5Criterion(None, label_smoothing=0.1, ce_weight=0.5, ctc_weight=0.5, report_accuracy=True)
+    loss, sample_size, log = crit(m, s)
+    assert sample_size == ss == B and abs(loss.item() - want.item()) < 1e-4 * abs(want.item())
+    assert abs(log["ce_loss"] - ce.item()) < 1e-3 and abs(log["ctc_loss"] - ctc.item()) < 1e-3
+    assert set(log) >= {"loss", "ce_loss", "ctc_loss", "nll_loss", "ntokens", "nsentences", "sample_size", "n_correct",
+                        "total"} and log["total"] == int(s["target"].ne(1).sum())
+    loss.backward()
+    assert dec_logits.grad.abs().sum() > 0 and ctc_logits.grad.abs().sum() > 0
+    # one term only: NOT multiplied by its weight (speech_to_text_loss.py:202-205); eval adds the unit error counts
+    only = SpeechtoTextLoss(None, label_smoothing=0.1, ce_weight=0.0, ctc_weight=0.3)
+    l2, _, log2 = only(m.eval(), s)
+    assert abs(l2.item() - ctc.item()) < 1e-3 and s.get("only_ctc") is True
+    assert log2["c_total"] == int(((s["target"] != 1) & (s["target"] != 2)).sum()) and 0 < log2["c_errors"]
+    from speecht5_b200.criterions.speech_to_text_loss import _edit_distance
+    assert _edit_distance([1, 2, 3, 4], [1, 3, 4, 5]) == 2 and _edit_distance([], [1, 2]) == 2
+
+
+def test_model_builds_the_opt_in_speech_input_branch():
+    """--build-speech-encoder / --build-text-decoder construct the waveform front end under the reference's parameter
+    names, and the s2t dispatch reaches it (CPU tensors are refused by the kernels, not by a missing branch)."""
+    import pytest
+    from speecht5_b200.models import T5TransformerModel, make_args
+    args = make_args("t5_transformer_base_asr", encoder_layers=1, decoder_layers=1, build_speech_encoder=True,
+                     build_text_decoder=True, use_conv_pos=True, use_sinc_pos=True)
+    model = T5TransformerModel.build_model(args)
+    keys = set(model.state_dict())
+    for k in ("speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight",
+              "speech_encoder_prenet.pos_conv.0.weight_g", "speech_encoder_prenet.mask_emb",
+              "speech_encoder_prenet.post_extract_proj.weight", "text_decoder_prenet.embed_tokens.weight",
+              "encoder.proj.weight"):
+        assert k in keys, k
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(source=torch.zeros(1, 4000), padding_mask=torch.zeros(1, 4000, dtype=torch.bool),
+              prev_output_tokens=torch.full((1, 3), 2), task_name="s2t")
+    plain = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", encoder_layers=1, decoder_layers=1))
+    assert plain.speech_encoder_prenet is None
+    with pytest.raises(NotImplementedError):
+        plain(source=torch.zeros(1, 4000), padding_mask=torch.zeros(1, 4000, dtype=torch.bool),
+              prev_output_tokens=torch.full((1, 3), 2), task_name="s2t")
