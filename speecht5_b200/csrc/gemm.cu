@@ -693,7 +693,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
     const char* e = getenv("ST5_GEMM_BN");
     return e ? atoi(e) : 0;
   }();
-  // ST5_GEMM_PAIR=1 (experimental, off by default until measured on the GPU): 256 x 256 tiles on CTA pairs for every
+  // ST5_GEMM_PAIR=1|2 (experimental, off by default until measured on the GPU; 2 = 5-stage ring): 256 x 256 tiles on CTA pairs for every
   // problem the 256-wide tile would have been chosen for and that has at least one full pair of row blocks.
   static const int pair_mode = [] {
     const char* e = getenv("ST5_GEMM_PAIR");
@@ -706,6 +706,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   const double c128 = g.N > 64 ? cost(128, 1.12) : 1e30;
   const double c64 = cost(64, 1.35);
   if (c256 <= c128 && c256 <= c64) {
+    if (pair_mode == 2 && g.M > BLOCK_M) return launch_major<256, 5, 2>(g, ep, stream);  // deeper ring (tuning)
     if (pair_mode && g.M > BLOCK_M) return launch_major<256, 4, 2>(g, ep, stream);
     return launch_major<256, 3>(g, ep, stream);
   }
