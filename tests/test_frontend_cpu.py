@@ -115,3 +115,26 @@ def test_speech_prenet_state_dict_uses_the_reference_names():
     assert m.state_dict()["pos_conv.0.weight_v"].shape == (768, 768 // args.conv_pos_groups, args.conv_pos)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 4000))  # CPU tensors: the product path refuses instead of falling back
+
+
+def test_logmel_device_composition_matches_the_oracle(monkeypatch):
+    """speecht5_b200/audio.py through the GEMM emulator: overlapping-frame STFT GEMM (row pitch = hop), magnitude, mel
+    GEMM, log10 -- against oracle.audio_oracle.logmelfilterbank (librosa semantics), batched, n not a multiple of hop."""
+    import numpy as np
+    from oracle.audio_oracle import logmelfilterbank as ref_fn, mel_basis
+    from speecht5_b200 import audio
+    gemm_emulator.install(monkeypatch)
+    audio._CONST.clear()
+    assert np.allclose(audio.slaney_mel_basis(16000, 1024, 80, 80, 7600).numpy(), mel_basis(), atol=1e-7)
+    rng = np.random.default_rng(3)
+    n = 5000
+    t = np.arange(n) / 16000.0
+    waves = np.stack([0.3 * np.sin(2 * np.pi * 300 * t) + 0.02 * rng.standard_normal(n),
+                      0.1 * np.sin(2 * np.pi * 2500 * t) + 0.05 * rng.standard_normal(n)]).astype(np.float32)
+    got = audio.logmelfilterbank(torch.from_numpy(waves)).numpy()
+    want = np.stack([ref_fn(w) for w in waves])
+    assert got.shape == want.shape == (2, 1 + n // 256, 80)
+    assert np.abs(got - want).max() < 1e-3, np.abs(got - want).max()
+    one = audio.logmelfilterbank(torch.from_numpy(waves[0])).numpy()
+    assert np.abs(one - want[0]).max() < 1e-3
+    audio._CONST.clear()

@@ -131,3 +131,19 @@ def test_speech_to_text_step_against_the_oracle(cuda, dtype):
     wg = got["speech_encoder_prenet.pos_conv.0.weight_v"].grad.cpu()
     assert rel(wg, ref["speech_encoder_prenet.pos_conv_v"].grad) < gtol
     RT.dtype = torch.bfloat16
+
+
+def test_logmel_on_device_against_the_oracle(cuda):
+    """speecht5_b200/audio.py (STFT and mel projection on the tcgen05 GEMM, split precision) vs oracle/audio_oracle.py."""
+    import numpy as np
+    from oracle.audio_oracle import logmelfilterbank as ref_fn
+    from speecht5_b200 import audio
+    rng = np.random.default_rng(3)
+    n = 16000 * 2 + 77
+    t = np.arange(n) / 16000.0
+    waves = np.stack([0.3 * np.sin(2 * np.pi * 300 * t) + 0.02 * rng.standard_normal(n),
+                      0.1 * np.sin(2 * np.pi * 2500 * t) + 0.05 * rng.standard_normal(n)]).astype(np.float32)
+    got = audio.logmelfilterbank(torch.from_numpy(waves).to(cuda)).cpu().numpy()
+    want = np.stack([ref_fn(w) for w in waves])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
