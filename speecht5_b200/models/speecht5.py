@@ -300,8 +300,57 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
                                   "SURVEY.md section 8a rows 2-3; use forward_text_encoder for text input")
 
     def forward_decoder(self, tokens, encoder_out, incremental_state):
-        raise NotImplementedError("text decoding (text decoder pre/post-net, incremental state) is a 'next' row: "
-                                  "SURVEY.md section 8a rows 9, 14, 21")
+        """(:1151-1164) vocabulary logits of the text decoder. With an incremental state the reference feeds only the
+        last token and returns [B, 1, V]; here the decoder is re-run on the whole prefix (causal self-attention makes
+        the last row identical) and the last position is returned -- the KV cache is the SURVEY 8f follow-up."""
+        if getattr(self, "text_decoder_prenet", None) is None:
+            raise NotImplementedError("text decoding needs the opt-in text decoder (--build-text-decoder): "
+                                      "SURVEY.md section 8a rows 9, 14, 21")
+        dec_in, tgt_mask, _ = self.text_decoder_prenet(tokens)
+        decoder_output, extra = self.decoder(dec_in, tgt_mask, encoder_out, alignment_layer=None)
+        if incremental_state is not None:
+            decoder_output = decoder_output[:, -1:, :]
+        return self.text_decoder_postnet(decoder_output), extra
+
+    @torch.no_grad()
+    def generate_text_greedy(self, source, padding_mask=None, max_len_a=0.0, max_len_b=200, min_len=1, unk_penalty=0.0,
+                             temperature=1.0, pad=1, eos=2, unk=3, blank=0, mask_idx=None):
+        """Beam-1 decoding as `generate.py --beam 1` runs it (speecht5/sequence_generator.py:207-655 with ctc_weight 0
+        and no LM): encoder once, then per step log_softmax(logits / T) of the last position with the reference's
+        masking order (:430-446: eos forbidden before min_len, NaN -> -inf, pad never, unk penalty, CTC blank and mask
+        symbol never, only eos once max_len is reached) and argmax. The prefix starts with eos; max_len counts PADDED
+        source samples (:249,262-265). Returns a list of 1-D LongTensors ending in eos. EXPERIMENTAL (opt-in branch)."""
+        import math
+        B, src_len = source.size(0), source.size(1)
+        max_len = min(int(max_len_a * src_len + max_len_b), self.args.max_text_positions - 1)
+        assert min_len <= max_len
+        enc = self.forward_encoder(source, padding_mask=padding_mask)
+        tokens = torch.full((B, max_len + 2), pad, dtype=torch.long, device=source.device)
+        tokens[:, 0] = eos
+        done = torch.zeros(B, dtype=torch.bool, device=source.device)
+        lengths = torch.zeros(B, dtype=torch.long, device=source.device)
+        for step in range(max_len + 1):
+            logits, _ = self.forward_decoder(tokens[:, : step + 1], enc, incremental_state={})
+            lprobs = F.log_softmax(logits[:, -1, :].float() / temperature, dim=-1)
+            if step < min_len:
+                lprobs[:, eos] = -math.inf
+            lprobs[lprobs != lprobs] = -math.inf
+            lprobs[:, pad] = -math.inf
+            lprobs[:, unk] -= unk_penalty
+            lprobs[:, blank] = -math.inf
+            if mask_idx is not None and mask_idx != unk:
+                lprobs[:, mask_idx] = -math.inf
+            if step >= max_len:
+                lprobs[:, :eos] = -math.inf
+                lprobs[:, eos + 1:] = -math.inf
+            nxt = lprobs.argmax(dim=-1)
+            tokens[:, step + 1] = nxt
+            newly = (~done) & nxt.eq(eos)
+            lengths = torch.where(newly, torch.full_like(lengths, step + 1), lengths)
+            done |= newly
+            if bool(done.all()):
+                break
+        return [tokens[b, 1: int(lengths[b]) + 1].clone() for b in range(B)]
 
     def forward_text_encoder(self, src_tokens):
         encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)

@@ -147,3 +147,32 @@ def test_logmel_on_device_against_the_oracle(cuda):
     want = np.stack([ref_fn(w) for w in waves])
     assert got.shape == want.shape
     assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
+
+
+def test_greedy_text_decoding_token_ids_match_the_oracle(cuda):
+    """SURVEY 8a row 21 (ASR half): beam-1 decoding on the device path (prefix recomputation) gives the oracle's token
+    ids (fp32 parity mode; random weights make near-ties unlikely but the logits are also compared)."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.float32
+    RT.invalidate_shadows()
+    torch.manual_seed(6)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
+    with torch.no_grad():
+        oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)  # spread the logits
+    args = make_args("t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
+                     use_sinc_pos=True, **over)
+    model = T5TransformerModel.build_model(args).to(cuda).eval()
+    sd = dict(oracle.state_dict())
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd["speech_encoder_prenet." + b] = sd.pop("speech_encoder_prenet." + a)
+    model.load_state_dict(sd)
+    s = O.synthetic_asr_batch(2, 12000, 6, seed=9)
+    src, pm = s["net_input"]["source"], s["net_input"]["padding_mask"]
+    want = O.greedy_decode(oracle, src, pm, max_len_b=12)
+    got = model.generate_text_greedy(src.to(cuda), pm.to(cuda), max_len_b=12)
+    assert [t.tolist() for t in got] == [t.tolist() for t in want]
+    RT.dtype = torch.bfloat16
