@@ -204,6 +204,19 @@ int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, con
                           int dtype, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride, int act,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------- CTC
+ * (speech-input branch, SURVEY section 8a row 18 -- EXPERIMENTAL: written without GPU time, not yet validated on device)
+ * Replaces F.log_softmax + F.ctc_loss(reduction="sum") of speech_to_text_loss.py:303-335 on the encoder's CTC head.
+ * logits fp32, element (t, b, k) at t*ld_t + b*ld_b + k; targets: flat int64 labels, utterance b's at
+ * targets[tgt_offsets[b] .. + target_lengths[b]); nll [B] receives the per-utterance negative log-likelihood (+inf for
+ * an infeasible utterance, or 0 with zero_infinity); grad (optional, same addressing as logits) receives
+ * d(sum_b nll_b)/d logits, zero for t >= input_lengths[b] and for infeasible utterances. S_max >= 2*max(target_lengths)+1
+ * (<= 1024) is the scratch pitch; ws: st5_ctc_ws_floats(T, B, S_max) floats. */
+int64_t st5_ctc_ws_floats(int32_t T, int32_t B, int32_t S_max);
+int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
+                 const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,
+                 int32_t T, int32_t B, int32_t V, int32_t S_max, int32_t blank, int32_t zero_infinity, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- optimizer
  * Replaces fairseq/optim/adam.py + fp16_optimizer.py:106-218 on a flat fp32 parameter buffer: one pass applies the
  * gradient scale (grad_mul x clip coefficient max_norm / (norm + 1e-6) capped at 1: fairseq/utils.py clip_grad_norm_,

@@ -76,6 +76,9 @@ _PROTOS = {
                                         _i32, _vp]),
     "st5_conv0_gn_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,
                                         _i32, _i32, _i32, _vp]),
+    "st5_ctc_ws_floats": (C.c_int64, [_i32, _i32, _i32]),
+    "st5_ctc_loss": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
+                               _vp]),
     "st5_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "st5_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i64, _vp, _f, _f, _vp, _vp, _vp]),
 }

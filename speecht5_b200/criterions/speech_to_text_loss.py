@@ -3,6 +3,8 @@ label_smoothed_nll_loss :93-110) for the opt-in speech-input branch. The arithme
 ([B, T_d, V] decoder logits, [T_e, B, V] CTC head) and is issued as torch library calls (log_softmax, gather,
 F.ctc_loss with cuDNN off like the reference :326); the hand-written per-utterance CTC recursion that replaces the
 library call is specified in tests/test_kernel_algorithms_cpu.py. EXPERIMENTAL (see speecht5_b200/frontend.py)."""
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -81,6 +83,11 @@ class SpeechtoTextLoss(FairseqCriterion):
         keep = (sample["target"] != self.pad_idx) & (sample["target"] != self.eos_idx)
         targets_flat = sample["target"].masked_select(keep)
         target_lengths = (sample["target_lengths"] if "target_lengths" in sample else keep.sum(-1)) - 1  # :324
+        raw = net_output["encoder_out_for_ctc"][0]
+        if os.environ.get("ST5_CTC_KERNEL") == "1" and raw.is_cuda:  # hand-written fused log-softmax + CTC (csrc/ctc.cu)
+            from ..frontend import ctc_loss_sum
+            loss = ctc_loss_sum(raw, targets_flat, input_lengths, target_lengths, self.blank_idx, self.zero_infinity)
+            return loss, lprobs, input_lengths
         with torch.backends.cudnn.flags(enabled=False):
             loss = F.ctc_loss(lprobs, targets_flat, input_lengths, target_lengths, blank=self.blank_idx,
                               reduction="sum", zero_infinity=self.zero_infinity)

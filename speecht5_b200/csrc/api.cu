@@ -148,6 +148,15 @@ int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, con
                    "st5_conv0_gn_gelu_bwd");
 }
 
+int64_t st5_ctc_ws_floats(int32_t T, int32_t B, int32_t S_max) { return ctc_ws_floats(T, B, S_max); }
+int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
+                 const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,
+                 int32_t T, int32_t B, int32_t V, int32_t S_max, int32_t blank, int32_t zero_infinity, void* stream) {
+  return set_error(ctc_loss_launch(logits, ld_t, ld_b, targets, tgt_offsets, input_lengths, target_lengths, nll, grad,
+                                   ws, T, B, V, S_max, blank, zero_infinity, (cudaStream_t)stream),
+                   "st5_ctc_loss");
+}
+
 int st5_sumsq(const float* x, int64_t n, float* out, void* stream) {
   return set_error(sumsq_launch(x, n, out, (cudaStream_t)stream), "st5_sumsq");
 }

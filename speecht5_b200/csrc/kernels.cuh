@@ -129,6 +129,11 @@ int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, cons
 int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
                      const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
                      int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
+int64_t ctc_ws_floats(int32_t T, int32_t B, int32_t S_max);
+int ctc_loss_launch(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
+                    const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,
+                    int32_t T, int32_t B, int32_t V, int32_t S_max, int32_t blank, int32_t zero_infinity,
+                    cudaStream_t s);
 int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s);
 int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, const float* grad_norm_sq, float max_norm,

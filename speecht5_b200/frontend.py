@@ -400,3 +400,31 @@ class SpeechEncoderPrenet(torch.nn.Module):
         if require_feat_pen:
             return (x, features_pen, mask_indices, None), frame_mask
         return x, frame_mask
+
+
+class CTCLossFn(torch.autograd.Function):
+    """sum_b CTC nll of the encoder head, log-softmax fused (csrc/ctc.cu); the gradient with respect to the logits is
+    produced in the same launch and scaled by the incoming scalar in backward. EXPERIMENTAL."""
+
+    @staticmethod
+    def forward(ctx, logits, targets_flat, input_lengths, target_lengths, blank, zero_infinity):
+        logits = logits.float().contiguous()
+        T, B, V = logits.shape
+        tl = target_lengths.long().contiguous()
+        offs = (torch.cumsum(tl, 0) - tl).contiguous()
+        s_max = 2 * int(tl.max().item()) + 1 if B > 0 else 1
+        nll = torch.empty(B, dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits)
+        K.ctc_loss(logits, targets_flat.long().contiguous(), offs, input_lengths.long().contiguous(), tl, nll, grad,
+                   s_max, int(blank), bool(zero_infinity))
+        ctx.save_for_backward(grad)
+        return nll.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None
+
+
+def ctc_loss_sum(logits_tbv, targets_flat, input_lengths, target_lengths, blank, zero_infinity):
+    return CTCLossFn.apply(logits_tbv, targets_flat, input_lengths, target_lengths, blank, zero_infinity)

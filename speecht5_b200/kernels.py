@@ -262,6 +262,22 @@ def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, s
     _count(4)
 
 
+def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, grad, s_max, blank, zero_infinity):
+    """EXPERIMENTAL (not yet validated on a GPU). logits [T, B, V] fp32 (inner stride 1); see st5_ctc_loss."""
+    _require_cuda(logits, targets, nll)
+    assert logits.dtype == torch.float32 and logits.stride(2) == 1
+    for t in (targets, tgt_offsets, input_lengths, target_lengths):
+        assert t.dtype == torch.int64 and t.is_contiguous()
+    T, B, V = logits.shape
+    assert grad is None or (grad.dtype == torch.float32 and grad.stride() == logits.stride())
+    lib = _lib.load()
+    ws = torch.empty(lib.st5_ctc_ws_floats(T, B, s_max), device=logits.device, dtype=torch.float32)
+    _lib.check(lib.st5_ctc_loss(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(targets), _ptr(tgt_offsets),
+                                _ptr(input_lengths), _ptr(target_lengths), _ptr(nll), _ptr(grad), _ptr(ws), T, B, V,
+                                s_max, blank, int(zero_infinity), _stream()), "st5_ctc_loss")
+    _count(2)
+
+
 def sumsq(x, out):
     lib = _lib.load()
     _lib.check(lib.st5_sumsq(_ptr(x), x.numel(), _ptr(out), _stream()), "st5_sumsq")

@@ -176,3 +176,26 @@ def test_greedy_text_decoding_token_ids_match_the_oracle(cuda):
     got = model.generate_text_greedy(src.to(cuda), pm.to(cuda), max_len_b=12)
     assert [t.tolist() for t in got] == [t.tolist() for t in want]
     RT.dtype = torch.bfloat16
+
+
+def test_ctc_kernel_against_torch(cuda):
+    """csrc/ctc.cu (fused log-softmax + CTC nll + logit gradient) vs torch's ctc_loss autograd: ASR-shaped batch with
+    ragged input / target lengths, repeated labels and one infeasible utterance under zero_infinity."""
+    import torch.nn.functional as F
+    from speecht5_b200.frontend import ctc_loss_sum
+    torch.manual_seed(13)
+    T, B, V = 120, 5, 81
+    tl = torch.tensor([30, 12, 1, 70, 25])
+    il = torch.tensor([120, 90, 3, 100, 120])  # utterance 3: 70 labels in 100 frames is feasible only without repeats
+    tg = [torch.randint(1, V, (int(n),)) for n in tl]
+    tg[3][::2] = tg[3][1::2]  # repeated pairs -> needs 70 + 35 = 105 frames > 100: infeasible
+    flat = torch.cat(tg)
+    logits = torch.randn(T, B, V, requires_grad=True)
+    ref = F.ctc_loss(F.log_softmax(logits, -1), flat, il, tl, blank=0, reduction="sum", zero_infinity=True)
+    ref.backward()
+    x = logits.detach().to(cuda).requires_grad_()
+    got = ctc_loss_sum(x, flat.to(cuda), il.to(cuda), tl.to(cuda), 0, True)
+    (got * 2.0).backward()
+    assert abs(got.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel(x.grad.cpu() / 2.0, logits.grad) < 1e-4
+    assert x.grad[:, 3].abs().max().item() == 0.0 and x.grad[100:, 1].abs().max().item() == 0.0

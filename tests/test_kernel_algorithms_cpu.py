@@ -311,3 +311,88 @@ def test_fused_conv0_groupnorm_gelu_statement_matches_autograd():
         dv = rstd[:, None] * gamma * (g - s1[:, None] / T0 - xh * s2[:, None] / T0)
         dw = torch.einsum("btc,btk->ck", dv, win)
         assert torch.allclose(dw, w.grad, atol=1e-9)
+
+
+def _ctc_kernel_emulation(logits, tg, Tn, blank=0):
+    """csrc/ctc.cu restated statement by statement in fp32 numpy, vectorised over the threads s of one CTA: the
+    prev/cur state exchange, the skip-transition predicates, the backward sweep that finishes each gradient row in the
+    linear domain (terms below e^-80 dropped), rows t >= Tn zeroed."""
+    f = np.float32
+    T, V = logits.shape
+    L = len(tg)
+    S = 2 * L + 1
+    s = np.arange(S)
+    sym = np.where(s & 1, np.asarray(tg, dtype=np.int64)[np.minimum(s >> 1, max(L - 1, 0))] if L else blank, blank)
+    odd = (s & 1) == 1
+    skip = np.zeros(S, bool)
+    skip_f = np.zeros(S, bool)
+    for i in range(S):
+        if odd[i] and i >= 2:
+            skip[i] = tg[(i >> 1) - 1] != sym[i]
+        if odd[i] and i + 2 < S:
+            skip_f[i] = tg[(i >> 1) + 1] != sym[i]
+    lse = np.logaddexp.reduce(logits.astype(np.float64), axis=1).astype(f)
+    ninf = f(-np.inf)
+
+    def lse2(a, b):
+        with np.errstate(invalid="ignore"):
+            m = np.maximum(a, b)
+            r = m + np.log1p(np.exp(-np.abs(a - b))).astype(f)
+        return np.where(np.isneginf(m), ninf, r).astype(f)
+
+    def shift(x, k):  # x[s - k] (k > 0) or x[s + |k|] (k < 0), -inf outside
+        out = np.full(S, ninf, f)
+        if k > 0:
+            out[k:] = x[:-k] if k < S else []
+        else:
+            out[:k] = x[-k:]
+        return out
+    aw = np.full((T, S), ninf, f)
+    prev = np.full(S, ninf, f)
+    if Tn >= 1:
+        prev[:2] = (logits[0, sym[:2]] - lse[0]).astype(f)
+    aw[0] = prev
+    for t in range(1, Tn):
+        v = lse2(prev, shift(prev, 1))
+        v = np.where(skip, lse2(v, shift(prev, 2)), v)
+        prev = (v + (logits[t, sym] - lse[t])).astype(f)
+        aw[t] = prev
+    ll = ninf if Tn < 1 else (lse2(prev[S - 1:S], prev[S - 2:S - 1])[0] if S >= 2 else prev[0])
+    nll = -ll
+    grad = np.zeros((T, V), f)
+    if not np.isfinite(nll):
+        return nll, grad
+    for t in range(Tn - 1, -1, -1):
+        lp_sym = (logits[t, sym] - lse[t]).astype(f)
+        if t == Tn - 1:
+            v = np.where(s >= S - 2, f(0), ninf)
+        else:
+            v = lse2(prev, shift(prev, -1))
+            v = np.where(skip_f, lse2(v, shift(prev, -2)), v)
+        be = (v + lp_sym).astype(f)
+        e = aw[t] + be - lp_sym + nll
+        acc = np.zeros(V, f)
+        with np.errstate(invalid="ignore"):
+            np.add.at(acc, sym[e > -80], np.exp(e[e > -80]).astype(f))
+        grad[t] = np.exp(logits[t] - lse[t]).astype(f) - acc
+        prev = be
+    return nll, grad
+
+
+def test_ctc_kernel_program_matches_torch():
+    """The thread program of csrc/ctc.cu (emulated in fp32) against torch's ctc_loss + log_softmax autograd: repeated
+    labels, an empty target, a one-frame input, ragged lengths and an infeasible utterance (zero_infinity)."""
+    torch.manual_seed(12)
+    T, V = 19, 7
+    cases = [([3, 3, 5, 1, 1, 2], 19), ([4, 2], 11), ([], 5), ([6], 1), ([2, 2, 2, 2, 2, 2], 10), ([1, 2, 3], 16)]
+    for tg, Tn in cases:
+        logits = torch.randn(T, 1, V, dtype=torch.float32, requires_grad=True)
+        loss = F.ctc_loss(F.log_softmax(logits, -1), torch.tensor(tg, dtype=torch.long)[None] if tg else
+                          torch.zeros(1, 0, dtype=torch.long), torch.tensor([Tn]), torch.tensor([len(tg)]), blank=0,
+                          reduction="sum", zero_infinity=True)
+        loss.backward()
+        nll, grad = _ctc_kernel_emulation(logits.detach().numpy()[:, 0], tg, Tn)
+        feasible = np.isfinite(nll)
+        assert abs((nll if feasible else 0.0) - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (tg, Tn)
+        assert np.abs(grad - logits.grad.numpy()[:, 0]).max() < 2e-5, (tg, Tn)
+    assert not np.isfinite(_ctc_kernel_emulation(np.zeros((T, V), np.float32), [2, 2, 2, 2, 2, 2], 10)[0])
