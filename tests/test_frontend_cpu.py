@@ -138,3 +138,30 @@ def test_logmel_device_composition_matches_the_oracle(monkeypatch):
     one = audio.logmelfilterbank(torch.from_numpy(waves[0])).numpy()
     assert np.abs(one - want[0]).max() < 1e-3
     audio._CONST.clear()
+
+
+def test_hifigan_device_composition_matches_the_oracle(monkeypatch):
+    """speecht5_b200/vocoder.py through the GEMM emulator (bf16 activations) against oracle HifiGanGenerator (fp32):
+    'same' convolutions, the stride-phase transposed convolutions, the de-interleaved dilated convolutions, ResBlock
+    residuals, averaging and the final tanh -- reduced configuration, T not a multiple of the dilations."""
+    from oracle.audio_oracle import HifiGanGenerator as Ref
+    from speecht5_b200 import vocoder
+    gemm_emulator.install(monkeypatch)
+    cfg = dict(model_in_dim=16, upsample_initial_channel=32, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+               resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3], [1, 5]])
+    torch.manual_seed(0)
+    ref = Ref(cfg, std=0.15, seed=1).eval()
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n.endswith("bias"):
+                p.add_(0.05 * torch.randn_like(p))
+        ref.mean.copy_(torch.randn(16) * 0.1)
+        ref.scale.copy_(1.0 + 0.1 * torch.rand(16))
+    gen = vocoder.HifiGanGenerator(ref.state_dict(), cfg, device="cpu")
+    mel = torch.randn(2, 13, 16)
+    with torch.no_grad():
+        want = ref(mel)
+    got = gen(mel)
+    assert got.shape == want.shape == (2, 13 * 8)
+    err = ((got.double() - want.double()).norm() / want.double().norm()).item()
+    assert err < 3e-2, err

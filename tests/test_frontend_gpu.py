@@ -199,3 +199,19 @@ def test_ctc_kernel_against_torch(cuda):
     assert abs(got.item() - ref.item()) < 1e-4 * abs(ref.item())
     assert rel(x.grad.cpu() / 2.0, logits.grad) < 1e-4
     assert x.grad[:, 3].abs().max().item() == 0.0 and x.grad[100:, 1].abs().max().item() == 0.0
+
+
+def test_hifigan_on_device_against_the_oracle(cuda):
+    """speecht5_b200/vocoder.py with the release configuration (512 channels, 4x4x4x4 up-sampling, ResBlocks 3/7/11 x
+    dilations 1/3/5) vs oracle HifiGanGenerator (fp32 CPU) on a short mel: bf16 activations, so a relative L2 bound."""
+    from oracle.audio_oracle import HifiGanGenerator as Ref
+    from speecht5_b200 import vocoder
+    torch.manual_seed(0)
+    ref = Ref(std=0.02, seed=1).eval()
+    gen = vocoder.HifiGanGenerator(ref.state_dict(), device=cuda)
+    mel = torch.randn(2, 37, 80)
+    with torch.no_grad():
+        want = ref(mel)
+    got = gen(mel.to(cuda)).cpu()
+    assert got.shape == want.shape == (2, 37 * 256)
+    assert rel(got, want) < 3e-2
