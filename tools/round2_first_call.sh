@@ -17,7 +17,7 @@ run pytest_gpu 600 python -m pytest tests -m gpu -x -q
 ST5_TEST_UNFUSED=1 run gated_unfused 120 python -m pytest tests/test_a_ops_gpu.py -k tensor_core_attention -q
 ST5_TEST_T2T=1 run gated_t2t 120 python -m pytest tests/test_model_gpu.py -k text_to_text -q
 ST5_TEST_CONV0=1 run gated_conv0 120 python -m pytest tests/test_a_ops_gpu.py -k conv0 -q
-ST5_TEST_FRONTEND=1 run gated_frontend 300 python -m pytest tests/test_frontend_gpu.py -q
+ST5_TEST_FRONTEND=1 run gated_frontend 900 python -m pytest tests/test_frontend_gpu.py -q   # no -x: every draft gets its verdict
 # 3. CTA-pair GEMM: bit-exactness against the single-CTA kernel + per-shape timings of both
 run pair_check 300 python tools/check_gemm_pair.py
 # 4. the step with and without the pair GEMM (same box, back to back)
