@@ -95,18 +95,20 @@ def _ddp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gradient_exchange_is_mean_over_ranks_gloo():
-    """legacy_distributed_data_parallel.py:76-165 semantics: grads /= world, all-reduce(sum); bucketed, world_size 2."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_gradient_exchange_is_mean_over_ranks_gloo(world):
+    """legacy_distributed_data_parallel.py:76-165 semantics: grads /= world, all-reduce(sum); bucketed; world_size 2 and
+    4 (the scaling run goes to 8 ranks with the same code)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29511 + os.getpid() % 500
-    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29511 + (os.getpid() * 7 + world) % 500
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    res = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert all(err < 1e-6 for _, err in res), res
+    assert len(res) == world and all(err < 1e-6 for _, err in res), res
 
 
 def test_model_exposes_the_reference_model_api():
