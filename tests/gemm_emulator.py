@@ -73,10 +73,38 @@ def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
     out.copy_(((out.double() if accumulate else 0) + tot).to(out.dtype))
 
 
+def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
+    """st5_ln_fwd without dropout: s = x (+ residual), y = LayerNorm(s) over the last dimension."""
+    assert drop_p == 0.0
+    s_ = x.double() + (residual.double() if residual is not None else 0.0)
+    mu = s_.mean(-1, keepdim=True)
+    var = s_.var(-1, unbiased=False, keepdim=True)
+    rs = 1.0 / torch.sqrt(var + eps)
+    y.copy_(((s_ - mu) * rs * gamma.double() + beta.double()).to(y.dtype))
+    if s_out is not None:
+        s_out.copy_(s_.to(s_out.dtype))
+    mean.copy_(mu.reshape(-1).float())
+    rstd.copy_(rs.reshape(-1).float())
+
+
+def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
+    """st5_conv0_gn_gelu_fwd: Conv1d(1 -> C, k, stride) + GroupNorm(C groups) + GELU, channels-last output."""
+    v = torch.nn.functional.conv1d(wave.double()[:, None], w.double()[:, None], stride=stride)  # [B, C, T0]
+    mu = v.mean(-1)
+    var = v.var(-1, unbiased=False)
+    rs = 1.0 / torch.sqrt(var + eps)
+    z = (v - mu[..., None]) * rs[..., None] * gamma.double()[None, :, None] + beta.double()[None, :, None]
+    y.copy_(torch.nn.functional.gelu(z).transpose(1, 2).to(y.dtype))
+    mean.copy_(mu.float())
+    rstd.copy_(rs.float())
+
+
 def install(monkeypatch):
     from speecht5_b200 import kernels as K
     monkeypatch.setattr(K, "gemm", gemm)
     monkeypatch.setattr(K, "cast_bf16", cast_bf16)
     monkeypatch.setattr(K, "act_bwd", act_bwd)
     monkeypatch.setattr(K, "colsum", colsum)
+    monkeypatch.setattr(K, "ln_fwd", ln_fwd)
+    monkeypatch.setattr(K, "conv0_gn_gelu_fwd", conv0_gn_gelu_fwd)
     monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)

@@ -165,3 +165,59 @@ def test_hifigan_device_composition_matches_the_oracle(monkeypatch):
     assert got.shape == want.shape == (2, 13 * 8)
     err = ((got.double() - want.double()).norm() / want.double().norm()).item()
     assert err < 3e-2, err
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_speech_encoder_prenet_module_forward_against_the_oracle(monkeypatch, dtype):
+    """The whole speech prenet module (frontend.SpeechEncoderPrenet, eval mode) with every kernel entry point emulated
+    on the CPU: conv stack, LayerNorm, projection, injected mask draw, positional conv, sinusoidal positions, frame
+    padding mask and the feature penalty -- against oracle SpeechEncoderPrenet with the same weights."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", dtype)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    torch.manual_seed(1)
+    args = O.base_asr_args(encoder_layers=1, decoder_layers=1, dropout=0.0)
+    for k, v in dict(encoder_speech_prenet="conv", mask_prob=0.0, hubert_mask_length=10, mask_selection="static",
+                     mask_other=0.0, no_mask_overlap=False, mask_min_space=1, mask_channel_prob=0.0,
+                     freeze_encoder_updates=0).items():
+        setattr(args, k, v)
+    args.conv_feature_layers = list(O.CONV_FEATURE_LAYERS)  # a list suits both (the CLI hands the product a string)
+    ref = O.SpeechEncoderPrenet(args).double().eval()
+    mine = frontend.SpeechEncoderPrenet(args).eval()
+    sd = {k: v.float() for k, v in ref.state_dict().items()}
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd[b] = sd.pop(a)
+    missing, unexpected = mine.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    B, n = 2, 4000
+    wave = torch.randn(B, n, dtype=torch.float64) * 0.3
+    pm = torch.arange(n)[None, :] >= torch.tensor([4000, 2600])[:, None]
+    T = int(ref.feature_extractor.get_out_seq_lens_tensor(torch.tensor([n]))[0])
+    mi = torch.zeros(B, T, dtype=torch.bool)
+    mi[0, 2:6] = True
+    mi[1, 1:3] = True
+    with torch.no_grad():
+        xr, mr, pen_r = ref(wave, pm, mask_indices=mi)
+        (x, pen, got_mi, _), m = mine(wave.float(), require_feat_pen=True, padding_mask=pm, mask=True, mask_indices=mi)
+    assert torch.equal(m, mr) and got_mi is mi
+    err = ((x.double() - xr).norm() / xr.norm()).item()
+    assert err < (2e-4 if dtype == torch.float32 else 3e-2), err
+    assert abs(pen.item() - pen_r.item()) / pen_r.item() < (1e-4 if dtype == torch.float32 else 2e-2)
+    RT.invalidate_shadows()
+
+
+def _cpu_extractor_forward(self, wave):
+    """ConvFeatureExtractor.forward without its CUDA guard (the kernels underneath are emulated in these tests)."""
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    blk0 = self.conv_layers[0]
+    x = frontend.Conv0GroupNormGeluFn.apply(wave, blk0[0].weight, blk0[2].weight, blk0[2].bias, self.specs[0][2],
+                                            blk0[2].eps, RT.dtype)
+    for i in range(1, len(self.specs)):
+        x = frontend.StridedConvGeluFn.apply(x, self.conv_layers[i][0].weight, self.specs[i][2])
+    return x

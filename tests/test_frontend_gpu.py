@@ -20,8 +20,7 @@ def _args():
     for k, v in dict(encoder_speech_prenet="conv", mask_prob=0.0, hubert_mask_length=10, mask_selection="static",
                      mask_other=0.0, no_mask_overlap=False, mask_min_space=1).items():
         setattr(args, k, v)
-    if not isinstance(getattr(args, "conv_feature_layers", None), (list, str)):
-        args.conv_feature_layers = "[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2"
+    args.conv_feature_layers = list(O.CONV_FEATURE_LAYERS)  # a list suits both the oracle and the product
     return args
 
 
