@@ -99,6 +99,40 @@ def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
     rstd.copy_(rs.float())
 
 
+def posenc_fwd(tokens, emb, x, pe, alpha, y, drop_p=0.0, seed=0, offset=0):
+    """st5_posenc_fwd without dropout: y[b, t] = (emb[tokens[b, t]] | x[b, t]) + alpha * pe[t]."""
+    assert drop_p == 0.0
+    T = y.shape[1]
+    base = emb.double()[tokens] if tokens is not None else x.double()
+    y.copy_((base + alpha.double() * pe.double()[:T][None]).to(y.dtype))
+
+
+def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, maxpos=0, key_pad=None, causal=False,
+              drop_p=0.0, return_probs=False):
+    """ops.attention (forward, no dropout) restated with torch: multihead_attention.py:340-389 incl. the relative-position
+    bias q_i . pe[clamp(i - j, -maxpos, maxpos - 1) + maxpos] (q already scaled)."""
+    assert drop_p == 0.0
+    kvb = q_buf if kv_buf is None else kv_buf
+    B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
+
+    def heads(buf, col, T):
+        return buf[..., col * d:(col + 1) * d].double().reshape(B, T, H, d // H).transpose(1, 2)
+    q, k, v = heads(q_buf, q_col, Tq) * scale, heads(kvb, k_col, Tk), heads(kvb, v_col, Tk)
+    s = q @ k.transpose(-1, -2)
+    if pe_k is not None:
+        i = torch.arange(Tq)[:, None]
+        j = torch.arange(Tk)[None, :]
+        pos = pe_k.double()[(i - j).clamp(-maxpos, maxpos - 1) + maxpos]  # [Tq, Tk, 64]
+        s = s + torch.einsum("bhic,ijc->bhij", q, pos)
+    if causal:
+        s = s + torch.triu(torch.full((Tq, Tk), float("-inf"), dtype=s.dtype), 1)
+    if key_pad is not None:
+        s = s.masked_fill(key_pad.bool()[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    out = (p @ v).transpose(1, 2).reshape(B, Tq, d).to(q_buf.dtype)
+    return out, (p.float() if return_probs else None)
+
+
 def install(monkeypatch):
     from speecht5_b200 import kernels as K
     monkeypatch.setattr(K, "gemm", gemm)
@@ -106,5 +140,8 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "act_bwd", act_bwd)
     monkeypatch.setattr(K, "colsum", colsum)
     monkeypatch.setattr(K, "ln_fwd", ln_fwd)
+    monkeypatch.setattr(K, "posenc_fwd", posenc_fwd)
+    from speecht5_b200 import ops
+    monkeypatch.setattr(ops, "attention", attention)
     monkeypatch.setattr(K, "conv0_gn_gelu_fwd", conv0_gn_gelu_fwd)
     monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)

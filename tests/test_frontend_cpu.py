@@ -221,3 +221,45 @@ def _cpu_extractor_forward(self, wave):
     for i in range(1, len(self.specs)):
         x = frontend.StridedConvGeluFn.apply(x, self.conv_layers[i][0].weight, self.specs[i][2])
     return x
+
+
+def test_speech_to_text_model_forward_and_greedy_decoding_on_emulated_kernels(monkeypatch):
+    """The opt-in s2t branch of T5TransformerModel.forward, forward_encoder / forward_decoder and generate_text_greedy
+    with every kernel entry point emulated on the CPU (fp32 parity arithmetic): logits and CTC head against the ASR
+    oracle, and beam-1 token ids against oracle greedy_decode."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    torch.manual_seed(6)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
+    with torch.no_grad():
+        oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)
+    args = make_args("t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
+                     use_sinc_pos=True, **over)
+    model = T5TransformerModel.build_model(args).eval()
+    sd = dict(oracle.state_dict())
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd["speech_encoder_prenet." + b] = sd.pop("speech_encoder_prenet." + a)
+    model.load_state_dict(sd)
+    s = O.synthetic_asr_batch(2, 6000, 6, seed=9)
+    with torch.no_grad():
+        (want, _), enc_ref = oracle(**s["net_input"])
+        (got, _), enc = model(**s["net_input"])
+    keep = s["target"].ne(1)
+    assert ((got[keep].double() - want[keep].double()).norm() / want[keep].double().norm()).item() < 2e-4
+    ctc_ref, ctc = enc_ref["encoder_out_for_ctc"][0], enc["encoder_out_for_ctc"][0]
+    valid = ~enc_ref["encoder_padding_mask"][0].t()  # [T, B]
+    assert ((ctc[valid].double() - ctc_ref[valid].double()).norm() / ctc_ref[valid].double().norm()).item() < 2e-4
+    assert torch.equal(enc["encoder_padding_mask"][0], enc_ref["encoder_padding_mask"][0])
+    src, pm = s["net_input"]["source"], s["net_input"]["padding_mask"]
+    ids_ref = O.greedy_decode(oracle, src, pm, max_len_b=10)
+    ids = model.generate_text_greedy(src, pm, max_len_b=10)
+    assert [t.tolist() for t in ids] == [t.tolist() for t in ids_ref]
+    RT.invalidate_shadows()
