@@ -22,7 +22,7 @@ def _gelu_grad(z):
 def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1, a_bs=(0, 0),
          b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None, act=None, alpha=1.0,
          accumulate=False, drop_p=0.0, seed=0, offset=0, actgrad_pre=None, actgrad_act=None):
-    assert nb2 == 1 and drop_p == 0.0 and bias2 is None and actgrad_pre is None
+    assert nb2 == 1 and drop_p == 0.0 and actgrad_pre is None
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a_ld = a_ld if a_ld is not None else (M if a_mn else K)
     b_ld = b_ld if b_ld is not None else (N if b_mn else K)
@@ -38,6 +38,9 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
     if bias is not None:
         assert bias.dtype == torch.float32
         v = v + bias[:N].double()
+    if bias2 is not None:  # per-utterance bias: row m takes bias2[m // bias2_rows]
+        assert nb1 == 1 and bias2.dtype == torch.float32 and bias2_rows > 0
+        v = v + bias2.double()[torch.arange(M) // bias2_rows][None, :, :N]
     if c_pre is not None:
         torch.as_strided(c_pre, (nb1, M, N), (c_bs[0], c_ld, 1), c_pre.storage_offset()).copy_(v.to(c_pre.dtype))
     if act in ("gelu", "gelu_tanh"):
@@ -133,6 +136,26 @@ def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, max
     return out, (p.float() if return_probs else None)
 
 
+def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd, y, y_ld, y_pre, rows, Cc, training,
+           momentum, eps, act, drop_p, seed, offset, scratch):
+    """st5_bn_fwd without dropout: BatchNorm1d over all rows of a channels-last [rows, C] tensor (+ tanh)."""
+    assert drop_p == 0.0 and x_ld == Cc and y_ld == Cc
+    xs = x.double().reshape(rows, Cc)
+    if training:
+        mu, var = xs.mean(0), xs.var(0, unbiased=False)
+    else:
+        mu, var = running_mean.double(), running_var.double()
+    rs = 1.0 / torch.sqrt(var + eps)
+    pre = (xs - mu) * rs * gamma.double() + beta.double()
+    if y_pre is not None:
+        y_pre.copy_(pre.reshape(y_pre.shape).to(y_pre.dtype))
+    out = torch.tanh(pre) if act == "tanh" else pre
+    assert act in (None, "none", "tanh")
+    y.copy_(out.reshape(y.shape).to(y.dtype))
+    save_mean.copy_(mu.float())
+    save_rstd.copy_(rs.float())
+
+
 def install(monkeypatch):
     from speecht5_b200 import kernels as K
     monkeypatch.setattr(K, "gemm", gemm)
@@ -141,6 +164,7 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "colsum", colsum)
     monkeypatch.setattr(K, "ln_fwd", ln_fwd)
     monkeypatch.setattr(K, "posenc_fwd", posenc_fwd)
+    monkeypatch.setattr(K, "bn_fwd", bn_fwd)
     from speecht5_b200 import ops
     monkeypatch.setattr(ops, "attention", attention)
     monkeypatch.setattr(K, "conv0_gn_gelu_fwd", conv0_gn_gelu_fwd)

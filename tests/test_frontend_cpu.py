@@ -263,3 +263,25 @@ def test_speech_to_text_model_forward_and_greedy_decoding_on_emulated_kernels(mo
     ids = model.generate_text_greedy(src, pm, max_len_b=10)
     assert [t.tolist() for t in ids] == [t.tolist() for t in ids_ref]
     RT.invalidate_shadows()
+
+
+def test_text_to_speech_forward_on_emulated_kernels_matches_the_golden_fixture(monkeypatch):
+    """Regression guard for the DEFAULT path without a GPU: T5TransformerModel.forward (t2s) with every kernel entry
+    point emulated on the CPU reproduces the committed golden outputs (tests/golden/tts_tiny.npz, training-mode
+    BatchNorm, no dropout) -- the model-level Python is exercised here, the kernels in the -m gpu tests."""
+    import os
+    from helpers import NO_DROPOUT, TINY, load_golden, rel
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    RT.invalidate_shadows()
+    state, sample, out_ref, _, _ = load_golden(os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    model = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **TINY, **NO_DROPOUT, bert_init=True))
+    model.train()
+    model.load_state_dict(state)
+    with torch.no_grad():
+        before, after, logits, attn = model(**sample["net_input"])
+    assert rel(after, out_ref["after"]) < 1e-4 and rel(before, out_ref["before"]) < 1e-4
+    assert rel(logits, out_ref["logits"]) < 3e-4 and rel(torch.stack(attn), out_ref["attn"]) < 3e-4
+    RT.invalidate_shadows()
