@@ -314,7 +314,7 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
 
     @torch.no_grad()
     def generate_text_greedy(self, source, padding_mask=None, max_len_a=0.0, max_len_b=200, min_len=1, unk_penalty=0.0,
-                             temperature=1.0, pad=1, eos=2, unk=3, blank=0, mask_idx=None):
+                             temperature=1.0, pad=1, eos=2, unk=3, blank=0, mask_idx=None, use_cache=False):
         """Beam-1 decoding as `generate.py --beam 1` runs it (speecht5/sequence_generator.py:207-655 with ctc_weight 0
         and no LM): encoder once, then per step log_softmax(logits / T) of the last position with the reference's
         masking order (:430-446: eos forbidden before min_len, NaN -> -inf, pad never, unk penalty, CTC blank and mask
@@ -329,8 +329,17 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         tokens[:, 0] = eos
         done = torch.zeros(B, dtype=torch.bool, device=source.device)
         lengths = torch.zeros(B, dtype=torch.long, device=source.device)
+        cache = None
+        if use_cache:  # key/value cache (speecht5_b200/incremental.py): one new row per step
+            from ..incremental import DecoderCache, decoder_step
+            cache = DecoderCache(self.decoder, enc, max_len + 1)
         for step in range(max_len + 1):
-            logits, _ = self.forward_decoder(tokens[:, : step + 1], enc, incremental_state={})
+            if cache is not None:
+                dec_in, _, _ = self.text_decoder_prenet(tokens[:, : step + 1])
+                z, _ = decoder_step(self.decoder, dec_in[:, -1:], cache)
+                logits = self.text_decoder_postnet(z)
+            else:
+                logits, _ = self.forward_decoder(tokens[:, : step + 1], enc, incremental_state={})
             lprobs = F.log_softmax(logits[:, -1, :].float() / temperature, dim=-1)
             if step < min_len:
                 lprobs[:, eos] = -math.inf
@@ -383,15 +392,22 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         maxlen, minlen = int(T_enc * maxlenratio / r), int(T_enc * minlenratio / r)
         ys = torch.zeros(1, 1, odim, dtype=torch.float32, device=src_tokens.device)
         outs, probs, attns, idx = [], [], [], 0
+        cache = None
+        if kwargs.get("use_cache", False):  # EXPERIMENTAL key/value cache (speecht5_b200/incremental.py)
+            from ..incremental import DecoderCache, decoder_step
+            cache = DecoderCache(self.decoder, encoder_out, max(maxlen, 1) + 1)
         while True:
             idx += 1
             decoder_in, _ = self.speech_decoder_prenet(ys, spkembs=spkembs)
-            z, extra = self.decoder(decoder_in, None, encoder_out, alignment_layer=-1)
+            if cache is not None:
+                z, layer_attn = decoder_step(self.decoder, decoder_in[:, -1:], cache, need_head_weights=True)
+            else:
+                z, extra = self.decoder(decoder_in, None, encoder_out, alignment_layer=-1)
+                layer_attn = extra["attn"][0]
             before, logits = post.project(z[:, -1:].contiguous())  # [1, r, odim], [1, r]
             outs.append(before[0])
             probs.append(torch.sigmoid(logits[0]))
             ys = torch.cat((ys, before[:, -1:, :]), dim=1)
-            layer_attn = extra["attn"][0]
             layer_attn = layer_attn if isinstance(layer_attn, (list, tuple)) else [layer_attn]
             attns.append(torch.stack([a[0, :, -1:, :].float() for a in layer_attn], dim=0))  # [layers, H, 1, T]
             if bool((probs[-1] >= threshold).any()) or idx >= maxlen:

@@ -285,3 +285,57 @@ def test_text_to_speech_forward_on_emulated_kernels_matches_the_golden_fixture(m
     assert rel(after, out_ref["after"]) < 1e-4 and rel(before, out_ref["before"]) < 1e-4
     assert rel(logits, out_ref["logits"]) < 3e-4 and rel(torch.stack(attn), out_ref["attn"]) < 3e-4
     RT.invalidate_shadows()
+
+
+def test_kv_cache_decoding_equals_prefix_recomputation_on_emulated_kernels(monkeypatch):
+    """speecht5_b200/incremental.py: (a) beam-1 text decoding with the cache gives the oracle's token ids, (b) greedy
+    speech synthesis with the cache gives the same mel / stop probabilities / cross-attention rows as the
+    prefix-recomputing path and as the oracle's generate_speech (prenet dropout off so the runs are comparable)."""
+    from helpers import NO_DROPOUT, rel
+    from oracle import speecht5_oracle as OT
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    # (a) text decoding
+    torch.manual_seed(6)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
+    with torch.no_grad():
+        oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)
+    model = T5TransformerModel.build_model(make_args(
+        "t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
+        use_sinc_pos=True, **over)).eval()
+    sd = dict(oracle.state_dict())
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd["speech_encoder_prenet." + b] = sd.pop("speech_encoder_prenet." + a)
+    model.load_state_dict(sd)
+    s = O.synthetic_asr_batch(2, 6000, 6, seed=9)
+    src, pm = s["net_input"]["source"], s["net_input"]["padding_mask"]
+    ids_ref = O.greedy_decode(oracle, src, pm, max_len_b=10)
+    ids = model.generate_text_greedy(src, pm, max_len_b=10, use_cache=True)
+    assert [t.tolist() for t in ids] == [t.tolist() for t in ids_ref]
+    # (b) speech synthesis
+    RT.invalidate_shadows()
+    torch.manual_seed(3)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, **NO_DROPOUT)
+    tts_oracle = OT.T5TransformerModelOracle(OT.base_args(**over)).eval()
+    with torch.no_grad():
+        tts_oracle.speech_decoder_postnet.prob_out.bias.fill_(-2.0)
+    tts = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **over)).eval()
+    tts.load_state_dict(tts_oracle.state_dict())
+    tok = torch.randint(4, 81, (1, 7))
+    spk = torch.randn(1, 512)
+    with torch.no_grad():
+        want = tts_oracle.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9)
+    plain = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9)
+    cached = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9, use_cache=True)
+    for a, b, c in zip(plain, cached, want):
+        assert a.shape == b.shape == c.shape
+        assert rel(b, a) < 1e-4 and rel(b, c) < 1e-3
+    RT.invalidate_shadows()

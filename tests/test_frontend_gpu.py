@@ -214,3 +214,26 @@ def test_hifigan_on_device_against_the_oracle(cuda):
     got = gen(mel.to(cuda)).cpu()
     assert got.shape == want.shape == (2, 37 * 256)
     assert rel(got, want) < 3e-2
+
+
+def test_kv_cache_synthesis_equals_prefix_recomputation(cuda):
+    """speecht5_b200/incremental.py on the device: greedy speech synthesis with the key/value cache (one-row attention
+    on the row kernels over strided cache views) vs the validated prefix-recomputing path (fp32 parity mode, prenet
+    dropout off so both runs see the same numbers)."""
+    from helpers import NO_DROPOUT
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.float32
+    RT.invalidate_shadows()
+    torch.manual_seed(3)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, **NO_DROPOUT)
+    tts = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **over)).to(cuda).eval()
+    with torch.no_grad():
+        tts.speech_decoder_postnet.prob_out.bias.fill_(-2.0)
+    tok = torch.randint(4, 81, (1, 23), device=cuda)
+    spk = torch.randn(1, 512, device=cuda)
+    plain = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9)
+    cached = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9, use_cache=True)
+    for a, b in zip(plain, cached):
+        assert a.shape == b.shape and rel(b, a) < 1e-4
+    RT.dtype = torch.bfloat16
