@@ -19,10 +19,20 @@ def _gelu_grad(z):
     return 0.5 * (1 + torch.erf(z / math.sqrt(2))) + z * torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
 
 
+def _act_grad(z, act):
+    if act in ("gelu", "gelu_tanh"):
+        return _gelu_grad(z)
+    if act == "relu":
+        return (z > 0).to(z.dtype)
+    if act == "tanh":
+        return 1.0 - torch.tanh(z) ** 2
+    raise AssertionError(act)
+
+
 def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_ld=None, nb1=1, nb2=1, a_bs=(0, 0),
          b_bs=(0, 0), c_bs=(0, 0), bias=None, bias2=None, bias2_rows=0, residual=None, c_pre=None, act=None, alpha=1.0,
          accumulate=False, drop_p=0.0, seed=0, offset=0, actgrad_pre=None, actgrad_act=None):
-    assert nb2 == 1 and drop_p == 0.0 and actgrad_pre is None
+    assert nb2 == 1 and drop_p == 0.0
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a_ld = a_ld if a_ld is not None else (M if a_mn else K)
     b_ld = b_ld if b_ld is not None else (N if b_mn else K)
@@ -51,6 +61,9 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         v = torch.tanh(v)
     else:
         assert act in (None, "none")
+    if actgrad_pre is not None:  # activation backward fused into the product: v *= act'(pre[m][n])
+        pre = torch.as_strided(actgrad_pre, (nb1, M, N), (c_bs[0], c_ld, 1), actgrad_pre.storage_offset()).double()
+        v = v * _act_grad(pre, actgrad_act)
     if residual is not None:  # same layout and dtype as C, added after the activation
         assert residual.dtype == out.dtype
         v = v + torch.as_strided(residual, (nb1, M, N), (c_bs[0], c_ld, 1), residual.storage_offset()).double()
@@ -66,14 +79,24 @@ def cast_bf16(src, hi, lo=None):
 
 
 def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
-    assert drop_p == 0.0 and act in ("gelu", "gelu_tanh")
-    dpre.copy_((dy.double() * _gelu_grad(pre.double())).to(dpre.dtype))
+    assert drop_p == 0.0
+    dpre.copy_((dy.double() * _act_grad(pre.double(), act)).to(dpre.dtype))
 
 
 def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
-    assert group_rows == 0 and ld is None
-    tot = x2d.double().sum(0)
-    out.copy_(((out.double() if accumulate else 0) + tot).to(out.dtype))
+    """st5_colsum: out[g][n] (+)= sum of the rows of group g (groups of `group_rows` consecutive rows; 0 = one group)."""
+    rows, cols = x2d.shape
+    assert ld is None or rows <= 1 or ld == x2d.stride(0)
+    xs = x2d.double()
+    if group_rows and group_rows > 0:
+        ng = (rows + group_rows - 1) // group_rows
+        padded = torch.zeros((ng * group_rows, cols), dtype=torch.float64)
+        padded[:rows] = xs
+        tot = padded.view(ng, group_rows, cols).sum(1)
+    else:
+        tot = xs.sum(0)
+    flat = out.reshape(-1)
+    flat.copy_(((flat.double() if accumulate else 0) + tot.reshape(-1)).to(out.dtype))
 
 
 def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
@@ -154,6 +177,46 @@ def bn_fwd(x, x_ld, gamma, beta, running_mean, running_var, save_mean, save_rstd
     y.copy_(out.reshape(y.shape).to(y.dtype))
     save_mean.copy_(mu.float())
     save_rstd.copy_(rs.float())
+
+
+def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, stride, act):
+    """st5_conv0_gn_gelu_bwd via autograd on the torch statement of the layer; dw / dgamma / dbeta accumulate."""
+    w_, g_, b_ = (t.double().clone().requires_grad_() for t in (w, gamma, beta))
+    with torch.enable_grad():
+        v = torch.nn.functional.conv1d(wave.double()[:, None], w_[:, None], stride=stride)
+        y = torch.nn.functional.gelu(torch.nn.functional.group_norm(v, w.shape[0], g_, b_, 1e-5)).transpose(1, 2)
+        gw, gg, gb = torch.autograd.grad(y, (w_, g_, b_), dy.double())
+    dw.add_(gw.float())
+    dgamma.add_(gg.float())
+    dbeta.add_(gb.float())
+
+
+def residual_layer_norm(x, residual, ln, drop_p=0.0):
+    """ops.residual_layer_norm as differentiable torch ops (for CPU checks of whole training steps)."""
+    assert drop_p == 0.0
+    s_ = x if residual is None else x + residual
+    return torch.nn.functional.layer_norm(s_.float(), (s_.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
+
+
+def scaled_posenc(pe, alpha, drop_p, tokens=None, emb=None, padding_idx=None, x=None):
+    """ops.scaled_posenc as differentiable torch ops."""
+    assert drop_p == 0.0
+    base = torch.nn.functional.embedding(tokens, emb, padding_idx) if tokens is not None else x
+    T = base.shape[1]
+    from speecht5_b200.ops import RT
+    return (base.float() + alpha * pe[:T][None]).to(RT.dtype)
+
+
+def install_autograd(monkeypatch):
+    """install() plus differentiable torch stand-ins for the ops whose backward kernels are not emulated (LayerNorm,
+    embedding + positions; the emulated attention is already plain torch): whole training steps can then be
+    back-propagated on the CPU, with LinearFn / FFNFn / the front-end Functions still running their own backward
+    compositions on the emulated GEMM."""
+    install(monkeypatch)
+    from speecht5_b200 import kernels as K, ops
+    monkeypatch.setattr(K, "conv0_gn_gelu_bwd", conv0_gn_gelu_bwd)
+    monkeypatch.setattr(ops, "residual_layer_norm", residual_layer_norm)
+    monkeypatch.setattr(ops, "scaled_posenc", scaled_posenc)
 
 
 def install(monkeypatch):

@@ -339,3 +339,58 @@ def test_kv_cache_decoding_equals_prefix_recomputation_on_emulated_kernels(monke
         assert a.shape == b.shape == c.shape
         assert rel(b, a) < 1e-4 and rel(b, c) < 1e-3
     RT.invalidate_shadows()
+
+
+def test_speech_to_text_training_step_gradients_on_emulated_kernels(monkeypatch):
+    """One s2t update (CE + CTC through the speecht5 criterion) back-propagated on the CPU: LinearFn / FFNFn / the
+    front-end autograd Functions run their own backward compositions on the emulated GEMM (LayerNorm, embedding and
+    attention are differentiable torch stand-ins); loss and parameter gradients against oracle asr_loss."""
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install_autograd(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    torch.manual_seed(4)
+    over = dict(encoder_layers=1, decoder_layers=1, bert_init=True, dropout=0.0, attention_dropout=0.0,
+                activation_dropout=0.0, encoder_layerdrop=0.0, decoder_layerdrop=0.0, mask_prob=0.0,
+                feature_grad_mult=1.0)
+    oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).train()
+    model = T5TransformerModel.build_model(make_args(
+        "t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
+        use_sinc_pos=True, **over)).train()
+    sd = dict(oracle.state_dict())
+    for a, b in (("pos_conv_g", "pos_conv.0.weight_g"), ("pos_conv_v", "pos_conv.0.weight_v"),
+                 ("pos_conv_bias", "pos_conv.0.bias")):
+        sd["speech_encoder_prenet." + b] = sd.pop("speech_encoder_prenet." + a)
+    model.load_state_dict(sd)
+    s = O.synthetic_asr_batch(2, 5000, 7, seed=3)
+    want, _, _, _ = O.asr_loss(oracle, s, ce_weight=0.5, ctc_weight=0.5, label_smoothing=0.1)
+    want.backward()
+    sample = dict(s, task_name="s2t")
+    loss, _, log = SpeechT5Criterion(None, label_smoothing=0.1, ce_weight=0.5, ctc_weight=0.5)(model, sample)
+    assert abs(loss.item() - want.item()) < 2e-4 * abs(want.item()), (loss.item(), want.item(), log)
+    loss.backward()
+    ref, got = dict(oracle.named_parameters()), dict(model.named_parameters())
+    rename = {"speech_encoder_prenet.pos_conv.0.weight_g": "speech_encoder_prenet.pos_conv_g",
+              "speech_encoder_prenet.pos_conv.0.weight_v": "speech_encoder_prenet.pos_conv_v",
+              "speech_encoder_prenet.pos_conv.0.bias": "speech_encoder_prenet.pos_conv_bias"}
+    checked = 0
+    for name, p in got.items():
+        r = ref.get(rename.get(name, name))
+        if r is None or r.grad is None or p.grad is None or float(r.grad.norm()) == 0.0:
+            continue
+        if name.endswith("k_proj.bias"):  # a key bias shifts every score of a row equally: its gradient is rounding noise
+            continue
+        err = ((p.grad.double() - r.grad.double()).norm() / r.grad.double().norm()).item()
+        assert err < 2e-3, (name, err)
+        checked += 1
+    assert checked > 40
+    for must in ("speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight",
+                 "speech_encoder_prenet.feature_extractor.conv_layers.4.0.weight",
+                 "speech_encoder_prenet.pos_conv.0.weight_v", "speech_encoder_prenet.mask_emb", "encoder.proj.weight"):
+        assert got[must].grad is not None or ref[rename.get(must, must)].grad is None, must
+    RT.invalidate_shadows()
