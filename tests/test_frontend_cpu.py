@@ -394,3 +394,42 @@ def test_speech_to_text_training_step_gradients_on_emulated_kernels(monkeypatch)
                  "speech_encoder_prenet.pos_conv.0.weight_v", "speech_encoder_prenet.mask_emb", "encoder.proj.weight"):
         assert got[must].grad is not None or ref[rename.get(must, must)].grad is None, must
     RT.invalidate_shadows()
+
+
+def test_text_to_speech_training_step_on_emulated_kernels_matches_the_golden_gradients(monkeypatch):
+    """Default-path regression guard including the backward: the t2s update (TexttoSpeechLoss with guided attention)
+    on emulated kernels reproduces the golden fixture's loss terms and parameter gradients; LinearFn, FFNFn and
+    Conv1dK5Fn run their own backward compositions on the emulated GEMM."""
+    import os
+    import torch.nn.functional as F
+    from helpers import NO_DROPOUT, TINY, load_golden, rel
+    from speecht5_b200 import ops
+    from speecht5_b200.criterions import TexttoSpeechLoss
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install_autograd(monkeypatch)
+
+    def batch_norm_act(x, bn, training, act=None, drop_p=0.0):
+        assert drop_p == 0.0 and training
+        y = F.batch_norm(x.float().reshape(-1, x.shape[-1]), None, None, bn.weight, bn.bias, True, 0.0, bn.eps)
+        y = torch.tanh(y) if act == "tanh" else y
+        return y.reshape(x.shape).to(x.dtype)
+    monkeypatch.setattr(ops, "batch_norm_act", batch_norm_act)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    RT.invalidate_shadows()
+    state, sample, out_ref, loss_ref, grads_ref = load_golden(
+        os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    model = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **TINY, **NO_DROPOUT, bert_init=True))
+    model.train()
+    model.load_state_dict(state)
+    crit = TexttoSpeechLoss(None, use_guided_attn_loss=True)
+    out = model(**sample["net_input"])
+    loss, l1, l2, bce, ga = crit.compute_loss(model, out, sample)
+    got = torch.stack([loss, l1, l2, bce, ga]).detach().double()
+    assert ((got - loss_ref).abs() / loss_ref.abs()).max().item() < 3e-4
+    loss.backward()
+    params = dict(model.named_parameters())
+    for name, g in grads_ref.items():
+        assert params[name].grad is not None, name
+        assert rel(params[name].grad, g) < 2e-3, name
+    RT.invalidate_shadows()
