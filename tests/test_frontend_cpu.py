@@ -433,3 +433,57 @@ def test_text_to_speech_training_step_on_emulated_kernels_matches_the_golden_gra
         assert params[name].grad is not None, name
         assert rel(params[name].grad, g) < 2e-3, name
     RT.invalidate_shadows()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pretraining_head_and_quantizer_on_emulated_kernels(monkeypatch, dtype):
+    """speecht5_b200/pretrain.py (projections through ops.linear on the emulated GEMM) against oracle/pretrain_oracle.py
+    with the same weights, masks, Gumbel noise and time permutation: NCE logits of the masked / unmasked frames, the
+    quantizer's codes, perplexities, the mixed encoder states, and the gradients that reach the projections."""
+    from oracle import pretrain_oracle as P
+    from speecht5_b200 import pretrain
+    from speecht5_b200.ops import RT
+    gemm_emulator.install_autograd(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", dtype)
+    RT.invalidate_shadows()
+    torch.manual_seed(5)
+    B, T, d = 2, 12, 64
+    tol = 2e-4 if dtype == torch.float32 else 4e-2
+    x = torch.randn(B, T, d)
+    pm = torch.zeros(B, T, dtype=torch.bool)
+    pm[1, 9:] = True
+    mi = torch.rand(B, T) < 0.4
+    targets = [torch.randint(0, 17, (B, T))]
+    ref_h = P.SpeechEncoderPostnet([17], encoder_embed_dim=d, final_dim=32)
+    mine_h = pretrain.SpeechEncoderPostnet([17], encoder_embed_dim=d, final_dim=32)
+    mine_h.load_state_dict(ref_h.state_dict())
+    xr = x.clone().requires_grad_()
+    xm = x.to(dtype).requires_grad_()
+    out_r, out_m = ref_h(xr, pm, mi, targets), mine_h(xm, pm, mi, targets)
+    def fin(t):  # the class equal to the positive is -inf by construction (compute_nce): compare the finite entries
+        return torch.where(torch.isfinite(t), t, torch.zeros_like(t))
+    for key in ("logit_m_list", "logit_u_list"):
+        a, b = out_m[key][0].float(), out_r[key][0]
+        assert a.shape == b.shape and torch.equal(torch.isfinite(a), torch.isfinite(b))
+        assert (torch.isinf(b).sum(1) == 1).all()
+        assert ((fin(a) - fin(b)).norm() / fin(b).norm()).item() < tol
+    (fin(out_r["logit_m_list"][0]).sum() + fin(out_r["logit_u_list"][0]).square().sum()).backward()
+    (fin(out_m["logit_m_list"][0].float()).sum() + fin(out_m["logit_u_list"][0].float()).square().sum()).backward()
+    gw_r, gw_m = ref_h.final_proj.weight.grad, mine_h.final_proj.weight.grad
+    assert ((gw_m - gw_r).norm() / gw_r.norm()).item() < max(tol, 2e-3)
+    # quantizer (training mode, injected noise) + code mixing
+    ref_q = P.GumbelVectorQuantizer(dim=d, num_vars=10, groups=2, vq_dim=d).train()
+    mine_q = pretrain.GumbelVectorQuantizer(dim=d, num_vars=10, groups=2, vq_dim=d).train()
+    mine_q.load_state_dict(ref_q.state_dict())
+    noise = -torch.empty(B * T * 2, 10).exponential_().log()
+    qr, qm = ref_q(x, noise), mine_q(x.to(dtype), noise)
+    if dtype == torch.float32:  # identical code choices, hence identical vectors
+        assert ((qm["x"].float() - qr["x"]).norm() / qr["x"].norm()).item() < 1e-5
+        assert abs(float(qm["prob_perplexity"]) - float(qr["prob_perplexity"])) < 1e-3
+        assert float(qm["code_perplexity"]) == float(qr["code_perplexity"])
+    assert qm["num_vars"] == 20 and qm["x"].shape == (B, T, d)
+    perm = torch.randperm(T)
+    mixed_r = P.mix_codes(x, qr["x"], 0.5, perm)
+    mixed_m = pretrain.mix_codes(x, qr["x"], 0.5, perm)
+    assert torch.equal(mixed_m, mixed_r)
+    RT.invalidate_shadows()
