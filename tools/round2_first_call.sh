@@ -24,12 +24,13 @@ run pair_check 300 python tools/check_gemm_pair.py
 run bench_single 400 python bench.py --steps 20 --warmup 5
 ST5_GEMM_PAIR=1 run bench_pair 400 python bench.py --steps 20 --warmup 5
 ST5_GEMM_PAIR=2 run bench_pair5 400 python bench.py --steps 20 --warmup 5   # same kernel, 5-stage operand ring
-# 5. launch list of the faster of the two is taken in a follow-up call (ncu replays are slow); summary:
+# 6. launch list of the faster of the two is taken in a follow-up call (ncu replays are slow); summary:
 echo "==== summary"
 for f in pytest_gpu gated_unfused gated_t2t gated_conv0 gated_frontend; do
   echo "$f: $(grep -E 'passed|failed|error' $OUT/$f.log | tail -1) $(tail -1 $OUT/$f.log)"
 done
 grep -E "PAIR GEMM|shape [0-9]+: single" $OUT/pair_check.log | tail -14
+head -12 gpurun_out/glue_profile.txt 2>/dev/null
 for f in bench_single bench_pair bench_pair5; do
   python - "$OUT/$f.log" <<'PY'
 import json, sys
