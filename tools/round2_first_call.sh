@@ -18,7 +18,8 @@ ST5_TEST_UNFUSED=1 run gated_unfused 120 python -m pytest tests/test_a_ops_gpu.p
 ST5_TEST_T2T=1 run gated_t2t 120 python -m pytest tests/test_model_gpu.py -k text_to_text -q
 ST5_TEST_CONV0=1 run gated_conv0 120 python -m pytest tests/test_a_ops_gpu.py -k conv0 -q
 ST5_TEST_FRONTEND=1 run gated_frontend 900 python -m pytest tests/test_frontend_gpu.py -q   # no -x: every draft gets its verdict
-# 3. CTA-pair GEMM: bit-exactness against the single-CTA kernel + per-shape timings of both
+# 3. CTA-pair GEMM: bit-exactness against the single-CTA kernel + per-shape timings of both (what the ST5_TEST_PAIR
+#    test wraps)
 run pair_check 300 python tools/check_gemm_pair.py
 # 4. the step with and without the pair GEMM (same box, back to back)
 run bench_single 400 python bench.py --steps 20 --warmup 5
