@@ -62,6 +62,12 @@ class _Dict:
     def pad(self):
         return self._pad
 
+    def eos(self):
+        return 2
+
+    def unk(self):
+        return 3
+
 
 @register_model("t5_transformer")
 class T5TransformerModel(FairseqEncoderDecoderModel):

@@ -67,6 +67,14 @@ class SpeechT5Task(LegacyFairseqTask):
     def setup_task(cls, args, **kwargs):
         return cls(args)
 
+    @property
+    def target_dictionary(self):  # tasks/speecht5.py:573-579
+        return self.dicts["text"]
+
+    @property
+    def source_dictionary(self):
+        return None
+
     def build_model(self, args):
         args.speech_odim = 80  # tasks/speecht5.py:581-597
         return T5TransformerModel.build_model(args, self)
