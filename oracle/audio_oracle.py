@@ -149,3 +149,27 @@ def hifigan_to_hf_state(sd, cfg=None):
                 m[f"resblocks.{r}.convs1.{j}.{wb}"] = sd[f"resblocks.{r}.convs1.{j}.{wb}"]
                 m[f"resblocks.{r}.convs2.{j}.{wb}"] = sd[f"resblocks.{r}.convs2.{j}.{wb}"]
     return m
+
+
+def fold_weight_norm(sd):
+    """torch.nn.utils.weight_norm (dim 0) as the reference generator applies it to every conv (hifigan.py:116-150):
+    weight = g * v / ||v||, the norm taken over all dims but the first. Returns a plain {.weight, .bias} state dict."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith("weight_g"):
+            base = k[: -len("weight_g")]
+            wv = sd[base + "weight_v"]
+            norm = wv.reshape(wv.size(0), -1).norm(dim=1).view(-1, *([1] * (wv.dim() - 1)))
+            out[base + "weight"] = v * wv / norm
+        elif not k.endswith("weight_v"):
+            out[k] = v
+    return out
+
+
+def load_reference_hifigan_state(gen, sd):
+    """Load a state dict of the reference's weight-normed Generator into the folded-weight oracle."""
+    folded = fold_weight_norm(sd)
+    folded.setdefault("mean", gen.mean)
+    folded.setdefault("scale", gen.scale)
+    gen.load_state_dict(folded)
+    return gen

@@ -442,3 +442,18 @@ class T5TransformerModelT2TOracle(nn.Module):
         dec_in, tgt_mask = self.text_decoder_prenet(prev_output_tokens)
         decoder_output, _ = self.decoder(dec_in, tgt_mask, encoder_output, alignment_layer=None)
         return (self.text_decoder_postnet(decoder_output), None), {}, encoder_output
+
+
+def reference_to_oracle_keys(sd):
+    """Rename a state dict of the REFERENCE model (checkpoint key layout) to this oracle's few differing names:
+    the weight-normed positional conv lives at `pos_conv.0.{weight_g,weight_v,bias}` in the reference
+    (speech_encoder_prenet.py:105-119) and the layer_norm-mode extractor wraps its norm as
+    Sequential(TransposeLast, Fp32LayerNorm, TransposeLast) -> `conv_layers.{i}.2.1.*` (:308-318)."""
+    import re
+    out = {}
+    for k, v in sd.items():
+        k = k.replace("pos_conv.0.weight_g", "pos_conv_g").replace("pos_conv.0.weight_v", "pos_conv_v")
+        k = k.replace("pos_conv.0.bias", "pos_conv_bias")
+        k = re.sub(r"(conv_layers\.\d+\.2)\.1\.", r"\1.", k)
+        out[k] = v
+    return out

@@ -254,11 +254,8 @@ def test_tensor_core_attention_matches_row_kernels_with_dropout(cuda, case):
     g = torch.randn(B, Tq, d, device=cuda).to(torch.bfloat16)
     res = []
     # (tensor core, fused): fused tcgen05 kernels / unfused tensor-core path (batched GEMMs + row kernels: the fallback
-    # for clipped relative positions and long sequences) / exact row kernels. The middle mode is opt-in until it has
-    # been re-confirmed on hardware after the dropout-pitch change (ST5_TEST_UNFUSED=1).
-    modes = [(True, True), (False, True)]
-    if os.environ.get("ST5_TEST_UNFUSED") == "1":
-        modes.insert(1, (True, False))
+    # for clipped relative positions and long sequences) / exact row kernels.
+    modes = [(True, True), (True, False), (False, True)]
     for tc, fused in modes:
         ops.RT.attn_tensor_core = tc
         ops.RT.attn_fused = fused
@@ -328,8 +325,6 @@ def test_fused_attention_forward_and_backward(cuda, case):
         assert rel(qkv.grad, torch.cat([flat(q.grad), flat(k.grad), flat(v.grad)], -1)) < 3e-2
 
 
-@pytest.mark.skipif(os.environ.get("ST5_TEST_PAIR") != "1",
-                    reason="experimental CTA-pair GEMM (ST5_GEMM_PAIR=1), not yet measured on the GPU: opt-in")
 def test_cta_pair_gemm_is_bit_identical_to_the_single_cta_kernel(cuda):
     """tools/check_gemm_pair.py: every GEMM class of the step through the 256 x 256 cta_group::2 variant, compared bit
     for bit with the default kernel (same fp32 accumulation order per output element)."""
@@ -341,8 +336,6 @@ def test_cta_pair_gemm_is_bit_identical_to_the_single_cta_kernel(cuda):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.skipif(os.environ.get("ST5_TEST_CONV0") != "1",
-                    reason="fused conv0 + GroupNorm + GELU front-end kernel: written without GPU time, opt-in until run")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv0_groupnorm_gelu_against_the_oracle_layer(cuda, dtype):
     """csrc/conv_frontend.cu vs layer 0 of oracle ConvFeatureExtractionModel (mode "default"): forward activations and

@@ -1,13 +1,12 @@
-"""-m gpu, OPT-IN (ST5_TEST_FRONTEND=1): the speech-input front end (speecht5_b200/frontend.py + csrc/conv_frontend.cu)
-against oracle/speecht5_oracle_asr.py. These kernels and compositions were written at the end of round 1 without GPU
-time; the gate comes off once they have run green on a B200."""
+"""-m gpu: the speech-input front end (speecht5_b200/frontend.py + csrc/conv_frontend.cu), CE + CTC criterion, greedy
+decoding, KV cache, log-mel, HiFi-GAN and the pre-training extras against the oracles (first green run on a B200:
+round 2, gpurun_out/r2_first/gated_frontend.log; the opt-in gate of round 1 is gone)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ST5_TEST_FRONTEND") != "1", reason="opt-in until first validated run")]
+pytestmark = [pytest.mark.gpu]
 
 
 def rel(a, b):

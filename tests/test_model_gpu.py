@@ -203,8 +203,6 @@ def test_large_style_pre_layernorm_against_oracle(cuda, dtype, tol):
         assert rel(got[n].grad, ref[n].grad) < gtol, (n, rel(got[n].grad, ref[n].grad))
 
 
-@pytest.mark.skipif(os.environ.get("ST5_TEST_T2T") != "1",
-                    reason="opt-in branch (--build-text-decoder) not yet confirmed on a B200: run with ST5_TEST_T2T=1")
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, MEL_TOL), (torch.bfloat16, 6e-2)])
 def test_text_to_text_branch_against_oracle(cuda, dtype, tol):
     """SURVEY 8a rows 9 + 14 on the CUDA path (opt-in --build-text-decoder): text decoder prenet (embedding + fairseq

@@ -1,0 +1,273 @@
+"""Pins the oracle restatements against the REFERENCE'S OWN CODE.
+
+Two layers:
+* fixtures `tests/golden/ref_*.npz` were produced by `/root/reference/SpeechT5/speecht5/**` itself (unmodified, loaded by
+  `oracle/ref_loader.py`; generator `tests/golden/make_golden_from_ref.py`): weights, inputs, outputs, the reference
+  criterions' loss terms, gradients, its SequenceGenerator's token ids, its compute_mask_indices draws. The oracle is
+  replayed on the stored weights + inputs and must agree to fp32 round-off (tolerances in each test). These run
+  everywhere (no reference tree needed).
+* when the reference tree is mounted (build container), the fixtures are regenerated in memory and must be identical to
+  the committed ones (stale-fixture guard), and the reference runs at real width / long sequences against the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLD)
+import make_golden_from_ref as mg  # noqa: E402  (constants + case builders; touches the reference only inside cases)
+from oracle import ref_loader as rl  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not rl.available(), reason="reference tree not mounted (GPU box): fixtures only")
+FP32 = 2e-5   # relative L2, fp32 forward of a 2+2-layer model: different summation orders only
+GRAD = 2e-4   # relative L2 of fp32 gradients
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def state_of(blob, prefix="state/"):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith(prefix)}
+
+
+def conv_layers():
+    return eval(mg.TINY_CONV)
+
+
+# ------------------------------------------------------------------------------------------------------------------ t2s
+@pytest.mark.parametrize("name,pre_ln", [("ref_tts_tiny", False), ("ref_tts_preln_tiny", True)])
+def test_tts_oracle_matches_reference_outputs_loss_and_gradients(name, pre_ln):
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args, tts_loss
+    blob = load(name)
+    over = dict(mg.TINY)
+    if pre_ln:
+        over.update(layer_norm_first=True, decoder_normalize_before=True)
+    model = T5TransformerModelOracle(base_args(**over)).train()
+    missing = model.load_state_dict(state_of(blob), strict=False)
+    assert not missing.unexpected_keys and all("num_batches_tracked" in k for k in missing.missing_keys), missing
+    ni = {k[3:]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("in/")}
+    out = model(**ni, task_name="t2s")
+    assert rel(out[0], blob["out/before"]) < FP32
+    assert rel(out[1], blob["out/after"]) < FP32
+    assert rel(out[2], blob["out/logits"]) < FP32
+    assert rel(torch.stack(out[3]), blob["out/attn"]) < FP32
+    sample = {k[7:]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("sample/")}
+    loss, l1, l2, bce, ga = tts_loss(out, sample)
+    got = np.array([loss.item(), l1.item(), l2.item(), bce.item(), ga.item()])
+    np.testing.assert_allclose(got, blob["loss"], rtol=2e-5)
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, v in blob.items():
+        if k.startswith("grad/"):
+            assert rel(named[k[5:]].grad, v) < GRAD, (k, rel(named[k[5:]].grad, v))
+
+
+# ------------------------------------------------------------------------------------------------------------------ s2t
+def _asr_oracle(blob, ln_mode):
+    from oracle.speecht5_oracle_asr import T5TransformerModelASROracle, base_asr_args, reference_to_oracle_keys
+    over = dict(mg.TINY, conv_feature_layers=conv_layers(), feature_grad_mult=1.0, conv_pos=16, conv_pos_groups=4,
+                dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)
+    if ln_mode:
+        over.update(extractor_mode="layer_norm", layer_norm_first=True, decoder_normalize_before=True, conv_bias=True,
+                    share_input_output_embed=True)
+    model = T5TransformerModelASROracle(base_asr_args(**over), vocab_size=mg.VOCAB).train()
+    missing = model.load_state_dict(reference_to_oracle_keys(state_of(blob)), strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    assert all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing.missing_keys
+    return model
+
+
+@pytest.mark.parametrize("name,ln_mode", [("ref_asr_tiny", False), ("ref_asr_ln_tiny", True)])
+def test_asr_oracle_matches_reference_outputs_loss_and_gradients(name, ln_mode):
+    """Conv feature extractor (GroupNorm / LayerNorm modes), speech prenet with the reference's OWN mask draws, encoder +
+    CTC head, text decoder pre/post-net; SpeechtoTextLoss CE + CTC; gradients down to conv layer 0."""
+    from oracle.speecht5_oracle_asr import asr_loss, reference_to_oracle_keys
+    blob = load(name)
+    model = _asr_oracle(blob, ln_mode)
+    ni = dict(source=torch.from_numpy(blob["in/source"]), padding_mask=torch.from_numpy(blob["in/padding_mask"]),
+              prev_output_tokens=torch.from_numpy(blob["in/prev_output_tokens"]),
+              mask_indices=torch.from_numpy(blob["in/mask_indices"]),
+              mask_channel_indices=torch.from_numpy(blob["in/mask_channel_indices"]))
+    sample = {"net_input": ni, "target": torch.from_numpy(blob["sample/target"]),
+              "target_lengths": torch.from_numpy(blob["sample/target_lengths"])}
+    (logits, _), enc = model(**ni)
+    assert rel(enc["encoder_out"][0], blob["out/encoder_out"]) < FP32
+    assert rel(enc["encoder_out_for_ctc"][0], blob["out/encoder_out_for_ctc"]) < FP32
+    assert torch.equal(enc["encoder_padding_mask"][0], torch.from_numpy(blob["out/encoder_padding_mask"]))
+    assert rel(logits, blob["out/logits"]) < FP32
+    loss, ce, ctc, _ = asr_loss(model, sample, ce_weight=0.5, ctc_weight=0.5, label_smoothing=0.1, blank_idx=mg.VOCAB - 1)
+    np.testing.assert_allclose([loss.item(), ce.item(), ctc.item()], blob["loss"][:3], rtol=2e-5)
+    loss.backward()
+    named = dict(model.named_parameters())
+    n = 0
+    for k, v in reference_to_oracle_keys({k[5:]: v for k, v in blob.items() if k.startswith("grad/")}).items():
+        assert rel(named[k].grad, v) < GRAD, (k, rel(named[k].grad, v))
+        n += 1
+    assert n >= 8
+
+
+@pytest.mark.parametrize("name,ln_mode", [("ref_asr_tiny", False), ("ref_asr_ln_tiny", True)])
+def test_oracle_greedy_token_ids_equal_the_reference_sequence_generator(name, ln_mode):
+    """north_star: bit-exact token ids for ASR greedy decode. The reference side is speecht5/sequence_generator.py itself
+    (beam 1, max_len_b 12), stored in the fixture."""
+    from oracle.speecht5_oracle_asr import greedy_decode
+    blob = load(name)
+    model = _asr_oracle(blob, ln_mode).eval()
+    hyp = greedy_decode(model, torch.from_numpy(blob["in/source"]), torch.from_numpy(blob["in/padding_mask"]),
+                        max_len_b=12, blank=mg.VOCAB - 1, mask_idx=mg.VOCAB - 2)
+    for b, t in enumerate(hyp):
+        n = int(blob["out/greedy_lengths"][b])
+        assert t.tolist() == blob["out/greedy_tokens"][b, :n].tolist(), (b, t.tolist())
+
+
+def test_t2t_oracle_matches_reference():
+    from oracle.speecht5_oracle_asr import T5TransformerModelT2TOracle, base_asr_args
+    blob = load("ref_t2t_tiny")
+    over = dict(mg.TINY, share_input_output_embed=True, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)
+    model = T5TransformerModelT2TOracle(base_asr_args(**over), vocab_size=mg.VOCAB).train()
+    missing = model.load_state_dict(state_of(blob), strict=False)
+    assert not missing.missing_keys, missing.missing_keys
+    out = model(src_tokens=torch.from_numpy(blob["in/src_tokens"]),
+                prev_output_tokens=torch.from_numpy(blob["in/prev_output_tokens"]))
+    assert rel(out[0][0], blob["out/logits"]) < FP32
+    assert rel(out[2]["encoder_out"][0], blob["out/encoder_out"]) < FP32
+
+
+# ------------------------------------------------------------------------------------------------------------ audio ends
+def test_hifigan_oracle_matches_the_reference_generator():
+    """SpeechUT/fairseq/.../hifigan.py Generator -> oracle.audio_oracle.HifiGanGenerator on the same weights."""
+    from oracle.audio_oracle import HifiGanGenerator
+    blob = load("ref_hifigan_tiny")
+    cfg = dict(model_in_dim=80, upsample_initial_channel=32, upsample_rates=[4, 4, 4, 4],
+               upsample_kernel_sizes=[8, 8, 8, 8], resblock_kernel_sizes=[3, 7, 11],
+               resblock_dilation_sizes=[[1, 3, 5]] * 3)
+    gen = HifiGanGenerator(cfg).eval()
+    from oracle.audio_oracle import load_reference_hifigan_state
+    load_reference_hifigan_state(gen, state_of(blob))
+    with torch.no_grad():
+        y = gen(torch.from_numpy(blob["in/mel"]).transpose(1, 2), normalize_before=False)
+    ref = torch.from_numpy(blob["out/wav"]).squeeze(1)
+    assert rel(y, ref) < 5e-5, rel(y, ref)
+
+
+def test_pretrain_oracles_match_reference_quantizer_and_hubert_head():
+    from oracle.pretrain_oracle import GumbelVectorQuantizer, SpeechEncoderPostnet
+    blob = load("ref_pretrain_tiny")
+    vq = GumbelVectorQuantizer(dim=64, num_vars=10, groups=2, vq_dim=64).eval()
+    sd = state_of(blob, "vq/state/")
+    vq.load_state_dict({"vars": sd["vars"], "weight_proj.weight": sd["weight_proj.weight"],
+                        "weight_proj.bias": sd["weight_proj.bias"]})
+    with torch.no_grad():
+        r = vq(torch.from_numpy(blob["vq/in"]))
+    assert rel(r["x"], blob["vq/x"]) < 1e-6
+    assert abs(r["code_perplexity"].item() - float(blob["vq/code_perplexity"])) < 1e-4
+    assert abs(r["prob_perplexity"].item() - float(blob["vq/prob_perplexity"])) < 1e-4
+    head = SpeechEncoderPostnet([20], encoder_embed_dim=64, final_dim=16, untie_final_proj=True).train()
+    head.load_state_dict(state_of(blob, "head/state/"))
+    out = head(torch.from_numpy(blob["head/in/x"]), torch.from_numpy(blob["head/in/padding_mask"]),
+               torch.from_numpy(blob["head/in/mask_indices"]), [torch.from_numpy(blob["head/in/target"])])
+    for got, want in ((out["logit_m_list"][0], blob["head/logit_m"]), (out["logit_u_list"][0], blob["head/logit_u"])):
+        want = torch.from_numpy(want)
+        assert torch.equal(torch.isinf(got), torch.isinf(want))  # a negative equal to the positive is -inf (:61-74)
+        fin = ~torch.isinf(want)
+        assert rel(got[fin], want[fin]) < 1e-5
+
+
+def test_host_mask_sampler_reproduces_the_reference_draws():
+    """speecht5_b200/data.py compute_mask_indices (host logic of the product) == fairseq/data/data_utils.py:393-520 under
+    the same numpy seed: the draw ORDER matters, so this is bit-exact."""
+    from speecht5_b200.data import compute_mask_indices
+    blob = load("ref_masks")
+    pad = torch.from_numpy(blob["padding_mask"])
+    for i in range(4):
+        seed, prob, length = blob[f"cfg/{i}"]
+        np.random.seed(int(seed))
+        m = compute_mask_indices((4, 120), pad, float(prob), int(length), "static", 0.0, min_masks=2)
+        c = compute_mask_indices((4, 64), None, 0.5, 16, "static", 0.0)
+        assert np.array_equal(np.asarray(m), blob[f"time/{i}"]), i
+        assert np.array_equal(np.asarray(c), blob[f"chan/{i}"]), i
+
+
+# ------------------------------------------------------------------------------------------- live reference (container)
+@needs_ref
+@pytest.mark.parametrize("name", sorted(mg.CASES))
+def test_committed_fixture_is_what_the_reference_produces_now(name):
+    fresh = mg.CASES[name]()
+    stored = load(name)
+    assert set(fresh) == set(stored)
+    for k in fresh:
+        a, b = np.asarray(fresh[k]), stored[k]
+        if a.dtype.kind in "biu":
+            assert np.array_equal(a, b), k
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@needs_ref
+@pytest.mark.parametrize("T", [199, 499])
+def test_reference_encoder_at_asr_lengths_matches_oracle(T):
+    """`TransformerEncoder.forward` of the reference at T = 199 / 499 (relative positions clipped at
+    +-160, key padding) against the oracle encoder, Base width, 2 layers."""
+    from argparse import Namespace
+    from oracle.speecht5_oracle import TransformerEncoder, base_args
+    ns = rl.load()
+    over = dict(encoder_layers=2, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, encoder_layerdrop=0.0)
+    rargs = rl.reference_args(**over)
+    torch.manual_seed(3)
+    enc_ref = ns.encoder.TransformerEncoder(rargs, rl.RefDictionary(mg.VOCAB), None).eval()
+    oargs = base_args(**over)
+    enc = TransformerEncoder(oargs, mg.VOCAB, None).eval()
+    enc.load_state_dict(enc_ref.state_dict())
+    x = torch.randn(2, T, 768, generator=torch.Generator().manual_seed(1))
+    pad = torch.zeros(2, T, dtype=torch.bool)
+    pad[1, T - 37:] = True
+    with torch.no_grad():
+        a = enc_ref(x, pad)
+        b = enc(x, pad)
+    assert rel(b["encoder_out"][0], a["encoder_out"][0]) < 1e-5
+    assert rel(b["encoder_out_for_ctc"][0], a["encoder_out_for_ctc"][0]) < 1e-5
+
+
+@needs_ref
+def test_reference_conv_feature_extractor_real_width_matches_oracle():
+    """ConvFeatureExtractionModel (speech_encoder_prenet.py:277-374) at the real 512 channels, both modes, 1 s of audio."""
+    from oracle.speecht5_oracle_asr import CONV_FEATURE_LAYERS, ConvFeatureExtractionModel, reference_to_oracle_keys
+    ns = rl.load()
+    x = torch.randn(2, 16000, generator=torch.Generator().manual_seed(1)) * 0.1
+    for mode in ("default", "layer_norm"):
+        torch.manual_seed(5)
+        ref = ns.speech_encoder_prenet.ConvFeatureExtractionModel(CONV_FEATURE_LAYERS, 0.0, mode, False).eval()
+        orc = ConvFeatureExtractionModel(CONV_FEATURE_LAYERS, mode, False).eval()
+        orc.load_state_dict(reference_to_oracle_keys(ref.state_dict()))
+        with torch.no_grad():
+            assert rel(orc(x), ref(x)) < 1e-5, mode
+
+
+@needs_ref
+def test_reference_generate_speech_matches_oracle_autoregressive_synthesis():
+    """`T5TransformerModel.generate_speech` (models/speecht5.py:1188-1249; its always-on prenet dropout disabled with
+    dprenet_dropout_rate 0) against the oracle's synthesis loop: same number of frames, same mel."""
+    from oracle.speecht5_oracle import T5TransformerModelOracle, base_args
+    over = dict(mg.TINY, conv_feature_layers=mg.TINY_CONV, conv_pos=16, conv_pos_groups=4)
+    torch.manual_seed(21)
+    ref = rl.build_reference_model(rl.reference_args(**over), rl.RefTask(mg.VOCAB, "t2s")).eval()
+    orc = T5TransformerModelOracle(base_args(**mg.TINY)).eval()
+    orc.load_state_dict({k: v for k, v in ref.state_dict().items() if k in orc.state_dict()})
+    g = torch.Generator().manual_seed(2)
+    toks = torch.randint(4, 70, (1, 12), generator=g)
+    spk = torch.randn(1, 512, generator=g)
+    with torch.no_grad():
+        a = ref.generate_speech(source=None, src_tokens=toks, spkembs=spk, threshold=0.5, minlenratio=0.0, maxlenratio=2.0)
+        b = orc.generate_speech(src_tokens=toks, spkembs=spk, threshold=0.5, minlenratio=0.0, maxlenratio=2.0)
+    assert a[0].shape == b[0].shape
+    assert rel(b[0], a[0]) < 1e-4

@@ -34,7 +34,7 @@ def main():
              for p in glob.glob(os.path.join(ROOT, pat), recursive=True)]
     lens, bad, n = {}, [], 0
     for f in sorted(set(files)):
-        if os.path.basename(f) in ("SURVEY.md", "PAPERS.md", "SNIPPETS.md", "BASELINE.md"):
+        if os.path.basename(f) in ("SURVEY.md", "PAPERS.md", "SNIPPETS.md", "BASELINE.md", "VERDICT.md", "ADVICE.md"):
             continue
         for ln, line in enumerate(open(f, errors="ignore"), 1):
             for m in PAT.finditer(line):
