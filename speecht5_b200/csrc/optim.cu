@@ -48,6 +48,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   } else if (lr_dev != nullptr) {
     step_size = lr * step_size;  // host passed the bias-correction factor only
   }
+  // fairseq/trainer.py:845-858 raises FloatingPointError on a NaN / Inf gradient norm and the update is not applied;
+  // here the whole launch is a no-op (parameters, both moments and the bf16 shadow untouched) and the host reads the
+  // overflow counter when it chooses to (B200Trainer.check_overflow) -- nothing to notice it inside a graph replay.
+  if (gnorm_sq != nullptr && !(*gnorm_sq <= 3.0e38f)) return;
   float gscale = grad_mul;
   if (gnorm_sq != nullptr && max_norm > 0.f) {
     const float norm = sqrtf(*gnorm_sq) * grad_mul;

@@ -5,14 +5,36 @@ fairseq/criterions/__init__.py) and `--user-dir speecht5_b200` registers task/cr
 names."""
 import torch.nn as nn
 
+import sys as _sys
+
 try:  # pragma: no cover - exercised only where fairseq is installed
+    if "fairseq" in _sys.modules and not hasattr(_sys.modules["fairseq"], "__file__"):
+        raise ImportError("a test stub package named fairseq is loaded (oracle/ref_loader.py), not fairseq itself")
     from fairseq.models import (FairseqEncoderDecoderModel, register_model,  # noqa: F401
                                 register_model_architecture)
     from fairseq.tasks import LegacyFairseqTask, register_task  # noqa: F401
     from fairseq.criterions import FairseqCriterion, register_criterion  # noqa: F401
+    from fairseq import metrics  # noqa: F401
     HAVE_FAIRSEQ = True
 except Exception:  # noqa: BLE001
     HAVE_FAIRSEQ = False
+
+    class _Metrics:
+        """fairseq.metrics stand-in: keeps the last value per key (log_scalar) and the derived-meter callables."""
+
+        def __init__(self):
+            self.scalars, self.derived = {}, {}
+
+        def reset(self):
+            self.scalars, self.derived = {}, {}
+
+        def log_scalar(self, key, value, weight=1, priority=10, round=None):
+            self.scalars[key] = value
+
+        def log_derived(self, key, fn, priority=20):
+            self.derived[key] = fn
+
+    metrics = _Metrics()
     MODEL_REGISTRY, ARCH_MODEL_REGISTRY, ARCH_CONFIG_REGISTRY = {}, {}, {}
     TASK_REGISTRY, CRITERION_REGISTRY = {}, {}
 

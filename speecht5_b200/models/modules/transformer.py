@@ -199,12 +199,24 @@ class TransformerEncoder(nn.Module):
             if self.args.relative_position_embedding:
                 pos_k, maxpos = self.pos_emb.pe_k.weight, self.pos_emb.maxlen
         r = d = None
+        keep_dev, keep_host = RT.layer_keep, RT.layer_keep_host
         for i, layer in enumerate(self.layers):
-            dropout_probability = np.random.random()  # numpy RNG, as encoder.py:252
+            x = RT.stage(("enc", i), x)  # gradient-exchange overlap point (trainer), identity otherwise
             frozen = (not ft) and i not in self.no_freeze_encoder_layer
             with torch.no_grad() if frozen else contextlib.ExitStack():
-                if not self.training or (dropout_probability > self.encoder_layerdrop) or i == self.unb_enc_layer:
-                    x, _ = layer(x, self_attn_padding_mask=encoder_padding_mask, pos_bias=pos_k, maxpos=maxpos)
+                if self.training and keep_dev is not None:
+                    # LayerDrop under CUDA-graph capture: the trainer drew the subset (same numpy stream as :252); a
+                    # dropped layer's output is replaced by its input, its parameters receive exactly zero gradient
+                    y, _ = layer(x, self_attn_padding_mask=encoder_padding_mask, pos_bias=pos_k, maxpos=maxpos)
+                    x = torch.where(keep_dev[i] > 0.5, y, x)
+                else:
+                    if keep_host is not None:
+                        run = bool(keep_host[i] > 0.5)
+                    else:
+                        dropout_probability = np.random.random()  # numpy RNG, as encoder.py:252
+                        run = (dropout_probability > self.encoder_layerdrop) or i == self.unb_enc_layer
+                    if not self.training or run:
+                        x, _ = layer(x, self_attn_padding_mask=encoder_padding_mask, pos_bias=pos_k, maxpos=maxpos)
                 if i == self.unb_enc_layer:
                     d = x
                 if i == tgt_layer:
@@ -365,13 +377,27 @@ class TransformerDecoder(nn.Module):
         x = _act_dtype(prev_output_tokens)
         attn_list, attn = [], None
         inner_states = [x]
+        keep_dev, keep_host = RT.layer_keep, RT.layer_keep_host
+        n_enc = 0 if (keep_dev is None and keep_host is None) else (len(keep_dev if keep_dev is not None else keep_host)
+                                                                    - len(self.layers))
         for idx, layer in enumerate(self.layers):
-            if self.training and self.decoder_layerdrop > 0:  # fairseq LayerDropModuleList (torch RNG)
-                if torch.empty(1).uniform_().item() <= self.decoder_layerdrop:
-                    continue
+            x = RT.stage(("dec", idx), x)  # gradient-exchange overlap point (trainer), identity otherwise
             want = bool(idx == alignment_layer or alignment_layer == -1)
-            x, layer_attn, _ = layer(x, enc, padding_mask, causal=not full_context_alignment,
-                                     self_attn_padding_mask=tgt_mask, need_attn=want, need_head_weights=want)
+            if self.training and keep_dev is not None:  # LayerDrop under capture: see TransformerEncoder
+                y, layer_attn, _ = layer(x, enc, padding_mask, causal=not full_context_alignment,
+                                         self_attn_padding_mask=tgt_mask, need_attn=want, need_head_weights=want)
+                x = torch.where(keep_dev[n_enc + idx] > 0.5, y, x)
+                # (the reference drops the layer's attention map from the list too; under a static graph it stays, the
+                #  s2t / pre-training criteria that use LayerDrop do not read it)
+            else:
+                if self.training and keep_host is not None:
+                    if not bool(keep_host[n_enc + idx] > 0.5):
+                        continue
+                elif self.training and self.decoder_layerdrop > 0:  # fairseq LayerDropModuleList (torch RNG)
+                    if torch.empty(1).uniform_().item() <= self.decoder_layerdrop:
+                        continue
+                x, layer_attn, _ = layer(x, enc, padding_mask, causal=not full_context_alignment,
+                                         self_attn_padding_mask=tgt_mask, need_attn=want, need_head_weights=want)
             inner_states.append(x)
             if layer_attn is not None and want:
                 attn = layer_attn.float()

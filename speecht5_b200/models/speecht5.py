@@ -224,9 +224,6 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
                 return None, encoder_output
             if not self.training and prev_output_tokens is None:
                 return encoder_output
-        hook = getattr(self, "_encoder_grad_hook", None)  # set by B200Trainer: gradient-exchange overlap point
-        if hook is not None and encoder_output["encoder_out"][0].requires_grad:
-            encoder_output["encoder_out"][0].register_hook(hook)
         if text_out:  # (:901-903, 955-957): decoder on token embeddings, vocabulary logits
             dec_in, tgt_mask, _ = self.text_decoder_prenet(prev_output_tokens)
             decoder_output, extra = self.decoder(
@@ -260,7 +257,7 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if dropped:
             logger.info("load_state_dict: ignoring %d keys absent/mismatched in the B200 t2s model", len(dropped))
         out = super().load_state_dict(filtered, strict=False)
-        RT.invalidate_shadows()
+        RT.params_written_externally()  # incl. the trainer's flat bf16 shadow, if one exists (fairseq: build, then load)
         return out
 
     def max_positions(self):

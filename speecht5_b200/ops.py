@@ -25,9 +25,17 @@ class Runtime:
         self._shadows = {}
         self._static = {}
         self._static_grad = {}  # key -> fp32 view of the trainer's flat gradient buffer (direct accumulation)
+        self._static_refresh = None  # callable that re-casts the owner's flat bf16 shadow from its fp32 master
+        self._static_dirty = False   # fp32 parameters were written behind the owner's back (load_state_dict)
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
         self.attn_fused = True        # bf16 mode, no RPE, Tk <= 320: single-launch fused forward (attention_fused.cu)
         self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
+        # trainer hooks: stage_callback(key, x) is called at the entry of every encoder / decoder layer (gradient-exchange
+        # overlap point); layer_keep (device [n_enc + n_dec] 0/1 mask, CUDA-graph mode) / layer_keep_host (eager mode)
+        # carry the trainer's LayerDrop draw -- when both are None the model draws for itself like the reference
+        self.stage_callback = None
+        self.layer_keep = None
+        self.layer_keep_host = None
 
     @property
     def seed(self):
@@ -59,9 +67,16 @@ class Runtime:
             self._seed += 1
         self._offset = 0
 
+    def stage(self, key, x):
+        cb = self.stage_callback
+        return x if cb is None else cb(key, x)
+
     def register_static(self, key, hi):
         """Shadow that is kept current by someone else (the trainer's flat bf16 buffer refreshed by the Adam kernel)."""
         self._static[key] = hi
+
+    def register_static_refresh(self, fn):
+        self._static_refresh = fn
 
     def register_static_grad(self, key, view):
         self._static_grad[key] = view
@@ -69,14 +84,28 @@ class Runtime:
     def clear_static(self):
         self._static = {}
         self._static_grad = {}
+        self._static_refresh = None
+        self._static_dirty = False
 
     def invalidate_shadows(self):
-        """Call after parameters change (optimizer step, load_state_dict)."""
+        """Call after parameters change through the owner of the static shadows (optimizer step) or when there is none:
+        cached per-parameter shadows are re-cast on next use."""
         self.param_epoch += 1
+
+    def params_written_externally(self):
+        """fp32 parameters were overwritten in place by someone who does not maintain the static bf16 shadows
+        (load_state_dict after the trainer was built, manual edits): the next shadow() lookup re-casts the flat shadow
+        from the fp32 master before handing out a view of it."""
+        self.param_epoch += 1
+        if self._static_refresh is not None:
+            self._static_dirty = True
 
     def shadow(self, key, build):
         """bf16 (hi, lo) copy of a (possibly fused / re-laid-out) fp32 weight; `build()` returns the fp32 2-D tensor."""
         need_lo = self.dtype == torch.float32
+        if self._static_dirty:
+            self._static_dirty = False
+            self._static_refresh()
         if not need_lo:
             st = self._static.get(key)
             if st is not None:

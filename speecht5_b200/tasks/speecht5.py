@@ -80,6 +80,10 @@ class SpeechT5Task(LegacyFairseqTask):
         return T5TransformerModel.build_model(args, self)
 
     def train_step(self, sample, model, criterion, optimizer, update_num, ignore_grad=False):
+        """tasks/speecht5.py:519-556: the loss is normalised by the criterion's own sample_size, the task reports
+        sample_size 1.0 and a logging dict {task_name: criterion log, "sample_size": 1, "ntokens", "nsentences",
+        "loss"} -- the shape SpeechT5Criterion.reduce_metrics consumes. Under B200Trainer (CUDA graph) the criterion
+        defers its scalars (`_stats` device tensor) and the loss stays a device tensor: no host sync inside the step."""
         model.train()
         model.set_num_updates(update_num)
         loss, sample_size, logging_output = criterion(model, sample)
@@ -90,10 +94,19 @@ class SpeechT5Task(LegacyFairseqTask):
             optimizer.backward(loss)
         else:
             loss.backward()
-        return loss.detach(), 1.0, logging_output
+        agg = {"sample_size": 1}
+        for k in ("ntokens", "nsentences"):
+            if k in logging_output:
+                agg[k] = logging_output[k]
+        agg[sample["task_name"]] = logging_output
+        deferred = "_stats" in logging_output
+        agg["loss"] = loss.detach() if deferred else loss.detach().item()
+        return agg["loss"], 1.0, agg
 
-    def valid_step(self, sample, model, criterion):
+    def valid_step(self, sample, model, criterion):  # tasks/speecht5.py:558-571
         model.eval()
         with torch.no_grad():
             loss, sample_size, logging_output = criterion(model, sample)
-        return loss, sample_size, logging_output
+            loss = loss / sample_size
+            agg_loss = loss.item() if torch.is_tensor(loss) else loss
+        return agg_loss, 1.0, {"sample_size": 1, sample["task_name"]: logging_output, "loss": agg_loss}

@@ -232,3 +232,56 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "attention", attention)
     monkeypatch.setattr(K, "conv0_gn_gelu_fwd", conv0_gn_gelu_fwd)
     monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)
+
+
+# ---------------------------------------------------------------------------------------------- optimizer (csrc/optim.cu)
+def sumsq(x, out):
+    out += (x.double() ** 2).sum().float()
+
+
+def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_norm_sq, max_norm, grad_mul,
+              lr_dev=None, step_dev=None):
+    """st5_adam_step semantics: skip on a non-finite norm; clip coefficient max_norm / (norm * grad_mul + 1e-6) capped
+    at 1; fairseq Adam (denominator sqrt(v) + eps, bias-corrected step size); bf16 shadow refresh."""
+    import math
+    if grad_norm_sq is not None and not bool(torch.isfinite(grad_norm_sq).all()):
+        return
+    if lr_dev is not None:
+        lr = float(lr_dev)
+    t = float(step_dev) if step_dev is not None else float(step)
+    step_size = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    gscale = grad_mul
+    if grad_norm_sq is not None and max_norm > 0:
+        norm = float(grad_norm_sq.sqrt()) * grad_mul
+        gscale *= min(1.0, max_norm / (norm + 1e-6))
+    gi = g * gscale
+    m.mul_(beta1).add_(gi, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+    if weight_decay != 0:
+        p.mul_(1 - weight_decay * lr)
+    p.addcdiv_(m, v.sqrt() + eps, value=-step_size)
+    if p_bf16 is not None:
+        p_bf16.copy_(p.to(torch.bfloat16))
+
+
+def install_trainer(monkeypatch):
+    """install_autograd() + the optimizer kernels + BatchNorm as a torch call: B200Trainer runs whole updates on CPU."""
+    install_autograd(monkeypatch)
+    import torch.nn.functional as F
+    from speecht5_b200 import kernels as K, ops
+    monkeypatch.setattr(K, "sumsq", sumsq)
+    monkeypatch.setattr(K, "adam_step", adam_step)
+
+    def batch_norm_act(x, bn, training, act=None, drop_p=0.0):
+        assert drop_p == 0.0 and training
+        y = F.batch_norm(x.float().reshape(-1, x.shape[-1]), None, None, bn.weight, bn.bias, True, 0.0, bn.eps)
+        y = torch.tanh(y) if act == "tanh" else y
+        return y.reshape(x.shape).to(x.dtype)
+    monkeypatch.setattr(ops, "batch_norm_act", batch_norm_act)
+
+
+class Patcher:
+    """monkeypatch stand-in for spawned worker processes (no pytest fixture there)."""
+
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)

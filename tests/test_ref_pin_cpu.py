@@ -271,3 +271,43 @@ def test_reference_generate_speech_matches_oracle_autoregressive_synthesis():
         b = orc.generate_speech(src_tokens=toks, spkembs=spk, threshold=0.5, minlenratio=0.0, maxlenratio=2.0)
     assert a[0].shape == b[0].shape
     assert rel(b[0], a[0]) < 1e-4
+
+
+@needs_ref
+def test_reduce_metrics_logs_the_reference_keys_and_values():
+    """SpeechT5Criterion.reduce_metrics (criterions/speecht5_criterion.py:123-436) run by the reference itself and by the
+    plugin on the same logging outputs: same meter names, same values."""
+    import importlib
+    ns = rl.load()
+    ref_cls = importlib.import_module("speecht5.criterions.speecht5_criterion").SpeechT5Criterion
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.fairseq_shim import metrics as ours
+    t2s = {"loss": 1.5, "l1_loss": 1.0, "l2_loss": 2.0, "bce_loss": 0.5, "sample_size": 1, "ntokens": 100,
+           "nsentences": 4, "enc_dec_attn_loss": 0.01, "encoder_alpha": 1.0, "decoder_alpha": 1.1}
+    s2t = {"loss": 80.0, "ce_loss": 60.0, "ctc_loss": 100.0, "nll_loss": 55.0, "ntokens": 37, "nsentences": 3,
+           "sample_size": 3, "n_correct": 11, "total": 37, "c_errors": 5, "c_total": 30, "w_errors": 2, "wv_errors": 3,
+           "w_total": 9}
+    text = {"loss": 12.0, "bart_loss": 12.0, "ntokens": 50, "sample_size": 50, "loss_prob_perplexity": 0.3,
+            "code_perplexity": 17.0}
+    hub = {"loss": 9.0, "ntokens": 20, "sample_size": 20, "dec_loss": 1.0, "l1_loss": 0.5, "l2_loss": 0.6, "bce_loss": 0.1,
+           "ngpu": 1, "count_m_0": 12, "correct_m_0": 5, "loss_m_0": 7.0, "enc_dec_attn_loss": 0.02}
+    logs = [{"t2s": t2s, "sample_size": 1, "loss": 1.5}, {"t2s": dict(t2s, loss=2.5), "sample_size": 1, "loss": 2.5},
+            {"s2t": s2t, "sample_size": 1, "loss": 80.0 / 3}, {"text_pretrain": text, "sample_size": 1, "loss": 0.24},
+            {"speech_pretrain": hub, "sample_size": 1, "loss": 0.45}]
+    ns.metrics.logged.clear()
+    ns.metrics.derived.clear()
+    ref_cls.reduce_metrics(logs)
+    ours.reset()
+    SpeechT5Criterion.reduce_metrics(logs)
+    assert set(ours.scalars) == set(ns.metrics.logged), set(ours.scalars) ^ set(ns.metrics.logged)
+    for k, v in ns.metrics.logged.items():
+        assert abs(float(ours.scalars[k]) - float(v)) < 1e-9, k
+    assert set(ours.derived) == set(ns.metrics.derived)
+
+
+def test_train_step_returns_the_reference_logging_shape():
+    """tasks/speecht5.py:519-556: (loss, 1.0, {task_name: log, 'sample_size': 1, 'loss': ..})."""
+    import inspect
+    from speecht5_b200.tasks import SpeechT5Task
+    src = inspect.getsource(SpeechT5Task.train_step)
+    assert 'agg[sample["task_name"]] = logging_output' in src and '"sample_size": 1' in src
