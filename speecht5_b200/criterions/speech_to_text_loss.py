@@ -81,9 +81,17 @@ class SpeechtoTextLoss(FairseqCriterion):
         else:
             input_lengths = lprobs.new_full((lprobs.size(1),), lprobs.size(0), dtype=torch.long)
         keep = (sample["target"] != self.pad_idx) & (sample["target"] != self.eos_idx)
-        targets_flat = sample["target"].masked_select(keep)
         target_lengths = (sample["target_lengths"] if "target_lengths" in sample else keep.sum(-1)) - 1  # :324
+        targets_flat = None if getattr(self, "defer_logging", False) else sample["target"].masked_select(keep)
         raw = net_output["encoder_out_for_ctc"][0]
+        if getattr(self, "defer_logging", False) and raw.is_cuda:
+            # captured step (B200Trainer): padded targets straight into the fused log-softmax + CTC kernel, lengths
+            # read on the device. Collated targets are right-padded tokens + eos + pad (:316-324 keeps the first
+            # target_lengths - 1 of each row, which is what masked_select(keep) concatenates)
+            from ..frontend import ctc_loss_sum_padded
+            loss = ctc_loss_sum_padded(raw, sample["target"], input_lengths, target_lengths, self.blank_idx,
+                                       self.zero_infinity)
+            return loss, lprobs, input_lengths
         if os.environ.get("ST5_CTC_KERNEL") == "1" and raw.is_cuda:  # hand-written fused log-softmax + CTC (csrc/ctc.cu)
             from ..frontend import ctc_loss_sum
             loss = ctc_loss_sum(raw, targets_flat, input_lengths, target_lengths, self.blank_idx, self.zero_infinity)
@@ -108,6 +116,13 @@ class SpeechtoTextLoss(FairseqCriterion):
             loss = loss_ce if loss_ce is not None else loss_ctc  # a single term is NOT scaled by its weight (:202-205)
         ntokens = sample["ntokens"] if "ntokens" in sample else int(sample["target_lengths"].sum().item())
         sample_size = sample["target"].size(0) if self.sentence_avg else ntokens
+        if getattr(self, "defer_logging", False):
+            # no device->host sync inside the step (CUDA-graph capture): the caller reads `_stats` after the update
+            z = loss.new_zeros(())
+            stats = torch.stack([loss.detach(), loss_ce.detach() if loss_ce is not None else z,
+                                 loss_ctc.detach() if loss_ctc is not None else z, nll.detach() if nll is not None else z])
+            return loss, sample_size, {"_stats": stats, "ntokens": ntokens, "nsentences": sample["target"].size(0),
+                                       "sample_size": sample_size}
         log = {"loss": loss.item(), "ce_loss": loss_ce.item() if loss_ce is not None else 0,
                "ctc_loss": loss_ctc.item() if loss_ctc is not None else 0, "nll_loss": nll.item() if nll is not None else 0,
                "ntokens": ntokens, "nsentences": sample["target"].size(0), "sample_size": sample_size}

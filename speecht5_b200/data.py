@@ -33,6 +33,21 @@ def synthetic_tts_batch(B, T_txt, T_mel, vocab=81, odim=80, r=2, seed=1, ragged=
     return sample
 
 
+def synthetic_asr_batch(B, n_samples, T_tgt, vocab=81, seed=1, ragged=True, pin=False):
+    """SURVEY 8(d) config 3 shaped batch through the s2t collater: waveforms N(0, 0.1^2) with lengths U{0.8 n .. n}
+    (-> padding_mask), `T_tgt - 1` target tokens U{4 .. vocab-3} + eos (the last two ids are <mask> / <ctc_blank>,
+    tasks/speecht5.py:283-287)."""
+    g = torch.Generator().manual_seed(seed)
+    items = []
+    for b in range(B):
+        n = n_samples if (b == 0 or not ragged) else int(torch.randint(int(0.8 * n_samples), n_samples + 1, (1,), generator=g))
+        t = T_tgt - 1 if (b == 0 or not ragged) else int(torch.randint(max(1, T_tgt // 2), T_tgt, (1,), generator=g))
+        items.append({"id": b, "source": torch.randn(n, generator=g) * 0.1,
+                      "label_list": [torch.randint(4, vocab - 2, (t,), generator=g)]})
+    sample = collate_asr(items)
+    return _pin(sample) if pin else sample
+
+
 def collate_frames(frames, is_audio_input=False):
     """text_to_speech_dataset.py:25-45 _collate_frames: zero-padded stack of [L_i, F] (or [L_i]) tensors."""
     max_len = max(f.size(0) for f in frames)
@@ -108,50 +123,79 @@ def collate_asr(samples, pad=1, eos=2):
             "target": target, "target_lengths": lengths, "task_name": "s2t", "ntokens": ntokens}
 
 
+def _span_lengths(rng, kind, count, length, other):
+    """Span lengths of one row; each non-static kind consumes `count` draws from the stream, like the reference."""
+    if kind == "static":
+        return [length] * count
+    if kind == "uniform":
+        return list(rng.randint(other, length * 2 + 1, size=count))
+    if kind == "normal":
+        return [max(1, int(round(v))) for v in rng.normal(length, other, size=count)]
+    if kind == "poisson":
+        return [int(round(v)) for v in rng.poisson(length, size=count)]
+    raise Exception("unknown mask selection " + kind)
+
+
 def compute_mask_indices(shape, padding_mask, mask_prob, mask_length, mask_type="static", mask_other=0.0, min_masks=0,
                          no_overlap=False, min_space=0):
-    """Span masks for the speech prenet (speech_encoder_prenet.py:236-262 calls fairseq/data/data_utils.py:393-517).
-    Host-side numpy, drawing from the GLOBAL np.random stream in the reference's order (one rand() for the whole
-    batch, one more per row when a padding mask is given, the span lengths, the span starts, then the per-row
-    thinning to the common count), so a run seeded like the reference masks the same frames. Returns a bool ndarray
-    [B, T]. `no_overlap` (off in every SpeechT5 recipe) is not built."""
+    """Span masks for the speech prenet: the host-side sampler behind `apply_hubert_mask`
+    (speech_encoder_prenet.py:236-262), which in the reference is fairseq's `compute_mask_indices`
+    (fairseq/data/data_utils.py:393-517, MIT licence, (c) Facebook). ATTRIBUTION: this is a re-statement of that
+    routine, not an independent design -- a run seeded like the reference must mask the same frames, so the sequence of
+    draws from the GLOBAL np.random stream has to be the reference's: one rand() for the batch-level span count, per
+    row one more rand() when a padding mask is given, then that row's span lengths, then its span starts (choice
+    without replacement); after all rows, one thinning choice() per row that has more masked frames than the shortest
+    row. tests/test_ref_pin_cpu.py::test_host_mask_sampler_reproduces_the_reference_draws pins it bit for bit against
+    the reference function. Returns a bool ndarray [B, T]. `no_overlap` (off in every SpeechT5 recipe) is not built."""
     import numpy as np
     if no_overlap:
         raise NotImplementedError("no_overlap span placement is not built (unused by the SpeechT5 recipes)")
-    bsz, all_sz = shape
-    mask = np.full((bsz, all_sz), False)
-    all_num_mask = max(min_masks, int(mask_prob * all_sz / float(mask_length) + np.random.rand()))
-    mask_idcs = []
-    for i in range(bsz):
-        if padding_mask is not None:
-            sz = all_sz - int(padding_mask[i].long().sum().item())
-            num_mask = max(min_masks, int(mask_prob * sz / float(mask_length) + np.random.rand()))
+    rng = np.random  # the global stream, on purpose
+    rows, width = shape
+
+    def span_count(n_valid):
+        return max(min_masks, int(mask_prob * n_valid / float(mask_length) + rng.rand()))
+    batch_count = span_count(width)
+    per_row = []
+    for r in range(rows):
+        if padding_mask is None:
+            n_valid, count = width, batch_count
         else:
-            sz, num_mask = all_sz, all_num_mask
-        if mask_type == "static":
-            lengths = np.full(num_mask, mask_length)
-        elif mask_type == "uniform":
-            lengths = np.random.randint(mask_other, mask_length * 2 + 1, size=num_mask)
-        elif mask_type == "normal":
-            lengths = [max(1, int(round(x))) for x in np.random.normal(mask_length, mask_other, size=num_mask)]
-        elif mask_type == "poisson":
-            lengths = [int(round(x)) for x in np.random.poisson(mask_length, size=num_mask)]
-        else:
-            raise Exception("unknown mask selection " + mask_type)
-        if sum(lengths) == 0:
-            lengths[0] = min(mask_length, sz - 1)
-        min_len = min(lengths)
-        if sz - min_len <= num_mask:
-            min_len = sz - num_mask - 1
-        starts = np.random.choice(sz - min_len, num_mask, replace=False)
-        idc = np.asarray([starts[j] + off for j in range(len(starts)) for off in range(lengths[j])])
-        mask_idcs.append(np.unique(idc[idc < sz]))
-    min_len = min(len(m) for m in mask_idcs)
-    for i, idc in enumerate(mask_idcs):
-        if len(idc) > min_len:
-            idc = np.random.choice(idc, min_len, replace=False)
-        mask[i, idc] = True
-    return mask
+            n_valid = width - int(padding_mask[r].long().sum().item())
+            count = span_count(n_valid)
+        spans = _span_lengths(rng, mask_type, count, mask_length, mask_other)
+        if sum(spans) == 0:
+            spans[0] = min(mask_length, n_valid - 1)
+        shortest = min(spans)
+        if n_valid - shortest <= count:
+            shortest = n_valid - count - 1
+        starts = rng.choice(n_valid - shortest, count, replace=False)
+        covered = np.concatenate([np.arange(b, b + n) for b, n in zip(starts, spans)]) if count else np.zeros(0, int)
+        per_row.append(np.unique(covered[covered < n_valid]))
+    common = min(len(c) for c in per_row)
+    out = np.zeros((rows, width), dtype=bool)
+    for r, covered in enumerate(per_row):
+        if len(covered) > common:
+            covered = rng.choice(covered, common, replace=False)
+        out[r, covered] = True
+    return out
+
+
+def draw_hubert_masks(prenet, batch_size, n_frames, frame_padding_mask):
+    """Both mask draws of `apply_hubert_mask` (speech_encoder_prenet.py:234-272) for one batch, on the host, in the
+    reference's order (time mask first, channel mask second). Returns (mask_indices [B,T] or None,
+    mask_channel_indices [B,C] or None) as bool tensors; used by the trainer before a CUDA-graph replay."""
+    mi = mc = None
+    if prenet.mask_prob > 0:
+        mi = torch.from_numpy(compute_mask_indices(
+            (batch_size, n_frames), frame_padding_mask, prenet.mask_prob, prenet.mask_length, prenet.mask_selection,
+            prenet.mask_other, min_masks=2, no_overlap=prenet.no_mask_overlap, min_space=prenet.mask_min_space))
+    if getattr(prenet, "mask_channel_prob", 0.0) > 0:
+        mc = torch.from_numpy(compute_mask_indices(
+            (batch_size, prenet.embed_dim), None, prenet.mask_channel_prob, prenet.mask_channel_length,
+            prenet.mask_channel_selection, prenet.mask_channel_other, no_overlap=prenet.no_mask_channel_overlap,
+            min_space=prenet.mask_channel_min_space))
+    return mi, mc
 
 
 def _pin(obj):

@@ -340,8 +340,13 @@ class SpeechEncoderPrenet(torch.nn.Module):
         self.embed_dim = d
         self.freeze_encoder_updates = getattr(args, "freeze_encoder_updates", 0)
         self.num_updates = 0
-        if getattr(args, "mask_channel_prob", 0.0) > 0:
-            raise NotImplementedError("channel masking (mask_channel_prob > 0) is not built (0 in every SpeechT5 recipe)")
+        # channel masks (:253-271): prob 0.5 / length 64 in t5_transformer_base_asr (models/speecht5.py:1443-1445)
+        self.mask_channel_prob = getattr(args, "mask_channel_prob", 0.0)
+        self.mask_channel_length = getattr(args, "mask_channel_length", 10)
+        self.mask_channel_selection = getattr(args, "mask_channel_selection", "static")
+        self.mask_channel_other = getattr(args, "mask_channel_other", 0)
+        self.no_mask_channel_overlap = getattr(args, "no_mask_channel_overlap", False)
+        self.mask_channel_min_space = getattr(args, "mask_channel_min_space", 1)
 
     def _positions(self, frame_mask, B, T, device):
         if self._pe is None or self._pe.shape[0] < self.padding_idx + 1 + T or self._pe.device != device:
@@ -355,18 +360,19 @@ class SpeechEncoderPrenet(torch.nn.Module):
         self.num_updates = num_updates
 
     def forward(self, src_tokens, require_feat_pen=False, target_list=None, padding_mask=None, mask=True,
-                mask_indices=None):
+                mask_indices=None, mask_channel_indices=None):
         """Reference signature and returns (speech_encoder_prenet.py:151-204): `(x, frame_padding_mask)`, or with
-        require_feat_pen `((x, features_pen, mask_indices, target_list), frame_padding_mask)`. `mask_indices` (extra,
-        optional) injects a precomputed mask draw instead of sampling one."""
+        require_feat_pen `((x, features_pen, mask_indices, target_list), frame_padding_mask)`. `mask_indices` [B,T] /
+        `mask_channel_indices` [B,C] (extra, optional) inject a precomputed mask draw instead of sampling one here --
+        the trainer draws them on the host before a CUDA-graph replay (speecht5_b200.data.draw_hubert_masks)."""
         import contextlib
         if target_list is not None:
             raise NotImplementedError("pre-training targets (forward_targets, SURVEY 8a row 22) are a later row")
         ft = self.freeze_encoder_updates <= self.num_updates
         with torch.no_grad() if not ft else contextlib.ExitStack():
-            return self._forward(src_tokens, require_feat_pen, padding_mask, mask, mask_indices)
+            return self._forward(src_tokens, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices)
 
-    def _forward(self, source, require_feat_pen, padding_mask, mask, mask_indices):
+    def _forward(self, source, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices=None):
         from . import ops
         if self.feature_grad_mult > 0:
             x = self.feature_extractor(source)
@@ -390,8 +396,16 @@ class SpeechEncoderPrenet(torch.nn.Module):
                 (B, T), frame_mask.cpu() if frame_mask is not None else None, self.mask_prob, self.mask_length,
                 self.mask_selection, self.mask_other, min_masks=2, no_overlap=self.no_mask_overlap,
                 min_space=self.mask_min_space)).to(x.device)
+        if mask and mask_channel_indices is None and self.mask_channel_prob > 0:  # second numpy draw, as :253-262
+            from .data import compute_mask_indices
+            mask_channel_indices = torch.from_numpy(compute_mask_indices(
+                (B, x.shape[-1]), None, self.mask_channel_prob, self.mask_channel_length, self.mask_channel_selection,
+                self.mask_channel_other, no_overlap=self.no_mask_channel_overlap,
+                min_space=self.mask_channel_min_space)).to(x.device)
         if mask_indices is not None:
             x = torch.where(mask_indices.unsqueeze(-1), self.mask_emb.to(x.dtype), x)
+        if mask_channel_indices is not None:
+            x = torch.where(mask_channel_indices.unsqueeze(1), torch.zeros((), dtype=x.dtype, device=x.device), x)
         if self.use_conv_pos:
             wn = self.pos_conv[0]
             x = GroupedPosConvFn.apply(x, wn.weight(), wn.bias, wn.groups)
@@ -428,3 +442,30 @@ class CTCLossFn(torch.autograd.Function):
 
 def ctc_loss_sum(logits_tbv, targets_flat, input_lengths, target_lengths, blank, zero_infinity):
     return CTCLossFn.apply(logits_tbv, targets_flat, input_lengths, target_lengths, blank, zero_infinity)
+
+
+class CTCLossPaddedFn(torch.autograd.Function):
+    """Same kernel on right-padded targets [B, S] (row b's labels are targets[b, :target_lengths[b]]): no host sync, no
+    data-dependent shapes -- the form a captured training step uses."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, input_lengths, target_lengths, blank, zero_infinity):
+        logits = logits.float().contiguous()
+        T, B, V = logits.shape
+        S = targets.size(1)
+        offs = torch.arange(B, device=logits.device, dtype=torch.int64) * S
+        nll = torch.empty(B, dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits)
+        K.ctc_loss(logits, targets.long().contiguous().view(-1), offs, input_lengths.long().contiguous(),
+                   target_lengths.long().contiguous(), nll, grad, 2 * S + 1, int(blank), bool(zero_infinity))
+        ctx.save_for_backward(grad)
+        return nll.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None
+
+
+def ctc_loss_sum_padded(logits_tbv, targets_bs, input_lengths, target_lengths, blank, zero_infinity):
+    return CTCLossPaddedFn.apply(logits_tbv, targets_bs, input_lengths, target_lengths, blank, zero_infinity)

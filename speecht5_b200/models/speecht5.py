@@ -197,7 +197,9 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
     # ------------------------------------------------------------------ forward (models/speecht5.py:786-963)
     def forward(self, source=None, src_tokens=None, src_lengths=None, prev_output_tokens=None, tgt_lengths=None,
                 spkembs=None, target_list=None, task_name=None, padding_mask=None, only_hubert=False, only_ctc=False,
-                feature_only=False, tgt_enc_layer=None, mask=True):
+                feature_only=False, tgt_enc_layer=None, mask=True, mask_indices=None, mask_channel_indices=None):
+        """Reference signature (:786) + two optional extras: `mask_indices` / `mask_channel_indices`, a HuBERT-style mask
+        draw made by the caller (the trainer draws on the host before replaying a captured step)."""
         assert source is not None or src_tokens is not None
         input_type = "text" if (source is None and padding_mask is None and not feature_only) else "speech"
         output_type = "text" if (prev_output_tokens is not None and prev_output_tokens.dim() == 2) else "speech"
@@ -211,8 +213,9 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
                 f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built yet in the "
                 "B200 path; round 1 covers text->speech (t2s), opt-in: text output and speech input")
         if speech_in:  # (:815-820) waveform -> frames; the HuBERT-style mask is drawn only in training
-            encoder_input, encoder_padding_mask = self.speech_encoder_prenet(source, padding_mask=padding_mask,
-                                                                             mask=self.training)
+            encoder_input, encoder_padding_mask = self.speech_encoder_prenet(
+                source, padding_mask=padding_mask, mask=self.training and mask, mask_indices=mask_indices,
+                mask_channel_indices=mask_channel_indices)
         else:
             encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
         encoder_output = self.encoder(encoder_input, encoder_padding_mask, tgt_layer=tgt_enc_layer)
@@ -488,6 +491,11 @@ def base_architecture(args):  # models/speecht5.py:1252-1383 (fields used by the
     g("no_mask_overlap", False)
     g("mask_min_space", 1)
     g("mask_channel_prob", 0.0)
+    g("mask_channel_length", 10)
+    g("mask_channel_selection", "static")
+    g("mask_channel_other", 0)
+    g("no_mask_channel_overlap", False)
+    g("mask_channel_min_space", 1)
     g("use_conv_pos", False)
     g("use_sinc_pos", False)
     g("encoder_speech_prenet", "conv")
@@ -541,6 +549,12 @@ def t5_transformer_base_asr(args):  # :1427-1447
     g("encoder_layerdrop", 0.1)
     g("decoder_layerdrop", 0.1)
     g("mask_prob", 0.75)
+    g("mask_selection", "static")
+    g("mask_channel_length", 64)
+    g("mask_channel_prob", 0.5)
+    g("mask_channel_selection", "static")
+    g("use_conv_pos", True)
+    g("use_sinc_pos", True)
     g("max_text_positions", 600)
     base_architecture(args)
 

@@ -420,6 +420,31 @@ class B200Trainer:
         self.layer_keep.copy_(keep, non_blocking=True)
         return True
 
+    def _with_host_draws(self, sample):
+        """Speech input: the HuBERT-style time / channel masks are drawn by numpy on the host in the reference
+        (speech_encoder_prenet.py:234-272, inside forward). A captured step cannot do that, so the trainer draws them
+        here -- same stream, same order -- and hands them to forward() as explicit inputs."""
+        prenet = getattr(self.model, "speech_encoder_prenet", None)
+        ni = sample.get("net_input", {})
+        if (sample.get("task_name") != "s2t" or prenet is None or not self.model.training or "mask_indices" in ni
+                or (prenet.mask_prob <= 0 and getattr(prenet, "mask_channel_prob", 0.0) <= 0)):
+            return sample
+        from .data import draw_hubert_masks
+        from .frontend import downsample_padding_mask
+        B, n = ni["source"].shape
+        T = int(prenet.feature_extractor.get_out_seq_lens_tensor(torch.tensor([n]))[0])
+        pm = ni.get("padding_mask")
+        frame_pm = downsample_padding_mask(pm.cpu(), T) if pm is not None else None
+        mi, mc = draw_hubert_masks(prenet, B, T, frame_pm)
+        extra = {}
+        if mi is not None:
+            extra["mask_indices"] = mi.pin_memory() if self.device.type == "cuda" else mi
+        if mc is not None:
+            extra["mask_channel_indices"] = mc.pin_memory() if self.device.type == "cuda" else mc
+        out = dict(sample)
+        out["net_input"] = dict(ni, **extra)
+        return out
+
     # ------------------------------------------------------------------ public step
     def _signature(self, samples):
         shapes = tuple(tuple((k, tuple(v.shape)) for k, v in _flatten(s).items()) + (s.get("task_name"),) for s in samples)
@@ -440,6 +465,7 @@ class B200Trainer:
                 c.defer_logging = True
         if self.shape_buckets:
             samples = [pad_to_buckets(s, self.shape_buckets) for s in samples]
+        samples = [self._with_host_draws(s) for s in samples]
         layerdrop = self._draw_layerdrop()
         if not self.use_cuda_graph:
             RT.layer_keep = None  # eager: the host decides, dropped layers are really skipped
