@@ -33,6 +33,9 @@ extern "C" {
 #define ST5_ACT_GELU 2
 #define ST5_ACT_TANH 3
 #define ST5_ACT_GELU_TANH 4 /* tanh-form GELU on the MUFU unit: |error| <= 4.8e-4 vs the erf form; bf16 throughput mode */
+#define ST5_ACT_GATE 5      /* actgrad_act only: actgrad_pre already holds the multiplier (written by ..._GATE below) */
+#define ST5_ACT_GELU_TANH_GATE 6 /* act only (bf16 output, N % 8 == 0, c_pre != NULL): C = dropout(gelu_tanh(x)) and c_pre
+                                    receives keep * scale * gelu_tanh'(x), the factor of the FFN's dH GEMM in backward */
 
 int st5_version(void);
 const char* st5_last_error(void);
@@ -91,6 +94,13 @@ int st5_posenc_bwd(const void* dy, const int64_t* tokens, int64_t padding_idx, c
 int st5_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
                float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
                uint64_t offset, void* stream);
+/* Same with an fp32 RESIDUAL STREAM next to the bf16 activations (throughput mode): residual_f32 (may be NULL) replaces
+ * `residual` as the addend, y_f32 (may be NULL) receives the un-rounded output. The GEMMs keep reading the bf16 `y`; the
+ * next block's residual add reads y_f32, so the post-LN stream of transformer_layer.py:112-132 / :343-391 is never
+ * rounded to bf16 between layers (the reference keeps it in fp32 on the CPU path / fp16 storage + fp32 LayerNorm on GPU). */
+int st5_ln_fwd_stream(const void* x, const void* residual, const float* residual_f32, const float* gamma,
+                      const float* beta, void* y, float* y_f32, void* s_out, float* mean, float* rstd, int dtype,
+                      int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed, uint64_t offset, void* stream);
 /* ds = LN backward wrt s; dx = dropout-backward(ds) (may alias / be NULL when drop_p == 0 and caller reuses ds);
  * dgamma/dbeta are accumulated (+=) in fp32. `partials` is a caller scratch of 2 * nblk * C floats where
  * nblk = st5_ln_bwd_blocks(rows). */

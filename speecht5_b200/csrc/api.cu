@@ -76,9 +76,16 @@ int st5_posenc_bwd(const void* dy, const int64_t* tokens, int64_t padding_idx, c
 int st5_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
                float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
                uint64_t offset, void* stream) {
-  return set_error(ln_fwd_launch(x, residual, gamma, beta, y, s_out, mean, rstd, dtype, rows, C, eps, drop_p, seed,
-                                 offset, (cudaStream_t)stream),
+  return set_error(ln_fwd_launch(x, residual, nullptr, gamma, beta, y, nullptr, s_out, mean, rstd, dtype, rows, C, eps,
+                                 drop_p, seed, offset, (cudaStream_t)stream),
                    "st5_ln_fwd");
+}
+int st5_ln_fwd_stream(const void* x, const void* residual, const float* residual_f32, const float* gamma,
+                      const float* beta, void* y, float* y_f32, void* s_out, float* mean, float* rstd, int dtype,
+                      int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed, uint64_t offset, void* stream) {
+  return set_error(ln_fwd_launch(x, residual, residual_f32, gamma, beta, y, y_f32, s_out, mean, rstd, dtype, rows, C,
+                                 eps, drop_p, seed, offset, (cudaStream_t)stream),
+                   "st5_ln_fwd_stream");
 }
 int64_t st5_ln_bwd_blocks(int64_t rows) { return ln_bwd_blocks(rows); }
 int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* ds,

@@ -60,8 +60,13 @@ __device__ __forceinline__ void actgrad8(float* v, const uint4 u) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const float2 f = __bfloat1622float2(h[t]);
-    v[2 * t] *= act_grad(f.x, ACT);
-    v[2 * t + 1] *= act_grad(f.y, ACT);
+    if constexpr (ACT == ACT_GATE) {  // the forward epilogue stored keep * scale * act'(pre): one multiply per output
+      v[2 * t] *= f.x;
+      v[2 * t + 1] *= f.y;
+    } else {
+      v[2 * t] *= act_grad(f.x, ACT);
+      v[2 * t + 1] *= act_grad(f.y, ACT);
+    }
   }
 }
 
@@ -70,7 +75,7 @@ __device__ __forceinline__ void actgrad8(float* v, const uint4 u) {
 // output element than 128 x 256), the leader's MMA warp issues tcgen05.mma.cta_group::2 for both, and each CTA drains
 // its own 128 accumulator rows. All pipeline barriers that cross the pair live in the leader's shared memory.
 template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
+__global__ void __maxnreg__(112) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_c,
                                                                   const __grid_constant__ CUtensorMap map_cpre,
@@ -398,6 +403,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           }
         }
       };
+      if (p.act == ACT_GELU_TANH_GATE) {
+        // fc1 of the FFN in throughput mode: out = drop(gelu_tanh(x)), and INSTEAD of the pre-activation the second
+        // output is the multiplier the backward pass needs, gate = keep * scale * gelu_tanh'(x) (tanh(u) is shared by
+        // both). The dH = dO.W2 GEMM of the backward then multiplies by it -- no Philox, no tanh in that epilogue.
+        // Eight columns at a time straight into the two halves of this warp's staging block (bf16: 2 KB each), so
+        // the chunk is never held twice in registers. Launcher guarantees: bf16 output, TMA-store layout, N % 8 == 0.
+        if (lane_id() == 0) bulk_wait_read0();
+        __syncwarp();
+        const int rr = (int)lane_id();
+        const uint64_t e0 = drop_row + (uint64_t)nb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o[8], d[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float x = v[8 * g + t];
+            const float x2 = x * x;
+            const float th = fast_tanh(x * fmaf(0.0356774081f, x2, 0.7978845608f));
+            const float hx = 0.5f * x;
+            o[t] = fmaf(hx, th, hx);
+            d[t] = fmaf(hx * fmaf(-th, th, 1.f), fmaf(0.1070322243f, x2, 0.7978845608f), fmaf(0.5f, th, 0.5f));
+          }
+          if (p.drop_thr != 0) {
+            const Philox4 r4 = philox4x32(dseed, doffset, (e0 + 8 * g) >> 3);
+            const uint32_t w[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float k0 = (w[t] & 0xFFFFu) >= p.drop_thr ? p.drop_scale : 0.f;
+              const float k1 = (w[t] >> 16) >= p.drop_thr ? p.drop_scale : 0.f;
+              o[2 * t] *= k0; d[2 * t] *= k0;
+              o[2 * t + 1] *= k1; d[2 * t + 1] *= k1;
+            }
+          }
+          uint4 po, pd;
+          {
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]), t1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]), t3 = __floats2bfloat162_rn(o[6], o[7]);
+            po.x = *reinterpret_cast<uint32_t*>(&t0); po.y = *reinterpret_cast<uint32_t*>(&t1);
+            po.z = *reinterpret_cast<uint32_t*>(&t2); po.w = *reinterpret_cast<uint32_t*>(&t3);
+            __nv_bfloat162 u0 = __floats2bfloat162_rn(d[0], d[1]), u1 = __floats2bfloat162_rn(d[2], d[3]);
+            __nv_bfloat162 u2 = __floats2bfloat162_rn(d[4], d[5]), u3 = __floats2bfloat162_rn(d[6], d[7]);
+            pd.x = *reinterpret_cast<uint32_t*>(&u0); pd.y = *reinterpret_cast<uint32_t*>(&u1);
+            pd.z = *reinterpret_cast<uint32_t*>(&u2); pd.w = *reinterpret_cast<uint32_t*>(&u3);
+          }
+          const int so = rr * 64 + ((g ^ ((rr >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(stg + so) = po;
+          *reinterpret_cast<uint4*>(stg + 2048 + so) = pd;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane_id() == 0) {
+          tma_store_4d(&map_c, stg, nb, m0 + q * 32, b1, b2);
+          tma_store_4d(&map_cpre, stg + 2048, nb, m0 + q * 32, b1, b2);
+          bulk_commit();
+        }
+        continue;
+      }
       if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
       if (p.act == ACT_GELU_TANH) act_chunk<ACT_GELU_TANH>(v);
       else if (p.act == ACT_GELU) act_chunk<ACT_GELU>(v);
@@ -419,14 +481,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           const float* pr = reinterpret_cast<const float*>(p.ag_pre) + roff + nb;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) v[j] *= act_grad(pr[j], p.ag_act);
+            if (full || nb + j < p.N) v[j] *= p.ag_act == ACT_GATE ? pr[j] : act_grad(pr[j], p.ag_act);
         } else {
           const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.ag_pre) + roff + nb;
           if (vec_ok && ((reinterpret_cast<uintptr_t>(p.ag_pre) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
-              if (p.ag_act == ACT_GELU_TANH) actgrad8<ACT_GELU_TANH>(v + j, u);
+              if (p.ag_act == ACT_GATE) actgrad8<ACT_GATE>(v + j, u);
+              else if (p.ag_act == ACT_GELU_TANH) actgrad8<ACT_GELU_TANH>(v + j, u);
               else if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
               else if (p.ag_act == ACT_RELU) actgrad8<ACT_RELU>(v + j, u);
               else actgrad8<ACT_TANH>(v + j, u);
@@ -434,7 +497,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (full || nb + j < p.N) v[j] *= act_grad(__bfloat162float(pr[j]), p.ag_act);
+              if (full || nb + j < p.N)
+                v[j] *= p.ag_act == ACT_GATE ? __bfloat162float(pr[j]) : act_grad(__bfloat162float(pr[j]), p.ag_act);
           }
         }
       }
@@ -621,6 +685,9 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
       e2.tma_store = r2 == 0 ? 1 : 0;
     }
   }
+  if (e2.act == ACT_GELU_TANH_GATE &&
+      (!e2.tma_store || g.c_fp32 || g.C_pre == nullptr || (g.N & 7) != 0 || g.residual != nullptr || g.ag_pre != nullptr))
+    return -5;  // the gate epilogue needs the TMA-store layout, bf16 outputs and an 8-aligned row length
   const long slots = num_sms() / CTAS;
   const int grid = (int)(total < slots ? total : slots) * CTAS;  // one persistent CTA (or CTA pair per TPC) per SM
   static const bool pdl = [] {
@@ -697,7 +764,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   // problem the 256-wide tile would have been chosen for and that has at least one full pair of row blocks.
   static const int pair_mode = [] {
     const char* e = getenv("ST5_GEMM_PAIR");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;  // -1 = automatic (measured rule below), 0 = never, 1 / 2 = wherever the 256-wide tile applies
   }();
   if (force_bn == 256) return launch_major<256, 3>(g, ep, stream);
   if (force_bn == 128) return launch_major<128, 5>(g, ep, stream);
@@ -707,7 +774,13 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   const double c64 = cost(64, 1.35);
   if (c256 <= c128 && c256 <= c64) {
     if (pair_mode == 2 && g.M > BLOCK_M) return launch_major<256, 5, 2>(g, ep, stream);  // deeper ring (tuning)
-    if (pair_mode && g.M > BLOCK_M) return launch_major<256, 4, 2>(g, ep, stream);
+    if (pair_mode == 1 && g.M > BLOCK_M) return launch_major<256, 4, 2>(g, ep, stream);
+    // Automatic: the CTA pair wins where operand feed is the limit and there are several rounds of tiles (measured on a
+    // B200, profiles/r02_pair_gemm_check.log: 8192^3 x1.15, M=10016 N=3072 K=768 x1.18, K=3072 x1.04), loses on
+    // single-round grids and on the two-output GELU epilogue (x0.89-0.97).
+    if (pair_mode == -1 && g.M >= 4096 && !g.a_mn && batch == 1 && g.C_pre == nullptr &&
+        ((long)g.K >= 3072 || ((long)g.N >= 3072 && (long)g.M >= 8192) || (g.ag_pre != nullptr && (long)g.N >= 3072)))
+      return launch_major<256, 4, 2>(g, ep, stream);
     return launch_major<256, 3>(g, ep, stream);
   }
   if (c128 <= c64) return launch_major<128, 5>(g, ep, stream);

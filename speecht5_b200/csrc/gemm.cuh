@@ -5,7 +5,11 @@
 
 namespace st5 {
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4 };
+enum Act : int {
+  ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3, ACT_GELU_TANH = 4,
+  ACT_GATE = 5,            // ag_act only: ag_pre already holds the backward multiplier (see ACT_GELU_TANH_GATE)
+  ACT_GELU_TANH_GATE = 6   // act only: tanh-form GELU + dropout, and C_pre receives keep * scale * GELU'(pre) instead of pre
+};
 
 // D[z][m][n] = epilogue( alpha * sum_k A[z][m][k] * B[z][n][k] )
 // Operands are bf16. "K-major" = k is the contiguous index (row-major [rows][K]); "MN-major" = the m (or n)

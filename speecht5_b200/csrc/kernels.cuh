@@ -99,9 +99,9 @@ int posenc_fwd_launch(const int64_t* tokens, const float* emb, const void* x, co
 int posenc_bwd_launch(const void* dy, const int64_t* tokens, int64_t padding_idx, const float* pe, void* dx,
                       float* demb, float* dalpha, int dtype, int64_t B, int64_t T, int64_t C, float drop_p,
                       uint64_t seed, uint64_t offset, cudaStream_t s);
-int ln_fwd_launch(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
-                  float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
-                  uint64_t offset, cudaStream_t s);
+int ln_fwd_launch(const void* x, const void* residual, const float* residual_f32, const float* gamma, const float* beta,
+                  void* y, float* y_f32, void* s_out, float* mean, float* rstd, int dtype, int64_t rows, int64_t C,
+                  float eps, float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int64_t ln_bwd_blocks(int64_t rows);
 int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
                   void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,

@@ -16,8 +16,9 @@ constexpr int LN_MAX_CHUNKS = 4;  // per lane: C <= 4 * 32 * 8 = 1024
 
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-    ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ s_out, float* __restrict__ mean,
+    ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ residual_f32,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+                  float* __restrict__ y_f32, T* __restrict__ s_out, float* __restrict__ mean,
                   float* __restrict__ rstd, int64_t rows, int C, float eps, uint32_t thr, float dscale, uint64_t seed,
                   uint64_t offset) {
   if (thr != 0) resolve_seed(seed, offset);
@@ -34,17 +35,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
       const int64_t e0 = row * C + ch * 8;
       load8<T>(x + e0, v[k]);
       if (thr != 0) dropout8(v[k], (uint64_t)e0, thr, dscale, seed, offset);
-      if (residual != nullptr) {
+      if (residual_f32 != nullptr) {  // fp32 residual stream: the un-rounded output of the previous LayerNorm
+        float r[8];
+        load8<float>(residual_f32 + e0, r);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[k][t] += r[t];
+      } else if (residual != nullptr) {
         float r[8];
         load8<T>(residual + e0, r);
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[k][t] += r[t];
       }
-      if (s_out != nullptr) {
-        store8<T>(s_out + e0, v[k]);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[k][t] = round_to<T>(v[k][t]);
-      }
+      // s is saved (in the activation dtype) for the backward pass only; the statistics and the output use the
+      // un-rounded sum -- rounding it first would put one more bf16 rounding (1.6e-3 rms) into every LayerNorm
+      if (s_out != nullptr) store8<T>(s_out + e0, v[k]);
 #pragma unroll
       for (int t = 0; t < 8; ++t) sum += v[k][t];
     }
@@ -78,26 +82,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 #pragma unroll
       for (int t = 0; t < 8; ++t) o[t] = (v[k][t] - mu) * rs * g[t] + b[t];
       store8<T>(y + row * C + ch * 8, o);
+      if (y_f32 != nullptr) store8<float>(y_f32 + row * C + ch * 8, o);
     }
   }
 }
 
-int ln_fwd_launch(const void* x, const void* residual, const float* gamma, const float* beta, void* y, void* s_out,
-                  float* mean, float* rstd, int dtype, int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed,
-                  uint64_t offset, cudaStream_t s) {
+int ln_fwd_launch(const void* x, const void* residual, const float* residual_f32, const float* gamma, const float* beta,
+                  void* y, float* y_f32, void* s_out, float* mean, float* rstd, int dtype, int64_t rows, int64_t C,
+                  float eps, float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s) {
   if (rows == 0) return 0;
   if (C > 8 * 32 * LN_MAX_CHUNKS || C <= 0 || (C & 7)) return -2;
   const uint32_t thr = drop_threshold(drop_p);
   const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   if (dtype == ST5_F32)
-    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y,
-                                                        (float*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed,
-                                                        offset);
+    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)x, (const float*)residual, residual_f32, gamma, beta,
+                                                        (float*)y, y_f32, (float*)s_out, mean, rstd, rows, (int)C, eps,
+                                                        thr, ds, seed, offset);
   else
     ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)s_out,
-        mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, residual_f32, gamma, beta, (__nv_bfloat16*)y, y_f32,
+        (__nv_bfloat16*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
   return (int)cudaGetLastError();
 }
 

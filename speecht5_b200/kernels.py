@@ -117,12 +117,19 @@ def posenc_bwd(dy, tokens, padding_idx, pe, dx, demb, dalpha, drop_p=0.0, seed=0
     _count(1)
 
 
-def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
+def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0, residual_f32=None,
+           y_f32=None):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     lib = _lib.load()
-    _lib.check(lib.st5_ln_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s_out), _ptr(mean),
-                              _ptr(rstd), dtype_id(x), rows, Cc, eps, drop_p, seed, offset, _stream()), "st5_ln_fwd")
+    if residual_f32 is not None or y_f32 is not None:
+        assert (residual_f32 is None or residual_f32.dtype == torch.float32) and (y_f32 is None or y_f32.dtype == torch.float32)
+        _lib.check(lib.st5_ln_fwd_stream(_ptr(x), _ptr(residual), _ptr(residual_f32), _ptr(gamma), _ptr(beta), _ptr(y),
+                                         _ptr(y_f32), _ptr(s_out), _ptr(mean), _ptr(rstd), dtype_id(x), rows, Cc, eps,
+                                         drop_p, seed, offset, _stream()), "st5_ln_fwd_stream")
+    else:
+        _lib.check(lib.st5_ln_fwd(_ptr(x), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s_out), _ptr(mean),
+                                  _ptr(rstd), dtype_id(x), rows, Cc, eps, drop_p, seed, offset, _stream()), "st5_ln_fwd")
     _count(1)
 
 

@@ -126,9 +126,9 @@ class TransformerSentenceEncoderLayer(nn.Module):
         else:  # :112-132
             a = self.self_attn.self_attend(x, self_attn_padding_mask, pe_k=pos_bias, maxpos=maxpos, training=tr)
             o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
-            x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p)
+            x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p, stream=True)
             o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
-            x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p)
+            x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p, stream=True)
         return x, None
 
 
@@ -190,7 +190,7 @@ class TransformerEncoder(nn.Module):
         with torch.no_grad() if not ft else contextlib.ExitStack():
             x = _act_dtype(encoder_in)
             if not self.layer_norm_first:
-                x = ops.residual_layer_norm(x, None, self.layer_norm)
+                x = ops.residual_layer_norm(x, None, self.layer_norm, stream=True)
             x = ops.dropout(x, self.dropout_p, self.training)
             encoder_states = []
             if return_all_hiddens:
@@ -304,7 +304,7 @@ class TransformerDecoderLayer(nn.Module):
             else:
                 a = self.self_attn.self_attend(x, self_attn_padding_mask, causal=causal, training=tr)
                 o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
-                x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p)
+                x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p, stream=True)
         attn = None
         if self.encoder_attn is not None and encoder_out is not None:
             want = need_attn or (not self.training and self.need_attn)
@@ -317,7 +317,7 @@ class TransformerDecoderLayer(nn.Module):
             else:
                 a, attn = self.encoder_attn.cross_attend(x, encoder_out, encoder_padding_mask, want, tr)
                 o = ops.linear(a, self.encoder_attn.out_proj.weight, self.encoder_attn.out_proj.bias)
-                x = ops.residual_layer_norm(o, x, self.encoder_attn_layer_norm, drop_p=p)
+                x = ops.residual_layer_norm(o, x, self.encoder_attn_layer_norm, drop_p=p, stream=True)
             if attn is not None and not need_head_weights:
                 attn = attn.mean(dim=1)
         with torch.no_grad() if not ft else contextlib.ExitStack():
@@ -327,7 +327,7 @@ class TransformerDecoderLayer(nn.Module):
                 x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
             else:
                 o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
-                x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p)
+                x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p, stream=True)
         return x, attn, None
 
     def set_num_updates(self, num_updates):

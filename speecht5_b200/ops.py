@@ -6,6 +6,8 @@ Two numeric modes (Runtime.dtype):
   * torch.float32  -- parity mode: fp32 activations; each GEMM is evaluated as hi*hi + hi*lo + lo*hi over bf16 splits of
     both operands (three accumulate passes of the same tcgen05 kernel), i.e. ~2^-16 relative operand error.
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -30,6 +32,8 @@ class Runtime:
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
         self.attn_fused = True        # bf16 mode, no RPE, Tk <= 320: single-launch fused forward (attention_fused.cu)
         self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
+        self.ffn_gate = os.environ.get("ST5_FFN_GATE", "1") != "0"  # bf16 mode: fc1 stores the backward gate (FFNFn)
+        self.fp32_stream = os.environ.get("ST5_FP32_STREAM", "1") != "0"  # bf16 mode: fp32 residual stream between LayerNorms
         # trainer hooks: stage_callback(key, x) is called at the entry of every encoder / decoder layer (gradient-exchange
         # overlap point); layer_keep (device [n_enc + n_dec] 0/1 mask, CUDA-graph mode) / layer_keep_host (eager mode)
         # carry the trainer's LayerDrop draw -- when both are None the model draws for itself like the reference
@@ -369,8 +373,13 @@ class FFNFn(torch.autograd.Function):
         pre = torch.empty_like(h)
         off_a = RT.next_offset() if drop_a > 0 else 0
         xa = _split(x2)
-        mm(xa, w1s, h, M=M, N=F_, Kd=D, a_ld=x2.stride(0), b_ld=D, c_ld=F_, bias=bb1, c_pre=pre, act=act,
-           drop_p=drop_a, seed=RT.seed, offset=off_a)
+        # throughput mode: the fc1 epilogue stores the backward GATE keep * scale * gelu'(pre) in place of the
+        # pre-activation (tanh(u) is shared with the forward value), so the dH GEMM's epilogue is a single multiply
+        gate = act == "gelu_tanh" and x.dtype == torch.bfloat16 and F_ % 8 == 0 and RT.ffn_gate
+        mm(xa, w1s, h, M=M, N=F_, Kd=D, a_ld=x2.stride(0), b_ld=D, c_ld=F_, bias=bb1, c_pre=pre,
+           act="gelu_tanh_gate" if gate else act, drop_p=drop_a, seed=RT.seed, offset=off_a)
+        if gate:
+            act = "gate"
         o = torch.empty((M, D), dtype=x.dtype, device=x.device)
         off_o = RT.next_offset() if drop_o > 0 else 0
         res2 = residual.reshape(M, D).contiguous() if residual is not None else None
@@ -398,8 +407,8 @@ class FFNFn(torch.autograd.Function):
         ga = _split(do2)
         # dH_pre = (dO W2) * dropmask_a * act'(pre)  -- fused into the GEMM epilogue
         dhp = torch.empty((M, F_), dtype=do.dtype, device=dev)
-        mm(ga, w2s, dhp, M=M, N=F_, Kd=D, a_ld=D, b_mn=True, b_ld=F_, c_ld=F_, drop_p=drop_a, seed=seed, offset=off_a,
-           actgrad_pre=pre, actgrad_act=act)
+        mm(ga, w2s, dhp, M=M, N=F_, Kd=D, a_ld=D, b_mn=True, b_ld=F_, c_ld=F_, drop_p=0.0 if act == "gate" else drop_a,
+           seed=seed, offset=off_a, actgrad_pre=pre, actgrad_act=act)
         gh = _split(dhp)
 
         def wgrad(gy, gy_ld, xin, xin_ld, w, n_out, n_in):
@@ -436,7 +445,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
     (transformer_layer.py:112-132, 343-391) and the encoder input LayerNorm (encoder.py:226-227)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps, drop_p):
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p, res_f32=None, y_f32=None):
         x = x.contiguous()
         Cc = x.shape[-1]
         rows = x.numel() // Cc
@@ -446,7 +455,8 @@ class ResidualLayerNormFn(torch.autograd.Function):
         rstd = torch.empty_like(mean)
         off = RT.next_offset() if drop_p > 0 else 0
         res = residual.contiguous() if residual is not None else None
-        K.ln_fwd(x, res, gamma.detach(), beta.detach(), y, s, mean, rstd, eps, drop_p, RT.seed, off)
+        K.ln_fwd(x, res, gamma.detach(), beta.detach(), y, s, mean, rstd, eps, drop_p, RT.seed, off,
+                 residual_f32=res_f32, y_f32=y_f32)
         ctx.save_for_backward(s, mean, rstd, gamma)
         ctx.meta = (drop_p, off, RT.seed, residual is not None, id(gamma), id(beta))
         return y
@@ -467,11 +477,24 @@ class ResidualLayerNormFn(torch.autograd.Function):
         K.ln_bwd(dy, s, mean, rstd, gamma.detach(), ds, dx, dgamma, dbeta, drop_p, seed, off)
         if direct:
             dgamma = dbeta = None
-        return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None
+        return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None, None, None
 
 
-def residual_layer_norm(x, residual, ln, drop_p=0.0):
-    return ResidualLayerNormFn.apply(x, residual, ln.weight, ln.bias, ln.eps, drop_p)
+def residual_layer_norm(x, residual, ln, drop_p=0.0, stream=False):
+    """stream=True (post-LN blocks, throughput mode): keep an fp32 copy of the output next to the bf16 activations and
+    feed it to the next block's residual add, so that the residual stream is never rounded to bf16 between layers. The
+    copy rides along as a plain attribute of the returned tensor (no autograd node: gradients flow through the bf16
+    tensor exactly as before)."""
+    res_f32 = getattr(residual, "_st5_f32", None) if residual is not None else None
+    y_f32 = None
+    if stream and RT.fp32_stream and x.dtype == torch.bfloat16 and x.is_cuda:
+        y_f32 = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if res_f32 is not None and (res_f32.shape != x.shape or not res_f32.is_contiguous()):
+        res_f32 = None
+    y = ResidualLayerNormFn.apply(x, residual, ln.weight, ln.bias, ln.eps, drop_p, res_f32, y_f32)
+    if y_f32 is not None:
+        y._st5_f32 = y_f32
+    return y
 
 
 # =================================================================================================== pos. encoding

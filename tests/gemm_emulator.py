@@ -52,8 +52,9 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         assert nb1 == 1 and bias2.dtype == torch.float32 and bias2_rows > 0
         v = v + bias2.double()[torch.arange(M) // bias2_rows][None, :, :N]
     if c_pre is not None:
-        torch.as_strided(c_pre, (nb1, M, N), (c_bs[0], c_ld, 1), c_pre.storage_offset()).copy_(v.to(c_pre.dtype))
-    if act in ("gelu", "gelu_tanh"):
+        second = _gelu_grad(v) if act == "gelu_tanh_gate" else v  # ..._gate: the backward multiplier replaces the pre-activation
+        torch.as_strided(c_pre, (nb1, M, N), (c_bs[0], c_ld, 1), c_pre.storage_offset()).copy_(second.to(c_pre.dtype))
+    if act in ("gelu", "gelu_tanh", "gelu_tanh_gate"):
         v = torch.nn.functional.gelu(v)
     elif act == "relu":
         v = torch.relu(v)
@@ -63,7 +64,7 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         assert act in (None, "none")
     if actgrad_pre is not None:  # activation backward fused into the product: v *= act'(pre[m][n])
         pre = torch.as_strided(actgrad_pre, (nb1, M, N), (c_bs[0], c_ld, 1), actgrad_pre.storage_offset()).double()
-        v = v * _act_grad(pre, actgrad_act)
+        v = v * (pre if actgrad_act == "gate" else _act_grad(pre, actgrad_act))
     if residual is not None:  # same layout and dtype as C, added after the activation
         assert residual.dtype == out.dtype
         v = v + torch.as_strided(residual, (nb1, M, N), (c_bs[0], c_ld, 1), residual.storage_offset()).double()
@@ -99,14 +100,18 @@ def colsum(x2d, out, group_rows=0, accumulate=False, ld=None):
     flat.copy_(((flat.double() if accumulate else 0) + tot.reshape(-1)).to(out.dtype))
 
 
-def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0):
-    """st5_ln_fwd without dropout: s = x (+ residual), y = LayerNorm(s) over the last dimension."""
+def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed=0, offset=0, residual_f32=None,
+           y_f32=None):
+    """st5_ln_fwd / st5_ln_fwd_stream without dropout: s = x (+ residual), y = LayerNorm(s) over the last dimension."""
     assert drop_p == 0.0
-    s_ = x.double() + (residual.double() if residual is not None else 0.0)
+    res = residual_f32 if residual_f32 is not None else residual
+    s_ = x.double() + (res.double() if res is not None else 0.0)
     mu = s_.mean(-1, keepdim=True)
     var = s_.var(-1, unbiased=False, keepdim=True)
     rs = 1.0 / torch.sqrt(var + eps)
     y.copy_(((s_ - mu) * rs * gamma.double() + beta.double()).to(y.dtype))
+    if y_f32 is not None:
+        y_f32.copy_(((s_ - mu) * rs * gamma.double() + beta.double()).float())
     if s_out is not None:
         s_out.copy_(s_.to(s_out.dtype))
     mean.copy_(mu.reshape(-1).float())
@@ -191,7 +196,7 @@ def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, s
     dbeta.add_(gb.float())
 
 
-def residual_layer_norm(x, residual, ln, drop_p=0.0):
+def residual_layer_norm(x, residual, ln, drop_p=0.0, stream=False):
     """ops.residual_layer_norm as differentiable torch ops (for CPU checks of whole training steps)."""
     assert drop_p == 0.0
     s_ = x if residual is None else x + residual

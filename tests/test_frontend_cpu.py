@@ -236,7 +236,7 @@ def test_speech_to_text_model_forward_and_greedy_decoding_on_emulated_kernels(mo
     monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
     RT.invalidate_shadows()
     torch.manual_seed(6)
-    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0, mask_channel_prob=0.0)
     oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
     with torch.no_grad():
         oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)
@@ -303,7 +303,7 @@ def test_kv_cache_decoding_equals_prefix_recomputation_on_emulated_kernels(monke
     RT.invalidate_shadows()
     # (a) text decoding
     torch.manual_seed(6)
-    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0, mask_channel_prob=0.0)
     oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
     with torch.no_grad():
         oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)
@@ -357,7 +357,7 @@ def test_speech_to_text_training_step_gradients_on_emulated_kernels(monkeypatch)
     torch.manual_seed(4)
     over = dict(encoder_layers=1, decoder_layers=1, bert_init=True, dropout=0.0, attention_dropout=0.0,
                 activation_dropout=0.0, encoder_layerdrop=0.0, decoder_layerdrop=0.0, mask_prob=0.0,
-                feature_grad_mult=1.0)
+                mask_channel_prob=0.0, feature_grad_mult=1.0)
     oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).train()
     model = T5TransformerModel.build_model(make_args(
         "t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,

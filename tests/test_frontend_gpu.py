@@ -98,7 +98,7 @@ def test_speech_to_text_step_against_the_oracle(cuda, dtype):
     torch.manual_seed(4)
     over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, dropout=0.0, attention_dropout=0.0,
                 activation_dropout=0.0, encoder_layerdrop=0.0, decoder_layerdrop=0.0, mask_prob=0.0,
-                feature_grad_mult=1.0)
+                mask_channel_prob=0.0, feature_grad_mult=1.0)
     oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).train()
     args = make_args("t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, use_conv_pos=True,
                      use_sinc_pos=True, **over)
@@ -156,7 +156,7 @@ def test_greedy_text_decoding_token_ids_match_the_oracle(cuda):
     RT.dtype = torch.float32
     RT.invalidate_shadows()
     torch.manual_seed(6)
-    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0, mask_channel_prob=0.0)
     oracle = O.T5TransformerModelASROracle(O.base_asr_args(**over)).eval()
     with torch.no_grad():
         oracle.text_decoder_postnet.output_projection.weight.mul_(8.0)  # spread the logits

@@ -21,7 +21,8 @@ def test_registry_names_and_forward_signature():
     sig = list(inspect.signature(T5TransformerModel.forward).parameters)
     assert sig == ["self", "source", "src_tokens", "src_lengths", "prev_output_tokens", "tgt_lengths", "spkembs",
                    "target_list", "task_name", "padding_mask", "only_hubert", "only_ctc", "feature_only",
-                   "tgt_enc_layer", "mask"]  # models/speecht5.py:786
+                   "tgt_enc_layer", "mask",
+                   "mask_indices", "mask_channel_indices"]  # reference signature + two optional extras (trailing, keyword)  # models/speecht5.py:786
 
 
 def test_arch_presets_match_reference_defaults():

@@ -148,8 +148,8 @@ def test_hifigan_oracle_matches_the_reference_generator():
     """SpeechUT/fairseq/.../hifigan.py Generator -> oracle.audio_oracle.HifiGanGenerator on the same weights."""
     from oracle.audio_oracle import HifiGanGenerator
     blob = load("ref_hifigan_tiny")
-    cfg = dict(model_in_dim=80, upsample_initial_channel=32, upsample_rates=[4, 4, 4, 4],
-               upsample_kernel_sizes=[8, 8, 8, 8], resblock_kernel_sizes=[3, 7, 11],
+    cfg = dict(model_in_dim=80, upsample_initial_channel=64, upsample_rates=[4, 4, 4],
+               upsample_kernel_sizes=[8, 8, 8], resblock_kernel_sizes=[3, 7, 11],
                resblock_dilation_sizes=[[1, 3, 5]] * 3)
     gen = HifiGanGenerator(cfg).eval()
     from oracle.audio_oracle import load_reference_hifigan_state
