@@ -153,20 +153,26 @@ int st5_attn_bwd(const st5_attn_args* args, void* stream);
 
 /* Fused tcgen05 attention forward (bf16, Tk <= 320): QK^T -> masks -> softmax -> dropout -> PV in ONE launch, scores
  * resident in TMEM. Uses the q/k/v/out/probs/key_pad/scale/dropout fields of st5_attn_args exactly like st5_attn_fwd;
- * additionally writes lse[b][h][i] = log sum_j exp(scale*q_i.k_j) (may be NULL). probs (optional) receives the
- * undropped probabilities in probs_dtype.
+ * additionally writes lse[b][h][i] = log sum_j exp(scale*q_i.k_j) (may be NULL). probs (optional, only when the caller
+ * wants them: need_head_weights) receives the undropped normalised probabilities in probs_dtype.
+ * What the backward pass reads back (both optional, but together): psave [B,H,Tq,p_ld] BF16 = exp(s - rowmax), NOT
+ * normalised, with the SIGN BIT set on elements dropout removed (probabilities are non-negative; a dropped zero is -0),
+ * and inv_l [B,H,Tq] = 1 / rowsum. p_ld must be a multiple of 8, psave 16-byte aligned. out_f32 (optional)
+ * [B,Tq,H*64] FP32 receives the un-rounded output: the backward's row constant delta = dO.O is the subtrahend of a
+ * cancelling difference (dS = P (dP - delta)) and must not carry the BF16 rounding of `out`.
  * Relative positions (encoder.py:239-246): pe_k != NULL selects the skewed-bias variant; here pe_k must point to a
  * BF16 copy of the [2*maxpos][64] table, and Tq, Tk <= maxpos <= 160 (clamp(i-j) never clips), no causal mask. */
-int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* stream);
-/* Fused tcgen05 attention backward (multihead_attention.py:340-389 differentiated). args->probs must be the
- * probabilities st5_attn_fused_fwd saved (BF16, or the FP32 copy returned to the caller; p_ld a multiple of 8): they are
- * read back instead of recomputed, so every step needs one score-sized MMA (dP = dO V^T) and the kernel double buffers
- * dP, the dropout(P)/dS operand tiles, dQ and the Q/dO tiles. Reads q/k/v, out (forward result), dout and the dropout
- * fields; optional dprobs_ext (needs FP32 probs); writes dq/dk/dv (same layouts as q/k/v). lse is unused (may be NULL).
- * Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
+int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* psave, float* inv_l, float* out_f32, void* stream);
+/* Fused tcgen05 attention backward (multihead_attention.py:340-389 differentiated). psave / inv_l are what
+ * st5_attn_fused_fwd wrote: probabilities and dropout decisions are read back instead of recomputed (no exponential, no
+ * Philox), so every step needs one score-sized MMA (dP = dO V^T) and the kernel double buffers dP, the dropout(P)/dS
+ * operand tiles, dQ and the Q/dO tiles. Reads q/k/v, out (forward result), dout and drop_p; optional dprobs_ext (then
+ * args->probs must be the FP32 probabilities the forward returned); writes dq/dk/dv (same layouts as q/k/v).
+ * out_f32 (optional): what the forward wrote there. Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
  * Relative positions (pe_k != NULL): args->ds additionally receives dS as BF16 [B,H,Tq,p_ld] for st5_attn_dqp_scatter
  * and the two table GEMMs; dq then holds only the q.k part of the gradient. */
-int st5_attn_fused_bwd(const st5_attn_args* args, const float* lse, float* delta, float* dq_acc, void* stream);
+int st5_attn_fused_bwd(const st5_attn_args* args, const void* psave, const float* inv_l, const float* out_f32,
+                       float* delta, float* dq_acc, void* stream);
 
 /* Tensor-core (bf16) attention path: the contractions run on st5_gemm_bf16 (batched over heads and utterances, q/k/v
  * read in place from the fused projection buffers); these three row kernels are the non-GEMM steps between them.

@@ -50,7 +50,10 @@ struct FusedFwdParams {
   float scale_log2;        // scale * log2(e)
   const uint8_t* key_pad;  // [B][Tk] or null
   __nv_bfloat16* out; long o_ld, o_bs;
-  float* lse;              // [B][H][Tq] natural-log sum-exp of the scaled scores (for the backward pass)
+  float* lse;              // [B][H][Tq] natural-log sum-exp of the scaled scores
+  __nv_bfloat16* psave;    // [B][H][Tq][p_ld] for the backward pass: exp(s - rowmax) (NOT normalised), sign bit = dropped
+  float* inv_l;            // [B][H][Tq] 1 / sum_j exp(s - rowmax): the backward's normaliser of psave
+  float* out_f32;          // optional [B][Tq][H*64]: the un-rounded output, for the backward's row constant dO.O
   void* probs; int probs_fp32; long p_ld;  // optional undropped probabilities [B][H][Tq][p_ld]
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
   int pe_row0;             // RPE: table row held by PE' row 0 of query tile 0 (= 1 + maxpos - 160; may be negative)
@@ -205,6 +208,13 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       if constexpr (NG == 2) tmem_ld_32x32(trow + FA_O_COL + (uint32_t)(half * CW), v);
       else tmem_ld_32x16(trow + FA_O_COL + (uint32_t)(half * CW), v);
       tmem_ld_wait();
+      if (row_ok && p.out_f32 != nullptr) {
+        float* d32 = p.out_f32 + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + half * CW;
+#pragma unroll
+        for (int t = 0; t < CW; t += 4)
+          *reinterpret_cast<float4*>(d32 + t) = make_float4(__uint_as_float(v[t]) * inv, __uint_as_float(v[t + 1]) * inv,
+                                                            __uint_as_float(v[t + 2]) * inv, __uint_as_float(v[t + 3]) * inv);
+      }
       if (row_ok) {
         __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)i * p.o_ld + h * 64 + half * CW;
 #pragma unroll
@@ -306,23 +316,34 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       if (p.drop_thr != 0)
         kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(c * 32), p.drop_thr);
       tmem_ld_wait();
-      float e[32];
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float ev = ((vb >> t) & 1u) ? fast_ex2(__uint_as_float(v[t]) * p.scale_log2 - mm) : 0.f;
-        sum += ev;
-        e[t] = ((kb_ >> t) & 1u) ? ev * p.drop_scale : 0.f;
-      }
       uint8_t* blk = sP + (c >> 1) * 16384 + r * 128;  // block = 64 keys, row r at r*128 B, chunk XOR (r & 7)
       const int cbase = (c & 1) * 4;
+      // what the backward pass reads back: the un-normalised exponentials, a dropped element carries the sign bit
+      // (probabilities are non-negative, so the bit is free; -0 for a dropped zero): no Philox and no exp there
+      __nv_bfloat16* psv = (p.psave != nullptr && row_ok) ? p.psave + prow * p.p_ld + c * 32 : nullptr;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 pk;
-        pk.x = pack_bf16(e[8 * g], e[8 * g + 1]);
-        pk.y = pack_bf16(e[8 * g + 2], e[8 * g + 3]);
-        pk.z = pack_bf16(e[8 * g + 4], e[8 * g + 5]);
-        pk.w = pack_bf16(e[8 * g + 6], e[8 * g + 7]);
+        float ev[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int u = 8 * g + t;
+          ev[t] = ((vb >> u) & 1u) ? fast_ex2(__uint_as_float(v[u]) * p.scale_log2 - mm) : 0.f;
+          sum += ev[t];
+        }
+        const uint32_t k8 = kb_ >> (8 * g);
+        uint4 pk, ps;
+        pk.x = pack_bf16((k8 & 1u) ? ev[0] * p.drop_scale : 0.f, (k8 & 2u) ? ev[1] * p.drop_scale : 0.f);
+        pk.y = pack_bf16((k8 & 4u) ? ev[2] * p.drop_scale : 0.f, (k8 & 8u) ? ev[3] * p.drop_scale : 0.f);
+        pk.z = pack_bf16((k8 & 16u) ? ev[4] * p.drop_scale : 0.f, (k8 & 32u) ? ev[5] * p.drop_scale : 0.f);
+        pk.w = pack_bf16((k8 & 64u) ? ev[6] * p.drop_scale : 0.f, (k8 & 128u) ? ev[7] * p.drop_scale : 0.f);
         *reinterpret_cast<uint4*>(blk + (((cbase + g) ^ (r & 7)) << 4)) = pk;
+        if (psv != nullptr && c * 32 + 8 * g + 8 <= p.p_ld) {
+          ps.x = pack_bf16((k8 & 1u) ? ev[0] : -ev[0], (k8 & 2u) ? ev[1] : -ev[1]);
+          ps.y = pack_bf16((k8 & 4u) ? ev[2] : -ev[2], (k8 & 8u) ? ev[3] : -ev[3]);
+          ps.z = pack_bf16((k8 & 16u) ? ev[4] : -ev[4], (k8 & 32u) ? ev[5] : -ev[5]);
+          ps.w = pack_bf16((k8 & 64u) ? ev[6] : -ev[6], (k8 & 128u) ? ev[7] : -ev[7]);
+          *reinterpret_cast<uint4*>(psv + 8 * g) = ps;
+        }
       }
     }
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -335,8 +356,10 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
 #pragma unroll
     for (int g = 1; g < NG; ++g) sum += red_sum[g * 128 + r];
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    if (half == 0 && row_ok && p.lse != nullptr)
-      p.lse[prow] = (sum > 0.f) ? (mm + log2f(sum)) * 0.6931471805599453f : -INFINITY;
+    if (half == 0 && row_ok) {
+      if (p.lse != nullptr) p.lse[prow] = (sum > 0.f) ? (mm + log2f(sum)) * 0.6931471805599453f : -INFINITY;
+      if (p.inv_l != nullptr) p.inv_l[prow] = inv;
+    }
     if (p.probs != nullptr) {
       // normalised, undropped probabilities for the caller (overlaps the PV MMA)
       const int pchunks = (int)((p.p_ld + 31) / 32);
@@ -411,13 +434,16 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld, i
 
 using namespace st5;
 
-extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stream) {
+extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* psave, float* inv_l, float* out_f32,
+                                  void* stream) {
   const bool rpe = a->pe_k != nullptr;
   if (a->dtype != ST5_BF16 || a->Tk > FA_MAX_TK || a->Tk <= 0 || a->Tq <= 0)
     return set_error(-2, "st5_attn_fused_fwd: needs bf16 and Tk <= 320");
   if (rpe && (a->causal || a->maxpos <= 0 || a->maxpos > FR_MAX_T || a->Tk > a->maxpos || a->Tq > a->maxpos))
     return set_error(-5, "st5_attn_fused_fwd: relative positions need Tq, Tk <= maxpos <= 160 (no clipping), no causal mask");
-  if (a->probs != nullptr && a->p_ld < a->Tk) return set_error(-3, "st5_attn_fused_fwd");
+  if ((a->probs != nullptr || psave != nullptr) && a->p_ld < a->Tk) return set_error(-3, "st5_attn_fused_fwd");
+  if (psave != nullptr && ((a->p_ld & 7) || (reinterpret_cast<uintptr_t>(psave) & 15) || inv_l == nullptr))
+    return set_error(-3, "st5_attn_fused_fwd: psave needs a row pitch that is a multiple of 8, 16-byte alignment and inv_l");
   if ((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return set_error(-4, "st5_attn_fused_fwd: out must be 16-byte aligned");
   CUtensorMap mq, mk, mv;
@@ -447,6 +473,9 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* stre
   p.key_pad = a->key_pad;
   p.out = (__nv_bfloat16*)a->out; p.o_ld = a->o_ld; p.o_bs = a->o_bs;
   p.lse = lse;
+  p.psave = reinterpret_cast<__nv_bfloat16*>(psave);
+  p.inv_l = inv_l;
+  p.out_f32 = out_f32;
   p.probs = a->probs; p.probs_fp32 = a->probs_dtype == ST5_F32; p.p_ld = a->p_ld;
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;

@@ -1,9 +1,10 @@
-// Fused attention backward on tcgen05. The probabilities come from the forward pass (bf16, or the fp32 copy returned
-// to the caller), so one step needs a single score-sized MMA and the schedule can be fully overlapped.
+// Fused attention backward on tcgen05. The probabilities come from the forward pass -- bf16 exp(s - rowmax) with the
+// dropout decision in the sign bit, normalised here by the saved 1/rowsum -- so one step needs a single score-sized MMA,
+// no exponential and no random numbers, and the schedule can be fully overlapped.
 //
 // One CTA per (head, utterance). Loop: key block kb (128 keys) outer, query tile qt (128 rows) inner; step it:
 //   MMA1(it)   dP = dO_qt V_kb^T                     -> TMEM dP[it & 1]               (issued one step AHEAD)
-//   threads    (16 warps, 1 thread = 1 query row x 32 keys): dropout mask, dS = P * (dP_masked + dP_ext - delta);
+//   threads    (16 warps, 1 thread = 1 query row x 32 keys): dS = P * (dP_masked + dP_ext - delta);
 //              dropout(P) and dS -> shared memory tiles [it & 1] (bf16, 128B-swizzled [q][key])
 //   MMA2(it)   dV_kb += dropout(P)^T dO_qt, dK_kb += dS^T Q_qt   (A = the smem tiles read MN-major)
 //              dQ_qt(kb) = dS K_kb                    -> TMEM dQ[it & 1]
@@ -33,15 +34,15 @@ struct FusedBwdParams {
   int B, H, Tq, Tk, causal;
   float scale, scale_log2;
   const uint8_t* key_pad;
-  const float* lse; const float* delta;
+  const float* inv_l; const float* delta;
   const float* dp_ext; long p_ld;
   __nv_bfloat16* dq; long q_ld, q_bs;
   __nv_bfloat16* dk; long k_ld, k_bs;
   __nv_bfloat16* dv; long v_ld, v_bs;
   float* dq_acc;  // [B][Tq][H*64] fp32 scratch
-  const void* probs_in; int probs_fp32;  // [B][H][Tq][p_ld]: P from the forward pass (bf16 or fp32)
+  const __nv_bfloat16* psave;  // [B][H][Tq][p_ld] from the forward pass: exp(s - rowmax), sign bit = dropped element
   __nv_bfloat16* ds_out;          // optional [B][H][Tq][p_ld]: dS for the relative-position contractions
-  uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
+  float drop_scale;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -52,9 +53,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // delta[row] = sum_c dO*O (+ sum_j P*dP_ext): the softmax-backward row constant.
 // Plain case: 8 lanes per (b,h,i) row (one 16-byte load of dO and O each), 4 rows per warp. With an external dP the
 // row also needs sum_j P*dP_ext over Tk fp32 pairs: one warp per row.
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, long o_ld,
-                                  long o_bs, const float* __restrict__ probs, const float* __restrict__ dpx, long p_ld,
-                                  float* __restrict__ delta, int B, int H, int Tq, int Tk) {
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
+                                  const float* __restrict__ O32, long o_ld, long o_bs, const float* __restrict__ probs,
+                                  const float* __restrict__ dpx, long p_ld, float* __restrict__ delta, int B, int H,
+                                  int Tq, int Tk) {
   const int lane = threadIdx.x & 31;
   const int64_t nrows = (int64_t)B * H * Tq;
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -64,13 +66,22 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
     if (row < nrows) {
       const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
       const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + (lane & 7) * 8;
-      const uint4 ua = *reinterpret_cast<const uint4*>(dO + off), uo = *reinterpret_cast<const uint4*>(O + off);
+      const uint4 ua = *reinterpret_cast<const uint4*>(dO + off);
       const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
-      const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
+      if (O32 != nullptr) {  // the forward's un-rounded output: dS = P (dP - delta) cancels, delta must not carry bf16 error
+        const float* o32 = O32 + ((int64_t)b * Tq + i) * (H * 64) + h * 64 + (lane & 7) * 8;
+        const float4 o0 = *reinterpret_cast<const float4*>(o32), o1 = *reinterpret_cast<const float4*>(o32 + 4);
+        const float2 a0 = __bfloat1622float2(ha[0]), a1 = __bfloat1622float2(ha[1]), a2 = __bfloat1622float2(ha[2]),
+                     a3 = __bfloat1622float2(ha[3]);
+        acc = a0.x * o0.x + a0.y * o0.y + a1.x * o0.z + a1.y * o0.w + a2.x * o1.x + a2.y * o1.y + a3.x * o1.z + a3.y * o1.w;
+      } else {
+        const uint4 uo = *reinterpret_cast<const uint4*>(O + off);
+        const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 a = __bfloat1622float2(ha[t]), o = __bfloat1622float2(ho[t]);
-        acc += a.x * o.x + a.y * o.y;
+        for (int t = 0; t < 4; ++t) {
+          const float2 a = __bfloat1622float2(ha[t]), o = __bfloat1622float2(ho[t]);
+          acc += a.x * o.x + a.y * o.y;
+        }
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -84,7 +95,9 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
   const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + lane * 2;
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
-  const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
+  float2 o;
+  if (O32 != nullptr) o = *reinterpret_cast<const float2*>(O32 + ((int64_t)b * Tq + i) * (H * 64) + h * 64 + lane * 2);
+  else o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
   float acc = a.x * o.x + a.y * o.y;
   const float* pr = probs + row * p_ld;
   const float* dx = dpx + row * p_ld;
@@ -93,8 +106,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   if (lane == 0) delta[row] = acc;
 }
 
-__global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 64 K file: removes the 36/64 B spill of the 96-register build
-
+__global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 20: 96 registers is the ceiling)
     attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
                           const FusedBwdParams p) {
@@ -228,8 +240,6 @@ __global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 6
     const int grp = (warp - 2) >> 2;  // 32-key chunk of the block, 16-channel slice of dQ, 32-channel slice of dK|dV
     const int r = q * 32 + (int)lane_id();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    uint64_t dseed = p.seed, doffset = p.offset;
-    if (p.drop_thr != 0) resolve_seed(dseed, doffset);
     // ---- read-out of one finished step: dQ partial of (kb, qt); dK / dV after the last query tile of a key block
     auto read_out = [&](int kb, int qt, int j) {
       const int buf = j & 1;
@@ -295,12 +305,12 @@ __global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 6
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&bar_tdone[buf]);
     };
-    // 64 bytes of this thread's row of P for step (kb2, qt2), as raw bf16x8 words
+    // 64 bytes of this thread's row of the saved exponentials for step (kb2, qt2), as raw bf16x8 words (zero -- "kept,
+    // probability 0" -- for dead rows and beyond the row pitch)
     auto fetch_p = [&](int kb2, int qt2, uint4 (&dst)[4]) {
       const int i2 = qt2 * FB_T + r;
       const int col = kb2 * FB_T + grp * 32;
-      const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(p.probs_in) +
-                                (((int64_t)b * p.H + h) * p.Tq + i2) * p.p_ld + col;
+      const __nv_bfloat16* pr = p.psave + (((int64_t)b * p.H + h) * p.Tq + i2) * p.p_ld + col;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         dst[g] = make_uint4(0u, 0u, 0u, 0u);
@@ -310,7 +320,7 @@ __global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 6
     uint4 pcur[4], pnext[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) pcur[g] = pnext[g] = make_uint4(0u, 0u, 0u, 0u);
-    if (!p.probs_fp32 && nkb > 0 && nqt > 0) fetch_p(0, 0, pcur);
+    if (nkb > 0 && nqt > 0) fetch_p(0, 0, pcur);
     int it = 0, pend_kb = -1, pend_qt = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int qt0 = p.causal ? kb : 0;
@@ -321,75 +331,74 @@ __global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 6
         const bool row_ok = i < p.Tq;
         const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
         const float delta = row_ok ? p.delta[prow] : 0.f;
+        const float invl = row_ok ? p.inv_l[prow] : 0.f;
         const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
         const int c = grp;  // this warp's 32-key chunk of the block
         const int col0 = k0 + c * 32;
-        // saved probabilities of this row's chunk (zero where masked, beyond the row pitch and for dead rows): the
-        // bf16 copy was prefetched during the previous step (pcur); the next step's chunk is requested now
-        if (!p.probs_fp32) {
+        // the saved exponentials of this row's chunk were prefetched during the previous step (pcur); the next step's
+        // chunk is requested now
+        {
           int kb2 = kb, qt2 = qt + 1;
           if (qt2 >= nqt) { kb2 = kb + 1; qt2 = p.causal ? kb2 : 0; }
           if (kb2 < nkb && qt2 < nqt) fetch_p(kb2, qt2, pnext);
         }
-        uint32_t kb_ = 0xffffffffu;
-        if (p.drop_thr != 0)
-          kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)col0, p.drop_thr);
         mbar_wait(&bar_dp[buf], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
-        uint32_t dv[32];
-        tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(buf * 128 + c * 32), dv);
-        tmem_ld_wait();
-        // dP as seen by the softmax: dropout backward of dO V^T, plus the caller's gradient on the probabilities
-        // (this row's 32 floats = one 128-byte line, fetched as eight 16-byte loads)
-#pragma unroll
-        for (int t = 0; t < 32; ++t)
-          dv[t] = ((kb_ >> t) & 1u) ? __float_as_uint(__uint_as_float(dv[t]) * p.drop_scale) : 0u;
-        if (dpx != nullptr) {
-          if ((p.p_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dp_ext) & 15) == 0) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (col0 + 4 * g + 4 <= p.p_ld) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 4 * g));
-                dv[4 * g] = __float_as_uint(__uint_as_float(dv[4 * g]) + x.x);
-                dv[4 * g + 1] = __float_as_uint(__uint_as_float(dv[4 * g + 1]) + x.y);
-                dv[4 * g + 2] = __float_as_uint(__uint_as_float(dv[4 * g + 2]) + x.z);
-                dv[4 * g + 3] = __float_as_uint(__uint_as_float(dv[4 * g + 3]) + x.w);
-              }
-          } else {
-#pragma unroll
-            for (int t = 0; t < 32; ++t)
-              if (col0 + t < p.Tk) dv[t] = __float_as_uint(__uint_as_float(dv[t]) + dpx[col0 + t]);
-          }
-        }
-        // (dP is finite everywhere: V rows beyond Tk and dO rows beyond Tq arrive as zeros from TMA)
         uint8_t* bp = sPd + buf * 32768 + (c >> 1) * 16384 + r * 128;
         uint8_t* bs = sdS + buf * 32768 + (c >> 1) * 16384 + r * 128;
         const int cbase = (c & 1) * 4;
+        // warp-uniform fast path: no live query row in this warp's 32 rows, or the whole key chunk lies beyond Tk --
+        // P is zero there, so both operand tiles get zeros (they are contracted over, so they must be written)
+        const bool dead = (qt * FB_T + q * 32 >= p.Tq) || (col0 >= p.Tk);
+        if (dead) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int sw = ((cbase + g) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(bp + sw) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(bs + sw) = make_uint4(0u, 0u, 0u, 0u);
+            if (p.ds_out != nullptr && row_ok && col0 + 8 * g + 8 <= p.p_ld)
+              *reinterpret_cast<uint4*>(p.ds_out + prow * p.p_ld + col0 + 8 * g) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+        // (dP is finite everywhere: V rows beyond Tk and dO rows beyond Tq arrive as zeros from TMA)
+        uint32_t dv[16];  // dP in two halves of 16 columns: 16 live registers instead of 32 (the kernel sits at the cap)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pd8[8], ds8[8], pv8[8];
-          if (p.probs_fp32) {
-            const float* pr = reinterpret_cast<const float*>(p.probs_in) + prow * p.p_ld + col0 + 8 * g;
-            float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-            if (row_ok && col0 + 8 * g + 8 <= p.p_ld) {
-              u0 = __ldg(reinterpret_cast<const float4*>(pr));
-              u1 = __ldg(reinterpret_cast<const float4*>(pr + 4));
-            }
-            pv8[0] = u0.x; pv8[1] = u0.y; pv8[2] = u0.z; pv8[3] = u0.w;
-            pv8[4] = u1.x; pv8[5] = u1.y; pv8[6] = u1.z; pv8[7] = u1.w;
-          } else {
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&pcur[g]);
+          if ((g & 1) == 0) {
+            tmem_ld_32x16(trow + FB_COL_DP + (uint32_t)(buf * 128 + c * 32 + 8 * g), dv);
+            tmem_ld_wait();
+          }
+          const uint32_t w4[4] = {pcur[g].x, pcur[g].y, pcur[g].z, pcur[g].w};
+          float xd[8];
+          xd[0] = xd[1] = xd[2] = xd[3] = xd[4] = xd[5] = xd[6] = xd[7] = 0.f;
+          if (dpx != nullptr) {  // the caller's gradient on the probabilities: this row's 8 floats of the chunk
+            if ((p.p_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dp_ext) & 15) == 0) {
+              if (col0 + 8 * g + 8 <= p.p_ld) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 8 * g));
+                const float4 x1 = __ldg(reinterpret_cast<const float4*>(dpx + col0 + 8 * g + 4));
+                xd[0] = x0.x; xd[1] = x0.y; xd[2] = x0.z; xd[3] = x0.w;
+                xd[4] = x1.x; xd[5] = x1.y; xd[6] = x1.z; xd[7] = x1.w;
+              }
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(hh[e]);
-              pv8[2 * e] = f.x;
-              pv8[2 * e + 1] = f.y;
+              for (int t = 0; t < 8; ++t)
+                if (col0 + 8 * g + t < p.Tk) xd[t] = dpx[col0 + 8 * g + t];
             }
           }
+          float pd8[8], ds8[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            pd8[t] = ((kb_ >> (8 * g + t)) & 1u) ? pv8[t] * p.drop_scale : 0.f;
-            ds8[t] = pv8[t] * (__uint_as_float(dv[8 * g + t]) - delta);
+          for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int t = 2 * e + hh;
+              const uint32_t raw = hh ? (w4[e] & 0xffff0000u) : (w4[e] << 16);  // bf16 -> fp32 bit pattern
+              const float keepf = (int32_t)raw < 0 ? 0.f : p.drop_scale;      // sign bit = dropped by the forward pass
+              const float pv = fabsf(__uint_as_float(raw)) * invl;           // the probability
+              // dP as the softmax sees it: dropout backward of dO V^T, plus the caller's gradient
+              const float dp = __uint_as_float(dv[8 * (g & 1) + t]) * keepf + xd[t];
+              pd8[t] = pv * keepf;
+              ds8[t] = pv * (dp - delta);
+            }
           }
           const int sw = ((cbase + g) ^ (r & 7)) << 4;
           uint4 a, d;
@@ -399,6 +408,7 @@ __global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 K of the 6
           *reinterpret_cast<uint4*>(bs + sw) = d;
           if (p.ds_out != nullptr && row_ok && col0 + 8 * g + 8 <= p.p_ld)
             *reinterpret_cast<uint4*>(p.ds_out + prow * p.p_ld + col0 + 8 * g) = d;
+        }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -433,16 +443,17 @@ static int make_map128(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld
 
 using namespace st5;
 
-extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, float* delta, float* dq_acc, void* stream) {
+extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, const float* inv_l, const float* out_f32,
+                                  float* delta, float* dq_acc, void* stream) {
   const bool rpe = a->pe_k != nullptr;
   if (a->dtype != ST5_BF16 || a->Tk <= 0 || a->Tq <= 0) return set_error(-2, "st5_attn_fused_bwd: needs bf16");
-  if (a->probs == nullptr || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(a->probs) & 15))
-    return set_error(-5, "st5_attn_fused_bwd: needs the probabilities saved by st5_attn_fused_fwd (16-byte aligned, "
-                         "row pitch a multiple of 8)");
+  if (psave == nullptr || inv_l == nullptr || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(psave) & 15))
+    return set_error(-5, "st5_attn_fused_bwd: needs psave / inv_l written by st5_attn_fused_fwd (16-byte aligned, row "
+                         "pitch a multiple of 8)");
   if (rpe && (a->ds == nullptr || a->dprobs_ext != nullptr || a->causal || (reinterpret_cast<uintptr_t>(a->ds) & 15)))
     return set_error(-5, "st5_attn_fused_bwd: relative positions need a dS buffer and take no external dP");
-  if (a->dprobs_ext != nullptr && a->probs_dtype != ST5_F32)
-    return set_error(-3, "st5_attn_fused_bwd: dprobs_ext needs the fp32 probabilities");
+  if (a->dprobs_ext != nullptr && (a->probs_dtype != ST5_F32 || a->probs == nullptr))
+    return set_error(-3, "st5_attn_fused_bwd: dprobs_ext needs the fp32 probabilities the forward returned");
   if (!a->dout || !a->out || !a->dq || !a->dk || !a->dv || !delta || !dq_acc)
     return set_error(-4, "st5_attn_fused_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
@@ -453,7 +464,7 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, floa
     return set_error(-4, "st5_attn_fused_bwd: out / dout must be 16-byte aligned");
   const int64_t warps_needed = ext ? nrows : (nrows + 3) / 4;
   attn_delta_kernel<<<(unsigned)((warps_needed + 7) / 8), 256, 0, s>>>(
-      (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, a->o_ld, a->o_bs,
+      (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs,
       a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
@@ -472,18 +483,15 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const float* lse, floa
   FusedBwdParams p;
   p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.causal = a->causal;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.key_pad = a->key_pad; p.lse = lse; p.delta = delta;
+  p.key_pad = a->key_pad; p.inv_l = inv_l; p.delta = delta;
   p.dp_ext = a->dprobs_ext; p.p_ld = a->p_ld;
   p.dq = (__nv_bfloat16*)a->dq; p.q_ld = a->q_ld; p.q_bs = a->q_bs;
   p.dk = (__nv_bfloat16*)a->dk; p.k_ld = a->k_ld; p.k_bs = a->k_bs;
   p.dv = (__nv_bfloat16*)a->dv; p.v_ld = a->v_ld; p.v_bs = a->v_bs;
   p.dq_acc = dq_acc;
-  p.probs_in = a->probs;
-  p.probs_fp32 = a->probs_dtype == ST5_F32;
+  p.psave = reinterpret_cast<const __nv_bfloat16*>(psave);
   p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
-  p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  p.seed = a->seed; p.offset = a->offset;
   attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_bwd");
 }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void actgrad8(float* v, const uint4 u) {
 // output element than 128 x 256), the leader's MMA warp issues tcgen05.mma.cta_group::2 for both, and each CTA drains
 // its own 128 accumulator rows. All pipeline barriers that cross the pair live in the leader's shared memory.
 template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
-__global__ void __maxnreg__(112) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_c,
                                                                   const __grid_constant__ CUtensorMap map_cpre,

@@ -620,8 +620,10 @@ class AttentionTCFn(torch.autograd.Function):
 
     @staticmethod
     def _fused_backward(q_buf, kv_buf, probs, cfg, off, seed, p_ld, same, fused, dout, dprobs):
-        """One launch (+ the row-constant pre-pass): flash-style backward on tcgen05 (attention_fused_bwd.cu)."""
-        out, lse, kp = fused
+        """One launch (+ the row-constant pre-pass): flash-style backward on tcgen05 (attention_fused_bwd.cu). `fused` =
+        (out, psave, inv_l, key_pad): psave / inv_l are the exponentials (dropout decision in the sign bit) and the row
+        normalisers the forward saved; `probs` the fp32 probabilities it returned to the caller (only with dprobs)."""
+        out, psave, inv_l, o32, kp = fused
         kvb = q_buf if same else kv_buf
         B, Tq, Tk = q_buf.shape[0], q_buf.shape[1], kvb.shape[1]
         H, d = cfg["H"], cfg["d"]
@@ -645,19 +647,21 @@ class AttentionTCFn(torch.autograd.Function):
         delta = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
         dq_acc = torch.empty((B, Tq, d), dtype=torch.float32, device=dev)
         a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)), maxpos=0,
-                        probs_dtype=K.dtype_id(probs), q=qv, q_ld=q_buf.stride(1), q_bs=q_buf.stride(0), k=kk, k_ld=kvb.stride(1),
+                        probs_dtype=K.dtype_id(probs) if probs is not None else 0, q=qv, q_ld=q_buf.stride(1),
+                        q_bs=q_buf.stride(0), k=kk, k_ld=kvb.stride(1),
                         k_bs=kvb.stride(0), v=vv, v_ld=kvb.stride(1), v_bs=kvb.stride(0), key_pad=kp, pe_k=None,
-                        out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld,
+                        out=out, o_ld=d, o_bs=Tq * d, probs=probs if dpx is not None else None, p_ld=p_ld,
                         scale=cfg["scale"], drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout,
                         dprobs_ext=dpx, ds=None, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
-        K.attn_fused_bwd(a, lse, delta, dq_acc)
+        K.attn_fused_bwd(a, psave, inv_l, o32, delta, dq_acc)
         return dq_buf, (None if same else dkv_buf), None, None, None
 
     @staticmethod
-    def _fused_backward_rpe(q_buf, pe_k, pe_hi, P, cfg, off, seed, p_ld, fused, dout, dprobs):
-        """Relative-position self-attention: the fused kernel (P read back, dS written) + the two table contractions."""
+    def _fused_backward_rpe(q_buf, pe_k, pe_hi, cfg, off, seed, p_ld, fused, dout, dprobs):
+        """Relative-position self-attention: the fused kernel (saved exponentials read back, dS written) + the two
+        table contractions."""
         assert dprobs is None, "external dP is not supported together with relative positions"
-        out, _, kp = fused
+        out, psave, inv_l, o32, kp = fused
         B, Tq, _ = q_buf.shape
         Tk = Tq
         H, d, scale, maxpos = cfg["H"], cfg["d"], cfg["scale"], cfg["maxpos"]
@@ -674,11 +678,11 @@ class AttentionTCFn(torch.autograd.Function):
         dq_acc = torch.empty((B, Tq, d), dtype=torch.float32, device=dev)
         dS = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
         a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=0, maxpos=maxpos,
-                        probs_dtype=K.dtype_id(P), q=qv, q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=q_ld, k_bs=q_bs, v=vv,
-                        v_ld=q_ld, v_bs=q_bs, key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=P, p_ld=p_ld,
+                        probs_dtype=0, q=qv, q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=q_ld, k_bs=q_bs, v=vv,
+                        v_ld=q_ld, v_bs=q_bs, key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=None, p_ld=p_ld,
                         scale=scale, drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout, dprobs_ext=None,
                         ds=dS, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
-        K.attn_fused_bwd(a, None, delta, dq_acc)
+        K.attn_fused_bwd(a, psave, inv_l, o32, delta, dq_acc)
         R = pe_k.shape[0]
         dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
         K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos)
@@ -713,47 +717,34 @@ class AttentionTCFn(torch.autograd.Function):
         q_ld, q_bs, kv_ld, kv_bs = q_buf.stride(1), q_buf.stride(0), kvb.stride(1), kvb.stride(0)
         pbs = (Tq * p_ld, H * Tq * p_ld)
         maxpos = cfg.get("maxpos", 0)
-        rpe_fused = (pe_k is not None and RT.attn_fused and not cfg.get("causal", False) and 0 < maxpos <= 160
+        use_fused = RT.attn_fused and RT.attn_fused_bwd
+        rpe_fused = (pe_k is not None and use_fused and not cfg.get("causal", False) and 0 < maxpos <= 160
                      and Tq <= maxpos and Tk <= maxpos and pe_k.shape[0] == 2 * maxpos)
-        if rpe_fused:
-            # same single launch with the relative-position bias gathered on chip from QP = Q PE^T (TMEM); the bf16
-            # probabilities are saved for the backward pass (T <= 160: 50 KB per head)
-            drop_p = cfg.get("drop_p", 0.0)
-            off = RT.next_offset() if drop_p > 0 else 0
-            kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
-            pe_hi = _pe_bf16(pe_k)
-            P = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
-            out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
-            a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=0, maxpos=maxpos,
-                            probs_dtype=K.dtype_id(P), q=qv, q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=kv_ld, k_bs=kv_bs, v=vv,
-                            v_ld=kv_ld, v_bs=kv_bs, key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=P,
-                            p_ld=p_ld, scale=scale, drop_p=drop_p, seed=RT.seed, offset=off)
-            K.attn_fused_fwd(a, None)
-            ctx.save_for_backward(q_buf, kv_buf, pe_k, P)
-            ctx.fused = (out, None, kp) if RT.attn_fused_bwd else None
-            ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
-            probs = P.float() if cfg.get("return_probs") else P
-            return out, probs[..., :Tk] if p_ld != Tk else probs
-        if pe_k is None and Tk <= 320 and RT.attn_fused:
-            # one launch: QK^T -> masks -> softmax -> dropout -> PV with the scores resident in TMEM
+        if rpe_fused or (pe_k is None and Tk <= 320 and use_fused):
+            # ONE launch: QK^T (+ the relative-position bias gathered on chip from QP = Q PE^T in TMEM) -> masks ->
+            # softmax -> dropout -> PV with the scores resident in TMEM. For the backward pass the kernel saves the
+            # exponentials (bf16, dropout decision in the sign bit) and 1/rowsum; normalised fp32 probabilities are
+            # written only when the caller asked for them (need_head_weights)
             drop_p = cfg.get("drop_p", 0.0)
             off = RT.next_offset() if drop_p > 0 else 0
             kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
             want = bool(cfg.get("return_probs"))
-            # the probabilities are saved for the backward pass (bf16; fp32 when the caller wants them returned --
-            # need_head_weights): one score-sized MMA less per backward step, which lets that kernel overlap fully
-            probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32 if want else torch.bfloat16, device=dev)
+            pe_hi = _pe_bf16(pe_k) if rpe_fused else None
+            probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev) if want else None
+            grad = any(ctx.needs_input_grad[:3])  # (inference: nothing is saved, the kernel skips those stores)
+            psave = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev) if grad else None
+            inv_l = torch.empty((B, H, Tq), dtype=torch.float32, device=dev) if grad else None
+            o32 = torch.empty((B, Tq, d), dtype=torch.float32, device=dev) if grad else None
             out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
-            lse = torch.empty((B, H, Tq), dtype=torch.float32, device=dev)
             a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
-                            maxpos=0, probs_dtype=K.dtype_id(probs) if probs is not None else 0, q=qv, q_ld=q_ld,
-                            q_bs=q_bs, k=kk, k_ld=kv_ld,
-                            k_bs=kv_bs, v=vv, v_ld=kv_ld, v_bs=kv_bs, key_pad=kp, pe_k=None, out=out, o_ld=d,
-                            o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale, drop_p=drop_p, seed=RT.seed, offset=off)
-            K.attn_fused_fwd(a, lse)
+                            maxpos=maxpos if rpe_fused else 0, probs_dtype=K.dtype_id(probs) if want else 0, q=qv,
+                            q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=kv_ld, k_bs=kv_bs, v=vv, v_ld=kv_ld, v_bs=kv_bs,
+                            key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale,
+                            drop_p=drop_p, seed=RT.seed, offset=off)
+            K.attn_fused_fwd(a, None, psave, inv_l, o32)
             ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
-            ctx.fused = (out, lse, kp) if RT.attn_fused_bwd else None
-            ctx.meta = (cfg, off, RT.seed, p_ld, same, None)
+            ctx.fused = (out, psave, inv_l, o32, kp)
+            ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
             if probs is None:
                 return out, None
             return out, probs[..., :Tk] if p_ld != Tk else probs
@@ -789,7 +780,7 @@ class AttentionTCFn(torch.autograd.Function):
         cfg, off, seed, p_ld, same, pe_hi = ctx.meta
         fused = getattr(ctx, "fused", None)
         if fused is not None and pe_k is not None:
-            return AttentionTCFn._fused_backward_rpe(q_buf, pe_k, pe_hi, P, cfg, off, seed, p_ld, fused, dout, dprobs)
+            return AttentionTCFn._fused_backward_rpe(q_buf, pe_k, pe_hi, cfg, off, seed, p_ld, fused, dout, dprobs)
         if fused is not None:
             return AttentionTCFn._fused_backward(q_buf, kv_buf, P, cfg, off, seed, p_ld, same, fused, dout, dprobs)
         if P.dtype != torch.bfloat16:  # fused forward returned fp32 probabilities to the caller

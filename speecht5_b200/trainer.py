@@ -493,6 +493,11 @@ class B200Trainer:
         self.num_updates += 1
         return static_out
 
+    def _capture_stream(self):
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device)
+        return self._cap_stream
+
     def _capture(self, samples, sig):
         static_samples = [_to_device(s, self.device) for s in samples]
         if not self._warmed:
@@ -503,7 +508,7 @@ class B200Trainer:
             snap = [t.clone() for t in state]
             bufs = [b.clone() for b in self.model.buffers()]
             seed = RT._seed_t.clone() if RT._seed_t is not None else None
-            side = torch.cuda.Stream()
+            side = self._capture_stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 self._update(static_samples)
@@ -522,7 +527,10 @@ class B200Trainer:
         # a cache miss later on captures directly: capture executes nothing (no state change, no collective runs)
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(graph):
+        # warm-up and every capture run on ONE side stream: autograd binds a parameter's AccumulateGrad node to the stream
+        # of the forward that created it, and a node that survives an iteration (the speech-input path keeps some alive)
+        # on a different stream than the capturing one forks the capture ("capturing stream has unjoined work")
+        with torch.cuda.graph(graph, stream=self._capture_stream()):
             static_out = self._update(static_samples)
         torch.cuda.synchronize()
         ent = (graph, static_samples, static_out)

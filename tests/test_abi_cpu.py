@@ -102,10 +102,34 @@ def test_argument_errors_are_reported_without_touching_a_device(lib):
     assert lib.st5_gemm_bf16(ctypes.byref(g), None) == -3
     a = _lib.AttnArgs()
     a.B, a.H, a.Tq, a.Tk, a.dtype = 1, 1, 4, 4, 0  # fp32 activations: the fused kernels are bf16 only
-    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None) == -2 and b"bf16" in lib.st5_last_error()
+    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None, None, None, None) == -2 and b"bf16" in lib.st5_last_error()
     a.dtype, a.Tk = 1, 400
-    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None) == -2
+    assert lib.st5_attn_fused_fwd(ctypes.byref(a), None, None, None, None, None) == -2
     if not torch.cuda.is_available():
         assert lib.st5_device_ok() != 0
     with pytest.raises(RuntimeError, match="st5_gemm_bf16"):
         _lib.check(-2, "st5_gemm_bf16")
+
+
+def test_register_budget_of_the_wide_kernels(lib):
+    """A launch fails with 'too many resources requested' when registers x allocated warps exceed the 64 K file. Warps
+    are allocated four at a time, so an 18-warp block (576 threads: the tcgen05 GEMM, both fused attention kernels)
+    pays for 20: 96 registers per thread is the ceiling. (A 112-register build once passed every CPU check and failed
+    every launch on the GPU; ptxas does not know the block size unless __launch_bounds__ says so.)"""
+    import shutil
+    import subprocess
+    from speecht5_b200.build import LIB
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+    threads = {"gemm_bf16_tcgen05": 576, "attn_fused_bwd_kernel": 576, "attn_fused_fwd_kernelILb0": 576,
+               "attn_fused_fwd_kernelILb1": 320, "attn_flash_fwd_kernel": 320, "attn_flash_bwd_kernel": 320}
+    seen = 0
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", out):
+        name, regs = m.group(1), int(m.group(2))
+        for key, nthr in threads.items():
+            if key in name:
+                warps = -(-(nthr // 32) // 4) * 4
+                assert warps * 32 * (-(-regs // 8) * 8) <= 65536, (name, regs, nthr)
+                seen += 1
+    assert seen >= 10
