@@ -163,6 +163,13 @@ int st5_attn_bwd(const st5_attn_args* args, void* stream);
  * Relative positions (encoder.py:239-246): pe_k != NULL selects the skewed-bias variant; here pe_k must point to a
  * BF16 copy of the [2*maxpos][64] table, and Tq, Tk <= maxpos <= 160 (clamp(i-j) never clips), no causal mask. */
 int st5_attn_fused_fwd(const st5_attn_args* args, float* lse, void* psave, float* inv_l, float* out_f32, void* stream);
+/* Streaming ("flash") tcgen05 attention forward for ANY Tq / Tk (bf16): 128-key blocks, the row maximum is made final
+ * in a first sweep over the key blocks (scores only), a second sweep computes exp / dropout / P V with the output
+ * accumulating in TMEM, a third one (only when args->probs != NULL, which must then be FP32) writes the normalised
+ * probabilities. Same arguments, outputs and psave / inv_l / out_f32 contract as st5_attn_fused_fwd, so
+ * st5_attn_fused_bwd is its backward. Relative positions: pe_k = BF16 copy of the [2*maxpos][64] table, any Tq / Tk --
+ * clamp(i - j, -maxpos, maxpos - 1) clips as encoder.py:40-59 does; no causal mask together with pe_k. */
+int st5_attn_flash_fwd(const st5_attn_args* args, float* lse, void* psave, float* inv_l, float* out_f32, void* stream);
 /* Fused tcgen05 attention backward (multihead_attention.py:340-389 differentiated). psave / inv_l are what
  * st5_attn_fused_fwd wrote: probabilities and dropout decisions are read back instead of recomputed (no exponential, no
  * Philox), so every step needs one score-sized MMA (dP = dO V^T) and the kernel double buffers dP, the dropout(P)/dS

@@ -95,8 +95,10 @@ class StridedConvGeluFn(torch.autograd.Function):
                 dx[:, r::s].zero_()
                 continue
             # window position q <-> tap j = J-1-q; W_r[ci, q*Cout + co] = W[co, ci, r + s*(J-1-q)]
-            wr = RT.shadow(("fe_b", id(weight), r), lambda taps=taps: weight.detach()[:, :, taps[::-1]]
-                           .permute(1, 2, 0).reshape(Cin, len(taps) * Cout))
+            # (slice + flip, not a Python index list: that would be a host tensor copied to the device -- illegal under
+            #  CUDA-graph capture -- every time the shadow is rebuilt after an optimizer step)
+            wr = RT.shadow(("fe_b", id(weight), r), lambda r=r, J=J: weight.detach()[:, :, r::s].flip(2)
+                           .permute(1, 2, 0).reshape(Cin, J * Cout))
             a_ops = _off(ga, (front - (J - 1)) * Cout)
             out_r = dx.reshape(-1)[r * Cin:]
             kw = dict(M=Mr, N=Cin, K=J * Cout, a_ld=Cout, b_ld=J * Cout, c_ld=s * Cin, nb1=B, nb2=1,

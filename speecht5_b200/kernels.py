@@ -195,6 +195,13 @@ def attn_fused_fwd(a, lse, psave=None, inv_l=None, out_f32=None):
     _count(1)
 
 
+def attn_flash_fwd(a, lse, psave=None, inv_l=None, out_f32=None):
+    lib = _lib.load()
+    _lib.check(lib.st5_attn_flash_fwd(C.byref(a), _ptr(lse), _ptr(psave), _ptr(inv_l), _ptr(out_f32), _stream()),
+               "st5_attn_flash_fwd")
+    _count(1)
+
+
 def attn_fused_bwd(a, psave, inv_l, out_f32, delta, dq_acc):
     lib = _lib.load()
     _lib.check(lib.st5_attn_fused_bwd(C.byref(a), _ptr(psave), _ptr(inv_l), _ptr(out_f32), _ptr(delta), _ptr(dq_acc),

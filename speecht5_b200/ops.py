@@ -32,6 +32,9 @@ class Runtime:
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
         self.attn_fused = True        # bf16 mode, no RPE, Tk <= 320: single-launch fused forward (attention_fused.cu)
         self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
+        # streaming forward for what the resident kernels cannot hold (Tk > 320, clipped relative positions); "all":
+        # every bf16 shape goes through it (ST5_ATTN_FLASH=all)
+        self.attn_flash = {"0": False, "all": "all"}.get(os.environ.get("ST5_ATTN_FLASH", "1"), True)
         self.ffn_gate = os.environ.get("ST5_FFN_GATE", "1") != "0"  # bf16 mode: fc1 stores the backward gate (FFNFn)
         self.fp32_stream = os.environ.get("ST5_FP32_STREAM", "1") != "0"  # bf16 mode: fp32 residual stream between LayerNorms
         # trainer hooks: stage_callback(key, x) is called at the entry of every encoder / decoder layer (gradient-exchange
@@ -718,9 +721,15 @@ class AttentionTCFn(torch.autograd.Function):
         pbs = (Tq * p_ld, H * Tq * p_ld)
         maxpos = cfg.get("maxpos", 0)
         use_fused = RT.attn_fused and RT.attn_fused_bwd
-        rpe_fused = (pe_k is not None and use_fused and not cfg.get("causal", False) and 0 < maxpos <= 160
+        causal = bool(cfg.get("causal", False))
+        rpe_fused = (pe_k is not None and use_fused and not causal and 0 < maxpos <= 160
                      and Tq <= maxpos and Tk <= maxpos and pe_k.shape[0] == 2 * maxpos)
-        if rpe_fused or (pe_k is None and Tk <= 320 and use_fused):
+        resident = rpe_fused or (pe_k is None and Tk <= 320 and use_fused)  # whole score rows fit TMEM: one launch
+        # streaming kernel (attention_flash.cu): any length, clipped relative positions; RT.attn_flash == "all" also
+        # routes the shapes the resident kernel could take through it
+        flash = (use_fused and RT.attn_flash and (pe_k is None or (not causal and maxpos > 0 and pe_k.shape[0] == 2 * maxpos))
+                 and (not resident or RT.attn_flash == "all"))
+        if resident or flash:
             # ONE launch: QK^T (+ the relative-position bias gathered on chip from QP = Q PE^T in TMEM) -> masks ->
             # softmax -> dropout -> PV with the scores resident in TMEM. For the backward pass the kernel saves the
             # exponentials (bf16, dropout decision in the sign bit) and 1/rowsum; normalised fp32 probabilities are
@@ -729,7 +738,8 @@ class AttentionTCFn(torch.autograd.Function):
             off = RT.next_offset() if drop_p > 0 else 0
             kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
             want = bool(cfg.get("return_probs"))
-            pe_hi = _pe_bf16(pe_k) if rpe_fused else None
+            with_pe = pe_k is not None
+            pe_hi = _pe_bf16(pe_k) if with_pe else None
             probs = torch.empty((B, H, Tq, p_ld), dtype=torch.float32, device=dev) if want else None
             grad = any(ctx.needs_input_grad[:3])  # (inference: nothing is saved, the kernel skips those stores)
             psave = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev) if grad else None
@@ -737,11 +747,11 @@ class AttentionTCFn(torch.autograd.Function):
             o32 = torch.empty((B, Tq, d), dtype=torch.float32, device=dev) if grad else None
             out = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=dev)
             a = K.attn_args(B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
-                            maxpos=maxpos if rpe_fused else 0, probs_dtype=K.dtype_id(probs) if want else 0, q=qv,
+                            maxpos=maxpos if with_pe else 0, probs_dtype=K.dtype_id(probs) if want else 0, q=qv,
                             q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=kv_ld, k_bs=kv_bs, v=vv, v_ld=kv_ld, v_bs=kv_bs,
                             key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale,
                             drop_p=drop_p, seed=RT.seed, offset=off)
-            K.attn_fused_fwd(a, None, psave, inv_l, o32)
+            (K.attn_flash_fwd if flash else K.attn_fused_fwd)(a, None, psave, inv_l, o32)
             ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
             ctx.fused = (out, psave, inv_l, o32, kp)
             ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
@@ -846,7 +856,8 @@ def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, max
     cfg = dict(H=H, d=d, q_col=q_col, k_col=k_col, v_col=v_col, scale=scale, maxpos=maxpos, causal=causal,
                drop_p=drop_p, return_probs=return_probs)
     Tk = (q_buf if kv_buf is None else kv_buf).shape[1]
-    if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and Tk <= 512:
+    streaming = RT.attn_flash and RT.attn_fused and RT.attn_fused_bwd and (pe_k is None or not causal)
+    if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and (Tk <= 512 or streaming):
         return AttentionTCFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
     return AttentionFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
 

@@ -371,3 +371,94 @@ def test_conv0_groupnorm_gelu_against_the_oracle_layer(cuda, dtype):
     assert rel(dw.cpu(), conv.weight.grad.reshape(512, 10)) < tol
     assert rel(dg.cpu(), gn.weight.grad) < tol
     assert rel(db.cpu(), gn.bias.grad) < tol
+
+
+@pytest.mark.parametrize("case", ["rpe_199", "rpe_499_pad", "rpe_781", "rpe_small_table_37", "causal_500", "self_400_pad",
+                                  "cross_160x499_probs", "cross_313x160_flash_probs_extdP"])
+def test_streaming_attention_any_length(cuda, case):
+    """attention_flash.cu (two sweeps over 128-key blocks, clipped relative positions) + the fused backward, against the
+    fp64 statement of multihead_attention.py:340-389 / encoder.py:40-59 at the lengths SURVEY section 7 names (199, 499,
+    781) -- padding, clipping at both table ends, a table smaller than one window, causal, returned probabilities with an
+    external gradient on them."""
+    from speecht5_b200 import ops
+    ops.RT.dtype = torch.bfloat16
+    ops.RT.attn_fused = ops.RT.attn_fused_bwd = ops.RT.attn_tensor_core = True
+    keep = ops.RT.attn_flash
+    ops.RT.attn_flash = "all"
+    try:
+        torch.manual_seed(2)
+        B, H = 2, 2
+        d = H * 64
+        cfgs = {"rpe_199": (199, 199, 160, False), "rpe_499_pad": (499, 499, 160, False), "rpe_781": (781, 781, 160, False),
+                "rpe_small_table_37": (37, 37, 8, False), "causal_500": (500, 500, 0, True),
+                "self_400_pad": (400, 400, 0, False), "cross_160x499_probs": (160, 499, 0, False),
+                "cross_313x160_flash_probs_extdP": (313, 160, 0, False)}
+        Tq, Tk, maxpos, causal = cfgs[case]
+        cross = case.startswith("cross")
+        lens = torch.tensor([Tk, max(1, Tk - 37)], device=cuda)
+        key_pad = torch.arange(Tk, device=cuda)[None, :] >= lens[:, None] if "causal" not in case else None
+        pe = torch.nn.Parameter(torch.randn(2 * maxpos, 64, device=cuda) * 0.3) if maxpos else None
+        if cross:
+            qb = (torch.randn(B, Tq, d, device=cuda) * 0.8).to(torch.bfloat16).requires_grad_()
+            kvb = (torch.randn(B, Tk, 2 * d, device=cuda) * 0.8).to(torch.bfloat16).requires_grad_()
+            out, probs = ops.attention(qb, kvb, H=H, d=d, q_col=0, k_col=0, v_col=1, scale=0.125, key_pad=key_pad,
+                                       return_probs=True)
+            q = qb.detach().double().reshape(B, Tq, H, 64).transpose(1, 2)
+            k, v = [t.reshape(B, Tk, H, 64).transpose(1, 2) for t in kvb.detach().double().split(d, dim=-1)]
+        else:
+            qkv = (torch.randn(B, Tq, 3 * d, device=cuda) * 0.8).to(torch.bfloat16).requires_grad_()
+            out, probs = ops.attention(qkv, None, H=H, d=d, q_col=0, k_col=1, v_col=2, scale=0.125, key_pad=key_pad,
+                                       causal=causal, pe_k=pe, maxpos=maxpos)
+            q, k, v = [t.reshape(B, Tq, H, 64).transpose(1, 2) for t in qkv.detach().double().split(d, dim=-1)]
+        q, k, v = q.requires_grad_(), k.requires_grad_(), v.requires_grad_()
+        # the kernel sees the bf16 copy of the table
+        per = pe.detach().to(torch.bfloat16).double().requires_grad_() if pe is not None else None
+        o_ref, p_ref = _ref_attention(q, k, v, per, maxpos, key_pad, causal, 0.125)
+        assert rel(out, o_ref.transpose(1, 2).reshape(B, Tq, d)) < 1.5e-2
+        g = torch.randn(B, Tq, d, device=cuda)
+        gp = None
+        if cross:
+            assert probs is not None and probs.dtype == torch.float32
+            assert rel(probs, p_ref) < 1e-2
+            if "extdP" in case:
+                gp = torch.randn(B, H, Tq, Tk, device=cuda)
+        else:
+            assert probs is None
+        ((out.float() * g).sum() + ((probs * gp).sum() if gp is not None else 0)).backward()
+        ((o_ref.transpose(1, 2).reshape(B, Tq, d) * g.double()).sum()
+         + ((p_ref * gp.double()).sum() if gp is not None else 0)).backward()
+
+        def flat(t):
+            return t.transpose(1, 2).reshape(B, -1, d)
+        if cross:
+            assert rel(qb.grad, flat(q.grad)) < 3e-2
+            assert rel(kvb.grad, torch.cat([flat(k.grad), flat(v.grad)], -1)) < 3e-2
+        else:
+            assert rel(qkv.grad, torch.cat([flat(q.grad), flat(k.grad), flat(v.grad)], -1)) < 3e-2
+            if pe is not None:
+                assert rel(pe.grad, per.grad) < 3e-2
+    finally:
+        ops.RT.attn_flash = keep
+
+
+def test_streaming_attention_dropout_matches_row_kernels(cuda):
+    """Same (seed, offset) => the same Philox mask in attention_flash.cu as in the exact row kernels, forward and (through
+    the sign bits of the saved exponentials) backward."""
+    from speecht5_b200 import ops
+    ops.RT.dtype = torch.bfloat16
+    torch.manual_seed(0)
+    B, H, T = 2, 2, 400
+    d = H * 64
+    base = (torch.randn(B, T, 3 * d, device=cuda) * 0.7).to(torch.bfloat16)
+    g = torch.randn(B, T, d, device=cuda).to(torch.bfloat16)
+    res = []
+    for tc in (True, False):
+        ops.RT.attn_tensor_core = tc
+        ops.RT.manual_seed(7)
+        qb = base.clone().requires_grad_()
+        out, _ = ops.attention(qb, None, H=H, d=d, q_col=0, k_col=1, v_col=2, scale=0.125, causal=True, drop_p=0.2)
+        out.backward(g)
+        res.append((out.detach(), qb.grad))
+    ops.RT.attn_tensor_core = True
+    assert rel(res[0][0], res[1][0]) < 3e-2
+    assert rel(res[0][1], res[1][1]) < 3e-2
