@@ -324,6 +324,16 @@ def run_asr(args):
     B = args.batch if args.batch != WORKLOAD["batch_per_gpu"] else ASR["batch_per_gpu"]
     host = [synthetic_asr_batch(B, ASR["n_samples"], ASR["target_len"], seed=100 * rank + i, pin=True) for i in range(4)]
     resident = [_to_device(s, dev) for s in host]
+    if args.profile_step:  # one eager update between cudaProfilerStart/Stop (ncu --profile-from-start off)
+        trainer.use_cuda_graph = False
+        for i in range(2):
+            trainer.train_step([resident[i]])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.train_step([resident[2]])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, win_dev, _, out = _timed_steps(trainer, resident, args.steps, args.warmup, world, dev, read_back=False)
     ms_e2e, _, last, out = _timed_steps(trainer, host, args.steps, args.warmup, world, dev, read_back=True)

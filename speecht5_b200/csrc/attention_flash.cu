@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
                     make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
             }
             __syncwarp();  // (each thread re-reads only its own row; this is the compiler / memory fence)
-            if (base - 31 >= 0 && base + 31 <= colmax) {  // interior: no clipping, cs == base - 31
+            if (cs == base - 31 && base + 31 <= colmax) {  // interior: no clipping, the staged window starts at base - 31
               const float* rd = stg + lane + 31;
 #pragma unroll
               for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + rd[-t]);

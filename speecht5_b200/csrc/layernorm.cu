@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "vec8.cuh"
+#include "tma_map.cuh"  // device_sm_count()
 
 namespace st5 {
 
@@ -200,6 +201,104 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Input gradient AND parameter gradients in ONE pass over dy / s (the two-kernel form reads both tensors twice):
+// persistent grid, warp per row, every lane keeps the dgamma / dbeta partials of its own channels in registers across
+// the rows it visits; per CTA they meet in shared memory (fp32 shared atomics, once) and leave as one global atomic per
+// channel. NCH = 16-byte chunks per lane (C <= NCH * 256).
+constexpr int LNB_WARPS = 8;
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 2)
+    ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ s_in, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ ds,
+                        T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
+                        uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
+  extern __shared__ float ln_acc[];  // [2][C]
+  if (thr != 0) resolve_seed(seed, offset);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nchunks = C >> 3;
+  for (int t = threadIdx.x; t < 2 * C; t += LNB_WARPS * 32) ln_acc[t] = 0.f;
+  __syncthreads();
+  float pg[NCH][8], pb[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pg[k][t] = pb[k][t] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LNB_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float d[NCH][8], xh[NCH][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = k * 32 + lane;
+      if (ch < nchunks) {
+        const int64_t e0 = row * C + ch * 8;
+        float sv[8], gm[8];
+        load8<T>(dy + e0, d[k]);
+        load8<T>(s_in + e0, sv);
+        load8<float>(gamma + ch * 8, gm);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          xh[k][t] = (sv[t] - mu) * rs;
+          pb[k][t] += d[k][t];
+          pg[k][t] += d[k][t] * xh[k][t];
+          d[k][t] *= gm[t];  // g = dy * gamma from here on
+          c1 += d[k][t];
+          c2 += d[k][t] * xh[k][t];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)C;
+    c2 = warp_sum(c2) / (float)C;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = k * 32 + lane;
+      if (ch < nchunks) {
+        const int64_t e0 = row * C + ch * 8;
+        float r[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) r[t] = rs * (d[k][t] - c1 - xh[k][t] * c2);
+        if (ds != nullptr) store8<T>(ds + e0, r);
+        if (dx != nullptr) {
+          if (thr != 0) dropout8(r, (uint64_t)e0, thr, dscale, seed, offset);
+          store8<T>(dx + e0, r);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int ch = k * 32 + lane;
+    if (ch < nchunks) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        atomicAdd(&ln_acc[ch * 8 + t], pg[k][t]);
+        atomicAdd(&ln_acc[C + ch * 8 + t], pb[k][t]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < C; t += LNB_WARPS * 32) {
+    if (dgamma != nullptr) atomicAdd(dgamma + t, ln_acc[t]);
+    if (dbeta != nullptr) atomicAdd(dbeta + t, ln_acc[C + t]);
+  }
+}
+
+template <typename T>
+static void ln_bwd_fused_dispatch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
+                                  void* ds, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, uint32_t thr,
+                                  float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS;
+  const int64_t cap = 2 * (int64_t)device_sm_count();
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if (C <= 768)
+    ln_bwd_fused_kernel<T, 3><<<grid, LNB_WARPS * 32, smem, s>>>((const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds,
+                                                                (T*)dx, dgamma, dbeta, rows, C, thr, dsc, seed, offset);
+  else
+    ln_bwd_fused_kernel<T, LN_MAX_CHUNKS><<<grid, LNB_WARPS * 32, smem, s>>>(
+        (const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds, (T*)dx, dgamma, dbeta, rows, C, thr, dsc, seed, offset);
+}
+
 int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
                   void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
                   float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s) {
@@ -208,6 +307,14 @@ int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const flo
   if (C > 8 * 32 * LN_MAX_CHUNKS || C <= 0 || (C & 7)) return -2;
   const uint32_t thr = drop_threshold(drop_p);
   const float dsc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if ((dgamma != nullptr || dbeta != nullptr) && rows >= 64) {  // one pass over dy / s for dx and the parameter sums
+    if (dtype == ST5_F32)
+      ln_bwd_fused_dispatch<float>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, rows, (int)C, thr, dsc, seed, offset, s);
+    else
+      ln_bwd_fused_dispatch<__nv_bfloat16>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, rows, (int)C, thr, dsc, seed,
+                                           offset, s);
+    return (int)cudaGetLastError();
+  }
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   int64_t splits = (rows + 255) / 256;
   if (splits > 96) splits = 96;

@@ -24,7 +24,7 @@ def _mode():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(4, 37, 768), (3, 5, 80), (2, 9, 1024)])
+@pytest.mark.parametrize("shape", [(4, 37, 768), (3, 5, 80), (2, 9, 1024), (7, 313, 768), (5, 67, 1024)])  # rows >= 64: fused dx + parameter pass
 def test_layer_norm_residual(cuda, dtype, shape):
     from speecht5_b200 import ops
     ops.RT.dtype = dtype

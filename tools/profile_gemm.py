@@ -22,6 +22,8 @@ def run(M, N, Kd, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, **epi):
     if epi.get("act"):
         kw["act"] = epi["act"]
         kw["c_pre"] = torch.empty_like(out)
+    if epi.get("res"):
+        kw["residual"] = torch.randn(M, N, device=dev).to(out_dtype)
     if epi.get("drop"):
         kw.update(drop_p=0.1, seed=1, offset=3)
     if epi.get("acc"):
@@ -34,11 +36,13 @@ def run(M, N, Kd, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, **epi):
     torch.cuda.synchronize()
 
 
-run(10016, 768, 768, bias=True)                          # decoder out_proj forward (plain bias epilogue)
-run(5120, 3072, 768, bias=True, act="gelu", drop=True)   # encoder fc1: GELU + pre-activation store + dropout
-run(5120, 768, 3072, bias=True)                          # encoder fc2
-run(5120, 3072, 768, b_mn=True, drop=True, ag="gelu")    # dH = (dY . W2) * dropmask * gelu'(pre)
+run(10016, 768, 768, bias=True)                                   # decoder out_proj forward (plain bias epilogue)
+run(5120, 3072, 768, bias=True, act="gelu_tanh_gate", drop=True)  # encoder fc1: GELU + backward gate store + dropout
+run(5120, 768, 3072, bias=True, res=True, drop=True)              # encoder fc2 (+ dropout + residual)
+run(5120, 3072, 768, b_mn=True, ag="gate")                        # dH = (dY . W2) * gate
+run(5120, 768, 3072, b_mn=True)                                   # dX of fc1
 run(768, 768, 10016, a_mn=True, b_mn=True, out_dtype=torch.float32, acc=True)   # dW of a 768x768 projection
 run(3072, 768, 5120, a_mn=True, b_mn=True, out_dtype=torch.float32, acc=True)   # dW of fc1
-run(8192, 8192, 8192)                                     # large square reference point
+run(2304, 768, 5120, a_mn=True, b_mn=True, out_dtype=torch.float32, acc=True)   # dW of q|k|v
+run(8192, 8192, 8192)                                              # large square reference point
 print("done")
