@@ -53,7 +53,10 @@ int st5_device_ok(void);
  * contiguous (the operand is used transposed without a copy). ld / batch strides are in elements and must be
  * multiples of 8 (16 bytes); base pointers 16-byte aligned. Batch index z = b2 * nb1 + b1.
  * epi(v) = dropout(act(v + c_old*accumulate + bias[n] + bias2[m / bias2_rows][n])) + residual[m][n]; the value before
- * act() is also stored to c_pre when non-null. */
+ * act() is also stored to c_pre when non-null.
+ * accumulate: 0 = overwrite; 1 = c += (read-modify-write in the epilogue, FP32 c); 2 = c += as a TMA reduce-add at the
+ * L2 (FP32 c, 16-byte aligned rows): batch entries may then SHARE one output (c_bs = 0) -- a contraction split over the
+ * batch dimension (weight gradients: a_bs / b_bs step along K) -- and nothing reads c first. */
 typedef struct st5_gemm_args {
   int32_t M, N, K, nb1, nb2;
   int32_t a_mn, b_mn, c_fp32, act, accumulate, bias2_rows;

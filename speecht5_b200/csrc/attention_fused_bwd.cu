@@ -109,7 +109,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
 __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 20: 96 registers is the ceiling)
     attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
-                          const FusedBwdParams p) {
+                          const __grid_constant__ CUtensorMap map_p, const FusedBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;             // [128 keys][128 B]
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
   uint64_t* bar_pds = bar_kv + 8;     // [2] threads: dropout(P)/dS tiles written, dP buffer read
   uint64_t* bar_mma2 = bar_kv + 10;   // [2] MMA2 complete: dQ buffer (and dK/dV) valid, smem tiles free
   uint64_t* bar_tdone = bar_kv + 12;  // [2] threads: dQ buffer (and dK/dV) read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 14);
+  uint64_t* bar_pin = bar_kv + 14;    // [2] the saved exponentials of a step have landed in sPd[buf] (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 16);
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -134,10 +135,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_p);
     mbar_init(bar_kv, 1); mbar_init(bar_kvfree, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_qdo[s], 1); mbar_init(&bar_qfree[s], 1); mbar_init(&bar_dp[s], 1);
       mbar_init(&bar_pds[s], FB_NG * 4); mbar_init(&bar_mma2[s], 1); mbar_init(&bar_tdone[s], FB_NG * 4);
+      mbar_init(&bar_pin[s], 1);
     }
     fence_mbar_init();
   }
@@ -169,6 +172,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
           mbar_expect_tx(&bar_qdo[buf], 32768);
           tma_load_4d(sQ + buf * 16384, &map_q, &bar_qdo[buf], 0, qt * FB_T, h, b);
           tma_load_4d(sdO + buf * 16384, &map_do, &bar_qdo[buf], 0, qt * FB_T, h, b);
+          // the saved exponentials of this (query tile, key block) go straight into the operand tile the threads will
+          // overwrite in place with dropout(P): same [128 rows][64 keys] x 2, 128B-swizzled layout. MMA2(it-2) -- the
+          // last reader of sPd[buf] -- has completed (bar_qfree above). A 64-key block that starts beyond the row
+          // pitch is not loaded (nothing reads it: those chunks are dead and get zeros from the threads).
+          const int nblk = (kb * FB_T + 64 < (int)p.p_ld) ? 2 : 1;
+          mbar_expect_tx(&bar_pin[buf], (uint32_t)nblk * 16384u);
+          for (int blk = 0; blk < nblk; ++blk)
+            tma_load_4d(sPd + buf * 32768 + blk * 16384, &map_p, &bar_pin[buf], kb * FB_T + blk * 64, qt * FB_T, h, b);
         }
       }
     }
@@ -240,6 +251,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
     const int grp = (warp - 2) >> 2;  // 32-key chunk of the block, 16-channel slice of dQ, 32-channel slice of dK|dV
     const int r = q * 32 + (int)lane_id();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    // this thread's 16 running dQ sums of query tile qt (written by this same thread one key block earlier)
+    float4 qpf[4];
+    auto prefetch_acc = [&](int kb, int qt) {
+      const int i = qt * FB_T + r;
+      if (kb > 0 && i < p.Tq) {
+        const float* acc = p.dq_acc + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64 + grp * 16;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) qpf[t] = *reinterpret_cast<const float4*>(acc + 4 * t);
+      }
+    };
     // ---- read-out of one finished step: dQ partial of (kb, qt); dK / dV after the last query tile of a key block
     auto read_out = [&](int kb, int qt, int j) {
       const int buf = j & 1;
@@ -258,10 +279,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
           float f[16];
 #pragma unroll
           for (int t = 0; t < 16; ++t) f[t] = __uint_as_float(v[t]) * p.scale;
-          if (kb > 0) {
+          if (kb > 0) {  // running sum over the earlier key blocks (requested a whole element phase ago: prefetch_acc)
 #pragma unroll
             for (int t = 0; t < 16; t += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(acc + t);
+              const float4 o = qpf[t >> 2];
               f[t] += o.x; f[t + 1] += o.y; f[t + 2] += o.z; f[t + 3] += o.w;
             }
           }
@@ -305,22 +326,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&bar_tdone[buf]);
     };
-    // 64 bytes of this thread's row of the saved exponentials for step (kb2, qt2), as raw bf16x8 words (zero -- "kept,
-    // probability 0" -- for dead rows and beyond the row pitch)
-    auto fetch_p = [&](int kb2, int qt2, uint4 (&dst)[4]) {
-      const int i2 = qt2 * FB_T + r;
-      const int col = kb2 * FB_T + grp * 32;
-      const __nv_bfloat16* pr = p.psave + (((int64_t)b * p.H + h) * p.Tq + i2) * p.p_ld + col;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        dst[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (i2 < p.Tq && col + 8 * g + 8 <= p.p_ld) dst[g] = __ldg(reinterpret_cast<const uint4*>(pr + 8 * g));
-      }
-    };
-    uint4 pcur[4], pnext[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) pcur[g] = pnext[g] = make_uint4(0u, 0u, 0u, 0u);
-    if (nkb > 0 && nqt > 0) fetch_p(0, 0, pcur);
+    // per-row constants of the NEXT step are requested one step ahead (two dependent global round trips per step less)
+    float delta_n = 0.f, invl_n = 0.f;
+    if (nkb > 0 && nqt > 0 && r < p.Tq) {
+      const int64_t pr0 = ((int64_t)b * p.H + h) * p.Tq + r;
+      delta_n = p.delta[pr0];
+      invl_n = p.inv_l[pr0];
+    }
     int it = 0, pend_kb = -1, pend_qt = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int qt0 = p.causal ? kb : 0;
@@ -330,20 +342,26 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
         const int i = qt * FB_T + r;
         const bool row_ok = i < p.Tq;
         const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
-        const float delta = row_ok ? p.delta[prow] : 0.f;
-        const float invl = row_ok ? p.inv_l[prow] : 0.f;
-        const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
-        const int c = grp;  // this warp's 32-key chunk of the block
-        const int col0 = k0 + c * 32;
-        // the saved exponentials of this row's chunk were prefetched during the previous step (pcur); the next step's
-        // chunk is requested now
+        const float delta = delta_n, invl = invl_n;
         {
           int kb2 = kb, qt2 = qt + 1;
           if (qt2 >= nqt) { kb2 = kb + 1; qt2 = p.causal ? kb2 : 0; }
-          if (kb2 < nkb && qt2 < nqt) fetch_p(kb2, qt2, pnext);
+          const int i2 = qt2 * FB_T + r;
+          delta_n = invl_n = 0.f;
+          if (kb2 < nkb && qt2 < nqt && i2 < p.Tq) {
+            const int64_t pr2 = ((int64_t)b * p.H + h) * p.Tq + i2;
+            delta_n = p.delta[pr2];
+            invl_n = p.inv_l[pr2];
+          }
         }
+        if (pend_kb >= 0) prefetch_acc(pend_kb, pend_qt);  // for the read-out that follows this step's element phase
+        const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
+        const int c = grp;  // this warp's 32-key chunk of the block
+        const int col0 = k0 + c * 32;
         mbar_wait(&bar_dp[buf], (uint32_t)((it >> 1) & 1));
         tc_fence_after();
+        mbar_wait(&bar_pin[buf], (uint32_t)((it >> 1) & 1));  // the exponentials are in sPd[buf] (every warp: nobody
+                                                               // may write the tile before the TMA has)
         uint8_t* bp = sPd + buf * 32768 + (c >> 1) * 16384 + r * 128;
         uint8_t* bs = sdS + buf * 32768 + (c >> 1) * 16384 + r * 128;
         const int cbase = (c & 1) * 4;
@@ -361,14 +379,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
           }
         } else {
         // (dP is finite everywhere: V rows beyond Tk and dO rows beyond Tq arrive as zeros from TMA)
-        uint32_t dv[16];  // dP in two halves of 16 columns: 16 live registers instead of 32 (the kernel sits at the cap)
+        uint32_t dv[32];
+        tmem_ld_32x32(trow + FB_COL_DP + (uint32_t)(buf * 128 + c * 32), dv);
+        tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if ((g & 1) == 0) {
-            tmem_ld_32x16(trow + FB_COL_DP + (uint32_t)(buf * 128 + c * 32 + 8 * g), dv);
-            tmem_ld_wait();
-          }
-          const uint32_t w4[4] = {pcur[g].x, pcur[g].y, pcur[g].z, pcur[g].w};
+          const int sw = ((cbase + g) ^ (r & 7)) << 4;
+          const uint4 praw = *reinterpret_cast<const uint4*>(bp + sw);  // this row's 8 saved exponentials (in place)
+          const uint32_t w4[4] = {praw.x, praw.y, praw.z, praw.w};
           float xd[8];
           xd[0] = xd[1] = xd[2] = xd[3] = xd[4] = xd[5] = xd[6] = xd[7] = 0.f;
           if (dpx != nullptr) {  // the caller's gradient on the probabilities: this row's 8 floats of the chunk
@@ -395,12 +413,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
               const float keepf = (int32_t)raw < 0 ? 0.f : p.drop_scale;      // sign bit = dropped by the forward pass
               const float pv = fabsf(__uint_as_float(raw)) * invl;           // the probability
               // dP as the softmax sees it: dropout backward of dO V^T, plus the caller's gradient
-              const float dp = __uint_as_float(dv[8 * (g & 1) + t]) * keepf + xd[t];
+              const float dp = __uint_as_float(dv[8 * g + t]) * keepf + xd[t];
               pd8[t] = pv * keepf;
               ds8[t] = pv * (dp - delta);
             }
           }
-          const int sw = ((cbase + g) ^ (r & 7)) << 4;
           uint4 a, d;
           a.x = pack2(pd8[0], pd8[1]); a.y = pack2(pd8[2], pd8[3]); a.z = pack2(pd8[4], pd8[5]); a.w = pack2(pd8[6], pd8[7]);
           d.x = pack2(ds8[0], ds8[1]); d.y = pack2(ds8[2], ds8[3]); d.z = pack2(ds8[4], ds8[5]); d.w = pack2(ds8[6], ds8[7]);
@@ -414,15 +431,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&bar_pds[buf]);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) pcur[g] = pnext[g];
         // ---- the previous step's accumulators are read while the tensor core works on this step and the next
         if (pend_kb >= 0) read_out(pend_kb, pend_qt, it - 1);
         pend_kb = kb;
         pend_qt = qt;
       }
     }
-    if (pend_kb >= 0) read_out(pend_kb, pend_qt, it - 1);
+    if (pend_kb >= 0) {
+      prefetch_acc(pend_kb, pend_qt);
+      read_out(pend_kb, pend_qt, it - 1);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -468,11 +486,17 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
       a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
-  CUtensorMap mq, mk, mv, mdo;
+  CUtensorMap mq, mk, mv, mdo, mp;
   int rc = make_map128(&mq, a->q, a->Tq, a->q_ld, a->q_bs, a->H, a->B);
   if (!rc) rc = make_map128(&mk, a->k, a->Tk, a->k_ld, a->k_bs, a->H, a->B);
   if (!rc) rc = make_map128(&mv, a->v, a->Tk, a->v_ld, a->v_bs, a->H, a->B);
   if (!rc) rc = make_map128(&mdo, a->dout, a->Tq, a->o_ld, a->o_bs, a->H, a->B);
+  if (!rc) {  // psave [B][H][Tq][p_ld] bf16: boxes of 64 keys x 128 query rows, out-of-range rows / columns read as zero
+    const uint64_t dims[4] = {(uint64_t)a->p_ld, (uint64_t)a->Tq, (uint64_t)a->H, (uint64_t)a->B};
+    const uint64_t strides[3] = {(uint64_t)a->p_ld * 2, (uint64_t)a->Tq * a->p_ld * 2, (uint64_t)a->H * a->Tq * a->p_ld * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    rc = encode_bf16_map_4d(&mp, psave, dims, strides, box);
+  }
   if (rc) return set_error(rc, "st5_attn_fused_bwd: tensor map");
   static bool attr_set = false;
   if (!attr_set) {
@@ -492,6 +516,6 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
   p.psave = reinterpret_cast<const __nv_bfloat16*>(psave);
   p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, p);
+  attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, mp, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_bwd");
 }

@@ -37,6 +37,7 @@ struct EpiParams {
   uint32_t drop_thr; float drop_scale; uint64_t drop_seed, drop_offset;
   int num_k_blocks;
   int a_m1, a_m2, b_m1, b_m2;  // 0 when the operand is broadcast over that batch dim (stride 0), else 1
+  int c_m1, c_m2;              // the same for the output (accumulate == 2: split-K batches share one output)
   const void* ag_pre; int ag_act;   // optional: multiply by act'(ag_pre[m][n]) (activation backward fused into dX)
   int tma_store;                    // 1: outputs leave through shared memory + TMA store (maps map_c / map_cpre)
   int tiles_m, tiles_n, num_tiles;  // persistent schedule: tile = (z * tiles_n + n_blk) * tiles_m + m_blk
@@ -261,11 +262,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
     const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
     const int row = m0 + q * 32 + (int)lane_id();
-    mbar_wait(&tfull_bar[acc], acc_phase);
-    tc_fence_after();
     const bool row_ok = row < p.M;
     const long zoff = (long)b1 * p.c_bs1 + (long)b2 * p.c_bs2;
     const long roff = zoff + (long)row * p.c_ld;
+    // Epilogue operands that come from global memory -- the bias of this chunk's 32 columns (one value per lane, handed
+    // round by shuffles) and this row's 64 bytes of the backward gate / residual -- are requested BEFORE the wait on
+    // the accumulator (first chunk) or while the previous chunk is being stored (later chunks): their latency used to
+    // sit, fully exposed, between the TMEM read and the math (ncu: 25-45 % of the dH / fc2 / out_proj samples).
+    const __nv_bfloat16* pf_src = nullptr;  // bf16 [rows][c_ld] operand with the output's layout, 16-byte vectors
+    if (!p.c_fp32 && ((p.c_ld & 7) == 0) && ((zoff & 7) == 0)) {
+      const void* cand = p.ag_pre != nullptr ? p.ag_pre : p.residual;
+      if (cand != nullptr && (reinterpret_cast<uintptr_t>(cand) & 15) == 0)
+        pf_src = reinterpret_cast<const __nv_bfloat16*>(cand);
+    }
+    const bool pf_is_gate = pf_src != nullptr && p.ag_pre != nullptr;
+    uint4 pf[4];
+    float bias_lane = 0.f;
+    auto prefetch = [&](int c) {
+      const int nb = n0 + c * 32;
+      if (p.bias != nullptr) {
+        const int jn = nb + (int)lane_id();
+        bias_lane = jn < p.N ? __ldg(p.bias + jn) : 0.f;
+      }
+      if (pf_src != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          pf[g] = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok && nb + 8 * g + 8 <= p.N) pf[g] = *reinterpret_cast<const uint4*>(pf_src + roff + nb + 8 * g);
+        }
+      }
+    };
+    if (grp < BN / 32) prefetch(grp);
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
     const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
     const uint64_t drop_row = ((uint64_t)z * (uint64_t)p.M + (uint64_t)row) * (uint64_t)p.N;
     if (grp >= BN / 32) {  // narrow tiles: this warp has no chunk, it only releases the accumulator stage
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
         for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
       }
       const bool full = (nb + 32 <= p.N);
-      if (p.accumulate && row_ok) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
+      if (p.accumulate == 1 && row_ok) {  // partial sums of a multi-pass (split-precision) product live in C (fp32)
         const float* src = reinterpret_cast<const float*>(p.C) + roff + nb;
         if (full && ((p.c_ld & 3) == 0) && ((zoff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
@@ -313,21 +342,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
             if (full || nb + j < p.N) v[j] += src[j];
         }
       }
-      if (p.bias != nullptr) {
-        if (full && ((reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0)) {
-          // every lane needs the same 32 values: eight 16-byte loads of one address per warp (L1 broadcast)
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+      if (p.bias != nullptr) {  // lane j holds the bias of column nb + j (prefetched): 32 register shuffles
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(bp + j);
-            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-          }
-        } else {  // ragged edge: one coalesced load per warp, then register shuffles
-          const int jn = nb + (int)lane_id();
-          const float bl = jn < p.N ? __ldg(p.bias + jn) : 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
-        }
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (bias2_row != nullptr) {
 #pragma unroll
@@ -365,7 +382,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           fence_proxy_async();
           __syncwarp();
           if (lane_id() == 0) {
-            tma_store_4d(tmap, stg, nb, m0 + q * 32, b1, b2);
+            if (p.accumulate == 2) tma_reduce_add_4d(tmap, stg, nb, m0 + q * 32, b1 * p.c_m1, b2 * p.c_m2);  // C += tile, at the L2
+            else tma_store_4d(tmap, stg, nb, m0 + q * 32, b1 * p.c_m1, b2 * p.c_m2);
             bulk_commit();
           }
           return;
@@ -458,6 +476,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           tma_store_4d(&map_cpre, stg + 2048, nb, m0 + q * 32, b1, b2);
           bulk_commit();
         }
+        if (c + NGRP < BN / 32) prefetch(c + NGRP);
         continue;
       }
       if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
@@ -487,7 +506,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           if (vec_ok && ((reinterpret_cast<uintptr_t>(p.ag_pre) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
+              const uint4 u = pf_is_gate ? pf[j >> 3] : *reinterpret_cast<const uint4*>(pr + j);
               if (p.ag_act == ACT_GATE) actgrad8<ACT_GATE>(v + j, u);
               else if (p.ag_act == ACT_GELU_TANH) actgrad8<ACT_GELU_TANH>(v + j, u);
               else if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
@@ -513,7 +532,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           if (vec_ok && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
+              const uint4 u = (pf_src != nullptr && !pf_is_gate) ? pf[j >> 3] : *reinterpret_cast<const uint4*>(rs + j);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -529,6 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           }
         }
       }
+      if (c + NGRP < BN / 32) prefetch(c + NGRP);  // (everything of this chunk has been consumed above)
       emit(p.C, &map_c);
     }
     }
@@ -676,15 +696,17 @@ static int launch_variant(const GemmDesc& g, const EpiParams& ep, cudaStream_t s
                     (g.nb2 <= 1 || (g.c_bs2 * es) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) &&
                     (g.C_pre == nullptr || reinterpret_cast<uintptr_t>(g.C_pre) % 16 == 0);
     if (ok) {
-      const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.nb1, (uint64_t)g.nb2};
-      const uint64_t strides[3] = {(uint64_t)(g.c_ld * es), (uint64_t)((g.nb1 > 1 ? g.c_bs1 : g.c_ld) * es),
-                                   (uint64_t)((g.nb2 > 1 ? g.c_bs2 : g.c_ld) * es)};
+      const int cn1 = (g.nb1 > 1 && g.c_bs1 != 0) ? g.nb1 : 1, cn2 = (g.nb2 > 1 && g.c_bs2 != 0) ? g.nb2 : 1;
+      const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)cn1, (uint64_t)cn2};
+      const uint64_t strides[3] = {(uint64_t)(g.c_ld * es), (uint64_t)((cn1 > 1 ? g.c_bs1 : g.c_ld) * es),
+                                   (uint64_t)((cn2 > 1 ? g.c_bs2 : g.c_ld) * es)};
       const uint32_t box[4] = {32, 32, 1, 1};
       int r2 = encode_map_4d(&mc, g.C, g.c_fp32, dims, strides, box, g.c_fp32 ? 128 : 64);
       if (!r2 && g.C_pre != nullptr) r2 = encode_map_4d(&mcp, g.C_pre, g.c_fp32, dims, strides, box, g.c_fp32 ? 128 : 64);
       e2.tma_store = r2 == 0 ? 1 : 0;
     }
   }
+  if (g.accumulate == 2 && !e2.tma_store) return -6;  // the L2-side accumulate is a TMA reduce: needs that output layout
   if (e2.act == ACT_GELU_TANH_GATE &&
       (!e2.tma_store || g.c_fp32 || g.C_pre == nullptr || (g.N & 7) != 0 || g.residual != nullptr || g.ag_pre != nullptr))
     return -5;  // the gate epilogue needs the TMA-store layout, bf16 outputs and an 8-aligned row length
@@ -734,6 +756,9 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.nb1 <= 0 || g.nb2 <= 0) return 0;
   if (g.K <= 0) return -2;
   if (g.accumulate && !g.c_fp32) return -3;
+  // a batch dimension with output stride 0 (split-K: several partial products into ONE output) is only sound with the
+  // L2-side accumulate
+  if (g.accumulate != 2 && ((g.nb1 > 1 && g.c_bs1 == 0) || (g.nb2 > 1 && g.c_bs2 == 0))) return -7;
   EpiParams ep;
   ep.M = g.M; ep.N = g.N; ep.nb1 = g.nb1;
   ep.C = g.C; ep.c_fp32 = g.c_fp32; ep.c_ld = g.c_ld; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2;
@@ -746,6 +771,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   ep.num_k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   ep.a_m1 = (g.nb1 > 1 && g.a_bs1 == 0) ? 0 : 1; ep.a_m2 = (g.nb2 > 1 && g.a_bs2 == 0) ? 0 : 1;
   ep.b_m1 = (g.nb1 > 1 && g.b_bs1 == 0) ? 0 : 1; ep.b_m2 = (g.nb2 > 1 && g.b_bs2 == 0) ? 0 : 1;
+  ep.c_m1 = (g.nb1 > 1 && g.c_bs1 == 0) ? 0 : 1; ep.c_m2 = (g.nb2 > 1 && g.c_bs2 == 0) ? 0 : 1;
   // Tile width: minimise (rounds of the persistent grid) x (time per tile). A 128x256 tile reads 12 KB of smem per
   // 128-cycle MMA (under the 128 B/clk port); 128x128 and 128x64 tiles are smem-port bound, hence the >1 factors.
   const long tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
@@ -772,6 +798,11 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   const double c256 = g.N > 128 ? cost(256, 1.0) : 1e30;
   const double c128 = g.N > 64 ? cost(128, 1.12) : 1e30;
   const double c64 = cost(64, 1.35);
+  // Weight gradients (accumulate == 2: both operands MN-major, long contraction split over the batch dimension by the
+  // caller so that the CTA pairs fill the machine): 256 x 256 pair tiles halve the operand bytes per FLOP, which is what
+  // bounds these GEMMs (128 x 128 tiles: 36 % tensor-pipe activity, the library reaches 1.45 PFLOP/s on the same shapes)
+  if (pair_mode != 0 && force_bn == 0 && g.accumulate == 2 && g.M >= 2 * BLOCK_M && g.N >= 192)
+    return launch_major<256, 4, 2>(g, ep, stream);
   if (c256 <= c128 && c256 <= c64) {
     if (pair_mode == 2 && g.M > BLOCK_M) return launch_major<256, 5, 2>(g, ep, stream);  // deeper ring (tuning)
     if (pair_mode == 1 && g.M > BLOCK_M) return launch_major<256, 4, 2>(g, ep, stream);

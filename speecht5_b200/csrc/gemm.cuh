@@ -29,7 +29,8 @@ struct GemmDesc {
   const void* residual;   // optional, same layout & dtype as C, added after activation/dropout
   int act;
   float alpha;
-  int accumulate;         // C += result (C must be fp32)
+  int accumulate;         // 1: C += result, read-modify-write in the epilogue; 2: C += result as a TMA reduce at the L2
+                          //    (batch entries may then share one output: split-K). C must be fp32
   float drop_p; uint64_t drop_seed, drop_offset;
   const void* ag_pre; int ag_act;  // optional: out *= act'(ag_pre[m][n]) after the dropout mask (same layout as C)
 };

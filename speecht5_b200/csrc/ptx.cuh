@@ -92,6 +92,14 @@ __device__ __forceinline__ void tma_store_4d(const void* map, const void* src, i
                : "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// TMA reduce: global tile += shared tile, element type from the tensor map (fp32 here); the read-modify-write happens at
+// the L2, so several CTAs may target the same tile (split-K partial products) and nobody has to read C first.
+__device__ __forceinline__ void tma_reduce_add_4d(const void* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory source of every committed bulk store of this thread has been read
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

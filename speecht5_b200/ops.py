@@ -36,6 +36,7 @@ class Runtime:
         # every bf16 shape goes through it (ST5_ATTN_FLASH=all)
         self.attn_flash = {"0": False, "all": "all"}.get(os.environ.get("ST5_ATTN_FLASH", "1"), True)
         self.ffn_gate = os.environ.get("ST5_FFN_GATE", "1") != "0"  # bf16 mode: fc1 stores the backward gate (FFNFn)
+        self.wgrad_splitk = os.environ.get("ST5_WGRAD_SPLITK", "1") != "0"  # weight gradients: pair tiles + split-K + L2 reduce
         self.fp32_stream = os.environ.get("ST5_FP32_STREAM", "1") != "0"  # bf16 mode: fp32 residual stream between LayerNorms
         # trainer hooks: stage_callback(key, x) is called at the entry of every encoder / decoder layer (gradient-exchange
         # overlap point); layer_keep (device [n_enc + n_dec] 0/1 mask, CUDA-graph mode) / layer_keep_host (eager mode)
@@ -199,7 +200,9 @@ def wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=None):
     dev = gy[0].device
     tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
     S = 1
-    if gy[1] is None and xin[1] is None and tiles <= 72 and M >= 2048:
+    splitk_l2 = (target is not None and gy[1] is None and xin[1] is None and RT.wgrad_splitk and n_out >= 256
+                 and n_in >= 192 and target.is_contiguous() and target.data_ptr() % 16 == 0 and n_in % 4 == 0)
+    if not splitk_l2 and gy[1] is None and xin[1] is None and tiles <= 72 and M >= 2048:
         for cand in (8, 6, 4, 3, 2):
             if cand * tiles <= 320 and M % cand == 0:
                 S = cand
@@ -212,6 +215,21 @@ def wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=None):
         out = target if target is not None else torch.empty((n_out, n_in), dtype=torch.float32, device=dev)
         K.colsum(parts.view(S, n_out * n_in), out.view(-1), accumulate=target is not None)
         return None if target is not None else out
+    if splitk_l2:
+        # throughput mode, straight into the flat gradient buffer: 256 x 256 CTA-pair tiles, the contraction split over
+        # the batch dimension so that (tiles x splits) fills the 74 pairs of the chip, every partial product added to
+        # the gradient by a TMA reduce at the L2 (nobody reads the gradient first, no partial buffers, no reduction
+        # launch). Splits must divide M: a batch entry is a [chunk]-row window of the MN-major operands.
+        tp = ((n_out + 255) // 256) * ((n_in + 255) // 256)
+        S = 1
+        for cand in (16, 12, 10, 8, 6, 5, 4, 3, 2):
+            if cand * tp <= 76 and M % cand == 0 and M // cand >= 512:
+                S = cand
+                break
+        chunk = M // S
+        K.gemm(gy[0], xin[0], target, M=n_out, N=n_in, K=chunk, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld,
+               c_ld=n_in, nb1=S, nb2=1, a_bs=(chunk * gy_ld, 0), b_bs=(chunk * xin_ld, 0), c_bs=(0, 0), accumulate=2)
+        return None
     if target is not None:
         mm(gy, xin, target, M=n_out, N=n_in, Kd=M, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld, c_ld=n_in,
            accumulate=True)

@@ -87,11 +87,12 @@ def _fused_groups(model):
     return [g for g in groups if all(p is not None for p in g)]
 
 
-def stage_of(name):
-    """Stage key of a parameter name: ("enc", i) / ("dec", i) for the transformer layers, None for everything else."""
+def stage_of(name, group=1):
+    """Stage key of a parameter name: ("enc", g) / ("dec", g) for the transformer layers (g = layer // group: `group`
+    consecutive layers form one exchange stage), None for everything else."""
     for prefix, tag in (("encoder.layers.", "enc"), ("decoder.layers.", "dec")):
         if name.startswith(prefix):
-            return (tag, int(name[len(prefix):].split(".", 1)[0]))
+            return (tag, int(name[len(prefix):].split(".", 1)[0]) // max(1, group))
     return None
 
 
@@ -101,8 +102,9 @@ class FlatParams:
     Layout: [stage 0 GEMM weights | stage 1 ... | stage S-1 | replicated tail]. A stage range is padded to a multiple
     of 8 * world elements (16-byte bf16 alignment of every shard). `stages` maps stage key -> (lo, hi)."""
 
-    def __init__(self, model, world=1, rank=0):
+    def __init__(self, model, world=1, rank=0, stage_group=1):
         params = [p for p in model.parameters()]
+        self.stage_group = max(1, int(stage_group))
         dev = params[0].device
         self.world, self.rank = world, rank
         groups = _fused_groups(model)
@@ -125,7 +127,7 @@ class FlatParams:
                 seen.update(id(q) for q in g)
 
         def key(u):  # stage of a unit; only 2-D GEMM weights (static flat shadows) are placed in stage ranges
-            return stage_of(names.get(id(u[0]), "")) if u[0].dim() == 2 else None
+            return stage_of(names.get(id(u[0]), ""), self.stage_group) if u[0].dim() == 2 else None
         order_keys = sorted({key(u) for u in units if key(u) is not None}, key=lambda k: (k[0] != "enc", k[1]))
         offsets, off = {}, 0
         self.stages = collections.OrderedDict()
@@ -200,7 +202,7 @@ class B200Trainer:
 
     def __init__(self, model, criterion, task, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0, clip_norm=25.0,
                  process_group=None, use_cuda_graph=True, bucket_mb=128, exchange=None, graph_cache=8,
-                 shape_buckets=None):
+                 shape_buckets=None, stage_group=1):
         self.model, self.criterion, self.task = model, criterion, task
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.device = next(model.parameters()).device
@@ -214,7 +216,10 @@ class B200Trainer:
         if RT.dtype == torch.float32 and exchange == "shard" and self.world > 1:
             raise ValueError("parity mode reads the fp32 masters in every GEMM: use exchange='allreduce'")
         self.exchange = exchange if self.world > 1 else "none"
-        self.fp = FlatParams(model, self.world if self.exchange == "shard" else 1, self.rank)
+        # layers per exchange stage: fewer, larger collectives (each NCCL launch has to squeeze its CTAs in between
+        # persistent 148-CTA GEMM grids) against later overlap; ST5_STAGE_GROUP overrides
+        self.stage_group = int(os.environ.get("ST5_STAGE_GROUP", stage_group))
+        self.fp = FlatParams(model, self.world if self.exchange == "shard" else 1, self.rank, self.stage_group)
         self.bucketer = GradBucketer(self.fp.grads, bucket_elems=bucket_mb * 1024 * 1024 // 4, group=process_group)
         # overlap of the exchange with backward: model code calls RT.stage(key, x) at the entry of every stage
         self._overlap = self.world > 1 and os.environ.get("ST5_OVERLAP_AR", "1") != "0"
@@ -270,6 +275,10 @@ class B200Trainer:
     def _on_stage(self, sk, x):
         """Called by the model at the entry of stage `sk` (forward). In backward, the gradient of this tensor arrives
         after every parameter gradient of the stage has been written: launch the stage's exchange there."""
+        tag, idx = sk
+        if idx % self.stage_group != 0:  # the gradient of a GROUP's first layer input is the last one of the group
+            return x
+        sk = (tag, idx // self.stage_group)
         if sk in self.fp.stages and self._overlap and torch.is_grad_enabled() and x.requires_grad:
             def hook(grad, sk=sk):
                 if self._last_micro and sk not in self._done:
@@ -339,7 +348,22 @@ class B200Trainer:
         return torch.stack(losses), (torch.stack(stats) if stats[0] is not None else None)
 
     def _gather(self, buf):
-        for sk in self.fp.stages:
+        """Every rank's shard of every stage -> every rank's full stage range. On NCCL the per-stage all-gathers are
+        issued as ONE coalesced group (a single launch instead of one per layer: they all sit, exposed, at the end of
+        the update)."""
+        stages = list(self.fp.stages)
+        if self.device.type == "cuda" and len(stages) > 1 and os.environ.get("ST5_COALESCE", "1") != "0":
+            try:
+                from torch.distributed.distributed_c10d import _coalescing_manager
+                with _coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                    for sk in stages:
+                        lo, hi = self.fp.stages[sk]
+                        slo, shi = self.fp.shard(sk)
+                        dist.all_gather_into_tensor(buf[lo:hi], buf[slo:shi], group=self.group)
+                return
+            except (ImportError, RuntimeError, NotImplementedError):
+                pass
+        for sk in stages:
             lo, hi = self.fp.stages[sk]
             slo, shi = self.fp.shard(sk)
             try:

@@ -462,3 +462,28 @@ def test_streaming_attention_dropout_matches_row_kernels(cuda):
     ops.RT.attn_tensor_core = True
     assert rel(res[0][0], res[1][0]) < 3e-2
     assert rel(res[0][1], res[1][1]) < 3e-2
+
+
+@pytest.mark.parametrize("shape", [(768, 768, 10016, 8), (3072, 768, 5120, 2), (2304, 768, 5120, 2), (256, 200, 1024, 2),
+                                   (768, 3072, 5120, 1)])
+def test_weight_gradient_split_k_with_l2_reduce(cuda, shape):
+    """accumulate = 2: dW += gy^T x with the contraction split over the batch dimension, every partial product added to
+    the SAME fp32 output by a TMA reduce (cp.reduce.async.bulk.tensor .add) on 256 x 256 CTA-pair tiles -- against an
+    fp64 product of the same bf16 operands, on top of a non-zero gradient buffer (fairseq accumulates micro-batches)."""
+    from speecht5_b200 import kernels as K
+    n_out, n_in, M, S = shape
+    torch.manual_seed(3)
+    gy = (torch.randn(M, n_out, device=cuda) * 0.5).to(torch.bfloat16)
+    x = (torch.randn(M, n_in, device=cuda) * 0.5).to(torch.bfloat16)
+    base = torch.randn(n_out, n_in, device=cuda)
+    out = base.clone()
+    chunk = M // S
+    K.gemm(gy, x, out, M=n_out, N=n_in, K=chunk, a_mn=True, a_ld=n_out, b_mn=True, b_ld=n_in, c_ld=n_in, nb1=S, nb2=1,
+           a_bs=(chunk * n_out, 0), b_bs=(chunk * n_in, 0), c_bs=(0, 0), accumulate=2)
+    ref = base.double() + gy.double().t() @ x.double()
+    assert rel(out, ref) < 2e-6
+    # and the same through the op the layers call, into a registered gradient view
+    from speecht5_b200 import ops
+    tgt = base.clone()
+    ops.wgrad_mm((gy, None), n_out, (x, None), n_in, n_out, n_in, M, target=tgt)
+    assert rel(tgt, ref) < 2e-6

@@ -38,7 +38,9 @@ for mode, graph in (("allreduce", False), ("shard", False), ("shard", True), ("a
     task = SpeechT5Task(args)
     model = task.build_model(args).to(dev).train()
     crit = SpeechT5Criterion(task, use_guided_attn_loss=True)
-    tr = B200Trainer(model, crit, task, lr=1e-3, clip_norm=25.0, use_cuda_graph=graph, exchange=mode)
+    # eps = 1: the update is ~linear in the gradient (Adam's default eps turns every noise-level gradient into a +-lr step,
+    # and the modes then differ by the order of fp32 atomics, not by the exchange)
+    tr = B200Trainer(model, crit, task, lr=5e-2, eps=1.0, clip_norm=25.0, use_cuda_graph=graph, exchange=mode)
     for _ in range(2):
         losses, _ = tr.train_step([sample])
     torch.cuda.synchronize()
@@ -61,7 +63,7 @@ for key, (shadow, flat, loss) in results.items():
     df = ((flat - base[1]).norm() / base[1].norm()).item()
     if rank == 0:
         print(f"{key}: shadow rel diff {ds:.2e}, master rel diff {df:.2e}", flush=True)
-    ok = ok and ds < 1e-3 and df < 1e-5
+    ok = ok and ds < 1e-3 and df < 2e-5
 if rank == 0:
     print("N2 CHECK", "OK" if ok else "FAILED", flush=True)
 dist.barrier()
