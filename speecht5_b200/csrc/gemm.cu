@@ -265,25 +265,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     const bool row_ok = row < p.M;
     const long zoff = (long)b1 * p.c_bs1 + (long)b2 * p.c_bs2;
     const long roff = zoff + (long)row * p.c_ld;
-    // Epilogue operands that come from global memory -- the bias of this chunk's 32 columns (one value per lane, handed
-    // round by shuffles) and this row's 64 bytes of the backward gate / residual -- are requested BEFORE the wait on
-    // the accumulator (first chunk) or while the previous chunk is being stored (later chunks): their latency used to
-    // sit, fully exposed, between the TMEM read and the math (ncu: 25-45 % of the dH / fc2 / out_proj samples).
+    // This row's 64 bytes of the backward gate / residual are requested BEFORE the wait on the accumulator (first chunk)
+    // or while the previous chunk is being stored (later chunks): their latency used to sit, fully exposed, between the
+    // TMEM read and the math (ncu: 25-45 % of the dH / fc2 / out_proj samples).
     const __nv_bfloat16* pf_src = nullptr;  // bf16 [rows][c_ld] operand with the output's layout, 16-byte vectors
+#ifndef ST5_NO_EPI_PREFETCH  // (A/B build switch: tools/build_variant.sh)
     if (!p.c_fp32 && ((p.c_ld & 7) == 0) && ((zoff & 7) == 0)) {
       const void* cand = p.ag_pre != nullptr ? p.ag_pre : p.residual;
       if (cand != nullptr && (reinterpret_cast<uintptr_t>(cand) & 15) == 0)
         pf_src = reinterpret_cast<const __nv_bfloat16*>(cand);
     }
+#endif
     const bool pf_is_gate = pf_src != nullptr && p.ag_pre != nullptr;
     uint4 pf[4];
-    float bias_lane = 0.f;
     auto prefetch = [&](int c) {
       const int nb = n0 + c * 32;
-      if (p.bias != nullptr) {
-        const int jn = nb + (int)lane_id();
-        bias_lane = jn < p.N ? __ldg(p.bias + jn) : 0.f;
-      }
       if (pf_src != nullptr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -342,9 +338,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
             if (full || nb + j < p.N) v[j] += src[j];
         }
       }
-      if (p.bias != nullptr) {  // lane j holds the bias of column nb + j (prefetched): 32 register shuffles
+      if (p.bias != nullptr) {
+        if (full && ((reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0)) {
+          // every lane needs the same 32 values: eight 16-byte loads of one address per warp (L1 broadcast)
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        } else {  // ragged edge: one coalesced load per warp, then register shuffles
+          const int jn = nb + (int)lane_id();
+          const float bl = jn < p.N ? __ldg(p.bias + jn) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+        }
       }
       if (bias2_row != nullptr) {
 #pragma unroll

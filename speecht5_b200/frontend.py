@@ -15,6 +15,7 @@ Device formulation (channels-last activations [B, T, C] throughout, no im2col, n
 * input gradient: the transposed convolution split by output phase r = i mod stride; phase r is a window GEMM over
   the (front-padded) gradient with the taps t = r, r+stride, ... in reverse order, written with row pitch stride*C_in;
 * weight gradient: per utterance dW2[b] = g_b^T . windows_b (both operands read MN-major), summed over b."""
+import numpy as np
 import torch
 
 from . import kernels as K
@@ -325,6 +326,9 @@ class SpeechEncoderPrenet(torch.nn.Module):
             raise NotImplementedError("--use-conv-pos is required (as in every speech-input recipe)")
         self.embed = layers[-1][0]
         d = args.encoder_embed_dim
+        # labels per frame (:89-92): label rate x total conv stride / sample rate (50 x 320 / 16000 = 1 for HuBERT labels)
+        self.feat2tar_ratio = (getattr(args, "label_rates", 50) * float(np.prod([st for _, _, st in layers]))
+                               / getattr(args, "sample_rate", 16000))
         self.feature_extractor = ConvFeatureExtractor(layers, args.extractor_mode, args.conv_bias)
         self.post_extract_proj = torch.nn.Linear(self.embed, d) if self.embed != d else None
         self.feature_grad_mult = args.feature_grad_mult
@@ -368,13 +372,24 @@ class SpeechEncoderPrenet(torch.nn.Module):
         `mask_channel_indices` [B,C] (extra, optional) inject a precomputed mask draw instead of sampling one here --
         the trainer draws them on the host before a CUDA-graph replay (speecht5_b200.data.draw_hubert_masks)."""
         import contextlib
-        if target_list is not None:
-            raise NotImplementedError("pre-training targets (forward_targets, SURVEY 8a row 22) are a later row")
         ft = self.freeze_encoder_updates <= self.num_updates
         with torch.no_grad() if not ft else contextlib.ExitStack():
-            return self._forward(src_tokens, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices)
+            return self._forward(src_tokens, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices,
+                                 target_list)
 
-    def _forward(self, source, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices=None):
+    def forward_targets(self, features, target_list):
+        """speech_encoder_prenet.py:206-217 on [B, T, C] frames: trim the frames to the span the k-means labels cover and
+        pick the label of every frame (label rate x frame stride / sample rate labels per frame)."""
+        feat_tsz = features.size(1)
+        targ_tsz = min(t.size(1) for t in target_list)
+        if self.feat2tar_ratio * feat_tsz > targ_tsz:
+            feat_tsz = int(targ_tsz / self.feat2tar_ratio)
+            features = features[:, :feat_tsz]
+        inds = (torch.arange(feat_tsz, device=target_list[0].device).float() * self.feat2tar_ratio).long()
+        return features, [t[:, inds] for t in target_list]
+
+    def _forward(self, source, require_feat_pen, padding_mask, mask, mask_indices, mask_channel_indices=None,
+                 target_list=None):
         from . import ops
         if self.feature_grad_mult > 0:
             x = self.feature_extractor(source)
@@ -383,6 +398,9 @@ class SpeechEncoderPrenet(torch.nn.Module):
         else:
             with torch.no_grad():
                 x = self.feature_extractor(source)
+        if target_list is not None:  # (:170-171) pre-training: frames aligned with the HuBERT labels
+            x, target_list = self.forward_targets(x, target_list)
+            x = x.contiguous()
         features_pen = x.float().pow(2).mean()
         B, T, _ = x.shape
         x = ops.residual_layer_norm(x, None, self.layer_norm)
@@ -414,7 +432,7 @@ class SpeechEncoderPrenet(torch.nn.Module):
         if self.use_sinc_pos:
             x = x + self._positions(frame_mask, B, T, x.device).to(x.dtype)
         if require_feat_pen:
-            return (x, features_pen, mask_indices, None), frame_mask
+            return (x, features_pen, mask_indices, target_list), frame_mask
         return x, frame_mask
 
 

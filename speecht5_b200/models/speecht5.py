@@ -90,7 +90,16 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         assert self.spk_embed_integration_type == "pre" or self.spk_embed_dim is None, \
             "only spk_embed_integration_type='pre' (the reference default) is implemented"
         self.use_codebook = args.use_codebook
-        assert not self.use_codebook, "Gumbel-VQ code mixing (pre-training, SURVEY 8a row 22) is a later row"
+        self.codebook_prob = getattr(args, "codebook_prob", 0.5)
+        if self.use_codebook:  # (:93-106) Gumbel vector quantizer of the pre-training recipes
+            from ..pretrain import GumbelVectorQuantizer
+            if getattr(args, "quantizer_depth", 1) != 1:
+                raise NotImplementedError("quantizer_depth > 1 (no SpeechT5 recipe uses it)")
+            temp = getattr(args, "latent_temp", (2.0, 0.5, 0.999995))
+            temp = eval(temp) if isinstance(temp, str) else temp
+            vq_dim = args.latent_dim if getattr(args, "latent_dim", 0) > 0 else args.encoder_embed_dim
+            self.quantizer = GumbelVectorQuantizer(dim=args.encoder_embed_dim, num_vars=getattr(args, "latent_vars", 100),
+                                                   temp=tuple(temp), groups=getattr(args, "latent_groups", 2), vq_dim=vq_dim)
         self.num_updates = 0
         if args.bert_init:
             self.apply(init_bert_params)
@@ -191,8 +200,20 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if getattr(args, "build_speech_encoder", False):
             from ..frontend import SpeechEncoderPrenet
             speech_encoder_prenet = SpeechEncoderPrenet(args)
+        # masked-prediction head of speech pre-training (:717-720): built when the task carries HuBERT label dictionaries
+        speech_encoder_postnet = None
+        hub = task.dicts.get("hubert") if (task is not None and hasattr(task, "dicts")) else None
+        classes = [len(dct) for dct in hub] if hub else getattr(args, "hubert_num_classes", None)
+        if classes:
+            from ..pretrain import SpeechEncoderPostnet
+            fd = getattr(args, "final_dim", 0)
+            speech_encoder_postnet = SpeechEncoderPostnet(
+                classes, args.encoder_embed_dim, fd if fd > 0 else args.encoder_embed_dim,
+                logit_temp=getattr(args, "logit_temp", 0.1), untie_final_proj=getattr(args, "untie_final_proj", True),
+                skip_masked=getattr(args, "skip_masked", False), skip_nomask=getattr(args, "skip_nomask", False),
+                target_glu=getattr(args, "target_glu", False))
         return cls(args, encoder, decoder, text_encoder_prenet, speech_encoder_prenet, text_decoder_prenet,
-                   speech_decoder_prenet, text_decoder_postnet, speech_decoder_postnet, None, None)
+                   speech_decoder_prenet, text_decoder_postnet, speech_decoder_postnet, None, speech_encoder_postnet)
 
     # ------------------------------------------------------------------ forward (models/speecht5.py:786-963)
     def forward(self, source=None, src_tokens=None, src_lengths=None, prev_output_tokens=None, tgt_lengths=None,
@@ -208,20 +229,53 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         speech_in = input_type == "speech" and self.speech_encoder_prenet is not None and not feature_only
         built = (input_type == "text" and output_type == "speech") or t2t or (
             speech_in and (text_out or output_type == "speech" or prev_output_tokens is None))
-        if not built or target_list is not None or only_hubert:
+        if target_list is not None and (self.hubert_layer is None or not speech_in):
+            raise NotImplementedError("pre-training targets need speech input and the masked-prediction head "
+                                      "(task with HuBERT label dictionaries, or --hubert-num-classes)")
+        if not built:
             raise NotImplementedError(
-                f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built yet in the "
-                "B200 path; round 1 covers text->speech (t2s), opt-in: text output and speech input")
-        if speech_in:  # (:815-820) waveform -> frames; the HuBERT-style mask is drawn only in training
+                f"T5TransformerModel.forward: {input_type}->{output_type} (task {task_name}) is not built in the B200 "
+                "path (speaker identification / voice conversion / enhancement branches)")
+        features_pen = frame_mask_indices = None
+        if speech_in and target_list is not None:  # (:813-815) speech pre-training: frames aligned with the labels
+            enc_in, encoder_padding_mask = self.speech_encoder_prenet(
+                source, require_feat_pen=True, target_list=target_list, padding_mask=padding_mask, mask=mask,
+                mask_indices=mask_indices, mask_channel_indices=mask_channel_indices)
+            encoder_input, features_pen, frame_mask_indices, target_list = enc_in
+        elif speech_in:  # (:815-820) waveform -> frames; the HuBERT-style mask is drawn only in training
             encoder_input, encoder_padding_mask = self.speech_encoder_prenet(
                 source, padding_mask=padding_mask, mask=self.training and mask, mask_indices=mask_indices,
                 mask_channel_indices=mask_channel_indices)
         else:
             encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)
         encoder_output = self.encoder(encoder_input, encoder_padding_mask, tgt_layer=tgt_enc_layer)
+        if task_name == "speech_pretrain" and feature_only:  # (:832-833)
+            return encoder_output["encoder_out"][0].transpose(0, 1)
+        hubert_results = None
+        if target_list is not None:  # (:844-852) masked / unmasked frame logits against the label embeddings
+            pm = encoder_padding_mask if encoder_padding_mask is not None else torch.zeros(
+                encoder_input.shape[:2], dtype=torch.bool, device=encoder_input.device)
+            mi = frame_mask_indices if frame_mask_indices is not None else torch.zeros_like(pm)
+            hubert_results = self.hubert_layer(encoder_output["_encoder_out_btc"], pm, mi, target_list)
+            hubert_results["features_pen"] = features_pen
         if "decoder_input" in encoder_output and encoder_output["decoder_input"][0] is not None:
             encoder_output["encoder_out"] = encoder_output["decoder_input"]
             encoder_output["_encoder_out_btc"] = encoder_output["decoder_input"][0].transpose(0, 1)
+        codebook_out = {}
+        if self.use_codebook:  # (:858-882) a random share of the time steps is replaced by its quantized code
+            from ..pretrain import mix_codes
+            x_btc = encoder_output["_encoder_out_btc"]
+            q = self.quantizer(x_btc, gumbel_noise=getattr(self, "_gumbel_noise", None))
+            mixed = mix_codes(x_btc, q["x"], self.codebook_prob, perm=getattr(self, "_codebook_perm", None))
+            encoder_output["_encoder_out_btc"] = mixed
+            encoder_output["encoder_out"] = [mixed.transpose(0, 1)]
+            stats = {k: q[k] for k in ("prob_perplexity", "code_perplexity", "num_vars", "temp")}
+            if output_type == "speech" and hubert_results is not None:
+                hubert_results.update(stats)
+            elif output_type == "text":
+                codebook_out.update(stats)
+        if only_hubert and target_list is not None:  # (:884-885)
+            return hubert_results, None
         if speech_in and task_name == "s2t":  # (:885-888)
             if only_ctc:
                 return None, encoder_output
@@ -236,12 +290,14 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
             logits = self.text_decoder_postnet(decoder_output)
             if task_name == "s2t":  # (:955-956)
                 return (logits, None), encoder_output
-            return (logits, None), {}, encoder_output
+            return (logits, None), codebook_out, encoder_output
         prev_output_tokens, tgt_mask = self.speech_decoder_prenet(prev_output_tokens, tgt_lengths, spkembs)
         decoder_output, extra = self.decoder(
             prev_output_tokens, tgt_mask, encoder_output,
             full_context_alignment=getattr(self.args, "decoder_full_context_alignment", False),
-            alignment_layer=-1)  # target_list is None and output is speech (:921-923)
+            alignment_layer=-1 if target_list is None else None)  # (:921-923)
+        if target_list is not None:  # (:960-961) speech pre-training: head results + the reconstruction branch
+            return hubert_results, (self.speech_decoder_postnet(decoder_output) + (extra["attn"][0],))
         return self.speech_decoder_postnet(decoder_output) + (extra["attn"][0],)
 
     # ------------------------------------------------------------------ fairseq model API used by callers

@@ -487,3 +487,92 @@ def test_pretraining_head_and_quantizer_on_emulated_kernels(monkeypatch, dtype):
     mixed_m = pretrain.mix_codes(x, qr["x"], 0.5, perm)
     assert torch.equal(mixed_m, mixed_r)
     RT.invalidate_shadows()
+
+
+def test_speech_pretraining_branch_of_forward_on_emulated_kernels(monkeypatch):
+    """models/speecht5.py:813-961 with target_list (speech pre-training): prenet with label alignment and feature penalty
+    -> encoder -> masked-prediction head, Gumbel quantizer + code mixing on the encoder output, speech decoder on the
+    mixed states -- T5TransformerModel.forward on emulated kernels against the same composition of the oracles
+    (speech prenet / encoder / decoder oracles + oracle/pretrain_oracle.py), same Gumbel noise and time permutation."""
+    from oracle import pretrain_oracle as P
+    from oracle import speecht5_oracle as OT
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200 import frontend
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    torch.manual_seed(11)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0, mask_channel_prob=0.0, dropout=0.0,
+                attention_dropout=0.0, activation_dropout=0.0, dprenet_dropout_rate=0.0, postnet_dropout_rate=0.0,
+                transformer_enc_positional_dropout_rate=0.0, transformer_dec_positional_dropout_rate=0.0,
+                encoder_layerdrop=0.0, decoder_layerdrop=0.0)
+    oargs = O.base_asr_args(**over)
+    tts = OT.T5TransformerModelOracle(oargs).train()          # encoder, decoder, speech decoder pre / post-net
+    prenet = O.SpeechEncoderPrenet(oargs).train()
+    d = oargs.encoder_embed_dim
+    head = P.SpeechEncoderPostnet([23], encoder_embed_dim=d, final_dim=32).train()
+    quant = P.GumbelVectorQuantizer(dim=d, num_vars=10, groups=2, vq_dim=d).train()
+    args = make_args("t5_transformer_base_asr", build_speech_encoder=True, use_conv_pos=True, use_sinc_pos=True,
+                     use_codebook=True, latent_vars=10, latent_groups=2, codebook_prob=0.5, hubert_num_classes=[23],
+                     final_dim=32, **over)
+    model = T5TransformerModel.build_model(args).train()
+    sd = {k: v for k, v in tts.state_dict().items() if not k.startswith("text_encoder_prenet.")}
+    for k, v in prenet.state_dict().items():
+        k = {"pos_conv_g": "pos_conv.0.weight_g", "pos_conv_v": "pos_conv.0.weight_v", "pos_conv_bias": "pos_conv.0.bias"}.get(k, k)
+        sd["speech_encoder_prenet." + k] = v
+    sd.update({"hubert_layer." + k: v for k, v in head.state_dict().items()})
+    sd.update({"quantizer." + k: v for k, v in quant.state_dict().items()})
+    own = model.state_dict()
+    assert all(k in own for k in sd if not k.startswith("encoder.proj")), [k for k in sd if k not in own][:5]
+    model.load_state_dict(sd)
+    B, n = 2, 6000
+    wave = torch.randn(B, n) * 0.3
+    pad = torch.zeros(B, n, dtype=torch.bool)
+    pad[1, 5200:] = True
+    with torch.no_grad():
+        x_ref, enc_pad, fpen_ref = prenet(wave, pad, None, None)
+    T = x_ref.shape[1]
+    labels = [torch.randint(0, 23, (B, T + 3))]                 # longer than the frames: no trimming, ratio 1
+    mask_idx = torch.zeros(B, T, dtype=torch.bool)
+    mask_idx[0, 2:7] = True
+    mask_idx[1, 4:9] = True
+    prev = torch.randn(B, 9, 80)
+    tgt_lengths = torch.tensor([9, 7])
+    spk = torch.randn(B, 512)
+    noise = -torch.empty(B * T * 2, 10).exponential_().log()
+    perm = torch.randperm(T)
+    with torch.no_grad():
+        x_ref, enc_pad, fpen_ref = prenet(wave, pad, mask_idx, None)
+        enc = tts.encoder(x_ref, enc_pad)
+        enc_btc = enc["encoder_out"][0].transpose(0, 1)
+        hub_ref = head(enc_btc, enc_pad, mask_idx, [labels[0][:, :T]])
+        q = quant(enc_btc, noise)
+        mixed = P.mix_codes(enc_btc, q["x"], 0.5, perm)
+        enc["encoder_out"] = [mixed.transpose(0, 1)]
+        dec_in, tgt_mask = tts.speech_decoder_prenet(prev, tgt_lengths, spk)
+        dec_out, extra = tts.decoder(dec_in, tgt_mask, enc, alignment_layer=None)
+        before_ref, after_ref, logits_ref = tts.speech_decoder_postnet(dec_out)
+        model._gumbel_noise, model._codebook_perm = noise, perm
+        hub, (before, after, logits, attn) = model(source=wave, padding_mask=pad, prev_output_tokens=prev,
+                                                   tgt_lengths=tgt_lengths, spkembs=spk, target_list=labels,
+                                                   task_name="speech_pretrain", mask_indices=mask_idx)
+
+    def close(a, b, tol=3e-4):
+        a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+        fin = torch.isfinite(b)
+        if not torch.equal(torch.isfinite(a), fin):  # (-inf marks a negative that equals the positive, :68-70)
+            return False
+        return ((a[fin] - b[fin]).norm() / b[fin].norm().clamp_min(1e-12)).item() < tol
+    assert close(hub["features_pen"], fpen_ref)
+    assert close(hub["logit_m_list"][0], hub_ref["logit_m_list"][0]) and close(hub["logit_u_list"][0], hub_ref["logit_u_list"][0])
+    assert close(hub["prob_perplexity"], q["prob_perplexity"]) and hub["num_vars"] == q["num_vars"]
+    assert close(after, after_ref) and close(before, before_ref) and close(logits, logits_ref)
+    # only_hubert returns the head alone (:884-885); feature_only the encoder states (:832-833)
+    with torch.no_grad():
+        only, none = model(source=wave, padding_mask=pad, target_list=labels, task_name="speech_pretrain",
+                           only_hubert=True, mask_indices=mask_idx)
+    assert none is None and close(only["logit_m_list"][0], hub_ref["logit_m_list"][0])
+    RT.invalidate_shadows()

@@ -236,3 +236,89 @@ def test_kv_cache_synthesis_equals_prefix_recomputation(cuda):
     for a, b in zip(plain, cached):
         assert a.shape == b.shape and rel(b, a) < 1e-4
     RT.dtype = torch.bfloat16
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 6e-2)])
+def test_speech_pretraining_branch_of_forward(cuda, dtype, tol):
+    """models/speecht5.py:813-961 with target_list on the device: prenet with label alignment + feature penalty ->
+    encoder -> masked-prediction head (speech_encoder_postnet.py:76-124), Gumbel quantizer + code mixing (:858-882),
+    speech decoder on the mixed states; against the same composition of the CPU oracles with the same Gumbel noise and
+    time permutation."""
+    from oracle import pretrain_oracle as P
+    from oracle import speecht5_oracle as OT
+    from oracle import speecht5_oracle_asr as O
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = dtype
+    RT.manual_seed(1)
+    RT.disable_device_seed()
+    RT.clear_static()
+    RT.invalidate_shadows()
+    torch.manual_seed(11)
+    over = dict(encoder_layers=2, decoder_layers=2, bert_init=True, mask_prob=0.0, mask_channel_prob=0.0, dropout=0.0,
+                attention_dropout=0.0, activation_dropout=0.0, dprenet_dropout_rate=0.0, postnet_dropout_rate=0.0,
+                transformer_enc_positional_dropout_rate=0.0, transformer_dec_positional_dropout_rate=0.0,
+                encoder_layerdrop=0.0, decoder_layerdrop=0.0, feature_grad_mult=1.0)
+    oargs = O.base_asr_args(**over)
+    tts = OT.T5TransformerModelOracle(oargs).train()
+    prenet = O.SpeechEncoderPrenet(oargs).train()
+    d = oargs.encoder_embed_dim
+    head = P.SpeechEncoderPostnet([23], encoder_embed_dim=d, final_dim=32).train()
+    quant = P.GumbelVectorQuantizer(dim=d, num_vars=10, groups=2, vq_dim=d).train()
+    args = make_args("t5_transformer_base_asr", build_speech_encoder=True, use_conv_pos=True, use_sinc_pos=True,
+                     use_codebook=True, latent_vars=10, latent_groups=2, codebook_prob=0.5, hubert_num_classes=[23],
+                     final_dim=32, **over)
+    model = T5TransformerModel.build_model(args).to(cuda).train()
+    sd = {k: v for k, v in tts.state_dict().items() if not k.startswith("text_encoder_prenet.")}
+    for k, v in prenet.state_dict().items():
+        k = {"pos_conv_g": "pos_conv.0.weight_g", "pos_conv_v": "pos_conv.0.weight_v", "pos_conv_bias": "pos_conv.0.bias"}.get(k, k)
+        sd["speech_encoder_prenet." + k] = v
+    sd.update({"hubert_layer." + k: v for k, v in head.state_dict().items()})
+    sd.update({"quantizer." + k: v for k, v in quant.state_dict().items()})
+    model.load_state_dict(sd)
+    B, n = 2, 8000
+    wave = torch.randn(B, n) * 0.3
+    pad = torch.zeros(B, n, dtype=torch.bool)
+    pad[1, 7000:] = True
+    with torch.no_grad():
+        T = prenet(wave, pad, None, None)[0].shape[1]
+    labels = [torch.randint(0, 23, (B, T + 3))]
+    mask_idx = torch.zeros(B, T, dtype=torch.bool)
+    mask_idx[0, 2:9] = True
+    mask_idx[1, 4:11] = True
+    prev, tgt_lengths, spk = torch.randn(B, 9, 80), torch.tensor([9, 7]), torch.randn(B, 512)
+    noise = -torch.empty(B * T * 2, 10).exponential_().log()
+    perm = torch.randperm(T)
+    with torch.no_grad():
+        x_ref, enc_pad, fpen_ref = prenet(wave, pad, mask_idx, None)
+        enc = tts.encoder(x_ref, enc_pad)
+        enc_btc = enc["encoder_out"][0].transpose(0, 1)
+        hub_ref = head(enc_btc, enc_pad, mask_idx, [labels[0][:, :T]])
+        q = quant(enc_btc, noise)
+        enc["encoder_out"] = [P.mix_codes(enc_btc, q["x"], 0.5, perm).transpose(0, 1)]
+        dec_in, tgt_mask = tts.speech_decoder_prenet(prev, tgt_lengths, spk)
+        dec_out, _ = tts.decoder(dec_in, tgt_mask, enc, alignment_layer=None)
+        before_ref, after_ref, logits_ref = tts.speech_decoder_postnet(dec_out)
+    model._gumbel_noise, model._codebook_perm = noise.to(cuda), perm.to(cuda)
+    hub, (before, after, logits, attn) = model(
+        source=wave.to(cuda), padding_mask=pad.to(cuda), prev_output_tokens=prev.to(cuda),
+        tgt_lengths=tgt_lengths.to(cuda), spkembs=spk.to(cuda), target_list=[labels[0].to(cuda)],
+        task_name="speech_pretrain", mask_indices=mask_idx.to(cuda))
+
+    def close(a, b, t):
+        a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).double()
+        fin = torch.isfinite(b)
+        return torch.equal(torch.isfinite(a), fin) and ((a[fin] - b[fin]).norm() / b[fin].norm().clamp_min(1e-12)).item() < t
+    assert close(hub["features_pen"], fpen_ref, tol)
+    assert close(hub["logit_m_list"][0], hub_ref["logit_m_list"][0], 4 * tol)
+    assert close(hub["logit_u_list"][0], hub_ref["logit_u_list"][0], 4 * tol)
+    assert close(hub["prob_perplexity"], q["prob_perplexity"], tol) and hub["num_vars"] == q["num_vars"]
+    if dtype == torch.float32:  # bf16: a flipped arg-max of the Gumbel draw swaps a whole code vector; fp32 only
+        assert close(after, after_ref, tol) and close(before, before_ref, tol) and close(logits, logits_ref, 3 * tol)
+    # the whole branch is differentiable end to end: reconstruction + head losses reach the waveform filters
+    loss = after.float().square().mean() + sum(x.float().logsumexp(-1).mean() for x in hub["logit_m_list"]) + hub["features_pen"]
+    loss.backward()
+    g = model.speech_encoder_prenet.feature_extractor.conv_layers[0][0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    assert torch.isfinite(model.quantizer.vars.grad).all() and torch.isfinite(model.hubert_layer.label_embs_concat.grad).all()
+    RT.dtype = torch.bfloat16

@@ -44,7 +44,7 @@ def timed(fn, reps=10):
 rows = []
 tot_ours = tot_lib = 0.0
 for (M, N, Kd, nb, a_mn, b_mn, f32), n in sorted(cnt.items(), key=lambda kv: -kv[1] * kv[0][0] * kv[0][1] * kv[0][2] * kv[0][3]):
-    if nb != 1 or M * N * Kd < 1e8:
+    if nb != 1 or M * N * Kd < 1e8 or N % 8:
         continue
     A = torch.randn((Kd, M) if a_mn else (M, Kd), device=dev).to(torch.bfloat16)
     B = torch.randn((Kd, N) if b_mn else (N, Kd), device=dev).to(torch.bfloat16)

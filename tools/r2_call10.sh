@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, call 10: suite (split-K tolerance, pre-training branch), A/B of the GEMM epilogue prefetch
+set -u
+OUT=gpurun_out/r2_call10
+mkdir -p $OUT
+run() { local name=$1 t=$2; shift 2; ( timeout $t "$@" ) > $OUT/$name.log 2>&1; echo "rc=$?" >> $OUT/$name.log; }
+run pytest_gpu 900 python -m pytest tests -m gpu -q -rs
+run bench_tts 600 python bench.py --steps 20 --warmup 5 --no-parity --no-cpu-baseline
+ST5_LIB=$PWD/speecht5_b200/lib/variant_noprefetch.so run bench_tts_noprefetch 600 python bench.py --steps 20 --warmup 5 --no-parity --no-cpu-baseline
+run bench_tts2 600 python bench.py --steps 20 --warmup 5 --no-parity --no-cpu-baseline
+ST5_LIB=$PWD/speecht5_b200/lib/variant_noprefetch.so run bench_tts_noprefetch2 600 python bench.py --steps 20 --warmup 5 --no-parity --no-cpu-baseline
+run bench_asr 600 python bench.py --workload asr --steps 10 --warmup 3 --no-cpu-baseline
+tail -8 $OUT/pytest_gpu.log
+for f in bench_tts bench_tts_noprefetch bench_tts2 bench_tts_noprefetch2 bench_asr; do grep '"metric"' $OUT/$f.log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print('$f', d['value'], d['unit'], d['ms_per_step'], 'e2e', d.get('e2e', {}).get('value'), 'roof', d.get('roofline', {}).get('frac'), d['roofline'].get('gemm_ms_per_step'), d.get('gpu_launches_per_step'))
+"; tail -2 $OUT/$f.log | cut -c1-200; done
