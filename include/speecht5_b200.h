@@ -190,7 +190,8 @@ int st5_attn_fused_bwd(const st5_attn_args* args, const void* psave, const float
  *   softmax_fwd: P = softmax(S + QP[i][clamp(i-j)+maxpos] + masks); writes P (bf16), optionally fp32 probabilities
  *                (may alias s) and dropout(P) (bf16). s already holds scale*q.k, qp (optional) scale*q.pe_k^T [rows][2*maxpos].
  *   ds:          dS = P * (dropout_bwd(dP) + dP_ext - rowsum(P * (...))) (bf16); optionally re-emits dropout(P).
- *   dqp_scatter: dQP[row][r] = sum over keys j with clamp(i-j)+maxpos == r of dS[row][j]  (gradient wrt QP). */
+ *   dqp_scatter: dQP[row][r] = sum over keys j with clamp(i-j)+maxpos == r of dS[row][j]  (gradient wrt QP); output rows
+ *                in the order of dS ((b, h, i)), or with h_major != 0 as (h, b, i). */
 int st5_attn_softmax_fwd(const float* s, const float* qp, int64_t qp_ld, const uint8_t* key_pad, void* p_bf16,
                          float* probs_f32, void* pdrop_bf16, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int64_t p_ld,
                          int32_t causal, int32_t maxpos, float drop_p, uint64_t seed, uint64_t offset, void* stream);
@@ -198,7 +199,7 @@ int st5_attn_ds(const void* p_bf16, const float* dp, const float* dp_ext, void* 
                 int32_t H, int32_t Tq, int32_t Tk, int64_t p_ld, float drop_p, uint64_t seed, uint64_t offset,
                 void* stream);
 int st5_attn_dqp_scatter(const void* ds_bf16, void* dqp_bf16, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
-                         int64_t p_ld, int32_t maxpos, void* stream);
+                         int64_t p_ld, int32_t maxpos, int32_t h_major, void* stream);
 
 /* ------------------------------------------------------------------------------------------------- BatchNorm1d
  * espnet Tacotron2 Postnet block (speech_decoder_postnet.py:39-51): y = dropout(tanh?(BN(x))) on channels-last

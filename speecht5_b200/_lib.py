@@ -70,7 +70,7 @@ _PROTOS = {
     "st5_attn_softmax_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _f,
                                        _u64, _u64, _vp]),
     "st5_attn_ds": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _f, _u64, _u64, _vp]),
-    "st5_attn_dqp_scatter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _vp]),
+    "st5_attn_dqp_scatter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _vp]),
     "st5_bn_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _i32, _f, _f,
                              _i32, _f, _u64, _u64, _vp, _vp]),
     "st5_bn_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64, _i64, _i32,

@@ -126,14 +126,21 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 // dQP[row][r] = sum_{j : idx(i,j) = r} dS[row][j]  (one warp per row; interior offsets map 1:1, the two clamped ends sum)
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     attn_dqp_scatter_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dQP, int64_t nrows, int Tq,
-                            int Tk, int64_t p_ld, int maxpos) {
+                            int Tk, int64_t p_ld, int maxpos, int B, int H, int h_major) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= nrows) return;
   const int i = (int)(row % Tq);
   const int R = 2 * maxpos;
   const __nv_bfloat16* dsrow = dS + row * p_ld;
-  __nv_bfloat16* orow = dQP + row * R;
+  // output row: (b, h, i) like dS, or head-major (h, b, i) -- then one head's rows are equidistant in memory and the
+  // two table contractions run as 12 long GEMMs instead of B x H short ones
+  int64_t orow_idx = row;
+  if (h_major) {
+    const int h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
+    orow_idx = ((int64_t)h * B + b) * Tq + i;
+  }
+  __nv_bfloat16* orow = dQP + orow_idx * R;
   // clamped ends
   float lo = 0.f, hi = 0.f;
   for (int j = i + maxpos + lane; j < Tk; j += 32) lo += __bfloat162float(dsrow[j]);       // i-j <= -maxpos
@@ -189,11 +196,11 @@ int st5_attn_ds(const void* p_bf16, const float* dp, const float* dp_ext, void* 
 }
 
 int st5_attn_dqp_scatter(const void* ds_bf16, void* dqp_bf16, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
-                         int64_t p_ld, int32_t maxpos, void* stream) {
+                         int64_t p_ld, int32_t maxpos, int32_t h_major, void* stream) {
   const int64_t nrows = (int64_t)B * H * Tq;
   if (nrows == 0) return 0;
   attn_dqp_scatter_kernel<<<(unsigned)((nrows + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)ds_bf16, (__nv_bfloat16*)dqp_bf16, nrows, Tq, Tk, p_ld, maxpos);
+      (const __nv_bfloat16*)ds_bf16, (__nv_bfloat16*)dqp_bf16, nrows, Tq, Tk, p_ld, maxpos, B, H, h_major);
   return set_error((int)cudaGetLastError(), "st5_attn_dqp_scatter");
 }
 

@@ -265,30 +265,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
     const bool row_ok = row < p.M;
     const long zoff = (long)b1 * p.c_bs1 + (long)b2 * p.c_bs2;
     const long roff = zoff + (long)row * p.c_ld;
-    // This row's 64 bytes of the backward gate / residual are requested BEFORE the wait on the accumulator (first chunk)
-    // or while the previous chunk is being stored (later chunks): their latency used to sit, fully exposed, between the
-    // TMEM read and the math (ncu: 25-45 % of the dH / fc2 / out_proj samples).
-    const __nv_bfloat16* pf_src = nullptr;  // bf16 [rows][c_ld] operand with the output's layout, 16-byte vectors
-#ifndef ST5_NO_EPI_PREFETCH  // (A/B build switch: tools/build_variant.sh)
-    if (!p.c_fp32 && ((p.c_ld & 7) == 0) && ((zoff & 7) == 0)) {
-      const void* cand = p.ag_pre != nullptr ? p.ag_pre : p.residual;
-      if (cand != nullptr && (reinterpret_cast<uintptr_t>(cand) & 15) == 0)
-        pf_src = reinterpret_cast<const __nv_bfloat16*>(cand);
-    }
-#endif
-    const bool pf_is_gate = pf_src != nullptr && p.ag_pre != nullptr;
-    uint4 pf[4];
-    auto prefetch = [&](int c) {
-      const int nb = n0 + c * 32;
-      if (pf_src != nullptr) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          pf[g] = make_uint4(0u, 0u, 0u, 0u);
-          if (row_ok && nb + 8 * g + 8 <= p.N) pf[g] = *reinterpret_cast<const uint4*>(pf_src + roff + nb + 8 * g);
-        }
-      }
-    };
-    if (grp < BN / 32) prefetch(grp);
+    // (Requesting the gate / residual / bias of a chunk ahead of the accumulator wait was tried -- A/B build, round 2:
+    // the 16-24 extra live registers cost more in spills than the hidden latency gave back, +0.3 ms per step.)
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     const float* bias2_row = (p.bias2 != nullptr && row_ok) ? p.bias2 + (long)(row / p.bias2_rows) * p.N : nullptr;
@@ -484,7 +462,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           tma_store_4d(&map_cpre, stg + 2048, nb, m0 + q * 32, b1, b2);
           bulk_commit();
         }
-        if (c + NGRP < BN / 32) prefetch(c + NGRP);
         continue;
       }
       if (p.C_pre != nullptr) emit(p.C_pre, &map_cpre);
@@ -514,7 +491,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           if (vec_ok && ((reinterpret_cast<uintptr_t>(p.ag_pre) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 u = pf_is_gate ? pf[j >> 3] : *reinterpret_cast<const uint4*>(pr + j);
+              const uint4 u = *reinterpret_cast<const uint4*>(pr + j);
               if (p.ag_act == ACT_GATE) actgrad8<ACT_GATE>(v + j, u);
               else if (p.ag_act == ACT_GELU_TANH) actgrad8<ACT_GELU_TANH>(v + j, u);
               else if (p.ag_act == ACT_GELU) actgrad8<ACT_GELU>(v + j, u);
@@ -540,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           if (vec_ok && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 u = (pf_src != nullptr && !pf_is_gate) ? pf[j >> 3] : *reinterpret_cast<const uint4*>(rs + j);
+              const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -556,7 +533,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05(const __gri
           }
         }
       }
-      if (c + NGRP < BN / 32) prefetch(c + NGRP);  // (everything of this chunk has been consumed above)
       emit(p.C, &map_c);
     }
     }

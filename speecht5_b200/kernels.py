@@ -226,9 +226,9 @@ def attn_ds(p, dp, dp_ext, ds, pdrop, B, H, Tq, Tk, p_ld, drop_p, seed, offset):
     _count(1)
 
 
-def attn_dqp_scatter(ds, dqp, B, H, Tq, Tk, p_ld, maxpos):
+def attn_dqp_scatter(ds, dqp, B, H, Tq, Tk, p_ld, maxpos, h_major=False):
     lib = _lib.load()
-    _lib.check(lib.st5_attn_dqp_scatter(_ptr(ds), _ptr(dqp), B, H, Tq, Tk, p_ld, maxpos, _stream()),
+    _lib.check(lib.st5_attn_dqp_scatter(_ptr(ds), _ptr(dqp), B, H, Tq, Tk, p_ld, maxpos, int(h_major), _stream()),
                "st5_attn_dqp_scatter")
     _count(1)
 

@@ -705,6 +705,24 @@ class AttentionTCFn(torch.autograd.Function):
                         ds=dS, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
         K.attn_fused_bwd(a, psave, inv_l, o32, delta, dq_acc)
         R = pe_k.shape[0]
+        rows = B * Tq
+        if q_bs == Tq * q_ld and RT.wgrad_splitk:
+            # head-major dQP: one head's rows (b, i) are equidistant in dQP and in the fused q|k|v buffer, so the two
+            # table contractions are 12 long GEMMs (M or K = B*T) instead of B x H short ones whose second 128-row tile
+            # is three quarters empty at T = 160
+            dQP = torch.empty((H, B, Tq, R), dtype=torch.bfloat16, device=dev)
+            K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos, h_major=True)
+            # dQ += scale dQP PE
+            K.gemm(dQP, pe_hi, dqv, M=rows, N=64, K=R, a_ld=R, b_mn=True, b_ld=64, c_ld=q_ld, nb1=H, nb2=1,
+                   a_bs=(rows * R, 0), b_bs=(0, 0), c_bs=(64, 0), alpha=scale, residual=dqv)
+            # dPE[r,c] = scale sum_{h} sum_{b,i} dQP[h,b,i,r] q[b,i,h,c]: heads and contraction splits all add into one
+            # [R, 64] output at the L2
+            S = next((c for c in (8, 6, 5, 4, 3, 2) if rows % c == 0 and rows // c >= 512), 1)
+            chunk = rows // S
+            dpe = torch.zeros((R, 64), dtype=torch.float32, device=dev)
+            K.gemm(dQP, qv, dpe, M=R, N=64, K=chunk, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=S,
+                   a_bs=(rows * R, chunk * R), b_bs=(64, chunk * q_ld), c_bs=(0, 0), alpha=scale, accumulate=2)
+            return dq_buf, None, dpe, None, None
         dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
         K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos)
         qpbs = (Tq * R, H * Tq * R)
@@ -881,6 +899,16 @@ def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, max
 
 
 # =================================================================================================== postnet blocks
+def _conv_wgrad_split(Cout, Ncols, Kd):
+    """Split of the post-net weight-gradient contraction (K = all frames of the batch, ~20 k) over the GEMM's batch
+    dimension: (S, chunk) with S * chunk >= Kd, chunk a multiple of 8 rows. The output has a handful of tiles only, so
+    without the split 5 - 20 CTAs do all the work (83 us per conv; the library needs 19)."""
+    tiles = ((Cout + 255) // 256 if Cout >= 256 else (Cout + 127) // 128) * ((Ncols + 255) // 256)
+    S = max(1, min(32, 148 // max(1, tiles) if Cout < 256 else 74 // max(1, tiles), Kd // 512))
+    chunk = ((Kd + S - 1) // S + 7) // 8 * 8
+    return S, chunk
+
+
 class Conv1dK5Fn(torch.autograd.Function):
     """Conv1d(kernel 5, padding 2, no bias) on channels-last activations [B,T,Cin] as ONE GEMM over an
     overlapping-window view of the zero-padded buffer (no im2col): out[b,t,:] = W2 . xpad[b, t:t+5, :].ravel().
@@ -892,12 +920,16 @@ class Conv1dK5Fn(torch.autograd.Function):
         Cout, _, Kw = weight.shape
         pad = (Kw - 1) // 2
         Tp = T + 2 * pad
-        xp = torch.zeros((B, Tp, Cin), dtype=x.dtype, device=x.device)
+        # (zero rows past the batch: the split weight-gradient GEMM of the backward reads whole chunks)
+        S, chunk = _conv_wgrad_split(Cout, Kw * Cin, B * Tp - 2 * pad)
+        rows = max(B * Tp, S * chunk + 2 * pad)
+        xflat = torch.zeros((rows, Cin), dtype=x.dtype, device=x.device)
+        xp = xflat[:B * Tp].view(B, Tp, Cin)
         xp[:, pad:pad + T] = x
         w_sh = RT.shadow(("conv_f", id(weight)), lambda: weight.detach().permute(0, 2, 1).reshape(Cout, Kw * Cin))
         ldc = _pad8(Cout)
         out = torch.empty((B, T, ldc), dtype=x.dtype, device=x.device)
-        xa = _split(xp.view(B * Tp, Cin))
+        xa = _split(xflat)
         # window GEMM: rows t (per batch b), K = Kw*Cin contiguous starting at xpad[b, t]; ld = Cin
         _conv_mm(xa, w_sh, out, B=B, T=T, Tp=Tp, Cin=Cin, Cout=Cout, Kw=Kw, ldc=ldc)
         ctx.save_for_backward(weight)
@@ -910,9 +942,13 @@ class Conv1dK5Fn(torch.autograd.Function):
         (weight,) = ctx.saved_tensors
         B, T, Tp, Cin, Cout, Kw, pad = ctx.meta
         dev = dy.device
-        dyp = torch.zeros((B, Tp, Cout), dtype=dy.dtype, device=dev)
+        Kd = B * Tp - 2 * pad
+        S, chunk = _conv_wgrad_split(Cout, Kw * Cin, Kd)
+        rows = max(B * Tp, S * chunk + 2 * pad)
+        dflat = torch.zeros((rows, Cout), dtype=dy.dtype, device=dev)
+        dyp = dflat[:B * Tp].view(B, Tp, Cout)
         dyp[:, pad:pad + T] = dy
-        ga = _split(dyp.view(B * Tp, Cout))
+        ga = _split(dflat)
         # dx[b,t,ci] = sum_{u,co} dypad[b,t+u,co] * W[co,ci,Kw-1-u]
         w_b = RT.shadow(("conv_b", id(weight)),
                         lambda: weight.detach().flip(2).permute(1, 2, 0).reshape(Cin, Kw * Cout))
@@ -920,10 +956,16 @@ class Conv1dK5Fn(torch.autograd.Function):
         dx = torch.empty((B, T, ldx), dtype=dy.dtype, device=dev)
         _conv_mm(ga, w_b, dx, B=B, T=T, Tp=Tp, Cin=Cout, Cout=Cin, Kw=Kw, ldc=ldx)
         # dW2[co, u*Cin+ci] = sum_rho dypad_flat[rho+pad, co] * xpad_flat[rho+u, ci]  (both MN-major, K = B*Tp - 2*pad)
-        Kd = B * Tp - 2 * pad
-        dW2 = torch.empty((Cout, Kw * Cin), dtype=torch.float32, device=dev)
         a_ops = tuple(None if t is None else t[pad:] for t in ga)
-        mm(a_ops, ctx.xa, dW2, M=Cout, N=Kw * Cin, Kd=Kd, a_mn=True, a_ld=Cout, b_mn=True, b_ld=Cin, c_ld=Kw * Cin)
+        if ga[1] is None and ctx.xa[1] is None and RT.wgrad_splitk and S > 1 and Cout % 8 == 0 and Cin % 8 == 0:
+            # contraction split over the batch dimension, partial products added at the L2 (st5_gemm_bf16 accumulate 2);
+            # rows past Kd are the zero tails of both buffers
+            dW2 = torch.zeros((Cout, Kw * Cin), dtype=torch.float32, device=dev)
+            K.gemm(a_ops[0], ctx.xa[0], dW2, M=Cout, N=Kw * Cin, K=chunk, a_mn=True, a_ld=Cout, b_mn=True, b_ld=Cin,
+                   c_ld=Kw * Cin, nb1=S, nb2=1, a_bs=(chunk * Cout, 0), b_bs=(chunk * Cin, 0), c_bs=(0, 0), accumulate=2)
+        else:
+            dW2 = torch.empty((Cout, Kw * Cin), dtype=torch.float32, device=dev)
+            mm(a_ops, ctx.xa, dW2, M=Cout, N=Kw * Cin, Kd=Kd, a_mn=True, a_ld=Cout, b_mn=True, b_ld=Cin, c_ld=Kw * Cin)
         dW = dW2.view(Cout, Kw, Cin).permute(0, 2, 1).contiguous()
         ctx.xa = None
         return (dx if ldx == Cin else dx[..., :Cin]), dW

@@ -41,8 +41,15 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_
         assert (t.storage_offset() * 2) % 16 == 0 and (ld * 2) % 16 == 0 and (bs * 2) % 16 == 0, "TMA alignment"
     A = _view(a, nb1, M, K, a_mn, a_ld, a_bs[0]).double()
     B = _view(b, nb1, N, K, b_mn, b_ld, b_bs[0]).double()
-    C = torch.as_strided(out, (nb1, M, N), (c_bs[0], c_ld, 1), out.storage_offset())
     v = alpha * torch.bmm(A, B.transpose(1, 2))
+    if int(accumulate) == 2:  # L2-side accumulate: batch entries may share one output (c_bs = 0), split-K
+        assert out.dtype == torch.float32 and (c_ld * 4) % 16 == 0 and bias is None and c_pre is None and act in (None, "none")
+        if nb1 > 1 and c_bs[0] == 0:
+            C1 = torch.as_strided(out, (M, N), (c_ld, 1), out.storage_offset())
+            C1.copy_((C1.double() + v.sum(0)).to(out.dtype))
+            return out
+    assert not (nb1 > 1 and c_bs[0] == 0), "several batch entries into one output need accumulate = 2"
+    C = torch.as_strided(out, (nb1, M, N), (c_bs[0], c_ld, 1), out.storage_offset())
     if accumulate:
         v = v + C.double()
     if bias is not None:
