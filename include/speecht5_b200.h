@@ -178,11 +178,13 @@ int st5_attn_flash_fwd(const st5_attn_args* args, float* lse, void* psave, float
  * Philox), so every step needs one score-sized MMA (dP = dO V^T) and the kernel double buffers dP, the dropout(P)/dS
  * operand tiles, dQ and the Q/dO tiles. Reads q/k/v, out (forward result), dout and drop_p; optional dprobs_ext (then
  * args->probs must be the FP32 probabilities the forward returned); writes dq/dk/dv (same layouts as q/k/v).
- * out_f32 (optional): what the forward wrote there. Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
+ * ext_heads > 0: dprobs_ext is known to be zero for heads >= ext_heads (the guided-attention loss reads the first two
+ * heads of every layer, text_to_speech_loss.py:210-212) -- those heads skip its loads. out_f32 (optional): what the
+ * forward wrote there. Scratch: delta [B*H*Tq] floats, dq_acc [B*Tq*H*64] floats.
  * Relative positions (pe_k != NULL): args->ds additionally receives dS as BF16 [B,H,Tq,p_ld] for st5_attn_dqp_scatter
  * and the two table GEMMs; dq then holds only the q.k part of the gradient. */
 int st5_attn_fused_bwd(const st5_attn_args* args, const void* psave, const float* inv_l, const float* out_f32,
-                       float* delta, float* dq_acc, void* stream);
+                       float* delta, float* dq_acc, int32_t ext_heads, void* stream);
 
 /* Tensor-core (bf16) attention path: the contractions run on st5_gemm_bf16 (batched over heads and utterances, q/k/v
  * read in place from the fused projection buffers); these three row kernels are the non-GEMM steps between them.

@@ -43,6 +43,7 @@ struct FusedBwdParams {
   const __nv_bfloat16* psave;  // [B][H][Tq][p_ld] from the forward pass: exp(s - rowmax), sign bit = dropped element
   __nv_bfloat16* ds_out;          // optional [B][H][Tq][p_ld]: dS for the relative-position contractions
   float drop_scale;
+  int ext_heads;  // dp_ext is non-zero only for heads < ext_heads
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -56,7 +57,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                   const float* __restrict__ O32, long o_ld, long o_bs, const float* __restrict__ probs,
                                   const float* __restrict__ dpx, long p_ld, float* __restrict__ delta, int B, int H,
-                                  int Tq, int Tk) {
+                                  int Tq, int Tk, int ext_heads) {
   const int lane = threadIdx.x & 31;
   const int64_t nrows = (int64_t)B * H * Tq;
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,6 +94,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   const int64_t row = gw;
   if (row >= nrows) return;
   const int i = (int)(row % Tq), h = (int)((row / Tq) % H), b = (int)(row / ((int64_t)Tq * H));
+  const bool ext = h < ext_heads;  // the caller's gradient on the probabilities is zero for the other heads (contract)
   const int64_t off = (int64_t)b * o_bs + (int64_t)i * o_ld + h * 64 + lane * 2;
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
   float2 o;
@@ -101,7 +103,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   float acc = a.x * o.x + a.y * o.y;
   const float* pr = probs + row * p_ld;
   const float* dx = dpx + row * p_ld;
-  for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
+  if (ext)
+    for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
   acc = warp_sum(acc);
   if (lane == 0) delta[row] = acc;
 }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
           }
         }
         if (pend_kb >= 0) prefetch_acc(pend_kb, pend_qt);  // for the read-out that follows this step's element phase
-        const float* dpx = (p.dp_ext != nullptr && row_ok) ? p.dp_ext + prow * p.p_ld : nullptr;
+        const float* dpx = (p.dp_ext != nullptr && row_ok && h < p.ext_heads) ? p.dp_ext + prow * p.p_ld : nullptr;
         const int c = grp;  // this warp's 32-key chunk of the block
         const int col0 = k0 + c * 32;
         mbar_wait(&bar_dp[buf], (uint32_t)((it >> 1) & 1));
@@ -462,7 +465,7 @@ static int make_map128(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ld
 using namespace st5;
 
 extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, const float* inv_l, const float* out_f32,
-                                  float* delta, float* dq_acc, void* stream) {
+                                  float* delta, float* dq_acc, int32_t ext_heads, void* stream) {
   const bool rpe = a->pe_k != nullptr;
   if (a->dtype != ST5_BF16 || a->Tk <= 0 || a->Tq <= 0) return set_error(-2, "st5_attn_fused_bwd: needs bf16");
   if (psave == nullptr || inv_l == nullptr || (a->p_ld & 7) || a->p_ld < a->Tk || (reinterpret_cast<uintptr_t>(psave) & 15))
@@ -483,7 +486,8 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
   const int64_t warps_needed = ext ? nrows : (nrows + 3) / 4;
   attn_delta_kernel<<<(unsigned)((warps_needed + 7) / 8), 256, 0, s>>>(
       (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs,
-      a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk);
+      a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk,
+      ext_heads > 0 ? ext_heads : a->H);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
   CUtensorMap mq, mk, mv, mdo, mp;
@@ -516,6 +520,7 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
   p.psave = reinterpret_cast<const __nv_bfloat16*>(psave);
   p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.ext_heads = ext_heads > 0 ? ext_heads : a->H;
   attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, mp, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_bwd");
 }

@@ -202,10 +202,10 @@ def attn_flash_fwd(a, lse, psave=None, inv_l=None, out_f32=None):
     _count(1)
 
 
-def attn_fused_bwd(a, psave, inv_l, out_f32, delta, dq_acc):
+def attn_fused_bwd(a, psave, inv_l, out_f32, delta, dq_acc, ext_heads=0):
     lib = _lib.load()
     _lib.check(lib.st5_attn_fused_bwd(C.byref(a), _ptr(psave), _ptr(inv_l), _ptr(out_f32), _ptr(delta), _ptr(dq_acc),
-                                      _stream()),
+                                      int(ext_heads), _stream()),
                "st5_attn_fused_bwd")
     _count(2)
 

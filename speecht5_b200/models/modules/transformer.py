@@ -25,6 +25,12 @@ def _act_dtype(x):
     return x if x.dtype == RT.dtype else x.to(RT.dtype)
 
 
+def _fold_residual_grad(x):
+    """Post-LN blocks: hand the block input to the residual add through the first GEMM's alias output, so that the
+    residual branch's gradient is added in that GEMM's dx epilogue (only when a gradient will flow at all)."""
+    return torch.is_grad_enabled() and x.requires_grad and ops.RT.fold_residual_grad
+
+
 class MultiheadAttention(nn.Module):
     """Parameter holder with the reference's names (q/k/v/out_proj Linear); compute happens in the owning layer through
     ops.linear (fused q|k|v projection) + ops.attention."""
@@ -59,23 +65,35 @@ class MultiheadAttention(nn.Module):
         if self.out_proj.bias is not None:
             nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def self_attend(self, x, key_padding_mask=None, causal=False, pe_k=None, maxpos=0, training=True):
-        """x [B,T,C] -> attention output before out_proj, [B,T,C]."""
-        qkv = ops.linear(x, (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight),
-                         (self.q_proj.bias, self.k_proj.bias, self.v_proj.bias))
+    def self_attend(self, x, key_padding_mask=None, causal=False, pe_k=None, maxpos=0, training=True, passthrough=False):
+        """x [B,T,C] -> attention output before out_proj, [B,T,C]. passthrough: also return the alias of x the caller
+        must use for its residual add (ops.LinearFn: the residual branch's gradient is then added in the dx GEMM)."""
+        x_pt = None
+        if passthrough:
+            qkv, x_pt = ops.linear(x, (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight),
+                                   (self.q_proj.bias, self.k_proj.bias, self.v_proj.bias), passthrough=True)
+        else:
+            qkv = ops.linear(x, (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight),
+                             (self.q_proj.bias, self.k_proj.bias, self.v_proj.bias))
         out, _ = ops.attention(qkv, None, H=self.num_heads, d=self.embed_dim, q_col=0, k_col=1, v_col=2,
                                scale=self.scaling, pe_k=pe_k if self.has_relative_attention_bias else None,
                                maxpos=maxpos, key_pad=key_padding_mask, causal=causal,
                                drop_p=self.dropout_p if training else 0.0)
-        return out
+        return (out, x_pt) if passthrough else out
 
-    def cross_attend(self, x, enc, key_padding_mask=None, need_head_weights=False, training=True):
-        """x [B,Tq,C], enc [B,Tk,C] -> (attention output before out_proj, probs [B,H,Tq,Tk] fp32 or None)."""
-        q = ops.linear(x, self.q_proj.weight, self.q_proj.bias)
+    def cross_attend(self, x, enc, key_padding_mask=None, need_head_weights=False, training=True, passthrough=False):
+        """x [B,Tq,C], enc [B,Tk,C] -> (attention output before out_proj, probs [B,H,Tq,Tk] fp32 or None[, alias of x])."""
+        x_pt = None
+        if passthrough:
+            q, x_pt = ops.linear(x, self.q_proj.weight, self.q_proj.bias, passthrough=True)
+        else:
+            q = ops.linear(x, self.q_proj.weight, self.q_proj.bias)
         kv = ops.linear(enc, (self.k_proj.weight, self.v_proj.weight), (self.k_proj.bias, self.v_proj.bias))
         out, probs = ops.attention(q, kv, H=self.num_heads, d=self.embed_dim, q_col=0, k_col=0, v_col=1,
                                    scale=self.scaling, key_pad=key_padding_mask,
                                    drop_p=self.dropout_p if training else 0.0, return_probs=need_head_weights)
+        if passthrough:
+            return out, (probs if need_head_weights else None), x_pt
         return out, (probs if need_head_weights else None)
 
 
@@ -124,11 +142,16 @@ class TransformerSentenceEncoderLayer(nn.Module):
             h = ops.residual_layer_norm(x, None, self.final_layer_norm)
             x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
         else:  # :112-132
-            a = self.self_attn.self_attend(x, self_attn_padding_mask, pe_k=pos_bias, maxpos=maxpos, training=tr)
+            # (the block input reaches the residual add as the alias its first GEMM hands back: ops.LinearFn.forward)
+            pt = _fold_residual_grad(x)
+            a = self.self_attn.self_attend(x, self_attn_padding_mask, pe_k=pos_bias, maxpos=maxpos, training=tr, passthrough=pt)
+            a, r = a if pt else (a, x)
             o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
-            x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p, stream=True)
-            o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
-            x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p, stream=True)
+            x = ops.residual_layer_norm(o, r, self.self_attn_layer_norm, drop_p=p, stream=True)
+            pt = _fold_residual_grad(x)
+            o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt)
+            o, r = o if pt else (o, x)
+            x = ops.residual_layer_norm(o, r, self.final_layer_norm, drop_p=p, stream=True)
         return x, None
 
 
@@ -302,9 +325,11 @@ class TransformerDecoderLayer(nn.Module):
                 x = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, drop_p=p,
                                residual=residual)
             else:
-                a = self.self_attn.self_attend(x, self_attn_padding_mask, causal=causal, training=tr)
+                pt = _fold_residual_grad(x)
+                a = self.self_attn.self_attend(x, self_attn_padding_mask, causal=causal, training=tr, passthrough=pt)
+                a, r = a if pt else (a, x)
                 o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
-                x = ops.residual_layer_norm(o, x, self.self_attn_layer_norm, drop_p=p, stream=True)
+                x = ops.residual_layer_norm(o, r, self.self_attn_layer_norm, drop_p=p, stream=True)
         attn = None
         if self.encoder_attn is not None and encoder_out is not None:
             want = need_attn or (not self.training and self.need_attn)
@@ -315,9 +340,11 @@ class TransformerDecoderLayer(nn.Module):
                 x = ops.linear(a, self.encoder_attn.out_proj.weight, self.encoder_attn.out_proj.bias, drop_p=p,
                                residual=residual)
             else:
-                a, attn = self.encoder_attn.cross_attend(x, encoder_out, encoder_padding_mask, want, tr)
+                pt = _fold_residual_grad(x)
+                res = self.encoder_attn.cross_attend(x, encoder_out, encoder_padding_mask, want, tr, passthrough=pt)
+                a, attn, r = res if pt else (res[0], res[1], x)
                 o = ops.linear(a, self.encoder_attn.out_proj.weight, self.encoder_attn.out_proj.bias)
-                x = ops.residual_layer_norm(o, x, self.encoder_attn_layer_norm, drop_p=p, stream=True)
+                x = ops.residual_layer_norm(o, r, self.encoder_attn_layer_norm, drop_p=p, stream=True)
             if attn is not None and not need_head_weights:
                 attn = attn.mean(dim=1)
         with torch.no_grad() if not ft else contextlib.ExitStack():
@@ -326,8 +353,10 @@ class TransformerDecoderLayer(nn.Module):
                 h = ops.residual_layer_norm(x, None, self.final_layer_norm)
                 x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
             else:
-                o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa)
-                x = ops.residual_layer_norm(o, x, self.final_layer_norm, drop_p=p, stream=True)
+                pt = _fold_residual_grad(x)
+                o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt)
+                o, r = o if pt else (o, x)
+                x = ops.residual_layer_norm(o, r, self.final_layer_norm, drop_p=p, stream=True)
         return x, attn, None
 
     def set_num_updates(self, num_updates):

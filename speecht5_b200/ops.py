@@ -32,6 +32,8 @@ class Runtime:
         self.attn_tensor_core = True  # bf16 mode: contractions of attention on the tcgen05 GEMM (else row kernels)
         self.attn_fused = True        # bf16 mode, no RPE, Tk <= 320: single-launch fused forward (attention_fused.cu)
         self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
+        self.fold_residual_grad = os.environ.get("ST5_FOLD_RESGRAD", "1") != "0"  # see LinearFn.forward (passthrough)
+        self.probs_grad_heads = 0     # > 0: gradients on returned probabilities exist for the first n heads only
         # streaming forward for what the resident kernels cannot hold (Tk > 320, clipped relative positions); "all":
         # every bf16 shape goes through it (ST5_ATTN_FLASH=all)
         self.attn_flash = {"0": False, "all": "all"}.get(os.environ.get("ST5_ATTN_FLASH", "1"), True)
@@ -281,13 +283,22 @@ class LinearFn(torch.autograd.Function):
                     x.shape, residual is not None, bias2 is not None, opts.get("bias2_rows", 0), RT.seed,
                     opts.get("need_dx", True))
         y = out if ldc == N else out[:, :N]
-        return y.reshape(*x.shape[:-1], N)
+        y = y.reshape(*x.shape[:-1], N)
+        if opts.get("passthrough"):
+            # second output = the input itself (an alias). The caller uses IT, not x, for the block's residual add: the
+            # gradient of the residual branch then arrives HERE, next to dy, and is added in the epilogue of the dx GEMM
+            # instead of by a separate elementwise kernel in autograd's accumulation (one launch + 3 tensor passes per block)
+            ctx.set_materialize_grads(False)
+            return y, x.view_as(x)
+        return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_pt=None):
         x2, pre = ctx.saved_tensors
         (weights, biases, w_sh, xa, act, drop_p, off, N, Kd, M, ldc, xshape, has_res, has_b2, b2rows, seed,
          need_dx) = ctx.meta
+        if dy is None:  # (passthrough form: only the residual branch carried a gradient)
+            dy = torch.zeros((M, N), dtype=x2.dtype, device=x2.device)
         dev = dy.device
         if dy.dtype != x2.dtype:  # fp32 head outputs of a bf16 network: gradients re-enter the bf16 stream here
             dy = dy.to(x2.dtype)
@@ -324,9 +335,15 @@ class LinearFn(torch.autograd.Function):
         dx = None
         if need_dx and ctx.needs_input_grad[0]:
             dx = torch.empty((M, Kd), dtype=dy.dtype, device=dev)
-            # dx[m,k] = sum_n dpre[m,n] W[n,k]: B operand rows = k, stored [n][k] -> MN-major
-            mm(ga, w_sh, dx, M=M, N=Kd, Kd=N, a_ld=dpre_ld, b_mn=True, b_ld=Kd, c_ld=Kd)
+            r_pt = None
+            if d_pt is not None:
+                r_pt = d_pt.reshape(M, Kd)
+                r_pt = r_pt if (r_pt.is_contiguous() and r_pt.dtype == dx.dtype) else r_pt.to(dx.dtype).contiguous()
+            # dx[m,k] = sum_n dpre[m,n] W[n,k] (+ the residual branch's gradient): B rows = k, stored [n][k] -> MN-major
+            mm(ga, w_sh, dx, M=M, N=Kd, Kd=N, a_ld=dpre_ld, b_mn=True, b_ld=Kd, c_ld=Kd, residual=r_pt)
             dx = dx.reshape(xshape)
+        elif d_pt is not None:
+            dx = d_pt
         # dW[n,k] = sum_m dpre[m,n] x[m,k]: both operands MN-major. When the trainer owns a flat gradient buffer the
         # GEMM accumulates straight into it (fused group = one contiguous [N,K] region) and autograd gets None.
         xop = xa if xa is not None else (x2, None)
@@ -360,16 +377,27 @@ class LinearFn(torch.autograd.Function):
         return (dx, d_res, d_b2, None, *grads_w, *grads_b)
 
 
+def _alias_with_stream(x_pt, x):
+    f32 = getattr(x, "_st5_f32", None)  # the fp32 copy of the residual stream rides along (residual_layer_norm)
+    if f32 is not None:
+        x_pt._st5_f32 = f32
+    return x_pt
+
+
 def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=None, bias2_rows=0, out_dtype=None,
-           need_dx=True, key=None):
+           need_dx=True, key=None, passthrough=False):
     if isinstance(weights, torch.Tensor):
         weights = (weights,)
     if isinstance(biases, torch.Tensor):
         biases = (biases,)
     biases = tuple(b for b in biases if b is not None)
-    opts = dict(n_weights=len(weights), act=act, drop_p=drop_p, bias2_rows=bias2_rows, need_dx=need_dx, key=key)
+    opts = dict(n_weights=len(weights), act=act, drop_p=drop_p, bias2_rows=bias2_rows, need_dx=need_dx, key=key,
+                passthrough=bool(passthrough))
     if out_dtype is not None:
         opts["out_dtype"] = out_dtype
+    if passthrough:  # (y, alias of x for the caller's residual add: see LinearFn.forward)
+        y, x_pt = LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
+        return y, _alias_with_stream(x_pt, x)
     return LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
 
 
@@ -380,7 +408,7 @@ class FFNFn(torch.autograd.Function):
     [rows, ffn])."""
 
     @staticmethod
-    def forward(ctx, x, residual, w1, b1, w2, b2, act, drop_a, drop_o):
+    def forward(ctx, x, residual, w1, b1, w2, b2, act, drop_a, drop_o, passthrough=False):
         x2 = x.reshape(-1, x.shape[-1])
         M, D = x2.shape
         F_ = w1.shape[0]
@@ -410,14 +438,19 @@ class FFNFn(torch.autograd.Function):
         ctx.save_for_backward(x2, h, pre)
         ctx.meta = (w1, b1, w2, b2, w1s, w2s, act, drop_a, off_a, drop_o, off_o, RT.seed, x.shape, residual is not None,
                     xa if x2.dtype == torch.float32 else None, ha if x2.dtype == torch.float32 else None)
+        if passthrough:  # (o, alias of x): the residual branch's gradient comes back into this backward (LinearFn.forward)
+            ctx.set_materialize_grads(False)
+            return o.reshape(x.shape), x.view_as(x)
         return o.reshape(x.shape)
 
     @staticmethod
-    def backward(ctx, do):
+    def backward(ctx, do, d_pt=None):
         x2, h, pre = ctx.saved_tensors
         (w1, b1, w2, b2, w1s, w2s, act, drop_a, off_a, drop_o, off_o, seed, xshape, has_res, xa, ha) = ctx.meta
         M, D = x2.shape
         F_ = h.shape[1]
+        if do is None:
+            do = torch.zeros(xshape, dtype=x2.dtype, device=x2.device)
         dev = do.device
         do2 = do.reshape(M, D).contiguous()
         d_res = do if has_res else None
@@ -451,12 +484,21 @@ class FFNFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, D), dtype=do.dtype, device=dev)
-            mm(gh, w1s, dx, M=M, N=D, Kd=F_, a_ld=F_, b_mn=True, b_ld=D, c_ld=D)
+            r_pt = None
+            if d_pt is not None:
+                r_pt = d_pt.reshape(M, D)
+                r_pt = r_pt if (r_pt.is_contiguous() and r_pt.dtype == dx.dtype) else r_pt.to(dx.dtype).contiguous()
+            mm(gh, w1s, dx, M=M, N=D, Kd=F_, a_ld=F_, b_mn=True, b_ld=D, c_ld=D, residual=r_pt)
             dx = dx.reshape(xshape)
-        return dx, d_res, dW1, db1, dW2, db2, None, None, None
+        elif d_pt is not None:
+            dx = d_pt
+        return dx, d_res, dW1, db1, dW2, db2, None, None, None, None
 
 
-def ffn(x, fc1, fc2, act, drop_a=0.0, drop_o=0.0, residual=None):
+def ffn(x, fc1, fc2, act, drop_a=0.0, drop_o=0.0, residual=None, passthrough=False):
+    if passthrough:
+        o, x_pt = FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o, True)
+        return o, _alias_with_stream(x_pt, x)
     return FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o)
 
 
@@ -674,7 +716,7 @@ class AttentionTCFn(torch.autograd.Function):
                         out=out, o_ld=d, o_bs=Tq * d, probs=probs if dpx is not None else None, p_ld=p_ld,
                         scale=cfg["scale"], drop_p=cfg.get("drop_p", 0.0), seed=seed, offset=off, dout=dout,
                         dprobs_ext=dpx, ds=None, dq=dqv, dk=dkk, dv=dvv, dpe_k=None)
-        K.attn_fused_bwd(a, psave, inv_l, o32, delta, dq_acc)
+        K.attn_fused_bwd(a, psave, inv_l, o32, delta, dq_acc, ext_heads=cfg.get("probs_grad_heads", 0) if dpx is not None else 0)
         return dq_buf, (None if same else dkv_buf), None, None, None
 
     @staticmethod
@@ -889,8 +931,10 @@ class AttentionTCFn(torch.autograd.Function):
 
 def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, maxpos=0, key_pad=None, causal=False,
               drop_p=0.0, return_probs=False):
+    # RT.probs_grad_heads: the consumer of the returned probabilities differentiates only through the first n heads (the
+    # guided-attention loss; set by the trainer from the criterion): the backward skips the zero gradient of the others
     cfg = dict(H=H, d=d, q_col=q_col, k_col=k_col, v_col=v_col, scale=scale, maxpos=maxpos, causal=causal,
-               drop_p=drop_p, return_probs=return_probs)
+               drop_p=drop_p, return_probs=return_probs, probs_grad_heads=RT.probs_grad_heads if return_probs else 0)
     Tk = (q_buf if kv_buf is None else kv_buf).shape[1]
     streaming = RT.attn_flash and RT.attn_fused and RT.attn_fused_bwd and (pe_k is None or not causal)
     if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and (Tk <= 512 or streaming):

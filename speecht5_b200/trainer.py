@@ -202,11 +202,16 @@ class B200Trainer:
 
     def __init__(self, model, criterion, task, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0, clip_norm=25.0,
                  process_group=None, use_cuda_graph=True, bucket_mb=128, exchange=None, graph_cache=8,
-                 shape_buckets=None, stage_group=1):
+                 shape_buckets=None, stage_group=3):
         self.model, self.criterion, self.task = model, criterion, task
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.device = next(model.parameters()).device
         self.criterion.to(self.device)  # criterion buffers (BCE pos_weight) must live on the device for capture
+        # the guided-attention loss reads the first n heads of every cross-attention map (text_to_speech_loss.py:210-212):
+        # the attention backward need not read the (zero) gradient of the other heads
+        t2s = getattr(criterion, "text_to_speech_loss", None)
+        RT.probs_grad_heads = (int(getattr(t2s, "num_heads_applied_guided_attn", 0))
+                               if (t2s is not None and getattr(t2s, "use_guided_attn_loss", False)) else 0)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -217,7 +222,8 @@ class B200Trainer:
             raise ValueError("parity mode reads the fp32 masters in every GEMM: use exchange='allreduce'")
         self.exchange = exchange if self.world > 1 else "none"
         # layers per exchange stage: fewer, larger collectives (each NCCL launch has to squeeze its CTAs in between
-        # persistent 148-CTA GEMM grids) against later overlap; ST5_STAGE_GROUP overrides
+        # persistent 148-CTA GEMM grids) against later overlap; ST5_STAGE_GROUP overrides. Measured at N=2 (weak scaling
+        # efficiency, profiles/r02_n2_exchange.txt): 1 layer per stage 0.960, 3 -> 0.972, 6 -> 0.975, no overlap 0.935
         self.stage_group = int(os.environ.get("ST5_STAGE_GROUP", stage_group))
         self.fp = FlatParams(model, self.world if self.exchange == "shard" else 1, self.rank, self.stage_group)
         self.bucketer = GradBucketer(self.fp.grads, bucket_elems=bucket_mb * 1024 * 1024 // 4, group=process_group)

@@ -487,3 +487,27 @@ def test_weight_gradient_split_k_with_l2_reduce(cuda, shape):
     tgt = base.clone()
     ops.wgrad_mm((gy, None), n_out, (x, None), n_in, n_out, n_in, M, target=tgt)
     assert rel(tgt, ref) < 2e-5
+
+
+def test_cross_attention_backward_with_a_gradient_on_two_heads_only(cuda):
+    """RT.probs_grad_heads = n (set by the trainer from the guided-attention criterion): the external gradient on the
+    returned probabilities is read for the first n heads only -- same result as the dense path when it is zero elsewhere."""
+    from speecht5_b200 import ops
+    ops.RT.dtype = torch.bfloat16
+    torch.manual_seed(4)
+    B, H, Tq, Tk = 2, 4, 200, 150
+    d = H * 64
+    base_q = (torch.randn(B, Tq, d, device=cuda) * 0.8).to(torch.bfloat16)
+    base_kv = (torch.randn(B, Tk, 2 * d, device=cuda) * 0.8).to(torch.bfloat16)
+    g = torch.randn(B, Tq, d, device=cuda).to(torch.bfloat16)
+    gp = torch.zeros(B, H, Tq, Tk, device=cuda)
+    gp[:, :2] = torch.randn(B, 2, Tq, Tk, device=cuda)
+    res = []
+    for hint in (0, 2):
+        ops.RT.probs_grad_heads = hint
+        qb, kvb = base_q.clone().requires_grad_(), base_kv.clone().requires_grad_()
+        out, probs = ops.attention(qb, kvb, H=H, d=d, q_col=0, k_col=0, v_col=1, scale=0.125, return_probs=True)
+        torch.autograd.backward([out, probs], [g, gp])
+        res.append((qb.grad, kvb.grad))
+    ops.RT.probs_grad_heads = 0
+    assert rel(res[1][0], res[0][0]) < 1e-6 and rel(res[1][1], res[0][1]) < 1e-6
