@@ -105,11 +105,13 @@ int st5_ln_fwd_stream(const void* x, const void* residual, const float* residual
                       const float* beta, void* y, float* y_f32, void* s_out, float* mean, float* rstd, int dtype,
                       int64_t rows, int64_t C, float eps, float drop_p, uint64_t seed, uint64_t offset, void* stream);
 /* ds = LN backward wrt s; dx = dropout-backward(ds) (may alias / be NULL when drop_p == 0 and caller reuses ds);
- * dgamma/dbeta are accumulated (+=) in fp32. `partials` is a caller scratch of 2 * nblk * C floats where
- * nblk = st5_ln_bwd_blocks(rows). */
+ * dgamma/dbeta are accumulated (+=) in fp32. `dxsum` (may be NULL; fp32 [C], accumulated +=) receives the column sums
+ * of dx (of ds when dx is NULL): in the post-LN tail y = LN(residual + dropout(W a + b)) that is the gradient of b, so
+ * the bias gradient of out_proj / fc2 (transformer_layer.py:112-132) costs no launch of its own.
+ * st5_ln_bwd_blocks is kept for ABI stability (returns 1; no scratch is needed). */
 int64_t st5_ln_bwd_blocks(int64_t rows);
 int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* ds,
-               void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C, float drop_p,
+               void* dx, float* dgamma, float* dbeta, float* dxsum, int dtype, int64_t rows, int64_t C, float drop_p,
                uint64_t seed, uint64_t offset, void* stream);
 
 /* y = dropout(x) (also its own backward when applied to the gradient). fairseq/modules/fairseq_dropout.py:23-37
@@ -234,13 +236,14 @@ int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, con
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------- CTC
- * (speech-input branch, SURVEY section 8a row 18 -- EXPERIMENTAL: written without GPU time, not yet validated on device)
+ * (speech-input branch)
  * Replaces F.log_softmax + F.ctc_loss(reduction="sum") of speech_to_text_loss.py:303-335 on the encoder's CTC head.
  * logits fp32, element (t, b, k) at t*ld_t + b*ld_b + k; targets: flat int64 labels, utterance b's at
  * targets[tgt_offsets[b] .. + target_lengths[b]); nll [B] receives the per-utterance negative log-likelihood (+inf for
  * an infeasible utterance, or 0 with zero_infinity); grad (optional, same addressing as logits) receives
  * d(sum_b nll_b)/d logits, zero for t >= input_lengths[b] and for infeasible utterances. S_max >= 2*max(target_lengths)+1
- * (<= 1024) is the scratch pitch; ws: st5_ctc_ws_floats(T, B, S_max) floats. */
+ * (<= 1024) is the scratch pitch; ws: st5_ctc_ws_floats(T, B, S_max) floats (row log-sum-exps, emission terms, alpha
+ * and beta lattices). Three launches: row pass, the two recursions side by side in one CTA per utterance, gradient rows. */
 int64_t st5_ctc_ws_floats(int32_t T, int32_t B, int32_t S_max);
 int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
                  const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,

@@ -1,12 +1,15 @@
 """@register_criterion("speecht5") dispatcher, mirroring speecht5/criterions/speecht5_criterion.py:23-120: routes on
-sample['task_name']. Round 1 wires the t2s branch (TexttoSpeechLoss); note the reference dispatcher does not forward
-guided_attn_loss_lambda, so the effective guided-attention weight is 1.0 (speecht5_criterion.py:61-71)."""
+sample['task_name'] to the t2s / s2s (TexttoSpeechLoss), s2t (SpeechtoTextLoss), text_pretrain and speech_pretrain
+criteria; note the reference dispatcher does not forward guided_attn_loss_lambda, so the effective guided-attention
+weight is 1.0 (speecht5_criterion.py:61-71)."""
 import math
 import re
 from dataclasses import dataclass, field
 
 from ..fairseq_shim import FairseqCriterion, metrics, register_criterion
+from .speech_pretrain_criterion import SpeechPretrainCriterion
 from .speech_to_text_loss import SpeechtoTextLoss
+from .text_pretrain_criterion import TextPretrainCriterion
 from .text_to_speech_loss import TexttoSpeechLoss
 
 
@@ -38,6 +41,8 @@ class SpeechT5CriterionConfig:
     # pre-training criteria (speech_pretrain_criterion.py, text_pretrain_criterion.py)
     pred_masked_weight: float = field(default=1.0)
     pred_nomask_weight: float = field(default=0.0)
+    loss_weights: list = field(default_factory=lambda: [10.0])
+    log_keys: list = field(default_factory=list)
     dec_weight: float = field(default=0.5)
     bart_weight: float = field(default=1.0)
     hubert_weight: float = field(default=1.0)
@@ -48,7 +53,9 @@ class SpeechT5Criterion(FairseqCriterion):
     def __init__(self, task, sentence_avg=True, use_masking=True, loss_type="L1", bce_pos_weight=5.0,
                  bce_loss_lambda=1.0, use_guided_attn_loss=False, guided_attn_loss_sigma=0.4,
                  num_heads_applied_guided_attn=2, label_smoothing=0.0, ignore_prefix_size=0, report_accuracy=False,
-                 ce_weight=1.0, ctc_weight=0.0, zero_infinity=False, post_process="sentencepiece", **unused):
+                 ce_weight=1.0, ctc_weight=0.0, zero_infinity=False, post_process="sentencepiece", pred_masked_weight=1.0,
+                 pred_nomask_weight=0.0, loss_weights=(10.0,), log_keys=None, use_weighted_masking=False,
+                 hubert_weight=1.0, dec_weight=1.0, bart_weight=1.0, **unused):
         super().__init__(task)
         self.text_to_speech_loss = TexttoSpeechLoss(
             task, sentence_avg, use_masking, False, loss_type, bce_pos_weight, bce_loss_lambda, use_guided_attn_loss,
@@ -56,6 +63,11 @@ class SpeechT5Criterion(FairseqCriterion):
         # s2t branch (speecht5_criterion.py:72-81); meaningful only with the opt-in speech-input / text-output model
         self.speech_to_text_loss = SpeechtoTextLoss(task, sentence_avg, label_smoothing, ignore_prefix_size,
                                                     report_accuracy, ce_weight, ctc_weight, zero_infinity, post_process)
+        # pre-training branches (speecht5_criterion.py:82-101): both share the configured loss_weights list
+        self.text_pretrain_criterion = TextPretrainCriterion(task, sentence_avg, bart_weight, loss_weights)
+        self.speech_pretrain_criterion = SpeechPretrainCriterion(
+            task, sentence_avg, pred_masked_weight, pred_nomask_weight, loss_weights, log_keys, use_masking,
+            use_weighted_masking, loss_type, bce_pos_weight, hubert_weight, dec_weight)
 
     def forward(self, model, sample, reduce=True):
         task_name = sample["task_name"]
@@ -63,7 +75,11 @@ class SpeechT5Criterion(FairseqCriterion):
             return self.text_to_speech_loss(model, sample)
         if task_name == "s2t":
             return self.speech_to_text_loss(model, sample, reduce)
-        raise NotImplementedError(f"criterion branch '{task_name}' is not built yet in the B200 path (round 1: t2s)")
+        if task_name == "text_pretrain":
+            return self.text_pretrain_criterion(model, sample, reduce)
+        if task_name == "speech_pretrain":
+            return self.speech_pretrain_criterion(model, sample, reduce)
+        raise NotImplementedError(f"criterion branch '{task_name}' is not built in the B200 path (speaker identification)")
 
     # ------------------------------------------------------------------ logging (speecht5_criterion.py:123-436)
     @staticmethod

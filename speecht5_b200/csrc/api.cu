@@ -89,9 +89,9 @@ int st5_ln_fwd_stream(const void* x, const void* residual, const float* residual
 }
 int64_t st5_ln_bwd_blocks(int64_t rows) { return ln_bwd_blocks(rows); }
 int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* ds,
-               void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C, float drop_p,
+               void* dx, float* dgamma, float* dbeta, float* dxsum, int dtype, int64_t rows, int64_t C, float drop_p,
                uint64_t seed, uint64_t offset, void* stream) {
-  return set_error(ln_bwd_launch(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, partials, dtype, rows, C, drop_p,
+  return set_error(ln_bwd_launch(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, dtype, rows, C, drop_p,
                                  seed, offset, (cudaStream_t)stream),
                    "st5_ln_bwd");
 }

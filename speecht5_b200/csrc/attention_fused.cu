@@ -240,7 +240,11 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
     const int i = i0 + r;
     const bool row_ok = i < p.Tq;
     const int64_t prow = ((int64_t)b * p.H + h) * p.Tq + i;
-    const int nchunks = nkb * 2;  // 32-column chunks (TMEM columns beyond tk16 hold garbage and are masked)
+    // warp-uniform: none of this warp's 32 rows exists (T = 160: three of the four lane quarters of the second tile;
+    // T = 313: two of the third). Such a warp only keeps the barrier protocol going: its P rows stay whatever they
+    // were (rows of P are independent in P V, and nothing of these rows is stored).
+    const bool warp_ok = i0 + q * 32 < p.Tq;
+    const int nchunks = warp_ok ? nkb * 2 : 0;  // 32-column chunks (TMEM columns beyond tk16 hold garbage and are masked)
     // validity bits of chunk c for THIS row: key exists, not padded (one coalesced byte load per lane + ballot), causal
     auto valid_bits = [&](int c) -> uint32_t {
       const int j = c * 32 + (int)lane_id();
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
     }
     if (p.probs != nullptr) {
       // normalised, undropped probabilities for the caller (overlaps the PV MMA)
-      const int pchunks = (int)((p.p_ld + 31) / 32);
+      const int pchunks = warp_ok ? (int)((p.p_ld + 31) / 32) : 0;
       for (int c = half; c < pchunks; c += NG) {
         float pr[32];
         if (c < nchunks) {

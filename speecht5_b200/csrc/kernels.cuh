@@ -104,7 +104,7 @@ int ln_fwd_launch(const void* x, const void* residual, const float* residual_f32
                   float eps, float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int64_t ln_bwd_blocks(int64_t rows);
 int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
-                  void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
+                  void* dx, float* dgamma, float* dbeta, float* dxsum, int dtype, int64_t rows, int64_t C,
                   float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s);
 int dropout_launch(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
                    cudaStream_t s);

@@ -202,45 +202,130 @@ __global__ void __launch_bounds__(256)
 }
 
 // Input gradient AND parameter gradients in ONE pass over dy / s (the two-kernel form reads both tensors twice):
-// persistent grid, warp per row, every lane keeps the dgamma / dbeta partials of its own channels in registers across
-// the rows it visits; per CTA they meet in shared memory (fp32 shared atomics, once) and leave as one global atomic per
-// channel. NCH = 16-byte chunks per lane (C <= NCH * 256).
+// persistent grid, warp per row. The per-channel sums -- dgamma, dbeta and, when asked for, the column sums of dx (= the
+// bias gradient of the projection that produced x: its separate column-sum launch disappears) -- live in a PRIVATE
+// shared-memory strip per warp (plain read-modify-write of the lane's own 16-byte slots, conflict-free layout), which
+// frees the registers for a one-row-ahead prefetch of dy / s: a warp visits only 2-5 rows, so without the prefetch every
+// row costs a full exposed HBM round trip (measured 2.5 TB/s before). The strips meet after a CTA barrier and leave as
+// 16-byte vector reductions (red.global.add.v4.f32) when the targets are 16-byte aligned. NCH = 16-byte chunks per lane.
 constexpr int LNB_WARPS = 8;
+constexpr int LNB_NACC = 3;  // dgamma | dbeta | column sums of dx
+
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void decode(float* v) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(h[t]);
+      v[2 * t] = f.x; v[2 * t + 1] = f.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = reinterpret_cast<const float4*>(p)[0];
+    b = reinterpret_cast<const float4*>(p)[1];
+  }
+  __device__ __forceinline__ void decode(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
     ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ s_in, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ ds,
-                        T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
-                        uint32_t thr, float dscale, uint64_t seed, uint64_t offset) {
-  extern __shared__ float ln_acc[];  // [2][C]
+                        T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        float* __restrict__ dxsum, int64_t rows, int C, uint32_t thr, float dscale, uint64_t seed,
+                        uint64_t offset) {
+  extern __shared__ __align__(16) float ln_acc[];  // [LNB_WARPS][LNB_NACC][C]; channel ch*8+t at (t>>2)*(C/2) + ch*4 + (t&3)
+  constexpr bool PF = sizeof(T) == 2;  // one-row-ahead prefetch (24 registers for bf16; fp32 rows would need 48)
   if (thr != 0) resolve_seed(seed, offset);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = C >> 3;
-  for (int t = threadIdx.x; t < 2 * C; t += LNB_WARPS * 32) ln_acc[t] = 0.f;
-  __syncthreads();
-  float pg[NCH][8], pb[NCH][8];
+  const int half4 = C >> 3;  // float4 index of the second half of an accumulator
+  float4* acc = reinterpret_cast<float4*>(ln_acc + (size_t)warp * LNB_NACC * C);
+  const int acc4 = C >> 2;   // float4 per accumulator
+  for (int t = lane; t < LNB_NACC * acc4; t += 32) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  const int64_t stride = (int64_t)gridDim.x * LNB_WARPS;
+  int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp;
+  Raw8<T> cd[NCH], cs[NCH];
+  float mu = 0.f, rs = 0.f;
+  if (PF && row < rows) {
 #pragma unroll
-  for (int k = 0; k < NCH; ++k)
+    for (int k = 0; k < NCH; ++k) {
+      const int ch = k * 32 + lane;
+      if (ch < nchunks) {
+        cd[k].load(dy + row * C + ch * 8);
+        cs[k].load(s_in + row * C + ch * 8);
+      }
+    }
+    mu = mean[row];
+    rs = rstd[row];
+  }
+  for (; row < rows; row += stride) {
+    if constexpr (!PF) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) pg[k][t] = pb[k][t] = 0.f;
-  for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < rows; row += (int64_t)gridDim.x * LNB_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
+      for (int k = 0; k < NCH; ++k) {
+        const int ch = k * 32 + lane;
+        if (ch < nchunks) {
+          cd[k].load(dy + row * C + ch * 8);
+          cs[k].load(s_in + row * C + ch * 8);
+        }
+      }
+      mu = mean[row];
+      rs = rstd[row];
+    }
     float d[NCH][8], xh[NCH][8];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      if (k * 32 + lane < nchunks) {
+        cd[k].decode(d[k]);
+        cs[k].decode(xh[k]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xh[k][t] = (xh[k][t] - mu) * rs;
+      }
+    }
+    const float rs_cur = rs;
+    if constexpr (PF) {  // the raw registers are free again: the next row's loads fly under this row's arithmetic
+      const int64_t nxt = row + stride;
+      if (nxt < rows) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int ch = k * 32 + lane;
+          if (ch < nchunks) {
+            cd[k].load(dy + nxt * C + ch * 8);
+            cs[k].load(s_in + nxt * C + ch * 8);
+          }
+        }
+        mu = mean[nxt];
+        rs = rstd[nxt];
+      }
+    }
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int ch = k * 32 + lane;
       if (ch < nchunks) {
-        const int64_t e0 = row * C + ch * 8;
-        float sv[8], gm[8];
-        load8<T>(dy + e0, d[k]);
-        load8<T>(s_in + e0, sv);
+        float gm[8];
         load8<float>(gamma + ch * 8, gm);
+        float4 g0 = acc[ch], g1 = acc[half4 + ch], b0 = acc[acc4 + ch], b1 = acc[acc4 + half4 + ch];
+        g0.x += d[k][0] * xh[k][0]; g0.y += d[k][1] * xh[k][1]; g0.z += d[k][2] * xh[k][2]; g0.w += d[k][3] * xh[k][3];
+        g1.x += d[k][4] * xh[k][4]; g1.y += d[k][5] * xh[k][5]; g1.z += d[k][6] * xh[k][6]; g1.w += d[k][7] * xh[k][7];
+        b0.x += d[k][0]; b0.y += d[k][1]; b0.z += d[k][2]; b0.w += d[k][3];
+        b1.x += d[k][4]; b1.y += d[k][5]; b1.z += d[k][6]; b1.w += d[k][7];
+        acc[ch] = g0; acc[half4 + ch] = g1; acc[acc4 + ch] = b0; acc[acc4 + half4 + ch] = b1;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          xh[k][t] = (sv[t] - mu) * rs;
-          pb[k][t] += d[k][t];
-          pg[k][t] += d[k][t] * xh[k][t];
           d[k][t] *= gm[t];  // g = dy * gamma from here on
           c1 += d[k][t];
           c2 += d[k][t] * xh[k][t];
@@ -256,64 +341,90 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
         const int64_t e0 = row * C + ch * 8;
         float r[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) r[t] = rs * (d[k][t] - c1 - xh[k][t] * c2);
+        for (int t = 0; t < 8; ++t) r[t] = rs_cur * (d[k][t] - c1 - xh[k][t] * c2);
         if (ds != nullptr) store8<T>(ds + e0, r);
         if (dx != nullptr) {
           if (thr != 0) dropout8(r, (uint64_t)e0, thr, dscale, seed, offset);
           store8<T>(dx + e0, r);
         }
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int ch = k * 32 + lane;
-    if (ch < nchunks) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        atomicAdd(&ln_acc[ch * 8 + t], pg[k][t]);
-        atomicAdd(&ln_acc[C + ch * 8 + t], pb[k][t]);
+        if (dxsum != nullptr) {  // (without dropout dx == ds: the sums are those of r either way)
+          float4 x0 = acc[2 * acc4 + ch], x1 = acc[2 * acc4 + half4 + ch];
+          x0.x += r[0]; x0.y += r[1]; x0.z += r[2]; x0.w += r[3];
+          x1.x += r[4]; x1.y += r[5]; x1.z += r[6]; x1.w += r[7];
+          acc[2 * acc4 + ch] = x0; acc[2 * acc4 + half4 + ch] = x1;
+        }
       }
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < C; t += LNB_WARPS * 32) {
-    if (dgamma != nullptr) atomicAdd(dgamma + t, ln_acc[t]);
-    if (dbeta != nullptr) atomicAdd(dbeta + t, ln_acc[C + t]);
+  // strips -> global: item = (accumulator a, float4 slot q); slot q < C/8 holds channels 8q..8q+3, else 8(q-C/8)+4..+7
+  const float4* all = reinterpret_cast<const float4*>(ln_acc);
+  for (int it = threadIdx.x; it < LNB_NACC * acc4; it += LNB_WARPS * 32) {
+    const int a = it / acc4, q = it - a * acc4;
+    float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dxsum);
+    if (dst == nullptr) continue;
+    float4 v = all[it];
+#pragma unroll
+    for (int w = 1; w < LNB_WARPS; ++w) {
+      const float4 o = all[(size_t)w * LNB_NACC * acc4 + it];
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    const int c0 = q < half4 ? q * 8 : (q - half4) * 8 + 4;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      red_add_v4(dst + c0, v);
+    } else {
+      atomicAdd(dst + c0, v.x); atomicAdd(dst + c0 + 1, v.y); atomicAdd(dst + c0 + 2, v.z); atomicAdd(dst + c0 + 3, v.w);
+    }
   }
 }
 
-template <typename T>
-static void ln_bwd_fused_dispatch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
-                                  void* ds, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, uint32_t thr,
-                                  float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
+template <typename T, int NCH>
+static int ln_bwd_fused_run(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
+                            void* ds, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int C,
+                            uint32_t thr, float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  static bool attr_set = false;  // (one per kernel instantiation)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ln_bwd_fused_kernel<T, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         LNB_WARPS * LNB_NACC * NCH * 256 * (int)sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
   int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS;
   const int64_t cap = 2 * (int64_t)device_sm_count();
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  const size_t smem = (size_t)2 * C * sizeof(float);
+  const size_t smem = (size_t)LNB_WARPS * LNB_NACC * C * sizeof(float);
+  ln_bwd_fused_kernel<T, NCH><<<grid, LNB_WARPS * 32, smem, s>>>((const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds,
+                                                                 (T*)dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset);
+  return 0;
+}
+
+template <typename T>
+static int ln_bwd_fused_dispatch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
+                                 void* ds, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int C,
+                                 uint32_t thr, float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
   if (C <= 768)
-    ln_bwd_fused_kernel<T, 3><<<grid, LNB_WARPS * 32, smem, s>>>((const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds,
-                                                                (T*)dx, dgamma, dbeta, rows, C, thr, dsc, seed, offset);
-  else
-    ln_bwd_fused_kernel<T, LN_MAX_CHUNKS><<<grid, LNB_WARPS * 32, smem, s>>>(
-        (const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds, (T*)dx, dgamma, dbeta, rows, C, thr, dsc, seed, offset);
+    return ln_bwd_fused_run<T, 3>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset, s);
+  return ln_bwd_fused_run<T, LN_MAX_CHUNKS>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed,
+                                            offset, s);
 }
 
 int ln_bwd_launch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma, void* ds,
-                  void* dx, float* dgamma, float* dbeta, float* partials, int dtype, int64_t rows, int64_t C,
+                  void* dx, float* dgamma, float* dbeta, float* dxsum, int dtype, int64_t rows, int64_t C,
                   float drop_p, uint64_t seed, uint64_t offset, cudaStream_t s) {
-  (void)partials;
   if (rows == 0) return 0;
   if (C > 8 * 32 * LN_MAX_CHUNKS || C <= 0 || (C & 7)) return -2;
   const uint32_t thr = drop_threshold(drop_p);
   const float dsc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  if ((dgamma != nullptr || dbeta != nullptr) && rows >= 64) {  // one pass over dy / s for dx and the parameter sums
+  if ((dgamma != nullptr || dbeta != nullptr || dxsum != nullptr) && (rows >= 64 || dxsum != nullptr)) {
+    // one pass over dy / s for dx, the parameter sums and the column sums of dx
+    int rc;
     if (dtype == ST5_F32)
-      ln_bwd_fused_dispatch<float>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, rows, (int)C, thr, dsc, seed, offset, s);
+      rc = ln_bwd_fused_dispatch<float>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, (int)C, thr, dsc,
+                                        seed, offset, s);
     else
-      ln_bwd_fused_dispatch<__nv_bfloat16>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, rows, (int)C, thr, dsc, seed,
-                                           offset, s);
-    return (int)cudaGetLastError();
+      rc = ln_bwd_fused_dispatch<__nv_bfloat16>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, (int)C, thr,
+                                                dsc, seed, offset, s);
+    return rc != 0 ? rc : (int)cudaGetLastError();
   }
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   int64_t splits = (rows + 255) / 256;

@@ -133,16 +133,18 @@ def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed
     _count(1)
 
 
-def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, offset=0):
+def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, offset=0, dxsum=None):
+    """dxsum (optional, fp32 [C], accumulated): column sums of dx = the bias gradient of the projection that fed x."""
     Cc = dy.shape[-1]
     rows = dy.numel() // Cc
     lib = _lib.load()
-    nblk = lib.st5_ln_bwd_blocks(rows)
-    partials = torch.empty(2 * nblk * Cc, dtype=torch.float32, device=dy.device)
+    if dxsum is not None:
+        assert dxsum.dtype == torch.float32 and dxsum.numel() >= Cc and dxsum.is_contiguous()
     _lib.check(lib.st5_ln_bwd(_ptr(dy), _ptr(s), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(ds), _ptr(dx),
-                              _ptr(dgamma), _ptr(dbeta), _ptr(partials), dtype_id(dy), rows, Cc, drop_p, seed, offset,
+                              _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), dtype_id(dy), rows, Cc, drop_p, seed, offset,
                               _stream()), "st5_ln_bwd")
-    _count(2)
+    fused = (dgamma is not None or dbeta is not None or dxsum is not None) and (rows >= 64 or dxsum is not None)
+    _count(1 if fused or (dgamma is None and dbeta is None) else 2)
 
 
 def dropout(x, y, drop_p, seed, offset):
@@ -281,7 +283,7 @@ def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, s
 
 
 def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, grad, s_max, blank, zero_infinity):
-    """EXPERIMENTAL (not yet validated on a GPU). logits [T, B, V] fp32 (inner stride 1); see st5_ctc_loss."""
+    """logits [T, B, V] fp32 (inner stride 1); see st5_ctc_loss (rows + concurrent alpha / beta sweeps + gradient rows)."""
     _require_cuda(logits, targets, nll)
     assert logits.dtype == torch.float32 and logits.stride(2) == 1
     for t in (targets, tgt_offsets, input_lengths, target_lengths):
@@ -293,7 +295,7 @@ def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, g
     _lib.check(lib.st5_ctc_loss(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(targets), _ptr(tgt_offsets),
                                 _ptr(input_lengths), _ptr(target_lengths), _ptr(nll), _ptr(grad), _ptr(ws), T, B, V,
                                 s_max, blank, int(zero_infinity), _stream()), "st5_ctc_loss")
-    _count(2)
+    _count(3 if grad is not None else 2)
 
 
 def sumsq(x, out):

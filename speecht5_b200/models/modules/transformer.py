@@ -146,10 +146,10 @@ class TransformerSentenceEncoderLayer(nn.Module):
             pt = _fold_residual_grad(x)
             a = self.self_attn.self_attend(x, self_attn_padding_mask, pe_k=pos_bias, maxpos=maxpos, training=tr, passthrough=pt)
             a, r = a if pt else (a, x)
-            o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
+            o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, bias_grad_by_consumer=True)
             x = ops.residual_layer_norm(o, r, self.self_attn_layer_norm, drop_p=p, stream=True)
             pt = _fold_residual_grad(x)
-            o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt)
+            o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt, bias_grad_by_consumer=True)
             o, r = o if pt else (o, x)
             x = ops.residual_layer_norm(o, r, self.final_layer_norm, drop_p=p, stream=True)
         return x, None
@@ -328,7 +328,8 @@ class TransformerDecoderLayer(nn.Module):
                 pt = _fold_residual_grad(x)
                 a = self.self_attn.self_attend(x, self_attn_padding_mask, causal=causal, training=tr, passthrough=pt)
                 a, r = a if pt else (a, x)
-                o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
+                o = ops.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias,
+                               bias_grad_by_consumer=True)
                 x = ops.residual_layer_norm(o, r, self.self_attn_layer_norm, drop_p=p, stream=True)
         attn = None
         if self.encoder_attn is not None and encoder_out is not None:
@@ -343,7 +344,8 @@ class TransformerDecoderLayer(nn.Module):
                 pt = _fold_residual_grad(x)
                 res = self.encoder_attn.cross_attend(x, encoder_out, encoder_padding_mask, want, tr, passthrough=pt)
                 a, attn, r = res if pt else (res[0], res[1], x)
-                o = ops.linear(a, self.encoder_attn.out_proj.weight, self.encoder_attn.out_proj.bias)
+                o = ops.linear(a, self.encoder_attn.out_proj.weight, self.encoder_attn.out_proj.bias,
+                               bias_grad_by_consumer=True)
                 x = ops.residual_layer_norm(o, r, self.encoder_attn_layer_norm, drop_p=p, stream=True)
             if attn is not None and not need_head_weights:
                 attn = attn.mean(dim=1)
@@ -354,7 +356,8 @@ class TransformerDecoderLayer(nn.Module):
                 x = ops.ffn(h, self.fc1, self.fc2, self.activation_fn, drop_a=pa, drop_o=p, residual=residual)
             else:
                 pt = _fold_residual_grad(x)
-                o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt)
+                o = ops.ffn(x, self.fc1, self.fc2, self.activation_fn, drop_a=pa, passthrough=pt,
+                            bias_grad_by_consumer=True)
                 o, r = o if pt else (o, x)
                 x = ops.residual_layer_norm(o, r, self.final_layer_norm, drop_p=p, stream=True)
         return x, attn, None

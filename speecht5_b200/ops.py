@@ -39,6 +39,8 @@ class Runtime:
         self.attn_flash = {"0": False, "all": "all"}.get(os.environ.get("ST5_ATTN_FLASH", "1"), True)
         self.ffn_gate = os.environ.get("ST5_FFN_GATE", "1") != "0"  # bf16 mode: fc1 stores the backward gate (FFNFn)
         self.wgrad_splitk = os.environ.get("ST5_WGRAD_SPLITK", "1") != "0"  # weight gradients: pair tiles + split-K + L2 reduce
+        # out_proj / fc2 bias gradients come out of the consuming LayerNorm's backward pass (no column-sum launch)
+        self.fold_bias_grad = os.environ.get("ST5_FOLD_BIAS_GRAD", "1") != "0"
         self.fp32_stream = os.environ.get("ST5_FP32_STREAM", "1") != "0"  # bf16 mode: fp32 residual stream between LayerNorms
         # trainer hooks: stage_callback(key, x) is called at the entry of every encoder / decoder layer (gradient-exchange
         # overlap point); layer_keep (device [n_enc + n_dec] 0/1 mask, CUDA-graph mode) / layer_keep_host (eager mode)
@@ -174,6 +176,24 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _key_pad_u8(key_pad):
+    """uint8 form of a key-padding mask. Every layer of a stack receives the SAME mask tensor: the converted copy rides
+    on it as an attribute, so the cast runs once per forward pass instead of once per attention call (24 per update)."""
+    if key_pad is None:
+        return None
+    if key_pad.dtype == torch.uint8 and key_pad.is_contiguous():
+        return key_pad
+    hit = getattr(key_pad, "_st5_u8", None)  # (version counter of the mask at conversion time, converted copy)
+    if hit is not None and hit[0] == key_pad._version and hit[1].shape == key_pad.shape and hit[1].device == key_pad.device:
+        return hit[1]
+    u8 = key_pad.to(torch.uint8).contiguous()
+    try:
+        key_pad._st5_u8 = (key_pad._version, u8)
+    except Exception:  # (tensor subclasses that refuse attributes)
+        pass
+    return u8
+
+
 def _pe_bf16(pe_k):
     """bf16 copy of the relative-position table. A Parameter is cached per parameter epoch; a computed tensor (the
     pre-LN layers pass norm_k(table), transformer_layer.py:94-95) is cast every call -- its id() is not stable."""
@@ -279,6 +299,7 @@ class LinearFn(torch.autograd.Function):
            bias2_rows=opts.get("bias2_rows", 0), residual=res2, c_pre=pre, act=act, drop_p=drop_p, seed=RT.seed,
            offset=off)
         ctx.save_for_backward(x2, pre)
+        ctx.bias_holder = opts.get("bias_holder")
         ctx.meta = (weights, biases, w_sh, xa if x2.dtype == torch.float32 else None, act, drop_p, off, N, Kd, M, ldc,
                     x.shape, residual is not None, bias2 is not None, opts.get("bias2_rows", 0), RT.seed,
                     opts.get("need_dx", True))
@@ -358,8 +379,19 @@ class LinearFn(torch.autograd.Function):
                 r0 += w.shape[0]
         grads_b = []
         d_b2 = None
+        holder = ctx.bias_holder
         if len(biases) > 0 or has_b2:
-            if len(biases) > 0:
+            if len(biases) > 0 and holder is not None and holder["taken"]:
+                # the LayerNorm that consumed y already summed the columns of its dx (= dpre) in its own backward pass
+                db = holder["value"]
+                if db is None:
+                    grads_b = [None] * len(biases)
+                else:
+                    r0 = 0
+                    for b in biases:
+                        grads_b.append(db[r0:r0 + b.shape[0]])
+                        r0 += b.shape[0]
+            elif len(biases) > 0:
                 gB = RT._static_grad.get(("bias",) + tuple(id(b) for b in biases))
                 if gB is not None:
                     K.colsum(dpre, gB, ld=dpre_ld, accumulate=True)
@@ -384,8 +416,15 @@ def _alias_with_stream(x_pt, x):
     return x_pt
 
 
+def _bias_holder(biases):
+    """Hand-over of a bias gradient to the LayerNorm that consumes the projection's output (residual_layer_norm picks it
+    up from the tensor): its backward pass sums the columns of its dx anyway-resident rows, so the projection's own
+    column-sum launch is skipped. `taken` stays False when nobody picked it up (the projection then sums itself)."""
+    return dict(taken=False, value=None, key=("bias",) + tuple(id(b) for b in biases), n=sum(b.shape[0] for b in biases))
+
+
 def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=None, bias2_rows=0, out_dtype=None,
-           need_dx=True, key=None, passthrough=False):
+           need_dx=True, key=None, passthrough=False, bias_grad_by_consumer=False):
     if isinstance(weights, torch.Tensor):
         weights = (weights,)
     if isinstance(biases, torch.Tensor):
@@ -395,10 +434,17 @@ def linear(x, weights, biases=(), *, act=None, drop_p=0.0, residual=None, bias2=
                 passthrough=bool(passthrough))
     if out_dtype is not None:
         opts["out_dtype"] = out_dtype
+    holder = None
+    if (bias_grad_by_consumer and len(biases) > 0 and act is None and drop_p == 0.0 and residual is None
+            and torch.is_grad_enabled() and RT.fold_bias_grad):
+        holder = opts["bias_holder"] = _bias_holder(biases)
     if passthrough:  # (y, alias of x for the caller's residual add: see LinearFn.forward)
         y, x_pt = LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
         return y, _alias_with_stream(x_pt, x)
-    return LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
+    y = LinearFn.apply(x, residual, bias2, opts, *weights, *biases)
+    if holder is not None:
+        y._st5_bias_holder = holder
+    return y
 
 
 class FFNFn(torch.autograd.Function):
@@ -408,7 +454,8 @@ class FFNFn(torch.autograd.Function):
     [rows, ffn])."""
 
     @staticmethod
-    def forward(ctx, x, residual, w1, b1, w2, b2, act, drop_a, drop_o, passthrough=False):
+    def forward(ctx, x, residual, w1, b1, w2, b2, act, drop_a, drop_o, passthrough=False, bias_holder=None):
+        ctx.bias_holder = bias_holder
         x2 = x.reshape(-1, x.shape[-1])
         M, D = x2.shape
         F_ = w1.shape[0]
@@ -478,7 +525,11 @@ class FFNFn(torch.autograd.Function):
             return db
 
         dW2 = wgrad(ga, D, ha if ha is not None else (h, None), F_, w2, D, F_)
-        db2 = bgrad(do2, b2)
+        holder = ctx.bias_holder
+        if holder is not None and holder["taken"]:  # summed by the consuming LayerNorm's backward (see _bias_holder)
+            db2 = holder["value"]
+        else:
+            db2 = bgrad(do2, b2)
         dW1 = wgrad(gh, F_, xa if xa is not None else (x2, None), x2.stride(0), w1, F_, D)
         db1 = bgrad(dhp, b1)
         dx = None
@@ -492,14 +543,23 @@ class FFNFn(torch.autograd.Function):
             dx = dx.reshape(xshape)
         elif d_pt is not None:
             dx = d_pt
-        return dx, d_res, dW1, db1, dW2, db2, None, None, None, None
+        return dx, d_res, dW1, db1, dW2, db2, None, None, None, None, None
 
 
-def ffn(x, fc1, fc2, act, drop_a=0.0, drop_o=0.0, residual=None, passthrough=False):
+def ffn(x, fc1, fc2, act, drop_a=0.0, drop_o=0.0, residual=None, passthrough=False, bias_grad_by_consumer=False):
+    holder = None
+    if (bias_grad_by_consumer and drop_o == 0.0 and residual is None and fc2.bias is not None and torch.is_grad_enabled()
+            and RT.fold_bias_grad):
+        holder = _bias_holder((fc2.bias,))
     if passthrough:
-        o, x_pt = FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o, True)
+        o, x_pt = FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o, True, holder)
+        if holder is not None:
+            o._st5_bias_holder = holder
         return o, _alias_with_stream(x_pt, x)
-    return FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o)
+    o = FFNFn.apply(x, residual, fc1.weight, fc1.bias, fc2.weight, fc2.bias, act, drop_a, drop_o, False, holder)
+    if holder is not None:
+        o._st5_bias_holder = holder
+    return o
 
 
 # =================================================================================================== LayerNorm
@@ -508,7 +568,8 @@ class ResidualLayerNormFn(torch.autograd.Function):
     (transformer_layer.py:112-132, 343-391) and the encoder input LayerNorm (encoder.py:226-227)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps, drop_p, res_f32=None, y_f32=None):
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p, res_f32=None, y_f32=None, bias_holder=None):
+        ctx.bias_holder = bias_holder
         x = x.contiguous()
         Cc = x.shape[-1]
         rows = x.numel() // Cc
@@ -537,10 +598,16 @@ class ResidualLayerNormFn(torch.autograd.Function):
         direct = gG is not None and gB is not None
         dgamma = gG if direct else torch.zeros_like(gamma, dtype=torch.float32)
         dbeta = gB if direct else torch.zeros_like(gamma, dtype=torch.float32)
-        K.ln_bwd(dy, s, mean, rstd, gamma.detach(), ds, dx, dgamma, dbeta, drop_p, seed, off)
+        holder, dxsum = ctx.bias_holder, None
+        if holder is not None:  # the producing projection's bias gradient = column sums of dx (see ops._bias_holder)
+            dxsum = RT._static_grad.get(holder["key"])
+            if dxsum is None:
+                dxsum = holder["value"] = torch.zeros(holder["n"], dtype=torch.float32, device=dy.device)
+            holder["taken"] = True
+        K.ln_bwd(dy, s, mean, rstd, gamma.detach(), ds, dx, dgamma, dbeta, drop_p, seed, off, dxsum=dxsum)
         if direct:
             dgamma = dbeta = None
-        return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None, None, None
+        return (dx if dx is not None else ds), (ds if has_res else None), dgamma, dbeta, None, None, None, None, None
 
 
 def residual_layer_norm(x, residual, ln, drop_p=0.0, stream=False):
@@ -554,7 +621,10 @@ def residual_layer_norm(x, residual, ln, drop_p=0.0, stream=False):
         y_f32 = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     if res_f32 is not None and (res_f32.shape != x.shape or not res_f32.is_contiguous()):
         res_f32 = None
-    y = ResidualLayerNormFn.apply(x, residual, ln.weight, ln.bias, ln.eps, drop_p, res_f32, y_f32)
+    holder = getattr(x, "_st5_bias_holder", None)
+    if holder is not None and (holder["n"] != x.shape[-1] or not torch.is_grad_enabled()):
+        holder = None
+    y = ResidualLayerNormFn.apply(x, residual, ln.weight, ln.bias, ln.eps, drop_p, res_f32, y_f32, holder)
     if y_f32 is not None:
         y._st5_f32 = y_f32
     return y
@@ -619,7 +689,7 @@ class AttentionFn(torch.autograd.Function):
         probs = torch.empty((B, H, Tq, p_ld), dtype=probs_dtype, device=dev)
         drop_p = cfg.get("drop_p", 0.0)
         off = RT.next_offset() if drop_p > 0 else 0
-        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        kp = _key_pad_u8(key_pad)
         esz = q_buf.element_size()
         common = dict(
             B=B, H=H, Tq=Tq, Tk=Tk, dtype=K.dtype_id(q_buf), causal=int(cfg.get("causal", False)),
@@ -761,10 +831,15 @@ class AttentionTCFn(torch.autograd.Function):
             # [R, 64] output at the L2
             S = next((c for c in (8, 6, 5, 4, 3, 2) if rows % c == 0 and rows // c >= 512), 1)
             chunk = rows // S
-            dpe = torch.zeros((R, 64), dtype=torch.float32, device=dev)
+            # (straight into the trainer's flat gradient buffer when the table is a registered parameter: no zero fill,
+            # no AccumulateGrad add per layer -- the 12 encoder layers share ONE table)
+            target = RT._static_grad.get(("lin", id(pe_k))) if isinstance(pe_k, torch.nn.Parameter) else None
+            if target is not None and (target.data_ptr() % 16 != 0 or not target.is_contiguous()):
+                target = None
+            dpe = target if target is not None else torch.zeros((R, 64), dtype=torch.float32, device=dev)
             K.gemm(dQP, qv, dpe, M=R, N=64, K=chunk, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=S,
                    a_bs=(rows * R, chunk * R), b_bs=(64, chunk * q_ld), c_bs=(0, 0), alpha=scale, accumulate=2)
-            return dq_buf, None, dpe, None, None
+            return dq_buf, None, (None if target is not None else dpe), None, None
         dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
         K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos)
         qpbs = (Tq * R, H * Tq * R)
@@ -814,7 +889,7 @@ class AttentionTCFn(torch.autograd.Function):
             # written only when the caller asked for them (need_head_weights)
             drop_p = cfg.get("drop_p", 0.0)
             off = RT.next_offset() if drop_p > 0 else 0
-            kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+            kp = _key_pad_u8(key_pad)
             want = bool(cfg.get("return_probs"))
             with_pe = pe_k is not None
             pe_hi = _pe_bf16(pe_k) if with_pe else None
@@ -848,7 +923,7 @@ class AttentionTCFn(torch.autograd.Function):
                    b_bs=(0, 0), c_bs=(Tq * R, H * Tq * R), alpha=scale)
         drop_p = cfg.get("drop_p", 0.0)
         off = RT.next_offset() if drop_p > 0 else 0
-        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        kp = _key_pad_u8(key_pad)
         P = torch.empty((B, H, Tq, p_ld), dtype=torch.bfloat16, device=dev)
         Pd = torch.empty_like(P) if drop_p > 0 else None
         want = bool(cfg.get("return_probs"))

@@ -125,6 +125,27 @@ def ln_fwd(x, residual, gamma, beta, y, s_out, mean, rstd, eps, drop_p=0.0, seed
     rstd.copy_(rs.reshape(-1).float())
 
 
+def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, offset=0, dxsum=None):
+    """st5_ln_bwd without dropout: ds (= dx), dgamma / dbeta accumulated, dxsum += column sums of dx (the producing
+    projection's bias gradient, include/speecht5_b200.h)."""
+    assert drop_p == 0.0
+    C = dy.shape[-1]
+    d = dy.double().reshape(-1, C)
+    xh = (s.double().reshape(-1, C) - mean.double()[:, None]) * rstd.double()[:, None]
+    g = d * gamma.double()
+    r = rstd.double()[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if ds is not None:
+        ds.copy_(r.reshape(ds.shape).to(ds.dtype))
+    if dx is not None:
+        dx.copy_(r.reshape(dx.shape).to(dx.dtype))
+    if dgamma is not None:
+        dgamma.add_((d * xh).sum(0).float())
+    if dbeta is not None:
+        dbeta.add_(d.sum(0).float())
+    if dxsum is not None:
+        dxsum[:C].add_(r.sum(0).float())
+
+
 def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
     """st5_conv0_gn_gelu_fwd: Conv1d(1 -> C, k, stride) + GroupNorm(C groups) + GELU, channels-last output."""
     v = torch.nn.functional.conv1d(wave.double()[:, None], w.double()[:, None], stride=stride)  # [B, C, T0]
@@ -238,6 +259,7 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "act_bwd", act_bwd)
     monkeypatch.setattr(K, "colsum", colsum)
     monkeypatch.setattr(K, "ln_fwd", ln_fwd)
+    monkeypatch.setattr(K, "ln_bwd", ln_bwd)
     monkeypatch.setattr(K, "posenc_fwd", posenc_fwd)
     monkeypatch.setattr(K, "bn_fwd", bn_fwd)
     from speecht5_b200 import ops

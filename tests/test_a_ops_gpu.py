@@ -50,6 +50,39 @@ def test_layer_norm_residual(cuda, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,C,drop_p", [(10016, 768, 0.1), (5120, 768, 0.0), (333, 1024, 0.1), (40, 256, 0.0)])
+def test_layer_norm_backward_column_sums_of_dx(cuda, dtype, rows, C, drop_p):
+    """st5_ln_bwd's dxsum output (the producing projection's bias gradient, include/speecht5_b200.h): += column sums of
+    the dx it writes, dropout included, for 16-byte aligned and unaligned targets; ds / dgamma / dbeta unchanged."""
+    from speecht5_b200 import kernels as K
+    torch.manual_seed(1)
+    dy = torch.randn(rows, C, device=cuda).to(dtype)
+    s = (torch.randn(rows, C, device=cuda) * 2 + 0.3).to(dtype)
+    mean = s.float().mean(-1)
+    rstd = 1.0 / torch.sqrt(s.float().var(-1, unbiased=False) + 1e-5)
+    gamma = torch.rand(C, device=cuda) + 0.5
+    for misalign in (0, 1):
+        ds, dx = torch.empty_like(dy), (torch.empty_like(dy) if drop_p > 0 else None)
+        dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+        buf = torch.full((C + 8,), 0.25, device=cuda)
+        dxsum = buf[misalign:misalign + C]
+        K.ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dg, db, drop_p, 11, 5, dxsum=dxsum)
+        ds2, dx2 = torch.empty_like(dy), (torch.empty_like(dy) if drop_p > 0 else None)
+        dg2, db2 = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+        K.ln_bwd(dy, s, mean, rstd, gamma, ds2, dx2, dg2, db2, drop_p, 11, 5)
+        assert torch.equal(ds, ds2) and (dx is None or torch.equal(dx, dx2))
+        out = dx if dx is not None else ds
+        want = out.double().sum(0) + 0.25
+        # the kernel sums the un-rounded fp32 values, the check the rounded ones: allow the bf16 rounding of `rows` terms
+        tol = 1e-4 if dtype == torch.float32 else 4e-3
+        assert (dxsum.double() - want).abs().max() < tol * out.double().abs().sum(0).max(), (misalign,)
+        assert rel(dg, dg2) < 1e-5 and rel(db, db2) < 1e-5
+        xh = (s.float() - mean[:, None]) * rstd[:, None]
+        assert rel(dg, (dy.float() * xh).sum(0)) < 1e-4 and rel(db, dy.float().sum(0)) < 1e-4
+        assert float(buf[C + misalign:].sub(0.25).abs().max()) == 0 and float(buf[:misalign].sub(0.25).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_linear_autograd(cuda, dtype):
     from speecht5_b200 import ops
     ops.RT.dtype = dtype

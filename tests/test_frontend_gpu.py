@@ -199,6 +199,37 @@ def test_ctc_kernel_against_torch(cuda):
     assert x.grad[:, 3].abs().max().item() == 0.0 and x.grad[100:, 1].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("T,B,V,lens", [(499, 8, 81, (160, 150, 97, 160, 3, 120, 160, 33)),   # the ASR step: S = 321
+                                           (700, 3, 40, (300, 10, 257))])                        # S = 601: sweeps one after the other
+def test_ctc_kernel_long_sequences_against_torch(cuda, T, B, V, lens):
+    """csrc/ctc.cu at the benched ASR shape (alpha / beta recursions side by side in one CTA) and beyond 512 states (the
+    same kernel runs the two recursions one after the other), ragged lengths, vs torch's ctc_loss autograd; also through
+    the padded-target entry the captured step uses."""
+    import torch.nn.functional as F
+    from speecht5_b200.frontend import ctc_loss_sum, ctc_loss_sum_padded
+    torch.manual_seed(5)
+    tl = torch.tensor(lens)
+    il = torch.tensor([T - 7 * (i % 3) for i in range(B)])
+    tg = [torch.randint(1, V, (int(n),)) for n in tl]
+    tg[1][1::3] = tg[1][0::3][:len(tg[1][1::3])]  # some repeated labels
+    flat = torch.cat(tg)
+    logits = (torch.randn(T, B, V) * 2).requires_grad_()
+    ref = F.ctc_loss(F.log_softmax(logits, -1), flat, il, tl, blank=0, reduction="sum", zero_infinity=True)
+    ref.backward()
+    x = logits.detach().to(cuda).requires_grad_()
+    got = ctc_loss_sum(x, flat.to(cuda), il.to(cuda), tl.to(cuda), 0, True)
+    got.backward()
+    assert abs(got.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel(x.grad.cpu(), logits.grad) < 2e-4
+    padded = torch.zeros(B, int(tl.max()), dtype=torch.long)
+    for i, t_ in enumerate(tg):
+        padded[i, :len(t_)] = t_
+    x2 = logits.detach().to(cuda).requires_grad_()
+    got2 = ctc_loss_sum_padded(x2, padded.to(cuda), il.to(cuda), tl.to(cuda), 0, True)
+    got2.backward()
+    assert abs(got2.item() - ref.item()) < 1e-4 * abs(ref.item()) and rel(x2.grad.cpu(), logits.grad) < 2e-4
+
+
 def test_hifigan_on_device_against_the_oracle(cuda):
     """speecht5_b200/vocoder.py with the release configuration (512 channels, 4x4x4x4 up-sampling, ResBlocks 3/7/11 x
     dilations 1/3/5) vs oracle HifiGanGenerator (fp32 CPU) on a short mel: bf16 activations, so a relative L2 bound."""
@@ -321,4 +352,41 @@ def test_speech_pretraining_branch_of_forward(cuda, dtype, tol):
     g = model.speech_encoder_prenet.feature_extractor.conv_layers[0][0].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
     assert torch.isfinite(model.quantizer.vars.grad).all() and torch.isfinite(model.hubert_layer.label_embs_concat.grad).all()
+    if dtype == torch.float32:
+        # the speech pre-training CRITERION (pinned to the reference's own in tests/test_ref_pin_cpu.py) through the
+        # dispatcher on the device model, against the same criterion fed with the oracle composition's outputs
+        from speecht5_b200.criterions import SpeechPretrainCriterion, SpeechT5Criterion
+        L = 2 * prev.shape[1]
+        olens = 2 * tgt_lengths
+        stop = torch.zeros(B, L)
+        for b_ in range(B):
+            stop[b_, int(olens[b_]) - 1:] = 1.0
+        sample = {"id": torch.arange(B), "task_name": "speech_pretrain", "target_list": [labels[0]],
+                  "labels": stop, "dec_target": torch.randn(B, L, 80), "dec_target_lengths": olens,
+                  "src_lengths": torch.tensor([T, T]),
+                  "net_input": dict(source=wave, padding_mask=pad, prev_output_tokens=prev, tgt_lengths=tgt_lengths,
+                                    spkembs=spk, task_name="speech_pretrain", mask_indices=mask_idx)}
+
+        class OracleOutputs(torch.nn.Module):
+            reduction_factor = 2
+            get_logits, get_targets, get_extra_losses = (T5TransformerModel.get_logits, T5TransformerModel.get_targets,
+                                                         T5TransformerModel.get_extra_losses)
+
+            def forward(self, target_list=None, **ni):
+                out = dict(hub_ref, features_pen=fpen_ref, **{k: q[k] for k in ("prob_perplexity", "code_perplexity", "num_vars")})
+                return out, (before_ref, after_ref, logits_ref, None)
+
+        kw = dict(pred_masked_weight=1.0, pred_nomask_weight=0.5, loss_weights=[10.0, 0.1], hubert_weight=1.0, dec_weight=0.5)
+        want, n_want, log_want = SpeechPretrainCriterion(None, True, **kw)(OracleOutputs(), sample)
+        dev_sample = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in sample.items()}
+        dev_sample["target_list"] = [labels[0].to(cuda)]
+        dev_sample["net_input"] = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in sample["net_input"].items()}
+        model.zero_grad()
+        got, n_got, log_got = SpeechT5Criterion(None, **kw)(model, dev_sample)
+        assert n_got == n_want and set(log_got) == set(log_want)
+        assert abs(got.item() - want.item()) < 5e-3 * abs(want.item()), (got.item(), want.item())
+        for k in ("loss_m_0", "loss_u_0", "dec_loss", "l1_loss", "bce_loss", "loss_features_pen", "loss_prob_perplexity"):
+            assert abs(log_got[k] - log_want[k]) < 1e-2 * max(1.0, abs(log_want[k])), (k, log_got[k], log_want[k])
+        (got / n_got).backward()
+        assert torch.isfinite(model.speech_encoder_prenet.feature_extractor.conv_layers[0][0].weight.grad).all()
     RT.dtype = torch.bfloat16

@@ -307,3 +307,76 @@ def test_model_builds_the_opt_in_speech_input_branch():
     with pytest.raises(NotImplementedError):
         plain(source=torch.zeros(1, 4000), padding_mask=torch.zeros(1, 4000, dtype=torch.bool),
               prev_output_tokens=torch.full((1, 3), 2), task_name="s2t")
+
+
+def test_bias_gradient_is_handed_over_to_the_consuming_layer_norm(monkeypatch):
+    """Post-LN tail y = LN(r + W a + b): the bias gradient of the projection (and of fc2 inside ops.ffn) is the column
+    sum of the LayerNorm's dx, which st5_ln_bwd produces in its own pass (dxsum) -- no column-sum launch. Checked on the
+    emulated kernels against plain autograd, with and without a trainer-style static gradient buffer, and that the
+    projection still sums by itself when nobody consumes the hand-over."""
+    import gemm_emulator
+    from speecht5_b200 import kernels as K, ops
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    RT.invalidate_shadows()
+    calls = []
+    real_colsum = K.colsum
+    monkeypatch.setattr(K, "colsum", lambda *a, **k: (calls.append(1), real_colsum(*a, **k))[1])
+    torch.manual_seed(0)
+    d, f = 16, 32
+    proj, fc1, fc2 = torch.nn.Linear(d, d), torch.nn.Linear(d, f), torch.nn.Linear(f, d)
+    ln1, ln2 = torch.nn.LayerNorm(d), torch.nn.LayerNorm(d)
+    a = torch.randn(2, 5, d)
+    r = torch.randn(2, 5, d)
+
+    def ours(fold):
+        for m in (proj, fc1, fc2, ln1, ln2):
+            m.zero_grad()
+        o = ops.linear(a, proj.weight, proj.bias, bias_grad_by_consumer=fold)
+        x = ops.residual_layer_norm(o, r, ln1)
+        o2 = ops.ffn(x, fc1, fc2, "relu", bias_grad_by_consumer=fold)
+        y = ops.residual_layer_norm(o2, x, ln2)
+        (y * torch.arange(d).float()).sum().backward()
+        return {n: p.grad.clone() for n, p in (("pb", proj.bias), ("b2", fc2.bias), ("b1", fc1.bias), ("pw", proj.weight),
+                                               ("g1", ln1.weight))}
+
+    for m in (proj, fc1, fc2, ln1, ln2):
+        m.zero_grad()
+    F = torch.nn.functional
+    x = F.layer_norm(r + F.linear(a, proj.weight, proj.bias), (d,), ln1.weight, ln1.bias)
+    y = F.layer_norm(x + F.linear(F.relu(F.linear(x, fc1.weight, fc1.bias)), fc2.weight, fc2.bias), (d,), ln2.weight, ln2.bias)
+    (y * torch.arange(d).float()).sum().backward()
+    want = dict(pb=proj.bias.grad.clone(), b2=fc2.bias.grad.clone(), b1=fc1.bias.grad.clone(), pw=proj.weight.grad.clone(),
+                g1=ln1.weight.grad.clone())
+    n_plain = None
+    for fold in (False, True):
+        del calls[:]
+        got = ours(fold)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=2e-2, atol=2e-2), (fold, k)  # (bf16 operands in the emulated GEMM)
+        assert torch.allclose(got["pb"], want["pb"], rtol=1e-4, atol=1e-4) or not fold  # the folded sums are fp32-exact
+        if not fold:
+            n_plain = len(calls)
+        else:
+            assert len(calls) == n_plain - 2, (len(calls), n_plain)  # proj.bias and fc2.bias no longer launch a column sum
+    # static gradient buffers (B200Trainer's flat buffer): the LayerNorm kernel accumulates straight into them
+    gpb, gb2 = torch.zeros(d), torch.zeros(d)
+    monkeypatch.setitem(RT._static_grad, ("bias", id(proj.bias)), gpb)
+    monkeypatch.setitem(RT._static_grad, ("bias", id(fc2.bias)), gb2)
+    for m in (proj, fc1, fc2, ln1, ln2):
+        m.zero_grad()
+    o = ops.linear(a, proj.weight, proj.bias, bias_grad_by_consumer=True)
+    xx = ops.residual_layer_norm(o, r, ln1)
+    o2 = ops.ffn(xx, fc1, fc2, "relu", bias_grad_by_consumer=True)
+    yy = ops.residual_layer_norm(o2, xx, ln2)
+    (yy * torch.arange(d).float()).sum().backward()
+    assert proj.bias.grad is None and fc2.bias.grad is None
+    assert torch.allclose(gpb, want["pb"], rtol=2e-2, atol=2e-2) and torch.allclose(gb2, want["b2"], rtol=2e-2, atol=2e-2)
+    # nobody consumes the hand-over: the projection sums its own columns
+    monkeypatch.delitem(RT._static_grad, ("bias", id(proj.bias)))
+    proj.zero_grad()
+    o = ops.linear(a, proj.weight, proj.bias, bias_grad_by_consumer=True)
+    (o * r).sum().backward()
+    assert torch.allclose(proj.bias.grad, r.sum((0, 1)), rtol=1e-5, atol=1e-5)
+    RT.invalidate_shadows()

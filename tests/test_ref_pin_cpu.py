@@ -311,3 +311,123 @@ def test_train_step_returns_the_reference_logging_shape():
     from speecht5_b200.tasks import SpeechT5Task
     src = inspect.getsource(SpeechT5Task.train_step)
     assert 'agg[sample["task_name"]] = logging_output' in src and '"sample_size": 1' in src
+
+
+class _PretrainStub(torch.nn.Module):
+    """A model-shaped object that returns canned tensors: what the pre-training criteria read from a model
+    (models/speecht5.py:731-784 helpers, shared by the reference's criterion and ours, so that the comparison isolates the
+    criterion arithmetic). The forward outputs carry gradients back to `self.leaf` tensors."""
+
+    reduction_factor = 2
+
+    def __init__(self, seed, text=False):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        B, T, r, odim, V = 3, 11, 2, 80, 37
+        self.text = text
+        if text:
+            self.logits = torch.nn.Parameter(torch.randn(B, 9, V, generator=g))
+            self.pp = torch.nn.Parameter(torch.tensor(12.5))
+        else:
+            self.lm = torch.nn.Parameter(torch.randn(17, 101, generator=g))
+            self.lu = torch.nn.Parameter(torch.randn(40, 101, generator=g))
+            self.pen = torch.nn.Parameter(torch.tensor(0.37))
+            self.pp = torch.nn.Parameter(torch.tensor(55.0))
+            self.before = torch.nn.Parameter(torch.randn(B, T * r, odim, generator=g))
+            self.after = torch.nn.Parameter(torch.randn(B, T * r, odim, generator=g))
+            self.stop = torch.nn.Parameter(torch.randn(B, T * r, generator=g))
+        self.calls = []
+
+    def forward(self, target_list=None, **net_input):
+        self.calls.append(dict(net_input, has_targets=target_list is not None))
+        if self.text:
+            return (self.logits, None), {"prob_perplexity": self.pp, "code_perplexity": torch.tensor(7.0), "num_vars": 200,
+                                         "temp": 2.0}, {"encoder_out": [None]}
+        out = {"logit_m_list": [self.lm], "logit_u_list": [self.lu], "features_pen": self.pen, "prob_perplexity": self.pp,
+               "code_perplexity": torch.tensor(31.0), "num_vars": 200, "temp": torch.tensor(2.0)}
+        if net_input.get("only_hubert"):
+            return out, None
+        attn = torch.softmax(torch.zeros(3, 12, 11, 6), -1)
+        return out, (self.before, self.after, self.stop, [attn, attn])
+
+    from speecht5_b200.models.speecht5 import T5TransformerModel as _M
+    get_logits, get_targets, get_extra_losses = _M.get_logits, _M.get_targets, _M.get_extra_losses
+    get_normalized_probs = _M.get_normalized_probs
+
+
+def _speech_pretrain_sample():
+    g = torch.Generator().manual_seed(9)
+    B, L, odim = 3, 22, 80
+    lens = torch.tensor([22, 18, 13])
+    labels = torch.zeros(B, L)
+    for b, n in enumerate(lens):
+        labels[b, n - 1:] = 1.0
+    return {"id": torch.arange(B), "target_list": [torch.zeros(B, 30, dtype=torch.long)], "net_input": {"source": None},
+            "labels": labels, "dec_target": torch.randn(B, L, odim, generator=g), "dec_target_lengths": lens,
+            "src_lengths": torch.tensor([6, 5, 4]), "task_name": "speech_pretrain"}
+
+
+def _close(a, b, tol=1e-5):
+    a, b = float(a), float(b)
+    return abs(a - b) <= tol * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("dec_weight,nomask,weights", [(1.0, 0.0, [10.0]), (0.0, 0.5, [10.0, 0.1]), (0.5, 1.0, [10.0, 0.1, 3.0]),
+                                                       (1.0, 0.0, None)])
+def test_speech_pretrain_criterion_equals_the_reference_criterion(dec_weight, nomask, weights):
+    """speecht5_b200/criterions/speech_pretrain_criterion.py against the reference's own SpeechPretrainCriterion
+    (speech_pretrain_criterion.py:50-190, loaded unmodified): loss, sample size, every logging key and the gradients on
+    the model outputs, with / without the decoder branch, the unmasked term and 1 / 2 / 3 configured extra weights."""
+    import importlib
+    from speecht5_b200.criterions import SpeechPretrainCriterion
+    rl.load()
+    ref_mod = importlib.import_module("speecht5.criterions.speech_pretrain_criterion")
+    task = rl.RefTask(mg.VOCAB, "pretrain")
+    kw = dict(pred_masked_weight=1.0, pred_nomask_weight=nomask, loss_weights=None if weights is None else list(weights),
+              log_keys=["temp"], hubert_weight=0.7, dec_weight=dec_weight)
+    ref_crit = ref_mod.SpeechPretrainCriterion(task, True, **kw)
+    kw["loss_weights"] = None if weights is None else list(weights)
+    our_crit = SpeechPretrainCriterion(task, True, **kw)
+    ms_ref, ms_our = _PretrainStub(4), _PretrainStub(4)
+    want, n_want, log_want = ref_crit(ms_ref, _speech_pretrain_sample())
+    got, n_got, log_got = our_crit(ms_our, _speech_pretrain_sample())
+    assert n_got == n_want and _close(got, want)
+    assert set(log_got) == set(log_want), (sorted(log_got), sorted(log_want))
+    for k in log_want:
+        assert _close(log_got[k], log_want[k]), (k, log_got[k], log_want[k])
+    assert ms_our.calls[0].get("only_hubert", False) == ms_ref.calls[0].get("only_hubert", False) == (dec_weight == 0)
+    want.backward()
+    got.backward()
+    for (n, p), q in zip(ms_ref.named_parameters(), ms_our.parameters()):
+        if p.grad is None:
+            assert q.grad is None, n
+        else:
+            assert torch.allclose(q.grad, p.grad, rtol=1e-5, atol=1e-7), n
+
+
+@pytest.mark.parametrize("sentence_avg,weights", [(False, [0.1]), (True, [0.1]), (False, [0.1, 2.0])])
+def test_text_pretrain_criterion_equals_the_reference_criterion(sentence_avg, weights):
+    """speecht5_b200/criterions/text_pretrain_criterion.py against the reference's TextPretrainCriterion
+    (text_pretrain_criterion.py:36-105): padded targets, both sample-size modes, and the reference's weight-list rule
+    when more weights than extra terms are configured (it keeps the tail, :74-75)."""
+    import importlib
+    from speecht5_b200.criterions import TextPretrainCriterion
+    rl.load()
+    ref_mod = importlib.import_module("speecht5.criterions.text_pretrain_criterion")
+    task = rl.RefTask(mg.VOCAB, "pretrain")
+    pad = task.target_dictionary.pad()
+    tgt = torch.randint(4, 37, (3, 9), generator=torch.Generator().manual_seed(2))
+    tgt[1, 6:] = pad
+    tgt[2, 3:] = pad
+    sample = {"net_input": {"src_tokens": None}, "target": tgt, "ntokens": int(tgt.ne(pad).sum()), "task_name": "text_pretrain"}
+    ms_ref, ms_our = _PretrainStub(6, text=True), _PretrainStub(6, text=True)
+    want, n_want, log_want = ref_mod.TextPretrainCriterion(task, sentence_avg, 0.9, list(weights))(ms_ref, sample)
+    got, n_got, log_got = TextPretrainCriterion(task, sentence_avg, 0.9, list(weights))(ms_our, sample)
+    assert n_got == n_want and _close(got, want)
+    assert set(log_got) == set(log_want), (sorted(log_got), sorted(log_want))
+    for k in log_want:
+        assert _close(log_got[k], log_want[k]), (k, log_got[k], log_want[k])
+    want.backward()
+    got.backward()
+    assert torch.allclose(ms_our.logits.grad, ms_ref.logits.grad, rtol=1e-5, atol=1e-7)
+    assert (ms_ref.pp.grad is None and ms_our.pp.grad is None) or torch.allclose(ms_our.pp.grad, ms_ref.pp.grad)
