@@ -249,6 +249,34 @@ int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t*
                  const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,
                  int32_t T, int32_t B, int32_t V, int32_t S_max, int32_t blank, int32_t zero_infinity, void* stream);
 
+/* ------------------------------------------------------------------------------------------------- TTS criterion
+ * The reductions of speecht5/criterions/text_to_speech_loss.py and their gradients.
+ * st5_tts_loss_fwd: Tacotron2Loss with use_masking (:217-345). after / before [B, L, D] fp32 contiguous, logits [B, L],
+ * ys: element (b, l, c) at b*y_bs + l*D + c (the target tensor may be longer than L), labels: (b, l) at b*lab_bs + l,
+ * olens int64 [B] (frames; the valid region of utterance b is l < olens[b] - olens[b] % r, and for r > 1 the stop label
+ * of its last valid frame counts as 1, :161-166). out[0..2] = l1, l2, bce (means over valid frames, l1 / l2 also over D);
+ * sums[4] is scratch that st5_tts_loss_bwd reads back (sums[3] = number of valid frames).
+ * st5_tts_loss_bwd: g[3] = upstream gradients of (l1, l2, bce) in device memory; writes d_after, d_before [B, L, D] and
+ * d_logits [B, L] everywhere (zeros outside the masks). */
+int st5_tts_loss_fwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                     const float* labels, int64_t lab_bs, const int64_t* olens, int32_t B, int32_t L, int32_t D,
+                     int32_t r, float pos_weight, float* sums, float* out, void* stream);
+int st5_tts_loss_bwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                     const float* labels, int64_t lab_bs, const int64_t* olens, const float* sums, const float* g,
+                     int32_t B, int32_t L, int32_t D, int32_t r, float pos_weight, float* d_after, float* d_before,
+                     float* d_logits, void* stream);
+/* GuidedMultiHeadAttentionLoss (text_to_speech_loss.py:370-427) over the first `heads` heads of n_layers (<= 8) returned cross-attention
+ * probability tensors att[i] = [B, H, T_out, p_ld] fp32: out[0] = alpha * sum_valid W * A / (sum_b il_b * ol_b * heads *
+ * n_layers), W = 1 - exp(-(t_in / il - t_out / ol)^2 / (2 sigma^2)), ol = olens[b] / r, il = ilens[b]. gsum[2]: scratch
+ * read back by the backward, which writes datt[i] (same layout) = g[0] * d out / d att on heads < `heads`; the other
+ * heads are cleared only with zero_rest != 0 (st5_attn_fused_bwd with ext_heads never reads them). */
+int st5_guided_attn_fwd(const float* const* att, int32_t n_layers, int32_t B, int32_t H, int32_t heads, int32_t T_out,
+                        int32_t T_in, int64_t p_ld, const int64_t* ilens, const int64_t* olens, int32_t r, float sigma,
+                        float alpha, float* gsum, float* out, void* stream);
+int st5_guided_attn_bwd(float* const* datt, int32_t n_layers, int32_t B, int32_t H, int32_t heads, int32_t T_out,
+                        int32_t T_in, int64_t p_ld, const int64_t* ilens, const int64_t* olens, int32_t r, float sigma,
+                        float alpha, const float* gsum, const float* g, int32_t zero_rest, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- optimizer
  * Replaces fairseq/optim/adam.py + fp16_optimizer.py:106-218 on a flat fp32 parameter buffer: one pass applies the
  * gradient scale (grad_mul x clip coefficient max_norm / (norm + 1e-6) capped at 1: fairseq/utils.py clip_grad_norm_,

@@ -155,6 +155,36 @@ int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, con
                    "st5_conv0_gn_gelu_bwd");
 }
 
+int st5_tts_loss_fwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                     const float* labels, int64_t lab_bs, const int64_t* olens, int32_t B, int32_t L, int32_t D,
+                     int32_t r, float pos_weight, float* sums, float* out, void* stream) {
+  return set_error(tts_loss_fwd_launch(after, before, logits, ys, y_bs, labels, lab_bs, olens, B, L, D, r, pos_weight, sums,
+                                       out, (cudaStream_t)stream),
+                   "st5_tts_loss_fwd");
+}
+int st5_tts_loss_bwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                     const float* labels, int64_t lab_bs, const int64_t* olens, const float* sums, const float* g,
+                     int32_t B, int32_t L, int32_t D, int32_t r, float pos_weight, float* d_after, float* d_before,
+                     float* d_logits, void* stream) {
+  return set_error(tts_loss_bwd_launch(after, before, logits, ys, y_bs, labels, lab_bs, olens, sums, g, B, L, D, r,
+                                       pos_weight, d_after, d_before, d_logits, (cudaStream_t)stream),
+                   "st5_tts_loss_bwd");
+}
+int st5_guided_attn_fwd(const float* const* att, int32_t n_layers, int32_t B, int32_t H, int32_t heads, int32_t T_out,
+                        int32_t T_in, int64_t p_ld, const int64_t* ilens, const int64_t* olens, int32_t r, float sigma,
+                        float alpha, float* gsum, float* out, void* stream) {
+  return set_error(guided_attn_fwd_launch(att, n_layers, B, H, heads, T_out, T_in, p_ld, ilens, olens, r, sigma, alpha,
+                                          gsum, out, (cudaStream_t)stream),
+                   "st5_guided_attn_fwd");
+}
+int st5_guided_attn_bwd(float* const* datt, int32_t n_layers, int32_t B, int32_t H, int32_t heads, int32_t T_out,
+                        int32_t T_in, int64_t p_ld, const int64_t* ilens, const int64_t* olens, int32_t r, float sigma,
+                        float alpha, const float* gsum, const float* g, int32_t zero_rest, void* stream) {
+  return set_error(guided_attn_bwd_launch(datt, n_layers, B, H, heads, T_out, T_in, p_ld, ilens, olens, r, sigma, alpha,
+                                          gsum, g, zero_rest, (cudaStream_t)stream),
+                   "st5_guided_attn_bwd");
+}
+
 int64_t st5_ctc_ws_floats(int32_t T, int32_t B, int32_t S_max) { return ctc_ws_floats(T, B, S_max); }
 int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
                  const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,

@@ -129,6 +129,19 @@ int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, cons
 int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
                      const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
                      int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
+int tts_loss_fwd_launch(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                        const float* labels, int64_t lab_bs, const int64_t* olens, int B, int L, int D, int r,
+                        float pos_weight, float* sums, float* out, cudaStream_t s);
+int tts_loss_bwd_launch(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
+                        const float* labels, int64_t lab_bs, const int64_t* olens, const float* sums, const float* g,
+                        int B, int L, int D, int r, float pos_weight, float* d_after, float* d_before, float* d_logits,
+                        cudaStream_t s);
+int guided_attn_fwd_launch(const float* const* att, int n_layers, int B, int H, int heads, int T_out, int T_in,
+                           int64_t p_ld, const int64_t* ilens, const int64_t* olens, int r, float sigma, float alpha,
+                           float* gsum, float* out, cudaStream_t s);
+int guided_attn_bwd_launch(float* const* datt, int n_layers, int B, int H, int heads, int T_out, int T_in, int64_t p_ld,
+                           const int64_t* ilens, const int64_t* olens, int r, float sigma, float alpha,
+                           const float* gsum, const float* g, int zero_rest, cudaStream_t s);
 int64_t ctc_ws_floats(int32_t T, int32_t B, int32_t S_max);
 int ctc_loss_launch(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t* targets, const int64_t* tgt_offsets,
                     const int64_t* input_lengths, const int64_t* target_lengths, float* nll, float* grad, float* ws,

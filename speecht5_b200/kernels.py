@@ -298,6 +298,65 @@ def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, g
     _count(3 if grad is not None else 2)
 
 
+def tts_loss_fwd(after, before, logits, ys, labels, olens, r, pos_weight, sums, out):
+    """st5_tts_loss_fwd: out[0..2] = l1, l2, bce of Tacotron2Loss (masked means); after / before [B, L, D] fp32."""
+    _require_cuda(after, before, logits, ys, labels, olens, sums, out)
+    B, L, D = after.shape
+    for t in (after, before, logits):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert ys.dtype == torch.float32 and ys.stride(2) == 1 and ys.stride(1) == D and ys.shape[1] >= L
+    assert labels.dtype == torch.float32 and labels.stride(1) == 1 and olens.dtype == torch.int64 and olens.is_contiguous()
+    _lib.check(_lib.load().st5_tts_loss_fwd(_ptr(after), _ptr(before), _ptr(logits), _ptr(ys), ys.stride(0), _ptr(labels),
+                                            labels.stride(0), _ptr(olens), B, L, D, r, pos_weight, _ptr(sums), _ptr(out),
+                                            _stream()), "st5_tts_loss_fwd")
+    _count(2)
+
+
+def tts_loss_bwd(after, before, logits, ys, labels, olens, sums, g, r, pos_weight, d_after, d_before, d_logits):
+    _require_cuda(after, g, d_after)
+    B, L, D = after.shape
+    assert g.dtype == torch.float32 and g.is_contiguous() and g.numel() == 3
+    for t in (d_after, d_before, d_logits):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _lib.check(_lib.load().st5_tts_loss_bwd(_ptr(after), _ptr(before), _ptr(logits), _ptr(ys), ys.stride(0), _ptr(labels),
+                                            labels.stride(0), _ptr(olens), _ptr(sums), _ptr(g), B, L, D, r, pos_weight,
+                                            _ptr(d_after), _ptr(d_before), _ptr(d_logits), _stream()), "st5_tts_loss_bwd")
+    _count(1)
+
+
+def _att_layout(atts):
+    B, H, T_out, T_in = atts[0].shape
+    p_ld = atts[0].stride(2)
+    for a in atts:
+        assert a.dtype == torch.float32 and a.shape == atts[0].shape and a.stride(3) == 1 and a.stride(2) == p_ld
+        assert a.stride(1) == T_out * p_ld and a.stride(0) == H * T_out * p_ld, "attention probabilities: [B,H,T_out,p_ld] pitch"
+    ptrs = (C.c_void_p * len(atts))(*[a.data_ptr() for a in atts])
+    return B, H, T_out, T_in, p_ld, ptrs
+
+
+def guided_attn_fwd(atts, heads, ilens, olens, r, sigma, alpha, gsum, out):
+    """st5_guided_attn_fwd over the first `heads` heads of each tensor in `atts` ([B, H, T_out, T_in] fp32 views)."""
+    _require_cuda(atts[0], ilens, olens, gsum, out)
+    B, H, T_out, T_in, p_ld, ptrs = _att_layout(atts)
+    assert ilens.dtype == torch.int64 and olens.dtype == torch.int64 and ilens.is_contiguous() and olens.is_contiguous()
+    _lib.check(_lib.load().st5_guided_attn_fwd(ptrs, len(atts), B, H, heads, T_out, T_in, p_ld, _ptr(ilens), _ptr(olens),
+                                               r, sigma, alpha, _ptr(gsum), _ptr(out), _stream()), "st5_guided_attn_fwd")
+    _count(2)
+
+
+def guided_attn_bwd(datts, heads, T_in, ilens, olens, r, sigma, alpha, gsum, g, zero_rest):
+    """datts: [B, H, T_out, p_ld] fp32 contiguous buffers (p_ld >= T_in)."""
+    _require_cuda(datts[0], gsum, g)
+    B, H, T_out, p_ld = datts[0].shape
+    for d in datts:
+        assert d.dtype == torch.float32 and d.is_contiguous() and d.shape == datts[0].shape
+    ptrs = (C.c_void_p * len(datts))(*[d.data_ptr() for d in datts])
+    _lib.check(_lib.load().st5_guided_attn_bwd(ptrs, len(datts), B, H, heads, T_out, T_in, p_ld, _ptr(ilens), _ptr(olens),
+                                               r, sigma, alpha, _ptr(gsum), _ptr(g), int(zero_rest), _stream()),
+               "st5_guided_attn_bwd")
+    _count(1)
+
+
 def sumsq(x, out):
     lib = _lib.load()
     _lib.check(lib.st5_sumsq(_ptr(x), x.numel(), _ptr(out), _stream()), "st5_sumsq")

@@ -455,7 +455,25 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         ys = torch.zeros(1, 1, odim, dtype=torch.float32, device=src_tokens.device)
         outs, probs, attns, idx = [], [], [], 0
         cache = None
-        if kwargs.get("use_cache", False):  # EXPERIMENTAL key/value cache (speecht5_b200/incremental.py)
+        if kwargs.get("use_cache", False) in ("graph", "graph_body_eager"):
+            # key/value cache + ONE captured CUDA graph per decoder step (speecht5_b200/incremental.py SynthesisGraph):
+            # the host replays and reads the stop flag, nothing else
+            from ..incremental import SynthesisGraph
+            seed_t = RT._seed_t
+            try:
+                sg = SynthesisGraph(self, encoder_out, spkembs, maxlen, threshold,
+                                    capture=kwargs["use_cache"] == "graph")
+                while True:
+                    idx += 1
+                    stop = sg.step(idx - 1)
+                    if stop or idx >= maxlen:
+                        if idx < minlen:
+                            continue
+                        mel = post.refine(sg.outs[:idx].reshape(1, idx * r, odim))[0]
+                        return mel, sg.probs[:idx].reshape(-1).clone(), sg.attn[:idx].permute(1, 2, 0, 3).contiguous()
+            finally:
+                RT._seed_t = seed_t
+        if kwargs.get("use_cache", False):  # key/value cache, eager step (speecht5_b200/incremental.py)
             from ..incremental import DecoderCache, decoder_step
             cache = DecoderCache(self.decoder, encoder_out, max(maxlen, 1) + 1)
         while True:

@@ -908,6 +908,7 @@ class AttentionTCFn(torch.autograd.Function):
             ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
             ctx.fused = (out, psave, inv_l, o32, kp)
             ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
+            cfg["_ext_ok"] = True  # this call's backward reads an external dP through the first probs_grad_heads heads only
             if probs is None:
                 return out, None
             return out, probs[..., :Tk] if p_ld != Tk else probs
@@ -1013,7 +1014,12 @@ def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, max
     Tk = (q_buf if kv_buf is None else kv_buf).shape[1]
     streaming = RT.attn_flash and RT.attn_fused and RT.attn_fused_bwd and (pe_k is None or not causal)
     if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and (Tk <= 512 or streaming):
-        return AttentionTCFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
+        out, probs = AttentionTCFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
+        if probs is not None and cfg.get("_ext_ok") and cfg["probs_grad_heads"] > 0:
+            # tells a producer of dP (criterions.text_to_speech_loss.GuidedAttnFn) that heads >= n are never read: it
+            # may leave them unwritten instead of clearing 10 of 12 heads of a [B,H,Tq,Tk] fp32 tensor
+            probs._st5_ext_heads = cfg["probs_grad_heads"]
+        return out, probs
     return AttentionFn.apply(q_buf, kv_buf, pe_k, key_pad, cfg)
 
 

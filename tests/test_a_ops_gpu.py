@@ -544,3 +544,62 @@ def test_cross_attention_backward_with_a_gradient_on_two_heads_only(cuda):
         res.append((qb.grad, kvb.grad))
     ops.RT.probs_grad_heads = 0
     assert rel(res[1][0], res[0][0]) < 1e-6 and rel(res[1][1], res[0][1]) < 1e-6
+
+
+@pytest.mark.parametrize("r,B,L,D,Ly", [(2, 5, 62, 80, 64), (1, 3, 33, 80, 33), (2, 4, 20, 30, 27)])
+def test_fused_tts_criterion_kernels_against_the_torch_formulation(cuda, r, B, L, D, Ly):
+    """csrc/criterion.cu through TacotronLossFn: (l1, l2, bce) and their gradients vs Tacotron2Loss (the broadcast torch
+    statement of text_to_speech_loss.py:217-345) in fp64 -- ragged lengths, lengths that are not multiples of r, targets
+    longer than the output, the forced stop label of the last valid frame, odd feature widths (scalar path)."""
+    from speecht5_b200.criterions.text_to_speech_loss import Tacotron2Loss, TacotronLossFn
+    torch.manual_seed(3)
+    after = torch.randn(B, L, D, device=cuda).requires_grad_()
+    before = torch.randn(B, L, D, device=cuda).requires_grad_()
+    logits = (torch.randn(B, L, device=cuda) * 2).requires_grad_()
+    ys = torch.randn(B, Ly, D, device=cuda)
+    olens = torch.tensor([L, L - 1, max(r, L // 2), r, L - 3][:B], device=cuda)
+    labels = torch.zeros(B, Ly, device=cuda)
+    for b in range(B):
+        labels[b, int(olens[b]) - 1:] = 1.0
+    got = TacotronLossFn.apply(after, before, logits, ys, labels, olens, r, 5.0)
+    w = torch.tensor([1.0, 0.3, 0.7], device=cuda)
+    (got * w).sum().backward()
+    a64, b64, l64 = (t.detach().double().requires_grad_() for t in (after, before, logits))
+    ol = olens - olens % r
+    y64, lab64 = ys[:, :L].double(), labels[:, :L].double().clone()
+    if r > 1:
+        lab64 = torch.scatter(lab64, 1, (ol - 1).unsqueeze(1), 1.0)
+    want = torch.stack(Tacotron2Loss(bce_pos_weight=5.0).to(cuda).double()(a64, b64, l64, y64, lab64, ol))
+    (want * w.double()).sum().backward()
+    assert rel(got, want) < 1e-5
+    assert rel(after.grad, a64.grad) < 1e-5 and rel(before.grad, b64.grad) < 1e-5 and rel(logits.grad, l64.grad) < 1e-5
+    assert float(after.grad[1, L - 1].abs().max()) == 0.0  # (a masked frame)
+
+
+@pytest.mark.parametrize("T_in,sparse", [(160, True), (160, False), (37, False)])
+def test_fused_guided_attention_kernels_against_the_torch_formulation(cuda, T_in, sparse):
+    """GuidedAttnFn vs GuidedMultiHeadAttentionLoss over torch.cat of the head slices (text_to_speech_loss.py:370-427):
+    several layers read in place, a row pitch that differs from T_in, and the backward with / without touching the heads
+    the attention backward never reads."""
+    from speecht5_b200.criterions.text_to_speech_loss import GuidedAttnFn, GuidedMultiHeadAttentionLoss
+    torch.manual_seed(4)
+    B, H, T_out, heads, r = 3, 12, 41, 2, 2
+    p_ld = (T_in + 7) // 8 * 8
+    bufs = [torch.rand(B, H, T_out, p_ld, device=cuda) for _ in range(3)]
+    atts = [(b[..., :T_in] if p_ld != T_in else b).requires_grad_() for b in bufs]
+    if sparse:
+        for a in atts:
+            a._st5_ext_heads = heads
+    ilens = torch.tensor([T_in, T_in - 5, 9], device=cuda)
+    olens = torch.tensor([2 * T_out, 2 * T_out - 3, 30], device=cuda)
+    got = GuidedAttnFn.apply(ilens, olens, r, heads, 0.4, 1.0, *atts)
+    grads = torch.autograd.grad(got * 3.0, atts)
+    ref_in = [a.detach().double().requires_grad_() for a in atts]
+    want = GuidedMultiHeadAttentionLoss(0.4, 1.0)(torch.cat([a[:, :heads] for a in ref_in], 1), ilens,
+                                                  torch.div(olens, r, rounding_mode="floor"))
+    ref_grads = torch.autograd.grad(want * 3.0, ref_in)
+    assert abs(got.item() - want.item()) < 1e-5 * abs(want.item())
+    for g, rg in zip(grads, ref_grads):
+        assert rel(g[:, :heads], rg[:, :heads]) < 1e-5
+        if not sparse:
+            assert float(g[:, heads:].abs().max()) == 0.0

@@ -213,21 +213,26 @@ def test_ctc_kernel_long_sequences_against_torch(cuda, T, B, V, lens):
     tg = [torch.randint(1, V, (int(n),)) for n in tl]
     tg[1][1::3] = tg[1][0::3][:len(tg[1][1::3])]  # some repeated labels
     flat = torch.cat(tg)
-    logits = (torch.randn(T, B, V) * 2).requires_grad_()
+    # fp64 reference: an fp32 log-domain lattice holds values of magnitude T * log V ~ 2000, i.e. 1 ulp = 1e-4 .. 2.5e-4
+    # absolute = the relative error of every posterior term; torch's own fp32 path is measured next to ours
+    logits = (torch.randn(T, B, V) * 2).double().requires_grad_()
     ref = F.ctc_loss(F.log_softmax(logits, -1), flat, il, tl, blank=0, reduction="sum", zero_infinity=True)
     ref.backward()
-    x = logits.detach().to(cuda).requires_grad_()
+    l32 = logits.detach().float().requires_grad_()
+    F.ctc_loss(F.log_softmax(l32, -1), flat, il, tl, blank=0, reduction="sum", zero_infinity=True).backward()
+    torch_fp32_err = rel(l32.grad, logits.grad)
+    x = logits.detach().float().to(cuda).requires_grad_()
     got = ctc_loss_sum(x, flat.to(cuda), il.to(cuda), tl.to(cuda), 0, True)
     got.backward()
     assert abs(got.item() - ref.item()) < 1e-4 * abs(ref.item())
-    assert rel(x.grad.cpu(), logits.grad) < 2e-4
+    assert rel(x.grad.cpu(), logits.grad) < max(2e-3, 4 * torch_fp32_err), (rel(x.grad.cpu(), logits.grad), torch_fp32_err)
     padded = torch.zeros(B, int(tl.max()), dtype=torch.long)
     for i, t_ in enumerate(tg):
         padded[i, :len(t_)] = t_
-    x2 = logits.detach().to(cuda).requires_grad_()
+    x2 = logits.detach().float().to(cuda).requires_grad_()
     got2 = ctc_loss_sum_padded(x2, padded.to(cuda), il.to(cuda), tl.to(cuda), 0, True)
     got2.backward()
-    assert abs(got2.item() - ref.item()) < 1e-4 * abs(ref.item()) and rel(x2.grad.cpu(), logits.grad) < 2e-4
+    assert abs(got2.item() - ref.item()) < 1e-4 * abs(ref.item()) and rel(x2.grad, x.grad) < 1e-5
 
 
 def test_hifigan_on_device_against_the_oracle(cuda):
@@ -264,8 +269,40 @@ def test_kv_cache_synthesis_equals_prefix_recomputation(cuda):
     spk = torch.randn(1, 512, device=cuda)
     plain = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9)
     cached = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9, use_cache=True)
-    for a, b in zip(plain, cached):
-        assert a.shape == b.shape and rel(b, a) < 1e-4
+    graphed = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=0.9, use_cache="graph")  # one replay per step
+    for a, b, c in zip(plain, cached, graphed):
+        assert a.shape == b.shape == c.shape and rel(b, a) < 1e-4 and rel(c, b) < 1e-5
+    RT.dtype = torch.bfloat16
+
+
+def test_graph_captured_synthesis_in_throughput_mode(cuda):
+    """SynthesisGraph (speecht5_b200/incremental.py) in bf16 with the always-on prenet dropout: more steps than one span
+    bucket (two graphs), a new dropout mask per replay from the device-resident seed (steps with identical inputs give
+    different frames), and the same seed gives the same utterance again."""
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.bfloat16
+    RT.invalidate_shadows()
+    torch.manual_seed(5)
+    tts = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", encoder_layers=2, decoder_layers=2,
+                                                   bert_init=True)).to(cuda).eval()
+    tok = torch.randint(4, 81, (1, 150), device=cuda)
+    spk = torch.randn(1, 512, device=cuda)
+    runs = []
+    for _ in range(2):
+        RT.manual_seed(7)
+        runs.append(tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=2.0, use_cache="graph"))  # maxlen = 150 steps
+    mel, probs, attn = runs[0]
+    assert mel.shape == (300, 80) and probs.shape == (300,) and attn.shape == (2, 12, 150, 150)
+    assert torch.isfinite(mel).all() and torch.isfinite(attn).all()
+    assert (attn.sum(-1) - 1).abs().max() < 1e-3
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)
+    RT.manual_seed(8)
+    other = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=2.0, use_cache="graph")
+    assert not torch.equal(other[0], mel)  # (another seed: other prenet masks)
+    eager = tts.generate_speech(src_tokens=tok, spkembs=spk, threshold=2.0, use_cache=True)
+    assert eager[0].shape == mel.shape
     RT.dtype = torch.bfloat16
 
 

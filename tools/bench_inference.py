@@ -44,7 +44,7 @@ def main():
     T_text = args.steps  # maxlen = int(T_text * 2.0 / 2) = T_text
     tok = torch.randint(4, 81, (1, T_text), device=dev)
     spk = torch.randn(1, 512, device=dev)
-    for name, kw in (("prefix", {}), ("kv_cache", dict(use_cache=True))):
+    for name, kw in (("prefix", {}), ("kv_cache", dict(use_cache=True)), ("kv_cache_graph", dict(use_cache="graph"))):
         ms = cuda_ms(lambda: model.generate_speech(src_tokens=tok, spkembs=spk, threshold=2.0, **kw), reps=2)
         out[f"generate_speech_{name}"] = dict(ms=ms, decoder_steps=args.steps, ms_per_step=ms / args.steps)
     # ---- row 16: HiFi-GAN, 8 s of audio per utterance (500 frames), batch 4

@@ -68,6 +68,10 @@ def main():
                 if fn.startswith(ROOT) and "/tools/" not in fn and not fn.endswith("bench.py"):
                     site = f"{fn[len(ROOT) + 1:]}:{fr.lineno} {fr.name}"
                     break
+            if site == "?":  # issued by one of autograd's built-in nodes: name the node and the tensor it produced
+                node = torch._C._current_autograd_node()
+                first = next((t for t in flat if isinstance(t, torch.Tensor)), None)
+                site = f"? autograd node {type(node).__name__ if node is not None else None} {tuple(first.shape) if first is not None else ''}"
             sites[(site, short)] += 1
             return out
 
