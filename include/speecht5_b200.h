@@ -152,6 +152,9 @@ typedef struct st5_attn_args {
   float* ds;                   /* scratch [B,H,Tq,p_ld] fp32 */
   void* dq; void* dk; void* dv;/* same layouts as q, k, v */
   float* dpe_k;                /* [2*maxpos][64] fp32, accumulated (+=) */
+  /* fused / flash forward only: > 0 = write `probs` for heads < probs_heads only (the caller reads no others: the
+   * guided-attention loss, text_to_speech_loss.py:210-212); the rest of the buffer is left untouched */
+  int32_t probs_heads;
 } st5_attn_args;
 int st5_attn_fwd(const st5_attn_args* args, void* stream);
 int st5_attn_bwd(const st5_attn_args* args, void* stream);
@@ -255,9 +258,12 @@ int st5_ctc_loss(const float* logits, int64_t ld_t, int64_t ld_b, const int64_t*
  * ys: element (b, l, c) at b*y_bs + l*D + c (the target tensor may be longer than L), labels: (b, l) at b*lab_bs + l,
  * olens int64 [B] (frames; the valid region of utterance b is l < olens[b] - olens[b] % r, and for r > 1 the stop label
  * of its last valid frame counts as 1, :161-166). out[0..2] = l1, l2, bce (means over valid frames, l1 / l2 also over D);
- * sums[4] is scratch that st5_tts_loss_bwd reads back (sums[3] = number of valid frames).
- * st5_tts_loss_bwd: g[3] = upstream gradients of (l1, l2, bce) in device memory; writes d_after, d_before [B, L, D] and
+ * sums: scratch of st5_tts_loss_ws_floats(B, L) floats that st5_tts_loss_bwd reads back (sums[3] = number of valid
+ * frames; the rest holds per-CTA partials, added in a fixed order: same inputs, same bits).
+ * st5_tts_loss_bwd (gradient of text_to_speech_loss.py:288-330): g[3] = upstream gradients of (l1, l2, bce) in device memory; writes d_after, d_before [B, L, D] and
  * d_logits [B, L] everywhere (zeros outside the masks). */
+int64_t st5_tts_loss_ws_floats(int32_t B, int32_t L);
+int64_t st5_guided_attn_ws_floats(int32_t n_layers, int32_t B, int32_t heads, int32_t T_out);
 int st5_tts_loss_fwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
                      const float* labels, int64_t lab_bs, const int64_t* olens, int32_t B, int32_t L, int32_t D,
                      int32_t r, float pos_weight, float* sums, float* out, void* stream);
@@ -267,7 +273,8 @@ int st5_tts_loss_bwd(const float* after, const float* before, const float* logit
                      float* d_logits, void* stream);
 /* GuidedMultiHeadAttentionLoss (text_to_speech_loss.py:370-427) over the first `heads` heads of n_layers (<= 8) returned cross-attention
  * probability tensors att[i] = [B, H, T_out, p_ld] fp32: out[0] = alpha * sum_valid W * A / (sum_b il_b * ol_b * heads *
- * n_layers), W = 1 - exp(-(t_in / il - t_out / ol)^2 / (2 sigma^2)), ol = olens[b] / r, il = ilens[b]. gsum[2]: scratch
+ * n_layers), W = 1 - exp(-(t_in / il - t_out / ol)^2 / (2 sigma^2)), ol = olens[b] / r, il = ilens[b]. gsum: scratch of
+ * st5_guided_attn_ws_floats(n_layers, B, heads, T_out) floats (fixed-order partial sums)
  * read back by the backward, which writes datt[i] (same layout) = g[0] * d out / d att on heads < `heads`; the other
  * heads are cleared only with zero_rest != 0 (st5_attn_fused_bwd with ext_heads never reads them). */
 int st5_guided_attn_fwd(const float* const* att, int32_t n_layers, int32_t B, int32_t H, int32_t heads, int32_t T_out,

@@ -42,6 +42,7 @@ class AttnArgs(C.Structure):
         ("scale", C.c_float), ("drop_p", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64),
         ("dout", C.c_void_p), ("dprobs_ext", C.c_void_p), ("ds", C.c_void_p),
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("dpe_k", C.c_void_p),
+        ("probs_heads", C.c_int32),
     ]
 
 
@@ -83,6 +84,8 @@ _PROTOS = {
     "st5_ctc_ws_floats": (C.c_int64, [_i32, _i32, _i32]),
     "st5_ctc_loss": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
                                _vp]),
+    "st5_tts_loss_ws_floats": (C.c_int64, [_i32, _i32]),
+    "st5_guided_attn_ws_floats": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "st5_tts_loss_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f, _vp, _vp, _vp]),
     "st5_tts_loss_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f, _vp,
                                    _vp, _vp, _vp]),

@@ -30,7 +30,7 @@ class TacotronLossFn(torch.autograd.Function):
         if labels.stride(1) != 1:
             labels = labels.contiguous()
         out = torch.empty(3, dtype=torch.float32, device=after.device)
-        sums = torch.empty(4, dtype=torch.float32, device=after.device)
+        sums = torch.empty(K.tts_loss_ws_floats(after.shape[0], after.shape[1]), dtype=torch.float32, device=after.device)
         K.tts_loss_fwd(after, before, logits, ys, labels, olens, int(r), float(pos_weight), sums, out)
         ctx.save_for_backward(after, before, logits, ys, labels, olens, sums)
         ctx.meta = (int(r), float(pos_weight))
@@ -57,7 +57,8 @@ class GuidedAttnFn(torch.autograd.Function):
         ilens, olens = ilens.long().contiguous(), olens.long().contiguous()
         heads = min(int(heads), atts[0].shape[1])  # (the reference's slice a[:, :heads] clips the same way)
         out = torch.empty(1, dtype=torch.float32, device=atts[0].device)
-        gsum = torch.empty(2, dtype=torch.float32, device=atts[0].device)
+        gsum = torch.empty(K.guided_attn_ws_floats(len(atts), atts[0].shape[0], heads, atts[0].shape[2]),
+                           dtype=torch.float32, device=atts[0].device)
         K.guided_attn_fwd(atts, int(heads), ilens, olens, int(r), float(sigma), float(alpha), gsum, out)
         ctx.save_for_backward(ilens, olens, gsum)
         sparse = all(getattr(a, "_st5_ext_heads", 0) >= heads for a in atts)

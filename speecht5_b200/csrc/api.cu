@@ -155,6 +155,10 @@ int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, con
                    "st5_conv0_gn_gelu_bwd");
 }
 
+int64_t st5_tts_loss_ws_floats(int32_t B, int32_t L) { return 4 + 4 * tts_loss_blocks(B, L); }
+int64_t st5_guided_attn_ws_floats(int32_t n_layers, int32_t B, int32_t heads, int32_t T_out) {
+  return 2 + guided_attn_blocks(n_layers, B, heads, T_out);
+}
 int st5_tts_loss_fwd(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
                      const float* labels, int64_t lab_bs, const int64_t* olens, int32_t B, int32_t L, int32_t D,
                      int32_t r, float pos_weight, float* sums, float* out, void* stream) {

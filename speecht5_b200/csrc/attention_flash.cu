@@ -60,6 +60,7 @@ struct FlashFwdParams {
   __nv_bfloat16* psave;
   float* probs; long p_ld;
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
+  int probs_heads;  // > 0: only heads < probs_heads get their probabilities written (no third sweep for the others)
 };
 
 __device__ __forceinline__ uint32_t fl_pack(float a, float b) {
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
   int tk = p.Tk;
   if (p.causal && i0 + FL_T < tk) tk = i0 + FL_T;
   const int nkb = (tk + FL_T - 1) / FL_T;
-  const int nsweep = p.probs != nullptr ? 3 : 2;
+  float* const probs = (p.probs_heads > 0 && h >= p.probs_heads) ? nullptr : p.probs;  // (uniform over the CTA)
+  const int nsweep = probs != nullptr ? 3 : 2;
   const int NS = nsweep * nkb;
 
   if (warp == 0 && elect_one()) {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
               }
             } else if (sweep == 2 && row_ok) {
               for (int t = 0; t < 32; ++t)
-                if (jc + t < p.p_ld) p.probs[prow * p.p_ld + jc + t] = 0.f;
+                if (jc + t < p.p_ld) probs[prow * p.p_ld + jc + t] = 0.f;
             }
             continue;
           }
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
               }
             }
           } else if (row_ok) {  // sweep 2: normalised, undropped probabilities for the caller
-            float* dst = p.probs + prow * p.p_ld + jc;
+            float* dst = probs + prow * p.p_ld + jc;
             if (jc + 32 <= p.p_ld && (p.p_ld & 3) == 0) {
 #pragma unroll
               for (int t = 0; t < 32; t += 4) {
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
           if (p.inv_l != nullptr) p.inv_l[prow] = inv;
         }
       } else if (p.causal && half == 0 && row_ok) {  // probabilities right of the last visible block
-        for (int j = nkb * FL_T; j < (int)p.p_ld; ++j) p.probs[prow * p.p_ld + j] = 0.f;
+        for (int j = nkb * FL_T; j < (int)p.p_ld; ++j) probs[prow * p.p_ld + j] = 0.f;
       }
     }
     // ---- epilogue: O / rowsum; this thread owns channels [32 half, 32 half + 32) of its row
@@ -489,6 +491,7 @@ extern "C" int st5_attn_flash_fwd(const st5_attn_args* a, float* lse, void* psav
   p.lse = lse; p.inv_l = inv_l;
   p.psave = reinterpret_cast<__nv_bfloat16*>(psave);
   p.probs = reinterpret_cast<float*>(a->probs); p.p_ld = a->p_ld;
+  p.probs_heads = a->probs_heads;
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.seed = a->seed; p.offset = a->offset;

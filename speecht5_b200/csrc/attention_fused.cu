@@ -55,6 +55,7 @@ struct FusedFwdParams {
   float* inv_l;            // [B][H][Tq] 1 / sum_j exp(s - rowmax): the backward's normaliser of psave
   float* out_f32;          // optional [B][Tq][H*64]: the un-rounded output, for the backward's row constant dO.O
   void* probs; int probs_fp32; long p_ld;  // optional undropped probabilities [B][H][Tq][p_ld]
+  int probs_heads;         // > 0: only heads < probs_heads get their probabilities written
   uint32_t drop_thr; float drop_scale; uint64_t seed, offset;
   int pe_row0;             // RPE: table row held by PE' row 0 of query tile 0 (= 1 + maxpos - 160; may be negative)
 };
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       if (p.lse != nullptr) p.lse[prow] = (sum > 0.f) ? (mm + log2f(sum)) * 0.6931471805599453f : -INFINITY;
       if (p.inv_l != nullptr) p.inv_l[prow] = inv;
     }
-    if (p.probs != nullptr) {
+    if (p.probs != nullptr && (p.probs_heads <= 0 || h < p.probs_heads)) {
       // normalised, undropped probabilities for the caller (overlaps the PV MMA)
       const int pchunks = warp_ok ? (int)((p.p_ld + 31) / 32) : 0;
       for (int c = half; c < pchunks; c += NG) {
@@ -481,6 +482,7 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* psav
   p.inv_l = inv_l;
   p.out_f32 = out_f32;
   p.probs = a->probs; p.probs_fp32 = a->probs_dtype == ST5_F32; p.p_ld = a->p_ld;
+  p.probs_heads = a->probs_heads;
   p.drop_thr = drop_threshold(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.seed = a->seed; p.offset = a->offset;

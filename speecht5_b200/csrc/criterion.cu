@@ -17,7 +17,9 @@ constexpr int CR_WARPS = 8;
 
 __device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
 
-// sums: [0] sum |da| + |db|, [1] sum da^2 + db^2, [2] sum bce, [3] number of valid frames
+// Reductions are two-stage and ORDER-FIXED (the same inputs give the same bits: a training step is reproducible from its
+// seed): every CTA writes its partial sums to its own slot, one CTA adds the slots in a fixed tree.
+// sums: [0] sum |da| + |db|, [1] sum da^2 + db^2, [2] sum bce, [3] number of valid frames; sums[4 + 4*cta + i] = partials
 __global__ void __launch_bounds__(CR_WARPS * 32)
     tts_loss_fwd_kernel(const float* __restrict__ after, const float* __restrict__ before,
                         const float* __restrict__ logits, const float* __restrict__ ys, int64_t y_bs,
@@ -65,12 +67,39 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < CR_WARPS; ++w) v += red[threadIdx.x][w];
-    if (v != 0.f) atomicAdd(sums + threadIdx.x, v);
+    sums[4 + 4 * (int64_t)blockIdx.x + threadIdx.x] = v;
   }
 }
 
+// fixed-order sum of n partial vectors of width W (W <= 4) laid out [n][W] -> dst[0..W): one CTA of 256 threads
+template <int W>
+__device__ __forceinline__ void fixed_order_sum(const float* __restrict__ part, int64_t n, float* __restrict__ dst) {
+  __shared__ float buf[W][256];
+  float v[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = 0.f;
+  for (int64_t k = threadIdx.x; k < n; k += 256)
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] += part[k * W + i];
+#pragma unroll
+  for (int i = 0; i < W; ++i) buf[i][threadIdx.x] = v[i];
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st)
+#pragma unroll
+      for (int i = 0; i < W; ++i) buf[i][threadIdx.x] += buf[i][threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int i = 0; i < W; ++i) dst[i] = buf[i][0];
+  __syncthreads();
+}
+
 // out: [0] l1, [1] l2, [2] bce  (means over the valid frames; an empty batch gives zeros)
-__global__ void tts_loss_finalize_kernel(const float* __restrict__ sums, int D, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+    tts_loss_finalize_kernel(float* __restrict__ sums, int64_t nblk, int D, float* __restrict__ out) {
+  fixed_order_sum<4>(sums + 4, nblk, sums);
   if (threadIdx.x == 0) {
     const float n = sums[3];
     const float inv = n > 0.f ? 1.f / n : 0.f;
@@ -173,14 +202,17 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < CR_WARPS; ++w) v += red[w];
-    if (v != 0.f) atomicAdd(gsum, v);
+    gsum[2 + (int64_t)blockIdx.x] = v;  // (summed in a fixed order by the finalize kernel)
   }
 }
 
-// gsum[1] = normaliser sum_b il_b * ol_b * (heads * layers); out[0] = alpha * gsum[0] / gsum[1]
-__global__ void guided_attn_finalize_kernel(const GuidedArgs p, const int64_t* __restrict__ ilens,
-                                            const int64_t* __restrict__ olens, float* __restrict__ gsum,
-                                            float* __restrict__ out) {
+// gsum[0] = sum of the per-CTA partials gsum[2..], gsum[1] = normaliser sum_b il_b * ol_b * (heads * layers);
+// out[0] = alpha * gsum[0] / gsum[1]
+__global__ void __launch_bounds__(256)
+    guided_attn_finalize_kernel(const GuidedArgs p, const int64_t* __restrict__ ilens, const int64_t* __restrict__ olens,
+                                float* __restrict__ gsum, int64_t nblk, float* __restrict__ out) {
+  fixed_order_sum<1>(gsum + 2, nblk, gsum);
+  if (threadIdx.x >= 32) return;
   float n = 0.f;
   for (int b = threadIdx.x; b < p.B; b += 32)
     n += (float)min((int64_t)p.T_out, olens[b] / p.r) * (float)min((int64_t)p.T_in, ilens[b]);
@@ -223,16 +255,19 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
   }
 }
 
+int64_t tts_loss_blocks(int B, int L) { return ((int64_t)B * L + CR_WARPS - 1) / CR_WARPS; }
+int64_t guided_attn_blocks(int n_layers, int B, int heads, int T_out) {
+  return ((int64_t)n_layers * B * heads * T_out + CR_WARPS - 1) / CR_WARPS;
+}
+
 int tts_loss_fwd_launch(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
                         const float* labels, int64_t lab_bs, const int64_t* olens, int B, int L, int D, int r,
                         float pos_weight, float* sums, float* out, cudaStream_t s) {
   if (B <= 0 || L <= 0 || D <= 0 || r <= 0) return -2;
-  cudaError_t e = cudaMemsetAsync(sums, 0, 4 * sizeof(float), s);
-  if (e != cudaSuccess) return (int)e;
-  const int64_t rows = (int64_t)B * L;
-  tts_loss_fwd_kernel<<<(unsigned)((rows + CR_WARPS - 1) / CR_WARPS), CR_WARPS * 32, 0, s>>>(
-      after, before, logits, ys, y_bs, labels, lab_bs, olens, B, L, D, r, pos_weight, sums);
-  tts_loss_finalize_kernel<<<1, 32, 0, s>>>(sums, D, out);
+  const int64_t nblk = tts_loss_blocks(B, L);
+  tts_loss_fwd_kernel<<<(unsigned)nblk, CR_WARPS * 32, 0, s>>>(after, before, logits, ys, y_bs, labels, lab_bs, olens, B, L,
+                                                              D, r, pos_weight, sums);
+  tts_loss_finalize_kernel<<<1, 256, 0, s>>>(sums, nblk, D, out);
   return (int)cudaGetLastError();
 }
 
@@ -268,11 +303,9 @@ int guided_attn_fwd_launch(const float* const* att, int n_layers, int B, int H, 
   GuidedArgs p;
   int rc = guided_fill(p, att, nullptr, n_layers, B, H, heads, T_out, T_in, p_ld, r, sigma, alpha);
   if (rc != 0) return rc;
-  cudaError_t e = cudaMemsetAsync(gsum, 0, 2 * sizeof(float), s);
-  if (e != cudaSuccess) return (int)e;
-  const int64_t rows = (int64_t)n_layers * B * heads * T_out;
-  guided_attn_fwd_kernel<<<(unsigned)((rows + CR_WARPS - 1) / CR_WARPS), CR_WARPS * 32, 0, s>>>(p, ilens, olens, gsum);
-  guided_attn_finalize_kernel<<<1, 32, 0, s>>>(p, ilens, olens, gsum, out);
+  const int64_t nblk = guided_attn_blocks(n_layers, B, heads, T_out);
+  guided_attn_fwd_kernel<<<(unsigned)nblk, CR_WARPS * 32, 0, s>>>(p, ilens, olens, gsum);
+  guided_attn_finalize_kernel<<<1, 256, 0, s>>>(p, ilens, olens, gsum, nblk, out);
   return (int)cudaGetLastError();
 }
 

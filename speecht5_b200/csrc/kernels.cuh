@@ -129,6 +129,8 @@ int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, cons
 int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
                      const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
                      int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
+int64_t tts_loss_blocks(int B, int L);
+int64_t guided_attn_blocks(int n_layers, int B, int heads, int T_out);
 int tts_loss_fwd_launch(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,
                         const float* labels, int64_t lab_bs, const int64_t* olens, int B, int L, int D, int r,
                         float pos_weight, float* sums, float* out, cudaStream_t s);

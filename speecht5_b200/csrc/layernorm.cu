@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(256)
 // bias gradient of the projection that produced x: its separate column-sum launch disappears) -- live in a PRIVATE
 // shared-memory strip per warp (plain read-modify-write of the lane's own 16-byte slots, conflict-free layout), which
 // frees the registers for a one-row-ahead prefetch of dy / s: a warp visits only 2-5 rows, so without the prefetch every
-// row costs a full exposed HBM round trip (measured 2.5 TB/s before). The strips meet after a CTA barrier and leave as
+// row costs a full exposed HBM round trip (measured 2.5 TB/s before, 3.1 TB/s with it; what bounds it now is bytes in
+// flight: 16 warps x 3 KB per SM. A three-CTA form that kept the rows packed in registers and decoded them twice was
+// measured at 2.2 TB/s -- spills and the doubled decode cost more than the third CTA's loads bought -- and removed). The strips meet after a CTA barrier and leave as
 // 16-byte vector reductions (red.global.add.v4.f32) when the targets are 16-byte aligned. NCH = 16-byte chunks per lane.
 constexpr int LNB_WARPS = 8;
 constexpr int LNB_NACC = 3;  // dgamma | dbeta | column sums of dx
@@ -379,140 +381,6 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
   }
 }
 
-// bf16 variant with THREE CTAs per SM (85 registers): what is kept across the two warp reductions is the row as it came
-// from memory (24 registers of packed bf16) instead of its decoded fp32 form (48), decoded once per pass; the next row's
-// 24 registers are in flight meanwhile. 24 instead of 16 warps per SM = 1.5x the bytes in flight, which is what bounds
-// this kernel (3 KB per row per warp against ~2 us of loaded HBM latency). Same strips / reduction as above.
-template <int NCH>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 3)
-    ln_bwd_fused_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ s_in,
-                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                             const float* __restrict__ gamma, __nv_bfloat16* __restrict__ ds,
-                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                             float* __restrict__ dxsum, int64_t rows, int C, uint32_t thr, float dscale, uint64_t seed,
-                             uint64_t offset) {
-  using T = __nv_bfloat16;
-  extern __shared__ __align__(16) float ln_acc[];
-  if (thr != 0) resolve_seed(seed, offset);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nchunks = C >> 3, half4 = C >> 3, acc4 = C >> 2;
-  float4* acc = reinterpret_cast<float4*>(ln_acc + (size_t)warp * LNB_NACC * C);
-  for (int t = lane; t < LNB_NACC * acc4; t += 32) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
-  const int64_t stride = (int64_t)gridDim.x * LNB_WARPS;
-  int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp;
-  Raw8<T> cd[NCH], cs[NCH], nd[NCH], ns[NCH];
-  float mu = 0.f, rs = 0.f, nmu = 0.f, nrs = 0.f;
-  if (row < rows) {
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int ch = k * 32 + lane;
-      if (ch < nchunks) {
-        cd[k].load(dy + row * C + ch * 8);
-        cs[k].load(s_in + row * C + ch * 8);
-      }
-    }
-    mu = mean[row];
-    rs = rstd[row];
-  }
-  for (; row < rows; row += stride) {
-    const int64_t nxt = row + stride;
-    if (nxt < rows) {
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const int ch = k * 32 + lane;
-        if (ch < nchunks) {
-          nd[k].load(dy + nxt * C + ch * 8);
-          ns[k].load(s_in + nxt * C + ch * 8);
-        }
-      }
-      nmu = mean[nxt];
-      nrs = rstd[nxt];
-    }
-    // four channels (two packed words) at a time: the decoded values never outlive one strip slot
-    auto word = [](const uint4& u, int i) { return i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w)); };
-    auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
-    auto hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int ch = k * 32 + lane;
-      if (ch < nchunks) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t dw0 = word(cd[k].u, 2 * hh), dw1 = word(cd[k].u, 2 * hh + 1);
-          const uint32_t sw0 = word(cs[k].u, 2 * hh), sw1 = word(cs[k].u, 2 * hh + 1);
-          const float4 gm = *reinterpret_cast<const float4*>(gamma + ch * 8 + 4 * hh);
-          const float d0 = lo(dw0), d1 = hi(dw0), d2 = lo(dw1), d3 = hi(dw1);
-          const float x0 = (lo(sw0) - mu) * rs, x1 = (hi(sw0) - mu) * rs, x2 = (lo(sw1) - mu) * rs, x3 = (hi(sw1) - mu) * rs;
-          const int slot = hh * half4 + ch;
-          float4 g = acc[slot], bb = acc[acc4 + slot];
-          g.x += d0 * x0; g.y += d1 * x1; g.z += d2 * x2; g.w += d3 * x3;
-          bb.x += d0; bb.y += d1; bb.z += d2; bb.w += d3;
-          acc[slot] = g; acc[acc4 + slot] = bb;
-          const float g0 = d0 * gm.x, g1 = d1 * gm.y, g2 = d2 * gm.z, g3 = d3 * gm.w;
-          c1 += (g0 + g1) + (g2 + g3);
-          c2 += (g0 * x0 + g1 * x1) + (g2 * x2 + g3 * x3);
-        }
-      }
-    }
-    c1 = warp_sum(c1) / (float)C;
-    c2 = warp_sum(c2) / (float)C;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int ch = k * 32 + lane;
-      if (ch < nchunks) {
-        const int64_t e0 = row * C + ch * 8;
-        float r[8];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t dw0 = word(cd[k].u, 2 * hh), dw1 = word(cd[k].u, 2 * hh + 1);
-          const uint32_t sw0 = word(cs[k].u, 2 * hh), sw1 = word(cs[k].u, 2 * hh + 1);
-          const float4 gm = *reinterpret_cast<const float4*>(gamma + ch * 8 + 4 * hh);
-          r[4 * hh + 0] = rs * (lo(dw0) * gm.x - c1 - (lo(sw0) - mu) * rs * c2);
-          r[4 * hh + 1] = rs * (hi(dw0) * gm.y - c1 - (hi(sw0) - mu) * rs * c2);
-          r[4 * hh + 2] = rs * (lo(dw1) * gm.z - c1 - (lo(sw1) - mu) * rs * c2);
-          r[4 * hh + 3] = rs * (hi(dw1) * gm.w - c1 - (hi(sw1) - mu) * rs * c2);
-        }
-        if (ds != nullptr) store8<T>(ds + e0, r);
-        if (dx != nullptr) {
-          if (thr != 0) dropout8(r, (uint64_t)e0, thr, dscale, seed, offset);
-          store8<T>(dx + e0, r);
-        }
-        if (dxsum != nullptr) {
-          float4 x0 = acc[2 * acc4 + ch], x1 = acc[2 * acc4 + half4 + ch];
-          x0.x += r[0]; x0.y += r[1]; x0.z += r[2]; x0.w += r[3];
-          x1.x += r[4]; x1.y += r[5]; x1.z += r[6]; x1.w += r[7];
-          acc[2 * acc4 + ch] = x0; acc[2 * acc4 + half4 + ch] = x1;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) { cd[k] = nd[k]; cs[k] = ns[k]; }
-    mu = nmu;
-    rs = nrs;
-  }
-  __syncthreads();
-  const float4* all = reinterpret_cast<const float4*>(ln_acc);
-  for (int it = threadIdx.x; it < LNB_NACC * acc4; it += LNB_WARPS * 32) {
-    const int a = it / acc4, q = it - a * acc4;
-    float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dxsum);
-    if (dst == nullptr) continue;
-    float4 v = all[it];
-#pragma unroll
-    for (int w = 1; w < LNB_WARPS; ++w) {
-      const float4 o = all[(size_t)w * LNB_NACC * acc4 + it];
-      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-    }
-    const int c0 = q < half4 ? q * 8 : (q - half4) * 8 + 4;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      red_add_v4(dst + c0, v);
-    } else {
-      atomicAdd(dst + c0, v.x); atomicAdd(dst + c0 + 1, v.y); atomicAdd(dst + c0 + 2, v.z); atomicAdd(dst + c0 + 3, v.w);
-    }
-  }
-}
-
 template <typename T, int NCH>
 static int ln_bwd_fused_run(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
                             void* ds, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int C,
@@ -533,42 +401,10 @@ static int ln_bwd_fused_run(const void* dy, const void* s_in, const float* mean,
   return 0;
 }
 
-// ST5_LN_BWD_2CTA=1 keeps the two-CTA form for A/B runs
-static bool ln_bwd_three_ctas() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ST5_LN_BWD_2CTA");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-static int ln_bwd_fused_bf16_run(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
-                                 void* ds, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int C,
-                                 uint32_t thr, float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ln_bwd_fused_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         LNB_WARPS * LNB_NACC * 768 * (int)sizeof(float));
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS;
-  const int64_t cap = 3 * (int64_t)device_sm_count();
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  const size_t smem = (size_t)LNB_WARPS * LNB_NACC * C * sizeof(float);
-  using T = __nv_bfloat16;
-  ln_bwd_fused_bf16_kernel<3><<<grid, LNB_WARPS * 32, smem, s>>>((const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds, (T*)dx,
-                                                                 dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset);
-  return 0;
-}
-
 template <typename T>
 static int ln_bwd_fused_dispatch(const void* dy, const void* s_in, const float* mean, const float* rstd, const float* gamma,
                                  void* ds, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int C,
                                  uint32_t thr, float dsc, uint64_t seed, uint64_t offset, cudaStream_t s) {
-  if (C <= 768 && sizeof(T) == 2 && ln_bwd_three_ctas())
-    return ln_bwd_fused_bf16_run(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset, s);
   if (C <= 768)
     return ln_bwd_fused_run<T, 3>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset, s);
   return ln_bwd_fused_run<T, LN_MAX_CHUNKS>(dy, s_in, mean, rstd, gamma, ds, dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed,

@@ -298,6 +298,14 @@ def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, g
     _count(3 if grad is not None else 2)
 
 
+def tts_loss_ws_floats(B, L):
+    return int(_lib.load().st5_tts_loss_ws_floats(B, L))
+
+
+def guided_attn_ws_floats(n_layers, B, heads, T_out):
+    return int(_lib.load().st5_guided_attn_ws_floats(n_layers, B, heads, T_out))
+
+
 def tts_loss_fwd(after, before, logits, ys, labels, olens, r, pos_weight, sums, out):
     """st5_tts_loss_fwd: out[0..2] = l1, l2, bce of Tacotron2Loss (masked means); after / before [B, L, D] fp32."""
     _require_cuda(after, before, logits, ys, labels, olens, sums, out)

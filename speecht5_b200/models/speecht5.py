@@ -387,6 +387,12 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         max_len = min(int(max_len_a * src_len + max_len_b), self.args.max_text_positions - 1)
         assert min_len <= max_len
         enc = self.forward_encoder(source, padding_mask=padding_mask)
+        if use_cache in ("graph", "graph_body_eager"):  # one captured CUDA graph per step (incremental.GreedyGraph)
+            from ..incremental import greedy_graph
+            S = enc["encoder_out"][0].size(0)
+            gg = greedy_graph(self, B, S, max_len, source.device, capture=use_cache == "graph")
+            return gg.decode(enc, max_len, min_len=min_len, unk_penalty=unk_penalty, temperature=temperature, pad=pad,
+                             eos=eos, unk=unk, blank=blank, mask_idx=mask_idx)
         tokens = torch.full((B, max_len + 2), pad, dtype=torch.long, device=source.device)
         tokens[:, 0] = eos
         done = torch.zeros(B, dtype=torch.bool, device=source.device)
@@ -457,20 +463,14 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         cache = None
         if kwargs.get("use_cache", False) in ("graph", "graph_body_eager"):
             # key/value cache + ONE captured CUDA graph per decoder step (speecht5_b200/incremental.py SynthesisGraph):
-            # the host replays and reads the stop flag, nothing else
-            from ..incremental import SynthesisGraph
+            # the host replays steps and reads their stop flags, nothing else; graphs are kept on the model
+            from ..incremental import synthesis_graph
             seed_t = RT._seed_t
             try:
-                sg = SynthesisGraph(self, encoder_out, spkembs, maxlen, threshold,
-                                    capture=kwargs["use_cache"] == "graph")
-                while True:
-                    idx += 1
-                    stop = sg.step(idx - 1)
-                    if stop or idx >= maxlen:
-                        if idx < minlen:
-                            continue
-                        mel = post.refine(sg.outs[:idx].reshape(1, idx * r, odim))[0]
-                        return mel, sg.probs[:idx].reshape(-1).clone(), sg.attn[:idx].permute(1, 2, 0, 3).contiguous()
+                sg = synthesis_graph(self, T_enc, max(maxlen, 1), src_tokens.device,
+                                     capture=kwargs["use_cache"] == "graph")
+                before, stop_probs, attn = sg.synthesize(encoder_out, spkembs, threshold, minlen, maxlen)
+                return post.refine(before)[0], stop_probs, attn
             finally:
                 RT._seed_t = seed_t
         if kwargs.get("use_cache", False):  # key/value cache, eager step (speecht5_b200/incremental.py)

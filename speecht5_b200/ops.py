@@ -22,6 +22,7 @@ class Runtime:
         self.dtype = torch.bfloat16
         self._seed = 1
         self._seed_t = None  # device-resident seed (CUDA-graph mode): kernels dereference it at run time
+        self._draws = 0
         self._offset = 0
         self.param_epoch = 0
         self._shadows = {}
@@ -34,6 +35,7 @@ class Runtime:
         self.attn_fused_bwd = True    # ... and the flash-style fused backward (attention_fused_bwd.cu)
         self.fold_residual_grad = os.environ.get("ST5_FOLD_RESGRAD", "1") != "0"  # see LinearFn.forward (passthrough)
         self.probs_grad_heads = 0     # > 0: gradients on returned probabilities exist for the first n heads only
+        self.probs_read_heads = 0     # > 0: nobody READS returned probabilities beyond the first n heads (trainer, per step)
         # streaming forward for what the resident kernels cannot hold (Tk > 320, clipped relative positions); "all":
         # every bf16 shape goes through it (ST5_ATTN_FLASH=all)
         self.attn_flash = {"0": False, "all": "all"}.get(os.environ.get("ST5_ATTN_FLASH", "1"), True)
@@ -60,6 +62,7 @@ class Runtime:
     def manual_seed(self, seed):
         self._seed = int(seed)
         self._offset = 0
+        self._draws = 0  # utterances synthesised since the last manual_seed (incremental.SynthesisGraph)
         if self._seed_t is not None:
             self._seed_t.fill_(self._seed)
 
@@ -903,7 +906,7 @@ class AttentionTCFn(torch.autograd.Function):
                             maxpos=maxpos if with_pe else 0, probs_dtype=K.dtype_id(probs) if want else 0, q=qv,
                             q_ld=q_ld, q_bs=q_bs, k=kk, k_ld=kv_ld, k_bs=kv_bs, v=vv, v_ld=kv_ld, v_bs=kv_bs,
                             key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale,
-                            drop_p=drop_p, seed=RT.seed, offset=off)
+                            drop_p=drop_p, seed=RT.seed, offset=off, probs_heads=cfg.get("probs_read_heads", 0) if want else 0)
             (K.attn_flash_fwd if flash else K.attn_fused_fwd)(a, None, psave, inv_l, o32)
             ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
             ctx.fused = (out, psave, inv_l, o32, kp)
@@ -1010,7 +1013,8 @@ def attention(q_buf, kv_buf, *, H, d, q_col, k_col, v_col, scale, pe_k=None, max
     # RT.probs_grad_heads: the consumer of the returned probabilities differentiates only through the first n heads (the
     # guided-attention loss; set by the trainer from the criterion): the backward skips the zero gradient of the others
     cfg = dict(H=H, d=d, q_col=q_col, k_col=k_col, v_col=v_col, scale=scale, maxpos=maxpos, causal=causal,
-               drop_p=drop_p, return_probs=return_probs, probs_grad_heads=RT.probs_grad_heads if return_probs else 0)
+               drop_p=drop_p, return_probs=return_probs, probs_grad_heads=RT.probs_grad_heads if return_probs else 0,
+               probs_read_heads=RT.probs_read_heads if return_probs else 0)
     Tk = (q_buf if kv_buf is None else kv_buf).shape[1]
     streaming = RT.attn_flash and RT.attn_fused and RT.attn_fused_bwd and (pe_k is None or not causal)
     if q_buf.dtype == torch.bfloat16 and RT.attn_tensor_core and (Tk <= 512 or streaming):
@@ -1133,6 +1137,7 @@ class BatchNormActFn(torch.autograd.Function):
                  training, momentum, eps, act, drop_p, RT.seed, off, scratch)
         ctx.save_for_backward(x, y_pre, gamma, mean, rstd)
         ctx.meta = (act, drop_p, off, RT.seed, rows, Cc, training)
+        ctx.param_ids = (id(gamma), id(beta))
         return y
 
     @staticmethod
@@ -1143,11 +1148,18 @@ class BatchNormActFn(torch.autograd.Function):
             raise RuntimeError("BatchNormActFn backward is only defined for training-mode statistics")
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        dgamma = torch.zeros(Cc, dtype=torch.float32, device=dy.device)
-        dbeta = torch.zeros_like(dgamma)
+        # the kernel ADDS the parameter gradients: aim it at the trainer's flat gradient buffer when one is registered
+        # (like ResidualLayerNormFn: no zero fills, no AccumulateGrad adds), else at fresh zero vectors for autograd
+        gid, bid = ctx.param_ids
+        gG, gB = RT._static_grad.get(("bias", gid)), RT._static_grad.get(("bias", bid))
+        direct = gG is not None and gB is not None
+        dgamma = gG if direct else torch.zeros(Cc, dtype=torch.float32, device=dy.device)
+        dbeta = gB if direct else torch.zeros(Cc, dtype=torch.float32, device=dy.device)
         scratch = torch.empty(2 * Cc, dtype=torch.float32, device=dy.device)
         K.bn_bwd(dy, Cc, x, Cc, y_pre, gamma.detach(), mean, rstd, dx, Cc, dgamma, dbeta, rows, Cc, act, drop_p, seed,
                  off, scratch)
+        if direct:
+            dgamma = dbeta = None
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 

@@ -212,6 +212,9 @@ class B200Trainer:
         t2s = getattr(criterion, "text_to_speech_loss", None)
         RT.probs_grad_heads = (int(getattr(t2s, "num_heads_applied_guided_attn", 0))
                                if (t2s is not None and getattr(t2s, "use_guided_attn_loss", False)) else 0)
+        # ... and inside an update the criterion is the ONLY reader of the returned maps: the forward need not write the
+        # other heads' probabilities at all (77 MB of fp32 per decoder layer at the benched shape). Scoped to train_step.
+        self._probs_read_heads = RT.probs_grad_heads
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -487,6 +490,13 @@ class B200Trainer:
     def train_step(self, samples, lr=None):
         """samples: list of micro-batch dicts (tensors on host -- pinned for async copies -- or on the device).
         Returns (losses [n_micro] device tensor, stats [n_micro, k] device tensor or None)."""
+        RT.probs_read_heads = self._probs_read_heads
+        try:
+            return self._train_step(samples, lr)
+        finally:
+            RT.probs_read_heads = 0
+
+    def _train_step(self, samples, lr=None):
         if lr is not None:
             self.lr = lr
             self.lr_dev.fill_(lr)

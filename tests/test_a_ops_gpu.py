@@ -70,7 +70,10 @@ def test_layer_norm_backward_column_sums_of_dx(cuda, dtype, rows, C, drop_p):
         ds2, dx2 = torch.empty_like(dy), (torch.empty_like(dy) if drop_p > 0 else None)
         dg2, db2 = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
         K.ln_bwd(dy, s, mean, rstd, gamma, ds2, dx2, dg2, db2, drop_p, 11, 5)
-        assert torch.equal(ds, ds2) and (dx is None or torch.equal(dx, dx2))
+        if rows >= 64:  # (both calls take the fused kernel; below 64 rows the call without dxsum takes the two-kernel form)
+            assert torch.equal(ds, ds2) and (dx is None or torch.equal(dx, dx2))
+        else:
+            assert rel(ds, ds2) < 1e-2 and (dx is None or rel(dx, dx2) < 1e-2)
         out = dx if dx is not None else ds
         want = out.double().sum(0) + 0.25
         # the kernel sums the un-rounded fp32 values, the check the rounded ones: allow the bf16 rounding of `rows` terms
@@ -603,3 +606,35 @@ def test_fused_guided_attention_kernels_against_the_torch_formulation(cuda, T_in
         assert rel(g[:, :heads], rg[:, :heads]) < 1e-5
         if not sparse:
             assert float(g[:, heads:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("Tq,Tk", [(313, 160), (200, 499)])
+def test_returned_probabilities_for_the_first_heads_only(cuda, Tq, Tk):
+    """RT.probs_read_heads (set by B200Trainer for the duration of an update: the guided-attention loss is the only
+    reader of the returned cross-attention maps, text_to_speech_loss.py:210-212): the fused (Tk <= 320) and the
+    streaming forward write the probabilities of heads < n only -- same output, same first-n maps, same gradients."""
+    from speecht5_b200 import ops
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.bfloat16
+    torch.manual_seed(2)
+    B, H, d = 2, 12, 768
+    q = (torch.randn(B, Tq, d, device=cuda) * 0.5).bfloat16()
+    kv = (torch.randn(B, Tk, 2 * d, device=cuda) * 0.5).bfloat16()
+    pad = torch.zeros(B, Tk, dtype=torch.bool, device=cuda)
+    pad[1, Tk - 9:] = True
+    res = []
+    for n in (0, 2):
+        RT.probs_read_heads = RT.probs_grad_heads = n
+        try:
+            qq, kk = q.clone().requires_grad_(), kv.clone().requires_grad_()
+            out, probs = ops.attention(qq, kk, H=H, d=d, q_col=0, k_col=0, v_col=1, scale=0.125, key_pad=pad, return_probs=True)
+            g = torch.zeros_like(probs)
+            g[:, :2] = torch.randn(B, 2, Tq, Tk, device=cuda, generator=torch.Generator(device=cuda).manual_seed(9))
+            (out.float().square().sum() + (probs[:, :2] * g[:, :2]).sum()).backward()
+            res.append((out.detach().clone(), probs.detach()[:, :2].clone(), qq.grad.clone(), kk.grad.clone(), g))
+        finally:
+            RT.probs_read_heads = RT.probs_grad_heads = 0
+    (o0, p0, dq0, dk0, g0), (o1, p1, dq1, dk1, g1) = res
+    assert torch.equal(o0, o1) and torch.equal(p0, p1)
+    assert (p1[0].sum(-1) - 1).abs().max() < 1e-3
+    assert rel(dq1, dq0) < 1e-5 and rel(dk1, dk0) < 1e-5

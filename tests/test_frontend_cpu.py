@@ -320,6 +320,12 @@ def test_kv_cache_decoding_equals_prefix_recomputation_on_emulated_kernels(monke
     ids_ref = O.greedy_decode(oracle, src, pm, max_len_b=10)
     ids = model.generate_text_greedy(src, pm, max_len_b=10, use_cache=True)
     assert [t.tolist() for t in ids] == [t.tolist() for t in ids_ref]
+    # the device-side form a CUDA graph replays (step counter, additive score masks, bookkeeping on tensors), run eagerly
+    ids_g = model.generate_text_greedy(src, pm, max_len_b=10, use_cache="graph_body_eager")
+    assert [t.tolist() for t in ids_g] == [t.tolist() for t in ids_ref]
+    ids_m = model.generate_text_greedy(src, pm, max_len_b=10, min_len=4, unk_penalty=0.5, use_cache=True)
+    ids_mg = model.generate_text_greedy(src, pm, max_len_b=10, min_len=4, unk_penalty=0.5, use_cache="graph_body_eager")
+    assert [t.tolist() for t in ids_mg] == [t.tolist() for t in ids_m] and all(len(t) >= 4 for t in ids_mg)
     # (b) speech synthesis
     RT.invalidate_shadows()
     torch.manual_seed(3)

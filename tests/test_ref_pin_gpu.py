@@ -162,10 +162,12 @@ def test_asr_step_against_reference_vectors(cuda, dtype, tol):
     assert n >= 8
 
 
-@pytest.mark.parametrize("use_cache", [False, True])
+@pytest.mark.parametrize("use_cache", [False, True, "graph"])
 def test_greedy_token_ids_equal_the_reference_sequence_generator(cuda, use_cache):
     """north_star: bit-exact token ids for ASR greedy decode. Expectation = the reference's own
-    speecht5/sequence_generator.py (beam 1) on the reference model; product = CUDA path in parity mode."""
+    speecht5/sequence_generator.py (beam 1) on the reference model; product = CUDA path in parity mode: prefix
+    recomputation, the eager key/value cache, and one captured CUDA graph per step (incremental.GreedyGraph; run twice:
+    the second call replays the graphs the first one captured)."""
     blob = load("ref_asr_tiny")
     model = _asr_model(cuda, torch.float32, blob).eval()
     hyp = model.generate_text_greedy(torch.from_numpy(blob["in/source"]).to(cuda),
@@ -174,6 +176,11 @@ def test_greedy_token_ids_equal_the_reference_sequence_generator(cuda, use_cache
     for b, t in enumerate(hyp):
         n = int(blob["out/greedy_lengths"][b])
         assert t.tolist() == blob["out/greedy_tokens"][b, :n].tolist(), (b, t.tolist())
+    if use_cache == "graph":
+        again = model.generate_text_greedy(torch.from_numpy(blob["in/source"]).to(cuda),
+                                           torch.from_numpy(blob["in/padding_mask"]).to(cuda), max_len_b=12,
+                                           blank=VOCAB - 1, mask_idx=VOCAB - 2, use_cache="graph")
+        assert [t.tolist() for t in again] == [t.tolist() for t in hyp]
 
 
 def test_hifigan_against_the_reference_generator(cuda):

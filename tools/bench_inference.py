@@ -47,6 +47,20 @@ def main():
     for name, kw in (("prefix", {}), ("kv_cache", dict(use_cache=True)), ("kv_cache_graph", dict(use_cache="graph"))):
         ms = cuda_ms(lambda: model.generate_speech(src_tokens=tok, spkembs=spk, threshold=2.0, **kw), reps=2)
         out[f"generate_speech_{name}"] = dict(ms=ms, decoder_steps=args.steps, ms_per_step=ms / args.steps)
+    # ---- row 21 (ASR half): beam-1 text decoding of 8 x 10 s waveforms, a fixed number of steps (eos forbidden until
+    # min_len = the step budget), encoder included: prefix recomputation / eager key-value cache / one graph per step
+    del model
+    aargs = make_args("t5_transformer_base_asr", build_speech_encoder=True, build_text_decoder=True, bert_init=True,
+                      encoder_layerdrop=0.0, decoder_layerdrop=0.0, max_text_positions=600)
+    asr = T5TransformerModel.build_model(aargs).to(dev).eval()
+    wav = torch.randn(8, 160000, device=dev) * 0.1
+    wpm = torch.zeros(8, 160000, dtype=torch.bool, device=dev)
+    nsteps = min(args.steps, 100)
+    for name, uc in (("prefix", False), ("kv_cache", True), ("kv_cache_graph", "graph")):
+        ms = cuda_ms(lambda: asr.generate_text_greedy(wav, wpm, max_len_b=nsteps, min_len=nsteps, use_cache=uc), reps=2)
+        out[f"greedy_text_{name}"] = dict(ms=ms, utterances=8, decoder_steps=nsteps + 1, ms_per_step=ms / (nsteps + 1),
+                                          utt_per_s=8 / (ms / 1e3))
+    del asr
     # ---- row 16: HiFi-GAN, 8 s of audio per utterance (500 frames), batch 4
     from oracle.audio_oracle import HifiGanGenerator as Ref, logmelfilterbank as ref_logmel
     ref = Ref(std=0.02, seed=1).eval()
