@@ -9,9 +9,8 @@
 //   backward: pass 1 sums of g and g*xhat (reads dy), pass 2 weight gradient (reads dy)      -> 2 reads of [B, T, C]
 // The input is the waveform, so there is no input gradient. One thread per channel, TCH output frames per block, the
 // waveform segment of the block staged in shared memory (every thread reads the same address: broadcast).
-//
-// Written at the end of round 1 without GPU time: validated only through its CPU restatement
-// (tests/test_kernel_algorithms_cpu.py); the gated GPU test compares it with oracle/speecht5_oracle_asr.py.
+// Checked on the device against oracle/speecht5_oracle_asr.py (tests/test_frontend_gpu.py) and, as an algorithm, through
+// its CPU restatement (tests/test_kernel_algorithms_cpu.py).
 #include "kernels.cuh"
 
 namespace st5 {
@@ -52,36 +51,60 @@ __global__ void conv0_stats_kernel(const float* __restrict__ wave, const float* 
   const int nt = c0_stage(wave, w, seg, wr, n, T0, C, K, S, t0);
   const int c = threadIdx.x;
   if (c >= C) return;
-  float sum = 0.f;
-  for (int t = 0; t < nt; ++t) sum += c0_conv(seg, wr, t, K, S);
-  const float mu = sum / (float)nt;
-  float m2 = 0.f;
-  for (int t = 0; t < nt; ++t) {
-    const float d = c0_conv(seg, wr, t, K, S) - mu;
-    m2 = fmaf(d, d, m2);
+  // one pass: sums of (v - pilot) and (v - pilot)^2 with the chunk's first value as the pilot, so the centred sum of
+  // squares M2 = Q - S^2 / n is formed from numbers of the size of the deviations, not of the mean (the convolution
+  // is the dominant cost of this kernel: a second, centred pass over the same frames doubled it)
+  const float pilot = c0_conv(seg, wr, 0, K, S);
+  float sh = 0.f, qh = 0.f;
+  for (int t = 1; t < nt; ++t) {
+    const float d = c0_conv(seg, wr, t, K, S) - pilot;
+    sh += d;
+    qh = fmaf(d, d, qh);
   }
+  const float sum = fmaf((float)nt, pilot, sh);
+  const float m2 = fmaxf(qh - sh * sh / (float)nt, 0.f);
   float* dst = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
   dst[c] = sum;
   dst[C + c] = m2;
 }
 
-// Chan's pairwise combination of the per-chunk (sum, M2) in double: mean / rstd per (utterance, channel)
-__global__ void conv0_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd,
-                                      int T0, int C, int chunks, float eps) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c >= C) return;
+// Chan's pairwise combination of the per-chunk (sum, M2) in double: mean / rstd per (utterance, channel).
+// block (64 channels, 8 chunk groups), grid (B, C / 64): the ~250 chunks of a 10 s utterance are walked by 8 threads per
+// channel and met in shared memory (the one-thread-per-channel form ran 8 CTAs for 156 us).
+constexpr int C0_FG = 8;
+__global__ void __launch_bounds__(64 * C0_FG)
+    conv0_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd, int T0,
+                          int C, int chunks, float eps) {
+  __shared__ double red[C0_FG][64];
+  const int b = blockIdx.x, c = blockIdx.y * 64 + threadIdx.x, g = threadIdx.y;
+  const bool on = c < C;
   const float* p = part + (int64_t)b * chunks * 2 * C;
   double tot = 0.0;
-  for (int i = 0; i < chunks; ++i) tot += (double)p[(int64_t)i * 2 * C + c];
+  if (on)
+    for (int i = g; i < chunks; i += C0_FG) tot += (double)p[(int64_t)i * 2 * C + c];
+  red[g][threadIdx.x] = tot;
+  __syncthreads();
+  tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < C0_FG; ++k) tot += red[k][threadIdx.x];
+  __syncthreads();
   const double mu = tot / (double)T0;
   double m2 = 0.0;
-  for (int i = 0; i < chunks; ++i) {
-    const int ni = min(C0_TCH, T0 - i * C0_TCH);
-    const double d = (double)p[(int64_t)i * 2 * C + c] / (double)ni - mu;
-    m2 += (double)p[(int64_t)i * 2 * C + C + c] + (double)ni * d * d;
+  if (on)
+    for (int i = g; i < chunks; i += C0_FG) {
+      const int ni = min(C0_TCH, T0 - i * C0_TCH);
+      const double d = (double)p[(int64_t)i * 2 * C + c] / (double)ni - mu;
+      m2 += (double)p[(int64_t)i * 2 * C + C + c] + (double)ni * d * d;
+    }
+  red[g][threadIdx.x] = m2;
+  __syncthreads();
+  if (g == 0 && on) {
+    m2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < C0_FG; ++k) m2 += red[k][threadIdx.x];
+    mean[b * C + c] = (float)mu;
+    rstd[b * C + c] = (float)(1.0 / sqrt(m2 / (double)T0 + (double)eps));  // biased variance, as GroupNorm
   }
-  mean[b * C + c] = (float)mu;
-  rstd[b * C + c] = (float)(1.0 / sqrt(m2 / (double)T0 + (double)eps));  // biased variance, as GroupNorm
 }
 
 template <typename T>
@@ -132,21 +155,36 @@ __global__ void conv0_bwd_sums_kernel(const T* __restrict__ dy, const float* __r
   dst[C + c] = s2;
 }
 
-// totals per (utterance, channel) + the affine gradients: dbeta[c] += sum_b S1, dgamma[c] += sum_b S2
-__global__ void conv0_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ sums,
-                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int chunks) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c >= C) return;
+// totals per (utterance, channel) + the affine gradients: dbeta[c] += sum_b S1, dgamma[c] += sum_b S2 (same block shape
+// as conv0_finalize_kernel)
+__global__ void __launch_bounds__(64 * C0_FG)
+    conv0_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ sums, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int C, int chunks) {
+  __shared__ double red[2][C0_FG][64];
+  const int b = blockIdx.x, c = blockIdx.y * 64 + threadIdx.x, g = threadIdx.y;
+  const bool on = c < C;
   const float* p = part + (int64_t)b * chunks * 2 * C;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < chunks; ++i) {
-    s1 += (double)p[(int64_t)i * 2 * C + c];
-    s2 += (double)p[(int64_t)i * 2 * C + C + c];
+  if (on)
+    for (int i = g; i < chunks; i += C0_FG) {
+      s1 += (double)p[(int64_t)i * 2 * C + c];
+      s2 += (double)p[(int64_t)i * 2 * C + C + c];
+    }
+  red[0][g][threadIdx.x] = s1;
+  red[1][g][threadIdx.x] = s2;
+  __syncthreads();
+  if (g == 0 && on) {
+    s1 = s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < C0_FG; ++k) {
+      s1 += red[0][k][threadIdx.x];
+      s2 += red[1][k][threadIdx.x];
+    }
+    sums[(b * 2) * C + c] = (float)s1;
+    sums[(b * 2 + 1) * C + c] = (float)s2;
+    atomicAdd(dbeta + c, (float)s1);
+    atomicAdd(dgamma + c, (float)s2);
   }
-  sums[(b * 2) * C + c] = (float)s1;
-  sums[(b * 2 + 1) * C + c] = (float)s2;
-  atomicAdd(dbeta + c, (float)s1);
-  atomicAdd(dgamma + c, (float)s2);
 }
 
 // backward pass 2: dv = rstd * gamma * (g - S1/T - xhat * S2/T); per-block partial dW[c][k] = sum_t dv[t] * wave[t*S + k]
@@ -221,7 +259,7 @@ int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, cons
   const size_t smem = ((size_t)(C0_TCH - 1) * S + K) * sizeof(float);
   if (smem > 48 * 1024) return -5;
   conv0_stats_kernel<<<grid, block, smem, st>>>(wave, w, ws, n, T0, C, K, S);
-  conv0_finalize_kernel<<<B, block, 0, st>>>(ws, mean, rstd, T0, C, chunks, eps);
+  conv0_finalize_kernel<<<dim3(B, (C + 63) / 64), dim3(64, C0_FG), 0, st>>>(ws, mean, rstd, T0, C, chunks, eps);
   if (dtype == ST5_BF16)
     conv0_apply_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(wave, w, gamma, beta, mean, rstd,
                                                                  reinterpret_cast<__nv_bfloat16*>(y), n, T0, C, K, S, act);
@@ -246,13 +284,13 @@ int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const fl
     const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(dy);
     conv0_bwd_sums_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, ws, n, T0, C, K,
                                                                     S, act);
-    conv0_bwd_finalize_kernel<<<B, block, 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
+    conv0_bwd_finalize_kernel<<<dim3(B, (C + 63) / 64), dim3(64, C0_FG), 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
     conv0_bwd_w_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, sums, ws, n, T0, C,
                                                                  K, S, act);
   } else {
     const float* g = reinterpret_cast<const float*>(dy);
     conv0_bwd_sums_kernel<float><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, ws, n, T0, C, K, S, act);
-    conv0_bwd_finalize_kernel<<<B, block, 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
+    conv0_bwd_finalize_kernel<<<dim3(B, (C + 63) / 64), dim3(64, C0_FG), 0, st>>>(ws, sums, dgamma, dbeta, C, chunks);
     conv0_bwd_w_kernel<float><<<grid, block, smem, st>>>(g, wave, w, gamma, beta, mean, rstd, sums, ws, n, T0, C, K, S,
                                                          act);
   }

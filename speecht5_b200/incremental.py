@@ -229,6 +229,15 @@ class SynthesisGraph:
             span *= 2
         return min(span, self.cache.max_len)
 
+    def _snapshot(self):
+        """State the step body overwrites that a replay of the same step does not rewrite first (capture warm-up)."""
+        keep = self.ys_last.clone()
+
+        def undo():
+            self.seed_t -= 1  # (the pass drew from the seed the replay of this step must see)
+            self.ys_last.copy_(keep)
+        return undo
+
     @torch.no_grad()
     def run(self, t0, n):
         """Decoder steps t0 .. t0+n-1 (the device counter holds t0). Returns their stop flags (one device->host copy)."""
@@ -243,12 +252,10 @@ class SynthesisGraph:
                 # undone: the cache row / result rows it wrote are rewritten by the replay of the same step
                 self.stream.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(self.stream):
-                    keep = self.ys_last.clone()
+                    undo = self._snapshot()
                     self._body(span)
                     self.t -= 1
-                    if getattr(self, "seed_t", None) is not None:
-                        self.seed_t -= 1  # (the pass drew from the seed the replay of this step must see)
-                    self.ys_last.copy_(keep)
+                    undo()
                     self.stream.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.stream):
@@ -400,6 +407,14 @@ class GreedyGraph:
 
     _span = SynthesisGraph._span
     run = SynthesisGraph.run
+
+    def _snapshot(self):
+        done, lengths = self.done.clone(), self.lengths.clone()
+
+        def undo():  # (tokens[t+1] and stop[t] are rewritten by the replay; the finished flags are read-modify-write)
+            self.done.copy_(done)
+            self.lengths.copy_(lengths)
+        return undo
 
     @torch.no_grad()
     def decode(self, encoder_out, max_len, **kw):

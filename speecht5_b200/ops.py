@@ -50,6 +50,9 @@ class Runtime:
         self.stage_callback = None
         self.layer_keep = None
         self.layer_keep_host = None
+        # weight-gradient GEMMs on a second stream (trainer, single GPU, ST5_WGRAD_SIDE=1): see wgrad_mm / side_join
+        self.wgrad_stream = None
+        self._side_keep = []
 
     @property
     def seed(self):
@@ -81,6 +84,12 @@ class Runtime:
         else:
             self._seed += 1
         self._offset = 0
+
+    def side_join(self):
+        """The main stream waits for every weight-gradient launch issued on the side stream; their operands may go."""
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+        self._side_keep.clear()
 
     def stage(self, key, x):
         cb = self.stage_callback
@@ -252,6 +261,17 @@ def wgrad_mm(gy, gy_ld, xin, xin_ld, n_out, n_in, M, target=None):
                 S = cand
                 break
         chunk = M // S
+        side = RT.wgrad_stream
+        if side is not None:
+            # off the critical path: nothing downstream of this launch reads the gradient before the update, and the
+            # TMA reduce-adds commute. A second stream lets it fill the SMs the main chain leaves idle at every kernel
+            # boundary; the operands are kept alive until RT.side_join() (their memory must not be reused under it)
+            side.wait_stream(torch.cuda.current_stream())
+            RT._side_keep.append((gy[0], xin[0]))
+            with torch.cuda.stream(side):
+                K.gemm(gy[0], xin[0], target, M=n_out, N=n_in, K=chunk, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld,
+                       c_ld=n_in, nb1=S, nb2=1, a_bs=(chunk * gy_ld, 0), b_bs=(chunk * xin_ld, 0), c_bs=(0, 0), accumulate=2)
+            return None
         K.gemm(gy[0], xin[0], target, M=n_out, N=n_in, K=chunk, a_mn=True, a_ld=gy_ld, b_mn=True, b_ld=xin_ld,
                c_ld=n_in, nb1=S, nb2=1, a_bs=(chunk * gy_ld, 0), b_bs=(chunk * xin_ld, 0), c_bs=(0, 0), accumulate=2)
         return None

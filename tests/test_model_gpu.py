@@ -258,3 +258,44 @@ def test_text_to_text_branch_against_oracle(cuda, dtype, tol):
               "text_encoder_prenet.encoder_prenet.1.alpha"):
         assert got[n].grad is not None, n
         assert rel(got[n].grad, ref[n].grad) < gtol, (n, rel(got[n].grad, ref[n].grad))
+
+
+def test_trainer_graph_replay_and_prefetch_equal_the_eager_update(cuda):
+    """B200Trainer on the device (bf16, dropout off): three updates as replays of the captured graph -- once with the
+    batches copied by train_step itself, once through the input pipeline (`prefetch`: copy stream + staging buffers +
+    device->device into the graph's inputs) -- give the parameters of three eager updates, and the losses agree."""
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.data import synthetic_tts_batch
+    from speecht5_b200.models import make_args
+    from speecht5_b200.ops import RT
+    from speecht5_b200.tasks import SpeechT5Task
+    from speecht5_b200.trainer import B200Trainer
+    host = [synthetic_tts_batch(3, 24, 40, seed=10 + i, pin=True) for i in range(2)]
+    order = [0, 1, 0]
+    results = []
+    for mode in ("eager", "graph", "graph+prefetch"):
+        RT.dtype = torch.bfloat16
+        RT.manual_seed(1)
+        RT.clear_static()
+        RT.invalidate_shadows()
+        torch.manual_seed(0)
+        args = make_args("t5_transformer_base_asr", **TINY, **NO_DROPOUT, bert_init=True)
+        task = SpeechT5Task(args)
+        model = task.build_model(args).to(cuda).train()
+        tr = B200Trainer(model, SpeechT5Criterion(task, use_guided_attn_loss=True), task, lr=1e-3,
+                         use_cuda_graph=mode != "eager")
+        losses = []
+        for k, i in enumerate(order):
+            out = tr.train_step([host[i]])
+            if mode == "graph+prefetch" and k + 1 < len(order):
+                tr.prefetch([host[order[k + 1]]])
+            losses.append(float(out[0][0]))
+        torch.cuda.synchronize()
+        results.append((losses, tr.fp.flat.clone()))
+        assert tr.graph_misses == (0 if mode == "eager" else 1)
+    (l0, p0), (l1, p1), (l2, p2) = results
+    for a, b, c in zip(l0, l1, l2):
+        assert abs(a - b) < 2e-3 * abs(a) and abs(b - c) < 1e-5 * abs(b), (l0, l1, l2)
+    assert rel(p1, p0) < 1e-3 and rel(p2, p1) < 1e-5
+    RT.clear_static()
+    RT.invalidate_shadows()
