@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace st5 {
@@ -21,6 +22,13 @@ int set_error(int code, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: invalid argument (code %d)", where, code);
   }
   return code;
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ST5_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 }  // namespace st5
 

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(fl_threads<RPE>(), RPE ? 1 : 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // (prologue done: nothing above touched global memory)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -497,8 +498,8 @@ extern "C" int st5_attn_flash_fwd(const st5_attn_args* a, float* lse, void* psav
   p.seed = a->seed; p.offset = a->offset;
   dim3 grid((a->Tq + FL_T - 1) / FL_T, a->H, a->B);
   if (rpe)
-    attn_flash_fwd_kernel<true><<<grid, fl_threads<true>(), fl_smem<true>(), (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    launch_pdl(attn_flash_fwd_kernel<true>, grid, dim3(fl_threads<true>()), fl_smem<true>(), (cudaStream_t)stream, mq, mk, mv, mpe, p);
   else
-    attn_flash_fwd_kernel<false><<<grid, fl_threads<false>(), fl_smem<false>(), (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    launch_pdl(attn_flash_fwd_kernel<false>, grid, dim3(fl_threads<false>()), fl_smem<false>(), (cudaStream_t)stream, mq, mk, mv, mpe, p);
   return set_error((int)cudaGetLastError(), "st5_attn_flash_fwd");
 }

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // barriers and tensor memory are set up: wait for the producers of q / k / v before the first load
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -489,8 +490,8 @@ extern "C" int st5_attn_fused_fwd(const st5_attn_args* a, float* lse, void* psav
   p.pe_row0 = 1 + a->maxpos - FR_MAX_T;
   dim3 grid(a->H, a->B);  // one persistent CTA per (head, utterance)
   if (rpe)
-    attn_fused_fwd_kernel<true><<<grid, fa_threads<true>(), FR_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    launch_pdl(attn_fused_fwd_kernel<true>, dim3(grid), dim3(fa_threads<true>()), FR_SMEM, (cudaStream_t)stream, mq, mk, mv, mpe, p);
   else
-    attn_fused_fwd_kernel<false><<<grid, fa_threads<false>(), FA_SMEM, (cudaStream_t)stream>>>(mq, mk, mv, mpe, p);
+    launch_pdl(attn_fused_fwd_kernel<false>, dim3(grid), dim3(fa_threads<false>()), FA_SMEM, (cudaStream_t)stream, mq, mk, mv, mpe, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_fwd");
 }

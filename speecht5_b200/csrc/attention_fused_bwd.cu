@@ -58,6 +58,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
                                   const float* __restrict__ O32, long o_ld, long o_bs, const float* __restrict__ probs,
                                   const float* __restrict__ dpx, long p_ld, float* __restrict__ delta, int B, int H,
                                   int Tq, int Tk, int ext_heads) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t nrows = (int64_t)B * H * Tq;
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();  // (prologue done: nothing above touched global memory)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -484,10 +486,7 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
                (reinterpret_cast<uintptr_t>(a->out) & 15)))
     return set_error(-4, "st5_attn_fused_bwd: out / dout must be 16-byte aligned");
   const int64_t warps_needed = ext ? nrows : (nrows + 3) / 4;
-  attn_delta_kernel<<<(unsigned)((warps_needed + 7) / 8), 256, 0, s>>>(
-      (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs,
-      a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk,
-      ext_heads > 0 ? ext_heads : a->H);
+  launch_pdl(attn_delta_kernel, dim3((unsigned)((warps_needed + 7) / 8)), dim3(256), 0, s, (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs, a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk, ext_heads > 0 ? ext_heads : a->H);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
   CUtensorMap mq, mk, mv, mdo, mp;
@@ -521,6 +520,6 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
   p.ds_out = rpe ? reinterpret_cast<__nv_bfloat16*>(a->ds) : nullptr;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.ext_heads = ext_heads > 0 ? ext_heads : a->H;
-  attn_fused_bwd_kernel<<<dim3(a->H, a->B), FB_THREADS, FB_SMEM, s>>>(mq, mk, mv, mdo, mp, p);
+  launch_pdl(attn_fused_bwd_kernel, dim3(a->H, a->B), dim3(FB_THREADS), FB_SMEM, s, mq, mk, mv, mdo, mp, p);
   return set_error((int)cudaGetLastError(), "st5_attn_fused_bwd");
 }

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 __global__ void __launch_bounds__(ROW_WARPS * 32)
     attn_dqp_scatter_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dQP, int64_t nrows, int Tq,
                             int Tk, int64_t p_ld, int maxpos, int B, int H, int h_major) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= nrows) return;
@@ -199,8 +200,9 @@ int st5_attn_dqp_scatter(const void* ds_bf16, void* dqp_bf16, int32_t B, int32_t
                          int64_t p_ld, int32_t maxpos, int32_t h_major, void* stream) {
   const int64_t nrows = (int64_t)B * H * Tq;
   if (nrows == 0) return 0;
-  attn_dqp_scatter_kernel<<<(unsigned)((nrows + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)ds_bf16, (__nv_bfloat16*)dqp_bf16, nrows, Tq, Tk, p_ld, maxpos, B, H, h_major);
+  launch_pdl(attn_dqp_scatter_kernel, dim3((unsigned)((nrows + ROW_WARPS - 1) / ROW_WARPS)), dim3(ROW_WARPS * 32), 0,
+             (cudaStream_t)stream, (const __nv_bfloat16*)ds_bf16, (__nv_bfloat16*)dqp_bf16, nrows, Tq, Tk, p_ld, maxpos, B, H,
+             h_major);
   return set_error((int)cudaGetLastError(), "st5_attn_dqp_scatter");
 }
 

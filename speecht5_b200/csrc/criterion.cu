@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
                         const float* __restrict__ logits, const float* __restrict__ ys, int64_t y_bs,
                         const float* __restrict__ labels, int64_t lab_bs, const int64_t* __restrict__ olens, int B, int L,
                         int D, int r, float pos_weight, float* __restrict__ sums) {
+  pdl_sync();
   __shared__ float red[4][CR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * CR_WARPS + warp;
@@ -99,6 +100,7 @@ __device__ __forceinline__ void fixed_order_sum(const float* __restrict__ part, 
 // out: [0] l1, [1] l2, [2] bce  (means over the valid frames; an empty batch gives zeros)
 __global__ void __launch_bounds__(256)
     tts_loss_finalize_kernel(float* __restrict__ sums, int64_t nblk, int D, float* __restrict__ out) {
+  pdl_sync();
   fixed_order_sum<4>(sums + 4, nblk, sums);
   if (threadIdx.x == 0) {
     const float n = sums[3];
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
                         const float* __restrict__ sums, const float* __restrict__ g, int B, int L, int D, int r,
                         float pos_weight, float* __restrict__ d_after, float* __restrict__ d_before,
                         float* __restrict__ d_logits) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * CR_WARPS + warp;
   if (row >= (int64_t)B * L) return;
@@ -174,6 +177,7 @@ struct GuidedArgs {
 __global__ void __launch_bounds__(CR_WARPS * 32)
     guided_attn_fwd_kernel(const GuidedArgs p, const int64_t* __restrict__ ilens, const int64_t* __restrict__ olens,
                            float* __restrict__ gsum) {
+  pdl_sync();
   __shared__ float red[CR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t nrows = (int64_t)p.n_layers * p.B * p.heads * p.T_out;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32)
 __global__ void __launch_bounds__(256)
     guided_attn_finalize_kernel(const GuidedArgs p, const int64_t* __restrict__ ilens, const int64_t* __restrict__ olens,
                                 float* __restrict__ gsum, int64_t nblk, float* __restrict__ out) {
+  pdl_sync();
   fixed_order_sum<1>(gsum + 2, nblk, gsum);
   if (threadIdx.x >= 32) return;
   float n = 0.f;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(CR_WARPS * 32)
     guided_attn_bwd_kernel(const GuidedArgs p, const int64_t* __restrict__ ilens, const int64_t* __restrict__ olens,
                            const float* __restrict__ gsum, const float* __restrict__ g, int zero_rest) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hh = zero_rest ? p.H : p.heads;
   const int64_t nrows = (int64_t)p.n_layers * p.B * hh * p.T_out;
@@ -265,9 +271,8 @@ int tts_loss_fwd_launch(const float* after, const float* before, const float* lo
                         float pos_weight, float* sums, float* out, cudaStream_t s) {
   if (B <= 0 || L <= 0 || D <= 0 || r <= 0) return -2;
   const int64_t nblk = tts_loss_blocks(B, L);
-  tts_loss_fwd_kernel<<<(unsigned)nblk, CR_WARPS * 32, 0, s>>>(after, before, logits, ys, y_bs, labels, lab_bs, olens, B, L,
-                                                              D, r, pos_weight, sums);
-  tts_loss_finalize_kernel<<<1, 256, 0, s>>>(sums, nblk, D, out);
+  launch_pdl(tts_loss_fwd_kernel, dim3((unsigned)nblk), dim3(CR_WARPS * 32), 0, s, after, before, logits, ys, y_bs, labels, lab_bs, olens, B, L, D, r, pos_weight, sums);
+  launch_pdl(tts_loss_finalize_kernel, dim3(1), dim3(256), 0, s, sums, nblk, D, out);
   return (int)cudaGetLastError();
 }
 
@@ -277,8 +282,7 @@ int tts_loss_bwd_launch(const float* after, const float* before, const float* lo
                         cudaStream_t s) {
   if (B <= 0 || L <= 0 || D <= 0 || r <= 0) return -2;
   const int64_t rows = (int64_t)B * L;
-  tts_loss_bwd_kernel<<<(unsigned)((rows + CR_WARPS - 1) / CR_WARPS), CR_WARPS * 32, 0, s>>>(
-      after, before, logits, ys, y_bs, labels, lab_bs, olens, sums, g, B, L, D, r, pos_weight, d_after, d_before, d_logits);
+  launch_pdl(tts_loss_bwd_kernel, dim3((unsigned)((rows + CR_WARPS - 1) / CR_WARPS)), dim3(CR_WARPS * 32), 0, s, after, before, logits, ys, y_bs, labels, lab_bs, olens, sums, g, B, L, D, r, pos_weight, d_after, d_before, d_logits);
   return (int)cudaGetLastError();
 }
 
@@ -304,8 +308,8 @@ int guided_attn_fwd_launch(const float* const* att, int n_layers, int B, int H, 
   int rc = guided_fill(p, att, nullptr, n_layers, B, H, heads, T_out, T_in, p_ld, r, sigma, alpha);
   if (rc != 0) return rc;
   const int64_t nblk = guided_attn_blocks(n_layers, B, heads, T_out);
-  guided_attn_fwd_kernel<<<(unsigned)nblk, CR_WARPS * 32, 0, s>>>(p, ilens, olens, gsum);
-  guided_attn_finalize_kernel<<<1, 256, 0, s>>>(p, ilens, olens, gsum, nblk, out);
+  launch_pdl(guided_attn_fwd_kernel, dim3((unsigned)nblk), dim3(CR_WARPS * 32), 0, s, p, ilens, olens, gsum);
+  launch_pdl(guided_attn_finalize_kernel, dim3(1), dim3(256), 0, s, p, ilens, olens, gsum, nblk, out);
   return (int)cudaGetLastError();
 }
 
@@ -316,8 +320,7 @@ int guided_attn_bwd_launch(float* const* datt, int n_layers, int B, int H, int h
   int rc = guided_fill(p, nullptr, datt, n_layers, B, H, heads, T_out, T_in, p_ld, r, sigma, alpha);
   if (rc != 0) return rc;
   const int64_t rows = (int64_t)n_layers * B * (zero_rest ? H : heads) * T_out;
-  guided_attn_bwd_kernel<<<(unsigned)((rows + CR_WARPS - 1) / CR_WARPS), CR_WARPS * 32, 0, s>>>(p, ilens, olens, gsum, g,
-                                                                                                zero_rest);
+  launch_pdl(guided_attn_bwd_kernel, dim3((unsigned)((rows + CR_WARPS - 1) / CR_WARPS)), dim3(CR_WARPS * 32), 0, s, p, ilens, olens, gsum, g, zero_rest);
   return (int)cudaGetLastError();
 }
 

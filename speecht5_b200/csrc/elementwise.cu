@@ -14,6 +14,7 @@ static inline int grid_for(int64_t n, int threads) {
 // ------------------------------------------------------------------ fp32 -> bf16 (hi [, lo])
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t src_ld, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, int64_t dst_ld, int64_t rows, int64_t cols) {
+  pdl_sync();
   const int64_t n = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
@@ -26,8 +27,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int64_t src_ld, 
 int cast_bf16_launch(const float* src, int64_t src_ld, void* hi, void* lo, int64_t dst_ld, int64_t rows, int64_t cols,
                      cudaStream_t s) {
   if (rows * cols == 0) return 0;
-  cast_bf16_kernel<<<grid_for(rows * cols, 256), 256, 0, s>>>(src, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
-                                                              dst_ld, rows, cols);
+  launch_pdl(cast_bf16_kernel, dim3(grid_for(rows * cols, 256)), dim3(256), 0, s, src, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, dst_ld, rows, cols);
   return (int)cudaGetLastError();
 }
 
@@ -190,6 +190,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __rest
 template <typename T, int VEC>
 __global__ void colsum_vec_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows,
                                   int64_t cols, int64_t group_rows, int64_t rows_per_split, int mode) {
+  pdl_sync();
   const int64_t col = ((int64_t)blockIdx.x * 32 + threadIdx.x) * VEC;
   const int64_t g = blockIdx.y;
   const int64_t r0 = g * group_rows + (int64_t)blockIdx.z * rows_per_split;
@@ -257,10 +258,9 @@ int colsum_launch(const void* x, int64_t ld, float* out, int dtype, int64_t rows
     if (e != cudaSuccess) return (int)e;
   }
   if (vec_ok && dtype == ST5_F32)
-    colsum_vec_kernel<float, 4><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps, mode);
+    launch_pdl(colsum_vec_kernel<float, 4>, dim3(grid), dim3(block), 0, s, (const float*)x, ld, out, rows, cols, group_rows, rps, mode);
   else if (vec_ok)
-    colsum_vec_kernel<__nv_bfloat16, 8><<<grid, block, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols,
-                                                               group_rows, rps, mode);
+    launch_pdl(colsum_vec_kernel<__nv_bfloat16, 8>, dim3(grid), dim3(block), 0, s, (const __nv_bfloat16*)x, ld, out, rows, cols, group_rows, rps, mode);
   else if (dtype == ST5_F32)
     colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, out, rows, cols, group_rows, rps);
   else

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
                   float* __restrict__ y_f32, T* __restrict__ s_out, float* __restrict__ mean,
                   float* __restrict__ rstd, int64_t rows, int C, float eps, uint32_t thr, float dscale, uint64_t seed,
                   uint64_t offset) {
+  pdl_sync();
   if (thr != 0) resolve_seed(seed, offset);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -98,12 +99,10 @@ int ln_fwd_launch(const void* x, const void* residual, const float* residual_f32
   const float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   if (dtype == ST5_F32)
-    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>((const float*)x, (const float*)residual, residual_f32, gamma, beta,
-                                                        (float*)y, y_f32, (float*)s_out, mean, rstd, rows, (int)C, eps,
-                                                        thr, ds, seed, offset);
+    launch_pdl(ln_fwd_kernel<float>, dim3(grid), dim3(LN_WARPS * 32), 0, s, (const float*)x, (const float*)residual,
+               residual_f32, gamma, beta, (float*)y, y_f32, (float*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
   else
-    ln_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, s>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, residual_f32, gamma, beta, (__nv_bfloat16*)y, y_f32,
+    launch_pdl(ln_fwd_kernel<__nv_bfloat16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, residual_f32, gamma, beta, (__nv_bfloat16*)y, y_f32,
         (__nv_bfloat16*)s_out, mean, rstd, rows, (int)C, eps, thr, ds, seed, offset);
   return (int)cudaGetLastError();
 }
@@ -251,14 +250,18 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
                         uint64_t offset) {
   extern __shared__ __align__(16) float ln_acc[];  // [LNB_WARPS][LNB_NACC][C]; channel ch*8+t at (t>>2)*(C/2) + ch*4 + (t&3)
   constexpr bool PF = sizeof(T) == 2;  // one-row-ahead prefetch (24 registers for bf16; fp32 rows would need 48)
+  {  // (the strips are this CTA's own shared memory: cleared while the preceding grid drains)
+    float4* z = reinterpret_cast<float4*>(ln_acc);
+    for (int t = threadIdx.x; t < LNB_WARPS * LNB_NACC * (C >> 2); t += LNB_WARPS * 32) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_sync();
+  __syncthreads();
   if (thr != 0) resolve_seed(seed, offset);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = C >> 3;
   const int half4 = C >> 3;  // float4 index of the second half of an accumulator
   float4* acc = reinterpret_cast<float4*>(ln_acc + (size_t)warp * LNB_NACC * C);
   const int acc4 = C >> 2;   // float4 per accumulator
-  for (int t = lane; t < LNB_NACC * acc4; t += 32) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
   const int64_t stride = (int64_t)gridDim.x * LNB_WARPS;
   int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp;
   Raw8<T> cd[NCH], cs[NCH];
@@ -396,7 +399,7 @@ static int ln_bwd_fused_run(const void* dy, const void* s_in, const float* mean,
   const int64_t cap = 2 * (int64_t)device_sm_count();
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   const size_t smem = (size_t)LNB_WARPS * LNB_NACC * C * sizeof(float);
-  ln_bwd_fused_kernel<T, NCH><<<grid, LNB_WARPS * 32, smem, s>>>((const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds,
+  launch_pdl(ln_bwd_fused_kernel<T, NCH>, dim3(grid), dim3(LNB_WARPS * 32), smem, s, (const T*)dy, (const T*)s_in, mean, rstd, gamma, (T*)ds,
                                                                  (T*)dx, dgamma, dbeta, dxsum, rows, C, thr, dsc, seed, offset);
   return 0;
 }

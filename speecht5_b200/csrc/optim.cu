@@ -7,6 +7,7 @@
 namespace st5 {
 
 __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  pdl_sync();
   float acc = 0.f;
   const int64_t n4 = n / 4;
   const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -32,7 +33,7 @@ int sumsq_launch(const float* x, int64_t n, float* out, cudaStream_t s) {
   int64_t g = (n / 4 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
   if (g < 1) g = 1;
-  sumsq_kernel<<<(unsigned)g, 256, 0, s>>>(x, n, out);
+  launch_pdl(sumsq_kernel, dim3((unsigned)g), dim3(256), 0, s, x, n, out);
   return (int)cudaGetLastError();
 }
 
@@ -41,6 +42,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float beta2, float eps, float wd, float step_size, const float* __restrict__ gnorm_sq,
                             float max_norm, float grad_mul, const float* __restrict__ lr_dev,
                             const int64_t* __restrict__ step_dev) {
+  pdl_sync();
   if (lr_dev != nullptr) lr = *lr_dev;
   if (step_dev != nullptr) {  // device-resident schedule state: a captured CUDA graph stays valid across updates
     const float t = (float)(*step_dev);
@@ -106,8 +108,7 @@ int adam_launch(float* p, const float* g, float* m, float* v, void* p_bf16, int6
   }
   int64_t gsz = (n + 255) / 256;
   if (gsz > 148 * 16) gsz = 148 * 16;
-  adam_kernel<<<(unsigned)gsz, 256, 0, s>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay,
-                                            step_size, grad_norm_sq, max_norm, grad_mul, lr_dev, step_dev);
+  launch_pdl(adam_kernel, dim3((unsigned)gsz), dim3(256), 0, s, p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, step_size, grad_norm_sq, max_norm, grad_mul, lr_dev, step_dev);
   return (int)cudaGetLastError();
 }
 

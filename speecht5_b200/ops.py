@@ -87,8 +87,8 @@ class Runtime:
 
     def side_join(self):
         """The main stream waits for every weight-gradient launch issued on the side stream; their operands may go."""
-        if self.wgrad_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+        if self.wgrad_stream is not None and self._side_keep:  # (only when something was issued there since the last
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)  # join: a capture may not wait on foreign work)
         self._side_keep.clear()
 
     def stage(self, key, x):

@@ -270,7 +270,7 @@ class B200Trainer:
             fn()
             return
         self._side.wait_stream(torch.cuda.current_stream())
-        if RT.wgrad_stream is not None:  # the weight gradients this collective moves were written on that stream
+        if RT.wgrad_stream is not None and RT._side_keep:  # the weight gradients this collective moves were written there
             self._side.wait_stream(RT.wgrad_stream)
         with torch.cuda.stream(self._side):
             fn()
