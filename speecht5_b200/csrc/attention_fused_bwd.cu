@@ -110,6 +110,25 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __
   if (lane == 0) delta[row] = acc;
 }
 
+// delta[b][h][i] += sum_j P[b][h][i][j] * dP_ext[b][h][i][j] for the heads that carry an external gradient on their
+// probabilities (h < ext_heads): one warp per (b, h < ext_heads, i) row. With the guided-attention loss that is 2 of 12
+// heads -- the other rows take the 8-lanes-per-row path of attn_delta_kernel and are not visited here.
+__global__ void attn_delta_ext_kernel(const float* __restrict__ probs, const float* __restrict__ dpx, long p_ld,
+                                      float* __restrict__ delta, int B, int H, int Tq, int Tk, int ext_heads) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)B * ext_heads * Tq) return;
+  const int i = (int)(w % Tq), h = (int)((w / Tq) % ext_heads), b = (int)(w / ((int64_t)Tq * ext_heads));
+  const int64_t row = ((int64_t)b * H + h) * Tq + i;
+  const float* pr = probs + row * p_ld;
+  const float* dx = dpx + row * p_ld;
+  float acc = 0.f;
+  for (int j = lane; j < Tk; j += 32) acc += pr[j] * dx[j];
+  acc = warp_sum(acc);
+  if (lane == 0) delta[row] += acc;
+}
+
 __global__ void __launch_bounds__(FB_THREADS, 1)  // (18 warps are allocated as 20: 96 registers is the ceiling)
     attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
@@ -485,8 +504,21 @@ extern "C" int st5_attn_fused_bwd(const st5_attn_args* a, const void* psave, con
   if (!ext && ((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->dout) & 15) ||
                (reinterpret_cast<uintptr_t>(a->out) & 15)))
     return set_error(-4, "st5_attn_fused_bwd: out / dout must be 16-byte aligned");
-  const int64_t warps_needed = ext ? nrows : (nrows + 3) / 4;
-  launch_pdl(attn_delta_kernel, dim3((unsigned)((warps_needed + 7) / 8)), dim3(256), 0, s, (const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs, a->dprobs_ext ? (const float*)a->probs : nullptr, a->dprobs_ext, a->p_ld, delta, a->B, a->H, a->Tq, a->Tk, ext_heads > 0 ? ext_heads : a->H);
+  const int eh = ext_heads > 0 && ext_heads < a->H ? ext_heads : a->H;
+  // external dP on a few heads only (and vector-loadable outputs): every row takes the cheap dO.O path, a second small
+  // launch adds sum_j P dP_ext on the rows of those heads (33.7 -> ~15 us per guided layer at the benched shape)
+  const bool split = ext && eh < a->H && !((a->o_ld & 7) || (a->o_bs & 7) || (reinterpret_cast<uintptr_t>(a->dout) & 15) ||
+                                           (reinterpret_cast<uintptr_t>(a->out) & 15));
+  const int64_t warps_needed = (ext && !split) ? nrows : (nrows + 3) / 4;
+  launch_pdl(attn_delta_kernel, dim3((unsigned)((warps_needed + 7) / 8)), dim3(256), 0, s, (const __nv_bfloat16*)a->dout,
+             (const __nv_bfloat16*)a->out, out_f32, a->o_ld, a->o_bs,
+             (ext && !split) ? (const float*)a->probs : (const float*)nullptr, split ? (const float*)nullptr : a->dprobs_ext,
+             a->p_ld, delta, a->B, a->H, a->Tq, a->Tk, eh);
+  if (split) {
+    const int64_t wext = (int64_t)a->B * eh * a->Tq;
+    launch_pdl(attn_delta_ext_kernel, dim3((unsigned)((wext + 7) / 8)), dim3(256), 0, s, (const float*)a->probs, a->dprobs_ext,
+               a->p_ld, delta, a->B, a->H, a->Tq, a->Tk, eh);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "st5_attn_fused_bwd(delta)");
   CUtensorMap mq, mk, mv, mdo, mp;

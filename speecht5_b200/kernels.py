@@ -209,7 +209,7 @@ def attn_fused_bwd(a, psave, inv_l, out_f32, delta, dq_acc, ext_heads=0):
     _lib.check(lib.st5_attn_fused_bwd(C.byref(a), _ptr(psave), _ptr(inv_l), _ptr(out_f32), _ptr(delta), _ptr(dq_acc),
                                       int(ext_heads), _stream()),
                "st5_attn_fused_bwd")
-    _count(2)
+    _count(3 if (a.dprobs_ext and 0 < int(ext_heads) < a.H) else 2)  # (+ the guided heads' row-constant launch)
 
 
 

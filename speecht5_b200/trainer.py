@@ -216,6 +216,7 @@ class B200Trainer:
         # other heads' probabilities at all (77 MB of fp32 per decoder layer at the benched shape). Scoped to train_step.
         self._probs_read_heads = RT.probs_grad_heads
         self._prefetched, self._staging, self._staging_read = None, {}, None
+        self._gate_thresholds = None
         self._wgrad_side = False  # (set below once the world size is known)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -491,10 +492,11 @@ class B200Trainer:
     # ------------------------------------------------------------------ public step
     def _signature(self, samples):
         shapes = tuple(tuple((k, tuple(v.shape)) for k, v in _flatten(s).items()) + (s.get("task_name"),) for s in samples)
-        gates = tuple(getattr(m, "freeze_encoder_updates", 0) <= self.num_updates for m in self.model.modules()
-                      if hasattr(m, "freeze_encoder_updates"))
-        gates += tuple(getattr(m, "freeze_decoder_updates", 0) <= self.num_updates for m in self.model.modules()
-                       if hasattr(m, "freeze_decoder_updates"))
+        if self._gate_thresholds is None:  # (walking ~500 modules every update cost more host time than the replay call)
+            self._gate_thresholds = tuple(
+                [getattr(m, "freeze_encoder_updates", 0) for m in self.model.modules() if hasattr(m, "freeze_encoder_updates")]
+                + [getattr(m, "freeze_decoder_updates", 0) for m in self.model.modules() if hasattr(m, "freeze_decoder_updates")])
+        gates = tuple(t <= self.num_updates for t in self._gate_thresholds)
         return shapes, gates, self.model.training
 
     def train_step(self, samples, lr=None):
@@ -541,11 +543,15 @@ class B200Trainer:
         else:
             self.graph_hits += 1
             self._graphs.move_to_end(sig)
-        graph, static_samples, static_out = ent
+        graph, static_samples, static_out, static_flat = ent
         if staged is not None:  # the host->device copies ran under the previous update: device->device into the graph's inputs
             torch.cuda.current_stream().wait_event(ready)
-            for st, s in zip(static_samples, staged):
-                _copy_into(st, s)
+            staged_views, staged_flat = staged
+            if staged_flat.numel() == static_flat.numel():
+                static_flat.copy_(staged_flat, non_blocking=True)  # both sets are views of one byte buffer: ONE copy
+            else:
+                for st, s in zip(static_samples, staged_views):
+                    _copy_into(st, s)
             self._staging_read = torch.cuda.Event()
             self._staging_read.record()
         else:
@@ -575,13 +581,13 @@ class B200Trainer:
             if staging is None:
                 if len(self._staging) >= 8:
                     self._staging.pop(next(iter(self._staging)))
-                staging = self._staging[shapes] = [_to_device(s, self.device) for s in samples]
+                staging = self._staging[shapes] = _to_device_packed(samples, self.device)
             else:
                 # the last reader of these buffers: the device->device copies train_step issued BEFORE its graph replay
                 # (waiting for the main stream itself would put this copy behind the update it is meant to hide under)
                 if self._staging_read is not None:
                     self._h2d_stream.wait_event(self._staging_read)
-                for st, s in zip(staging, samples):
+                for st, s in zip(staging[0], samples):
                     _copy_into(st, s)
             ready = torch.cuda.Event()
             ready.record(self._h2d_stream)
@@ -593,7 +599,7 @@ class B200Trainer:
         return self._cap_stream
 
     def _capture(self, samples, sig):
-        static_samples = [_to_device(s, self.device) for s in samples]
+        static_samples, static_flat = _to_device_packed(samples, self.device)
         if not self._warmed:
             # ONE eager update outside capture, first capture only (lazy inits: NCCL communicator, allocator pools,
             # module caches); every rank reaches it at its first step, so the collectives it issues pair up. It is a real
@@ -627,7 +633,7 @@ class B200Trainer:
         with torch.cuda.graph(graph, stream=self._capture_stream()):
             static_out = self._update(static_samples)
         torch.cuda.synchronize()
-        ent = (graph, static_samples, static_out)
+        ent = (graph, static_samples, static_out, static_flat)
         self._graphs[sig] = ent
         while len(self._graphs) > self.graph_cache_size:
             self._graphs.popitem(last=False)
@@ -702,6 +708,31 @@ def _to_device(sample, dev):
     if isinstance(sample, dict):
         return {k: _to_device(v, dev) for k, v in sample.items()}
     return sample
+
+
+def _to_device_packed(samples, dev):
+    """Device copies of a list of micro-batches whose tensors are views of ONE byte buffer (every tensor 256-byte
+    aligned): a second set made the same way can be moved over it with a single device->device copy. Returns
+    (list of dicts with the samples' structure, the byte buffer)."""
+    sizes, total = [], 0
+    for s in samples:
+        for v in _flatten(s).values():
+            n = v.numel() * v.element_size()
+            sizes.append((total, n))
+            total += (n + 255) // 256 * 256
+    flat = torch.empty(max(total, 256), dtype=torch.uint8, device=dev)
+    it = iter(sizes)
+
+    def build(x):
+        if torch.is_tensor(x):
+            off, n = next(it)
+            view = flat[off:off + n].view(x.dtype).view(x.shape)
+            view.copy_(x, non_blocking=True)
+            return view
+        if isinstance(x, dict):
+            return {k: build(v) for k, v in x.items()}
+        return x
+    return [build(s) for s in samples], flat
 
 
 def _copy_into(static, new):
