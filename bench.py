@@ -718,7 +718,8 @@ def main():
     # under ncu (cold L2 per launch), so it is an upper bound of what the warm step moves
     traffic, traffic_note = None, "no ncu traffic file committed"
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+        tj = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
         traffic = tj["dram_bytes_per_launch"]
         traffic_note = tj.get("note", "")
     except Exception:  # noqa: BLE001

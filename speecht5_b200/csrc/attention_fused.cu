@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
     float m = -INFINITY;
 #pragma unroll 1
     for (int c = half; c < nchunks; c += NG) {
-      if (RPE && c * 32 >= tk) continue;  // warp-uniform: nothing visible in this chunk (pass 2 masks it by vb == 0)
+      if (c * 32 >= tk) continue;  // warp-uniform: nothing visible in this chunk (pass 2 writes its zeros)
       uint32_t v[32];
       tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
       const uint32_t vb = valid_bits(c);
@@ -315,6 +315,19 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
     // The normaliser is applied to O at the end (PV is linear in P).
     float sum = 0.f;
     for (int c = half; c < nchunks; c += NG) {
+      uint8_t* blk = sP + (c >> 1) * 16384 + r * 128;  // block = 64 keys, row r at r*128 B, chunk XOR (r & 7)
+      const int cbase = (c & 1) * 4;
+      if (c * 32 >= tk) {
+        // warp-uniform: the whole chunk lies beyond the keys (T_k = 160: the second half of the third 64-key block).
+        // P is zero there -- the operand tile needs the zeros, the saved exponentials too -- nothing else to do
+        __nv_bfloat16* pz = (p.psave != nullptr && row_ok) ? p.psave + prow * p.p_ld + c * 32 : nullptr;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(blk + (((cbase + g) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          if (pz != nullptr && c * 32 + 8 * g + 8 <= p.p_ld) *reinterpret_cast<uint4*>(pz + 8 * g) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
       uint32_t v[32];
       tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
       const uint32_t vb = valid_bits(c);
@@ -322,8 +335,6 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       if (p.drop_thr != 0)
         kb_ = dropout_keep_mask32(dseed, doffset, (uint64_t)prow * attn_drop_pitch(p.Tk) + (uint64_t)(c * 32), p.drop_thr);
       tmem_ld_wait();
-      uint8_t* blk = sP + (c >> 1) * 16384 + r * 128;  // block = 64 keys, row r at r*128 B, chunk XOR (r & 7)
-      const int cbase = (c & 1) * 4;
       // what the backward pass reads back: the un-normalised exponentials, a dropped element carries the sign bit
       // (probabilities are non-negative, so the bit is free; -0 for a dropped zero): no Philox and no exp there
       __nv_bfloat16* psv = (p.psave != nullptr && row_ok) ? p.psave + prow * p.p_ld + c * 32 : nullptr;
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(fa_threads<RPE>(), 1)
       const int pchunks = warp_ok ? (int)((p.p_ld + 31) / 32) : 0;
       for (int c = half; c < pchunks; c += NG) {
         float pr[32];
-        if (c < nchunks) {
+        if (c < nchunks && c * 32 < tk) {
           uint32_t v[32];
           tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
           const uint32_t vb = valid_bits(c);

@@ -546,7 +546,9 @@ def test_cross_attention_backward_with_a_gradient_on_two_heads_only(cuda):
         torch.autograd.backward([out, probs], [g, gp])
         res.append((qb.grad, kvb.grad))
     ops.RT.probs_grad_heads = 0
-    assert rel(res[1][0], res[0][0]) < 1e-6 and rel(res[1][1], res[0][1]) < 1e-6
+    # (the guided heads' row constant is summed in two launches -- dO.O on the vector path, sum P dP_ext per warp -- so
+    #  its fp32 order differs from the all-heads form: an occasional last-bit flip of a bf16 gradient)
+    assert rel(res[1][0], res[0][0]) < 2e-4 and rel(res[1][1], res[0][1]) < 2e-4
 
 
 @pytest.mark.parametrize("r,B,L,D,Ly", [(2, 5, 62, 80, 64), (1, 3, 33, 80, 33), (2, 4, 20, 30, 27)])
@@ -637,4 +639,4 @@ def test_returned_probabilities_for_the_first_heads_only(cuda, Tq, Tk):
     (o0, p0, dq0, dk0, g0), (o1, p1, dq1, dk1, g1) = res
     assert torch.equal(o0, o1) and torch.equal(p0, p1)
     assert (p1[0].sum(-1) - 1).abs().max() < 1e-3
-    assert rel(dq1, dq0) < 1e-5 and rel(dk1, dk0) < 1e-5
+    assert rel(dq1, dq0) < 2e-4 and rel(dk1, dk0) < 2e-4  # (row constants summed in a different fp32 order)
