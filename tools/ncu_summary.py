@@ -11,11 +11,12 @@ rows = list(csv.reader(open(path)))
 hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[hi]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+mi = hdr.index("Metric Name") if "Metric Name" in hdr else None  # (lists with several metrics per launch: durations only)
 agg = collections.defaultdict(lambda: [0, 0.0])
 gemm = []
 tot = 0.0
 for r in rows[hi + 1:]:
-    if len(r) <= vi:
+    if len(r) <= vi or (mi is not None and r[mi] != "gpu__time_duration.sum"):
         continue
     v = float(r[vi].replace(",", ""))
     v = v / 1000.0 if r[ui] == "ns" else (v * 1000.0 if r[ui] == "ms" else v)
