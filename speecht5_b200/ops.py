@@ -53,6 +53,7 @@ class Runtime:
         # weight-gradient GEMMs on a second stream (trainer, single GPU, ST5_WGRAD_SIDE=1): see wgrad_mm / side_join
         self.wgrad_stream = None
         self._side_keep = []
+        self.side_small = os.environ.get("ST5_SIDE_SMALL", "1") != "0"  # bias / table gradients ride on that stream too
 
     @property
     def seed(self):
@@ -186,6 +187,20 @@ def mm(a, b, out, *, M, N, Kd, a_mn=False, b_mn=False, a_ld=None, b_ld=None, c_l
 
 def _pad8(n):
     return (n + 7) // 8 * 8
+
+
+def _off_critical_path(fn, *keep):
+    """Run a launch whose result nothing reads before the optimizer (a gradient accumulated into the trainer's flat
+    buffer) on the weight-gradient stream when the trainer opened one: the main chain does not wait for it, its operands
+    are kept alive until RT.side_join()."""
+    side = RT.wgrad_stream if RT.side_small else None
+    if side is None:
+        fn()
+        return
+    side.wait_stream(torch.cuda.current_stream())
+    RT._side_keep.append(keep)
+    with torch.cuda.stream(side):
+        fn()
 
 
 def _key_pad_u8(key_pad):
@@ -417,7 +432,7 @@ class LinearFn(torch.autograd.Function):
             elif len(biases) > 0:
                 gB = RT._static_grad.get(("bias",) + tuple(id(b) for b in biases))
                 if gB is not None:
-                    K.colsum(dpre, gB, ld=dpre_ld, accumulate=True)
+                    _off_critical_path(lambda: K.colsum(dpre, gB, ld=dpre_ld, accumulate=True), dpre, dy)
                     grads_b = [None] * len(biases)
                 else:
                     db = torch.empty(N, dtype=torch.float32, device=dev)
@@ -541,7 +556,7 @@ class FFNFn(torch.autograd.Function):
         def bgrad(gy2d, b):
             gB = RT._static_grad.get(("bias", id(b)))
             if gB is not None:
-                K.colsum(gy2d, gB, accumulate=True)
+                _off_critical_path(lambda: K.colsum(gy2d, gB, accumulate=True), gy2d)
                 return None
             db = torch.empty(b.shape[0], dtype=torch.float32, device=dev)
             K.colsum(gy2d, db)
@@ -860,8 +875,14 @@ class AttentionTCFn(torch.autograd.Function):
             if target is not None and (target.data_ptr() % 16 != 0 or not target.is_contiguous()):
                 target = None
             dpe = target if target is not None else torch.zeros((R, 64), dtype=torch.float32, device=dev)
-            K.gemm(dQP, qv, dpe, M=R, N=64, K=chunk, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=S,
-                   a_bs=(rows * R, chunk * R), b_bs=(64, chunk * q_ld), c_bs=(0, 0), alpha=scale, accumulate=2)
+
+            def table_grad():
+                K.gemm(dQP, qv, dpe, M=R, N=64, K=chunk, a_mn=True, a_ld=R, b_mn=True, b_ld=q_ld, c_ld=64, nb1=H, nb2=S,
+                       a_bs=(rows * R, chunk * R), b_bs=(64, chunk * q_ld), c_bs=(0, 0), alpha=scale, accumulate=2)
+            if target is not None:
+                _off_critical_path(table_grad, dQP, q_buf)
+            else:
+                table_grad()
             return dq_buf, None, (None if target is not None else dpe), None, None
         dQP = torch.empty((B, H, Tq, R), dtype=torch.bfloat16, device=dev)
         K.attn_dqp_scatter(dS, dQP, B, H, Tq, Tk, p_ld, maxpos)

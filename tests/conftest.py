@@ -31,6 +31,10 @@ def _reset_runtime_hints():
     try:
         from speecht5_b200.ops import RT
         RT.probs_grad_heads = 0
+        RT.probs_read_heads = 0
         RT.stage_callback = None
+        RT.clear_static()  # (flat-buffer views keyed by id(parameter): a later test's parameters may reuse the ids)
+        RT.wgrad_stream = None
+        RT._side_keep.clear()
     except Exception:  # noqa: BLE001  (package not importable in a collection-only run)
         pass
