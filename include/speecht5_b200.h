@@ -114,6 +114,13 @@ int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rs
                void* dx, float* dgamma, float* dbeta, float* dxsum, int dtype, int64_t rows, int64_t C, float drop_p,
                uint64_t seed, uint64_t offset, void* stream);
 
+/* HiFi-GAN operand staging (SpeechUT/fairseq/fairseq/models/text_to_speech/hifigan.py:70-100, 154-170: F.leaky_relu
+ * before every convolution): out[b][m][:] = leaky_relu(x[b][ph + d*m - pad][:], slope) for source frames inside [0, T),
+ * zeros outside -- the zero-padded (d = 1) or de-interleaved (phase ph of dilation d) bf16 operand of the window GEMM in
+ * one pass. x [B, T, C], out [B, n_in, C], C a multiple of 8; slope = 1 copies. */
+int st5_lrelu_pad(const void* x, void* out, int64_t B, int64_t T, int64_t C, int64_t n_in, int32_t d, int32_t ph,
+                  int32_t pad, float slope, void* stream);
+
 /* y = dropout(x) (also its own backward when applied to the gradient). fairseq/modules/fairseq_dropout.py:23-37
  * (F.dropout semantics: keep with probability 1-p, scale by 1/(1-p)); mask = the counter-based generator above. */
 int st5_dropout(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,

@@ -104,6 +104,11 @@ int st5_ln_bwd(const void* dy, const void* s, const float* mean, const float* rs
                    "st5_ln_bwd");
 }
 
+int st5_lrelu_pad(const void* x, void* out, int64_t B, int64_t T, int64_t C, int64_t n_in, int32_t d, int32_t ph,
+                  int32_t pad, float slope, void* stream) {
+  return set_error(lrelu_pad_launch(x, out, B, T, C, n_in, d, ph, pad, slope, (cudaStream_t)stream), "st5_lrelu_pad");
+}
+
 int st5_dropout(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
                 void* stream) {
   return set_error(dropout_launch(x, y, dtype, n, drop_p, seed, offset, (cudaStream_t)stream), "st5_dropout");

@@ -202,6 +202,41 @@ int posenc_bwd_launch(const void* dy, const int64_t* tokens, int64_t padding_idx
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ leaky-ReLU into a padded / de-interleaved operand
+// HiFi-GAN (SpeechUT/.../hifigan.py:70-100,154-170): every convolution is preceded by a leaky-ReLU and consumed here as a
+// window GEMM over a zero-padded copy of its input; dilated convolutions read one PHASE (frames ph, ph+d, ...) of it.
+// out[b][m][:] = lrelu(x[b][ph + d*m - pad][:]) for frames inside [0, T), zeros outside: one pass instead of the
+// activation, the zero fill and the strided copy (three launches, two extra round trips of the activations).
+__global__ void lrelu_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t B,
+                                 int64_t T, int64_t C, int64_t n_in, int d, int ph, int pad, float slope) {
+  pdl_sync();
+  const int64_t cpr = C >> 3, n8 = B * n_in * cpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / cpr, c = (i - row * cpr) * 8;
+    const int64_t b = row / n_in, m = row - b * n_in;
+    const int64_t xi = (int64_t)ph + (int64_t)d * m - pad;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (xi >= 0 && xi < T) {
+      float v[8];
+      load8<__nv_bfloat16>(x + (b * T + xi) * C + c, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    }
+    *reinterpret_cast<uint4*>(out + row * C + c) = o;
+  }
+}
+int lrelu_pad_launch(const void* x, void* out, int64_t B, int64_t T, int64_t C, int64_t n_in, int d, int ph, int pad,
+                     float slope, cudaStream_t s) {
+  if (B <= 0 || T <= 0 || C <= 0 || (C & 7) || n_in <= 0 || d <= 0 || ph < 0 || ph >= d || !aligned16(x) || !aligned16(out))
+    return -2;
+  launch_pdl(lrelu_pad_kernel, dim3(grid_for(B * n_in * (C >> 3), 256)), dim3(256), 0, s, (const __nv_bfloat16*)x,
+             (__nv_bfloat16*)out, B, T, C, n_in, d, ph, pad, slope);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ dropout
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, uint32_t thr, float dscale,

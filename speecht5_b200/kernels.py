@@ -147,6 +147,17 @@ def ln_bwd(dy, s, mean, rstd, gamma, ds, dx, dgamma, dbeta, drop_p=0.0, seed=0, 
     _count(1 if fused or (dgamma is None and dbeta is None) else 2)
 
 
+def lrelu_pad(x, out, d, ph, pad, slope):
+    """st5_lrelu_pad: out [B, n_in, C] <- leaky_relu(x [B, T, C]) at frames ph + d*m - pad (zeros outside [0, T))."""
+    _require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    B, T, Cc = x.shape
+    assert out.shape[0] == B and out.shape[2] == Cc
+    _lib.check(_lib.load().st5_lrelu_pad(_ptr(x), _ptr(out), B, T, Cc, out.shape[1], int(d), int(ph), int(pad),
+                                         float(slope), _stream()), "st5_lrelu_pad")
+    _count(1)
+
+
 def dropout(x, y, drop_p, seed, offset):
     lib = _lib.load()
     _lib.check(lib.st5_dropout(_ptr(x), _ptr(y), dtype_id(x), x.numel(), drop_p, seed, offset, _stream()),

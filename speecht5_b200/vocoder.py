@@ -1,7 +1,7 @@
 """HiFi-GAN generator (mel -> waveform) on the device, inference only (reference: the sibling
 tree's SpeechUT/fairseq/fairseq/models/text_to_speech/hifigan.py:13-170 with the SpeechT5 vocoder configuration).
 
-EXPERIMENTAL -- written at the end of round 1 without GPU time. Every convolution is a window GEMM on the existing
+Every convolution is a window GEMM on the existing
 tcgen05 kernel over channels-last activations (no im2col); the operand views are checked on the CPU through the GEMM
 emulator against oracle/audio_oracle.py:HifiGanGenerator (tests/test_frontend_cpu.py).
 
@@ -11,8 +11,8 @@ emulator against oracle/audio_oracle.py:HifiGanGenerator (tests/test_frontend_cp
   output frames r, r+u, ... (row pitch u*C_out).
 * dilated Conv1d(dilation d): the leaky-ReLU that precedes it writes its result de-interleaved into d phase buffers
   (frame t -> phase t mod d); inside a phase the dilation is 1, and each phase GEMM writes its rows back with pitch d*C.
-Leaky-ReLU, padding / de-interleaving copies and the ResBlock averaging are torch elementwise calls for now: fusing
-them into the producing epilogue needs a leaky-ReLU epilogue kind (round 2)."""
+The leaky-ReLU, the zero padding and the de-interleave of every convolution input are ONE launch (st5_lrelu_pad); the
+ResBlock averaging is a torch elementwise call."""
 import torch
 import torch.nn.functional as F
 
@@ -54,7 +54,7 @@ def _conv_same(x, conv, out=None, act=None, residual=None, pre_act_slope=None):
     input while it is copied into the padded / de-interleaved operand buffer."""
     B, T, Cin = x.shape
     k, d, Cout = conv.k, conv.d, conv.cout
-    xin = F.leaky_relu(x, pre_act_slope) if pre_act_slope is not None else x
+    x = x.contiguous()
     pad = (k * d - d) // 2
     y = out if out is not None else torch.empty((B, T, Cout), dtype=torch.bfloat16, device=x.device)
     for ph in range(d):
@@ -63,13 +63,10 @@ def _conv_same(x, conv, out=None, act=None, residual=None, pre_act_slope=None):
         if n_out <= 0:
             continue
         n_in = n_out + k - 1
-        buf = torch.zeros((B, n_in, Cin), dtype=torch.bfloat16, device=x.device)
-        # padded index p = ph + d*i  <->  x index p - pad
-        i0 = max(0, -((ph - pad) // d))  # first i with ph + d*i - pad >= 0
-        first = ph + d * i0 - pad
-        src = xin[:, first::d]
-        n_copy = min(src.shape[1], n_in - i0)
-        buf[:, i0:i0 + n_copy] = src[:, :n_copy]
+        # phase-frame i is padded index ph + d*i, i.e. x frame ph + d*i - pad: activation, zero borders and the
+        # de-interleave in ONE launch (st5_lrelu_pad; slope 1 = plain copy)
+        buf = torch.empty((B, n_in, Cin), dtype=torch.bfloat16, device=x.device)
+        K.lrelu_pad(x, buf, d, ph, pad, pre_act_slope if pre_act_slope is not None else 1.0)
         kw = dict(M=n_out, N=Cout, K=k * Cin, a_ld=Cin, b_ld=conv.ld, c_ld=d * Cout, nb1=B, nb2=1, a_bs=(n_in * Cin, 0),
                   b_bs=(0, 0), c_bs=(T * Cout, 0), bias=conv.bias, act=act)
         if residual is not None:
@@ -98,10 +95,9 @@ class _ConvT:
 
 def _conv_transpose(x, ct, pre_act_slope=None):
     B, T, Cin = x.shape
-    xin = F.leaky_relu(x, pre_act_slope) if pre_act_slope is not None else x
     fr = ct.taps - 1
-    buf = torch.zeros((B, T + 2 * fr, Cin), dtype=torch.bfloat16, device=x.device)
-    buf[:, fr:fr + T] = xin
+    buf = torch.empty((B, T + 2 * fr, Cin), dtype=torch.bfloat16, device=x.device)
+    K.lrelu_pad(x.contiguous(), buf, 1, 0, fr, pre_act_slope if pre_act_slope is not None else 1.0)
     y = torch.empty((B, T * ct.u, ct.cout), dtype=torch.bfloat16, device=x.device)
     Tp = T + 2 * fr
     for r, (d0, nt, w, ld) in enumerate(ct.phases):

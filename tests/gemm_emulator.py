@@ -86,6 +86,17 @@ def cast_bf16(src, hi, lo=None):
         lo.copy_((src - h.float()).to(torch.bfloat16))
 
 
+def lrelu_pad(x, out, d, ph, pad, slope):
+    """st5_lrelu_pad: out[b, m] = leaky_relu(x[b, ph + d*m - pad]) inside [0, T), zeros outside."""
+    B, T, C = x.shape
+    n_in = out.shape[1]
+    idx = ph + d * torch.arange(n_in) - pad
+    ok = (idx >= 0) & (idx < T)
+    out.zero_()
+    v = x[:, idx[ok]].float()
+    out[:, ok] = torch.where(v > 0, v, v * slope).to(out.dtype)
+
+
 def act_bwd(dy, pre, dpre, act, drop_p=0.0, seed=0, offset=0):
     assert drop_p == 0.0
     dpre.copy_((dy.double() * _act_grad(pre.double(), act)).to(dpre.dtype))
@@ -257,6 +268,7 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "gemm", gemm)
     monkeypatch.setattr(K, "cast_bf16", cast_bf16)
     monkeypatch.setattr(K, "act_bwd", act_bwd)
+    monkeypatch.setattr(K, "lrelu_pad", lrelu_pad)
     monkeypatch.setattr(K, "colsum", colsum)
     monkeypatch.setattr(K, "ln_fwd", ln_fwd)
     monkeypatch.setattr(K, "ln_bwd", ln_bwd)
