@@ -228,7 +228,7 @@ int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const
                float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------- waveform front end
- * (speech-input branch, SURVEY section 8a row 2 -- EXPERIMENTAL: written without GPU time, not yet validated on device)
+ * (speech-input branch)
  * Layer 0 of ConvFeatureExtractionModel in mode "default" (speech_encoder_prenet.py:290-327,349-354): Conv1d(1 -> C, K
  * taps, `stride`, no bias) + Fp32GroupNorm(C groups: statistics per utterance and channel over time) + GELU
  * (fairseq/modules/gelu.py:24), fused. wave [B, n_samples] fp32; w [C, K]; y [B, T0, C] channels-last in `dtype`,

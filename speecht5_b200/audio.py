@@ -2,8 +2,8 @@
 speecht5/data/text_to_speech_dataset.py:95-138, whose arithmetic is librosa's): reflect-pad n_fft/2, frames of n_fft
 samples every hop, periodic-hann window, |rFFT|, Slaney mel projection, log10(max(eps, .)).
 
-EXPERIMENTAL -- written at the end of round 1 without GPU time; the operand views are checked on the CPU through the
-GEMM emulator against oracle/audio_oracle.py (tests/test_frontend_cpu.py).
+The operand views are checked on the CPU through the GEMM emulator against oracle/audio_oracle.py
+(tests/test_frontend_cpu.py), the device path in tests/test_frontend_gpu.py.
 
 Device formulation: the STFT of every utterance is ONE batched tcgen05 GEMM -- row t of utterance b is the n_fft
 contiguous samples starting at t*hop of the padded waveform (row pitch = hop: overlapping windows, no framing copy),

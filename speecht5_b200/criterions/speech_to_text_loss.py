@@ -1,9 +1,8 @@
 """Speech-to-text criterion: behaviour of speecht5/criterions/speech_to_text_loss.py (SpeechtoTextLoss :113-337,
 label_smoothed_nll_loss :93-110) for the opt-in speech-input branch. The arithmetic acts on vocabulary-sized tensors
 ([B, T_d, V] decoder logits, [T_e, B, V] CTC head) and is issued as torch library calls (log_softmax, gather,
-F.ctc_loss with cuDNN off like the reference :326); the hand-written per-utterance CTC recursion that replaces the
-library call is specified in tests/test_kernel_algorithms_cpu.py. EXPERIMENTAL (see speecht5_b200/frontend.py)."""
-import os
+on CPU tensors F.ctc_loss with cuDNN off like the reference :326; on the device csrc/ctc.cu through
+frontend.ctc_loss_sum / ctc_loss_sum_padded, whose recursion is specified in tests/test_kernel_algorithms_cpu.py)."""
 
 import torch
 import torch.nn.functional as F
@@ -92,7 +91,7 @@ class SpeechtoTextLoss(FairseqCriterion):
             loss = ctc_loss_sum_padded(raw, sample["target"], input_lengths, target_lengths, self.blank_idx,
                                        self.zero_infinity)
             return loss, lprobs, input_lengths
-        if os.environ.get("ST5_CTC_KERNEL") == "1" and raw.is_cuda:  # hand-written fused log-softmax + CTC (csrc/ctc.cu)
+        if raw.is_cuda:  # device tensors always take csrc/ctc.cu (fused log-softmax + CTC + logit gradient)
             from ..frontend import ctc_loss_sum
             loss = ctc_loss_sum(raw, targets_flat, input_lengths, target_lengths, self.blank_idx, self.zero_infinity)
             return loss, lprobs, input_lengths

@@ -2,9 +2,9 @@
 speecht5/models/modules/speech_encoder_prenet.py:277-374, mode "default"): seven bias-free Conv1d layers
 [(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2, GroupNorm(512 groups) after the first, GELU after each.
 
-EXPERIMENTAL -- written at the end of round 1 without GPU time. The index algebra is checked on the CPU against
-torch's convolutions through a GEMM emulator (tests/test_frontend_cpu.py); the device run is the gated GPU test
-(ST5_TEST_CONV0=1 / ST5_TEST_FRONTEND=1). Nothing on the validated TTS path imports this module.
+The index algebra is checked on the CPU against torch's convolutions through a GEMM emulator
+(tests/test_frontend_cpu.py), the device path against the oracle and the reference fixtures (tests/test_frontend_gpu.py,
+tests/test_ref_pin_gpu.py). The TTS path does not import this module.
 
 Device formulation (channels-last activations [B, T, C] throughout, no im2col, no transposes):
 * layer 0: csrc/conv_frontend.cu -- conv + GroupNorm + GELU fused, the convolution recomputed from the waveform in
@@ -313,7 +313,7 @@ class SpeechEncoderPrenet(torch.nn.Module):
     """speech_encoder_prenet.py:57-275 for the built configuration (encoder_speech_prenet "conv", extractor_mode
     "default", use_conv_pos and use_sinc_pos as in the Base arch): waveform -> [B, T, d], frame padding mask and the
     mean-square feature penalty. The HuBERT-style mask draw stays on the host (speecht5_b200.data.compute_mask_indices,
-    numpy, like the reference :236-262); its result is applied here. EXPERIMENTAL (see module docstring)."""
+    numpy, like the reference :236-262); its result is applied here."""
 
     def __init__(self, args):
         super().__init__()
@@ -438,7 +438,7 @@ class SpeechEncoderPrenet(torch.nn.Module):
 
 class CTCLossFn(torch.autograd.Function):
     """sum_b CTC nll of the encoder head, log-softmax fused (csrc/ctc.cu); the gradient with respect to the logits is
-    produced in the same launch and scaled by the incoming scalar in backward. EXPERIMENTAL."""
+    produced in the same launch and scaled by the incoming scalar in backward."""
 
     @staticmethod
     def forward(ctx, logits, targets_flat, input_lengths, target_lengths, blank, zero_infinity):

@@ -266,7 +266,7 @@ def bn_bwd(dy, dy_ld, x, x_ld, y_pre, gamma, save_mean, save_rstd, dx, dx_ld, dg
 
 
 def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
-    """EXPERIMENTAL (not yet validated on a GPU). wave [B, n] fp32, w [C, K] fp32 -> y [B, T0, C] (y.dtype)."""
+    """st5_conv0_gn_gelu_fwd: wave [B, n] fp32, w [C, K] fp32 -> y [B, T0, C] (y.dtype)."""
     _require_cuda(wave, w, y)
     assert wave.dtype == torch.float32 and w.dtype == torch.float32 and wave.is_contiguous() and w.is_contiguous()
     B, n = wave.shape
@@ -280,7 +280,7 @@ def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
 
 
 def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, stride, act):
-    """EXPERIMENTAL. dw / dgamma / dbeta (fp32) are accumulated."""
+    """st5_conv0_gn_gelu_bwd: dw / dgamma / dbeta (fp32) are accumulated."""
     _require_cuda(dy, wave, w)
     assert dy.is_contiguous()
     B, n = wave.shape

@@ -195,7 +195,7 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         if getattr(args, "build_text_decoder", False):
             text_decoder_prenet = TextDecoderPrenet(text_decoder_embed_tokens, args)
             text_decoder_postnet = TextDecoderPostnet(text_decoder_embed_tokens, len(text_dict), args)
-        # waveform front end: opt-in (--build-speech-encoder), EXPERIMENTAL -- see frontend.py
+        # waveform front end: opt-in (--build-speech-encoder), see frontend.py
         speech_encoder_prenet = None
         if getattr(args, "build_speech_encoder", False):
             from ..frontend import SpeechEncoderPrenet
@@ -381,7 +381,8 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         and no LM): encoder once, then per step log_softmax(logits / T) of the last position with the reference's
         masking order (:430-446: eos forbidden before min_len, NaN -> -inf, pad never, unk penalty, CTC blank and mask
         symbol never, only eos once max_len is reached) and argmax. The prefix starts with eos; max_len counts PADDED
-        source samples (:249,262-265). Returns a list of 1-D LongTensors ending in eos. EXPERIMENTAL (opt-in branch)."""
+        source samples (:249,262-265). Returns a list of 1-D LongTensors ending in eos.
+        use_cache: False (prefix recomputation), True (key/value cache), "graph" (one captured CUDA graph per step)."""
         import math
         B, src_len = source.size(0), source.size(1)
         max_len = min(int(max_len_a * src_len + max_len_b), self.args.max_text_positions - 1)

@@ -3,8 +3,8 @@
 (fairseq/modules/gumbel_vector_quantizer.py:13-202 in the SpeechT5 configuration: 100 variables x 2 groups, one linear
 projection, time-first input) and the code mixing of models/speecht5.py:858-872.
 
-EXPERIMENTAL -- written at the end of round 1 without GPU time and not wired into T5TransformerModel.forward yet (the
-speech_pretrain / text_pretrain tasks and their criteria are later rows). The two projections run on the tcgen05 GEMM
+Used by the speech pre-training branch of T5TransformerModel.forward (target_list / --use-codebook); the criteria
+are criterions/speech_pretrain_criterion.py and text_pretrain_criterion.py. The two projections run on the tcgen05 GEMM
 (ops.linear); the rest acts on [frames, classes]-sized tensors (cosine similarities against the label embeddings,
 Gumbel-softmax over 100 variables, a 200 x d codebook product) and is issued as torch calls. Checked on the CPU against
 oracle/pretrain_oracle.py through the kernel emulation (tests/test_frontend_cpu.py), forward and backward.
