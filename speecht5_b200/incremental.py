@@ -270,6 +270,7 @@ class SynthesisGraph:
         """The reference's loop (:1222-1249): returns (before frames [1, L, odim], stop probabilities [L], attention
         [layers, H, L/r, S])."""
         assert maxlen <= self.maxlen
+        minlen = min(minlen, max(maxlen, 1))  # (the reference's loop has no exit past maxlen frames otherwise)
         S = self.begin(encoder_out, spkembs, threshold)
         idx = 0
         while True:

@@ -217,6 +217,7 @@ class B200Trainer:
         self._probs_read_heads = RT.probs_grad_heads
         self._prefetched, self._staging, self._staging_read = None, {}, None
         self._gate_thresholds = None
+        self._frame_pm_cache = {}
         self._wgrad_side = False  # (set below once the world size is known)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -224,6 +225,7 @@ class B200Trainer:
         # weight-gradient GEMMs on a second stream (ops.wgrad_mm): +1.1 % at N = 1; the stage collectives wait for it
         self._wgrad_side = os.environ.get("ST5_WGRAD_SIDE", "1") != "0" and self.device.type == "cuda"
         RT.wgrad_stream = None
+        self._wgrad_stream = None
         if exchange is None:
             exchange = os.environ.get("ST5_EXCHANGE") or ("shard" if RT.dtype == torch.bfloat16 else "allreduce")
         assert exchange in ("shard", "allreduce")
@@ -325,19 +327,25 @@ class B200Trainer:
 
     # ------------------------------------------------------------------ the update, as a sequence of device work
     def _update(self, samples):
-        if self._wgrad_side and RT.wgrad_stream is None:
-            RT.wgrad_stream = torch.cuda.Stream(device=self.device)
+        if self._wgrad_side and self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(device=self.device)
         self.fp.grads.zero_()
         losses, stats = [], []
         self._done = set()
-        for k, sample in enumerate(samples):  # --update-freq micro-batches
-            self._last_micro = k == len(samples) - 1
-            loss, sample_size, logging_output = self.task.train_step(sample, self.model, self.criterion, None,
-                                                                     self.num_updates)
-            losses.append(loss if torch.is_tensor(loss) else torch.tensor(loss, device=self.device))
-            stats.append(logging_output.get(sample["task_name"], logging_output).get("_stats"))
-        self._last_micro = False
-        RT.side_join()
+        # the side stream is visible to the ops only while this update's backward passes run: a backward issued outside
+        # the trainer (tests, user code) must not leave work on a stream nobody joins
+        RT.wgrad_stream = self._wgrad_stream
+        try:
+            for k, sample in enumerate(samples):  # --update-freq micro-batches
+                self._last_micro = k == len(samples) - 1
+                loss, sample_size, logging_output = self.task.train_step(sample, self.model, self.criterion, None,
+                                                                         self.num_updates)
+                losses.append(loss if torch.is_tensor(loss) else torch.tensor(loss, device=self.device))
+                stats.append(logging_output.get(sample["task_name"], logging_output).get("_stats"))
+            self._last_micro = False
+            RT.side_join()
+        finally:
+            RT.wgrad_stream = None
         if self.world > 1:
             self._finish_exchange()
         # legacy_ddp.py:110 divides by world before the sum; trainer.py:796 multiply_grads(world / sample_size) with
@@ -478,7 +486,21 @@ class B200Trainer:
         B, n = ni["source"].shape
         T = int(prenet.feature_extractor.get_out_seq_lens_tensor(torch.tensor([n]))[0])
         pm = ni.get("padding_mask")
-        frame_pm = downsample_padding_mask(pm.cpu(), T) if pm is not None else None
+        frame_pm = None
+        if pm is not None:
+            # the frame-level padding mask of a batch is a function of its sample-level mask only: remember it per mask
+            # tensor (object + version), so that a batch that already lives on the device does not cost a device->host
+            # read -- and a drained pipeline -- every time it is stepped on
+            key = (id(pm), pm._version, tuple(pm.shape))
+            hit = self._frame_pm_cache.get(key)
+            if hit is not None and hit[0]() is pm:
+                frame_pm = hit[1]
+            else:
+                import weakref
+                frame_pm = downsample_padding_mask(pm.cpu(), T)
+                if len(self._frame_pm_cache) >= 64:
+                    self._frame_pm_cache.pop(next(iter(self._frame_pm_cache)))
+                self._frame_pm_cache[key] = (weakref.ref(pm), frame_pm)
         mi, mc = draw_hubert_masks(prenet, B, T, frame_pm)
         extra = {}
         if mi is not None:
