@@ -175,3 +175,29 @@ def test_pad_to_buckets_keeps_the_valid_region():
     assert p["dec_target"].shape == (3, 192, 80) and p["labels"].shape == (3, 192)
     assert p["net_input"]["prev_output_tokens"].shape == (3, 96, 80)
     assert torch.equal(p["dec_target"][:, :150], s["dec_target"]) and torch.equal(p["dec_target_lengths"], s["dec_target_lengths"])
+
+
+def test_packed_device_copies_keep_structure_and_share_one_buffer():
+    """trainer._to_device_packed (the graph's static inputs and the prefetch staging set): same nested structure and
+    values as the samples, every tensor a 256-byte aligned view of ONE byte buffer, so two sets built from batches of the
+    same shapes can be moved over each other with a single copy."""
+    from speecht5_b200.trainer import _flatten, _to_device_packed
+    torch.manual_seed(0)
+    mk = lambda seed: {"id": torch.arange(3) + seed, "task_name": "t2s",  # noqa: E731
+                       "net_input": {"src_tokens": torch.randint(0, 50, (3, 7)) + seed, "spkembs": torch.randn(3, 5),
+                                     "pad": torch.tensor([[True, False, True]])},
+                       "labels": torch.randn(3, 9).to(torch.bfloat16)}
+    a, b = [mk(0), mk(1)], [mk(7), mk(8)]
+    va, fa = _to_device_packed(a, torch.device("cpu"))
+    vb, fb = _to_device_packed(b, torch.device("cpu"))
+    assert fa.numel() == fb.numel() and fa.dtype == torch.uint8
+    for s, v in zip(a, va):
+        assert v["task_name"] == "t2s"
+        for (k, x), (k2, y) in zip(_flatten(s).items(), _flatten(v).items()):
+            assert k == k2 and x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y)
+            off = y.data_ptr() - fa.data_ptr()
+            assert 0 <= off < fa.numel() and off % 256 == 0
+    fa.copy_(fb)  # ONE copy moves the second set of batches over the first
+    for s, v in zip(b, va):
+        for x, y in zip(_flatten(s).values(), _flatten(v).values()):
+            assert torch.equal(x, y)
