@@ -590,8 +590,13 @@ def run_ragged(args):
     hits, misses = trainer.graph_hits, trainer.graph_misses
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in order[:args.steps]:
+    # steady state through the input pipeline: bucket padding (host) and the host->device copy of the NEXT batch run
+    # under the current update (B200Trainer.prefetch), like the end-to-end leg of the fixed-shape bench
+    timed = order[:args.steps]
+    trainer.prefetch([stream[timed[0]]])
+    for k, i in enumerate(timed):
         out = trainer.train_step([stream[i]])
+        trainer.prefetch([stream[timed[(k + 1) % len(timed)]]])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps

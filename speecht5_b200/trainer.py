@@ -700,6 +700,10 @@ def pad_to_buckets(sample, buckets):
             out["dec_target"] = pad_dim(sample["dec_target"], 1, L, 0.0)
             out["labels"] = pad_dim(sample["labels"], 1, L, 0.0)
             ni["prev_output_tokens"] = pad_dim(ni["prev_output_tokens"], 1, L // r, 0.0)
+            # the collater's padded features (data/text_to_speech_dataset.py:250-262; only their batch size is read):
+            # left at their raw length they made every raw shape its own graph signature
+            if torch.is_tensor(sample.get("target")) and sample["target"].dim() == 3:
+                out["target"] = pad_dim(sample["target"], 1, up(sample["target"].size(1), buckets["frames"]), 0.0)
     elif task == "s2t":
         if "wave" in buckets:
             n = up(ni["source"].size(1), buckets["wave"])

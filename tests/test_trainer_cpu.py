@@ -175,6 +175,14 @@ def test_pad_to_buckets_keeps_the_valid_region():
     assert p["dec_target"].shape == (3, 192, 80) and p["labels"].shape == (3, 192)
     assert p["net_input"]["prev_output_tokens"].shape == (3, 96, 80)
     assert torch.equal(p["dec_target"][:, :150], s["dec_target"]) and torch.equal(p["dec_target_lengths"], s["dec_target_lengths"])
+    # every tensor whose shape follows the raw lengths is padded: batches of 12 raw shapes fall into 2 x 2 signatures
+    # (the collater's `target` features were once left at their raw length -- every raw shape then captured its own graph)
+    from speecht5_b200.trainer import _flatten
+    sigs = set()
+    for i, (t, m) in enumerate([(t, m) for t in (40, 50, 60, 70) for m in (130, 150, 200)]):
+        q = pad_to_buckets(synthetic_tts_batch(3, t, m, seed=i), {"text": 32, "frames": 64})
+        sigs.add(tuple((k, tuple(v.shape)) for k, v in _flatten(q).items()))
+    assert len(sigs) == 4, len(sigs)
 
 
 def test_packed_device_copies_keep_structure_and_share_one_buffer():
