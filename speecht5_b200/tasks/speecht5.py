@@ -65,7 +65,30 @@ class SpeechT5Task(LegacyFairseqTask):
 
     @classmethod
     def setup_task(cls, args, **kwargs):
-        return cls(args)
+        """tasks/speecht5.py:298-318: the text vocabulary is `<data>/dict.txt`, pre-training adds one HuBERT label
+        vocabulary per `--hubert-labels` entry from `<hubert-label-dir>/dict.<label>.txt`; `<mask>` and `<ctc_blank>` are
+        appended to the text vocabulary like the reference's constructor does (:282-286). Without a data directory (unit
+        tests, synthetic benches) the length-only stand-in of `__init__` is used."""
+        import os
+        from ..dictionary import load_dictionary
+        data = getattr(args, "data", None)
+        path = os.path.join(data, "dict.txt") if data else None
+        if path is None or not os.path.exists(path):
+            return cls(args)
+        dicts = {"text": load_dictionary(path)}
+        if getattr(args, "t5_task", "t2s") == "pretrain":
+            if not hasattr(args, "shuffle_instance"):
+                args.shuffle_instance = False
+            label_dir = getattr(args, "hubert_label_dir", None) or data
+            dicts["hubert"] = [load_dictionary(os.path.join(label_dir, f"dict.{label}.txt"))
+                               for label in (getattr(args, "hubert_labels", None) or ["km"])]
+        task = cls(args, dicts=dicts)
+        task.mask_idx = dicts["text"].add_symbol("<mask>")
+        task.blank_symbol_idx = dicts["text"].add_symbol("<ctc_blank>")
+        task.blank_symbol = "<ctc_blank>"
+        if getattr(args, "iid_noise_target", False):  # (:289-293)
+            task.uni_mask_idxs = torch.tensor([dicts["text"].add_symbol("<mask>" + str(i)) for i in range(600)])
+        return task
 
     @property
     def target_dictionary(self):  # tasks/speecht5.py:573-579

@@ -431,3 +431,70 @@ def test_text_pretrain_criterion_equals_the_reference_criterion(sentence_avg, we
     got.backward()
     assert torch.allclose(ms_our.logits.grad, ms_ref.logits.grad, rtol=1e-5, atol=1e-7)
     assert (ms_ref.pp.grad is None and ms_our.pp.grad is None) or torch.allclose(ms_our.pp.grad, ms_ref.pp.grad)
+
+
+def _reference_dictionary_class():
+    """fairseq/data/dictionary.py of the reference, executed unmodified with its five package imports stubbed (utils,
+    binarizer.safe_readline, data.data_utils, file_io.PathManager, tokenizer.tokenize_line: none of them is reached by
+    load / add_symbol / index / string on an in-memory id list)."""
+    import types
+    path = os.path.join(rl.FAIRSEQ, "data", "dictionary.py")
+    names = ["fairseq", "fairseq.utils", "fairseq.binarizer", "fairseq.data", "fairseq.data.data_utils", "fairseq.file_io",
+             "fairseq.tokenizer"]
+    saved = {n: sys.modules.get(n) for n in names}
+    try:
+        mods = {n: types.ModuleType(n) for n in names}
+        mods["fairseq"].utils = mods["fairseq.utils"]
+        mods["fairseq.utils"].item = lambda t: t.item() if hasattr(t, "item") else t
+        mods["fairseq.binarizer"].safe_readline = lambda f: f.readline()
+        mods["fairseq.data"].data_utils = mods["fairseq.data.data_utils"]
+        mods["fairseq.data.data_utils"].post_process = lambda s, sym: s
+        mods["fairseq.file_io"].PathManager = type("PathManager", (), {"get_local_path": staticmethod(lambda p: p)})
+        mods["fairseq.tokenizer"].tokenize_line = lambda line: line.split()
+        sys.modules.update(mods)
+        ns = {"__name__": "fairseq_dictionary_under_test"}
+        exec(compile(open(path).read(), path, "exec"), ns)
+        return ns["Dictionary"]
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+
+
+def test_vocabulary_files_load_like_the_reference_dictionary(tmp_path):
+    """speecht5_b200/dictionary.py (what SpeechT5Task.setup_task loads `dict.txt` / `dict.<label>.txt` with when fairseq
+    is not importable) against the reference's own fairseq Dictionary: same indices, length, lookups, appended task
+    symbols and id -> text conversion; then the task built from a data directory (tasks/speecht5.py:272-318)."""
+    from speecht5_b200.dictionary import Vocabulary
+    from speecht5_b200.tasks import SpeechT5Task
+    from speecht5_b200.models import make_args
+    Ref = _reference_dictionary_class()
+    words = ["▁", "e", "t", "a", "o", "n", "'", "<weird token>", "zz"]
+    (tmp_path / "dict.txt").write_text("".join(f"{w} {100 - i}\n" for i, w in enumerate(words)), encoding="utf-8")
+    (tmp_path / "dict.km.txt").write_text("".join(f"{i} 1\n" for i in range(25)), encoding="utf-8")
+    ref, got = Ref.load(str(tmp_path / "dict.txt")), Vocabulary.load(str(tmp_path / "dict.txt"))
+    assert len(got) == len(ref) == 4 + len(words) and got.symbols == ref.symbols and got.indices == ref.indices
+    assert (got.bos(), got.pad(), got.eos(), got.unk()) == (ref.bos(), ref.pad(), ref.eos(), ref.unk()) == (0, 1, 2, 3)
+    for w in words + ["missing", "<pad>"]:
+        assert got.index(w) == ref.index(w)
+    assert got.add_symbol("<mask>") == ref.add_symbol("<mask>") and got.add_symbol("e") == ref.add_symbol("e")
+    assert got.count == ref.count and got[999] == ref[999]
+    ids = torch.tensor([[0, 5, 6, 3, 2, 1], [7, 8, 4, 2, 1, 1]])
+    assert got.string(ids, extra_symbols_to_ignore={1}) == ref.string(ids, extra_symbols_to_ignore={1})
+    assert got.string(ids[0], include_eos=True, unk_string="?") == ref.string(ids[0], include_eos=True, unk_string="?")
+    (tmp_path / "dup.txt").write_text("a 1\na 2\n")
+    with pytest.raises(RuntimeError):
+        Vocabulary.load(str(tmp_path / "dup.txt"))
+    # the task: vocabulary from <data>/dict.txt, <mask> and <ctc_blank> appended, HuBERT label sets for pre-training
+    args = make_args("t5_transformer_base_asr", data=str(tmp_path), t5_task="pretrain", hubert_labels=["km"],
+                     hubert_label_dir=str(tmp_path), build_speech_encoder=True, use_conv_pos=True, use_sinc_pos=True,
+                     encoder_layers=1, decoder_layers=1)
+    task = SpeechT5Task.setup_task(args)
+    n = 4 + len(words)
+    assert (task.mask_idx, task.blank_symbol_idx) == (n, n + 1) and len(task.target_dictionary) == n + 2
+    assert len(task.dicts["hubert"]) == 1 and len(task.dicts["hubert"][0]) == 4 + 25
+    model = task.build_model(args)
+    assert model.text_encoder_prenet.encoder_prenet[0].weight.shape[0] == n + 2
+    assert model.hubert_layer is not None
