@@ -332,6 +332,7 @@ class GreedyGraph:
         self.done = torch.zeros(B, dtype=torch.bool, device=dev)
         self.lengths = torch.zeros(B, dtype=torch.long, device=dev)
         self.stop = torch.zeros(rows, dtype=torch.int32, device=dev)
+        self.pos_scores = torch.zeros((B, rows), dtype=torch.float32, device=dev)  # log-probability of the token emitted at t
         self.pos = torch.arange(rows, device=dev)
         pre = model.text_decoder_prenet
         self.pe = pre._table(rows, dev)
@@ -400,6 +401,7 @@ class GreedyGraph:
             + torch.where(self.t >= self.max_len, self.only_eos, zero)
         nxt = lp.argmax(dim=-1)
         self.tokens.index_copy_(1, self.t + 1, nxt[:, None])
+        self.pos_scores.index_copy_(1, self.t, lp.gather(1, nxt[:, None]))
         newly = (~self.done) & nxt.eq(self.eos)
         self.lengths.copy_(torch.where(newly, (self.t + 1).expand(self.B), self.lengths))
         self.done |= newly

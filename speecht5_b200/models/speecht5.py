@@ -376,7 +376,8 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
 
     @torch.no_grad()
     def generate_text_greedy(self, source, padding_mask=None, max_len_a=0.0, max_len_b=200, min_len=1, unk_penalty=0.0,
-                             temperature=1.0, pad=1, eos=2, unk=3, blank=0, mask_idx=None, use_cache=False):
+                             temperature=1.0, pad=1, eos=2, unk=3, blank=0, mask_idx=None, use_cache=False,
+                             return_scores=False):
         """Beam-1 decoding as `generate.py --beam 1` runs it (speecht5/sequence_generator.py:207-655 with ctc_weight 0
         and no LM): encoder once, then per step log_softmax(logits / T) of the last position with the reference's
         masking order (:430-446: eos forbidden before min_len, NaN -> -inf, pad never, unk penalty, CTC blank and mask
@@ -392,12 +393,16 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
             from ..incremental import greedy_graph
             S = enc["encoder_out"][0].size(0)
             gg = greedy_graph(self, B, S, max_len, source.device, capture=use_cache == "graph")
-            return gg.decode(enc, max_len, min_len=min_len, unk_penalty=unk_penalty, temperature=temperature, pad=pad,
-                             eos=eos, unk=unk, blank=blank, mask_idx=mask_idx)
+            hyp = gg.decode(enc, max_len, min_len=min_len, unk_penalty=unk_penalty, temperature=temperature, pad=pad,
+                            eos=eos, unk=unk, blank=blank, mask_idx=mask_idx)
+            if return_scores:  # (log-probability of every emitted token, eos included)
+                return hyp, [gg.pos_scores[b, : len(h)].clone() for b, h in enumerate(hyp)]
+            return hyp
         tokens = torch.full((B, max_len + 2), pad, dtype=torch.long, device=source.device)
         tokens[:, 0] = eos
         done = torch.zeros(B, dtype=torch.bool, device=source.device)
         lengths = torch.zeros(B, dtype=torch.long, device=source.device)
+        pos_scores = torch.zeros((B, max_len + 1), dtype=torch.float32, device=source.device)
         cache = None
         if use_cache:  # key/value cache (speecht5_b200/incremental.py): one new row per step
             from ..incremental import DecoderCache, decoder_step
@@ -423,12 +428,16 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
                 lprobs[:, eos + 1:] = -math.inf
             nxt = lprobs.argmax(dim=-1)
             tokens[:, step + 1] = nxt
+            pos_scores[:, step] = lprobs.gather(1, nxt[:, None])[:, 0]
             newly = (~done) & nxt.eq(eos)
             lengths = torch.where(newly, torch.full_like(lengths, step + 1), lengths)
             done |= newly
             if bool(done.all()):
                 break
-        return [tokens[b, 1: int(lengths[b]) + 1].clone() for b in range(B)]
+        hyp = [tokens[b, 1: int(lengths[b]) + 1].clone() for b in range(B)]
+        if return_scores:
+            return hyp, [pos_scores[b, : len(h)].clone() for b, h in enumerate(hyp)]
+        return hyp
 
     def forward_text_encoder(self, src_tokens):
         encoder_input, encoder_padding_mask = self.text_encoder_prenet(src_tokens)

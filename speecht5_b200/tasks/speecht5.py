@@ -98,6 +98,29 @@ class SpeechT5Task(LegacyFairseqTask):
     def source_dictionary(self):
         return None
 
+    def build_generator(self, models, args, seq_gen_cls=None, extra_gen_cls_kwargs=None):
+        """tasks/speecht5.py:599-613 for beam size 1 (the reference hands its SequenceGenerator the task's ctc_weight)."""
+        from ..generator import GreedyGenerator
+        kw = dict(beam_size=getattr(args, "beam", 1), max_len_a=getattr(args, "max_len_a", 0),
+                  max_len_b=getattr(args, "max_len_b", 200), min_len=getattr(args, "min_len", 1),
+                  normalize_scores=not getattr(args, "unnormalized", False), len_penalty=getattr(args, "lenpen", 1.0),
+                  unk_penalty=getattr(args, "unkpen", 0.0), temperature=getattr(args, "temperature", 1.0),
+                  ctc_weight=getattr(self.args, "ctc_weight", 0.0), blank=getattr(self, "blank_symbol_idx", None),
+                  mask_idx=getattr(self, "mask_idx", None))
+        kw.update(extra_gen_cls_kwargs or {})
+        return GreedyGenerator(models, self.target_dictionary, **kw)
+
+    def inference_step(self, generator, models, sample, prefix_tokens=None, constraints=None):
+        with torch.no_grad():  # fairseq/tasks/fairseq_task.py inference_step
+            return generator.generate(models, sample, prefix_tokens=prefix_tokens, constraints=constraints)
+
+    def generate_speech(self, models, net_input, **kwargs):
+        """tasks/speecht5.py:640-646 (what scripts/generate_speech.py calls)."""
+        with torch.no_grad():
+            encoder_input = {k: v for k, v in net_input.items() if k not in ("prev_output_tokens", "task_name")}
+            encoder_input.update(kwargs)
+            return models[0].generate_speech(**encoder_input)
+
     def build_model(self, args):
         args.speech_odim = 80  # tasks/speecht5.py:581-597
         return T5TransformerModel.build_model(args, self)

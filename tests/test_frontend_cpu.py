@@ -326,6 +326,45 @@ def test_kv_cache_decoding_equals_prefix_recomputation_on_emulated_kernels(monke
     ids_m = model.generate_text_greedy(src, pm, max_len_b=10, min_len=4, unk_penalty=0.5, use_cache=True)
     ids_mg = model.generate_text_greedy(src, pm, max_len_b=10, min_len=4, unk_penalty=0.5, use_cache="graph_body_eager")
     assert [t.tolist() for t in ids_mg] == [t.tolist() for t in ids_m] and all(len(t) >= 4 for t in ids_mg)
+    # the generator object fairseq's generate.py drives (task.build_generator / inference_step): hypotheses in the
+    # SequenceGenerator's return shape, token log-probabilities equal on the three decoding paths and equal to the
+    # oracle's teacher-forced log-probabilities of the same tokens
+    from types import SimpleNamespace
+    from speecht5_b200.dictionary import Vocabulary
+    from speecht5_b200.tasks.speecht5 import SpeechT5Task
+    vocab = Vocabulary()
+    for i in range(model.text_decoder_postnet.output_projection.weight.shape[0] - len(vocab) - 2):
+        vocab.add_symbol("s%d" % i)
+    vocab.add_symbol("<mask>"), vocab.add_symbol("<ctc_blank>")
+    task = SpeechT5Task.__new__(SpeechT5Task)
+    task.args, task.dicts = SimpleNamespace(ctc_weight=0.0), {"text": vocab}
+    task.blank_symbol_idx, task.mask_idx = 0, vocab.index("<mask>")
+    gen_args = SimpleNamespace(beam=1, max_len_a=0, max_len_b=10, min_len=1, unnormalized=False, lenpen=1.0, unkpen=0.0)
+    per_path = []
+    for mode in (False, True, "graph_body_eager"):
+        gen = task.build_generator([model], gen_args, extra_gen_cls_kwargs=dict(use_cache=mode))
+        hypos = task.inference_step(gen, [model], s)
+        assert [h[0]["tokens"].tolist() for h in hypos] == [t.tolist() for t in ids_ref]
+        for h in hypos:
+            assert len(h) == 1 and h[0]["positional_scores"].shape == h[0]["tokens"].shape
+            assert abs(float(h[0]["score"]) - float(h[0]["positional_scores"].mean())) < 1e-6
+        per_path.append(torch.cat([h[0]["positional_scores"] for h in hypos]))
+    assert rel(per_path[1], per_path[0]) < 1e-4 and rel(per_path[2], per_path[0]) < 1e-4
+    with torch.no_grad():  # teacher-forced oracle log-probabilities of the hypothesis tokens
+        x, enc_pad, _ = oracle.speech_encoder_prenet(src, pm, None, None)
+        enc = oracle.encoder(x, enc_pad)
+        want = []
+        for b, hyp in enumerate(ids_ref):
+            prev = torch.cat([hyp.new_tensor([2]), hyp[:-1]])[None]
+            dec_in, tgt_mask = oracle.text_decoder_prenet(prev)
+            one = dict(enc, encoder_out=[enc["encoder_out"][0][:, b: b + 1]],
+                       encoder_padding_mask=[enc["encoder_padding_mask"][0][b: b + 1]])
+            z, _ = oracle.decoder(dec_in, tgt_mask, one, alignment_layer=None)
+            lp = F.log_softmax(oracle.text_decoder_postnet(z)[0].float(), dim=-1)
+            want.append(lp.gather(1, hyp[:, None])[:, 0])
+    assert rel(per_path[0], torch.cat(want)) < 1e-3
+    with pytest.raises(NotImplementedError):
+        task.build_generator([model], SimpleNamespace(beam=5))
     # (b) speech synthesis
     RT.invalidate_shadows()
     torch.manual_seed(3)

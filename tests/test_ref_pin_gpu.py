@@ -183,6 +183,29 @@ def test_greedy_token_ids_equal_the_reference_sequence_generator(cuda, use_cache
         assert [t.tolist() for t in again] == [t.tolist() for t in hyp]
 
 
+def test_greedy_generator_scores_agree_between_the_eager_cached_and_graph_paths(cuda):
+    """speecht5_b200/generator.py (the object task.build_generator returns for beam 1): SequenceGenerator-shaped
+    hypotheses whose tokens are the fixture's and whose token log-probabilities agree between the three decoding paths."""
+    from types import SimpleNamespace
+    from speecht5_b200.generator import GreedyGenerator
+    blob = load("ref_asr_tiny")
+    model = _asr_model(cuda, torch.float32, blob).eval()
+    vocab = SimpleNamespace(pad=lambda: 1, eos=lambda: 2, unk=lambda: 3)
+    sample = {"net_input": {"source": torch.from_numpy(blob["in/source"]).to(cuda),
+                            "padding_mask": torch.from_numpy(blob["in/padding_mask"]).to(cuda)}}
+    scores = []
+    for mode in (False, True, "graph"):
+        gen = GreedyGenerator([model], vocab, max_len_b=12, blank=VOCAB - 1, mask_idx=VOCAB - 2, use_cache=mode)
+        hypos = gen.generate([model], sample)
+        for b, h in enumerate(hypos):
+            n = int(blob["out/greedy_lengths"][b])
+            assert h[0]["tokens"].tolist() == blob["out/greedy_tokens"][b, :n].tolist()
+            assert h[0]["positional_scores"].shape == (n,) and bool((h[0]["positional_scores"] <= 0).all())
+            assert abs(float(h[0]["score"]) - float(h[0]["positional_scores"].mean())) < 1e-5
+        scores.append(torch.cat([h[0]["positional_scores"] for h in hypos]))
+    assert rel(scores[1], scores[0]) < 1e-4 and rel(scores[2], scores[0]) < 1e-4
+
+
 def test_hifigan_against_the_reference_generator(cuda):
     from oracle.audio_oracle import fold_weight_norm
     from speecht5_b200 import vocoder
