@@ -36,10 +36,12 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--decoder-layers", type=int, default=WORKLOAD["decoder_layers"])
-    ap.add_argument("--workload", default="tts", choices=["tts", "tts_ragged", "asr", "hifigan"],
+    ap.add_argument("--workload", default="tts", choices=["tts", "tts_ragged", "asr", "hifigan", "pretrain"],
                     help="tts = the BASELINE.json metric (config 2, default); tts_ragged = the same model on a stream of "
                          "distinct batch shapes through the shape-bucket graph cache; asr = config 3 (speech -> text "
-                         "fine-tune step); hifigan = config 5 (vocoder inference, waveform samples/s)")
+                         "fine-tune step); hifigan = config 5 (vocoder inference, waveform samples/s); pretrain = config "
+                         "4 (t5_transformer_large joint pre-training update: one speech + one text micro-batch)")
+    ap.add_argument("--pretrain-arch", default="t5_transformer_large", choices=["t5_transformer_large", "t5_transformer_base"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the parity-mode (fp32 activations, 3-pass split-bf16 GEMMs) leg and the mel-L2 measurement")
@@ -170,14 +172,15 @@ def _timed_steps(trainer, batches, steps, warmup, world, dev, read_back):
             dist.barrier()
         torch.cuda.synchronize()
     out = None
+    micro = lambda b: b if isinstance(b, list) else [b]  # noqa: E731  (an element may already be a list of micro-batches)
     # end-to-end runs (host batches): the input pipeline of B200Trainer -- the NEXT step's pinned batch is copied to the
     # device on a copy stream while the current update executes (every timed step still issues one full host->device
     # copy inside the timed region: the one for its successor)
     pipelined = read_back and hasattr(trainer, "prefetch")
     for i in range(warmup):
-        out = trainer.train_step([batches[i % len(batches)]])
+        out = trainer.train_step(micro(batches[i % len(batches)]))
         if pipelined:
-            trainer.prefetch([batches[(i + 1) % len(batches)]])
+            trainer.prefetch(micro(batches[(i + 1) % len(batches)]))
         if read_back and out[1] is not None:
             out[1].cpu()
     barrier()
@@ -187,9 +190,9 @@ def _timed_steps(trainer, batches, steps, warmup, world, dev, read_back):
     e0.record()
     last = None
     for i in range(steps):
-        out = trainer.train_step([batches[(warmup + i) % len(batches)] if pipelined else batches[i % len(batches)]])
+        out = trainer.train_step(micro(batches[(warmup + i) % len(batches)] if pipelined else batches[i % len(batches)]))
         if pipelined:
-            trainer.prefetch([batches[(warmup + i + 1) % len(batches)]])
+            trainer.prefetch(micro(batches[(warmup + i + 1) % len(batches)]))
         if read_back:
             last = (out[1] if out[1] is not None else out[0]).cpu()  # device->host read of the step's loss statistics
     e1.record()
@@ -435,6 +438,110 @@ def run_asr(args):
     _emit(line, world)
 
 
+PRETRAIN = dict(speech_batch=5, n_samples=250000, text_batch=23, text_len=512, vocab=10000, km_classes=500)
+# forward GFLOP per speech utterance (conv FE 76.7 + encoder 544 + 6-layer decoder 121) and per
+# 512-token text sample (encoder 343 + decoder 116); an update is 3x the forward of one micro-batch of each
+PRETRAIN_GFLOP_PER_UPDATE = 3.0 * (5 * (76.7 + 544.0 + 121.0) + 23 * (343.0 + 116.0))
+
+
+def run_pretrain(args):
+    """BASELINE config 4: t5_transformer_large (24 + 6 layers, d = 1024, layer_norm waveform extractor, pre-LN) joint
+    pre-training update -- one speech micro-batch (5 x 250 000 samples -> 781 frames, HuBERT k-means labels at 50 Hz,
+    mask p = 0.8, mel reconstruction through the speech decoder) and one text micro-batch (23 x 512 tokens, V = 10 000,
+    BART denoising), `--update-freq 2`, shared Gumbel quantizer (codebook-prob 0.1, loss weights [10, 0.1]), clip 5, Adam
+    (0.9, 0.98) eps 1e-6 wd 0.01 -- the README's pre-training recipe. The pre-training criteria gather the masked
+    frames (a different count every draw) and read their statistics back inside forward, so these updates run eagerly:
+    the step includes the host's launch overhead. Same JSON contract; `value` counts speech utterances + text samples."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local, dev = _init_dist()
+    from speecht5_b200 import kernels as K
+    from speecht5_b200 import _lib
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.data import synthetic_speech_pretrain_batch, synthetic_text_pretrain_batch
+    from speecht5_b200.models import make_args
+    from speecht5_b200.tasks import SpeechT5Task
+    from speecht5_b200.trainer import B200Trainer, _to_device, h2d_bytes
+    _lib.check(_lib.load().st5_device_ok(), "st5_device_ok")
+    _fresh_runtime(torch.bfloat16, 1 + rank)
+    torch.manual_seed(1337)
+    import numpy as np
+    np.random.seed(17 + rank)
+    P = PRETRAIN
+    V = P["vocab"]
+    margs = make_args(args.pretrain_arch, build_speech_encoder=True, build_text_decoder=True, bert_init=True,
+                      share_input_output_embed=True, use_codebook=True, codebook_prob=0.1, vocab_size=V,
+                      hubert_num_classes=[P["km_classes"] + 4], max_text_positions=600)
+    task = SpeechT5Task(margs)
+    model = task.build_model(margs).to(dev).train()
+    n_params = sum(p.numel() for p in model.parameters())
+    crit = SpeechT5Criterion(task, loss_weights=[10.0, 0.1], dec_weight=0.5, bart_weight=1.0, hubert_weight=1.0)
+    trainer = B200Trainer(model, crit, task, lr=2e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, clip_norm=5.0,
+                          use_cuda_graph=False, exchange=args.exchange)
+    host = [[synthetic_speech_pretrain_batch(P["speech_batch"], P["n_samples"], n_classes=P["km_classes"],
+                                             seed=100 * rank + i, pin=True),
+             synthetic_text_pretrain_batch(P["text_batch"], P["text_len"], V, mask_idx=V - 2, seed=200 * rank + i, pin=True)]
+            for i in range(2)]
+    resident = [[_to_device(s, dev) for s in pair] for pair in host]
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, win_dev, _, out = _timed_steps(trainer, resident, args.steps, args.warmup, world, dev, read_back=False)
+    ms_e2e, _, last, out = _timed_steps(trainer, host, args.steps, args.warmup, world, dev, read_back=True)
+    losses = [float(v) for v in out[0].tolist()]
+    K.LAUNCHES = 0
+    K.GEMM_RECORD = []
+    trainer.train_step(resident[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches_step = K.LAUNCHES
+    records, K.GEMM_RECORD = K.GEMM_RECORD, None
+    gemm_flops = sum(2.0 * g.M * g.N * g.K * g.nb1 * g.nb2 for g in records)
+    K.gemm_replay(records)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        K.gemm_replay(records)
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / 3
+    peak_tf = _peaks().get("bf16_tflops_sustained", 1400.0)
+    clocks = sampler.window(*win_dev) if sampler else None
+    if sampler:
+        sampler.stop()
+    if rank != 0:
+        _finish(world)
+        return
+    per_update = (P["speech_batch"] + P["text_batch"]) * world
+    value, e2e = per_update / (ms_dev * 1e-3), per_update / (ms_e2e * 1e-3)
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    line = {
+        "metric": "samples/sec (joint pre-training update: speech utterances + text samples)", "value": value,
+        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.pretrain_arch} joint pre-training update (BASELINE config 4): speech micro-batch "
+                               f"{P['speech_batch']} x {P['n_samples']} samples (781 frames, k-means labels @ 50 Hz, mask "
+                               f"0.8 / 10, mel reconstruction 977 -> 488 decoder steps) + text micro-batch "
+                               f"{P['text_batch']} x {P['text_len']} tokens (V = {V}), update-freq 2, Gumbel quantizer "
+                               "(codebook-prob 0.1, loss weights [10, 0.1]), clip 5, Adam wd 0.01; eager (the masked-frame "
+                               "gather has a data-dependent size)",
+                   "global_batch": per_update, "parallelism": f"dp{world}", "exchange": trainer.exchange,
+                   "cuda_graph": False, "parameters": n_params, "losses_speech_text": losses,
+                   "extractor_mode": margs.extractor_mode,
+                   "l2": "2 distinct input pairs are cycled; the update's activations exceed the 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": sum(h2d_bytes(s) for s in host[0]), "d2h_bytes_per_step": int(last.numel() * 4)},
+        "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step, "clocks": clocks,
+        "step_tflops": PRETRAIN_GFLOP_PER_UPDATE * world / 1e3 / (ms_dev * 1e-3),
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all GEMM launches of one update)",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": None, "launches": len(records), "gemm_ms_per_step": gemm_ms,
+                     "gemm_share_of_step": gemm_ms / ms_dev},
+        "cpu_baseline": None,
+    }
+    _emit(line, world)
+
+
 def asr_cpu_baseline(B=2, steps=3):
     """The reference math of the same step on the host cores: oracle port (pinned to the reference by
     tests/test_ref_pin_cpu.py), fp32, no masks / LayerDrop (they only remove work), a bounded sample."""
@@ -627,6 +734,8 @@ def main():
         return run_hifigan(args)
     if args.workload == "tts_ragged":
         return run_ragged(args)
+    if args.workload == "pretrain":
+        return run_pretrain(args)
     import torch
     import torch.distributed as dist
     world, rank, local, dev = _init_dist()

@@ -125,6 +125,9 @@ int st5_lrelu_pad(const void* x, void* out, int64_t B, int64_t T, int64_t C, int
  * (F.dropout semantics: keep with probability 1-p, scale by 1/(1-p)); mask = the counter-based generator above. */
 int st5_dropout(const void* x, void* y, int dtype, int64_t n, float drop_p, uint64_t seed, uint64_t offset,
                 void* stream);
+/* y = act(x), stand-alone: the GELU behind the per-frame LayerNorm of layers 1..6 of the "layer_norm" waveform
+ * extractor (speech_encoder_prenet.py:308-318). x, y 16-byte aligned. */
+int st5_act_fwd(const void* x, void* y, int dtype, int act, int64_t n, void* stream);
 /* dpre = dropout-backward(dy) * act'(pre): backward of activation_fn + activation dropout
  * (transformer_layer.py:127-129, speech_decoder_prenet.py:41-47 via espnet Prenet). */
 int st5_act_bwd(const void* dy, const void* pre, void* dpre, int dtype, int act, int64_t n, float drop_p, uint64_t seed,
@@ -241,6 +244,20 @@ int st5_conv0_gn_gelu_fwd(const float* wave, const float* w, const float* gamma,
                           float* mean, float* rstd, float* ws, int32_t B, int64_t n_samples, int32_t C, int32_t K,
                           int32_t stride, float eps, int act, void* stream);
 int st5_conv0_gn_gelu_bwd(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws,
+                          int dtype, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride, int act,
+                          void* stream);
+
+/* Layer 0 in extractor mode "layer_norm" (t5_transformer_large, models/speecht5.py:1421; block builder
+ * speech_encoder_prenet.py:308-318): Conv1d(1 -> C, K taps, `stride`, no bias) + Fp32LayerNorm over the C channels of
+ * each frame + GELU, fused in ONE pass (a warp per frame). y [B, T0, C] channels-last in `dtype`; mean / rstd [B * T0]
+ * are saved for the backward. C even, C <= 512, K <= 16. Backward: dw [C, K], dgamma [C], dbeta [C] are ACCUMULATED
+ * (+=); ws: st5_conv0_ln_ws_floats(...) floats of scratch; no input gradient (the input is the waveform). */
+int64_t st5_conv0_ln_ws_floats(int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride);
+int st5_conv0_ln_gelu_fwd(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                          float* mean, float* rstd, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride,
+                          float eps, int act, void* stream);
+int st5_conv0_ln_gelu_bwd(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
                           const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws,
                           int dtype, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride, int act,
                           void* stream);

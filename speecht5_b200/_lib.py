@@ -78,6 +78,12 @@ _PROTOS = {
     "st5_bn_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64, _i64, _i32,
                              _f, _u64, _u64, _vp, _vp]),
     "st5_conv0_ws_floats": (C.c_int64, [_i32, _i64, _i32, _i32, _i32]),
+    "st5_conv0_ln_ws_floats": (C.c_int64, [_i32, _i64, _i32, _i32, _i32]),
+    "st5_conv0_ln_gelu_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f, _i32,
+                                        _vp]),
+    "st5_conv0_ln_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,
+                                        _i32, _i32, _i32, _vp]),
+    "st5_act_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp]),
     "st5_conv0_gn_gelu_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _f,
                                         _i32, _vp]),
     "st5_conv0_gn_gelu_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,

@@ -149,6 +149,28 @@ int st5_bn_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const
                    "st5_bn_bwd");
 }
 
+int64_t st5_conv0_ln_ws_floats(int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride) {
+  return conv0_ln_ws_floats(B, n_samples, C, K, stride);
+}
+int st5_conv0_ln_gelu_fwd(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                          float* mean, float* rstd, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride,
+                          float eps, int act, void* stream) {
+  return set_error(conv0_ln_fwd_launch(wave, w, gamma, beta, y, dtype, mean, rstd, B, n_samples, C, K, stride, eps, act,
+                                       (cudaStream_t)stream),
+                   "st5_conv0_ln_gelu_fwd");
+}
+int st5_conv0_ln_gelu_bwd(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws,
+                          int dtype, int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride, int act,
+                          void* stream) {
+  return set_error(conv0_ln_bwd_launch(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, ws, dtype, B, n_samples,
+                                       C, K, stride, act, (cudaStream_t)stream),
+                   "st5_conv0_ln_gelu_bwd");
+}
+int st5_act_fwd(const void* x, void* y, int dtype, int act, int64_t n, void* stream) {
+  return set_error(act_fwd_launch(x, y, dtype, act, n, (cudaStream_t)stream), "st5_act_fwd");
+}
+
 int64_t st5_conv0_ws_floats(int32_t B, int64_t n_samples, int32_t C, int32_t K, int32_t stride) {
   return conv0_ws_floats(B, n_samples, C, K, stride);
 }

@@ -286,6 +286,42 @@ int act_bwd_launch(const void* dy, const void* pre, void* dpre, int dtype, int a
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ activation forward (stand-alone)
+// y = act(x): the GELU that follows the per-frame LayerNorm of the "layer_norm" waveform extractor
+// (speech_encoder_prenet.py:308-318: conv -> dropout(0) -> LayerNorm -> GELU). 8 (bf16) / 4 (fp32) elements per thread.
+__device__ __forceinline__ float act_value(float z, int act) {
+  if (act == 4) return gelu_tanh_fwd(z);
+  if (act == 2) return gelu_fwd(z);
+  if (act == 1) return fmaxf(z, 0.f);
+  if (act == 3) return tanhf(z);
+  return z;
+}
+template <typename T, int V>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int act, int64_t n) {
+  const int64_t nv = n / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 in = reinterpret_cast<const uint4*>(x)[i];
+    const T* e = reinterpret_cast<const T*>(&in);
+    uint4 out;
+    T* o = reinterpret_cast<T*>(&out);
+#pragma unroll
+    for (int k = 0; k < V; ++k) stf<T>(o + k, act_value(ldf<T>(e + k), act));
+    reinterpret_cast<uint4*>(y)[i] = out;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nv * V + threadIdx.x; i < n; i += blockDim.x) stf<T>(y + i, act_value(ldf<T>(x + i), act));
+}
+int act_fwd_launch(const void* x, void* y, int dtype, int act, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (!aligned16(x) || !aligned16(y)) return -2;
+  if (dtype == ST5_F32)
+    act_fwd_kernel<float, 4><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>((const float*)x, (float*)y, act, n);
+  else
+    act_fwd_kernel<__nv_bfloat16, 8><<<grid_for(n / 8 + 1, 256), 256, 0, s>>>((const __nv_bfloat16*)x,
+                                                                             (__nv_bfloat16*)y, act, n);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ grouped column sums (bias gradients)
 // grid: (col tiles of 32, groups, row splits). block (32, 8). Partial sums are combined with fp32 atomics.
 template <typename T>

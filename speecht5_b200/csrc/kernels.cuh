@@ -160,6 +160,14 @@ int conv0_fwd_launch(const float* wave, const float* w, const float* gamma, cons
 int conv0_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
                      const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws, int dtype,
                      int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
+int64_t conv0_ln_ws_floats(int32_t B, int64_t n, int32_t C, int32_t K, int32_t S);
+int conv0_ln_fwd_launch(const float* wave, const float* w, const float* gamma, const float* beta, void* y, int dtype,
+                        float* mean, float* rstd, int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, float eps,
+                        int act, cudaStream_t s);
+int conv0_ln_bwd_launch(const void* dy, const float* wave, const float* w, const float* gamma, const float* beta,
+                        const float* mean, const float* rstd, float* dw, float* dgamma, float* dbeta, float* ws,
+                        int dtype, int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, int act, cudaStream_t s);
+int act_fwd_launch(const void* x, void* y, int dtype, int act, int64_t n, cudaStream_t s);
 int64_t tts_loss_blocks(int B, int L);
 int64_t guided_attn_blocks(int n_layers, int B, int heads, int T_out);
 int tts_loss_fwd_launch(const float* after, const float* before, const float* logits, const float* ys, int64_t y_bs,

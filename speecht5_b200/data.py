@@ -48,6 +48,52 @@ def synthetic_asr_batch(B, n_samples, T_tgt, vocab=81, seed=1, ragged=True, pin=
     return _pin(sample) if pin else sample
 
 
+def synthetic_speech_pretrain_batch(B, n_samples, n_classes=500, label_rate=50, sample_rate=16000, hop=256, odim=80, r=2,
+                                    seed=1, pin=False):
+    """SURVEY 8(d) config 4, speech micro-batch, with the key contract of speecht5/data/speech_dataset.py:302-386 for the
+    pre-training recipe (pad_audio False: every waveform cropped to one length, so the padding mask is all False):
+    waveforms N(0, 0.1^2) [B, n], HuBERT k-means labels U{0..n_classes-1} at `label_rate` Hz (:409-425: round(n *
+    rate / 16000) per utterance), log-mel reconstruction target [B, 1 + n // hop, odim], decoder input = every r-th
+    frame shifted by one (:335-344), stop labels 1 from the last real frame on (:346-349), 512-d x-vectors."""
+    g = torch.Generator().manual_seed(seed)
+    wave = torch.randn(B, n_samples, generator=g) * 0.1
+    L = 1 + n_samples // hop
+    fbank = torch.randn(B, L, odim, generator=g)
+    fb_in = fbank[:, r - 1::r]
+    len_in = torch.full((B,), L // r, dtype=torch.long)
+    prev = torch.cat([fb_in.new_zeros((B, 1, odim)), fb_in[:, :-1]], dim=1).contiguous()
+    labels = torch.zeros(B, L)
+    labels[:, L - 1:] = 1.0
+    n_lab = int(round(n_samples * label_rate / sample_rate))
+    km = torch.randint(0, n_classes, (B, n_lab), generator=g)
+    net_input = dict(source=wave, padding_mask=torch.zeros(B, n_samples, dtype=torch.bool), prev_output_tokens=prev,
+                     spkembs=torch.randn(B, 512, generator=g), tgt_lengths=len_in)
+    sample = dict(id=torch.arange(B), net_input=net_input, labels=labels, dec_target=fbank,
+                  dec_target_lengths=torch.full((B,), L, dtype=torch.long), src_lengths=[n_samples] * B,
+                  task_name="speech_pretrain", target_lengths_list=[torch.full((B,), n_lab, dtype=torch.long)],
+                  ntokens_list=[B * n_lab], target_list=[km])
+    return _pin(sample) if pin else sample
+
+
+def synthetic_text_pretrain_batch(B, T, vocab, mask_idx, mask_ratio=0.3, pad=1, eos=2, seed=1, pin=False):
+    """SURVEY 8(d) config 4, text micro-batch: `--sample-break-mode eos --tokens-per-sample 512` blocks through the
+    denoising collater (speecht5/data/text_dataset.py:18-98 `collate`, called from :434-443: source = noised tokens, target = the
+    clean block, prev_output_tokens = the target rotated so that eos comes first). The BART span infilling itself is the
+    host pipeline's; here `mask_ratio` of the positions carry <mask> (same shapes: the step's cost does not depend on
+    which positions)."""
+    g = torch.Generator().manual_seed(seed)
+    target = torch.randint(4, vocab - 2, (B, T), generator=g)
+    target[:, -1] = eos
+    source = target.clone()
+    hide = torch.rand(B, T - 1, generator=g) < mask_ratio
+    source[:, :-1][hide] = mask_idx
+    prev = torch.cat([target[:, -1:], target[:, :-1]], dim=1).contiguous()
+    sample = dict(id=torch.arange(B), nsentences=B, ntokens=B * T, target=target, task_name="text_pretrain",
+                  net_input=dict(src_tokens=source, src_lengths=torch.full((B,), T, dtype=torch.long),
+                                 prev_output_tokens=prev))
+    return _pin(sample) if pin else sample
+
+
 def collate_frames(frames, is_audio_input=False):
     """text_to_speech_dataset.py:25-45 _collate_frames: zero-padded stack of [L_i, F] (or [L_i]) tensors."""
     max_len = max(f.size(0) for f in frames)
@@ -203,4 +249,6 @@ def _pin(obj):
         return obj.pin_memory()
     if isinstance(obj, dict):
         return {k: _pin(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_pin(v) for v in obj)
     return obj

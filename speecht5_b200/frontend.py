@@ -1,6 +1,8 @@
 """Waveform feature extractor of the speech-input branch (reference
-speecht5/models/modules/speech_encoder_prenet.py:277-374, mode "default"): seven bias-free Conv1d layers
-[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2, GroupNorm(512 groups) after the first, GELU after each.
+speecht5/models/modules/speech_encoder_prenet.py:277-374): seven bias-free Conv1d layers
+[(512,10,5)] + [(512,3,2)]*4 + [(512,2,2)]*2 with GELU after each; mode "default" (Base recipes) puts a GroupNorm(512
+groups) after the first, mode "layer_norm" (t5_transformer_large, models/speecht5.py:1421) a LayerNorm over the channels
+of every frame after every conv (:308-318).
 
 The index algebra is checked on the CPU against torch's convolutions through a GEMM emulator
 (tests/test_frontend_cpu.py), the device path against the oracle and the reference fixtures (tests/test_frontend_gpu.py,
@@ -8,7 +10,10 @@ tests/test_ref_pin_gpu.py). The TTS path does not import this module.
 
 Device formulation (channels-last activations [B, T, C] throughout, no im2col, no transposes):
 * layer 0: csrc/conv_frontend.cu -- conv + GroupNorm + GELU fused, the convolution recomputed from the waveform in
-  every pass (kernels.conv0_gn_gelu_fwd / _bwd);
+  every pass (kernels.conv0_gn_gelu_fwd / _bwd); in "layer_norm" mode conv + per-frame LayerNorm + GELU in ONE pass, a
+  warp per frame (kernels.conv0_ln_gelu_fwd / _bwd);
+* layers 1..6 in "layer_norm" mode: the same window GEMM without an epilogue activation, the row LayerNorm kernel of
+  the transformer blocks (ops.residual_layer_norm, fp32 statistics) and a stand-alone GELU (kernels.act_fwd / act_bwd);
 * layers 1..6 forward: ONE batched tcgen05 GEMM each over an overlapping-window view of the input -- row t of
   utterance b is the k*C_in contiguous elements starting at frame t*stride (row pitch stride*C_in) -- with GELU and
   the pre-activation store in the epilogue;
@@ -46,23 +51,24 @@ def conv_out_len(T, k, s):
 
 
 class StridedConvGeluFn(torch.autograd.Function):
-    """y = GELU(Conv1d(C_in -> C_out, k, stride, no bias)(x)) on channels-last x [B, T, C_in] -> [B, T_out, C_out]."""
+    """y = GELU(Conv1d(C_in -> C_out, k, stride, no bias)(x)) on channels-last x [B, T, C_in] -> [B, T_out, C_out];
+    activation=None leaves the convolution alone (the "layer_norm" extractor normalises before its GELU)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride):
+    def forward(ctx, x, weight, stride, activation="gelu"):
         x = x.contiguous()
         B, T, Cin = x.shape
         Cout, _, k = weight.shape
         s = int(stride)
         To = conv_out_len(T, k, s)
-        act = _resolve_act("gelu", x.dtype)
+        act = _resolve_act(activation, x.dtype)
         w2 = RT.shadow(("fe_f", id(weight)), lambda: weight.detach().permute(0, 2, 1).reshape(Cout, k * Cin))
         xa = _split(x.view(B * T, Cin))
         y = torch.empty((B, To, Cout), dtype=x.dtype, device=x.device)
-        pre = torch.empty_like(y)
+        pre = torch.empty_like(y) if act is not None else None
         kw = dict(M=To, N=Cout, K=k * Cin, a_ld=s * Cin, b_ld=k * Cin, c_ld=Cout, nb1=B, nb2=1, a_bs=(T * Cin, 0),
                   b_bs=(0, 0), c_bs=(To * Cout, 0))
-        _passes(xa, w2, y, kw, dict(act=act, c_pre=pre))
+        _passes(xa, w2, y, kw, dict(act=act, c_pre=pre) if act is not None else None)
         ctx.save_for_backward(weight, pre)
         ctx.xa = xa
         ctx.meta = (B, T, Cin, Cout, k, s, To, act)
@@ -80,9 +86,12 @@ class StridedConvGeluFn(torch.autograd.Function):
         gp = torch.zeros((B, rows_p, Cout), dtype=dt, device=dev)
         g = gp[:, front:front + To]
         # g = dy * gelu'(pre), written straight into the padded buffer the phase GEMMs read
-        gtmp = torch.empty((B, To, Cout), dtype=dt, device=dev)
-        K.act_bwd(dy.contiguous(), pre, gtmp, act)
-        g.copy_(gtmp)
+        if act is not None:
+            gtmp = torch.empty((B, To, Cout), dtype=dt, device=dev)
+            K.act_bwd(dy.contiguous(), pre, gtmp, act)
+            g.copy_(gtmp)
+        else:
+            g.copy_(dy)
         ga = _split(gp.view(B * rows_p, Cout))
         # ---- input gradient, one window GEMM per phase r: dx[b, s*m + r, :] = sum_q gpad[b, m + q', :] . Wr[q]
         dx = torch.empty((B, T, Cin), dtype=dt, device=dev)  # every frame belongs to exactly one phase
@@ -112,7 +121,61 @@ class StridedConvGeluFn(torch.autograd.Function):
         _passes(_off(ga, front * Cout), ctx.xa, dW2, kw)
         dW = dW2.sum(0).view(Cout, k, Cin).permute(0, 2, 1).contiguous()
         ctx.xa = None
-        return dx, dW, None
+        return dx, dW, None, None
+
+
+class GeluFn(torch.autograd.Function):
+    """Stand-alone GELU (exact erf form in parity mode, tanh form on bf16 activations) behind the per-frame LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, z):
+        z = z.contiguous()
+        act = _resolve_act("gelu", z.dtype)
+        y = torch.empty_like(z)
+        K.act_fwd(z, y, act)
+        ctx.save_for_backward(z)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        dz = torch.empty_like(z)
+        K.act_bwd(dy.contiguous(), z, dz, ctx.act)
+        return dz
+
+
+class Conv0LayerNormGeluFn(torch.autograd.Function):
+    """Layer 0 of the "layer_norm" extractor: waveform [B, n] fp32 -> GELU(LayerNorm_C(Conv1d(1 -> C, k, stride)))
+    channels-last [B, T0, C]; per-frame statistics (fp32) saved for the backward."""
+
+    @staticmethod
+    def forward(ctx, wave, weight, gamma, beta, stride, eps, out_dtype):
+        wave = wave.float().contiguous()
+        B, n = wave.shape
+        Cc, _, k = weight.shape
+        s = int(stride)
+        T0 = conv_out_len(n, k, s)
+        act = _resolve_act("gelu", out_dtype)
+        w2 = weight.detach().reshape(Cc, k).float().contiguous()
+        y = torch.empty((B, T0, Cc), dtype=out_dtype, device=wave.device)
+        mean = torch.empty((B * T0,), dtype=torch.float32, device=wave.device)
+        rstd = torch.empty_like(mean)
+        K.conv0_ln_gelu_fwd(wave, w2, gamma.detach().float(), beta.detach().float(), y, mean, rstd, s, eps, act)
+        ctx.save_for_backward(wave, w2, gamma, beta, mean, rstd)
+        ctx.meta = (s, act, tuple(weight.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        wave, w2, gamma, beta, mean, rstd = ctx.saved_tensors
+        s, act, wshape = ctx.meta
+        dw = torch.zeros_like(w2)
+        dg = torch.zeros(w2.shape[0], dtype=torch.float32, device=w2.device)
+        db = torch.zeros_like(dg)
+        K.conv0_ln_gelu_bwd(dy.contiguous(), wave, w2, gamma.detach().float(), beta.detach().float(), mean, rstd, dw, dg,
+                            db, s, act)
+        return None, dw.view(wshape), dg, db, None, None, None
 
 
 class Conv0GroupNormGeluFn(torch.autograd.Function):
@@ -151,14 +214,17 @@ CONV_FEATURE_LAYERS = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
 
 
 class ConvFeatureExtractor(torch.nn.Module):
-    """speech_encoder_prenet.py:277-374 in mode "default" (the Base recipes). Parameter names follow the reference
-    (`conv_layers.{i}.0.weight` [C_out, C_in, k], GroupNorm affine at `conv_layers.0.2.{weight,bias}`). Output is
-    channels-last [B, T, C] -- the reference's [B, C, T] transposed, which is what its caller does next (:169)."""
+    """speech_encoder_prenet.py:277-374, modes "default" (the Base recipes) and "layer_norm" (t5_transformer_large).
+    Parameter names follow the reference: `conv_layers.{i}.0.weight` [C_out, C_in, k]; GroupNorm affine at
+    `conv_layers.0.2.{weight,bias}`; in "layer_norm" mode the norm of block i sits between two TransposeLast modules,
+    `conv_layers.{i}.2.1.{weight,bias}` (:308-318). Output is channels-last [B, T, C] -- the reference's [B, C, T]
+    transposed, which is what its caller does next (:169)."""
 
     def __init__(self, conv_layers=None, mode="default", conv_bias=False):
         super().__init__()
-        if mode != "default" or conv_bias:
-            raise NotImplementedError("only extractor_mode=default without conv bias (the Base recipes) is built")
+        if mode not in ("default", "layer_norm") or conv_bias:
+            raise NotImplementedError("extractor_mode default / layer_norm without conv bias (the reference's recipes) are built")
+        self.mode = mode
         self.specs = list(conv_layers or CONV_FEATURE_LAYERS)
         assert self.specs[0][1] <= 16
         self.conv_layers = torch.nn.ModuleList()
@@ -167,7 +233,9 @@ class ConvFeatureExtractor(torch.nn.Module):
             conv = torch.nn.Conv1d(in_d, dim, k, stride=s, bias=False)
             torch.nn.init.kaiming_normal_(conv.weight)
             mods = [conv, torch.nn.Dropout(0.0)]
-            if i == 0:
+            if mode == "layer_norm":  # Sequential(TransposeLast, Fp32LayerNorm, TransposeLast): the key layout only
+                mods.append(torch.nn.Sequential(torch.nn.Identity(), torch.nn.LayerNorm(dim), torch.nn.Identity()))
+            elif i == 0:
                 mods.append(torch.nn.GroupNorm(dim, dim, affine=True))
             mods.append(torch.nn.GELU())
             self.conv_layers.append(torch.nn.Sequential(*mods))
@@ -176,7 +244,19 @@ class ConvFeatureExtractor(torch.nn.Module):
     def forward(self, wave):
         if not wave.is_cuda:
             raise RuntimeError("speecht5_b200 kernels need CUDA tensors (no CPU fallback)")
+        return self._layers(wave)
+
+    def _layers(self, wave):
         blk0 = self.conv_layers[0]
+        if self.mode == "layer_norm":
+            from . import ops
+            ln0 = blk0[2][1]
+            x = Conv0LayerNormGeluFn.apply(wave, blk0[0].weight, ln0.weight, ln0.bias, self.specs[0][2], ln0.eps, RT.dtype)
+            for i in range(1, len(self.specs)):
+                blk = self.conv_layers[i]
+                u = StridedConvGeluFn.apply(x, blk[0].weight, self.specs[i][2], None)
+                x = GeluFn.apply(ops.residual_layer_norm(u, None, blk[2][1]))
+            return x
         x = Conv0GroupNormGeluFn.apply(wave, blk0[0].weight, blk0[2].weight, blk0[2].bias, self.specs[0][2],
                                        blk0[2].eps, RT.dtype)
         for i in range(1, len(self.specs)):

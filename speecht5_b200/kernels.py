@@ -293,6 +293,42 @@ def conv0_gn_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, s
     _count(4)
 
 
+def conv0_ln_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
+    """st5_conv0_ln_gelu_fwd: wave [B, n] fp32, w [C, K] fp32 -> y [B, T0, C] (y.dtype), mean / rstd [B * T0]."""
+    _require_cuda(wave, w, y)
+    assert wave.dtype == torch.float32 and w.dtype == torch.float32 and wave.is_contiguous() and w.is_contiguous()
+    B, n = wave.shape
+    Cc, Kt = w.shape
+    lib = _lib.load()
+    _lib.check(lib.st5_conv0_ln_gelu_fwd(_ptr(wave), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(y), dtype_id(y), _ptr(mean),
+                                         _ptr(rstd), B, n, Cc, Kt, stride, eps, ACT_IDS[act], _stream()),
+               "st5_conv0_ln_gelu_fwd")
+    _count(1)
+
+
+def conv0_ln_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, stride, act):
+    """st5_conv0_ln_gelu_bwd: dw / dgamma / dbeta (fp32) are accumulated."""
+    _require_cuda(dy, wave, w)
+    assert dy.is_contiguous()
+    B, n = wave.shape
+    Cc, Kt = w.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.st5_conv0_ln_ws_floats(B, n, Cc, Kt, stride), device=wave.device, dtype=torch.float32)
+    _lib.check(lib.st5_conv0_ln_gelu_bwd(_ptr(dy), _ptr(wave), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd),
+                                         _ptr(dw), _ptr(dgamma), _ptr(dbeta), _ptr(ws), dtype_id(dy), B, n, Cc, Kt,
+                                         stride, ACT_IDS[act], _stream()), "st5_conv0_ln_gelu_bwd")
+    _count(4)
+
+
+def act_fwd(x, y, act):
+    """st5_act_fwd: y = act(x), contiguous tensors of one dtype."""
+    _require_cuda(x, y)
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype
+    lib = _lib.load()
+    _lib.check(lib.st5_act_fwd(_ptr(x), _ptr(y), dtype_id(x), ACT_IDS[act], x.numel(), _stream()), "st5_act_fwd")
+    _count(1)
+
+
 def ctc_loss(logits, targets, tgt_offsets, input_lengths, target_lengths, nll, grad, s_max, blank, zero_infinity):
     """logits [T, B, V] fp32 (inner stride 1); see st5_ctc_loss (rows + concurrent alpha / beta sweeps + gradient rows)."""
     _require_cuda(logits, targets, nll)

@@ -588,6 +588,8 @@ def base_architecture(args):  # models/speecht5.py:1252-1383 (fields used by the
 @register_model_architecture("t5_transformer", "t5_transformer_base")
 def t5_transformer_base(args):  # :1385-1400
     g = lambda k, v: setattr(args, k, getattr(args, k, v))  # noqa: E731
+    g("use_conv_pos", True)
+    g("use_sinc_pos", True)
     g("layer_norm_first", False)
     g("relative_position_embedding", True)
     g("dropout", 0.1)
@@ -617,6 +619,10 @@ def t5_transformer_large(args):  # :1402-1425
     g("encoder_attention_heads", 16)
     g("decoder_attention_heads", 16)
     g("feature_grad_mult", 1.0)
+    g("extractor_mode", "layer_norm")
+    g("final_dim", 768)
+    g("use_conv_pos", True)
+    g("use_sinc_pos", True)
     g("mask_prob", 0.80)
     base_architecture(args)
 

@@ -547,7 +547,10 @@ class B200Trainer:
                 samples = [pad_to_buckets(s, self.shape_buckets) for s in samples]
             samples = [self._with_host_draws(s) for s in samples]
         layerdrop = self._draw_layerdrop()
-        if not self.use_cuda_graph:
+        # the pre-training criteria gather the MASKED frames (a different count every draw) and read their statistics
+        # back inside forward (speech_pretrain_criterion.py:101-189): not capturable -- those updates run eagerly
+        eager = not self.use_cuda_graph or any(s.get("task_name") in ("speech_pretrain", "text_pretrain") for s in samples)
+        if eager:
             RT.layer_keep = None  # eager: the host decides, dropped layers are really skipped
             RT.layer_keep_host = self._keep_host if layerdrop else None
             dev_samples = [_to_device(s, self.device) for s in samples]
@@ -733,6 +736,8 @@ def _to_device(sample, dev):
         return sample.to(dev, non_blocking=True)
     if isinstance(sample, dict):
         return {k: _to_device(v, dev) for k, v in sample.items()}
+    if isinstance(sample, (list, tuple)):  # (target_list of the pre-training collater, speech_dataset.py:383-385)
+        return type(sample)(_to_device(v, dev) for v in sample)
     return sample
 
 
@@ -770,4 +775,10 @@ def _copy_into(static, new):
 
 
 def h2d_bytes(sample):
-    return sum(v.numel() * v.element_size() for v in _flatten(sample).values())
+    if torch.is_tensor(sample):
+        return sample.numel() * sample.element_size()
+    if isinstance(sample, dict):
+        return sum(h2d_bytes(v) for v in sample.values())
+    if isinstance(sample, (list, tuple)):
+        return sum(h2d_bytes(v) for v in sample)
+    return 0

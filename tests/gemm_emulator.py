@@ -169,6 +169,37 @@ def conv0_gn_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
     rstd.copy_(rs.float())
 
 
+def _conv0_ln(wave, w, gamma, beta, eps):
+    v = torch.nn.functional.conv1d(wave.double()[:, None], w[:, None], stride=_conv0_ln.stride).transpose(1, 2)  # [B, T0, C]
+    return v, torch.nn.functional.layer_norm(v, (v.shape[-1],), gamma, beta, eps)
+
+
+def conv0_ln_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, stride, eps, act):
+    """st5_conv0_ln_gelu_fwd: Conv1d(1 -> C, k, stride) + LayerNorm over the channels of each frame + GELU."""
+    _conv0_ln.stride = stride
+    v, z = _conv0_ln(wave, w.double(), gamma.double(), beta.double(), eps)
+    y.copy_(torch.nn.functional.gelu(z).to(y.dtype))
+    mean.copy_(v.mean(-1).reshape(-1).float())
+    rstd.copy_((1.0 / torch.sqrt(v.var(-1, unbiased=False) + eps)).reshape(-1).float())
+
+
+def conv0_ln_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dgamma, dbeta, stride, act):
+    """st5_conv0_ln_gelu_bwd via autograd on the torch statement of the layer; dw / dgamma / dbeta accumulate."""
+    _conv0_ln.stride = stride
+    w_, g_, b_ = (t.double().clone().requires_grad_() for t in (w, gamma, beta))
+    with torch.enable_grad():
+        y = torch.nn.functional.gelu(_conv0_ln(wave, w_, g_, b_, 1e-5)[1])
+        gw, gg, gb = torch.autograd.grad(y, (w_, g_, b_), dy.double())
+    dw.add_(gw.float())
+    dgamma.add_(gg.float())
+    dbeta.add_(gb.float())
+
+
+def act_fwd(x, y, act):
+    assert act in ("gelu", "gelu_tanh")
+    y.copy_(torch.nn.functional.gelu(x.double()).to(y.dtype))
+
+
 def posenc_fwd(tokens, emb, x, pe, alpha, y, drop_p=0.0, seed=0, offset=0):
     """st5_posenc_fwd without dropout: y[b, t] = (emb[tokens[b, t]] | x[b, t]) + alpha * pe[t]."""
     assert drop_p == 0.0
@@ -259,6 +290,7 @@ def install_autograd(monkeypatch):
     install(monkeypatch)
     from speecht5_b200 import kernels as K, ops
     monkeypatch.setattr(K, "conv0_gn_gelu_bwd", conv0_gn_gelu_bwd)
+    monkeypatch.setattr(K, "conv0_ln_gelu_bwd", conv0_ln_gelu_bwd)
     monkeypatch.setattr(ops, "residual_layer_norm", residual_layer_norm)
     monkeypatch.setattr(ops, "scaled_posenc", scaled_posenc)
 
@@ -277,6 +309,8 @@ def install(monkeypatch):
     from speecht5_b200 import ops
     monkeypatch.setattr(ops, "attention", attention)
     monkeypatch.setattr(K, "conv0_gn_gelu_fwd", conv0_gn_gelu_fwd)
+    monkeypatch.setattr(K, "conv0_ln_gelu_fwd", conv0_ln_gelu_fwd)
+    monkeypatch.setattr(K, "act_fwd", act_fwd)
     monkeypatch.setattr(K, "_require_cuda", lambda *ts: None)
 
 

@@ -211,16 +211,48 @@ def test_speech_encoder_prenet_module_forward_against_the_oracle(monkeypatch, dt
     RT.invalidate_shadows()
 
 
-def _cpu_extractor_forward(self, wave):
-    """ConvFeatureExtractor.forward without its CUDA guard (the kernels underneath are emulated in these tests)."""
+@pytest.mark.parametrize("dims", ["[(32, 10, 5)] + [(32, 3, 2)] * 2 + [(32, 2, 2)]", "[(64, 10, 5), (48, 3, 2), (64, 2, 2)]"])
+def test_layer_norm_extractor_composition_matches_the_oracle(monkeypatch, dims):
+    """ConvFeatureExtractor(mode="layer_norm") (t5_transformer_large): layer-0 Function, window GEMM without epilogue
+    activation + row LayerNorm + stand-alone GELU for the rest, forward and every gradient against the oracle's
+    ConvFeatureExtractionModel (itself pinned to the reference's in both modes, tests/test_ref_pin_cpu.py); parameter
+    names are the reference checkpoint's (conv_layers.{i}.2.1.*)."""
+    from helpers import rel
+    from oracle.speecht5_oracle_asr import ConvFeatureExtractionModel
     from speecht5_b200 import frontend
     from speecht5_b200.ops import RT
-    blk0 = self.conv_layers[0]
-    x = frontend.Conv0GroupNormGeluFn.apply(wave, blk0[0].weight, blk0[2].weight, blk0[2].bias, self.specs[0][2],
-                                            blk0[2].eps, RT.dtype)
-    for i in range(1, len(self.specs)):
-        x = frontend.StridedConvGeluFn.apply(x, self.conv_layers[i][0].weight, self.specs[i][2])
-    return x
+    gemm_emulator.install_autograd(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    torch.manual_seed(3)
+    layers = eval(dims)
+    ref = ConvFeatureExtractionModel(layers, "layer_norm", False).double()
+    for blk in ref.conv_layers:
+        torch.nn.init.normal_(blk[2].weight, 1.0, 0.2), torch.nn.init.normal_(blk[2].bias, 0.0, 0.2)
+    mine = frontend.ConvFeatureExtractor(layers, "layer_norm", False)
+    import re
+    to_ref = lambda k: re.sub(r"^(conv_layers\.\d+\.2)\.", r"\1.1.", k)  # noqa: E731
+    sd = {to_ref(k): v.float() for k, v in ref.state_dict().items()}
+    assert set(sd) == set(mine.state_dict())
+    mine.load_state_dict(sd)
+    wave = torch.randn(2, 700, dtype=torch.float64) * 0.3
+    want = ref(wave).transpose(1, 2)
+    got = mine(wave.float())
+    assert got.shape == want.shape and rel(got, want) < 1e-5
+    probe = torch.randn_like(want)
+    (want * probe).sum().backward()
+    (got * probe.float()).sum().backward()
+    named = dict(mine.named_parameters())
+    for k, p in ref.named_parameters():
+        g = named[to_ref(k)].grad
+        assert g is not None and rel(g, p.grad) < 2e-5, (k, rel(g, p.grad))
+    RT.invalidate_shadows()
+
+
+def _cpu_extractor_forward(self, wave):
+    """ConvFeatureExtractor.forward without its CUDA guard (the kernels underneath are emulated in these tests)."""
+    return self._layers(wave)
 
 
 def test_speech_to_text_model_forward_and_greedy_decoding_on_emulated_kernels(monkeypatch):
@@ -623,4 +655,61 @@ def test_speech_pretraining_branch_of_forward_on_emulated_kernels(monkeypatch):
         only, none = model(source=wave, padding_mask=pad, target_list=labels, task_name="speech_pretrain",
                            only_hubert=True, mask_indices=mask_idx)
     assert none is None and close(only["logit_m_list"][0], hub_ref["logit_m_list"][0])
+    RT.invalidate_shadows()
+
+
+def test_joint_pretraining_update_through_the_trainer_on_emulated_kernels(monkeypatch):
+    """BASELINE config 4 in miniature: t5_transformer_large's structure (layer_norm waveform extractor, pre-LN, tied
+    embeddings, masked-prediction head, shared Gumbel quantizer) at tiny widths; one update = a speech_pretrain and a
+    text_pretrain micro-batch (`--update-freq 2`) through B200Trainer and the `speecht5` criterion dispatcher. The
+    pre-training criteria read their statistics back inside forward, so the trainer runs these updates eagerly even
+    when graphs are on; the loss falls over a few updates of the same batches and every parameter group moves."""
+    import numpy as np
+    from helpers import NO_DROPOUT, TINY
+    from speecht5_b200 import frontend
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.data import synthetic_speech_pretrain_batch, synthetic_text_pretrain_batch
+    from speecht5_b200.models import make_args
+    from speecht5_b200.ops import RT
+    from speecht5_b200.tasks import SpeechT5Task
+    from speecht5_b200.trainer import B200Trainer
+    gemm_emulator.install_autograd(monkeypatch)
+    gemm_emulator.install_trainer(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.disable_device_seed()
+    RT.clear_static()
+    RT.invalidate_shadows()
+    torch.manual_seed(5)
+    np.random.seed(5)
+    V = 40
+    args = make_args("t5_transformer_large", **dict(TINY, **NO_DROPOUT), bert_init=True, build_speech_encoder=True,
+                     build_text_decoder=True, share_input_output_embed=True, use_codebook=True, latent_vars=10,
+                     latent_groups=2, codebook_prob=0.5, hubert_num_classes=[23], final_dim=16, vocab_size=V,
+                     conv_feature_layers="[(32, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2", conv_pos=16,
+                     conv_pos_groups=4, mask_prob=0.5, hubert_mask_length=3, max_text_positions=600)
+    assert args.extractor_mode == "layer_norm" and args.layer_norm_first
+    task = SpeechT5Task(args)
+    model = task.build_model(args).train()
+    assert model.speech_encoder_prenet.feature_extractor.mode == "layer_norm"
+    crit = SpeechT5Criterion(task, loss_weights=[10.0], dec_weight=0.5, bart_weight=1.0, hubert_weight=1.0)
+    tr = B200Trainer(model, crit, task, lr=2e-3, clip_norm=10.0, use_cuda_graph=True)  # (pre-training -> eager anyway)
+    speech = synthetic_speech_pretrain_batch(2, 6400, n_classes=23, seed=1)
+    text = synthetic_text_pretrain_batch(3, 12, V, mask_idx=V - 2, seed=2)
+    assert speech["target_list"][0].shape == (2, 20) and speech["net_input"]["prev_output_tokens"].shape == (2, 13, 80)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    losses = []
+    for _ in range(6):
+        out, stats = tr.train_step([speech, text])
+        assert stats is None and out.shape == (2,) and bool(torch.isfinite(out).all())
+        losses.append(out.tolist())
+    assert tr.graph_misses == 0 and tr.num_updates == 6
+    assert losses[-1][0] < losses[0][0] and losses[-1][1] < losses[0][1], losses
+    moved = {n for n, p in model.named_parameters() if not torch.equal(p.detach(), before[n])}
+    for key in ("speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight",
+                "speech_encoder_prenet.feature_extractor.conv_layers.3.2.1.weight", "hubert_layer.label_embs_concat",
+                "quantizer.vars", "text_encoder_prenet.encoder_prenet.0.weight", "encoder.layers.0.fc1.weight",
+                "decoder.layers.0.encoder_attn.k_proj.weight", "speech_decoder_postnet.feat_out.weight"):
+        assert key in moved, key
+    RT.clear_static()
     RT.invalidate_shadows()

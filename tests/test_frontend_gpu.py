@@ -427,3 +427,130 @@ def test_speech_pretraining_branch_of_forward(cuda, dtype, tol):
         (got / n_got).backward()
         assert torch.isfinite(model.speech_encoder_prenet.feature_extractor.conv_layers[0][0].weight.grad).all()
     RT.dtype = torch.bfloat16
+
+
+@pytest.mark.parametrize("C,k,s,n,dtype", [(512, 10, 5, 4000, torch.float32), (512, 10, 5, 16000, torch.bfloat16),
+                                           (32, 10, 5, 1203, torch.float32), (96, 16, 4, 999, torch.float32),
+                                           (258, 7, 3, 2000, torch.bfloat16)])
+def test_layer0_layer_norm_kernels_against_torch(cuda, C, k, s, n, dtype):
+    """st5_conv0_ln_gelu_fwd / _bwd (layer 0 of the "layer_norm" extractor: conv + per-frame LayerNorm + GELU in one
+    pass; speech_encoder_prenet.py:308-318) against the same statement in torch fp64 autograd: output, saved
+    statistics, and the accumulated dw / dgamma / dbeta. Widths: the real 512, the tiny fixtures' 32, a channel count
+    that is not a multiple of 64, more than 10 taps (the 8-taps-per-warp instantiation)."""
+    from speecht5_b200 import kernels as K
+    from speecht5_b200.ops import _resolve_act
+    g = torch.Generator().manual_seed(C + n)
+    B = 3
+    wave = (torch.randn(B, n, generator=g) * 0.2).to(cuda)
+    w = (torch.randn(C, k, generator=g) * (2.0 / k) ** 0.5).to(cuda)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(cuda)
+    beta = (0.2 * torch.randn(C, generator=g)).to(cuda)
+    T0 = (n - k) // s + 1
+    act = _resolve_act("gelu", dtype)
+    y = torch.empty(B, T0, C, dtype=dtype, device=cuda)
+    mean = torch.empty(B * T0, device=cuda)
+    rstd = torch.empty_like(mean)
+    K.conv0_ln_gelu_fwd(wave, w, gamma, beta, y, mean, rstd, s, 1e-5, act)
+    w64, g64, b64 = (t.double().clone().requires_grad_() for t in (w, gamma, beta))
+    v = torch.nn.functional.conv1d(wave.double()[:, None], w64[:, None], stride=s).transpose(1, 2)
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(v, (C,), g64, b64, 1e-5))
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+    assert rel(y, want.detach()) < tol
+    assert rel(mean, v.detach().mean(-1).reshape(-1)) < 1e-5
+    assert rel(rstd, (v.detach().var(-1, unbiased=False) + 1e-5).rsqrt().reshape(-1)) < 1e-5
+    dy = torch.randn(B, T0, C, generator=g).to(cuda).to(dtype)
+    gw, gg, gb = torch.autograd.grad(want, (w64, g64, b64), dy.double())
+    dw = torch.full_like(w, 0.5)  # (accumulated into what is there)
+    dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    K.conv0_ln_gelu_bwd(dy, wave, w, gamma, beta, mean, rstd, dw, dg, db, s, act)
+    gtol = 1e-4 if dtype == torch.float32 else 2e-2  # (bf16 mode differentiates the tanh form of GELU)
+    assert rel(dw - 0.5, gw) < gtol and rel(dg, gg) < gtol and rel(db, gb) < gtol
+    # stand-alone GELU of the later layers (odd element count: vector body + scalar tail)
+    z = torch.randn(7, 331, generator=g).to(cuda).to(dtype)
+    out = torch.empty_like(z)
+    K.act_fwd(z, out, act)
+    assert rel(out, torch.nn.functional.gelu(z.double())) < (1e-6 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype,tol,gtol", [(torch.float32, 1e-4, 2e-3), (torch.bfloat16, 3e-2, 0.2)])
+def test_layer_norm_extractor_real_width_against_oracle(cuda, dtype, tol, gtol):
+    """ConvFeatureExtractor(mode="layer_norm") at the real seven layers x 512 channels on 0.5 s of audio: output and
+    every parameter gradient against the oracle's ConvFeatureExtractionModel (pinned to the reference's in this mode)."""
+    import re
+    from oracle.speecht5_oracle_asr import CONV_FEATURE_LAYERS, ConvFeatureExtractionModel
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    RT.dtype = dtype
+    RT.clear_static()
+    RT.invalidate_shadows()
+    torch.manual_seed(21)
+    ref = ConvFeatureExtractionModel(CONV_FEATURE_LAYERS, "layer_norm", False).double()
+    for blk in ref.conv_layers:
+        torch.nn.init.normal_(blk[2].weight, 1.0, 0.2), torch.nn.init.normal_(blk[2].bias, 0.0, 0.2)
+    mine = frontend.ConvFeatureExtractor(CONV_FEATURE_LAYERS, "layer_norm", False)
+    to_ref = lambda k: re.sub(r"^(conv_layers\.\d+\.2)\.", r"\1.1.", k)  # noqa: E731
+    mine.load_state_dict({to_ref(k): v.float() for k, v in ref.state_dict().items()})
+    mine = mine.to(cuda)
+    wave = torch.randn(2, 8000, dtype=torch.float64) * 0.3
+    want = ref(wave).transpose(1, 2)
+    got = mine(wave.float().to(cuda))
+    assert got.shape == want.shape and got.dtype == dtype and rel(got.cpu(), want.detach()) < tol
+    probe = torch.randn_like(want)
+    (want * probe).sum().backward()
+    (got.float() * probe.float().to(cuda)).sum().backward()
+    named = dict(mine.named_parameters())
+    for k, p in ref.named_parameters():
+        g = named[to_ref(k)].grad
+        assert g is not None and rel(g.cpu(), p.grad) < gtol, (k, rel(g.cpu(), p.grad))
+    RT.dtype = torch.bfloat16
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_joint_pretraining_update_through_the_trainer(cuda, dtype):
+    """BASELINE config 4 in miniature on the device: t5_transformer_large's structure (layer_norm extractor, pre-LN, tied
+    embeddings, masked-prediction head, shared quantizer) at tiny widths; a speech_pretrain + a text_pretrain micro-batch
+    per update through B200Trainer (these updates run eagerly, graphs on or off). Loss falls, parameters move, no
+    graph is captured. (tests/test_frontend_cpu.py runs the same on emulated kernels.)"""
+    import numpy as np
+    from helpers import NO_DROPOUT, TINY
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.data import synthetic_speech_pretrain_batch, synthetic_text_pretrain_batch
+    from speecht5_b200.models import make_args
+    from speecht5_b200.ops import RT
+    from speecht5_b200.tasks import SpeechT5Task
+    from speecht5_b200.trainer import B200Trainer
+    RT.dtype = dtype
+    RT.manual_seed(3)
+    RT.clear_static()
+    RT.invalidate_shadows()
+    torch.manual_seed(5)
+    np.random.seed(5)
+    V = 40
+    args = make_args("t5_transformer_large", **dict(TINY, **NO_DROPOUT), bert_init=True, build_speech_encoder=True,
+                     build_text_decoder=True, share_input_output_embed=True, use_codebook=True, latent_vars=10,
+                     latent_groups=2, codebook_prob=0.5, hubert_num_classes=[23], final_dim=16, vocab_size=V,
+                     conv_feature_layers="[(32, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2", conv_pos=16,
+                     conv_pos_groups=4, mask_prob=0.5, hubert_mask_length=3, max_text_positions=600)
+    task = SpeechT5Task(args)
+    model = task.build_model(args).to(cuda).train()
+    crit = SpeechT5Criterion(task, loss_weights=[10.0], dec_weight=0.5, bart_weight=1.0, hubert_weight=1.0)
+    tr = B200Trainer(model, crit, task, lr=2e-3, clip_norm=10.0, use_cuda_graph=True)
+    speech = synthetic_speech_pretrain_batch(2, 6400, n_classes=23, seed=1, pin=True)
+    text = synthetic_text_pretrain_batch(3, 12, V, mask_idx=V - 2, seed=2, pin=True)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    losses = []
+    for _ in range(8):
+        out, stats = tr.train_step([speech, text])
+        assert stats is None and out.shape == (2,) and bool(torch.isfinite(out).all())
+        losses.append(out.tolist())
+    tr.check_overflow()  # (raises if an update was skipped for a non-finite gradient norm)
+    assert tr.graph_misses == 0 and tr.num_updates == 8
+    assert losses[-1][0] < losses[0][0] and losses[-1][1] < losses[0][1], losses
+    moved = {n for n, p in model.named_parameters() if not torch.equal(p.detach(), before[n])}
+    for key in ("speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight",
+                "speech_encoder_prenet.feature_extractor.conv_layers.3.2.1.weight", "hubert_layer.label_embs_concat",
+                "quantizer.vars", "encoder.layers.0.fc1.weight", "decoder.layers.0.encoder_attn.k_proj.weight"):
+        assert key in moved, key
+    RT.dtype = torch.bfloat16
+    RT.clear_static()
+    RT.invalidate_shadows()

@@ -34,6 +34,8 @@ def test_arch_presets_match_reference_defaults():
     lg = make_args("t5_transformer_large")
     assert (lg.encoder_layers, lg.decoder_layers, lg.encoder_embed_dim, lg.encoder_attention_heads) == (24, 6, 1024, 16)
     assert lg.layer_norm_first and lg.decoder_normalize_before
+    assert lg.extractor_mode == "layer_norm" and lg.final_dim == 768 and lg.use_conv_pos and lg.use_sinc_pos  # :1402-1425
+    assert make_args("t5_transformer_base").use_conv_pos and a.extractor_mode == "default"
 
 
 def test_state_dict_keys_equal_oracle_and_reference_names():

@@ -78,8 +78,8 @@ def _asr_oracle(blob, ln_mode):
     over = dict(mg.TINY, conv_feature_layers=conv_layers(), feature_grad_mult=1.0, conv_pos=16, conv_pos_groups=4,
                 dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)
     if ln_mode:
-        over.update(extractor_mode="layer_norm", layer_norm_first=True, decoder_normalize_before=True, conv_bias=True,
-                    share_input_output_embed=True)
+        over.update(extractor_mode="layer_norm", layer_norm_first=True, decoder_normalize_before=True,
+                    conv_bias=ln_mode != "no_conv_bias", share_input_output_embed=True)
     model = T5TransformerModelASROracle(base_asr_args(**over), vocab_size=mg.VOCAB).train()
     missing = model.load_state_dict(reference_to_oracle_keys(state_of(blob)), strict=False)
     assert not missing.unexpected_keys, missing.unexpected_keys
@@ -87,7 +87,8 @@ def _asr_oracle(blob, ln_mode):
     return model
 
 
-@pytest.mark.parametrize("name,ln_mode", [("ref_asr_tiny", False), ("ref_asr_ln_tiny", True)])
+@pytest.mark.parametrize("name,ln_mode", [("ref_asr_tiny", False), ("ref_asr_ln_tiny", True),
+                                          ("ref_asr_large_style_tiny", "no_conv_bias")])
 def test_asr_oracle_matches_reference_outputs_loss_and_gradients(name, ln_mode):
     """Conv feature extractor (GroupNorm / LayerNorm modes), speech prenet with the reference's OWN mask draws, encoder +
     CTC head, text decoder pre/post-net; SpeechtoTextLoss CE + CTC; gradients down to conv layer 0."""

@@ -111,11 +111,14 @@ def test_tts_forward_loss_gradients_against_reference_vectors(cuda, name, pre_ln
         assert vals[len(vals) // 2] < 0.25, errs
 
 
-def _asr_model(cuda, dtype, blob):
+def _asr_model(cuda, dtype, blob, large_style=False):
     over = dict(TINY, **NO_DROPOUT, bert_init=True, build_speech_encoder=True, build_text_decoder=True,
                 conv_feature_layers=TINY_CONV, feature_grad_mult=1.0, conv_pos=16, conv_pos_groups=4, use_conv_pos=True,
                 use_sinc_pos=True, mask_prob=0.5, hubert_mask_length=4, mask_channel_prob=0.25, mask_channel_length=8,
                 max_text_positions=600)
+    if large_style:  # t5_transformer_large's structure (models/speecht5.py:1402-1425) on the tiny widths
+        over.update(extractor_mode="layer_norm", layer_norm_first=True, decoder_normalize_before=True,
+                    share_input_output_embed=True)
     model = _build(cuda, dtype, **over)
     missing = model.load_state_dict(state_of(blob))
     other = ("text_encoder_prenet.", "speech_decoder_prenet.", "speech_decoder_postnet.")  # not on the s2t branch, not stored
@@ -124,13 +127,17 @@ def _asr_model(cuda, dtype, blob):
     return model
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 4e-2)])
-def test_asr_step_against_reference_vectors(cuda, dtype, tol):
+@pytest.mark.parametrize("name,dtype,tol", [("ref_asr_tiny", torch.float32, 1e-3), ("ref_asr_tiny", torch.bfloat16, 4e-2),
+                                            ("ref_asr_large_style_tiny", torch.float32, 1e-3),
+                                            ("ref_asr_large_style_tiny", torch.bfloat16, 6e-2)])
+def test_asr_step_against_reference_vectors(cuda, name, dtype, tol):
     """s2t branch with the reference's OWN mask draws: conv front end, prenet (time + channel masks), encoder + CTC
-    head, text decoder; SpeechtoTextLoss CE + CTC and gradients down to conv layer 0 -- the reference's numbers."""
+    head, text decoder; SpeechtoTextLoss CE + CTC and gradients down to conv layer 0 -- the reference's numbers. The
+    large-style fixture is t5_transformer_large's structure: the "layer_norm" waveform extractor (per-frame LayerNorm
+    after every conv), pre-LN encoder / decoder, tied output embedding."""
     from speecht5_b200.criterions import SpeechT5Criterion
-    blob = load("ref_asr_tiny")
-    model = _asr_model(cuda, dtype, blob).train()
+    blob = load(name)
+    model = _asr_model(cuda, dtype, blob, large_style="large_style" in name).train()
     ni = dict(source=torch.from_numpy(blob["in/source"]).to(cuda),
               padding_mask=torch.from_numpy(blob["in/padding_mask"]).to(cuda),
               prev_output_tokens=torch.from_numpy(blob["in/prev_output_tokens"]).to(cuda), task_name="s2t",
