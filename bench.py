@@ -483,8 +483,41 @@ def run_pretrain(args):
              synthetic_text_pretrain_batch(P["text_batch"], P["text_len"], V, mask_idx=V - 2, seed=200 * rank + i, pin=True)]
             for i in range(2)]
     resident = [[_to_device(s, dev) for s in pair] for pair in host]
+    mem_log = []
+    if os.environ.get("ST5_MEMLOG", "0") == "1":  # per micro-batch: live / peak bytes on the device (to stderr)
+        inner = task.train_step
+
+        def logged(sample, *a, **kw):
+            torch.cuda.reset_peak_memory_stats()
+            r = inner(sample, *a, **kw)
+            mem_log.append((sample["task_name"], torch.cuda.memory_allocated() / 2**30, torch.cuda.max_memory_allocated() / 2**30))
+            print("mem", mem_log[-1], file=sys.stderr, flush=True)
+            return r
+        task.train_step = logged
+        for name in ("speech_encoder_prenet", "speech_encoder_prenet.feature_extractor", "text_encoder_prenet", "encoder",
+                     "hubert_layer", "quantizer", "decoder", "speech_decoder_postnet", "text_decoder_postnet"):
+            mod = model.get_submodule(name)
+            mod.register_forward_hook(lambda m, i, o, name=name: print(
+                "  after", name, round(torch.cuda.memory_allocated() / 2**30, 2), "GiB, peak",
+                round(torch.cuda.max_memory_allocated() / 2**30, 2), file=sys.stderr, flush=True))
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, win_dev, _, out = _timed_steps(trainer, resident, args.steps, args.warmup, world, dev, read_back=False)
+    try:
+        ms_dev, win_dev, _, out = _timed_steps(trainer, resident, args.steps, args.warmup, world, dev, read_back=False)
+    except torch.OutOfMemoryError:
+        import gc
+        seen = {}
+        for o in gc.get_objects():
+            try:
+                if torch.is_tensor(o) and o.is_cuda:
+                    st = o.untyped_storage()
+                    seen[st.data_ptr()] = (st.nbytes() / 2**30, tuple(o.shape), str(o.dtype))
+            except Exception:  # noqa: BLE001
+                pass
+        print("OOM: live python-visible GiB", sum(v[0] for v in seen.values()), "allocated GiB",
+              torch.cuda.memory_allocated() / 2**30, file=sys.stderr)
+        for v in sorted(seen.values(), reverse=True)[:25]:
+            print("   ", v, file=sys.stderr)
+        raise
     ms_e2e, _, last, out = _timed_steps(trainer, host, args.steps, args.warmup, world, dev, read_back=True)
     losses = [float(v) for v in out[0].tolist()]
     K.LAUNCHES = 0
@@ -527,7 +560,7 @@ def run_pretrain(args):
                                "gather has a data-dependent size)",
                    "global_batch": per_update, "parallelism": f"dp{world}", "exchange": trainer.exchange,
                    "cuda_graph": False, "parameters": n_params, "losses_speech_text": losses,
-                   "extractor_mode": margs.extractor_mode,
+                   "extractor_mode": margs.extractor_mode, "peak_memory_gib": torch.cuda.max_memory_allocated() / 2**30,
                    "l2": "2 distinct input pairs are cycled; the update's activations exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": sum(h2d_bytes(s) for s in host[0]), "d2h_bytes_per_step": int(last.numel() * 4)},

@@ -949,8 +949,11 @@ class AttentionTCFn(torch.autograd.Function):
                             key_pad=kp, pe_k=pe_hi, out=out, o_ld=d, o_bs=Tq * d, probs=probs, p_ld=p_ld, scale=scale,
                             drop_p=drop_p, seed=RT.seed, offset=off, probs_heads=cfg.get("probs_read_heads", 0) if want else 0)
             (K.attn_flash_fwd if flash else K.attn_fused_fwd)(a, None, psave, inv_l, o32)
-            ctx.save_for_backward(q_buf, kv_buf, pe_k, probs)
-            ctx.fused = (out, psave, inv_l, o32, kp)
+            # `out` is an OUTPUT of this Function: it goes through save_for_backward (as an attribute of ctx it closes
+            # the cycle out -> grad_fn -> ctx -> out, and psave / o32 of every layer would live until the next pass of
+            # Python's cycle collector -- ~12 GB per eager update of the Large pre-training step)
+            ctx.save_for_backward(q_buf, kv_buf, pe_k, probs, out)
+            ctx.fused = (psave, inv_l, o32, kp)
             ctx.meta = (cfg, off, RT.seed, p_ld, same, pe_hi)
             cfg["_ext_ok"] = True  # this call's backward reads an external dP through the first probs_grad_heads heads only
             if probs is None:
@@ -984,9 +987,11 @@ class AttentionTCFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, dprobs):
-        q_buf, kv_buf, pe_k, P = ctx.saved_tensors
+        q_buf, kv_buf, pe_k, P = ctx.saved_tensors[:4]
         cfg, off, seed, p_ld, same, pe_hi = ctx.meta
         fused = getattr(ctx, "fused", None)
+        if fused is not None:
+            fused = (ctx.saved_tensors[4],) + tuple(fused)  # (out, psave, inv_l, o32, key_pad)
         if fused is not None and pe_k is not None:
             return AttentionTCFn._fused_backward_rpe(q_buf, pe_k, pe_hi, cfg, off, seed, p_ld, fused, dout, dprobs)
         if fused is not None:

@@ -382,3 +382,50 @@ def test_bias_gradient_is_handed_over_to_the_consuming_layer_norm(monkeypatch):
     (o * r).sum().backward()
     assert torch.allclose(proj.bias.grad, r.sum((0, 1)), rtol=1e-5, atol=1e-5)
     RT.invalidate_shadows()
+
+
+def test_fused_attention_function_leaves_no_reference_cycle(monkeypatch):
+    """ops.AttentionTCFn (fused / streaming path) with the three kernel entry points stubbed: the output tensor reaches
+    the backward through save_for_backward (same storage as the forward's), and once the caller drops its references
+    the saved exponentials die by reference counting -- no object is left for Python's cycle collector (as a ctx
+    attribute the output closed a cycle that kept ~12 GB per eager update of the Large pre-training step alive)."""
+    import gc
+    import weakref
+    from speecht5_b200 import kernels as K
+    from speecht5_b200 import ops
+    seen = {}
+
+    def fwd(a, lse, psave=None, inv_l=None, out_f32=None):
+        seen["out"], seen["psave"] = a.out, weakref.ref(psave)
+        psave.zero_(), inv_l.fill_(1.0), out_f32.zero_()
+
+    def bwd(a, psave, inv_l, out_f32, delta, dq_acc, ext_heads=0):
+        seen["bwd_out"], seen["bwd_psave"] = a.out, psave.data_ptr()
+
+    monkeypatch.setattr(K, "attn_fused_fwd", fwd)
+    monkeypatch.setattr(K, "attn_flash_fwd", fwd)
+    monkeypatch.setattr(K, "attn_fused_bwd", bwd)
+    B, T, H, d = 2, 24, 2, 128
+    cfg = dict(H=H, d=d, q_col=0, k_col=1, v_col=2, scale=0.125, maxpos=0, causal=True, drop_p=0.0, return_probs=False,
+               probs_grad_heads=0, probs_read_heads=0)
+    gc.collect()
+    gc.disable()
+    try:
+        before = len(gc.get_objects())
+        q = torch.zeros(B, T, 3 * d, dtype=torch.bfloat16, requires_grad=True)
+        out, probs = ops.AttentionTCFn.apply(q, None, None, None, cfg)
+        assert probs is None and out.shape == (B, T, d)
+        psave_ptr = seen["psave"]().data_ptr()
+        out.float().sum().backward()
+        assert seen["bwd_out"] == seen["out"] == out.data_ptr() and seen["bwd_psave"] == psave_ptr
+        # a second pass whose graph is dropped WITHOUT running backward (the unmasked-frame head of the pre-training
+        # criterion with weight 0, inference under enable_grad, ...)
+        out2, _ = ops.AttentionTCFn.apply(q, None, None, None, cfg)
+        ref = seen["psave"]
+        assert ref() is not None
+        del out, out2
+        assert ref() is None, "saved exponentials must die with the last reference to the output"
+        assert gc.collect() == 0
+    finally:
+        gc.enable()
+    del before
