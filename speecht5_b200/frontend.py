@@ -391,7 +391,7 @@ class _WeightNormConv(torch.nn.Module):
 
 class SpeechEncoderPrenet(torch.nn.Module):
     """speech_encoder_prenet.py:57-275 for the built configuration (encoder_speech_prenet "conv", extractor_mode
-    "default", use_conv_pos and use_sinc_pos as in the Base arch): waveform -> [B, T, d], frame padding mask and the
+    "default" or "layer_norm", use_conv_pos and use_sinc_pos as in the Base / Large archs): waveform -> [B, T, d], frame padding mask and the
     mean-square feature penalty. The HuBERT-style mask draw stays on the host (speecht5_b200.data.compute_mask_indices,
     numpy, like the reference :236-262); its result is applied here."""
 

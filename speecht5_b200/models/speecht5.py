@@ -3,9 +3,11 @@ speecht5/models/speecht5.py (reference): same registry names (@register_model "t
 t5_transformer_base, t5_transformer_large, t5_transformer_base_asr :1252,1385,1402,1427), same forward signature
 (:786) and return tuples, same parameter names (checkpoints load with load_state_dict).
 
-Round-1 coverage of forward(): text -> speech (t2s, the BASELINE.json metric path). The speech-input branches
-(speech_encoder_prenet / hubert / codebook / s2c) are SURVEY.md section-8 rows still to come and raise
-NotImplementedError rather than silently falling back to PyTorch."""
+Coverage of forward(): text -> speech (t2s, the BASELINE.json metric path), speech -> text (s2t: waveform front end,
+CE + CTC), text -> text (t2t / text pre-training), speech pre-training (HuBERT targets, masked-prediction head, shared
+Gumbel quantizer, reconstruction through the speech decoder; only_hubert / feature_only returns), greedy generation of
+speech and text. The branches SURVEY.md section 2 leaves out (speaker identification s2c, voice conversion /
+enhancement s2s inputs) raise NotImplementedError rather than silently falling back to PyTorch."""
 import argparse
 import logging
 from argparse import Namespace
