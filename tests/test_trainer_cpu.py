@@ -209,3 +209,93 @@ def test_packed_device_copies_keep_structure_and_share_one_buffer():
     for s, v in zip(b, va):
         for x, y in zip(_flatten(s).values(), _flatten(v).values()):
             assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------- joint pre-training update on two ranks
+def _pretrain_build():
+    import gemm_emulator
+    from helpers import NO_DROPOUT, TINY
+    from speecht5_b200 import frontend
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.models import make_args
+    from speecht5_b200.ops import RT
+    from speecht5_b200.tasks import SpeechT5Task
+    p = gemm_emulator.Patcher()
+    gemm_emulator.install_autograd(p)
+    gemm_emulator.install_trainer(p)
+    frontend.ConvFeatureExtractor.forward = lambda self, wave: self._layers(wave)  # (no CUDA guard: emulated kernels)
+    RT.dtype = torch.bfloat16
+    RT.disable_device_seed()
+    RT.clear_static()
+    RT.invalidate_shadows()
+    torch.manual_seed(7)
+    args = make_args("t5_transformer_large", **dict(TINY, **NO_DROPOUT), bert_init=True, build_speech_encoder=True,
+                     build_text_decoder=True, share_input_output_embed=True, hubert_num_classes=[23], final_dim=16,
+                     vocab_size=40, conv_feature_layers="[(32, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2",
+                     conv_pos=16, conv_pos_groups=4, mask_prob=0.5, hubert_mask_length=3, max_text_positions=600)
+    task = SpeechT5Task(args)
+    model = task.build_model(args).train()
+    crit = SpeechT5Criterion(task, loss_weights=[10.0], dec_weight=0.5, bart_weight=1.0, hubert_weight=1.0)
+    return task, model, crit
+
+
+def _pretrain_batches(r):
+    """(speech, text) micro-batches of rank r; the HuBERT mask is part of the batch (the in-model numpy draw would differ
+    between a one-process and a two-process run)."""
+    from speecht5_b200.data import synthetic_speech_pretrain_batch, synthetic_text_pretrain_batch
+    speech = synthetic_speech_pretrain_batch(2, 6400, n_classes=23, seed=11 + r)
+    g = torch.Generator().manual_seed(5 + r)
+    speech["net_input"]["mask_indices"] = torch.rand(2, 19, generator=g) < 0.5
+    return [speech, synthetic_text_pretrain_batch(3, 12, 40, mask_idx=38, seed=21 + r)]
+
+
+def _pretrain_worker(rank, world, port, mode, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from speecht5_b200.trainer import B200Trainer
+    task, model, crit = _pretrain_build()
+    tr = B200Trainer(model, crit, task, lr=1e-2, use_cuda_graph=False, exchange=mode)
+    for _ in range(2):
+        tr.train_step(_pretrain_batches(rank))
+    tr.consolidate()
+    q.put((rank, {n: p.detach().numpy().copy() for n, p in model.named_parameters()}, tr.grad_norm()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["shard", "allreduce"])
+def test_two_rank_joint_pretraining_update_equals_four_micro_batches_on_one_rank(mode):
+    """The pre-training recipe trains with `--find-unused-parameters` (README): the text micro-batch -- the LAST one of an
+    update -- never touches the waveform front end, the masked-prediction head or the speech decoder pre/post-net, and
+    the speech one never touches the text pre/post-nets. Stages whose backward hook does not fire on the last
+    micro-batch are exchanged at the end of the update: two ranks with (speech_r, text_r) each reach the parameters one
+    process reaches with the four micro-batches."""
+    from speecht5_b200.trainer import B200Trainer
+    task, model, crit = _pretrain_build()
+    tr = B200Trainer(model, crit, task, lr=1e-2, use_cuda_graph=False)
+    for _ in range(2):
+        tr.train_step(_pretrain_batches(0) + _pretrain_batches(1))
+    ref = {n: p.detach().clone() for n, p in model.named_parameters()}
+    gn1 = tr.grad_norm()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29911 + (os.getpid() * 3 + (mode == "shard")) % 300
+    procs = [ctx.Process(target=_pretrain_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, out, gn in res:
+        assert abs(gn - gn1) < 1e-3 * gn1, (gn, gn1)
+        for n, v in out.items():
+            if n.endswith("norm_k.bias"):
+                continue  # shifts every logit of a row alike: analytically zero gradient, Adam normalises its rounding noise
+            err = ((torch.from_numpy(v) - ref[n]).norm() / (ref[n].norm() + 1e-12)).item()
+            assert err < 2e-3, (n, err)
+    for n in res[0][1]:
+        assert (res[0][1][n] == res[1][1][n]).all(), n
+    moved = [n for n in ("speech_encoder_prenet.feature_extractor.conv_layers.0.0.weight", "hubert_layer.label_embs_concat",
+                         "text_encoder_prenet.encoder_prenet.0.weight", "speech_decoder_postnet.feat_out.weight")
+             if not torch.equal(ref[n], dict(_pretrain_build()[1].named_parameters())[n].detach())]
+    assert len(moved) == 4, moved
