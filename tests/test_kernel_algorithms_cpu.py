@@ -4,6 +4,7 @@ against torch's convolution. The postnet's 5-tap convolution already runs this w
 import math
 
 import numpy as np
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -396,3 +397,83 @@ def test_ctc_kernel_program_matches_torch():
         assert abs((nll if feasible else 0.0) - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (tg, Tn)
         assert np.abs(grad - logits.grad.numpy()[:, 0]).max() < 2e-5, (tg, Tn)
     assert not np.isfinite(_ctc_kernel_emulation(np.zeros((T, V), np.float32), [2, 2, 2, 2, 2, 2], 10)[0])
+
+
+def _conv0_ln_kernel_program(wave, w, gamma, beta, dy, stride, eps, n_ctas=3):
+    """csrc/conv_frontend.cu conv0_ln_fwd_kernel / conv0_ln_bwd_kernel restated step for step: a warp per frame, lane l
+    owns the channel pairs (2l + 64j, 2l + 64j + 1); forward = convolution from k broadcast taps, mean, CENTRED variance,
+    normalise, affine, GELU. Backward = a PAIR of warps per frame: both recompute x-hat, g = dy * gelu'(z) and the two
+    LayerNorm sums; warp `role` accumulates the taps k = role (mod 2) of dW and one of dgamma (role 0) / dbeta (role 1)
+    over its frames (frames are dealt to pairs round-robin); every pair writes ONE partial row [C*K | C | C] and a last
+    pass sums the rows. Returns (y, mean, rstd, dW, dgamma, dbeta)."""
+    B, n = wave.shape
+    C, K = w.shape
+    T0 = (n - K) // stride + 1
+    frames = B * T0
+    pairs = n_ctas * 4                                  # C0L_WARPS / 2 pairs per CTA
+    lanes = [[c for j in range(8) for c in (2 * l + 64 * j, 2 * l + 64 * j + 1) if c < C] for l in range(32)]
+    assert sorted(c for ln in lanes for c in ln) == list(range(C))  # the lanes partition the channels
+    y = np.zeros((frames, C))
+    mean, rstd = np.zeros(frames), np.zeros(frames)
+    part = np.zeros((pairs, C * K + 2 * C))
+
+    def gelu(z):
+        return 0.5 * z * (1.0 + np.vectorize(math.erf)(z / math.sqrt(2.0)))
+
+    def dgelu(z):
+        return 0.5 * (1.0 + np.vectorize(math.erf)(z / math.sqrt(2.0))) + z * np.exp(-0.5 * z * z) / math.sqrt(2.0 * math.pi)
+
+    for f in range(frames):
+        b, t = divmod(f, T0)
+        x = wave[b, t * stride: t * stride + K]
+        v = w @ x                                        # every lane: its channels, the same K taps
+        mu = v.sum() / C                                 # warp_sum over the lanes' partial sums
+        q = ((v - mu) ** 2).sum() / C
+        rs = 1.0 / math.sqrt(q + eps)
+        mean[f], rstd[f] = mu, rs
+        y[f] = gelu((v - mu) * rs * gamma + beta)
+    for p in range(pairs):
+        for role in (0, 1):
+            acc_w = np.zeros((C, K))
+            acc_aff = np.zeros(C)
+            for f in range(p, frames, pairs):
+                b, t = divmod(f, T0)
+                x = wave[b, t * stride: t * stride + K]
+                xh = (w @ x - mean[f]) * rstd[f]
+                g = dy[f] * dgelu(xh * gamma + beta)
+                acc_aff += g if role else g * xh
+                dxh = g * gamma
+                m1, m2 = dxh.sum() / C, (dxh * xh).sum() / C
+                du = rstd[f] * (dxh - m1 - xh * m2)
+                for k in range(role, K, 2):               # taps 2i + role
+                    acc_w[:, k] += du * x[k]
+            for k in range(role, K, 2):
+                part[p, np.arange(C) * K + k] = acc_w[:, k]
+            off = C * K + (C if role else 0)
+            part[p, off: off + C] = acc_aff
+    tot = part.sum(0)                                    # conv0_reduce_w_kernel over the rows
+    return (y.reshape(B, T0, C), mean, rstd, tot[: C * K].reshape(C, K), tot[C * K: C * K + C], tot[C * K + C:])
+
+
+@pytest.mark.parametrize("C,K,stride", [(32, 10, 5), (70, 7, 3)])
+def test_conv0_layer_norm_kernel_program_matches_autograd(C, K, stride):
+    """The layer-0 kernel pair of the "layer_norm" waveform extractor (speech_encoder_prenet.py:308-318) as a program:
+    channel ownership, per-frame statistics, the role split of the backward and the partial-row layout reproduce
+    torch's conv1d + layer_norm + gelu and its gradients (the device kernels are checked against the same statement in
+    tests/test_frontend_gpu.py)."""
+    rng = np.random.default_rng(C)
+    B, n = 2, 83
+    wave, w = rng.normal(size=(B, n)) * 0.3, rng.normal(size=(C, K)) * 0.4
+    gamma, beta = 1 + 0.2 * rng.normal(size=C), 0.2 * rng.normal(size=C)
+    T0 = (n - K) // stride + 1
+    dy = rng.normal(size=(B * T0, C))
+    y, mean, rstd, dW, dg, db = _conv0_ln_kernel_program(wave, w, gamma, beta, dy, stride, 1e-5)
+    tw, tg, tb = (torch.tensor(a, requires_grad=True) for a in (w, gamma, beta))
+    v = F.conv1d(torch.tensor(wave)[:, None], tw[:, None], stride=stride).transpose(1, 2)
+    want = F.gelu(F.layer_norm(v, (C,), tg, tb, 1e-5))
+    gw, gg, gb = torch.autograd.grad(want, (tw, tg, tb), torch.tensor(dy).view(B, T0, C))
+    np.testing.assert_allclose(y, want.detach().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(mean, v.detach().mean(-1).reshape(-1).numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dW, gw.numpy(), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(dg, gg.numpy(), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(db, gb.numpy(), rtol=1e-8, atol=1e-10)
