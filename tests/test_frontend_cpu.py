@@ -713,3 +713,45 @@ def test_joint_pretraining_update_through_the_trainer_on_emulated_kernels(monkey
         assert key in moved, key
     RT.clear_static()
     RT.invalidate_shadows()
+
+
+@pytest.mark.parametrize("name", ["ref_asr_tiny", "ref_asr_large_style_tiny"])
+def test_generator_scores_equal_the_reference_sequence_generator_on_emulated_kernels(monkeypatch, name):
+    """speecht5_b200/generator.py against the reference's OWN SequenceGenerator (sequence_generator.py:207-655, beam 1)
+    run on the reference model (tests/golden/ref_asr_*.npz, produced by make_golden_from_ref.py): same weights in the
+    product model on emulated kernels -> the same token ids, per-token log-probabilities and length-normalised score,
+    on the prefix-recomputing, cached and graph-body decoding paths."""
+    import os
+    import numpy as np
+    from types import SimpleNamespace
+    from helpers import NO_DROPOUT, TINY, rel
+    from speecht5_b200 import frontend
+    from speecht5_b200.generator import GreedyGenerator
+    from speecht5_b200.models import T5TransformerModel, make_args
+    from speecht5_b200.ops import RT
+    gemm_emulator.install(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.invalidate_shadows()
+    blob = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz")))
+    over = dict(TINY, **NO_DROPOUT, bert_init=True, build_speech_encoder=True, build_text_decoder=True,
+                conv_feature_layers="[(32, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2", feature_grad_mult=1.0,
+                conv_pos=16, conv_pos_groups=4, use_conv_pos=True, use_sinc_pos=True, mask_prob=0.5,
+                hubert_mask_length=4, mask_channel_prob=0.25, mask_channel_length=8, max_text_positions=600)
+    if "large_style" in name:
+        over.update(extractor_mode="layer_norm", layer_norm_first=True, decoder_normalize_before=True,
+                    share_input_output_embed=True)
+    model = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **over)).eval()
+    model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("state/")}, strict=False)
+    V = 81
+    vocab = SimpleNamespace(pad=lambda: 1, eos=lambda: 2, unk=lambda: 3)
+    sample = {"net_input": {"source": torch.from_numpy(blob["in/source"]),
+                            "padding_mask": torch.from_numpy(blob["in/padding_mask"])}}
+    for mode in (False, True, "graph_body_eager"):
+        gen = GreedyGenerator([model], vocab, max_len_b=12, blank=V - 1, mask_idx=V - 2, use_cache=mode)
+        for b, h in enumerate(gen.generate([model], sample)):
+            n = int(blob["out/greedy_lengths"][b])
+            assert h[0]["tokens"].tolist() == blob["out/greedy_tokens"][b, :n].tolist(), (mode, b)
+            assert rel(h[0]["positional_scores"], torch.from_numpy(blob["out/greedy_pos_scores"][b, :n])) < 1e-4, (mode, b)
+            assert abs(float(h[0]["score"]) - float(blob["out/greedy_scores"][b])) < 1e-4, (mode, b)
+    RT.invalidate_shadows()

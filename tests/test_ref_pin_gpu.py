@@ -192,7 +192,8 @@ def test_greedy_token_ids_equal_the_reference_sequence_generator(cuda, use_cache
 
 def test_greedy_generator_scores_agree_between_the_eager_cached_and_graph_paths(cuda):
     """speecht5_b200/generator.py (the object task.build_generator returns for beam 1): SequenceGenerator-shaped
-    hypotheses whose tokens are the fixture's and whose token log-probabilities agree between the three decoding paths."""
+    hypotheses whose tokens, per-token log-probabilities and length-normalised score are the reference generator's own
+    (fixture) and agree between the three decoding paths."""
     from types import SimpleNamespace
     from speecht5_b200.generator import GreedyGenerator
     blob = load("ref_asr_tiny")
@@ -209,6 +210,9 @@ def test_greedy_generator_scores_agree_between_the_eager_cached_and_graph_paths(
             assert h[0]["tokens"].tolist() == blob["out/greedy_tokens"][b, :n].tolist()
             assert h[0]["positional_scores"].shape == (n,) and bool((h[0]["positional_scores"] <= 0).all())
             assert abs(float(h[0]["score"]) - float(h[0]["positional_scores"].mean())) < 1e-5
+            # the reference SequenceGenerator's own numbers for these hypotheses (sequence_generator.py:596-655)
+            assert rel(h[0]["positional_scores"].cpu(), torch.from_numpy(blob["out/greedy_pos_scores"][b, :n])) < 1e-3
+            assert abs(float(h[0]["score"]) - float(blob["out/greedy_scores"][b])) < 2e-3
         scores.append(torch.cat([h[0]["positional_scores"] for h in hypos]))
     assert rel(scores[1], scores[0]) < 1e-4 and rel(scores[2], scores[0]) < 1e-4
 
