@@ -36,3 +36,35 @@ def to_device(obj, dev):
     if isinstance(obj, dict):
         return {k: to_device(v, dev) for k, v in obj.items()}
     return obj
+
+
+def speech_pretrain_fixture_case(dev):
+    """Product model + criterion + the batch of tests/golden/ref_speech_pretrain_tiny.npz (the REFERENCE model's own
+    speech pre-training update, make_golden_from_ref.py:case_speech_pretrain) on `dev`."""
+    import os
+    import numpy as np
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.models import T5TransformerModel, make_args
+    blob = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_speech_pretrain_tiny.npz")))
+    over = dict(TINY, **NO_DROPOUT, bert_init=True, build_speech_encoder=True,
+                conv_feature_layers="[(32, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2", feature_grad_mult=1.0,
+                conv_pos=16, conv_pos_groups=4, use_conv_pos=True, use_sinc_pos=True, mask_prob=0.5,
+                hubert_mask_length=4, mask_channel_prob=0.0, use_codebook=True, latent_vars=10, latent_groups=2,
+                codebook_prob=0.5, final_dim=16, untie_final_proj=True, hubert_num_classes=[23])
+    model = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **over)).to(dev).train()
+    missing = model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("state/")},
+                                    strict=False)
+    assert not missing.unexpected_keys and all(
+        k.startswith(("text_encoder_prenet.", "text_decoder")) or "num_batches_tracked" in k or "version" in k
+        for k in missing.missing_keys), missing
+    t = lambda k: torch.from_numpy(blob[k]).to(dev)  # noqa: E731
+    ni = dict(source=t("in/source"), padding_mask=t("in/padding_mask"), prev_output_tokens=t("in/prev_output_tokens"),
+              spkembs=t("in/spkembs"), tgt_lengths=t("in/tgt_lengths"), mask_indices=t("in/mask_indices"),
+              task_name="speech_pretrain")
+    sample = {"id": torch.arange(3), "task_name": "speech_pretrain", "net_input": ni,
+              "target_list": [t("sample/target_list0")], "labels": t("sample/labels"), "dec_target": t("sample/dec_target"),
+              "dec_target_lengths": t("sample/dec_target_lengths"), "src_lengths": [blob["in/source"].shape[1]] * 3}
+    model._gumbel_noise, model._codebook_perm = t("in/gumbel_noise"), t("in/codebook_perm")
+    crit = SpeechT5Criterion(None, pred_masked_weight=1.0, pred_nomask_weight=0.5, loss_weights=[10.0, 0.1],
+                             hubert_weight=1.0, dec_weight=0.5)
+    return blob, model, crit, sample

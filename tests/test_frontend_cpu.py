@@ -755,3 +755,37 @@ def test_generator_scores_equal_the_reference_sequence_generator_on_emulated_ker
             assert rel(h[0]["positional_scores"], torch.from_numpy(blob["out/greedy_pos_scores"][b, :n])) < 1e-4, (mode, b)
             assert abs(float(h[0]["score"]) - float(blob["out/greedy_scores"][b])) < 1e-4, (mode, b)
     RT.invalidate_shadows()
+
+
+def test_speech_pretraining_update_equals_the_reference_model_on_emulated_kernels(monkeypatch):
+    """SURVEY 8a row 22 pinned END TO END to the reference's own code: the reference T5TransformerModel's speech
+    pre-training forward (prenet + its own mask draw, encoder, masked-prediction head, Gumbel quantizer + code mixing,
+    speech decoder) under the reference SpeechPretrainCriterion gives the fixture's loss, sample size, logging values
+    and gradients; the product model with the same weights, mask, Gumbel noise and permutation (kernels emulated on the
+    CPU, parity arithmetic) reproduces them through the `speecht5` criterion dispatcher."""
+    from helpers import rel, speech_pretrain_fixture_case
+    from speecht5_b200 import frontend
+    from speecht5_b200.ops import RT
+    gemm_emulator.install_trainer(monkeypatch)  # (install_autograd + the post-net BatchNorm as a differentiable torch call)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    monkeypatch.setattr(frontend.ConvFeatureExtractor, "forward", _cpu_extractor_forward)
+    RT.clear_static()
+    RT.invalidate_shadows()
+    blob, model, crit, sample = speech_pretrain_fixture_case(torch.device("cpu"))
+    loss, n, log = crit(model, sample)
+    assert n == int(blob["loss"][1])
+    assert abs(loss.item() - blob["loss"][0]) < 1e-4 * abs(blob["loss"][0]), (loss.item(), blob["loss"])
+    keys = [k[4:] for k in blob if k.startswith("log/")]
+    assert len(keys) >= 15
+    for k in keys:
+        want = float(blob["log/" + k])
+        assert k in log and abs(float(log[k]) - want) <= 2e-4 * max(1.0, abs(want)), (k, log.get(k), want)
+    loss.backward()
+    params = dict(model.named_parameters())
+    grads = [k[5:] for k in blob if k.startswith("grad/")]
+    assert len(grads) >= 12
+    for k in grads:
+        assert params[k].grad is not None, k
+        assert rel(params[k].grad, torch.from_numpy(blob["grad/" + k])) < 2e-4, (k, rel(params[k].grad, torch.from_numpy(blob["grad/" + k])))
+    RT.clear_static()
+    RT.invalidate_shadows()
