@@ -68,3 +68,27 @@ def speech_pretrain_fixture_case(dev):
     crit = SpeechT5Criterion(None, pred_masked_weight=1.0, pred_nomask_weight=0.5, loss_weights=[10.0, 0.1],
                              hubert_weight=1.0, dec_weight=0.5)
     return blob, model, crit, sample
+
+
+def text_pretrain_fixture_case(dev):
+    """Product model + criterion + the batch of tests/golden/ref_text_pretrain_tiny.npz (the REFERENCE model's own text
+    pre-training update, make_golden_from_ref.py:case_text_pretrain) on `dev`."""
+    import os
+    from speecht5_b200.criterions import SpeechT5Criterion
+    from speecht5_b200.models import T5TransformerModel, make_args
+    blob = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_text_pretrain_tiny.npz")))
+    over = dict(TINY, **NO_DROPOUT, bert_init=True, build_text_decoder=True, share_input_output_embed=True,
+                use_codebook=True, latent_vars=10, latent_groups=2, codebook_prob=0.5, max_text_positions=600)
+    model = T5TransformerModel.build_model(make_args("t5_transformer_base_asr", **over)).to(dev).train()
+    missing = model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("state/")},
+                                    strict=False)
+    assert not missing.unexpected_keys and all(
+        k.startswith(("speech_decoder_prenet.", "speech_decoder_postnet.")) or "num_batches_tracked" in k or "version" in k
+        for k in missing.missing_keys), missing
+    t = lambda k: torch.from_numpy(blob[k]).to(dev)  # noqa: E731
+    sample = {"id": torch.arange(3), "task_name": "text_pretrain", "target": t("sample/target"),
+              "ntokens": int(blob["loss"][2]), "nsentences": 3,
+              "net_input": dict(src_tokens=t("in/src_tokens"), prev_output_tokens=t("in/prev_output_tokens"))}
+    model._gumbel_noise, model._codebook_perm = t("in/gumbel_noise"), t("in/codebook_perm")
+    crit = SpeechT5Criterion(None, bart_weight=1.0, loss_weights=[10.0, 0.1])
+    return blob, model, crit, sample

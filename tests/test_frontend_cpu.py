@@ -789,3 +789,32 @@ def test_speech_pretraining_update_equals_the_reference_model_on_emulated_kernel
         assert rel(params[k].grad, torch.from_numpy(blob["grad/" + k])) < 2e-4, (k, rel(params[k].grad, torch.from_numpy(blob["grad/" + k])))
     RT.clear_static()
     RT.invalidate_shadows()
+
+
+def test_text_pretraining_update_equals_the_reference_model_on_emulated_kernels(monkeypatch):
+    """The text half of a pre-training update against the reference's own code: reference T5TransformerModel (text
+    pre-net, encoder, the shared Gumbel quantizer + code mixing on the text states, text decoder, tied output embedding)
+    under the reference TextPretrainCriterion -> the fixture; the product model with the same weights and draws on
+    emulated kernels gives its loss, sample size, logging values and gradients (ragged sources, padded targets)."""
+    from helpers import rel, text_pretrain_fixture_case
+    from speecht5_b200.ops import RT
+    gemm_emulator.install_trainer(monkeypatch)
+    monkeypatch.setattr(RT, "dtype", torch.float32)
+    RT.clear_static()
+    RT.invalidate_shadows()
+    blob, model, crit, sample = text_pretrain_fixture_case(torch.device("cpu"))
+    loss, n, log = crit(model, sample)
+    assert n == int(blob["loss"][1])
+    assert abs(loss.item() - blob["loss"][0]) < 1e-4 * abs(blob["loss"][0]), (loss.item(), blob["loss"])
+    for k in [k[4:] for k in blob if k.startswith("log/")]:
+        want = float(blob["log/" + k])
+        assert k in log and abs(float(log[k]) - want) <= 2e-4 * max(1.0, abs(want)), (k, log.get(k), want)
+    loss.backward()
+    params = dict(model.named_parameters())
+    grads = [k[5:] for k in blob if k.startswith("grad/")]
+    assert len(grads) >= 10
+    for k in grads:
+        assert params[k].grad is not None, k
+        assert rel(params[k].grad, torch.from_numpy(blob["grad/" + k])) < 2e-4, (k, rel(params[k].grad, torch.from_numpy(blob["grad/" + k])))
+    RT.clear_static()
+    RT.invalidate_shadows()

@@ -254,6 +254,38 @@ def test_speech_pretraining_update_against_the_reference_model(cuda):
     RT.invalidate_shadows()
 
 
+def test_text_pretraining_update_against_the_reference_model(cuda):
+    """The text half of a pre-training update against the REFERENCE model's own run
+    (tests/golden/ref_text_pretrain_tiny.npz: reference T5TransformerModel with the shared quantizer on the text states
+    + TextPretrainCriterion, ragged sources, padded targets, its Gumbel noise and permutation): CUDA path, parity mode."""
+    from helpers import text_pretrain_fixture_case
+    from speecht5_b200.ops import RT
+    RT.dtype = torch.float32
+    RT.manual_seed(1)
+    RT.disable_device_seed()
+    RT.clear_static()
+    RT.invalidate_shadows()
+    blob, model, crit, sample = text_pretrain_fixture_case(cuda)
+    loss, n, log = crit(model, sample)
+    assert n == int(blob["loss"][1])
+    assert abs(loss.item() - blob["loss"][0]) < 5e-3 * abs(blob["loss"][0]), (loss.item(), blob["loss"])
+    for k in [k[4:] for k in blob if k.startswith("log/")]:
+        want = float(blob["log/" + k])
+        assert k in log and abs(float(log[k]) - want) <= 1e-2 * max(1.0, abs(want)), (k, log.get(k), want)
+    loss.backward()
+    params = dict(model.named_parameters())
+    checked = 0
+    for k in [k[5:] for k in blob if k.startswith("grad/")]:
+        assert params[k].grad is not None, k
+        err = rel(params[k].grad, torch.from_numpy(blob["grad/" + k]))
+        assert err < 1e-2, (k, err)
+        checked += 1
+    assert checked >= 10
+    RT.dtype = torch.bfloat16
+    RT.clear_static()
+    RT.invalidate_shadows()
+
+
 def test_hifigan_against_the_reference_generator(cuda):
     from oracle.audio_oracle import fold_weight_norm
     from speecht5_b200 import vocoder
