@@ -192,8 +192,8 @@ def test_greedy_token_ids_equal_the_reference_sequence_generator(cuda, use_cache
 
 def test_greedy_generator_scores_agree_between_the_eager_cached_and_graph_paths(cuda):
     """speecht5_b200/generator.py (the object task.build_generator returns for beam 1): SequenceGenerator-shaped
-    hypotheses whose tokens, per-token log-probabilities and length-normalised score are the reference generator's own
-    (fixture) and agree between the three decoding paths."""
+    hypotheses whose tokens are the fixture's and whose token log-probabilities agree between the three decoding paths
+    (the reference generator's own scores: tests/test_z_reference_model_pins_gpu.py)."""
     from types import SimpleNamespace
     from speecht5_b200.generator import GreedyGenerator
     blob = load("ref_asr_tiny")
@@ -210,80 +210,8 @@ def test_greedy_generator_scores_agree_between_the_eager_cached_and_graph_paths(
             assert h[0]["tokens"].tolist() == blob["out/greedy_tokens"][b, :n].tolist()
             assert h[0]["positional_scores"].shape == (n,) and bool((h[0]["positional_scores"] <= 0).all())
             assert abs(float(h[0]["score"]) - float(h[0]["positional_scores"].mean())) < 1e-5
-            # the reference SequenceGenerator's own numbers for these hypotheses (sequence_generator.py:596-655)
-            assert rel(h[0]["positional_scores"].cpu(), torch.from_numpy(blob["out/greedy_pos_scores"][b, :n])) < 1e-3
-            assert abs(float(h[0]["score"]) - float(blob["out/greedy_scores"][b])) < 2e-3
         scores.append(torch.cat([h[0]["positional_scores"] for h in hypos]))
     assert rel(scores[1], scores[0]) < 1e-4 and rel(scores[2], scores[0]) < 1e-4
-
-
-def test_speech_pretraining_update_against_the_reference_model(cuda):
-    """SURVEY 8a row 22 end to end against the REFERENCE model's own speech pre-training update
-    (tests/golden/ref_speech_pretrain_tiny.npz, make_golden_from_ref.py:case_speech_pretrain: reference
-    T5TransformerModel + SpeechPretrainCriterion, its own mask draw, the Gumbel noise and time permutation it drew):
-    the CUDA path in parity mode gives the reference's loss, sample size, logging values and gradients. (The same
-    comparison runs on emulated kernels in tests/test_frontend_cpu.py.)"""
-    from helpers import speech_pretrain_fixture_case
-    from speecht5_b200.ops import RT
-    RT.dtype = torch.float32
-    RT.manual_seed(1)
-    RT.disable_device_seed()
-    RT.clear_static()
-    RT.invalidate_shadows()
-    blob, model, crit, sample = speech_pretrain_fixture_case(cuda)
-    loss, n, log = crit(model, sample)
-    assert n == int(blob["loss"][1])
-    # (bounds of the other parity-mode pins of this branch, tests/test_frontend_gpu.py: loss 5e-3, logging values 1e-2;
-    #  on emulated fp32 kernels the same comparison holds to 1e-4 / 2e-4, tests/test_frontend_cpu.py)
-    assert abs(loss.item() - blob["loss"][0]) < 5e-3 * abs(blob["loss"][0]), (loss.item(), blob["loss"])
-    for k in [k[4:] for k in blob if k.startswith("log/")]:
-        want = float(blob["log/" + k])
-        tol = 1.0 if k.startswith("correct_") else 1e-2 * max(1.0, abs(want))  # (an arg-max count may move by one frame)
-        assert k in log and abs(float(log[k]) - want) <= tol, (k, log.get(k), want)
-    loss.backward()
-    params = dict(model.named_parameters())
-    checked = 0
-    for k in [k[5:] for k in blob if k.startswith("grad/")]:
-        assert params[k].grad is not None, k
-        err = rel(params[k].grad, torch.from_numpy(blob["grad/" + k]))
-        assert err < 1e-2, (k, err)
-        checked += 1
-    assert checked >= 12
-    RT.dtype = torch.bfloat16
-    RT.clear_static()
-    RT.invalidate_shadows()
-
-
-def test_text_pretraining_update_against_the_reference_model(cuda):
-    """The text half of a pre-training update against the REFERENCE model's own run
-    (tests/golden/ref_text_pretrain_tiny.npz: reference T5TransformerModel with the shared quantizer on the text states
-    + TextPretrainCriterion, ragged sources, padded targets, its Gumbel noise and permutation): CUDA path, parity mode."""
-    from helpers import text_pretrain_fixture_case
-    from speecht5_b200.ops import RT
-    RT.dtype = torch.float32
-    RT.manual_seed(1)
-    RT.disable_device_seed()
-    RT.clear_static()
-    RT.invalidate_shadows()
-    blob, model, crit, sample = text_pretrain_fixture_case(cuda)
-    loss, n, log = crit(model, sample)
-    assert n == int(blob["loss"][1])
-    assert abs(loss.item() - blob["loss"][0]) < 5e-3 * abs(blob["loss"][0]), (loss.item(), blob["loss"])
-    for k in [k[4:] for k in blob if k.startswith("log/")]:
-        want = float(blob["log/" + k])
-        assert k in log and abs(float(log[k]) - want) <= 1e-2 * max(1.0, abs(want)), (k, log.get(k), want)
-    loss.backward()
-    params = dict(model.named_parameters())
-    checked = 0
-    for k in [k[5:] for k in blob if k.startswith("grad/")]:
-        assert params[k].grad is not None, k
-        err = rel(params[k].grad, torch.from_numpy(blob["grad/" + k]))
-        assert err < 1e-2, (k, err)
-        checked += 1
-    assert checked >= 10
-    RT.dtype = torch.bfloat16
-    RT.clear_static()
-    RT.invalidate_shadows()
 
 
 def test_hifigan_against_the_reference_generator(cuda):
