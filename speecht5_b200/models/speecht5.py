@@ -560,6 +560,21 @@ def base_architecture(args):  # models/speecht5.py:1252-1383 (fields used by the
     g("layer_norm_first", False)
     g("use_sent_enc_layer", True)
     g("use_codebook", False)
+    # pre-training options (:1338-1339, :1370-1376 of the reference's base_architecture): the Base checkpoints carry
+    # 256-d label embeddings and a 100 x 2 codebook
+    g("final_dim", 256)
+    g("untie_final_proj", True)
+    g("logit_temp", 0.1)
+    g("target_glu", False)
+    g("skip_masked", False)
+    g("skip_nomask", False)
+    g("label_rates", 50)
+    g("sample_rate", 16000)
+    g("latent_vars", 100)
+    g("latent_groups", 2)
+    g("latent_dim", 0)
+    g("latent_temp", (2, 0.5, 0.999995))
+    g("codebook_prob", 0.5)
     g("relative_position_embedding", False)
     g("encoder_max_relative_position", 160)
     g("decoder_max_relative_position", 160)

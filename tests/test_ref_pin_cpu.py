@@ -499,3 +499,23 @@ def test_vocabulary_files_load_like_the_reference_dictionary(tmp_path):
     model = task.build_model(args)
     assert model.text_encoder_prenet.encoder_prenet[0].weight.shape[0] == n + 2
     assert model.hubert_layer is not None
+
+
+@needs_ref
+@pytest.mark.parametrize("arch", ["t5_transformer", "t5_transformer_base", "t5_transformer_large", "t5_transformer_base_asr"])
+def test_arch_presets_equal_the_reference_arch_functions(arch):
+    """models/speecht5.py:1252-1447: every option both sides know gets the value the reference's OWN arch function
+    assigns (run unmodified through oracle/ref_loader.py) -- layer counts, widths, dropouts, extractor mode, final_dim,
+    codebook sizes, positional options: what decides whether a reference checkpoint loads and trains the same."""
+    from speecht5_b200.models import make_args
+    ref = vars(rl.reference_args(arch=arch))
+    ours = vars(make_args(arch))
+    shared = [k for k in ours if k in ref]
+    assert len(shared) >= 80
+    for k in ("final_dim", "latent_vars", "latent_groups", "latent_temp", "codebook_prob", "logit_temp", "extractor_mode",
+              "use_conv_pos", "use_sinc_pos", "untie_final_proj", "label_rates"):
+        assert k in shared, k
+    def same(a, b):
+        return tuple(a) == tuple(b) if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)) else a == b
+    diff = {k: (ours[k], ref[k]) for k in shared if not same(ours[k], ref[k])}
+    assert not diff, diff
