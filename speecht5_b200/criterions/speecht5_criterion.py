@@ -41,9 +41,10 @@ class SpeechT5CriterionConfig:
     # pre-training criteria (speech_pretrain_criterion.py, text_pretrain_criterion.py)
     pred_masked_weight: float = field(default=1.0)
     pred_nomask_weight: float = field(default=0.0)
-    loss_weights: list = field(default_factory=lambda: [10.0])
+    # (the reference dataclass inherits the text criterion's default for the shared list, the recipes pass [10, 0.1])
+    loss_weights: list = field(default_factory=lambda: [0.1])
     log_keys: list = field(default_factory=list)
-    dec_weight: float = field(default=0.5)
+    dec_weight: float = field(default=1.0)
     bart_weight: float = field(default=1.0)
     hubert_weight: float = field(default=1.0)
 

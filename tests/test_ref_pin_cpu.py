@@ -519,3 +519,30 @@ def test_arch_presets_equal_the_reference_arch_functions(arch):
         return tuple(a) == tuple(b) if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)) else a == b
     diff = {k: (ours[k], ref[k]) for k in shared if not same(ours[k], ref[k])}
     assert not diff, diff
+
+
+@needs_ref
+def test_criterion_config_defaults_equal_the_reference_dataclass():
+    """speecht5_criterion.py:23-30: fairseq builds the criterion from this dataclass, so its defaults decide what a
+    recipe that omits a flag trains with. Every field both sides define has the reference's default (sentence_avg is an
+    interpolation of optimization.sentence_avg there)."""
+    import dataclasses
+    import importlib
+    from speecht5_b200.criterions.speecht5_criterion import SpeechT5CriterionConfig
+    rl.load()
+    ref_cls = importlib.import_module("speecht5.criterions.speecht5_criterion").SpeechT5CriterionConfig
+
+    def defaults(cls):
+        out = {}
+        for f in dataclasses.fields(cls):
+            if f.default is not dataclasses.MISSING:
+                out[f.name] = f.default
+            elif f.default_factory is not dataclasses.MISSING:
+                out[f.name] = f.default_factory()
+        return out
+    ref, ours = defaults(ref_cls), defaults(SpeechT5CriterionConfig)
+    shared = [k for k in ours if k in ref and k != "sentence_avg"]
+    assert len(shared) >= 20
+    diff = {k: (ours[k], ref[k]) for k in shared
+            if (list(ours[k]) != list(ref[k]) if isinstance(ours[k], (list, tuple)) else ours[k] != ref[k])}
+    assert not diff, diff
