@@ -157,6 +157,51 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         ("--extractor-mode", dict(choices=["default", "layer_norm"])),
         ("--bert-init", dict(action="store_true")),
         ("--unb-enc-layer", dict(type=int, default=-1)),
+        # waveform front end, HuBERT masking and head, freezing (add_args :217-232, :418-520): read by the speech-input branch
+        ("--freeze-encoder-updates", dict(type=int)),
+        ("--freeze-decoder-updates", dict(type=int)),
+        ("--no-freeze-encoder-layer", dict(type=str)),
+        ("--feature-grad-mult", dict(type=float)),
+        ("--logit-temp", dict(type=float)),
+        ("--final-dim", dict(type=int)),
+        ("--hubert-mask-length", dict(type=int)),
+        ("--mask-prob", dict(type=float)),
+        ("--mask-other", dict(type=float)),
+        ("--mask-min-space", dict(type=int)),
+        ("--mask-channel-length", dict(type=int)),
+        ("--mask-channel-prob", dict(type=float)),
+        ("--mask-channel-other", dict(type=float)),
+        ("--mask-channel-min-space", dict(type=int)),
+        ("--conv-pos", dict(type=int)),
+        ("--conv-pos-groups", dict(type=int)),
+        ("--get-code-distribution", dict(action="store_true")),
+        # options of branches this implementation does not build (speaker identification, enhancement, the
+        # convolutional subsampler, sliding-window / branched encoders): accepted so that every recipe's command line
+        # parses; they only matter once such a branch is called, and those raise NotImplementedError
+        ("--encoder-sliding-window-attn", dict(type=int, default=None)),
+        ("--conv-kernel-sizes", dict(type=str, default="5,5")),
+        ("--conv-channels", dict(type=int, default=1024)),
+        ("--subsample-stride", dict(type=str, default="2,2")),
+        ("--se-predict", dict(default=None, choices=["masking", "target", "delta"])),
+        ("--se-decoder-input", dict(type=str, default="previous_target", choices=["previous_target", "source"])),
+        ("--encoder-attn-branch", dict(type=str, default="identity,full")),
+        ("--encoder-block-branch", dict(type=str, default=None)),
+        ("--sid-pad-prenet", dict(action="store_true")),
+        ("--sid-encoder-cls", dict(default=None, choices=["encoder"])),
+        ("--sid-shuffle-encoder-input", dict(action="store_true")),
+        ("--sid-decoder-speaker", dict(action="store_true")),
+        ("--sid-decoder-attn-dim", dict(type=int, default=128)),
+        ("--sid-t5-postnet", dict(action="store_true")),
+        ("--sid-embed-dim", dict(type=int, default=128)),
+        ("--sid-pooling-layer", dict(type=str, default="decoder",
+                                     choices=["decoder-las", "decoder", "encoder", "encoder-cls", "encoder-speaker"])),
+        ("--sid-no-pooling-bn", dict(action="store_true")),
+        ("--sid-no-embed-postnet", dict(action="store_true")),
+        ("--sid-normalize-postnet", dict(action="store_true")),
+        ("--sid-softmax-type", dict(default="softmax", choices=["softmax", "amsoftmax", "aamsoftmax"])),
+        ("--softmax-scale", dict(type=float, default=1.0)),
+        ("--softmax-margin", dict(type=float, default=0.0)),
+        ("--softmax-easy-margin", dict(action="store_true")),
         # this implementation only: construct the text decoder pre/post-net (the reference always does)
         ("--build-text-decoder", dict(action="store_true")),
         ("--build-speech-encoder", dict(action="store_true")),

@@ -546,3 +546,32 @@ def test_criterion_config_defaults_equal_the_reference_dataclass():
     diff = {k: (ours[k], ref[k]) for k in shared
             if (list(ours[k]) != list(ref[k]) if isinstance(ours[k], (list, tuple)) else ours[k] != ref[k])}
     assert not diff, diff
+
+
+@needs_ref
+def test_model_command_line_options_cover_the_reference_add_args():
+    """models/speecht5.py:117-560 (T5TransformerModel.add_args of the reference, run unmodified): every option it
+    defines is defined here with the same value type and choices, so a recipe's command line -- README fine-tuning
+    commands pass --freeze-encoder-updates, --mask-prob, --mask-channel-prob, --feature-grad-mult -- parses under this
+    plugin; ours adds only the two opt-in builders."""
+    import argparse
+    from speecht5_b200.models import T5TransformerModel
+    ns = rl.load()
+
+    def opts(cls):
+        p = argparse.ArgumentParser(allow_abbrev=False)
+        cls.add_args(p)
+        return p, {a.dest: (tuple(a.option_strings), type(a).__name__, getattr(a.type, "__name__", a.type),
+                            tuple(a.choices) if a.choices else None) for a in p._actions if a.dest != "help"}
+    _, ref = opts(ns.T5TransformerModel)
+    parser, ours = opts(T5TransformerModel)
+    assert sorted(k for k in ref if k not in ours) == []
+    assert sorted(k for k in ours if k not in ref) == ["build_speech_encoder", "build_text_decoder"]
+    loose = {"latent_temp", "mask_selection", "mask_channel_selection"}  # (str vs literal_eval / untyped: same strings accepted)
+    diff = {k: (ours[k], ref[k]) for k in ref if k not in loose and ours[k] != ref[k]}
+    assert not diff, diff
+    got = parser.parse_args("--share-input-output-embed --bert-init --relative-position-embedding --freeze-encoder-updates "
+                            "13000 --mask-prob 0.5 --mask-channel-prob 0.5 --feature-grad-mult 1.0 --dropout 0.1 "
+                            "--use-codebook --codebook-prob 0.1 --sid-no-pooling-bn --sid-no-embed-postnet".split())
+    assert got.freeze_encoder_updates == 13000 and got.mask_prob == 0.5 and got.feature_grad_mult == 1.0
+    assert not hasattr(got, "encoder_layers")  # unset options fall through to the arch function
