@@ -575,3 +575,35 @@ def test_model_command_line_options_cover_the_reference_add_args():
                             "--use-codebook --codebook-prob 0.1 --sid-no-pooling-bn --sid-no-embed-postnet".split())
     assert got.freeze_encoder_updates == 13000 and got.mask_prob == 0.5 and got.feature_grad_mult == 1.0
     assert not hasattr(got, "encoder_layers")  # unset options fall through to the arch function
+
+
+@needs_ref
+def test_task_command_line_options_equal_the_reference_add_args():
+    """tasks/speecht5.py:44-213 (SpeechT5Task.add_args; the module itself needs fairseq's data package, so its
+    add_argument calls are read from the source text): same flags, value types, defaults, choices and actions here."""
+    import ast
+    from speecht5_b200.tasks.speecht5 import SpeechT5Task
+    src = open("/root/reference/SpeechT5/speecht5/tasks/speecht5.py").read()
+    ref = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "add_argument":
+            flags = [a.value for a in node.args if isinstance(a, ast.Constant)]
+            kw = {}
+            for k in node.keywords:
+                if k.arg in ("help", "metavar"):
+                    continue
+                try:
+                    kw[k.arg] = ast.literal_eval(k.value)
+                except ValueError:
+                    kw[k.arg] = getattr(k.value, "id", None) or ast.unparse(k.value)
+            ref[flags[-1]] = kw
+    ours = {}
+    for flag, kw in SpeechT5Task._OPTIONS:
+        kw = {k: (getattr(v, "__name__", v) if k == "type" else v) for k, v in kw.items() if k not in ("help", "metavar")}
+        ours[flag] = kw
+    assert sorted(k for k in ref if k not in ours) == ["data"]  # (the positional argument, added in add_args itself)
+    assert sorted(k for k in ours if k not in ref) == []
+    ref["--t5-task"]["choices"] = SpeechT5Task.TASK_NAME  # (the reference names its list the same way, :42)
+    diff = {k: (ours[k], ref[k]) for k in ours if ours[k] != ref[k]}
+    assert not diff, diff
+    assert len(ours) >= 35
