@@ -603,7 +603,7 @@ def test_task_command_line_options_equal_the_reference_add_args():
         ours[flag] = kw
     assert sorted(k for k in ref if k not in ours) == ["data"]  # (the positional argument, added in add_args itself)
     assert sorted(k for k in ours if k not in ref) == []
-    ref["--t5-task"]["choices"] = SpeechT5Task.TASK_NAME  # (the reference names its list the same way, :42)
+    ref["--t5-task"]["choices"] = SpeechT5Task.TASK_NAME  # (the reference names its list the same way, :40)
     diff = {k: (ours[k], ref[k]) for k in ours if ours[k] != ref[k]}
     assert not diff, diff
     assert len(ours) >= 35
