@@ -17,7 +17,7 @@ from .text_to_speech_loss import TexttoSpeechLoss
 class SpeechT5CriterionConfig:
     """Union of the reference's criterion configs (speecht5_criterion.py:23-30 inherits the text-to-speech,
     speech-to-text, label-smoothed CE and pre-training configs), so every recipe's `--criterion speecht5 ...` flags
-    parse. Fields of branches that are not built yet are accepted and only matter once that branch is called."""
+    parse. Fields of branches that are not built (speaker identification) are accepted and only matter once that branch is called."""
     sentence_avg: bool = field(default=True)
     # text_to_speech_loss.py:21-69
     use_masking: bool = field(default=True)

@@ -109,7 +109,8 @@ class TextDecoderPrenet(nn.Module):
 
     def forward(self, prev_output_tokens, incremental_state=None):
         if incremental_state is not None:
-            raise NotImplementedError("incremental decoding is a 'next' row (SURVEY.md section 8f)")
+            raise NotImplementedError("fairseq's incremental_state protocol is not used here: the key/value cache and "
+                                      "the per-step CUDA graphs live in speecht5_b200/incremental.py")
         ft = self.freeze_decoder_updates <= self.num_updates
         with torch.no_grad() if not ft else contextlib.ExitStack():
             pe = self._table(prev_output_tokens.shape[1], prev_output_tokens.device)

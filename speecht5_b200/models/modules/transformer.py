@@ -389,7 +389,8 @@ class TransformerDecoder(nn.Module):
                 full_context_alignment=False, alignment_layer=None, alignment_heads=None, src_lengths=None,
                 return_all_hiddens=False):
         if incremental_state is not None:
-            raise NotImplementedError("incremental decoding is a 'next' row (SURVEY.md section 8f)")
+            raise NotImplementedError("fairseq's incremental_state protocol is not used here: the key/value cache and "
+                                      "the per-step CUDA graphs live in speecht5_b200/incremental.py")
         return self.extract_features(prev_output_tokens, tgt_mask, encoder_out, full_context_alignment,
                                      alignment_layer, alignment_heads)
 

@@ -405,13 +405,21 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
             encoder_input, encoder_padding_mask = self.speech_encoder_prenet(source, padding_mask=padding_mask,
                                                                              mask=False)
             return self.encoder(encoder_input, encoder_padding_mask)
-        raise NotImplementedError("speech input (conv feature extractor + speech encoder prenet) is a 'next' row: "
-                                  "SURVEY.md section 8a rows 2-3; use forward_text_encoder for text input")
+        raise NotImplementedError("forward_encoder takes a waveform: build the model with --build-speech-encoder "
+                                  "(use forward_text_encoder for text input)")
+
+    def forward_encoder_torchscript(self, net_input):
+        """(:1112-1124) what fairseq's generator calls; TorchScript export is not a target of this implementation."""
+        return self.forward_encoder_non_torchscript(net_input)
+
+    def forward_encoder_non_torchscript(self, net_input):  # (:1126-1131)
+        return self.forward_encoder(**{k: v for k, v in net_input.items() if k not in ("prev_output_tokens", "task_name")})
 
     def forward_decoder(self, tokens, encoder_out, incremental_state):
         """(:1151-1164) vocabulary logits of the text decoder. With an incremental state the reference feeds only the
-        last token and returns [B, 1, V]; here the decoder is re-run on the whole prefix (causal self-attention makes
-        the last row identical) and the last position is returned -- the KV cache is the SURVEY 8f follow-up."""
+        last token and returns [B, 1, V]; this entry point re-runs the decoder on the whole prefix (causal
+        self-attention makes the last row identical) and returns the last position. The cached forms -- key/value cache
+        and one captured CUDA graph per step -- live in speecht5_b200/incremental.py (generate_text_greedy use_cache)."""
         if getattr(self, "text_decoder_prenet", None) is None:
             raise NotImplementedError("text decoding needs the opt-in text decoder (--build-text-decoder): "
                                       "SURVEY.md section 8a rows 9, 14, 21")
@@ -497,13 +505,14 @@ class T5TransformerModel(FairseqEncoderDecoderModel):
         kwargs["threshold"] for the threshold, minlenratio AND maxlenratio (:1190-1199); defaults 0.5 / 0.0 / 20.0.
         Returns (mel [L, odim] fp32, stop probabilities [L], cross-attention [layers, H, L/r, T_text]).
 
-        The decoder is re-run on the whole prefix every step (causal self-attention makes that equal to the
-        reference's incremental state, and every step reuses the training kernels); a KV cache is the SURVEY 8f
-        follow-up. The always-on prenet dropout therefore draws one mask per step for the whole prefix, where the
-        reference keeps the cached keys/values of earlier draws -- identical in distribution for the newest frame."""
+        use_cache=False re-runs the decoder on the whole prefix every step (causal self-attention makes that equal to
+        the reference's incremental state, and every step reuses the training kernels; the always-on prenet dropout then
+        draws one mask per step for the whole prefix, where the reference keeps the cached keys/values of earlier draws
+        -- identical in distribution for the newest frame); use_cache=True keeps a key/value cache, "graph" replays one
+        captured CUDA graph per decoder step (speecht5_b200/incremental.py)."""
         assert source is not None or src_tokens is not None
         if source is not None:
-            raise NotImplementedError("generate_speech from speech input (voice conversion) is not built yet")
+            raise NotImplementedError("generate_speech from speech input (voice conversion, out of scope: SURVEY.md section 2)")
         assert src_tokens.size(0) == 1
         threshold = kwargs.get("threshold", 0.5)
         minlenratio = kwargs.get("threshold", 0.0)
